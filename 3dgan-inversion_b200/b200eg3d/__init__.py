@@ -1,0 +1,14 @@
+"""b200eg3d -- Blackwell-native EG3D tri-plane generator forward+backward (the 3DGAN-Inversion hot path).
+
+Public surface (mirrors the reference's generator API, see generator.py):
+    TriPlaneGenerator, ImportanceRenderer, RaySampler, OSGDecoder, SuperresolutionHybrid8X
+    ops.bias_act / ops.upfirdn2d / ops.upsample2d / ops.setup_filter      (torch_utils.ops equivalents)
+    seam.convert_generator / seam.load_old_G                               (drop-in replacement of utils/models_utils.py:21-25)
+"""
+from . import ops  # noqa: F401
+from .generator import (FullyConnectedLayer, Generator, ImportanceRenderer, MappingNetwork, OSGDecoder, RaySampler,  # noqa: F401
+                        SuperresolutionHybrid8X, SynthesisBlock, SynthesisLayer, SynthesisNetwork, ToRGBLayer,
+                        TriPlaneGenerator)
+from . import seam  # noqa: F401
+
+__version__ = '0.1.0'

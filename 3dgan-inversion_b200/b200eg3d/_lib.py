@@ -1,0 +1,90 @@
+"""ctypes binding of libb200eg3d.so -- the C-ABI boundary of the CUDA hot path (include/b200eg3d.h).
+
+There is deliberately no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libb200eg3d.so')
+
+_P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
+
+# name -> argument ctypes (every function returns int status; 0 = ok)
+SIGNATURES = {
+    'b200_conv_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_dgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_wgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_modconv_weight_prep': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'b200_modconv_weight_prep_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'b200_bias_act': [_P, _P, _P, _P, _P, _P, _I, _L, _L, _I, _I, _F, _F, _F, _P],
+    'b200_layer_act_fwd': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200_layer_act_bwd': [_P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200_upfirdn2d': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P],
+    'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],
+    'b200_depth_minmax': [_P, _L, _P, _P],
+    'b200_ray_importance': [_P, _P, _P, _P, _L, _I, _I, _P],
+    'b200_ray_composite_fwd': [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _L, _P, _P, _P, _P],
+    'b200_ray_composite_bwd': [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P],
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f'{LIB_PATH} is missing: run `python __graft_entry__.py build` (no CPU/PyTorch fallback exists)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    lib.b200_last_error.restype = ctypes.c_char_p
+    lib.b200_last_error.argtypes = []
+    lib.b200_version.restype = ctypes.c_int
+    lib.b200_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be a contiguous fp32/int32 CUDA tensor."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('b200eg3d: tensor is not on a CUDA device (there is no CPU path)')
+    if not t.is_contiguous():
+        raise RuntimeError('b200eg3d: tensor must be contiguous')
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+LAUNCHES = 0        # number of C-ABI kernel calls made (bench.py reads it for `gpu_launches`)
+PROFILE = None      # when a dict: name -> [(start_event, end_event), ...] recorded around every call (bench.py roofline leg)
+
+
+def call(name, *args):
+    global LAUNCHES
+    lib = load()
+    LAUNCHES += 1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f'{name} failed: {lib.b200_last_error().decode()}')

@@ -1,0 +1,91 @@
+// C-ABI entry points of the convolution family (fp32 universal path).
+// Activations are NHWC fp32 per sample; modulated weights are wmod[n][tap][cout][cin] (tap = kh*k + kw).
+//
+// Replaces, for the synthesis path, the reference's F.conv2d / F.conv_transpose2d calls made through
+// torch_utils/ops/conv2d_gradfix.py:37-45 and torch_utils/ops/conv2d_resample.py:113-136.
+#include "common.cuh"
+#include "conv_geom.h"
+
+thread_local char g_b200_err[512] = "";
+
+static void plain_out(ConvGeom& g, int wo) { g.Wo = wo; g.osy = g.osx = 1; g.ooy = g.oox = 0; }
+
+B200_API int b200_conv_fwd(const float* x, const float* wmod, float* y, int n, int h, int w, int cin, int cout,
+                           int ksize, int up, void* stream) {
+    B200_REQUIRE(ksize == 1 || ksize == 3, "conv_fwd: ksize must be 1 or 3");
+    B200_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv_fwd: up must be 1, or 2 with ksize 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int taps = ksize * ksize;
+    ConvPixParams p{};
+    p.A = x; p.a_bs = (long)h * w * cin;
+    p.B = wmod; p.b_ts = (long)cout * cin; p.b_ks = 1; p.b_ns = cin; p.b_bs = (long)taps * cout * cin; p.b_mode = 1;
+    p.N = cout; p.C = y; p.ldc = cout; p.accumulate = 0;
+    p.g.Hs = h; p.g.Ws = w; p.g.Ca = cin; p.g.sy = p.g.sx = 1;
+    if (up == 1) {
+        p.c_bs = (long)h * w * cout;
+        p.g.Hi = h; p.g.Wi = w; p.g.ntaps = taps; plain_out(p.g, w);
+        for (int t = 0; t < taps; ++t) { p.g.dy[t] = t / ksize - ksize / 2; p.g.dx[t] = t % ksize - ksize / 2; p.g.wt[t] = t; }
+        return launch_conv_pix_simt(p, n, st);
+    }
+    // up == 2: stride-2 transposed convolution written straight onto the (2h+1)x(2w+1) grid, one launch per
+    // output-parity class (each class has 4, 2, 2 or 1 contributing taps; no zero MACs, no atomics).
+    p.c_bs = (long)(2 * h + 1) * (2 * w + 1) * cout;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            p.g.Hi = h + 1 - py; p.g.Wi = w + 1 - px;
+            p.g.Wo = 2 * w + 1; p.g.osy = p.g.osx = 2; p.g.ooy = py; p.g.oox = px;
+            int t = 0;
+            for (int kh = py; kh < 3; kh += 2)
+                for (int kw = px; kw < 3; kw += 2) { p.g.dy[t] = -(kh >> 1); p.g.dx[t] = -(kw >> 1); p.g.wt[t] = kh * 3 + kw; ++t; }
+            p.g.ntaps = t;
+            if (int e = launch_conv_pix_simt(p, n, st)) return e;
+        }
+    return 0;
+}
+
+B200_API int b200_conv_dgrad(const float* dy, const float* wmod, float* dx, int n, int h, int w, int cin, int cout,
+                             int ksize, int up, void* stream) {
+    B200_REQUIRE(ksize == 1 || ksize == 3, "conv_dgrad: ksize must be 1 or 3");
+    B200_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv_dgrad: up must be 1, or 2 with ksize 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int taps = ksize * ksize;
+    ConvPixParams p{};
+    const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
+    p.A = dy; p.a_bs = (long)hs * ws * cout;
+    p.B = wmod; p.b_ts = (long)cout * cin; p.b_ks = cin; p.b_ns = 1; p.b_bs = (long)taps * cout * cin;
+    p.b_mode = (cin % 4 == 0) ? 2 : 0;
+    p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin; p.accumulate = 0;
+    p.g.Hi = h; p.g.Wi = w; p.g.Hs = hs; p.g.Ws = ws; p.g.Ca = cout; p.g.sy = p.g.sx = up; p.g.ntaps = taps;
+    plain_out(p.g, w);
+    for (int t = 0; t < taps; ++t) {
+        const int kh = t / ksize, kw = t % ksize;
+        p.g.dy[t] = up == 1 ? ksize / 2 - kh : kh;
+        p.g.dx[t] = up == 1 ? ksize / 2 - kw : kw;
+        p.g.wt[t] = t;
+    }
+    return launch_conv_pix_simt(p, n, st);
+}
+
+B200_API int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int n, int h, int w, int cin, int cout,
+                             int ksize, int up, void* stream) {
+    B200_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
+    B200_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv_wgrad: up must be 1, or 2 with ksize 3");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int taps = ksize * ksize;
+    ConvWgradParams p{};
+    const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
+    p.A = dy; p.a_bs = (long)hs * ws * cout; p.HA = hs; p.WA = ws; p.Cm = cout; p.sAy = p.sAx = up;
+    p.B = x; p.b_bs = (long)h * w * cin; p.HB = h; p.WB = w; p.Cn = cin; p.sBy = p.sBx = 1;
+    p.Hi = h; p.Wi = w; p.ntaps = taps; p.ctaps = taps;
+    p.C = dwmod; p.c_bs = (long)taps * cout * cin;
+    for (int t = 0; t < taps; ++t) {
+        const int kh = t / ksize, kw = t % ksize;
+        p.dAy[t] = up == 1 ? 0 : kh; p.dAx[t] = up == 1 ? 0 : kw;
+        p.dBy[t] = up == 1 ? kh - ksize / 2 : 0; p.dBx[t] = up == 1 ? kw - ksize / 2 : 0;
+        p.wt[t] = t;
+    }
+    return launch_conv_wgrad_simt(p, n, st);
+}
+
+B200_API const char* b200_last_error() { return g_b200_err; }
+B200_API int b200_version() { return 100; }

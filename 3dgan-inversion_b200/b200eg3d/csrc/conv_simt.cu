@@ -1,0 +1,248 @@
+// fp32 SIMT implicit-GEMM convolution kernels over NHWC activations.
+//
+// These are the exact-fp32 "universal" path of the modulated-conv stack: every conv variant of
+// the StyleGAN2 / SR blocks (reference: training/networks_stylegan2.py:34-91,
+// torch_utils/ops/conv2d_resample.py:48-143) is expressed as one of two gather-GEMMs
+//   pix  : C[pixel, n]     = sum_{tap, c} A[src(pixel, tap), c] * B[tap, c, n]        (fwd, dgrad, 1x1, convT classes)
+//   wgrad: C[tap, m, n]    = sum_{pixel}  A[srcA(pixel, tap), m] * B[srcB(pixel, tap), n]
+// with a tap table (dy, dx, weight-slice) and integer strides describing the gather.  They handle any
+// channel count (guards everywhere) and are used for layers whose shapes do not fit the tcgen05 tiles.
+#include "common.cuh"
+#include "conv_geom.h"
+
+#define BM 128
+#define BN 128
+#define BK 8
+
+__global__ void __launch_bounds__(256) conv_pix_kernel(ConvPixParams p) {
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const float* __restrict__ A = p.A + (long)b * p.a_bs;
+    const float* __restrict__ B = p.B + (long)b * p.b_bs;
+    float* __restrict__ C = p.C + (long)b * p.c_bs;
+    const int M = p.g.Hi * p.g.Wi;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    // A-tile loader coordinates: one pixel row, 4 consecutive channels.
+    const int a_row = tid >> 1, a_kq = (tid & 1) * 4;
+    const int am = m0 + a_row;
+    const bool a_valid = am < M;
+    const int a_iy = a_valid ? am / p.g.Wi : 0, a_ix = a_valid ? am % p.g.Wi : 0;
+    const bool vecA = (p.g.Ca & 3) == 0;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    const int ty = tid >> 4, tx = tid & 15;
+
+    for (int t = 0; t < p.g.ntaps; ++t) {
+        const int sy = a_iy * p.g.sy + p.g.dy[t], sx = a_ix * p.g.sx + p.g.dx[t];
+        const bool inb = a_valid && sy >= 0 && sy < p.g.Hs && sx >= 0 && sx < p.g.Ws;
+        const float* arow = A + ((long)sy * p.g.Ws + sx) * p.g.Ca;
+        const float* Bt = B + (long)p.g.wt[t] * p.b_ts;
+        for (int c0 = 0; c0 < p.g.Ca; c0 += BK) {
+            // ---- A tile
+            float av[4] = {0.f, 0.f, 0.f, 0.f};
+            const int ca = c0 + a_kq;
+            if (inb) {
+                if (vecA && ca + 3 < p.g.Ca) {
+                    float4 v = __ldg(reinterpret_cast<const float4*>(arow + ca));
+                    av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (ca + j < p.g.Ca) av[j] = __ldg(arow + ca + j);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) As[a_kq + j][a_row] = av[j];
+            // ---- B tile
+            if (p.b_mode == 1) {            // K-contiguous: 4 consecutive k for one n
+                const int n = tid >> 1, kq = (tid & 1) * 4;
+                float bv[4] = {0.f, 0.f, 0.f, 0.f};
+                const int c = c0 + kq;
+                if (n0 + n < p.N) {
+                    const float* bp = Bt + (long)(n0 + n) * p.b_ns + c;
+                    if (c + 3 < p.g.Ca) {
+                        float4 v = __ldg(reinterpret_cast<const float4*>(bp));
+                        bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (c + j < p.g.Ca) bv[j] = __ldg(bp + j);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) Bs[kq + j][n] = bv[j];
+            } else if (p.b_mode == 2) {     // N-contiguous: 4 consecutive n for one k
+                const int k = tid >> 5, n4 = (tid & 31) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int c = c0 + k;
+                if (c < p.g.Ca && n0 + n4 + 3 < p.N)
+                    v = __ldg(reinterpret_cast<const float4*>(Bt + (long)c * p.b_ks + n0 + n4));
+                else if (c < p.g.Ca) {
+                    const float* bp = Bt + (long)c * p.b_ks + n0 + n4;
+                    if (n0 + n4 + 0 < p.N) v.x = __ldg(bp + 0);
+                    if (n0 + n4 + 1 < p.N) v.y = __ldg(bp + 1);
+                    if (n0 + n4 + 2 < p.N) v.z = __ldg(bp + 2);
+                }
+                *reinterpret_cast<float4*>(&Bs[k][n4]) = v;
+            } else {                         // generic strides
+                const int k = tid >> 5, n4 = (tid & 31) * 4;
+                const int c = c0 + k;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = 0.f;
+                    if (c < p.g.Ca && n0 + n4 + j < p.N) v = __ldg(Bt + (long)c * p.b_ks + (long)(n0 + n4 + j) * p.b_ns);
+                    Bs[k][n4 + j] = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < BK; ++k) {
+                float a[8], bb[8];
+                *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+                *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+                *reinterpret_cast<float4*>(&bb[0]) = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+                *reinterpret_cast<float4*>(&bb[4]) = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+    }
+    // ---- store
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (m >= M) continue;
+        const int iy = m / p.g.Wi, ix = m % p.g.Wi;
+        const long opix = (long)(iy * p.g.osy + p.g.ooy) * p.g.Wo + (ix * p.g.osx + p.g.oox);
+        float* crow = C + opix * p.ldc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            if (n < p.N) {
+                float v = acc[i][j];
+                if (p.accumulate) v += crow[n];
+                crow[n] = v;
+            }
+        }
+    }
+}
+
+// C[wt[t]][m][n] (+)= sum_pixels A[srcA(pixel,t)][m] * B[srcB(pixel,t)][n]
+__global__ void __launch_bounds__(256) conv_wgrad_kernel(ConvWgradParams p) {
+    __shared__ __align__(16) float As[BK][BM];
+    __shared__ __align__(16) float Bs[BK][BN];
+    const int tid = threadIdx.x;
+    int z = blockIdx.z;
+    const int ks = z % p.ksplit; z /= p.ksplit;
+    const int t = z % p.ntaps;
+    const int b = z / p.ntaps;
+    const float* __restrict__ A = p.A + (long)b * p.a_bs;
+    const float* __restrict__ B = p.B + (long)b * p.b_bs;
+    float* __restrict__ C = p.C + (long)b * p.c_bs + (long)p.wt[t] * p.Cm * p.Cn;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int K = p.Hi * p.Wi;
+    const int kchunk = ((K + p.ksplit - 1) / p.ksplit + BK - 1) / BK * BK;
+    const int kbeg = ks * kchunk, kend = min(K, kbeg + kchunk);
+
+    const int kk = tid >> 5, c4 = (tid & 31) * 4;
+    const bool vecA = (p.Cm & 3) == 0, vecB = (p.Cn & 3) == 0;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int ty = tid >> 4, tx = tid & 15;
+
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        const int k = k0 + kk;
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        if (k < kend) {
+            const int iy = k / p.Wi, ix = k % p.Wi;
+            const int ay = iy * p.sAy + p.dAy[t], ax = ix * p.sAx + p.dAx[t];
+            if (ay >= 0 && ay < p.HA && ax >= 0 && ax < p.WA) {
+                const float* ap = A + ((long)ay * p.WA + ax) * p.Cm + m0 + c4;
+                if (vecA && m0 + c4 + 3 < p.Cm) va = __ldg(reinterpret_cast<const float4*>(ap));
+                else {
+                    if (m0 + c4 + 0 < p.Cm) va.x = __ldg(ap + 0);
+                    if (m0 + c4 + 1 < p.Cm) va.y = __ldg(ap + 1);
+                    if (m0 + c4 + 2 < p.Cm) va.z = __ldg(ap + 2);
+                    if (m0 + c4 + 3 < p.Cm) va.w = __ldg(ap + 3);
+                }
+            }
+            const int by = iy * p.sBy + p.dBy[t], bx = ix * p.sBx + p.dBx[t];
+            if (by >= 0 && by < p.HB && bx >= 0 && bx < p.WB) {
+                const float* bp = B + ((long)by * p.WB + bx) * p.Cn + n0 + c4;
+                if (vecB && n0 + c4 + 3 < p.Cn) vb = __ldg(reinterpret_cast<const float4*>(bp));
+                else {
+                    if (n0 + c4 + 0 < p.Cn) vb.x = __ldg(bp + 0);
+                    if (n0 + c4 + 1 < p.Cn) vb.y = __ldg(bp + 1);
+                    if (n0 + c4 + 2 < p.Cn) vb.z = __ldg(bp + 2);
+                    if (n0 + c4 + 3 < p.Cn) vb.w = __ldg(bp + 3);
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(&As[kk][c4]) = va;
+        *reinterpret_cast<float4*>(&Bs[kk][c4]) = vb;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < BK; ++q) {
+            float a[8], bb[8];
+            *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[q][ty * 4]);
+            *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[q][64 + ty * 4]);
+            *reinterpret_cast<float4*>(&bb[0]) = *reinterpret_cast<const float4*>(&Bs[q][tx * 4]);
+            *reinterpret_cast<float4*>(&bb[4]) = *reinterpret_cast<const float4*>(&Bs[q][64 + tx * 4]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (m >= p.Cm) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+            if (n < p.Cn) {
+                if (p.ksplit > 1) atomicAdd(C + (long)m * p.Cn + n, acc[i][j]);
+                else C[(long)m * p.Cn + n] = acc[i][j];
+            }
+        }
+    }
+}
+
+int launch_conv_pix_simt(const ConvPixParams& p, int batch, cudaStream_t st) {
+    const int M = p.g.Hi * p.g.Wi;
+    if (M <= 0 || p.N <= 0 || batch <= 0) return 0;
+    dim3 grid(cdiv(M, BM), cdiv(p.N, BN), batch);
+    conv_pix_kernel<<<grid, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_conv_wgrad_simt(ConvWgradParams p, int batch, cudaStream_t st) {
+    const int K = p.Hi * p.Wi;
+    if (K <= 0 || p.Cm <= 0 || p.Cn <= 0 || batch <= 0) return 0;
+    const int tiles = cdiv(p.Cm, BM) * cdiv(p.Cn, BN) * p.ntaps * batch;
+    int ksplit = 1;
+    if (tiles < 296) ksplit = min(cdiv(296, tiles), max(1, K / 64));
+    p.ksplit = ksplit;
+    if (ksplit > 1)
+        for (int b = 0; b < batch; ++b)
+            B200_CUDA(cudaMemsetAsync(p.C + (long)b * p.c_bs, 0, sizeof(float) * (size_t)p.ctaps * p.Cm * p.Cn, st));
+    dim3 grid(cdiv(p.Cm, BM), cdiv(p.Cn, BN), p.ntaps * ksplit * batch);
+    conv_wgrad_kernel<<<grid, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

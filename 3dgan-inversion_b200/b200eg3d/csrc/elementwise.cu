@@ -1,0 +1,288 @@
+// Elementwise / FIR kernels of the synthesis stack:
+//   b200_bias_act        generic bias+activation+gain+clamp, forward and first-order gradient
+//                        (semantics of torch_utils/ops/bias_act.cu:28-151, plugin entry bias_act.cpp:36)
+//   b200_layer_act_*     the SynthesisLayer epilogue: + noise*strength, + bias, lrelu, gain, clamp
+//                        (training/networks_stylegan2.py:318-329) and its backward incl. all reductions
+//   b200_upfirdn2d       pad / zero-insert upsample / FIR / decimate on NHWC tensors, optional fused "+ add"
+//                        (semantics of torch_utils/ops/upfirdn2d.py:169-213, plugin entry upfirdn2d.cpp:20)
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Generic bias_act.  act codes follow the reference table (bias_act.py:20-30): 1 linear, 2 relu, 3 lrelu,
+// 4 tanh, 5 sigmoid, 6 elu, 7 selu, 8 softplus, 9 swish.  grad: 0 forward, 1 first-order gradient.
+
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ xref,
+                                const float* __restrict__ yref, const float* __restrict__ dy, float* __restrict__ y,
+                                int grad, long sizeX, long stepB, int sizeB, int act, float alpha, float gain, float clamp) {
+    const float seluScale = 1.0507009873554804934193349852946f, seluAlpha = 1.6732632423543772848170429916717f;
+    for (long xi = (long)blockIdx.x * blockDim.x + threadIdx.x; xi < sizeX; xi += (long)gridDim.x * blockDim.x) {
+        float xv = x[xi];
+        const float bv = b ? b[(xi / stepB) % sizeB] : 0.f;
+        float xr = xref ? xref[xi] : 0.f;
+        float yr = yref ? yref[xi] : 0.f;
+        const float dyv = dy ? dy[xi] : 1.f;
+        const float yy = gain != 0.f ? yr / gain : 0.f;
+        float out = 0.f;
+        if (grad == 0) xv += bv; else xr += bv;
+        switch (act) {
+            case 1: out = xv; break;
+            case 2: out = grad == 0 ? (xv > 0.f ? xv : 0.f) : (yy > 0.f ? xv : 0.f); break;
+            case 3: out = grad == 0 ? (xv > 0.f ? xv : xv * alpha) : (yy > 0.f ? xv : xv * alpha); break;
+            case 4: if (grad == 0) { float c = expf(xv), d = 1.f / c; out = xv < -80.f ? -1.f : xv > 80.f ? 1.f : (c - d) / (c + d); }
+                    else out = xv * (1.f - yy * yy); break;
+            case 5: out = grad == 0 ? (xv < -80.f ? 0.f : 1.f / (expf(-xv) + 1.f)) : xv * yy * (1.f - yy); break;
+            case 6: out = grad == 0 ? (xv >= 0.f ? xv : expf(xv) - 1.f) : (yy >= 0.f ? xv : xv * (yy + 1.f)); break;
+            case 7: out = grad == 0 ? (xv >= 0.f ? seluScale * xv : seluScale * seluAlpha * (expf(xv) - 1.f))
+                                    : (yy >= 0.f ? xv * seluScale : xv * (yy + seluScale * seluAlpha)); break;
+            case 8: out = grad == 0 ? (xv > 80.f ? xv : logf(expf(xv) + 1.f)) : xv * (1.f - expf(-yy)); break;
+            case 9: if (grad == 0) out = xv < -80.f ? 0.f : xv / (expf(-xv) + 1.f);
+                    else { float c = expf(xr), d = c + 1.f; out = xr > 40.f ? xv : xv * c * (xr + d) / (d * d);
+                           yr = xr < -80.f ? 0.f : xr / (expf(-xr) + 1.f) * gain; } break;
+            default: break;
+        }
+        out *= gain * dyv;
+        if (clamp >= 0.f) {
+            if (grad == 0) out = (out > -clamp && out < clamp) ? out : (out >= 0.f ? clamp : -clamp);
+            else out = (yr > -clamp && yr < clamp) ? out : 0.f;
+        }
+        y[xi] = out;
+    }
+}
+
+B200_API int b200_bias_act(const float* x, const float* b, const float* xref, const float* yref, const float* dy, float* y,
+                           int grad, long sizeX, long stepB, int sizeB, int act, float alpha, float gain, float clamp,
+                           void* stream) {
+    B200_REQUIRE(grad == 0 || grad == 1, "bias_act: only forward (0) and first-order gradient (1) are implemented");
+    B200_REQUIRE(act >= 1 && act <= 9, "bias_act: unknown activation code");
+    B200_REQUIRE(!b || (stepB > 0 && sizeB > 0), "bias_act: bad bias indexing");
+    if (sizeX <= 0) return 0;
+    const int blocks = (int)((sizeX + 255) / 256 < 148 * 16 ? (sizeX + 255) / 256 : 148 * 16);
+    bias_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, b, xref, yref, dy, y, grad, sizeX, stepB > 0 ? stepB : 1,
+                                                              sizeB > 0 ? sizeB : 1, act, alpha, gain, clamp);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SynthesisLayer epilogue on NHWC [n][hw][c]:  z = clamp(act(y + noise[pix]*strength + bias[c]) * gain, +-clamp)
+// noise may be null; noise_bs = per-sample stride of the noise map (0 for the shared 'const' buffer).
+
+__global__ void layer_act_fwd_kernel(const float4* __restrict__ y, float4* __restrict__ z, const float* __restrict__ bias,
+                                     const float* __restrict__ noise, const float* __restrict__ strength, long noise_bs,
+                                     long total4, int hw, int c4, int lrelu, float alpha, float gain, float clamp) {
+    const float str = (noise && strength) ? *strength : 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c4);
+        const long pix = i / c4;
+        float4 v = y[i];
+        float add = 0.f;
+        if (noise) add = noise[(pix / hw) * noise_bs + pix % hw] * str;
+        float4 bv = bias ? *reinterpret_cast<const float4*>(bias + cc * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float o[4] = {v.x + add + bv.x, v.y + add + bv.y, v.z + add + bv.z, v.w + add + bv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = o[j];
+            if (lrelu) t = t > 0.f ? t : t * alpha;
+            t *= gain;
+            if (clamp >= 0.f) t = (t > -clamp && t < clamp) ? t : (t >= 0.f ? clamp : -clamp);
+            o[j] = t;
+        }
+        z[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// scalar fallback for channel counts that are not a multiple of 4
+__global__ void layer_act_fwd_kernel_s(const float* __restrict__ y, float* __restrict__ z, const float* __restrict__ bias,
+                                       const float* __restrict__ noise, const float* __restrict__ strength, long noise_bs,
+                                       long total, int hw, int c, int lrelu, float alpha, float gain, float clamp) {
+    const float str = (noise && strength) ? *strength : 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c);
+        const long pix = i / c;
+        float t = y[i] + (bias ? bias[cc] : 0.f);
+        if (noise) t += noise[(pix / hw) * noise_bs + pix % hw] * str;
+        if (lrelu) t = t > 0.f ? t : t * alpha;
+        t *= gain;
+        if (clamp >= 0.f) t = (t > -clamp && t < clamp) ? t : (t >= 0.f ? clamp : -clamp);
+        z[i] = t;
+    }
+}
+
+B200_API int b200_layer_act_fwd(const float* y, float* z, const float* bias, const float* noise, const float* strength,
+                                long noise_bs, int n, int hw, int c, int lrelu, float alpha, float gain, float clamp,
+                                void* stream) {
+    const long total = (long)n * hw * c;
+    if (total <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c % 4 == 0) {
+        const long t4 = total / 4;
+        const int blocks = (int)((t4 + 255) / 256 < 148 * 16 ? (t4 + 255) / 256 : 148 * 16);
+        layer_act_fwd_kernel<<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, bias, noise, strength, noise_bs, t4, hw,
+                                                     c / 4, lrelu, alpha, gain, clamp);
+    } else {
+        const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+        layer_act_fwd_kernel_s<<<blocks, 256, 0, st>>>(y, z, bias, noise, strength, noise_bs, total, hw, c, lrelu, alpha,
+                                                       gain, clamp);
+    }
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// Backward: one warp per pixel.  dy = dz * gain * slope(z) * [|z| < clamp]   (uses the saved OUTPUT z, bias_act.cu:73-77,143-145)
+// Also reduces dbias[c] += sum_pix dy, dstrength += sum dy*noise, dnoise[pix] += strength * sum_c dy.
+template <int R>
+__global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ z,
+                                                            float* __restrict__ dy, float* __restrict__ dbias,
+                                                            const float* __restrict__ noise, const float* __restrict__ strength,
+                                                            long noise_bs, float* __restrict__ dstrength,
+                                                            float* __restrict__ dnoise, long npix, int hw, int c, int lrelu,
+                                                            float alpha, float gain, float clamp) {
+    __shared__ float s_col[R * 32];
+    __shared__ float s_str[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < R * 32; i += blockDim.x) s_col[i] = 0.f;
+    __syncthreads();
+    float col[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) col[j] = 0.f;
+    float sacc = 0.f;
+    const float str = (noise && strength) ? *strength : 0.f;
+    const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    for (long pix = (long)blockIdx.x * (blockDim.x >> 5) + wid; pix < npix; pix += nwarps) {
+        const float* dzr = dz + pix * c;
+        const float* zr = z + pix * c;
+        float* dyr = dy + pix * c;
+        float row = 0.f;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int ch = lane + 32 * j;
+            if (ch < c) {
+                const float zz = zr[ch];
+                float g = dzr[ch] * gain;
+                if (lrelu && !(zz > 0.f)) g *= alpha;
+                if (clamp >= 0.f && !(zz > -clamp && zz < clamp)) g = 0.f;
+                dyr[ch] = g;
+                col[j] += g;
+                row += g;
+            }
+        }
+        if (noise) {
+            row = warp_sum(row);
+            if (lane == 0) {
+                const long nidx = (pix / hw) * noise_bs + pix % hw;
+                sacc += row * noise[nidx];
+                if (dnoise) atomicAdd(dnoise + nidx, row * str);
+            }
+        }
+    }
+    if (dbias) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (lane + 32 * j < c) atomicAdd(&s_col[lane + 32 * j], col[j]);
+        __syncthreads();
+        for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(dbias + i, s_col[i]);
+    }
+    if (noise && dstrength) {
+        if (lane == 0) s_str[wid] = sacc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += s_str[i];
+            atomicAdd(dstrength, t);
+        }
+    }
+}
+
+B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, float* dbias, const float* noise,
+                                const float* strength, long noise_bs, float* dstrength, float* dnoise, int n, int hw, int c,
+                                int lrelu, float alpha, float gain, float clamp, void* stream) {
+    // dbias / dstrength / dnoise are ACCUMULATED into (callers zero them); any of them may be null.
+    const long npix = (long)n * hw;
+    if (npix <= 0 || c <= 0) return 0;
+    B200_REQUIRE(c <= 512, "layer_act_bwd: at most 512 channels");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)((npix + 7) / 8 < 148 * 8 ? (npix + 7) / 8 : 148 * 8);
+#define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, dy, dbias, noise, strength, noise_bs, dstrength, \
+                                                                     dnoise, npix, hw, c, lrelu, alpha, gain, clamp)
+    if (c <= 32) LAUNCH_R(1); else if (c <= 64) LAUNCH_R(2); else if (c <= 128) LAUNCH_R(4);
+    else if (c <= 256) LAUNCH_R(8); else LAUNCH_R(16);
+#undef LAUNCH_R
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upfirdn2d on NHWC [n][h][w][c]:  out[y,x] = sum_{a,b} g[a,b] * Upad[y*downy + a, x*downx + b]  (+ add[y,x])
+// U = zero-inserted input (U[u*up] = in[u]), Upad shifted by (pady0, padx0) (negative pads crop),
+// g = gain * (flip ? f : reversed f)   -- the reference correlates with the reversed filter unless flip_filter.
+
+struct UpfirdnParams {
+    const float* x; const float* f; const float* add; float* y;
+    int n, h, w, c, oh, ow, fh, fw, upx, upy, downx, downy, padx0, pady0, flip;
+    float gain;
+};
+
+template <int V>
+__global__ void upfirdn2d_kernel(UpfirdnParams p) {
+    const int cv = p.c / V;
+    const long total = (long)p.n * p.oh * p.ow * cv;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % cv) * V;
+        long r = i / cv;
+        const int ox = (int)(r % p.ow); r /= p.ow;
+        const int oy = (int)(r % p.oh);
+        const int b = (int)(r / p.oh);
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        for (int a = 0; a < p.fh; ++a) {
+            const int uy = oy * p.downy + a - p.pady0;
+            if (uy < 0 || uy % p.upy != 0) continue;
+            const int iy = uy / p.upy;
+            if (iy >= p.h) continue;
+            for (int q = 0; q < p.fw; ++q) {
+                const int ux = ox * p.downx + q - p.padx0;
+                if (ux < 0 || ux % p.upx != 0) continue;
+                const int ix = ux / p.upx;
+                if (ix >= p.w) continue;
+                const float g = p.flip ? p.f[a * p.fw + q] : p.f[(p.fh - 1 - a) * p.fw + (p.fw - 1 - q)];
+                const float* src = p.x + (((long)b * p.h + iy) * p.w + ix) * p.c + cc;
+                if (V == 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                    acc[0] = fmaf(g, v.x, acc[0]); acc[1] = fmaf(g, v.y, acc[1]);
+                    acc[2 % V] = fmaf(g, v.z, acc[2 % V]); acc[3 % V] = fmaf(g, v.w, acc[3 % V]);
+                } else {
+                    acc[0] = fmaf(g, __ldg(src), acc[0]);
+                }
+            }
+        }
+        const long o = (((long)b * p.oh + oy) * p.ow + ox) * p.c + cc;
+        if (V == 4) {
+            float4 out = make_float4(acc[0] * p.gain, acc[1] * p.gain, acc[2 % V] * p.gain, acc[3 % V] * p.gain);
+            if (p.add) { const float4 ad = *reinterpret_cast<const float4*>(p.add + o); out.x += ad.x; out.y += ad.y; out.z += ad.z; out.w += ad.w; }
+            *reinterpret_cast<float4*>(p.y + o) = out;
+        } else {
+            float out = acc[0] * p.gain;
+            if (p.add) out += p.add[o];
+            p.y[o] = out;
+        }
+    }
+}
+
+B200_API int b200_upfirdn2d(const float* x, const float* f, const float* add, float* y, int n, int h, int w, int c, int fh,
+                            int fw, int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
+                            int flip, float gain, void* stream) {
+    B200_REQUIRE(upx >= 1 && upy >= 1 && downx >= 1 && downy >= 1, "upfirdn2d: up/down factors must be >= 1");
+    B200_REQUIRE(fh >= 1 && fw >= 1, "upfirdn2d: empty filter");
+    UpfirdnParams p{x, f, add, y, n, h, w, c, 0, 0, fh, fw, upx, upy, downx, downy, padx0, pady0, flip, gain};
+    p.oh = (h * upy + pady0 + pady1 - fh + downy) / downy;
+    p.ow = (w * upx + padx0 + padx1 - fw + downx) / downx;
+    B200_REQUIRE(p.oh >= 1 && p.ow >= 1, "upfirdn2d: output would be empty");
+    const bool v4 = (c % 4 == 0);
+    const long total = (long)n * p.oh * p.ow * (v4 ? c / 4 : c);
+    if (total <= 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    if (v4) upfirdn2d_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else upfirdn2d_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

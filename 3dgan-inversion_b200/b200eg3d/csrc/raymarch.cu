@@ -1,0 +1,290 @@
+// Per-ray kernels of the volume renderer: one warp owns one ray.
+//   b200_ray_depths_coarse   stratified depths             (renderer.py:224-247)
+//   b200_depth_minmax        global min/max of all depths  (ray_marcher.py:50)
+//   b200_ray_importance      coarse weights -> smoothed pdf -> inverse-CDF fine depths   (renderer.py:249-308)
+//   b200_ray_composite_fwd   merge coarse+fine by depth, mid-point alpha compositing     (renderer.py:212-222, ray_marcher.py:25-57)
+//   b200_ray_composite_bwd   its backward (gradients to colours and densities; depths carry no gradient)
+#include "common.cuh"
+#include <cfloat>
+
+namespace {
+constexpr int MAXS = 256;     // max samples per ray after merging (96+96 = 192 for the stress config)
+
+__device__ __forceinline__ unsigned f2ord(float f) {      // order-preserving float -> uint
+    const unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void depths_coarse_kernel(const float* __restrict__ t_base, const float* __restrict__ u, float* __restrict__ t,
+                                     long total, int S, float delta) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+        t[i] = t_base[i % S] + u[i] * delta;
+}
+
+__global__ void depth_minmax_kernel(const float* __restrict__ t, long total, unsigned* __restrict__ mm) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const float v = t[i];
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+}
+
+// alpha_k / weights of the mid-point rule on SORTED samples held in shared memory (lane-strided + lane-0 scan)
+__device__ __forceinline__ void march_weights(const float* ts, const float* ss, int S, float* alpha, float* trans, float* w,
+                                              int lane) {
+    for (int k = lane; k < S - 1; k += 32) {
+        const float delta = ts[k + 1] - ts[k];
+        const float sp = softplus_f(0.5f * (ss[k] + ss[k + 1]) - 1.f);
+        alpha[k] = 1.f - expf(-sp * delta);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float T = 1.f;
+        for (int k = 0; k < S - 1; ++k) { trans[k] = T; w[k] = alpha[k] * T; T *= (1.f - alpha[k] + 1e-10f); }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) ray_importance_kernel(const float* __restrict__ t_c, const float* __restrict__ sigma_c,
+                                                             const float* __restrict__ u, float* __restrict__ t_f,
+                                                             long n_rays, int S, int S_imp) {
+    __shared__ float sm[4][5 * MAXS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* ts = sm[wid]; float* ss = ts + MAXS; float* alpha = ss + MAXS; float* trans = alpha + MAXS; float* w = trans + MAXS;
+    for (long ray = (long)blockIdx.x * 4 + wid; ray < n_rays; ray += (long)gridDim.x * 4) {
+        for (int k = lane; k < S; k += 32) { ts[k] = t_c[ray * S + k]; ss[k] = sigma_c[ray * S + k]; }
+        __syncwarp();
+        march_weights(ts, ss, S, alpha, trans, w, lane);
+        const int L = S - 1;                       // number of weights
+        // w_hat = avgpool2(maxpool2_pad1(w)) + 0.01        (length L), stored in alpha[]
+        for (int i = lane; i < L; i += 32) {
+            const float m0 = i == 0 ? w[0] : fmaxf(w[i - 1], w[i]);
+            const float m1 = i + 1 <= L - 1 ? fmaxf(w[i], w[i + 1]) : w[L - 1];
+            alpha[i] = 0.5f * (m0 + m1) + 0.01f;
+        }
+        __syncwarp();
+        // pdf over w_hat[1 : L-1] + 1e-5 (NB = L-2 entries), cdf with leading zero (NB+1 entries) in trans[]
+        const int NB = L - 2;
+        if (lane == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < NB; ++i) tot += alpha[1 + i] + 1e-5f;
+            float c = 0.f;
+            trans[0] = 0.f;
+            for (int i = 0; i < NB; ++i) { c += (alpha[1 + i] + 1e-5f) / tot; trans[1 + i] = c; }
+        }
+        __syncwarp();
+        for (int j = lane; j < S_imp; j += 32) {
+            const float uu = u[ray * S_imp + j];
+            int lo = 0, hi = NB + 1;                // searchsorted(right=True): first index with cdf > u
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (trans[mid] <= uu) lo = mid + 1; else hi = mid; }
+            const int below = max(lo - 1, 0), above = min(lo, NB);
+            const float c0 = trans[below], c1 = trans[above];
+            const float b0 = 0.5f * (ts[below] + ts[below + 1]), b1 = 0.5f * (ts[above] + ts[above + 1]);
+            float den = c1 - c0;
+            if (den < 1e-5f) den = 1.f;
+            t_f[ray * S_imp + j] = b0 + (uu - c0) / den * (b1 - b0);
+        }
+        __syncwarp();
+    }
+}
+
+struct CompositeParams {
+    const float* t_c; const float* sigma_c; const float* rgb_c; int S1;
+    const float* t_f; const float* sigma_f; const float* rgb_f; int S2;
+    const unsigned* minmax; int white_back; long n_rays;
+    float* feat; float* depth; float* wsum;
+    const float* d_feat; const float* d_depth; const float* d_wsum;
+    float* d_rgb_c; float* d_sigma_c; float* d_rgb_f; float* d_sigma_f;
+};
+
+// Loads one ray, ranks the merged samples by depth (ties broken by original index) and fills
+// ts/ss (sorted depth, density) and rk[i] = sorted position of original sample i.
+__device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray, float* traw, float* ts, float* ss, int* rk,
+                                              int lane) {
+    const int S = p.S1 + p.S2;
+    for (int i = lane; i < S; i += 32) traw[i] = i < p.S1 ? p.t_c[ray * p.S1 + i] : p.t_f[ray * p.S2 + i - p.S1];
+    __syncwarp();
+    for (int i = lane; i < S; i += 32) {
+        const float ti = traw[i];
+        int r = 0;
+        for (int j = 0; j < S; ++j) { const float tj = traw[j]; r += (tj < ti) || (tj == ti && j < i); }
+        rk[i] = r;
+        ts[r] = ti;
+        ss[r] = i < p.S1 ? p.sigma_c[ray * p.S1 + i] : p.sigma_f[ray * p.S2 + i - p.S1];
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams p) {
+    __shared__ float sm[4][6 * MAXS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* traw = sm[wid]; float* ts = traw + MAXS; float* ss = ts + MAXS; float* alpha = ss + MAXS;
+    float* trans = alpha + MAXS; float* w = trans + MAXS;
+    __shared__ int srk[4][MAXS];
+    int* rk = srk[wid];
+    const int S = p.S1 + p.S2;
+    const float dmin = ord2f(p.minmax[0]), dmax = ord2f(p.minmax[1]);
+    for (long ray = (long)blockIdx.x * 4 + wid; ray < p.n_rays; ray += (long)gridDim.x * 4) {
+        load_and_rank(p, ray, traw, ts, ss, rk, lane);
+        march_weights(ts, ss, S, alpha, trans, w, lane);
+        float ws = 0.f, dn = 0.f;
+        for (int k = lane; k < S - 1; k += 32) { ws += w[k]; dn += w[k] * 0.5f * (ts[k] + ts[k + 1]); }
+        ws = warp_sum(ws); dn = warp_sum(dn);
+        float acc = 0.f;
+        for (int i = 0; i < S; ++i) {
+            const int r = rk[i];
+            const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+            const float c = i < p.S1 ? p.rgb_c[(ray * p.S1 + i) * 32 + lane] : p.rgb_f[(ray * p.S2 + i - p.S1) * 32 + lane];
+            acc = fmaf(om, c, acc);
+        }
+        if (p.white_back) acc += 1.f - ws;
+        p.feat[ray * 32 + lane] = acc * 2.f - 1.f;
+        if (lane == 0) {
+            float d = dn / ws;
+            d = (d != d) ? dmax : fminf(fmaxf(d, dmin), dmax);
+            p.depth[ray] = d;
+            p.wsum[ray] = ws;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams p) {
+    __shared__ float sm[4][8 * MAXS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* traw = sm[wid]; float* ts = traw + MAXS; float* ss = ts + MAXS; float* alpha = ss + MAXS;
+    float* trans = alpha + MAXS; float* w = trans + MAXS; float* dom = w + MAXS; float* dsb = dom + MAXS;
+    __shared__ int srk[4][MAXS];
+    int* rk = srk[wid];
+    const int S = p.S1 + p.S2;
+    const float dmin = ord2f(p.minmax[0]), dmax = ord2f(p.minmax[1]);
+    for (long ray = (long)blockIdx.x * 4 + wid; ray < p.n_rays; ray += (long)gridDim.x * 4) {
+        load_and_rank(p, ray, traw, ts, ss, rk, lane);
+        march_weights(ts, ss, S, alpha, trans, w, lane);
+        float ws = 0.f, dn = 0.f;
+        for (int k = lane; k < S - 1; k += 32) { ws += w[k]; dn += w[k] * 0.5f * (ts[k] + ts[k + 1]); }
+        ws = warp_sum(ws); dn = warp_sum(dn);
+        const float D = dn / ws;
+        const bool d_pass = (D == D) && D >= dmin && D <= dmax;
+        const float gD = (d_pass && p.d_depth) ? p.d_depth[ray] : 0.f;
+        const float gW = p.d_wsum ? p.d_wsum[ray] : 0.f;
+        const float g = 2.f * p.d_feat[ray * 32 + lane];        // through rgb*2-1
+        const float gsum = p.white_back ? warp_sum(g) : 0.f;     // through + 1 - wsum
+        // colours: d c_i = omega_rank(i) * g ; d omega_rank(i) = sum_lane g * c_i
+        for (int i = 0; i < S; ++i) {
+            const int r = rk[i];
+            const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+            const bool co = i < p.S1;
+            const long idx = co ? (ray * p.S1 + i) * 32 + lane : (ray * p.S2 + i - p.S1) * 32 + lane;
+            const float c = co ? p.rgb_c[idx] : p.rgb_f[idx];
+            (co ? p.d_rgb_c : p.d_rgb_f)[idx] = om * g;
+            const float t = warp_sum(g * c);
+            if (lane == 0) dom[r] = t;
+        }
+        __syncwarp();
+        // d w_k, stored in dsb[]
+        for (int k = lane; k < S - 1; k += 32) {
+            float dw = 0.5f * (dom[k] + dom[k + 1]) - gsum + gW;
+            if (gD != 0.f) dw += gD * (0.5f * (ts[k] + ts[k + 1]) - D) / ws;
+            dsb[k] = dw;
+        }
+        __syncwarp();
+        // reverse scan: d alpha_k (into dom[])
+        if (lane == 0) {
+            float dTn = 0.f;
+            for (int k = S - 2; k >= 0; --k) {
+                const float dw = dsb[k];
+                dom[k] = trans[k] * (dw - dTn);
+                dTn = dw * alpha[k] + dTn * (1.f - alpha[k] + 1e-10f);
+            }
+        }
+        __syncwarp();
+        // d sigma_mid_k (into dsb[])
+        for (int k = lane; k < S - 1; k += 32) {
+            const float delta = ts[k + 1] - ts[k];
+            const float x = 0.5f * (ss[k] + ss[k + 1]) - 1.f;
+            const float sp = softplus_f(x);
+            const float dsp = dom[k] * delta * expf(-sp * delta);
+            dsb[k] = dsp * (x > 20.f ? 1.f : sigmoid_f(x));
+        }
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) {
+            const int r = rk[i];
+            const float ds = 0.5f * ((r > 0 ? dsb[r - 1] : 0.f) + (r < S - 1 ? dsb[r] : 0.f));
+            if (i < p.S1) p.d_sigma_c[ray * p.S1 + i] = ds; else p.d_sigma_f[ray * p.S2 + i - p.S1] = ds;
+        }
+        __syncwarp();
+    }
+}
+}  // namespace
+
+B200_API int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta,
+                                    void* stream) {
+    const long total = n_rays * S;
+    if (total <= 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    depths_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t_base, u, t, total, S, delta);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// minmax: two uint32 in order-preserving encoding, initialised by the caller to {0xFFFFFFFF, 0}.
+B200_API int b200_depth_minmax(const float* t, long total, unsigned* minmax, void* stream) {
+    if (total <= 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 4 ? (total + 255) / 256 : 148 * 4);
+    depth_minmax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t, total, minmax);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+B200_API int b200_ray_importance(const float* t_c, const float* sigma_c, const float* u, float* t_f, long n_rays, int S,
+                                 int S_imp, void* stream) {
+    B200_REQUIRE(S >= 4 && S <= MAXS, "ray_importance: need 4 <= depth_resolution <= 256");
+    if (n_rays <= 0 || S_imp <= 0) return 0;
+    const int blocks = (int)((n_rays + 3) / 4 < 148 * 8 ? (n_rays + 3) / 4 : 148 * 8);
+    ray_importance_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(t_c, sigma_c, u, t_f, n_rays, S, S_imp);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+B200_API int b200_ray_composite_fwd(const float* t_c, const float* sigma_c, const float* rgb_c, int S1, const float* t_f,
+                                    const float* sigma_f, const float* rgb_f, int S2, const unsigned* minmax,
+                                    int white_back, long n_rays, float* feat, float* depth, float* wsum, void* stream) {
+    B200_REQUIRE(S1 >= 1 && S2 >= 0 && S1 + S2 >= 2 && S1 + S2 <= MAXS, "ray_composite: need 2 <= samples per ray <= 256");
+    if (n_rays <= 0) return 0;
+    CompositeParams p{};
+    p.t_c = t_c; p.sigma_c = sigma_c; p.rgb_c = rgb_c; p.S1 = S1; p.t_f = t_f; p.sigma_f = sigma_f; p.rgb_f = rgb_f; p.S2 = S2;
+    p.minmax = minmax; p.white_back = white_back; p.n_rays = n_rays; p.feat = feat; p.depth = depth; p.wsum = wsum;
+    const int blocks = (int)((n_rays + 3) / 4 < 148 * 8 ? (n_rays + 3) / 4 : 148 * 8);
+    ray_composite_fwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+B200_API int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, const float* rgb_c, int S1, const float* t_f,
+                                    const float* sigma_f, const float* rgb_f, int S2, const unsigned* minmax,
+                                    int white_back, long n_rays, const float* d_feat, const float* d_depth,
+                                    const float* d_wsum, float* d_rgb_c, float* d_sigma_c, float* d_rgb_f, float* d_sigma_f,
+                                    void* stream) {
+    B200_REQUIRE(S1 >= 1 && S2 >= 0 && S1 + S2 >= 2 && S1 + S2 <= MAXS, "ray_composite: need 2 <= samples per ray <= 256");
+    B200_REQUIRE(d_feat, "ray_composite_bwd: d_feat is required");
+    if (n_rays <= 0) return 0;
+    CompositeParams p{};
+    p.t_c = t_c; p.sigma_c = sigma_c; p.rgb_c = rgb_c; p.S1 = S1; p.t_f = t_f; p.sigma_f = sigma_f; p.rgb_f = rgb_f; p.S2 = S2;
+    p.minmax = minmax; p.white_back = white_back; p.n_rays = n_rays;
+    p.d_feat = d_feat; p.d_depth = d_depth; p.d_wsum = d_wsum;
+    p.d_rgb_c = d_rgb_c; p.d_sigma_c = d_sigma_c; p.d_rgb_f = d_rgb_f; p.d_sigma_f = d_sigma_f;
+    const int blocks = (int)((n_rays + 3) / 4 < 148 * 8 ? (n_rays + 3) / 4 : 148 * 8);
+    ray_composite_bwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,429 @@
+// Fused tri-plane sampling + OSG decoder MLP (+ its backward).
+//
+// Restates, as one kernel per direction, what the reference does with grid_sample -> mean -> FC(32,64)
+// -> softplus -> FC(64,33) -> sigmoid (training/volumetric_rendering/renderer.py:39-66,
+// training/triplane.py:124-136).  Planes are read in NHWC [n][H][W][96] (plane p = channels 32p..32p+31,
+// one 128-byte line per texel and plane), so a warp gathers one texel with one coalesced request.
+//
+// Work decomposition: a warp owns 32 consecutive sample points.
+//   gather : lane == channel, the 12 texels of one point are 12 coalesced 128 B requests
+//   MLP    : lane == point, weights broadcast from shared memory (LDS.128), activations in registers
+// The two phases are stitched with a per-warp shared-memory transpose.
+#include "common.cuh"
+
+namespace {
+constexpr int C = 32, HID = 64, OUT = 33, PC = 96;
+constexpr int SA = 33;      // stride of the feature staging tile
+constexpr int SO = 36;      // stride of the d_out tile (16 B aligned rows for LDS.128 broadcasts)
+constexpr int SH = 68;      // stride of the hidden tile
+
+struct TriplaneParams {
+    const float* planes; int n, hp, wp;
+    const float* coords;                                   // [n][P][3] or null (ray mode)
+    const float* ray_o; const float* ray_d; const float* depths; int S;   // ray mode: point p belongs to ray p / S
+    long P;
+    float coord_scale;                                     // 2 / box_warp
+    const float* W1; const float* b1; const float* W2; const float* b2;
+    float w1g, b1g, w2g, b2g;
+    float* rgb; float* sigma;
+    // backward only
+    const float* d_rgb; const float* d_sigma;
+    float* d_planes; float* d_coords;
+    float* dW1; float* db1; float* dW2; float* db2;
+};
+
+struct Bilin {
+    int x0, y0; float wx0, wx1, wy0, wy1; bool xin0, xin1, yin0, yin1;
+};
+
+__device__ __forceinline__ Bilin make_bilin(float gx, float gy, int hp, int wp) {
+    // grid_sample unnormalise, align_corners=False: ix = ((x+1)*W - 1)/2 ; zeros padding
+    float ix = ((gx + 1.f) * wp - 1.f) * 0.5f, iy = ((gy + 1.f) * hp - 1.f) * 0.5f;
+    ix = fminf(fmaxf(ix, -2.f), (float)wp + 1.f);
+    iy = fminf(fmaxf(iy, -2.f), (float)hp + 1.f);
+    const float fx = floorf(ix), fy = floorf(iy);
+    Bilin b;
+    b.x0 = (int)fx; b.y0 = (int)fy;
+    b.wx1 = ix - fx; b.wx0 = 1.f - b.wx1; b.wy1 = iy - fy; b.wy0 = 1.f - b.wy1;
+    b.xin0 = b.x0 >= 0 && b.x0 < wp; b.xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < wp;
+    b.yin0 = b.y0 >= 0 && b.y0 < hp; b.yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < hp;
+    return b;
+}
+
+__device__ __forceinline__ float bilin_gather(const float* __restrict__ base, const Bilin& b, int wp) {
+    const float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
+    const float* r1 = r0 + (long)wp * PC;
+    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
+    if (b.yin0 && b.xin0) t00 = __ldg(r0);
+    if (b.yin0 && b.xin1) t01 = __ldg(r0 + PC);
+    if (b.yin1 && b.xin0) t10 = __ldg(r1);
+    if (b.yin1 && b.xin1) t11 = __ldg(r1 + PC);
+    return b.wy0 * (b.wx0 * t00 + b.wx1 * t01) + b.wy1 * (b.wx0 * t10 + b.wx1 * t11);
+}
+
+__device__ __forceinline__ void bilin_scatter(float* __restrict__ base, const Bilin& b, int wp, float g) {
+    float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
+    float* r1 = r0 + (long)wp * PC;
+    if (b.yin0 && b.xin0) atomicAdd(r0, g * b.wy0 * b.wx0);
+    if (b.yin0 && b.xin1) atomicAdd(r0 + PC, g * b.wy0 * b.wx1);
+    if (b.yin1 && b.xin0) atomicAdd(r1, g * b.wy1 * b.wx0);
+    if (b.yin1 && b.xin1) atomicAdd(r1 + PC, g * b.wy1 * b.wx1);
+}
+
+// per-channel partial derivatives of the bilinear value w.r.t. (ix, iy)
+__device__ __forceinline__ void bilin_dcoord(const float* __restrict__ base, const Bilin& b, int wp, float& dix, float& diy) {
+    const float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
+    const float* r1 = r0 + (long)wp * PC;
+    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
+    if (b.yin0 && b.xin0) t00 = __ldg(r0);
+    if (b.yin0 && b.xin1) t01 = __ldg(r0 + PC);
+    if (b.yin1 && b.xin0) t10 = __ldg(r1);
+    if (b.yin1 && b.xin1) t11 = __ldg(r1 + PC);
+    dix = b.wy0 * (t01 - t00) + b.wy1 * (t11 - t10);
+    diy = b.wx0 * (t10 - t00) + b.wx1 * (t11 - t01);
+}
+
+__device__ __forceinline__ void load_weights(const TriplaneParams& p, float* W1s, float* b1s, float* W2s, float* b2s) {
+    for (int i = threadIdx.x; i < HID * C; i += blockDim.x) W1s[i] = p.W1[i] * p.w1g;
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) b1s[i] = p.b1[i] * p.b1g;
+    for (int i = threadIdx.x; i < OUT * HID; i += blockDim.x) W2s[i] = p.W2[i] * p.w2g;
+    for (int i = threadIdx.x; i < OUT; i += blockDim.x) b2s[i] = p.b2[i] * p.b2g;
+}
+
+__device__ __forceinline__ void point_coords(const TriplaneParams& p, int n, long pi, float& cx, float& cy, float& cz) {
+    cx = cy = cz = 0.f;
+    if (pi >= p.P) return;
+    if (p.coords) {
+        const float* c = p.coords + ((long)n * p.P + pi) * 3;
+        cx = c[0]; cy = c[1]; cz = c[2];
+    } else {
+        const long M = p.P / p.S;
+        const long ray = pi / p.S;
+        const float t = p.depths[(long)n * p.P + pi];
+        const float* o = p.ray_o + ((long)n * M + ray) * 3;
+        const float* d = p.ray_d + ((long)n * M + ray) * 3;
+        cx = o[0] + t * d[0]; cy = o[1] + t * d[1]; cz = o[2] + t * d[2];
+    }
+    cx *= p.coord_scale; cy *= p.coord_scale; cz *= p.coord_scale;
+}
+
+// gather the 32-channel mean feature of the warp's 32 points into sf[q*SA + channel]
+__device__ __forceinline__ void gather_features(const TriplaneParams& p, const float* __restrict__ pl, float cx, float cy,
+                                                float cz, float* sf, int lane) {
+#pragma unroll 2
+    for (int q = 0; q < 32; ++q) {
+        const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
+        const Bilin b0 = make_bilin(gx, gy, p.hp, p.wp), b1 = make_bilin(gx, gz, p.hp, p.wp), b2 = make_bilin(gz, gx, p.hp, p.wp);
+        const float v = bilin_gather(pl + lane, b0, p.wp) + bilin_gather(pl + C + lane, b1, p.wp) +
+                        bilin_gather(pl + 2 * C + lane, b2, p.wp);
+        sf[q * SA + lane] = v / 3.f;
+    }
+}
+
+__device__ __forceinline__ void mlp_hidden(const float* f, const float* W1s, const float* b1s, float* h) {
+#pragma unroll
+    for (int j = 0; j < HID; ++j) {
+        float a = b1s[j];
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(&W1s[j * C + c]);
+            a = fmaf(f[c], w.x, a); a = fmaf(f[c + 1], w.y, a); a = fmaf(f[c + 2], w.z, a); a = fmaf(f[c + 3], w.w, a);
+        }
+        h[j] = softplus_f(a);
+    }
+}
+
+__device__ __forceinline__ float mlp_out(const float* h, const float* W2s, const float* b2s, int k) {
+    float o = b2s[k];
+#pragma unroll
+    for (int j = 0; j < HID; j += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(&W2s[k * HID + j]);
+        o = fmaf(h[j], w.x, o); o = fmaf(h[j + 1], w.y, o); o = fmaf(h[j + 2], w.z, o); o = fmaf(h[j + 3], w.w, o);
+    }
+    return o;
+}
+
+__global__ void __launch_bounds__(128) triplane_mlp_fwd_kernel(TriplaneParams p) {
+    __shared__ __align__(16) float W1s[HID * C];
+    __shared__ __align__(16) float W2s[OUT * HID];
+    __shared__ float b1s[HID], b2s[OUT];
+    __shared__ float sfeat[4][32 * SA];
+    load_weights(p, W1s, b1s, W2s, b2s);
+    __syncthreads();
+    const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* sf = sfeat[wid];
+    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
+    for (long base = ((long)blockIdx.x * 4 + wid) * 32; base < p.P; base += (long)gridDim.x * 128) {
+        const long pi = base + lane;
+        float cx, cy, cz;
+        point_coords(p, n, pi, cx, cy, cz);
+        gather_features(p, pl, cx, cy, cz, sf, lane);
+        __syncwarp();
+        float f[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[c] = sf[lane * SA + c];
+        __syncwarp();
+        float h[HID];
+        mlp_hidden(f, W1s, b1s, h);
+        const float sig = mlp_out(h, W2s, b2s, 0);
+        if (pi < p.P) p.sigma[(long)n * p.P + pi] = sig;
+#pragma unroll
+        for (int k = 1; k < OUT; ++k) {
+            const float o = mlp_out(h, W2s, b2s, k);
+            sf[lane * SA + k - 1] = sigmoid_f(o) * 1.002f - 0.001f;
+        }
+        __syncwarp();
+        const int cnt = (int)min((long)32, p.P - base);
+        float* out = p.rgb + ((long)n * p.P + base) * C;
+        for (int q = 0; q < cnt; ++q) out[q * C + lane] = sf[q * SA + lane];
+        __syncwarp();
+    }
+}
+
+// dynamic shared memory layout of the backward kernel (floats)
+constexpr int BW_W = HID * C + HID + OUT * HID + OUT + 3;            // weights, padded to a multiple of 4
+constexpr int BW_WPAD = (BW_W + 3) / 4 * 4;
+constexpr int BW_ACC = HID * C + HID + OUT * HID + OUT;              // block-level parameter-gradient accumulators
+constexpr int BW_ACCPAD = (BW_ACC + 3) / 4 * 4;
+constexpr int BW_WARP = 32 * SA + 32 * SH + 32 * SO;                 // per-warp staging
+constexpr int BW_SMEM = (BW_WPAD + BW_ACCPAD + 4 * BW_WARP) * 4;
+
+__global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* W1s = smem;                       // [64][32]
+    float* W2s = W1s + HID * C;              // [33][64]
+    float* b1s = W2s + OUT * HID;
+    float* b2s = b1s + HID;
+    float* acc = smem + BW_WPAD;             // dW1 | db1 | dW2 | db2
+    float* aW1 = acc; float* ab1 = aW1 + HID * C; float* aW2 = ab1 + HID; float* ab2 = aW2 + OUT * HID;
+    const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* sA = smem + BW_WPAD + BW_ACCPAD + wid * BW_WARP;   // [32][SA] features f, later d_f
+    float* sH = sA + 32 * SA;                                 // [32][SH] hidden h, later d_a
+    float* sO = sH + 32 * SH;                                 // [32][SO] d_rgb|d_sigma in, d_out
+    const bool wgrad = p.dW1 != nullptr;
+    load_weights(p, W1s, b1s, W2s, b2s);
+    for (int i = threadIdx.x; i < BW_ACC; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
+    float* dpl = p.d_planes ? p.d_planes + (long)n * p.hp * p.wp * PC : nullptr;
+
+    for (long base = ((long)blockIdx.x * 4 + wid) * 32; base < p.P; base += (long)gridDim.x * 128) {
+        const long pi = base + lane;
+        const bool valid = pi < p.P;
+        const int cnt = (int)min((long)32, p.P - base);
+        float cx, cy, cz;
+        point_coords(p, n, pi, cx, cy, cz);
+        // 1. features and incoming gradients
+        gather_features(p, pl, cx, cy, cz, sA, lane);
+        {
+            const float* g = p.d_rgb + ((long)n * p.P + base) * C;
+            for (int q = 0; q < 32; ++q) sO[q * SO + 1 + lane] = q < cnt ? g[q * C + lane] : 0.f;
+            sO[lane * SO] = valid ? p.d_sigma[(long)n * p.P + pi] : 0.f;
+        }
+        __syncwarp();
+        float h[HID];
+        {
+            float f[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) f[c] = sA[lane * SA + c];
+            mlp_hidden(f, W1s, b1s, h);
+        }
+        // 2. d_out (k = 0: sigma, linear; k >= 1: rgb = sigmoid(o)*1.002 - 0.001)
+        float dout[OUT];
+        dout[0] = sO[lane * SO];
+#pragma unroll
+        for (int k = 1; k < OUT; ++k) {
+            const float s = sigmoid_f(mlp_out(h, W2s, b2s, k));
+            dout[k] = sO[lane * SO + k] * 1.002f * s * (1.f - s);
+        }
+        if (wgrad) {
+#pragma unroll
+            for (int k = 0; k < OUT; ++k) sO[lane * SO + k] = dout[k];
+#pragma unroll
+            for (int j = 0; j < HID; ++j) sH[lane * SH + j] = h[j];
+            __syncwarp();
+            // dW2[k][j] += sum_q dout[q][k] * h[q][j]   (lane owns j = lane, lane+32)
+            float a0[OUT], a1[OUT];
+#pragma unroll
+            for (int k = 0; k < OUT; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
+            for (int q = 0; q < 32; ++q) {
+                const float h0 = sH[q * SH + lane], h1 = sH[q * SH + 32 + lane];
+#pragma unroll
+                for (int k4 = 0; k4 < 32; k4 += 4) {
+                    const float4 d = *reinterpret_cast<const float4*>(&sO[q * SO + k4]);
+                    a0[k4] = fmaf(d.x, h0, a0[k4]); a1[k4] = fmaf(d.x, h1, a1[k4]);
+                    a0[k4 + 1] = fmaf(d.y, h0, a0[k4 + 1]); a1[k4 + 1] = fmaf(d.y, h1, a1[k4 + 1]);
+                    a0[k4 + 2] = fmaf(d.z, h0, a0[k4 + 2]); a1[k4 + 2] = fmaf(d.z, h1, a1[k4 + 2]);
+                    a0[k4 + 3] = fmaf(d.w, h0, a0[k4 + 3]); a1[k4 + 3] = fmaf(d.w, h1, a1[k4 + 3]);
+                }
+                const float d32 = sO[q * SO + 32];
+                a0[32] = fmaf(d32, h0, a0[32]); a1[32] = fmaf(d32, h1, a1[32]);
+            }
+#pragma unroll
+            for (int k = 0; k < OUT; ++k) {
+                atomicAdd(&aW2[k * HID + lane], a0[k]);
+                atomicAdd(&aW2[k * HID + 32 + lane], a1[k]);
+            }
+            // db2[k] += sum_q dout[q][k]
+            {
+                float s = 0.f, s32 = 0.f;
+                for (int q = 0; q < 32; ++q) { s += sO[q * SO + lane]; if (lane == 0) s32 += sO[q * SO + 32]; }
+                atomicAdd(&ab2[lane], s);
+                if (lane == 0) atomicAdd(&ab2[32], s32);
+            }
+            __syncwarp();
+        }
+        // 3. d_a = (W2^T d_out) * softplus'(a),  softplus'(a) = 1 - exp(-h)
+        float da[HID];
+#pragma unroll
+        for (int j = 0; j < HID; ++j) da[j] = 0.f;
+#pragma unroll
+        for (int k = 0; k < OUT; ++k) {
+#pragma unroll
+            for (int j = 0; j < HID; j += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(&W2s[k * HID + j]);
+                da[j] = fmaf(dout[k], w.x, da[j]); da[j + 1] = fmaf(dout[k], w.y, da[j + 1]);
+                da[j + 2] = fmaf(dout[k], w.z, da[j + 2]); da[j + 3] = fmaf(dout[k], w.w, da[j + 3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < HID; ++j) da[j] *= (1.f - expf(-h[j]));
+        if (wgrad) {
+#pragma unroll
+            for (int j = 0; j < HID; ++j) sH[lane * SH + j] = da[j];
+            __syncwarp();
+            // dW1[j][c] += sum_q da[q][j] * f[q][c]   (lane owns c = lane)
+            float a[HID];
+#pragma unroll
+            for (int j = 0; j < HID; ++j) a[j] = 0.f;
+            for (int q = 0; q < 32; ++q) {
+                const float fq = sA[q * SA + lane];
+#pragma unroll
+                for (int j = 0; j < HID; j += 4) {
+                    const float4 d = *reinterpret_cast<const float4*>(&sH[q * SH + j]);
+                    a[j] = fmaf(d.x, fq, a[j]); a[j + 1] = fmaf(d.y, fq, a[j + 1]);
+                    a[j + 2] = fmaf(d.z, fq, a[j + 2]); a[j + 3] = fmaf(d.w, fq, a[j + 3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < HID; ++j) atomicAdd(&aW1[j * C + lane], a[j]);
+            {
+                float s0 = 0.f, s1 = 0.f;
+                for (int q = 0; q < 32; ++q) { s0 += sH[q * SH + lane]; s1 += sH[q * SH + 32 + lane]; }
+                atomicAdd(&ab1[lane], s0); atomicAdd(&ab1[32 + lane], s1);
+            }
+        }
+        __syncwarp();
+        // 4. d_f = W1^T d_a  -> staging tile (transposed back to lane == channel)
+        {
+            float df[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) df[c] = 0.f;
+#pragma unroll
+            for (int j = 0; j < HID; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; c += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(&W1s[j * C + c]);
+                    df[c] = fmaf(da[j], w.x, df[c]); df[c + 1] = fmaf(da[j], w.y, df[c + 1]);
+                    df[c + 2] = fmaf(da[j], w.z, df[c + 2]); df[c + 3] = fmaf(da[j], w.w, df[c + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) sA[lane * SA + c] = valid ? df[c] * (1.f / 3.f) : 0.f;
+        }
+        __syncwarp();
+        // 5. scatter into the plane gradient (+ optional coordinate gradient)
+        for (int q = 0; q < cnt; ++q) {
+            const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
+            const Bilin b0 = make_bilin(gx, gy, p.hp, p.wp), b1 = make_bilin(gx, gz, p.hp, p.wp), b2 = make_bilin(gz, gx, p.hp, p.wp);
+            const float g = sA[q * SA + lane];
+            if (dpl) {
+                bilin_scatter(dpl + lane, b0, p.wp, g);
+                bilin_scatter(dpl + C + lane, b1, p.wp, g);
+                bilin_scatter(dpl + 2 * C + lane, b2, p.wp, g);
+            }
+            if (p.d_coords) {
+                float ax, ay, bx, by, ex, ey;
+                bilin_dcoord(pl + lane, b0, p.wp, ax, ay);
+                bilin_dcoord(pl + C + lane, b1, p.wp, bx, by);
+                bilin_dcoord(pl + 2 * C + lane, b2, p.wp, ex, ey);
+                const float hx = 0.5f * p.wp, hy = 0.5f * p.hp;
+                // plane0 (x->W, y->H), plane1 (x->W, z->H), plane2 (z->W, x->H)
+                float dx = g * (ax * hx + bx * hx + ey * hy);
+                float dy = g * (ay * hy);
+                float dz = g * (by * hy + ex * hx);
+                dx = warp_sum(dx); dy = warp_sum(dy); dz = warp_sum(dz);
+                if (lane == 0) {
+                    float* dc = p.d_coords + ((long)n * p.P + base + q) * 3;
+                    dc[0] = dx * p.coord_scale; dc[1] = dy * p.coord_scale; dc[2] = dz * p.coord_scale;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (wgrad) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < HID * C; i += blockDim.x) atomicAdd(p.dW1 + i, aW1[i] * p.w1g);
+        for (int i = threadIdx.x; i < HID; i += blockDim.x) atomicAdd(p.db1 + i, ab1[i] * p.b1g);
+        for (int i = threadIdx.x; i < OUT * HID; i += blockDim.x) atomicAdd(p.dW2 + i, aW2[i] * p.w2g);
+        for (int i = threadIdx.x; i < OUT; i += blockDim.x) atomicAdd(p.db2 + i, ab2[i] * p.b2g);
+    }
+}
+
+int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
+                const float* ray_d, const float* depths, int S, long P, float box_warp, const float* W1, const float* b1,
+                const float* W2, const float* b2, float lr_mul) {
+    B200_REQUIRE(planes && W1 && b1 && W2 && b2, "triplane: null plane/weight pointer");
+    B200_REQUIRE(coords || (ray_o && ray_d && depths && S > 0 && P % S == 0), "triplane: need coords or (ray_o, ray_d, depths, S)");
+    B200_REQUIRE(n > 0 && hp > 0 && wp > 0 && P >= 0 && box_warp != 0.f, "triplane: bad shape");
+    p.planes = planes; p.n = n; p.hp = hp; p.wp = wp; p.coords = coords; p.ray_o = ray_o; p.ray_d = ray_d; p.depths = depths;
+    p.S = S; p.P = P; p.coord_scale = 2.f / box_warp; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+    p.w1g = lr_mul / sqrtf((float)C); p.b1g = lr_mul; p.w2g = lr_mul / sqrtf((float)HID); p.b2g = lr_mul;
+    return 0;
+}
+}  // namespace
+
+// planes: [n][hp][wp][96] fp32.  Either coords [n][P][3], or rays (ray_o/ray_d [n][P/S][3], depths [n][P]).
+// W1 [64][32], b1 [64], W2 [33][64], b2 [33] are the raw decoder parameters (gains lr_mul/sqrt(fan_in) applied here,
+// training/networks_stylegan2.py:111-112).  Outputs rgb [n][P][32], sigma [n][P].
+B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
+                                   const float* ray_d, const float* depths, int S, long P, float box_warp,
+                                   const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
+                                   float* rgb, float* sigma, void* stream) {
+    TriplaneParams p{};
+    if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
+    B200_REQUIRE(rgb && sigma, "triplane_fwd: null output");
+    if (P == 0) return 0;
+    p.rgb = rgb; p.sigma = sigma;
+    const long groups = (P + 127) / 128;
+    dim3 grid((unsigned)(groups < 148 * 8 ? groups : 148 * 8), n);
+    triplane_mlp_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// d_planes [n][hp][wp][96] is ACCUMULATED into (zero it first); d_coords [n][P][3] is written (may be null);
+// dW1/db1/dW2/db2 are ACCUMULATED into (all four null => parameter gradients skipped).
+B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
+                                   const float* ray_d, const float* depths, int S, long P, float box_warp,
+                                   const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
+                                   const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
+                                   float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+    TriplaneParams p{};
+    if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
+    B200_REQUIRE(d_rgb && d_sigma, "triplane_bwd: null incoming gradient");
+    B200_REQUIRE((dW1 && db1 && dW2 && db2) || (!dW1 && !db1 && !dW2 && !db2), "triplane_bwd: pass all four parameter gradients or none");
+    if (P == 0) return 0;
+    p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
+    p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+        attr_set = true;
+    }
+    const long groups = (P + 127) / 128;
+    dim3 grid((unsigned)(groups < 148 * 2 ? groups : 148 * 2), n);
+    triplane_mlp_bwd_kernel<<<grid, 128, BW_SMEM, (cudaStream_t)stream>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,481 @@
+"""Host-side operators of the EG3D hot path: thin autograd wrappers over the C-ABI CUDA library.
+
+Public names mirror the reference's operator layer so that its call sites read the same:
+    bias_act(x, b, dim, act, alpha, gain, clamp)          torch_utils/ops/bias_act.py:54
+    upfirdn2d / upsample2d / setup_filter                  torch_utils/ops/upfirdn2d.py:72,120,315
+    modulated_conv2d-based layers                          training/networks_stylegan2.py:34-91,311-357
+Internally the synthesis stack keeps activations NHWC ([N,H,W,C] fp32): one channel vector per pixel is the
+K-contiguous GEMM operand and the coalescing unit of every elementwise kernel.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+_ACT = {'linear': (1, 0.0, 1.0), 'relu': (2, 0.0, math.sqrt(2)), 'lrelu': (3, 0.2, math.sqrt(2)), 'tanh': (4, 0.0, 1.0),
+        'sigmoid': (5, 0.0, 1.0), 'elu': (6, 0.0, 1.0), 'selu': (7, 0.0, 1.0), 'softplus': (8, 0.0, 1.0),
+        'swish': (9, 0.0, math.sqrt(2))}
+_ACT_REF = {'linear': '', 'relu': 'y', 'lrelu': 'y', 'tanh': 'y', 'sigmoid': 'y', 'elu': 'y', 'selu': 'y', 'softplus': 'y',
+            'swish': 'x'}
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+# bias_act (generic, any layout; reference plugin signature bias_act.cpp:36)
+
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, b, dim, act, alpha, gain, clamp):
+        code = _ACT[act][0]
+        xc = _f32c(x)
+        y = torch.empty_like(xc)
+        step = int(np.prod(xc.shape[dim + 1:])) if xc.ndim > dim + 1 else 1
+        bc = _f32c(b) if b is not None else None
+        call('b200_bias_act', ptr(xc), ptr(bc), None, None, None, ptr(y), 0, xc.numel(), step,
+             xc.shape[dim] if bc is not None else 1, code, alpha, gain, clamp, stream())
+        ctx.cfg = (dim, act, alpha, gain, clamp, step, b is not None)
+        ctx.save_for_backward(xc if _ACT_REF[act] == 'x' else None, bc if _ACT_REF[act] == 'x' else None,
+                              y if _ACT_REF[act] == 'y' or clamp >= 0 else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dim, act, alpha, gain, clamp, step, has_b = ctx.cfg
+        xref, bref, yref = ctx.saved_tensors
+        dyc = _f32c(dy)
+        dx = torch.empty_like(dyc)
+        call('b200_bias_act', ptr(dyc), ptr(bref), ptr(xref), ptr(yref), None, ptr(dx), 1, dyc.numel(), step,
+             dyc.shape[dim] if bref is not None else 1, _ACT[act][0], alpha, gain, clamp, stream())
+        db = dx.sum([i for i in range(dx.ndim) if i != dim]) if has_b else None
+        return dx, db, None, None, None, None, None
+
+
+def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
+    """y = clamp(act(x + b) * gain).  Same argument meaning as the reference op; CUDA only."""
+    if act not in _ACT:
+        raise ValueError(f'unknown activation {act!r}')
+    _, a0, g0 = _ACT[act]
+    alpha = float(alpha if alpha is not None else a0)
+    gain = float(gain if gain is not None else g0)
+    clamp = float(clamp if clamp is not None else -1)
+    if b is not None and (b.ndim != 1 or b.shape[0] != x.shape[dim]):
+        raise ValueError('bias must be a vector matching x.shape[dim]')
+    return _BiasAct.apply(x, b, dim, act, alpha, gain, clamp)
+
+
+# ----------------------------------------------------------------------------------------------
+# upfirdn2d
+
+def setup_filter(f, device=torch.device('cpu'), normalize=True, flip_filter=False, gain=1, separable=None):
+    """Same contract as upfirdn2d.setup_filter (upfirdn2d.py:72-116)."""
+    if f is None:
+        f = 1
+    f = torch.as_tensor(f, dtype=torch.float32)
+    if f.ndim == 0:
+        f = f[None]
+    if separable is None:
+        separable = f.ndim == 1 and f.numel() >= 8
+    if f.ndim == 1 and not separable:
+        f = f.ger(f)
+    if normalize:
+        f = f / f.sum()
+    if flip_filter:
+        f = f.flip(list(range(f.ndim)))
+    f = f * (gain ** (f.ndim / 2))
+    return f.to(device=device)
+
+
+def _filter2d(f, device):
+    if f is None:
+        f = torch.ones([1, 1], dtype=torch.float32)
+    f = f.detach().to(device=device, dtype=torch.float32)
+    if f.ndim == 1:
+        f = f.ger(f)                       # separable filters are applied as their outer product
+    return f.contiguous()
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def _pad4(p):
+    if isinstance(p, int):
+        return p, p, p, p
+    p = [int(v) for v in p]
+    if len(p) == 2:
+        return p[0], p[0], p[1], p[1]
+    return tuple(p)
+
+
+def _upfirdn_nhwc_raw(x, f2, up, down, pad, flip, gain, add=None):
+    """x [N,H,W,C] contiguous fp32 -> [N,OH,OW,C]; no autograd."""
+    n, h, w, c = x.shape
+    (upx, upy), (dx, dy) = up, down
+    px0, px1, py0, py1 = pad
+    fh, fw = f2.shape
+    oh = (h * upy + py0 + py1 - fh + dy) // dy
+    ow = (w * upx + px0 + px1 - fw + dx) // dx
+    y = torch.empty([n, oh, ow, c], device=x.device, dtype=torch.float32)
+    call('b200_upfirdn2d', ptr(x), ptr(f2), ptr(add), ptr(y), n, h, w, c, fh, fw, upx, upy, dx, dy, px0, px1, py0, py1,
+         int(flip), float(gain), stream())
+    return y
+
+
+class _UpfirdnNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, f2, up, down, pad, flip, gain):
+        xc = _f32c(x)
+        ctx.cfg = (up, down, pad, flip, gain, xc.shape)
+        ctx.save_for_backward(f2)
+        return _upfirdn_nhwc_raw(xc, f2, up, down, pad, flip, gain)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (f2,) = ctx.saved_tensors
+        up, down, pad, flip, gain, xs = ctx.cfg
+        n, ih, iw, c = xs
+        oh, ow = dy.shape[1:3]
+        fh, fw = f2.shape
+        px0, px1, py0, py1 = pad
+        # upfirdn2d.py:257-268: the adjoint is the same op with up/down swapped and the filter flipped
+        p = (fw - px0 - 1, iw * up[0] - ow * down[0] + px0 - up[0] + 1, fh - py0 - 1, ih * up[1] - oh * down[1] + py0 - up[1] + 1)
+        dx = _upfirdn_nhwc_raw(_f32c(dy), f2, down, up, p, not flip, gain)
+        return dx, None, None, None, None, None, None
+
+
+def upfirdn2d_nhwc(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
+    f2 = _filter2d(f, x.device)
+    return _UpfirdnNHWC.apply(x, f2, _pair(up), _pair(down), _pad4(padding), bool(flip_filter), float(gain))
+
+
+def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda'):
+    """NCHW front-end with the reference's signature (upfirdn2d.py:120): every (n, c) image is one single-channel map."""
+    n, c, h, w = x.shape
+    y = upfirdn2d_nhwc(x.reshape(n * c, h, w, 1), f, up, down, padding, flip_filter, gain)
+    return y.reshape(n, c, y.shape[1], y.shape[2])
+
+
+def upsample2d(x, f, up=2, padding=0, flip_filter=False, gain=1, impl='cuda'):
+    """upfirdn2d.py:315-350."""
+    upx, upy = _pair(up)
+    px0, px1, py0, py1 = _pad4(padding)
+    fh, fw = (1, 1) if f is None else ((f.shape[0], f.shape[0]) if f.ndim == 1 else (f.shape[0], f.shape[1]))
+    p = [px0 + (fw + upx - 1) // 2, px1 + (fw - upx) // 2, py0 + (fh + upy - 1) // 2, py1 + (fh - upy) // 2]
+    return upfirdn2d(x, f, up=up, padding=p, flip_filter=flip_filter, gain=gain * upx * upy)
+
+
+# ----------------------------------------------------------------------------------------------
+# Modulated convolution layer (SynthesisLayer body) on NHWC activations
+
+def _fir4(device):
+    k = torch.tensor([1.0, 3.0, 3.0, 1.0], dtype=torch.float64)
+    f = torch.outer(k, k)
+    return (f / f.sum()).to(device=device, dtype=torch.float32).contiguous()
+
+
+_FIR_CACHE = {}
+
+
+def fir_filter(device):
+    key = str(device)
+    if key not in _FIR_CACHE:
+        _FIR_CACHE[key] = _fir4(device)
+    return _FIR_CACHE[key]
+
+
+class _ModConvLayer(torch.autograd.Function):
+    """z = clamp(lrelu(modconv(x, W, styles) [-> FIR if up=2] + noise*strength + bias) * act_gain, +-clamp)
+
+    x [N,H,W,Cin] NHWC, weight [Cout,Cin,3,3], styles [N,Cin], noise [H',W'] or [N,1,H',W'] or None,
+    strength 0-dim tensor.  networks_stylegan2.py:311-330 + :34-91 (fused_modconv path).
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, styles, bias, noise, strength, up, act_gain, clamp):
+        x = _f32c(x)
+        n, h, w, cin = x.shape
+        cout, _, k, _ = weight.shape
+        taps = k * k
+        dev = x.device
+        W = _f32c(weight)
+        s = _f32c(styles)
+        wmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
+        dcoef = torch.empty([n, cout], device=dev, dtype=torch.float32)
+        call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), ptr(dcoef), n, cout, cin, taps, 1, stream())
+        if up == 1:
+            oh, ow = h, w
+            y = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
+            call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cout, k, 1, stream())
+        else:
+            oh, ow = 2 * h, 2 * w
+            zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
+            call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(zt), n, h, w, cin, cout, k, 2, stream())
+            y = _upfirdn_nhwc_raw(zt, fir_filter(dev), (1, 1), (1, 1), (1, 1, 1, 1), False, 4.0)
+        nz = None
+        nbs = 0
+        if noise is not None:
+            nz = _f32c(noise)
+            nbs = oh * ow if nz.ndim == 4 else 0
+        b = _f32c(bias)
+        st = _f32c(strength) if noise is not None else None
+        z = torch.empty_like(y)
+        call('b200_layer_act_fwd', ptr(y), ptr(z), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
+             float(act_gain), float(clamp if clamp is not None else -1), stream())
+        ctx.cfg = (up, float(act_gain), float(clamp if clamp is not None else -1), k, nbs, noise is not None and noise.ndim)
+        ctx.save_for_backward(x, W, s, wmod, dcoef, z, nz, st)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, W, s, wmod, dcoef, z, nz, st = ctx.saved_tensors
+        up, act_gain, clamp, k, nbs, noise_ndim = ctx.cfg
+        n, h, w, cin = x.shape
+        cout = W.shape[0]
+        taps = k * k
+        dev = x.device
+        oh, ow = z.shape[1:3]
+        need = ctx.needs_input_grad
+        dzc = _f32c(dz)
+        dy = torch.empty_like(dzc)
+        dbias = torch.zeros([cout], device=dev, dtype=torch.float32)
+        has_noise = nz is not None
+        dstr = torch.zeros([], device=dev, dtype=torch.float32) if has_noise else None
+        dnoise = torch.zeros_like(nz) if (has_noise and need[4]) else None
+        call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr), ptr(dnoise),
+             n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
+        if up == 2:
+            # adjoint of the 4x4 FIR (pad 1,1,1,1) back onto the (2h+1)x(2w+1) transposed-conv grid
+            dy = _upfirdn_nhwc_raw(dy, fir_filter(dev), (1, 1), (1, 1), (2, 2, 2, 2), True, 4.0)
+        dx = None
+        if need[0]:
+            dx = torch.empty_like(x)
+            call('b200_conv_dgrad', ptr(dy), ptr(wmod), ptr(dx), n, h, w, cin, cout, k, up, stream())
+        dW = ds = None
+        if need[1] or need[2]:
+            dwmod = torch.empty_like(wmod)
+            call('b200_conv_wgrad', ptr(x), ptr(dy), ptr(dwmod), n, h, w, cin, cout, k, up, stream())
+            dW = torch.empty_like(W)
+            ds = torch.empty_like(s)
+            call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin,
+                 taps, 1, stream())
+        return dx, dW, ds, dbias, dnoise, dstr, None, None, None
+
+
+def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp):
+    return _ModConvLayer.apply(x, weight, styles, bias, noise, strength, up, act_gain, clamp)
+
+
+class _ToRGB(torch.autograd.Function):
+    """img = [upsample2d(img_prev)] + clamp(conv1x1(x, W*styles) + bias, +-clamp)     (networks_stylegan2.py:353-357, 451-457)
+
+    x [N,H,W,Cin], weight [Cimg,Cin,1,1], styles [N,Cin] (already scaled by 1/sqrt(Cin)), img_prev [N,H/2,W/2,Cimg] or None.
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, styles, bias, img_prev, clamp):
+        x = _f32c(x)
+        n, h, w, cin = x.shape
+        cimg = weight.shape[0]
+        dev = x.device
+        W = _f32c(weight)
+        s = _f32c(styles)
+        wmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
+        call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), None, n, cimg, cin, 1, 0, stream())
+        y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
+        call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
+        b = _f32c(bias)
+        cl = float(clamp if clamp is not None else -1)
+        call('b200_bias_act', ptr(y), ptr(b), None, None, None, ptr(y), 0, y.numel(), 1, cimg, 1, 0.0, 1.0, cl, stream())
+        if img_prev is not None:
+            img = _upfirdn_nhwc_raw(_f32c(img_prev), fir_filter(dev), (2, 2), (1, 1), (2, 1, 2, 1), False, 4.0, add=y)
+        else:
+            img = y
+        ctx.cfg = (cl, img_prev is not None)
+        ctx.save_for_backward(x, W, s, wmod, y)
+        return img
+
+    @staticmethod
+    def backward(ctx, dimg):
+        x, W, s, wmod, y = ctx.saved_tensors
+        cl, has_prev = ctx.cfg
+        n, h, w, cin = x.shape
+        cimg = W.shape[0]
+        dev = x.device
+        need = ctx.needs_input_grad
+        dimg = _f32c(dimg)
+        dy = torch.empty_like(dimg)
+        # gradient of bias+clamp uses the saved clamped output (bias_act.cu:143-145)
+        call('b200_bias_act', ptr(dimg), None, None, ptr(y), None, ptr(dy), 1, dy.numel(), 1, 1, 1, 0.0, 1.0, cl, stream())
+        dbias = dy.sum([0, 1, 2])
+        dx = None
+        if need[0]:
+            dx = torch.empty_like(x)
+            call('b200_conv_dgrad', ptr(dy), ptr(wmod), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
+        dW = ds = None
+        if need[1] or need[2]:
+            dwmod = torch.empty_like(wmod)
+            call('b200_conv_wgrad', ptr(x), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream())
+            dW = torch.empty_like(W)
+            ds = torch.empty_like(s)
+            call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), None, ptr(dwmod), ptr(dW), ptr(ds), n, cimg, cin, 1, 0, stream())
+        dprev = None
+        if has_prev and need[4]:
+            dprev = _upfirdn_nhwc_raw(dimg, fir_filter(dev), (1, 1), (2, 2), (1, 2, 1, 2), True, 4.0)
+        return dx, dW, ds, dbias, dprev, None
+
+
+def torgb_layer(x, weight, styles, bias, img_prev, clamp):
+    return _ToRGB.apply(x, weight, styles, bias, img_prev, clamp)
+
+
+# ----------------------------------------------------------------------------------------------
+# Renderer: fused tri-plane sampling + decoder, per-ray hierarchical sampling and compositing
+
+def _decoder_params(decoder):
+    fc0, fc1 = decoder.net[0], decoder.net[2]
+    return fc0.weight, fc0.bias, fc1.weight, fc1.bias, float(fc0.lr_multiplier)
+
+
+class _RunModel(torch.autograd.Function):
+    """rgb, sigma = decoder(sample_from_planes(planes, coords))   (renderer.py:197-203 without density noise)
+
+    planes_nhwc [N,H,W,96]; coords [N,P,3].
+    """
+
+    @staticmethod
+    def forward(ctx, planes, coords, W1, b1, W2, b2, lr_mul, box_warp):
+        pl = _f32c(planes)
+        co = _f32c(coords)
+        n, hp, wp, _ = pl.shape
+        P = co.shape[1]
+        rgb = torch.empty([n, P, 32], device=pl.device, dtype=torch.float32)
+        sigma = torch.empty([n, P, 1], device=pl.device, dtype=torch.float32)
+        w = [_f32c(t) for t in (W1, b1, W2, b2)]
+        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, P, float(box_warp), *map(ptr, w),
+             float(lr_mul), ptr(rgb), ptr(sigma), stream())
+        ctx.cfg = (float(lr_mul), float(box_warp))
+        ctx.save_for_backward(pl, co, *w)
+        return rgb, sigma
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_sigma):
+        pl, co, W1, b1, W2, b2 = ctx.saved_tensors
+        lr_mul, box_warp = ctx.cfg
+        n, hp, wp, _ = pl.shape
+        P = co.shape[1]
+        need = ctx.needs_input_grad
+        d_planes = torch.zeros_like(pl) if need[0] else None
+        d_coords = torch.empty_like(co) if need[1] else None
+        wg = any(need[2:6])
+        dws = [torch.zeros_like(t) for t in (W1, b1, W2, b2)] if wg else [None] * 4
+        call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, P, box_warp, ptr(W1), ptr(b1), ptr(W2),
+             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(d_planes), ptr(d_coords), *map(ptr, dws), stream())
+        return (d_planes, d_coords, *dws, None, None)
+
+
+def run_model_nhwc(planes_nhwc, decoder, coords, box_warp):
+    W1, b1, W2, b2, lr_mul = _decoder_params(decoder)
+    return _RunModel.apply(planes_nhwc, coords, W1, b1, W2, b2, lr_mul, box_warp)
+
+
+class _Render(torch.autograd.Function):
+    """ImportanceRenderer.forward as one autograd node (renderer.py:143-195, numeric ray_start / ray_end).
+
+    planes [N,H,W,96]; ray_o, ray_d [N,M,3]; t_base [S] (linspace(ray_start, ray_end, S));
+    u_strat [N,M,S,1], u_imp [N*M,S_imp] are the two uniform draws of the reference (renderer.py:245,292).
+    Returns feat [N,M,32], depth [N,M,1], wsum [N,M,1].
+    """
+
+    @staticmethod
+    def forward(ctx, planes, ray_o, ray_d, W1, b1, W2, b2, lr_mul, box_warp, t_base, delta, u_strat, u_imp, white_back,
+                density_noise):
+        pl = _f32c(planes)
+        ro, rd = _f32c(ray_o), _f32c(ray_d)
+        dev = pl.device
+        n, hp, wp, _ = pl.shape
+        M = ro.shape[1]
+        S = t_base.numel()
+        S2 = 0 if u_imp is None else u_imp.shape[1]
+        w = [_f32c(t) for t in (W1, b1, W2, b2)]
+        st = stream()
+        t_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
+        call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), st)
+        rgb_c = torch.empty([n, M, S, 32], device=dev, dtype=torch.float32)
+        sig_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
+        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_c), S, M * S, float(box_warp),
+             *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), st)
+        if density_noise > 0:
+            sig_c += torch.randn_like(sig_c) * density_noise
+        minmax = torch.tensor([-1, 0], device=dev, dtype=torch.int32)
+        call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(minmax), st)
+        t_f = rgb_f = sig_f = None
+        if S2 > 0:
+            t_f = torch.empty([n, M, S2], device=dev, dtype=torch.float32)
+            call('b200_ray_importance', ptr(t_c), ptr(sig_c), ptr(_f32c(u_imp)), ptr(t_f), n * M, S, S2, st)
+            rgb_f = torch.empty([n, M, S2, 32], device=dev, dtype=torch.float32)
+            sig_f = torch.empty([n, M, S2], device=dev, dtype=torch.float32)
+            call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_f), S2, M * S2, float(box_warp),
+                 *map(ptr, w), float(lr_mul), ptr(rgb_f), ptr(sig_f), st)
+            if density_noise > 0:
+                sig_f += torch.randn_like(sig_f) * density_noise
+            call('b200_depth_minmax', ptr(t_f), t_f.numel(), ptr(minmax), st)
+        feat = torch.empty([n, M, 32], device=dev, dtype=torch.float32)
+        depth = torch.empty([n, M, 1], device=dev, dtype=torch.float32)
+        wsum = torch.empty([n, M, 1], device=dev, dtype=torch.float32)
+        call('b200_ray_composite_fwd', ptr(t_c), ptr(sig_c), ptr(rgb_c), S, ptr(t_f), ptr(sig_f), ptr(rgb_f), S2, ptr(minmax),
+             int(bool(white_back)), n * M, ptr(feat), ptr(depth), ptr(wsum), st)
+        ctx.cfg = (float(lr_mul), float(box_warp), int(bool(white_back)), S, S2)
+        ctx.save_for_backward(pl, ro, rd, *w, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax)
+        return feat, depth, wsum
+
+    @staticmethod
+    def backward(ctx, d_feat, d_depth, d_wsum):
+        pl, ro, rd, W1, b1, W2, b2, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax = ctx.saved_tensors
+        lr_mul, box_warp, white_back, S, S2 = ctx.cfg
+        n, hp, wp, _ = pl.shape
+        M = ro.shape[1]
+        dev = pl.device
+        st = stream()
+        need = ctx.needs_input_grad
+        d_rgb_c = torch.empty_like(rgb_c)
+        d_sig_c = torch.empty_like(sig_c)
+        d_rgb_f = torch.empty_like(rgb_f) if S2 > 0 else None
+        d_sig_f = torch.empty_like(sig_f) if S2 > 0 else None
+        call('b200_ray_composite_bwd', ptr(t_c), ptr(sig_c), ptr(rgb_c), S, ptr(t_f), ptr(sig_f), ptr(rgb_f), S2, ptr(minmax),
+             white_back, n * M, ptr(_f32c(d_feat)), ptr(_f32c(d_depth)), ptr(_f32c(d_wsum)), ptr(d_rgb_c), ptr(d_sig_c),
+             ptr(d_rgb_f), ptr(d_sig_f), st)
+        d_planes = torch.zeros_like(pl) if need[0] else None
+        want_rays = need[1] or need[2]
+        wg = any(need[3:7])
+        dws = [torch.zeros_like(t) for t in (W1, b1, W2, b2)] if wg else [None] * 4
+        d_ro = d_rd = None
+        if want_rays:
+            d_ro = torch.zeros_like(ro)
+            d_rd = torch.zeros_like(rd)
+        for t, d_rgb, d_sig, s in ((t_c, d_rgb_c, d_sig_c, S), (t_f, d_rgb_f, d_sig_f, S2)):
+            if s == 0:
+                continue
+            d_pts = torch.empty([n, M, s, 3], device=dev, dtype=torch.float32) if want_rays else None
+            call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t), s, M * s, box_warp, ptr(W1),
+                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(d_planes), ptr(d_pts), *map(ptr, dws), st)
+            if want_rays:                      # point = o + t*d  (renderer.py:161,178)
+                d_ro += d_pts.sum(2)
+                d_rd += (d_pts * t.unsqueeze(-1)).sum(2)
+        return (d_planes, d_ro, d_rd, *dws, None, None, None, None, None, None, None, None)
+
+
+def render(planes_nhwc, decoder, ray_o, ray_d, box_warp, t_base, delta, u_strat, u_imp, white_back=False, density_noise=0.0):
+    W1, b1, W2, b2, lr_mul = _decoder_params(decoder)
+    return _Render.apply(planes_nhwc, ray_o, ray_d, W1, b1, W2, b2, lr_mul, box_warp, t_base, delta, u_strat, u_imp,
+                         white_back, density_noise)
+
+
+def library_info():
+    lib = _lib.load()
+    return {'path': _lib.LIB_PATH, 'version': lib.b200_version()}

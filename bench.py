@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""PTI steps/sec (fwd+bwd) of the EG3D tri-plane generator at 512 px out / 128 px neural render / 48+48 depth samples.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One step = G.synthesis(ws, c, noise_mode='const', force_fp32=True) -> stand-in PTI loss (MSE@512 + MSE@128 + depth TV,
+base_coach.py:101-126,294-305; LPIPS weights are not available offline) -> backward to ALL generator parameters ->
+Adam step (lr 3e-4, base_coach.py:96-99).  Random-init generator of the ffhqrebalanced512-128 architecture, synthetic
+latent / camera / targets.  Multi-GPU: one independent image per rank (no data-path collective), NCCL only for the
+final max-over-ranks time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, '3dgan-inversion_b200'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+
+import torch  # noqa: E402
+
+METRIC = 'PTI steps/sec (fwd+bwd) 512px out, 128px neural render, 48+48 depth samples'
+WORKLOAD = 'ffhqrebalanced512-128 EG3D (random-init), single-image PTI step, R=128, 48+48 samples, batch 1 per GPU'
+R, S, S_IMP = 128, 48, 48
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith('Active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def conv_flops_per_step():
+    """Algorithmic conv FLOPs of one PTI step: fwd + dgrad + wgrad = 3 x 2 x 71.387 GMAC."""
+    return 3 * 2 * 71.387e9
+
+
+def make_problem(seed, device):
+    import synth_params as sp
+    import b200eg3d
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=rk, **sp.G_KWARGS_FULL).eval()
+    named = dict(list(G.named_parameters()) + list(G.named_buffers()))
+    sp.fill_params_(named, 7 + seed)
+    G = G.to(device).float().requires_grad_(True)
+    G.neural_rendering_resolution = R
+    ws = sp.latent_ws(1 + seed)
+    c = sp.camera(0.3, -0.2)
+    t512, t_raw = sp.targets(2 + seed, R)
+    return G, ws, c, t512.contiguous(), t_raw.contiguous()
+
+
+def pti_loss(out, t512, t_raw):
+    import eg3d_oracle as oracle       # loss definition only (caller-side code, shared with the parity tests)
+    return oracle.pti_loss(out, t512, t_raw)
+
+
+def run_b200(args):
+    import b200eg3d
+    from b200eg3d import _lib
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    b200eg3d.ops.library_info()
+    G, ws_h, c_h, t512_h, traw_h = make_problem(100 + rank if world > 1 else 0, dev)
+    params = [p for n, p in G.named_parameters() if '.mapping.' not in n]
+    opt = torch.optim.Adam(params, lr=3e-4, fused=True)
+    host = [t.pin_memory() for t in (ws_h, c_h, t512_h, traw_h)]
+    resident = [t.to(dev) for t in host]
+
+    def step(inputs):
+        ws, c, t512, traw = inputs
+        out = G.synthesis(ws, c, noise_mode='const', force_fp32=True)
+        loss = pti_loss(out, t512, traw)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, e2e):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            if e2e:
+                loss = step([t.to(dev, non_blocking=True) for t in host])
+                loss.item()                                   # device -> host read of the step's result
+            else:
+                step(resident)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.LAUNCHES = 0
+    ms = timed(args.steps, e2e=False)
+    launches = _lib.LAUNCHES
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(args.steps, e2e=True)
+
+    # per-kernel device time of the same step, instrumented with CUDA events on the launching stream (separate steps)
+    roof = None
+    cpu = None
+    if rank == 0:
+        _lib.PROFILE = {}
+        for _ in range(2):
+            step(resident)
+        torch.cuda.synchronize()
+        prof = {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _lib.PROFILE.items()}
+        _lib.PROFILE = None
+        pk, how = peaks()
+        conv_ms = sum(prof[k][0] for k in prof if k.startswith('b200_conv_')) / 2
+        tot_ms = sum(v[0] for v in prof.values()) / 2
+        n_conv = sum(prof[k][1] for k in prof if k.startswith('b200_conv_')) / 2
+        achieved = conv_flops_per_step() / (conv_ms * 1e-3) / 1e12
+        peak = pk['bf16_tflops_sustained']
+        roof = {'kernel': 'modulated-conv stack (b200_conv_fwd/dgrad/wgrad)', 'bound': 'tensor', 'achieved': round(achieved, 2),
+                'peak': peak, 'unit': 'TFLOP/s', 'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': how,
+                'launches_per_step': n_conv, 'ms_per_step_in_kernel': round(conv_ms, 3), 'share_of_kernel_time': round(conv_ms / tot_ms, 3),
+                'per_call_ms': {k: round(v[0] / 2, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(1, 1)
+    if rank == 0:
+        n_in = sum(t.numel() * t.element_size() for t in host)
+        line = {
+            'metric': METRIC, 'value': round(world * args.steps / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': world,
+            'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
+            'config': {'workload': WORKLOAD, 'parallelism': f'independent images x{world}',
+                       'l2': 'per-step working set (>1 GB of activations and gradients) exceeds the 126 MB L2; no explicit flush',
+                       'loss': 'mse512 + mse128 + depth TV (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4 (fused)'},
+            'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
+                    'd2h_bytes_per_step': 4},
+            'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def cpu_baseline(warm, steps):
+    """The oracle port (CPU restatement of the reference path) timed on this host's cores: full PTI steps."""
+    import eg3d_oracle as oracle
+    import synth_params as sp
+    from golden_util import param_shapes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
+    P = {k: torch.zeros(v) for k, v in param_shapes(sp.G_KWARGS_FULL).items()}
+    sp.fill_params_(P, 7)
+    for v in P.values():
+        v.requires_grad_(True)
+    opt = torch.optim.Adam(list(P.values()), lr=3e-4)
+    ws, c = sp.latent_ws(1), sp.camera(0.3, -0.2)
+    t512, traw = sp.targets(2, R)
+    times = []
+    for i in range(warm + steps):
+        t0 = time.perf_counter()
+        u1, u2 = oracle.draw_depth_noise(11 + i, 1, R * R, S, S_IMP)
+        out = oracle.synthesis(P, ws, c, rk, R, u1, u2)
+        loss = oracle.pti_loss(out, t512, traw)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    t = sum(times[warm:]) / steps
+    return {'value': round(1.0 / t, 4), 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+            'sample': f'{steps} full PTI step(s) after {warm} warm-up, same workload, torch CPU fp32 oracle (oracle/eg3d_oracle.py)',
+            'seconds_per_step': round(t, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    first = cpu_baseline(0, 1)
+    per = first['seconds_per_step']
+    budget = 150.0
+    k = max(1, min(args.steps, int(budget / per) - 1))
+    w = 1
+    res = cpu_baseline(0, k) if k > 0 else first
+    line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'steps/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
+            'steps': k, 'warmup': w, 'ms_per_step': round(1e3 / res['value'], 1), 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
+            'config': {'workload': WORKLOAD, 'note': 'reference CPU path restated by the oracle port, all host threads; steps bounded to ~150 s'},
+            'cpu_baseline': dict(res, value=res['value']),
+            'e2e': {'value': res['value'], 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    a = ap.parse_args()
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,100 @@
+"""GPU end-to-end parity: TriPlaneGenerator.synthesis() on the B200 path against fixtures recorded from the REAL
+reference (tests/golden/*.npz, made by oracle/make_goldens.py) -- forward outputs at the north-star tolerance
+(max-abs 1e-3 on image / image_raw / image_depth) and gradients of the PTI stand-in loss (relative L2 1e-2)."""
+import numpy as np
+import pytest
+import torch
+
+import eg3d_oracle as oracle
+import synth_params as sp
+from golden_util import load_case
+
+pytestmark = pytest.mark.gpu
+
+TOL_OUT = 1e-3        # BASELINE.json north_star: "within 1e-3 max-abs fp32"
+TOL_GRAD = 1e-2       # relative L2 of gradients
+
+
+def build_G(case, requires_grad=False):
+    import b200eg3d
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=case.rk, **case.gk).eval()
+    named = dict(list(G.named_parameters()) + list(G.named_buffers()))
+    sp.fill_params_(named, case.param_seed)
+    G = G.cuda().requires_grad_(requires_grad)
+    G.neural_rendering_resolution = case.R
+    G.renderer.fixed_noise = (case.u_strat, case.u_imp)
+    return G
+
+
+def rel_l2(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize('name', ['tiny_r64_s16', 'tiny_r32_s8_n2_white', 'tiny_r64_s12_noimp', 'full_r64_s16', 'full_r128_s48',
+                                  'full_r256_s96'])
+def test_forward_matches_reference(name, golden_dir):
+    case = load_case(golden_dir, name)
+    G = build_G(case)
+    with torch.no_grad():
+        out = G.synthesis(case.ws.cuda(), case.c.cuda(), noise_mode='const', force_fp32=True, cache_backbone=True)
+    fx = case.fx
+    d_raw = np.abs(out['image_raw'].cpu().numpy() - fx['image_raw']).max()
+    d_dep = np.abs(out['image_depth'].cpu().numpy() - fx['image_depth']).max()
+    d_img = np.abs(out['image'][..., ::4, ::4].cpu().numpy() - fx['image_sub4']).max()
+    d_pl = np.abs(G._last_planes[..., ::8, ::8].cpu().numpy() - fx['planes_sub8']).max()
+    print(f'{name}: max-abs image {d_img:.2e} raw {d_raw:.2e} depth {d_dep:.2e} planes {d_pl:.2e}')
+    assert out['image'].shape == (case.N, 3, 512, 512) and out['image_depth'].shape == (case.N, 1, case.R, case.R)
+    assert d_raw < TOL_OUT and d_dep < TOL_OUT and d_img < TOL_OUT
+    mom = fx['image_mom']
+    assert abs(out['image'].double().sum().item() - mom[0]) < 1e-3 * max(1.0, abs(mom[0]))
+
+
+@pytest.mark.parametrize('name', ['tiny_r64_s16', 'tiny_r32_s8_n2_white', 'full_r128_s48'])
+def test_gradients_match_reference(name, golden_dir):
+    case = load_case(golden_dir, name)
+    G = build_G(case, requires_grad=True)
+    ws = case.ws.cuda().requires_grad_(True)
+    c = case.c.cuda().requires_grad_(True)
+    out = G.synthesis(ws, c, noise_mode='const', force_fp32=True)
+    loss = oracle.pti_loss(out, case.t512.cuda(), case.t_raw.cuda())
+    fx = case.fx
+    assert abs(loss.item() - fx['loss'][0]) < 1e-3 * max(1.0, abs(fx['loss'][0]))
+    loss.backward()
+    e_ws, e_c = rel_l2(ws.grad.cpu().numpy(), fx['grad_ws']), rel_l2(c.grad.cpu().numpy(), fx['grad_c'])
+    print(f'{name}: rel-L2 grad_ws {e_ws:.2e} grad_c {e_c:.2e}')
+    assert e_ws < TOL_GRAD and e_c < TOL_GRAD
+    params = dict(G.named_parameters())
+    worst = 0.0
+    for i, n in enumerate(fx['grad_names']):
+        g = params[str(n)].grad
+        assert g is not None, n
+        ssq = g.double().square().sum().item()
+        ref = fx['grad_mom'][i][1]
+        assert abs(ssq - ref) <= 2 * TOL_GRAD * max(ref, 1e-20), (str(n), ssq, ref)
+        head = g.reshape(-1)[:16].cpu().numpy()
+        ref_head = fx['grad_head'][i][:head.size]
+        scale = max(np.sqrt(ref / max(g.numel(), 1)), 1e-20)
+        worst = max(worst, float(np.abs(head - ref_head).max() / scale))
+    print(f'{name}: worst head deviation / rms = {worst:.2e}')
+    assert worst < 0.05
+
+
+def test_noise_modes_and_cache(golden_dir):
+    case = load_case(golden_dir, 'tiny_r64_s16')
+    G = build_G(case)
+    ws, c = case.ws.cuda(), case.c.cuda()
+    with torch.no_grad():
+        a = G.synthesis(ws, c, noise_mode='const', cache_backbone=True)
+        b = G.synthesis(ws * 0, c, noise_mode='const', use_cached_backbone=True)        # planes come from the cache
+        assert torch.equal(a['image_raw'], b['image_raw'])
+        torch.manual_seed(0)
+        r1 = G.synthesis(ws, c, noise_mode='random')
+        torch.manual_seed(0)
+        r2 = G.synthesis(ws, c, noise_mode='random')
+        assert torch.equal(r1['image'], r2['image'])
+        n0 = G.synthesis(ws, c, noise_mode='none')
+        assert not torch.equal(n0['image'], a['image'])
+    G2 = __import__('copy').deepcopy(G)                                              # w_projector.py:61
+    with torch.no_grad():
+        assert torch.equal(G2.synthesis(ws, c, noise_mode='const')['image'], a['image'])

@@ -1,0 +1,253 @@
+"""GPU parity of the individual CUDA operators (called through the C-ABI) against the CPU oracle on seeded inputs."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import eg3d_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def b2():
+    import b200eg3d
+    assert torch.cuda.is_available()
+    b200eg3d.ops.library_info()          # raises if the .so is missing
+    return b200eg3d
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def maxdiff(a, b):
+    return (a.detach().cpu().double() - b.detach().cpu().double()).abs().max().item()
+
+
+def relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ---------------------------------------------------------------------------------------------- modconv layer
+
+@pytest.mark.parametrize('cin,cout,res,up', [(8, 16, 8, 1), (16, 8, 8, 2), (64, 64, 16, 1), (64, 32, 16, 2), (12, 20, 5, 1),
+                                             (20, 12, 5, 2), (128, 128, 32, 1), (256, 128, 16, 2)])
+def test_modconv_layer_fwd_bwd(b2, cin, cout, res, up):
+    n = 2
+    g = gen(cin * 1000 + cout + up)
+    x = torch.randn(n, cin, res, res, generator=g)
+    W = torch.randn(cout, cin, 3, 3, generator=g)
+    s = 1 + 0.3 * torch.randn(n, cin, generator=g)
+    b = 0.2 * torch.randn(cout, generator=g)
+    ores = res * up
+    noise = torch.randn(ores, ores, generator=g)
+    strength = torch.tensor(0.13)
+    dz = torch.randn(n, cout, ores, ores, generator=g)
+    gain, clamp = 1.0, 2.5       # small clamp so that the clamp branch is exercised
+
+    leaves = [t.clone().requires_grad_(True) for t in (x, W, s, b, noise, strength)]
+    xr, Wr, sr, br, nr, str_ = leaves
+    y = oracle.modulated_conv2d(xr, Wr, sr, noise=nr * str_, up=up, f=oracle.fir_1331())
+    z_ref = oracle.bias_act(y, br, act='lrelu', gain=math.sqrt(2) * gain, clamp=clamp * gain)
+    z_ref.backward(dz)
+
+    dev = 'cuda'
+    cl = [t.detach().to(dev).requires_grad_(True) for t in (nhwc(x), W, s, b, noise, strength)]
+    z = b2.ops.modconv_layer(cl[0], cl[1], cl[2], cl[3], cl[4], cl[5], up, math.sqrt(2) * gain, clamp * gain)
+    z.backward(nhwc(dz).to(dev))
+    assert maxdiff(nchw(z), z_ref) < 2e-4 * max(1.0, z_ref.abs().max().item())
+    names = ['dx', 'dW', 'dstyles', 'dbias', 'dnoise', 'dstrength']
+    refs = [nhwc(xr.grad), Wr.grad, sr.grad, br.grad, nr.grad, str_.grad]
+    for nm, a, r in zip(names, cl, refs):
+        assert relerr(a.grad, r) < 2e-4, (nm, relerr(a.grad, r))
+
+
+@pytest.mark.parametrize('cin,cimg,res,prev', [(16, 96, 8, True), (64, 3, 16, True), (32, 96, 4, False), (10, 3, 6, True)])
+def test_torgb_fwd_bwd(b2, cin, cimg, res, prev):
+    n = 2
+    g = gen(cin + cimg)
+    x = torch.randn(n, cin, res, res, generator=g)
+    W = torch.randn(cimg, cin, 1, 1, generator=g)
+    s = (1 + 0.3 * torch.randn(n, cin, generator=g)) / math.sqrt(cin)
+    b = 0.2 * torch.randn(cimg, generator=g)
+    ip = torch.randn(n, cimg, res // 2, res // 2, generator=g) if prev else None
+    dimg = torch.randn(n, cimg, res, res, generator=g)
+    clamp = 1.5
+    leaves = [t.clone().requires_grad_(True) for t in (x, W, s, b)]
+    ipr = ip.clone().requires_grad_(True) if prev else None
+    y = oracle.bias_act(oracle.modulated_conv2d(leaves[0], leaves[1], leaves[2], demodulate=False), leaves[3], clamp=clamp)
+    img_ref = oracle.upsample2d(ipr, oracle.fir_1331()) + y if prev else y
+    img_ref.backward(dimg)
+
+    dev = 'cuda'
+    cl = [t.detach().to(dev).requires_grad_(True) for t in (nhwc(x), W, s, b)]
+    ipc = nhwc(ip).to(dev).requires_grad_(True) if prev else None
+    img = b2.ops.torgb_layer(cl[0], cl[1], cl[2], cl[3], ipc, clamp)
+    img.backward(nhwc(dimg).to(dev))
+    assert maxdiff(nchw(img), img_ref) < 1e-4
+    for nm, a, r in zip(['dx', 'dW', 'ds', 'db'], cl, [nhwc(leaves[0].grad), leaves[1].grad, leaves[2].grad, leaves[3].grad]):
+        assert relerr(a.grad, r) < 2e-4, (nm, relerr(a.grad, r))
+    if prev:
+        assert relerr(ipc.grad, nhwc(ipr.grad)) < 2e-4
+
+
+# ---------------------------------------------------------------------------------------------- bias_act / upfirdn2d
+
+@pytest.mark.parametrize('act', ['linear', 'relu', 'lrelu', 'tanh', 'sigmoid', 'elu', 'selu', 'softplus', 'swish'])
+@pytest.mark.parametrize('clamp', [None, 0.7])
+def test_bias_act_all_activations(b2, act, clamp):
+    g = gen(3)
+    x = torch.randn(2, 5, 7, 3, generator=g)
+    b = torch.randn(5, generator=g)
+    dy = torch.randn(2, 5, 7, 3, generator=g)
+    fn = {'linear': lambda t: t, 'relu': torch.relu, 'lrelu': lambda t: F.leaky_relu(t, 0.2), 'tanh': torch.tanh,
+          'sigmoid': torch.sigmoid, 'elu': F.elu, 'selu': F.selu, 'softplus': F.softplus, 'swish': lambda t: torch.sigmoid(t) * t}[act]
+    gain = {'relu': math.sqrt(2), 'lrelu': math.sqrt(2), 'swish': math.sqrt(2)}.get(act, 1.0)
+    xr, br = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y_ref = fn(xr + br.reshape(1, -1, 1, 1)) * gain
+    if clamp is not None:
+        y_ref = y_ref.clamp(-clamp, clamp)
+    y_ref.backward(dy)
+    xc, bc = x.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = b2.ops.bias_act(xc, bc, dim=1, act=act, clamp=clamp)
+    y.backward(dy.cuda())
+    assert maxdiff(y, y_ref) < 2e-6
+    assert maxdiff(xc.grad, xr.grad) < 5e-6
+    assert maxdiff(bc.grad, br.grad) < 5e-5
+
+
+@pytest.mark.parametrize('up,down,pad,flip', [(1, 1, (1, 1, 1, 1), False), (2, 1, (2, 1, 2, 1), False), (1, 2, (1, 1, 1, 1), True),
+                                              (2, 2, (3, 0, 1, 2), False), (1, 1, (-1, 2, 0, -1), False), (3, 1, (2, 2, 2, 2), False)])
+def test_upfirdn2d_matches_oracle(b2, up, down, pad, flip):
+    g = gen(up * 10 + down)
+    x = torch.randn(2, 3, 9, 11, generator=g)
+    f = torch.rand(4, 4, generator=g)
+    f = f / f.sum()
+    dy = None
+    xr = x.clone().requires_grad_(True)
+    fr = f.flip([0, 1]) if flip else f
+    y_ref = oracle.upfirdn2d(xr, fr, up=up, down=down, pad=pad, gain=1.7)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    xc = x.cuda().requires_grad_(True)
+    y = b2.ops.upfirdn2d(xc, f.cuda(), up=up, down=down, padding=list(pad), flip_filter=flip, gain=1.7)
+    assert y.shape == y_ref.shape
+    y.backward(dy.cuda())
+    assert maxdiff(y, y_ref) < 1e-5
+    assert maxdiff(xc.grad, xr.grad) < 1e-5
+
+
+def test_upsample2d_and_setup_filter(b2):
+    f = b2.ops.setup_filter([1, 3, 3, 1])
+    assert maxdiff(f, oracle.fir_1331()) < 1e-7
+    x = torch.randn(1, 4, 6, 6, generator=gen(0))
+    assert maxdiff(b2.ops.upsample2d(x.cuda(), f.cuda()), oracle.upsample2d(x, oracle.fir_1331())) < 1e-5
+
+
+def test_empty_and_error_paths(b2):
+    from b200eg3d import _lib
+    with pytest.raises(RuntimeError):
+        b2.ops.bias_act(torch.zeros(2, 3), None)                 # CPU tensor: no CPU path exists
+    with pytest.raises(RuntimeError):
+        _lib.call('b200_conv_fwd', None, None, None, 1, 4, 4, 8, 8, 5, 1, None)     # bad kernel size
+    y = b2.ops.bias_act(torch.zeros(0, 3, device='cuda'), torch.zeros(3, device='cuda'))
+    assert y.numel() == 0
+
+
+# ---------------------------------------------------------------------------------------------- renderer pieces
+
+def _decoder(b2, seed):
+    g = gen(seed)
+    dec = b2.OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32})
+    P = {}
+    with torch.no_grad():
+        for k, v in dec.named_parameters():
+            v.copy_(torch.randn(v.shape, generator=g) * (0.3 if k.endswith('bias') else 1.0))
+            P['decoder.' + k] = v.detach().clone()
+    return dec, P
+
+
+@pytest.mark.parametrize('npts', [1, 31, 32, 1000])
+def test_run_model_fwd_bwd(b2, npts):
+    n, res = 2, 16
+    g = gen(npts)
+    planes = torch.randn(n, 3, 32, res, res, generator=g)
+    coords = (torch.rand(n, npts, 3, generator=g) - 0.5) * 1.3       # some points fall outside the box (zero padding)
+    dec, P = _decoder(b2, 5)
+    d_rgb = torch.randn(n, npts, 32, generator=g)
+    d_sig = torch.randn(n, npts, 1, generator=g)
+    rk = {'box_warp': 1.2}
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    pr, cr = planes.clone().requires_grad_(True), coords.clone().requires_grad_(True)
+    rgb_ref, sig_ref = oracle.run_model(Pr, pr, cr, rk)
+    (rgb_ref * d_rgb).sum().add((sig_ref * d_sig).sum()).backward()
+
+    dec = dec.cuda()
+    for p in dec.parameters():
+        p.requires_grad_(True)
+    pl = planes.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96).contiguous().cuda().requires_grad_(True)
+    cc = coords.cuda().requires_grad_(True)
+    out = b2.ImportanceRenderer().run_model(pl, dec, cc, None, rk)
+    (out['rgb'] * d_rgb.cuda()).sum().add((out['sigma'] * d_sig.cuda()).sum()).backward()
+    assert maxdiff(out['rgb'], rgb_ref) < 2e-5
+    assert maxdiff(out['sigma'], sig_ref) < 1e-4
+    dpl_ref = pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)
+    assert relerr(pl.grad, dpl_ref) < 1e-4
+    assert relerr(cc.grad, cr.grad) < 1e-3
+    for k, v in dec.named_parameters():
+        assert relerr(v.grad, Pr['decoder.' + k].grad) < 1e-4, k
+
+
+@pytest.mark.parametrize('S,S2,white', [(12, 12, False), (16, 0, False), (8, 8, True), (48, 48, False)])
+def test_render_fwd_bwd(b2, S, S2, white):
+    n, res, R = 1, 32, 12
+    M = R * R
+    g = gen(S * 7 + S2)
+    planes = torch.randn(n, 3, 32, res, res, generator=g)
+    dec, P = _decoder(b2, 9)
+    import synth_params as sp
+    c = sp.camera(0.2, -0.1, n=n)
+    ro, rd = oracle.ray_sampler(c[:, :16].reshape(-1, 4, 4), c[:, 16:].reshape(-1, 3, 3), R)
+    ro, rd = ro.contiguous(), rd.contiguous()
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S2, white_back=white)
+    u1 = torch.rand(n, M, S, 1, generator=g)
+    u2 = torch.rand(n * M, max(S2, 1), generator=g)
+    dfeat = torch.randn(n, M, 32, generator=g)
+    ddepth = torch.randn(n, M, 1, generator=g)
+    dws = torch.randn(n, M, 1, generator=g)
+
+    Pr = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    pr = planes.clone().requires_grad_(True)
+    ror, rdr = ro.clone().requires_grad_(True), rd.clone().requires_grad_(True)
+    f_ref, d_ref, w_ref = oracle.render(Pr, pr, ror, rdr, rk, u1, u2)
+    ((f_ref * dfeat).sum() + (d_ref * ddepth).sum() + (w_ref * dws).sum()).backward()
+
+    dec = dec.cuda()
+    for p in dec.parameters():
+        p.requires_grad_(True)
+    ren = b2.ImportanceRenderer()
+    ren.fixed_noise = (u1, u2)
+    pl = planes.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96).contiguous().cuda().requires_grad_(True)
+    roc, rdc = ro.cuda().requires_grad_(True), rd.cuda().requires_grad_(True)
+    f, d, w = ren(pl, dec, roc, rdc, rk)
+    ((f * dfeat.cuda()).sum() + (d * ddepth.cuda()).sum() + (w * dws.cuda()).sum()).backward()
+    assert maxdiff(f, f_ref) < 5e-5
+    assert maxdiff(d, d_ref) < 5e-5
+    assert maxdiff(w, w_ref) < 5e-5
+    assert relerr(pl.grad, pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)) < 2e-3
+    assert relerr(roc.grad, ror.grad) < 5e-3
+    assert relerr(rdc.grad, rdr.grad) < 5e-3
+    for k, v in dec.named_parameters():
+        assert relerr(v.grad, Pr['decoder.' + k].grad) < 2e-3, k
