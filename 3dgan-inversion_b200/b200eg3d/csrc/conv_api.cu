@@ -18,7 +18,7 @@ B200_API int b200_conv_fwd(const float* x, const float* wmod, float* y, int n, i
     const int taps = ksize * ksize;
     ConvPixParams p{};
     p.A = x; p.a_bs = (long)h * w * cin;
-    p.B = wmod; p.b_ts = (long)cout * cin; p.b_ks = 1; p.b_ns = cin; p.b_bs = (long)taps * cout * cin; p.b_mode = 1;
+    p.B = wmod; p.b_ts = (long)cout * cin; p.b_ks = 1; p.b_ns = cin; p.b_bs = (long)taps * cout * cin; p.b_mode = (cin % 4 == 0) ? 1 : 0;
     p.N = cout; p.C = y; p.ldc = cout; p.accumulate = 0;
     p.g.Hs = h; p.g.Ws = w; p.g.Ca = cin; p.g.sy = p.g.sx = 1;
     if (up == 1) {

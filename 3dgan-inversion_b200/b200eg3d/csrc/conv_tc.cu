@@ -1,0 +1,316 @@
+// tcgen05 / TMA implicit-GEMM convolution for sm_100a ("tensor-core path" of the modulated-conv stack).
+//
+// Operands are bf16 "split-float" pairs: x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  A forward convolution
+// issues three MMAs per k-step (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM), which restores ~16 mantissa bits
+// -- enough for the 1e-3 max-abs parity bar against the fp32 reference at half the smem bytes of a
+// 3xTF32 scheme.  Backward GEMMs may run single-pass (hi*hi).
+//
+// Pixel-GEMM kernel (forward, dgrad, 1x1, transposed-conv classes): C[pixel, n] = sum_{tap, c} A[src(pixel,tap), c] * B[tap, c, n]
+//   A tile  : 128 pixels (th x tw patch) x 64 channels, one TMA box {64, tw, th, 1} of the NHWC tensor at the tap's
+//             shifted coordinate (TMA zero-fill == conv zero padding; elementStrides give the stride-2 gather)
+//   B tile  : K-major  [BN rows][64 k]  (forward: wmod[tap][cout][cin])        one box {64, BN}
+//             MN-major [64 k rows][64 n] x BN/64 (dgrad: wmod[tap][cout][cin] read as [k = cout][n = cin])
+//   D       : 128 lanes x BN fp32 columns in TMEM, drained by 4 epilogue warps with tcgen05.ld
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one thread), warps 2-5 = epilogue.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <cuda_bf16.h>
+
+using namespace tc;
+
+namespace {
+
+constexpr int TILE_M = 128, TILE_K = 64, MAX_BN = 128, STAGES = 3;
+constexpr int A_BYTES = TILE_M * TILE_K * 2;              // 16 KB
+constexpr int B_BYTES = MAX_BN * TILE_K * 2;              // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // hi + lo of both operands
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcPixParams {
+    CUtensorMap tmA[2];          // hi, lo : 4-D {C, W, H, N}
+    CUtensorMap tmB[2];          // hi, lo : 2-D {inner, rows}
+    int th, tw, tiles_x;
+    int Hi, Wi;
+    int kchunks, ntaps, npass;
+    int dy[9], dx[9], wt[9];
+    int s;                       // source pixel = iteration pixel * s + (dy, dx)
+    int b_rows_per_tap;          // K-major B: total N; MN-major B: total K per tap
+    int b_taps;                  // tap slices per sample in B
+    int BN, N;
+    float* C; long ldc, c_bs; int Wo, osy, osx, ooy, oox;
+};
+
+template <bool B_MN>
+__global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_constant__ TcPixParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t bars = base + STAGES * STAGE_BYTES;                 // full[3], empty[3], accum, then tmem slot
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    const int x0 = (tile % p.tiles_x) * p.tw, y0 = (tile / p.tiles_x) * p.th;
+    const int n0 = blockIdx.y * p.BN;
+    const int b = blockIdx.z;
+    const int nk = p.ntaps * p.kchunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
+        if (p.npass == 3) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmB[1]); }
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(A_BYTES + p.BN * TILE_K * 2) * (p.npass == 3 ? 2u : 1u);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(empty(s), ph ^ 1);
+                mbar_arrive_expect_tx(full(s), bytes);
+                const int t = it / p.kchunks, c0 = (it % p.kchunks) * TILE_K;
+                const uint32_t st = base + s * STAGE_BYTES;
+                const int ax = x0 * p.s + p.dx[t], ay = y0 * p.s + p.dy[t];
+                const int nh = p.npass == 3 ? 2 : 1;
+                for (int h = 0; h < nh; ++h) {
+                    tma_load_4d(st + h * A_BYTES, &p.tmA[h], full(s), c0, ax, ay, b);
+                    const uint32_t bdst = st + 2 * A_BYTES + h * B_BYTES;
+                    if (!B_MN) {
+                        tma_load_2d(bdst, &p.tmB[h], full(s), c0, (b * p.b_taps + p.wt[t]) * p.b_rows_per_tap + n0);
+                    } else {
+                        const int krow = (b * p.b_taps + p.wt[t]) * p.b_rows_per_tap + c0;
+                        for (int j = 0; j < p.BN / 64; ++j) tma_load_2d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), n0 + j * 64, krow);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16(TILE_M, p.BN, 0, B_MN ? 1 : 0);
+            for (int it = 0; it < nk; ++it) {
+                const int s = it % STAGES, ph = (it / STAGES) & 1;
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t st = base + s * STAGE_BYTES;
+                const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < TILE_K / 16; ++k) {
+                    const uint32_t ao = k * 32, bo = B_MN ? k * 2048 : k * 32;
+                    const uint32_t blbo = B_MN ? TILE_K * 128 : 0;
+                    const uint64_t dah = smem_desc(a_hi + ao, 0, 1024), dbh = smem_desc(b_hi + bo, blbo, 1024);
+                    umma_bf16(tmem, dah, dbh, idesc, (it | k) != 0);
+                    if (p.npass == 3) {
+                        const uint64_t dal = smem_desc(a_lo + ao, 0, 1024), dbl = smem_desc(b_lo + bo, blbo, 1024);
+                        umma_bf16(tmem, dah, dbl, idesc, 1);
+                        umma_bf16(tmem, dal, dbh, idesc, 1);
+                    }
+                }
+                umma_commit(empty(s));
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int m = q * 32 + lane;
+        const int iy = y0 + m / p.tw, ix = x0 + m % p.tw;
+        const bool valid = iy < p.Hi && ix < p.Wi;
+        const long opix = (long)(iy * p.osy + p.ooy) * p.Wo + (ix * p.osx + p.oox);
+        float* crow = p.C + (long)b * p.c_bs + opix * p.ldc + n0;
+        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+__global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, long n4) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2bfloat16_rn(f[j]);
+            l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+        }
+        hi[i] = *reinterpret_cast<uint2*>(h);
+        if (lo) lo[i] = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)f;
+    }
+    return fn;
+}
+
+// bf16 NHWC tensor {C, W, H, N}; box {64, tw*s, th*s, 1} with traversal stride s on W and H
+int make_map_nhwc(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int tw, int th, int s) {
+    EncodeTiledFn f = encode_fn();
+    B200_REQUIRE(f, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dim[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t str[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(tw * s), (cuuint32_t)(th * s), 1};
+    cuuint32_t es[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+    CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for an NHWC activation map");
+    return 0;
+}
+
+// bf16 row-major matrix {inner, rows}; box {64, box_rows}
+int make_map_2d(CUtensorMap* m, const void* ptr, long rows, int inner, int box_rows) {
+    EncodeTiledFn f = encode_fn();
+    B200_REQUIRE(f, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dim[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)inner * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = f(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dim, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for a weight map");
+    return 0;
+}
+
+void pick_tile(int Hi, int Wi, int& th, int& tw) {
+    long best = -1;
+    for (int w = 128; w >= 1; w >>= 1) {
+        const int h = 128 / w;
+        const long tiles = (long)((Wi + w - 1) / w) * ((Hi + h - 1) / h);
+        if (best < 0 || tiles < best) { best = tiles; tw = w; th = h; }
+    }
+}
+
+int pick_bn(int n) {
+    if (n % 128 == 0) return 128;
+    if (n % 96 == 0) return 96;
+    if (n % 64 == 0) return 64;
+    if (n % 32 == 0) return 32;
+    return 0;
+}
+
+template <bool B_MN>
+int launch_pix(const TcPixParams& p, int batch, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(conv_tc_pix_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    const int tiles_y = (p.Hi + p.th - 1) / p.th;
+    dim3 grid(p.tiles_x * tiles_y, p.N / p.BN, batch);
+    conv_tc_pix_kernel<B_MN><<<grid, 192, SMEM_BYTES, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+// 1 when the tcgen05 path handles this shape; kind: 0 forward, 1 dgrad, 2 wgrad
+B200_API int b200_conv_tc_supported(int kind, int h, int w, int cin, int cout, int ksize, int up) {
+    if (!(ksize == 1 || ksize == 3) || !(up == 1 || (up == 2 && ksize == 3))) return 0;
+    if (kind == 0) return cin % 64 == 0 && pick_bn(cout) > 0;
+    if (kind == 1) return cout % 64 == 0 && cin % 64 == 0;       // K = cout chunks of 64, N = cin in MN-major blocks of 64
+    return 0;
+}
+
+B200_API int b200_split_bf16(const float* x, void* hi, void* lo, long count, void* stream) {
+    B200_REQUIRE(count % 4 == 0, "split_bf16: element count must be a multiple of 4");
+    if (count == 0) return 0;
+    const long n4 = count / 4;
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n4);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// Forward conv on split-bf16 operands.  x_* [n][h][w][cin] bf16, w_* [n][taps][cout][cin] bf16, y fp32 NHWC
+// (up == 2: y is the (2h+1)x(2w+1) transposed-conv grid, as in b200_conv_fwd).  npass: 1 (hi*hi) or 3.
+B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int n, int h,
+                              int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+    B200_REQUIRE(b200_conv_tc_supported(0, h, w, cin, cout, ksize, up), "conv_fwd_tc: unsupported shape");
+    B200_REQUIRE(npass == 1 || (npass == 3 && x_lo && w_lo), "conv_fwd_tc: npass must be 1, or 3 with lo operands");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int taps = ksize * ksize;
+    TcPixParams p{};
+    p.kchunks = cin / 64; p.npass = npass; p.s = 1; p.b_rows_per_tap = cout; p.b_taps = taps;
+    p.BN = pick_bn(cout); p.N = cout; p.C = y; p.ldc = cout;
+    for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
+        if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, p.BN)) return e;
+    if (up == 1) {
+        p.Hi = h; p.Wi = w; pick_tile(h, w, p.th, p.tw); p.tiles_x = (w + p.tw - 1) / p.tw;
+        p.ntaps = taps; p.c_bs = (long)h * w * cout; p.Wo = w; p.osy = p.osx = 1; p.ooy = p.oox = 0;
+        for (int t = 0; t < taps; ++t) { p.dy[t] = t / ksize - ksize / 2; p.dx[t] = t % ksize - ksize / 2; p.wt[t] = t; }
+        for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
+            if (int e = make_map_nhwc(&p.tmA[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
+        return launch_pix<false>(p, n, st);
+    }
+    p.c_bs = (long)(2 * h + 1) * (2 * w + 1) * cout; p.Wo = 2 * w + 1; p.osy = p.osx = 2;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {
+            p.Hi = h + 1 - py; p.Wi = w + 1 - px; pick_tile(p.Hi, p.Wi, p.th, p.tw); p.tiles_x = (p.Wi + p.tw - 1) / p.tw;
+            p.ooy = py; p.oox = px;
+            int t = 0;
+            for (int kh = py; kh < 3; kh += 2)
+                for (int kw = px; kw < 3; kw += 2) { p.dy[t] = -(kh >> 1); p.dx[t] = -(kw >> 1); p.wt[t] = kh * 3 + kw; ++t; }
+            p.ntaps = t;
+            for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
+                if (int e = make_map_nhwc(&p.tmA[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
+            if (int e = launch_pix<false>(p, n, st)) return e;
+        }
+    return 0;
+}
+
+// dgrad on split-bf16 operands.  dy_* bf16 ([h][w][cout], or the (2h+1)x(2w+1) grid when up == 2), w_* as above, dx fp32.
+B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int n,
+                                int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+    B200_REQUIRE(b200_conv_tc_supported(1, h, w, cin, cout, ksize, up), "conv_dgrad_tc: unsupported shape");
+    B200_REQUIRE(npass == 1 || (npass == 3 && dy_lo && w_lo), "conv_dgrad_tc: npass must be 1, or 3 with lo operands");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int taps = ksize * ksize;
+    const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
+    TcPixParams p{};
+    p.kchunks = cout / 64; p.npass = npass; p.s = up; p.b_rows_per_tap = cout; p.b_taps = taps;
+    p.BN = cin % 128 == 0 ? 128 : 64; p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin;
+    p.Hi = h; p.Wi = w; pick_tile(h, w, p.th, p.tw); p.tiles_x = (w + p.tw - 1) / p.tw;
+    p.ntaps = taps; p.Wo = w; p.osy = p.osx = 1; p.ooy = p.oox = 0;
+    for (int t = 0; t < taps; ++t) {
+        const int kh = t / ksize, kw = t % ksize;
+        p.dy[t] = up == 1 ? ksize / 2 - kh : kh; p.dx[t] = up == 1 ? ksize / 2 - kw : kw; p.wt[t] = t;
+    }
+    for (int i = 0; i < (npass == 3 ? 2 : 1); ++i) {
+        if (int e = make_map_nhwc(&p.tmA[i], i ? dy_lo : dy_hi, n, hs, ws, cout, p.tw, p.th, up)) return e;
+        if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, 64)) return e;
+    }
+    return launch_pix<true>(p, n, st);
+}
