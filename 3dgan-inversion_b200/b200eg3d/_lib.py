@@ -17,6 +17,10 @@ SIGNATURES = {
     'b200_conv_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_dgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_wgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_split_bf16': [_P, _P, _P, _L, _P],
+    'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_wgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_modconv_weight_prep': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200_modconv_weight_prep_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200_bias_act': [_P, _P, _P, _P, _P, _P, _I, _L, _L, _I, _I, _F, _F, _F, _P],
@@ -51,6 +55,8 @@ def load():
     lib.b200_last_error.argtypes = []
     lib.b200_version.restype = ctypes.c_int
     lib.b200_version.argtypes = []
+    lib.b200_conv_tc_supported.restype = ctypes.c_int
+    lib.b200_conv_tc_supported.argtypes = [_I] * 7
     _lib = lib
     return lib
 

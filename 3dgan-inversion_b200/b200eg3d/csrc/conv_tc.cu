@@ -130,13 +130,147 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         const bool valid = iy < p.Hi && ix < p.Wi;
         const long opix = (long)(iy * p.osy + p.ooy) * p.Wo + (ix * p.osx + p.oox);
         float* crow = p.C + (long)b * p.c_bs + opix * p.ldc + n0;
+        const bool vec = (p.N & 3) == 0;
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
             float v[32];
             tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (valid) {
+                if (vec && n0 + c0 + 32 <= p.N) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j < p.N) crow[c0 + j] = v[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight-gradient kernel: D[tap][m = cout][n = cin] += sum_{pixels} A[pixA(pixel, tap)][m] * B[pixB(pixel, tap)][n]
+// Both operands are MN-major (the reduction index is the pixel, channels are contiguous): a k-block is a th x tw patch
+// of 64 pixels, loaded as {64 ch, tw, th} boxes = [64 k rows][64 ch] swizzle-128B atoms.  One CTA owns one tap, one
+// 128 x BN output tile and one slice of the pixel range (split-K); partial tiles are reduced with red.global.add.v4.f32.
+struct TcWgradParams {
+    CUtensorMap tmA[2];          // hi, lo of the M-side tensor (dy / dz): 4-D {C, W, H, N}
+    CUtensorMap tmB[2];          // hi, lo of the N-side tensor (x)
+    int th, tw, tiles_x, ntiles; // pixel patches (64 pixels each) over the iteration grid
+    int sA, sB;                  // pixel strides of the two gathers
+    int dAy[9], dAx[9], dBy[9], dBx[9];
+    int ntaps, ksplit, npass;
+    int BN, Cm, Cn;
+    float* C; long c_bs;         // C[b][tap][Cm][Cn]
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - raw);
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TILE_M, n0 = blockIdx.y * p.BN;
+    int z = blockIdx.z;
+    const int ks = z % p.ksplit; z /= p.ksplit;
+    const int t = z % p.ntaps;
+    const int b = z / p.ntaps;
+    const int per = (p.ntiles + p.ksplit - 1) / p.ksplit;
+    const int kb0 = ks * per, kb1 = min(p.ntiles, kb0 + per);
+    const int nk = max(kb1 - kb0, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (nk > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const int nh = p.npass == 3 ? 2 : 1;
+                const uint32_t bytes = (uint32_t)(A_BYTES + p.BN * TILE_K * 2) * nh;
+                for (int it = 0; it < nk; ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full(s), bytes);
+                    const int tile = kb0 + it;
+                    const int x0 = (tile % p.tiles_x) * p.tw, y0 = (tile / p.tiles_x) * p.th;
+                    const uint32_t st = base + s * STAGE_BYTES;
+                    for (int h = 0; h < nh; ++h) {
+                        const uint32_t adst = st + h * A_BYTES, bdst = st + 2 * A_BYTES + h * B_BYTES;
+                        for (int j = 0; j < 2; ++j)
+                            tma_load_4d(adst + j * (TILE_K * 128), &p.tmA[h], full(s), m0 + j * 64, x0 * p.sA + p.dAx[t], y0 * p.sA + p.dAy[t], b);
+                        for (int j = 0; j < p.BN / 64; ++j)
+                            tma_load_4d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), n0 + j * 64, x0 * p.sB + p.dBx[t], y0 * p.sB + p.dBy[t], b);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = instr_desc_bf16(TILE_M, p.BN, 1, 1);
+                for (int it = 0; it < nk; ++it) {
+                    const int s = it % STAGES, ph = (it / STAGES) & 1;
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = base + s * STAGE_BYTES;
+                    const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TILE_K / 16; ++k) {
+                        const uint32_t o = k * 2048, lbo = TILE_K * 128;
+                        const uint64_t dah = smem_desc(a_hi + o, lbo, 1024), dbh = smem_desc(b_hi + o, lbo, 1024);
+                        umma_bf16(tmem, dah, dbh, idesc, (it | k) != 0);
+                        if (p.npass == 3) {
+                            const uint64_t dal = smem_desc(a_lo + o, lbo, 1024), dbl = smem_desc(b_lo + o, lbo, 1024);
+                            umma_bf16(tmem, dah, dbl, idesc, 1);
+                            umma_bf16(tmem, dal, dbh, idesc, 1);
+                        }
+                    }
+                    umma_commit(empty(s));
+                }
+                umma_commit(accum_bar);
+            }
+        } else {
+            const int q = warp & 3;
+            mbar_wait(accum_bar, 0);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            float* crow = p.C + (long)b * p.c_bs + ((long)t * p.Cm + m) * p.Cn + n0;
+            const bool vec = (p.Cn & 3) == 0;
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (m < p.Cm) {
+                    if (vec && n0 + c0 + 32 <= p.Cn) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) red_add_v4(crow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + c0 + j < p.Cn) atomicAdd(crow + c0 + j, v[j]);
+                    }
+                }
             }
         }
     }
@@ -212,12 +346,11 @@ void pick_tile(int Hi, int Wi, int& th, int& tw) {
     }
 }
 
-int pick_bn(int n) {
-    if (n % 128 == 0) return 128;
-    if (n % 96 == 0) return 96;
-    if (n % 64 == 0) return 64;
-    if (n % 32 == 0) return 32;
-    return 0;
+int pick_bn(int n) {           // N tile of the K-major-B kernels (a multiple of 32, MMA N)
+    if (n <= 32) return 32;
+    if (n <= 64) return 64;
+    if (n <= 96) return 96;
+    return 128;
 }
 
 template <bool B_MN>
@@ -228,7 +361,7 @@ int launch_pix(const TcPixParams& p, int batch, cudaStream_t st) {
         attr = true;
     }
     const int tiles_y = (p.Hi + p.th - 1) / p.th;
-    dim3 grid(p.tiles_x * tiles_y, p.N / p.BN, batch);
+    dim3 grid(p.tiles_x * tiles_y, (p.N + p.BN - 1) / p.BN, batch);
     conv_tc_pix_kernel<B_MN><<<grid, 192, SMEM_BYTES, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
@@ -239,8 +372,11 @@ int launch_pix(const TcPixParams& p, int batch, cudaStream_t st) {
 // 1 when the tcgen05 path handles this shape; kind: 0 forward, 1 dgrad, 2 wgrad
 B200_API int b200_conv_tc_supported(int kind, int h, int w, int cin, int cout, int ksize, int up) {
     if (!(ksize == 1 || ksize == 3) || !(up == 1 || (up == 2 && ksize == 3))) return 0;
-    if (kind == 0) return cin % 64 == 0 && pick_bn(cout) > 0;
-    if (kind == 1) return cout % 64 == 0 && cin % 64 == 0;       // K = cout chunks of 64, N = cin in MN-major blocks of 64
+    // TMA needs 16-byte global strides: channel counts must be multiples of 8 (bf16).  Ragged K / N edges are
+    // handled by TMA zero-fill and by column masking in the epilogue.
+    if (kind == 0) return cin % 8 == 0;
+    if (kind == 1) return cout % 8 == 0 && cin % 8 == 0;
+    if (kind == 2) return cout % 8 == 0 && cin % 8 == 0;
     return 0;
 }
 
@@ -263,7 +399,7 @@ B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_
     cudaStream_t st = (cudaStream_t)stream;
     const int taps = ksize * ksize;
     TcPixParams p{};
-    p.kchunks = cin / 64; p.npass = npass; p.s = 1; p.b_rows_per_tap = cout; p.b_taps = taps;
+    p.kchunks = (cin + 63) / 64; p.npass = npass; p.s = 1; p.b_rows_per_tap = cout; p.b_taps = taps;
     p.BN = pick_bn(cout); p.N = cout; p.C = y; p.ldc = cout;
     for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
         if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, p.BN)) return e;
@@ -300,8 +436,8 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
     const int taps = ksize * ksize;
     const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
     TcPixParams p{};
-    p.kchunks = cout / 64; p.npass = npass; p.s = up; p.b_rows_per_tap = cout; p.b_taps = taps;
-    p.BN = cin % 128 == 0 ? 128 : 64; p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin;
+    p.kchunks = (cout + 63) / 64; p.npass = npass; p.s = up; p.b_rows_per_tap = cout; p.b_taps = taps;
+    p.BN = cin > 64 ? 128 : 64; p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin;
     p.Hi = h; p.Wi = w; pick_tile(h, w, p.th, p.tw); p.tiles_x = (w + p.tw - 1) / p.tw;
     p.ntaps = taps; p.Wo = w; p.osy = p.osx = 1; p.ooy = p.oox = 0;
     for (int t = 0; t < taps; ++t) {
@@ -313,4 +449,47 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
         if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, 64)) return e;
     }
     return launch_pix<true>(p, n, st);
+}
+
+// wgrad on bf16 operands: dwmod[n][taps][cout][cin] (fp32, overwritten) = sum over pixels of dy (x) x.
+// x_* [n][h][w][cin], dy_* [n][h][w][cout] (up == 2: the (2h+1)x(2w+1) transposed-conv grid).
+B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod, int n,
+                                int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+    B200_REQUIRE(b200_conv_tc_supported(2, h, w, cin, cout, ksize, up), "conv_wgrad_tc: unsupported shape");
+    B200_REQUIRE(npass == 1 || (npass == 3 && x_lo && dy_lo), "conv_wgrad_tc: npass must be 1, or 3 with lo operands");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int taps = ksize * ksize;
+    const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
+    TcWgradParams p{};
+    p.npass = npass; p.ntaps = taps; p.Cm = cout; p.Cn = cin; p.BN = cin > 64 ? 128 : 64;
+    p.C = dwmod; p.c_bs = (long)taps * cout * cin; p.sA = up; p.sB = 1;
+    // 64-pixel patches over the h x w iteration grid
+    { long best = -1; for (int tw = 64; tw >= 1; tw >>= 1) { const int th = 64 / tw; const long tl = (long)((w + tw - 1) / tw) * ((h + th - 1) / th);
+        if (best < 0 || tl < best) { best = tl; p.tw = tw; p.th = th; } } }
+    p.tiles_x = (w + p.tw - 1) / p.tw; p.ntiles = p.tiles_x * ((h + p.th - 1) / p.th);
+    for (int t = 0; t < taps; ++t) {
+        const int kh = t / ksize, kw = t % ksize;
+        p.dAy[t] = up == 1 ? 0 : kh; p.dAx[t] = up == 1 ? 0 : kw;
+        p.dBy[t] = up == 1 ? kh - ksize / 2 : 0; p.dBx[t] = up == 1 ? kw - ksize / 2 : 0;
+    }
+    for (int i = 0; i < (npass == 3 ? 2 : 1); ++i) {
+        if (int e = make_map_nhwc(&p.tmA[i], i ? dy_lo : dy_hi, n, hs, ws, cout, p.tw, p.th, up)) return e;
+        if (int e = make_map_nhwc(&p.tmB[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
+    }
+    const int mt = (cout + TILE_M - 1) / TILE_M, nt = (cin + p.BN - 1) / p.BN;
+    const int base_ctas = mt * nt * taps * n;
+    int ksplit = (296 + base_ctas - 1) / base_ctas;
+    if (ksplit > p.ntiles) ksplit = p.ntiles;
+    if (ksplit < 1) ksplit = 1;
+    p.ksplit = ksplit;
+    B200_CUDA(cudaMemsetAsync(dwmod, 0, sizeof(float) * (size_t)n * taps * cout * cin, st));
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr = true;
+    }
+    dim3 grid(mt, nt, n * taps * ksplit);
+    conv_tc_wgrad_kernel<<<grid, 192, SMEM_BYTES, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
 }

@@ -188,7 +188,7 @@ constexpr int BW_ACCPAD = (BW_ACC + 3) / 4 * 4;
 constexpr int BW_WARP = 32 * SA + 32 * SH + 32 * SO;                 // per-warp staging
 constexpr int BW_SMEM = (BW_WPAD + BW_ACCPAD + 4 * BW_WARP) * 4;
 
-__global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p) {
+__global__ void __launch_bounds__(128, 2) triplane_mlp_bwd_kernel(TriplaneParams p) {
     extern __shared__ __align__(16) float smem[];
     float* W1s = smem;                       // [64][32]
     float* W2s = W1s + HID * C;              // [33][64]
@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p)
     float* acc = smem + BW_WPAD;             // dW1 | db1 | dW2 | db2
     float* aW1 = acc; float* ab1 = aW1 + HID * C; float* aW2 = ab1 + HID; float* ab2 = aW2 + OUT * HID;
     const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* sA = smem + BW_WPAD + BW_ACCPAD + wid * BW_WARP;   // [32][SA] features f, later d_f
+    float* sA = smem + BW_WPAD + BW_ACCPAD + wid * BW_WARP;   // [32][SA] features f
     float* sH = sA + 32 * SA;                                 // [32][SH] hidden h, later d_a
-    float* sO = sH + 32 * SH;                                 // [32][SO] d_rgb|d_sigma in, d_out
+    float* sO = sH + 32 * SH;                                 // [32][SO] d_rgb|d_sigma -> d_out -> d_f
     const bool wgrad = p.dW1 != nullptr;
     load_weights(p, W1s, b1s, W2s, b2s);
     for (int i = threadIdx.x; i < BW_ACC; i += blockDim.x) acc[i] = 0.f;
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p)
         const int cnt = (int)min((long)32, p.P - base);
         float cx, cy, cz;
         point_coords(p, n, pi, cx, cy, cz);
-        // 1. features and incoming gradients
+        // ---- 1. features (lane == channel) and incoming gradients, transposed through shared memory
         gather_features(p, pl, cx, cy, cz, sA, lane);
         {
             const float* g = p.d_rgb + ((long)n * p.P + base) * C;
@@ -221,28 +221,27 @@ __global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p)
             sO[lane * SO] = valid ? p.d_sigma[(long)n * p.P + pi] : 0.f;
         }
         __syncwarp();
-        float h[HID];
+        // ---- 2. forward recompute (lane == point): h -> sH, d_out -> sO (in place)
         {
-            float f[C];
+            float h[HID];
+            {
+                float f[C];
 #pragma unroll
-            for (int c = 0; c < C; ++c) f[c] = sA[lane * SA + c];
-            mlp_hidden(f, W1s, b1s, h);
-        }
-        // 2. d_out (k = 0: sigma, linear; k >= 1: rgb = sigmoid(o)*1.002 - 0.001)
-        float dout[OUT];
-        dout[0] = sO[lane * SO];
+                for (int c = 0; c < C; ++c) f[c] = sA[lane * SA + c];
+                mlp_hidden(f, W1s, b1s, h);
+            }
 #pragma unroll
-        for (int k = 1; k < OUT; ++k) {
-            const float s = sigmoid_f(mlp_out(h, W2s, b2s, k));
-            dout[k] = sO[lane * SO + k] * 1.002f * s * (1.f - s);
+            for (int j = 0; j < HID; j += 4)
+                *reinterpret_cast<float4*>(&sH[lane * SH + j]) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+#pragma unroll
+            for (int k = 1; k < OUT; ++k) {
+                const float sg = sigmoid_f(mlp_out(h, W2s, b2s, k));       // rgb = sigmoid(o)*1.002 - 0.001
+                sO[lane * SO + k] *= 1.002f * sg * (1.f - sg);
+            }
         }
+        __syncwarp();
+        // ---- 3. dW2[k][j] += sum_q d_out[q][k] * h[q][j]   (lane owns j = lane, lane + 32), db2
         if (wgrad) {
-#pragma unroll
-            for (int k = 0; k < OUT; ++k) sO[lane * SO + k] = dout[k];
-#pragma unroll
-            for (int j = 0; j < HID; ++j) sH[lane * SH + j] = h[j];
-            __syncwarp();
-            // dW2[k][j] += sum_q dout[q][k] * h[q][j]   (lane owns j = lane, lane+32)
             float a0[OUT], a1[OUT];
 #pragma unroll
             for (int k = 0; k < OUT; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
@@ -264,35 +263,55 @@ __global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p)
                 atomicAdd(&aW2[k * HID + lane], a0[k]);
                 atomicAdd(&aW2[k * HID + 32 + lane], a1[k]);
             }
-            // db2[k] += sum_q dout[q][k]
-            {
-                float s = 0.f, s32 = 0.f;
-                for (int q = 0; q < 32; ++q) { s += sO[q * SO + lane]; if (lane == 0) s32 += sO[q * SO + 32]; }
-                atomicAdd(&ab2[lane], s);
-                if (lane == 0) atomicAdd(&ab2[32], s32);
-            }
+            float sb = 0.f, sb32 = 0.f;
+            for (int q = 0; q < 32; ++q) { sb += sO[q * SO + lane]; sb32 += sO[q * SO + 32]; }
+            atomicAdd(&ab2[lane], sb);
+            if (lane == 0) atomicAdd(&ab2[32], sb32);
             __syncwarp();
         }
-        // 3. d_a = (W2^T d_out) * softplus'(a),  softplus'(a) = 1 - exp(-h)
-        float da[HID];
+        // ---- 4. d_a = (W2^T d_out) * softplus'(a) with softplus'(a) = 1 - exp(-h);  d_f = W1^T d_a
+        {
+            float da[HID];
 #pragma unroll
-        for (int j = 0; j < HID; ++j) da[j] = 0.f;
+            for (int j = 0; j < HID; ++j) da[j] = 0.f;
 #pragma unroll
-        for (int k = 0; k < OUT; ++k) {
+            for (int k = 0; k < OUT; ++k) {
+                const float d = sO[lane * SO + k];
+#pragma unroll
+                for (int j = 0; j < HID; j += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(&W2s[k * HID + j]);
+                    da[j] = fmaf(d, w.x, da[j]); da[j + 1] = fmaf(d, w.y, da[j + 1]);
+                    da[j + 2] = fmaf(d, w.z, da[j + 2]); da[j + 3] = fmaf(d, w.w, da[j + 3]);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < HID; j += 4) {
-                const float4 w = *reinterpret_cast<const float4*>(&W2s[k * HID + j]);
-                da[j] = fmaf(dout[k], w.x, da[j]); da[j + 1] = fmaf(dout[k], w.y, da[j + 1]);
-                da[j + 2] = fmaf(dout[k], w.z, da[j + 2]); da[j + 3] = fmaf(dout[k], w.w, da[j + 3]);
+                const float4 hv = *reinterpret_cast<const float4*>(&sH[lane * SH + j]);
+                da[j] *= 1.f - __expf(-hv.x); da[j + 1] *= 1.f - __expf(-hv.y);
+                da[j + 2] *= 1.f - __expf(-hv.z); da[j + 3] *= 1.f - __expf(-hv.w);
+                *reinterpret_cast<float4*>(&sH[lane * SH + j]) = make_float4(da[j], da[j + 1], da[j + 2], da[j + 3]);
             }
+            float df[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) df[c] = 0.f;
+#pragma unroll
+            for (int j = 0; j < HID; ++j) {
+#pragma unroll
+                for (int c = 0; c < C; c += 4) {
+                    const float4 w = *reinterpret_cast<const float4*>(&W1s[j * C + c]);
+                    df[c] = fmaf(da[j], w.x, df[c]); df[c + 1] = fmaf(da[j], w.y, df[c + 1]);
+                    df[c + 2] = fmaf(da[j], w.z, df[c + 2]); df[c + 3] = fmaf(da[j], w.w, df[c + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C; c += 4)
+                *reinterpret_cast<float4*>(&sO[lane * SO + c]) =
+                    valid ? make_float4(df[c] * (1.f / 3.f), df[c + 1] * (1.f / 3.f), df[c + 2] * (1.f / 3.f), df[c + 3] * (1.f / 3.f))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-#pragma unroll
-        for (int j = 0; j < HID; ++j) da[j] *= (1.f - expf(-h[j]));
+        __syncwarp();
+        // ---- 5. dW1[j][c] += sum_q d_a[q][j] * f[q][c]   (lane owns c = lane), db1
         if (wgrad) {
-#pragma unroll
-            for (int j = 0; j < HID; ++j) sH[lane * SH + j] = da[j];
-            __syncwarp();
-            // dW1[j][c] += sum_q da[q][j] * f[q][c]   (lane owns c = lane)
             float a[HID];
 #pragma unroll
             for (int j = 0; j < HID; ++j) a[j] = 0.f;
@@ -307,36 +326,15 @@ __global__ void __launch_bounds__(128) triplane_mlp_bwd_kernel(TriplaneParams p)
             }
 #pragma unroll
             for (int j = 0; j < HID; ++j) atomicAdd(&aW1[j * C + lane], a[j]);
-            {
-                float s0 = 0.f, s1 = 0.f;
-                for (int q = 0; q < 32; ++q) { s0 += sH[q * SH + lane]; s1 += sH[q * SH + 32 + lane]; }
-                atomicAdd(&ab1[lane], s0); atomicAdd(&ab1[32 + lane], s1);
-            }
+            float s0 = 0.f, s1 = 0.f;
+            for (int q = 0; q < 32; ++q) { s0 += sH[q * SH + lane]; s1 += sH[q * SH + 32 + lane]; }
+            atomicAdd(&ab1[lane], s0); atomicAdd(&ab1[32 + lane], s1);
         }
-        __syncwarp();
-        // 4. d_f = W1^T d_a  -> staging tile (transposed back to lane == channel)
-        {
-            float df[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) df[c] = 0.f;
-#pragma unroll
-            for (int j = 0; j < HID; ++j) {
-#pragma unroll
-                for (int c = 0; c < C; c += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(&W1s[j * C + c]);
-                    df[c] = fmaf(da[j], w.x, df[c]); df[c + 1] = fmaf(da[j], w.y, df[c + 1]);
-                    df[c + 2] = fmaf(da[j], w.z, df[c + 2]); df[c + 3] = fmaf(da[j], w.w, df[c + 3]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < C; ++c) sA[lane * SA + c] = valid ? df[c] * (1.f / 3.f) : 0.f;
-        }
-        __syncwarp();
-        // 5. scatter into the plane gradient (+ optional coordinate gradient)
+        // ---- 6. scatter d_f (lane == channel) into the plane gradient (+ optional coordinate gradient)
         for (int q = 0; q < cnt; ++q) {
             const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
             const Bilin b0 = make_bilin(gx, gy, p.hp, p.wp), b1 = make_bilin(gx, gz, p.hp, p.wp), b2 = make_bilin(gz, gx, p.hp, p.wp);
-            const float g = sA[q * SA + lane];
+            const float g = sO[q * SO + lane];
             if (dpl) {
                 bilin_scatter(dpl + lane, b0, p.wp, g);
                 bilin_scatter(dpl + C + lane, b1, p.wp, g);

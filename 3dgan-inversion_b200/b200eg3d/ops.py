@@ -8,6 +8,7 @@ Internally the synthesis stack keeps activations NHWC ([N,H,W,C] fp32): one chan
 K-contiguous GEMM operand and the coalescing unit of every elementwise kernel.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -22,8 +23,58 @@ _ACT_REF = {'linear': '', 'relu': 'y', 'lrelu': 'y', 'tanh': 'y', 'sigmoid': 'y'
             'swish': 'x'}
 
 
+# Numerics of the convolution stack.  tc: use the tcgen05 kernels when the shape allows; *_passes: 3 = split-bf16
+# (hi*hi + hi*lo + lo*hi, ~fp32 accuracy), 1 = plain bf16 operands.  B200EG3D_TC=0 forces the exact-fp32 SIMT kernels.
+CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
+          'fwd_passes': int(os.environ.get('B200EG3D_FWD_PASSES', '3')),
+          'dgrad_passes': int(os.environ.get('B200EG3D_DGRAD_PASSES', '3')),
+          'wgrad_passes': int(os.environ.get('B200EG3D_WGRAD_PASSES', '1'))}
+
+
 def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
+
+
+def _tc_ok(kind, h, w, cin, cout, k, up):
+    return CONFIG['tc'] and _lib.load().b200_conv_tc_supported(kind, h, w, cin, cout, k, up) == 1
+
+
+def _split(t, need_lo):
+    """fp32 tensor -> (hi, lo) bf16 tensors with t ~= hi + lo (lo None when not needed)."""
+    hi = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+    lo = torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) if need_lo else None
+    call('b200_split_bf16', ptr(t), ptr(hi), ptr(lo), t.numel(), stream())
+    return hi, lo
+
+
+def _conv_fwd(x, wmod, y, n, h, w, cin, cout, k, up):
+    if _tc_ok(0, h, w, cin, cout, k, up):
+        npass = CONFIG['fwd_passes']
+        xh, xl = _split(x, npass == 3)
+        wh, wl = _split(wmod, npass == 3)
+        call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, npass, stream())
+    else:
+        call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cout, k, up, stream())
+
+
+def _conv_dgrad(dy, wmod, dx, n, h, w, cin, cout, k, up):
+    if _tc_ok(1, h, w, cin, cout, k, up):
+        npass = CONFIG['dgrad_passes']
+        dh, dl = _split(dy, npass == 3)
+        wh, wl = _split(wmod, npass == 3)
+        call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, npass, stream())
+    else:
+        call('b200_conv_dgrad', ptr(dy), ptr(wmod), ptr(dx), n, h, w, cin, cout, k, up, stream())
+
+
+def _conv_wgrad(x, dy, dwmod, n, h, w, cin, cout, k, up):
+    if _tc_ok(2, h, w, cin, cout, k, up):
+        npass = CONFIG['wgrad_passes']
+        xh, xl = _split(x, npass == 3)
+        dh, dl = _split(dy, npass == 3)
+        call('b200_conv_wgrad_tc', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(dwmod), n, h, w, cin, cout, k, up, npass, stream())
+    else:
+        call('b200_conv_wgrad', ptr(x), ptr(dy), ptr(dwmod), n, h, w, cin, cout, k, up, stream())
 
 
 # ----------------------------------------------------------------------------------------------
@@ -211,11 +262,11 @@ class _ModConvLayer(torch.autograd.Function):
         if up == 1:
             oh, ow = h, w
             y = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
-            call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cout, k, 1, stream())
+            _conv_fwd(x, wmod, y, n, h, w, cin, cout, k, 1)
         else:
             oh, ow = 2 * h, 2 * w
             zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
-            call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(zt), n, h, w, cin, cout, k, 2, stream())
+            _conv_fwd(x, wmod, zt, n, h, w, cin, cout, k, 2)
             y = _upfirdn_nhwc_raw(zt, fir_filter(dev), (1, 1), (1, 1), (1, 1, 1, 1), False, 4.0)
         nz = None
         nbs = 0
@@ -255,11 +306,11 @@ class _ModConvLayer(torch.autograd.Function):
         dx = None
         if need[0]:
             dx = torch.empty_like(x)
-            call('b200_conv_dgrad', ptr(dy), ptr(wmod), ptr(dx), n, h, w, cin, cout, k, up, stream())
+            _conv_dgrad(dy, wmod, dx, n, h, w, cin, cout, k, up)
         dW = ds = None
         if need[1] or need[2]:
             dwmod = torch.empty_like(wmod)
-            call('b200_conv_wgrad', ptr(x), ptr(dy), ptr(dwmod), n, h, w, cin, cout, k, up, stream())
+            _conv_wgrad(x, dy, dwmod, n, h, w, cin, cout, k, up)
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin,
@@ -288,7 +339,7 @@ class _ToRGB(torch.autograd.Function):
         wmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
         call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), None, n, cimg, cin, 1, 0, stream())
         y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
-        call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
+        _conv_fwd(x, wmod, y, n, h, w, cin, cimg, 1, 1)
         b = _f32c(bias)
         cl = float(clamp if clamp is not None else -1)
         call('b200_bias_act', ptr(y), ptr(b), None, None, None, ptr(y), 0, y.numel(), 1, cimg, 1, 0.0, 1.0, cl, stream())
@@ -316,11 +367,11 @@ class _ToRGB(torch.autograd.Function):
         dx = None
         if need[0]:
             dx = torch.empty_like(x)
-            call('b200_conv_dgrad', ptr(dy), ptr(wmod), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
+            _conv_dgrad(dy, wmod, dx, n, h, w, cin, cimg, 1, 1)
         dW = ds = None
         if need[1] or need[2]:
             dwmod = torch.empty_like(wmod)
-            call('b200_conv_wgrad', ptr(x), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream())
+            _conv_wgrad(x, dy, dwmod, n, h, w, cin, cimg, 1, 1)
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), None, ptr(dwmod), ptr(dW), ptr(ds), n, cimg, cin, 1, 0, stream())

@@ -42,9 +42,15 @@ def relerr(a, b):
 
 # ---------------------------------------------------------------------------------------------- modconv layer
 
+@pytest.mark.parametrize('tc', [False, True])
 @pytest.mark.parametrize('cin,cout,res,up', [(8, 16, 8, 1), (16, 8, 8, 2), (64, 64, 16, 1), (64, 32, 16, 2), (12, 20, 5, 1),
-                                             (20, 12, 5, 2), (128, 128, 32, 1), (256, 128, 16, 2)])
-def test_modconv_layer_fwd_bwd(b2, cin, cout, res, up):
+                                             (20, 12, 5, 2), (128, 128, 32, 1), (256, 128, 16, 2), (32, 128, 24, 2), (96, 64, 40, 1)])
+def test_modconv_layer_fwd_bwd(b2, cin, cout, res, up, tc, monkeypatch):
+    """tc=False: exact-fp32 SIMT kernels; tc=True: tcgen05 kernels where the shape allows (3-pass split-bf16 forward and,
+    for this test, 3-pass backward so that the tight tolerance applies to both)."""
+    monkeypatch.setitem(b2.ops.CONFIG, 'tc', tc)
+    monkeypatch.setitem(b2.ops.CONFIG, 'dgrad_passes', 3)
+    monkeypatch.setitem(b2.ops.CONFIG, 'wgrad_passes', 3)
     n = 2
     g = gen(cin * 1000 + cout + up)
     x = torch.randn(n, cin, res, res, generator=g)
@@ -71,11 +77,42 @@ def test_modconv_layer_fwd_bwd(b2, cin, cout, res, up):
     names = ['dx', 'dW', 'dstyles', 'dbias', 'dnoise', 'dstrength']
     refs = [nhwc(xr.grad), Wr.grad, sr.grad, br.grad, nr.grad, str_.grad]
     for nm, a, r in zip(names, cl, refs):
-        assert relerr(a.grad, r) < 2e-4, (nm, relerr(a.grad, r))
+        # scalar / mask-driven reductions move a little when split-bf16 rounding flips a clamp or lrelu mask
+        tol = 2e-3 if (tc and nm in ('dstrength', 'dnoise', 'dbias')) else 2e-4
+        assert relerr(a.grad, r) < tol, (nm, relerr(a.grad, r))
 
 
+def test_modconv_layer_single_pass_backward(b2, monkeypatch):
+    """Default PTI numerics: 3-pass forward, single-pass bf16 backward GEMMs -> gradients within 1e-2 relative L2."""
+    monkeypatch.setitem(b2.ops.CONFIG, 'tc', True)
+    monkeypatch.setitem(b2.ops.CONFIG, 'dgrad_passes', 1)
+    monkeypatch.setitem(b2.ops.CONFIG, 'wgrad_passes', 1)
+    n, cin, cout, res = 1, 128, 64, 32
+    g = gen(77)
+    x = torch.randn(n, cin, res, res, generator=g)
+    W = torch.randn(cout, cin, 3, 3, generator=g)
+    s = 1 + 0.3 * torch.randn(n, cin, generator=g)
+    dz = torch.randn(n, cout, res, res, generator=g)
+    for up in (1, 2):
+        xr, Wr, sr = [t.clone().requires_grad_(True) for t in (x, W, s)]
+        y = oracle.modulated_conv2d(xr, Wr, sr, up=up, f=oracle.fir_1331())
+        z_ref = oracle.bias_act(y, None, act='lrelu')
+        dzz = dz if up == 1 else torch.randn(n, cout, 2 * res, 2 * res, generator=g)
+        z_ref.backward(dzz)
+        cl = [t.detach().cuda().requires_grad_(True) for t in (nhwc(x), W, s)]
+        z = b2.ops.modconv_layer(cl[0], cl[1], cl[2], torch.zeros(cout, device='cuda'), None, None, up, math.sqrt(2), None)
+        z.backward(nhwc(dzz).cuda())
+        assert maxdiff(nchw(z), z_ref) < 2e-4 * z_ref.abs().max().item()
+        for nm, a, r in zip(['dx', 'dW', 'ds'], cl, [nhwc(xr.grad), Wr.grad, sr.grad]):
+            assert relerr(a.grad, r) < 1e-2, (up, nm, relerr(a.grad, r))
+
+
+@pytest.mark.parametrize('tc', [False, True])
 @pytest.mark.parametrize('cin,cimg,res,prev', [(16, 96, 8, True), (64, 3, 16, True), (32, 96, 4, False), (10, 3, 6, True)])
-def test_torgb_fwd_bwd(b2, cin, cimg, res, prev):
+def test_torgb_fwd_bwd(b2, cin, cimg, res, prev, tc, monkeypatch):
+    monkeypatch.setitem(b2.ops.CONFIG, 'tc', tc)
+    monkeypatch.setitem(b2.ops.CONFIG, 'dgrad_passes', 3)
+    monkeypatch.setitem(b2.ops.CONFIG, 'wgrad_passes', 3)
     n = 2
     g = gen(cin + cimg)
     x = torch.randn(n, cin, res, res, generator=g)
