@@ -1,0 +1,119 @@
+/* b200eg3d.h -- C ABI of libb200eg3d.so: the sm_100a kernels behind the EG3D tri-plane generator hot path
+ * (TriPlaneGenerator.synthesis of cvlab-kaist/3DGAN-Inversion).
+ *
+ * Conventions (every entry point):
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers of the current CUDA device unless noted
+ *   - nothing is allocated, nothing synchronises, no global state: the caller owns inputs, outputs and workspaces
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call returns immediately
+ *   - returns 0 on success; non-zero on error, with a message available from b200_last_error() (thread-local)
+ *   - activations are NHWC fp32: x[n][h][w][c]; modulated weights are wmod[n][tap][cout][cin], tap = kh*ksize + kw
+ *   - "bf16" pointers are raw __nv_bfloat16 arrays in the same layouts (split-float operands hi + lo ~= fp32 value)
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference repository).
+ */
+#ifndef B200EG3D_H
+#define B200EG3D_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int b200_version(void);                 /* replaces the plugin identity of torch_utils/custom_ops.py:61 get_plugin() */
+const char* b200_last_error(void);      /* replaces TORCH_CHECK -> RuntimeError text, torch_utils/ops/bias_act.cpp:39-55 */
+
+/* ---- modulated convolution (training/networks_stylegan2.py:34-91 modulated_conv2d, fused path) ---------------- */
+
+/* w' = W * s; d = rsqrt(sum w'^2 + 1e-8); wmod = w' * d (demod != 0), written in GEMM layout.  networks_stylegan2.py:58-67.
+ * W [cout][cin][taps], styles [n][cin], wmod [n][taps][cout][cin], dcoef [n][cout] (may be NULL when demod == 0). */
+int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod, float* dcoef,
+                             int n, int cout, int cin, int taps, int demod, void* stream);
+/* Backward of the above: dwmod -> dW [cout][cin][taps] (overwritten), dstyles [n][cin] (overwritten; may be NULL). */
+int b200_modconv_weight_prep_bwd(const float* W, const float* styles, const float* dcoef, const float* dwmod,
+                                 float* dW, float* dstyles, int n, int cout, int cin, int taps, int demod, void* stream);
+
+/* Exact-fp32 gather-GEMM convolutions (any channel count).  Replace F.conv2d / F.conv_transpose2d reached through
+ * torch_utils/ops/conv2d_gradfix.py:37-45 from torch_utils/ops/conv2d_resample.py:113-136, and their autograd.
+ * ksize in {1,3}; up == 1: 'same' correlation (padding ksize/2); up == 2 (ksize 3): stride-2 transposed convolution whose
+ * output y / incoming dy live on the (2h+1) x (2w+1) grid (conv2d_resample.py:121-127, before the FIR of :128).
+ * h, w are the INPUT spatial size. */
+int b200_conv_fwd(const float* x, const float* wmod, float* y, int n, int h, int w, int cin, int cout,
+                  int ksize, int up, void* stream);
+int b200_conv_dgrad(const float* dy, const float* wmod, float* dx, int n, int h, int w, int cin, int cout,
+                    int ksize, int up, void* stream);
+int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int n, int h, int w, int cin, int cout,
+                    int ksize, int up, void* stream);
+
+/* tcgen05 / TMA tensor-core convolutions on split-bf16 operands (same geometry as above).
+ * npass = 3: hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (fp32-parity mode); npass = 1: hi*hi only (lo may be NULL).
+ * b200_conv_tc_supported(kind, ...) -> 1 if the shape is handled (kind 0 fwd, 1 dgrad, 2 wgrad), else use the fp32 entry points. */
+int b200_conv_tc_supported(int kind, int h, int w, int cin, int cout, int ksize, int up);
+int b200_split_bf16(const float* x, void* hi_bf16, void* lo_bf16 /* may be NULL */, long count, void* stream);
+int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y,
+                     int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx,
+                       int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod,
+                       int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+
+/* ---- bias / activation (torch_utils/ops/bias_act.cpp:36 bias_act(x,b,xref,yref,dy,grad,dim,act,alpha,gain,clamp)) ---- */
+
+/* Generic op with the plugin's semantics (kernel bias_act.cu:28-151).  act: 1 linear 2 relu 3 lrelu 4 tanh 5 sigmoid 6 elu
+ * 7 selu 8 softplus 9 swish.  grad: 0 forward (y = clamp(act(x+b)*gain)), 1 first-order gradient (x is dy).  Any of b, xref,
+ * yref, dy may be NULL ("absent", bias_act.cpp:65-68).  Bias index of element i is (i / stepB) % sizeB (bias_act.cu:49). */
+int b200_bias_act(const float* x, const float* b, const float* xref, const float* yref, const float* dy, float* y,
+                  int grad, long sizeX, long stepB, int sizeB, int act, float alpha, float gain, float clamp, void* stream);
+
+/* SynthesisLayer epilogue on NHWC [n][hw][c]: z = clamp(lrelu(y + noise[pix]*strength + bias[c]) * gain, +-clamp)
+ * (training/networks_stylegan2.py:318-329).  noise [hw] (noise_bs 0, shared 'const' buffer) or [n][hw] (noise_bs = hw) or NULL;
+ * strength: device scalar; clamp < 0 disables clamping. */
+int b200_layer_act_fwd(const float* y, float* z, const float* bias, const float* noise, const float* strength, long noise_bs,
+                       int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream);
+/* Backward from the saved OUTPUT z (bias_act.cu:73-77,143-145): dy, plus ACCUMULATED dbias[c], dstrength[1], dnoise (any NULL). */
+int b200_layer_act_bwd(const float* dz, const float* z, float* dy, float* dbias, const float* noise, const float* strength,
+                       long noise_bs, float* dstrength, float* dnoise, int n, int hw, int c, int lrelu, float alpha, float gain,
+                       float clamp, void* stream);
+
+/* ---- upfirdn2d (torch_utils/ops/upfirdn2d.cpp:20 upfirdn2d(x,f,upx,upy,downx,downy,padx0,padx1,pady0,pady1,flip,gain)) ---- */
+/* NHWC x [n][h][w][c] -> y [n][oh][ow][c], oh = (h*upy + pady0 + pady1 - fh + downy) / downy (upfirdn2d.cpp:37-38); f [fh][fw];
+ * optional `add` (same shape as y) is added to the result (the img.add_(y) of networks_stylegan2.py:457). */
+int b200_upfirdn2d(const float* x, const float* f, const float* add, float* y, int n, int h, int w, int c, int fh, int fw,
+                   int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
+                   void* stream);
+
+/* ---- fused tri-plane sampling + OSG decoder (renderer.py:39-66 sample_from_planes, triplane.py:124-136 OSGDecoder.forward) ---- */
+/* planes [n][hp][wp][96] (plane p = channels 32p..32p+31).  Points: coords [n][P][3], or (coords NULL) rays ray_o/ray_d
+ * [n][P/S][3] with depths [n][P] (point p on ray p / S).  W1 [64][32], b1 [64], W2 [33][64], b2 [33] raw parameters
+ * (gains lr_mul/sqrt(fan_in), networks_stylegan2.py:111-112, applied inside).  Out: rgb [n][P][32], sigma [n][P]. */
+int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
+                          const float* ray_d, const float* depths, int S, long P, float box_warp,
+                          const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
+                          float* rgb, float* sigma, void* stream);
+/* d_planes is ACCUMULATED (zero it first; may be NULL); d_coords [n][P][3] written (may be NULL); dW1..db2 ACCUMULATED (all or none). */
+int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
+                          const float* ray_d, const float* depths, int S, long P, float box_warp,
+                          const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
+                          const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
+                          float* dW1, float* db1, float* dW2, float* db2, void* stream);
+
+/* ---- per-ray kernels (renderer.py:143-308 ImportanceRenderer, ray_marcher.py:25-57 MipRayMarcher2) ---------------- */
+/* t[ray][s] = t_base[s] + u[ray][s] * delta          (renderer.py:224-247 sample_stratified, numeric ray_start/ray_end) */
+int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta, void* stream);
+/* global min / max of depths for the clamp of ray_marcher.py:50; minmax: 2 x uint32 (order-preserving), initialised {~0u, 0} */
+int b200_depth_minmax(const float* t, long total, unsigned* minmax, void* stream);
+/* coarse weights -> maxpool/avgpool smoothing -> inverse-CDF fine depths (renderer.py:249-308).  u [n_rays][S_imp]. */
+int b200_ray_importance(const float* t_c, const float* sigma_c, const float* u, float* t_f, long n_rays, int S, int S_imp,
+                        void* stream);
+/* merge coarse+fine by depth (renderer.py:212-222) and composite (ray_marcher.py:25-57): feat [n_rays][32], depth, wsum. */
+int b200_ray_composite_fwd(const float* t_c, const float* sigma_c, const float* rgb_c, int S1, const float* t_f,
+                           const float* sigma_f, const float* rgb_f, int S2, const unsigned* minmax, int white_back,
+                           long n_rays, float* feat, float* depth, float* wsum, void* stream);
+int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, const float* rgb_c, int S1, const float* t_f,
+                           const float* sigma_f, const float* rgb_f, int S2, const unsigned* minmax, int white_back,
+                           long n_rays, const float* d_feat, const float* d_depth, const float* d_wsum, float* d_rgb_c,
+                           float* d_sigma_c, float* d_rgb_f, float* d_sigma_f, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200EG3D_H */
