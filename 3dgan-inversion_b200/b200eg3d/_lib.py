@@ -21,12 +21,13 @@ SIGNATURES = {
     'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_wgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    'b200_modconv_weight_prep': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    'b200_modconv_weight_prep': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200_modconv_weight_prep_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200_bias_act': [_P, _P, _P, _P, _P, _P, _I, _L, _L, _I, _I, _F, _F, _F, _P],
-    'b200_layer_act_fwd': [_P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
-    'b200_layer_act_bwd': [_P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200_layer_act_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200_layer_act_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_upfirdn2d': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
+    'b200_upfirdn2d_fused': [_P] * 6 + [_I] * 13 + [_F, _I, _P, _P, _P, _L, _I, _F, _F, _F, _P],
     'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P],
     'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],

@@ -6,6 +6,15 @@
 //   b200_upfirdn2d       pad / zero-insert upsample / FIR / decimate on NHWC tensors, optional fused "+ add"
 //                        (semantics of torch_utils/ops/upfirdn2d.py:169-213, plugin entry upfirdn2d.cpp:20)
 #include "common.cuh"
+#include <cuda_bf16.h>
+
+__device__ __forceinline__ void split4(const float* o, uint2* hi, uint2* lo, long i) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(o[j]); l[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h[j])); }
+    if (hi) hi[i] = *reinterpret_cast<uint2*>(h);
+    if (lo) lo[i] = *reinterpret_cast<uint2*>(l);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Generic bias_act.  act codes follow the reference table (bias_act.py:20-30): 1 linear, 2 relu, 3 lrelu,
@@ -67,7 +76,8 @@ B200_API int b200_bias_act(const float* x, const float* b, const float* xref, co
 // SynthesisLayer epilogue on NHWC [n][hw][c]:  z = clamp(act(y + noise[pix]*strength + bias[c]) * gain, +-clamp)
 // noise may be null; noise_bs = per-sample stride of the noise map (0 for the shared 'const' buffer).
 
-__global__ void layer_act_fwd_kernel(const float4* __restrict__ y, float4* __restrict__ z, const float* __restrict__ bias,
+__global__ void layer_act_fwd_kernel(const float4* __restrict__ y, float4* __restrict__ z, uint2* __restrict__ zhi,
+                                     uint2* __restrict__ zlo, const float* __restrict__ bias,
                                      const float* __restrict__ noise, const float* __restrict__ strength, long noise_bs,
                                      long total4, int hw, int c4, int lrelu, float alpha, float gain, float clamp) {
     const float str = (noise && strength) ? *strength : 0.f;
@@ -87,7 +97,8 @@ __global__ void layer_act_fwd_kernel(const float4* __restrict__ y, float4* __res
             if (clamp >= 0.f) t = (t > -clamp && t < clamp) ? t : (t >= 0.f ? clamp : -clamp);
             o[j] = t;
         }
-        z[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (z) z[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (zhi) split4(o, zhi, zlo, i);
     }
 }
 
@@ -108,17 +119,19 @@ __global__ void layer_act_fwd_kernel_s(const float* __restrict__ y, float* __res
     }
 }
 
-B200_API int b200_layer_act_fwd(const float* y, float* z, const float* bias, const float* noise, const float* strength,
-                                long noise_bs, int n, int hw, int c, int lrelu, float alpha, float gain, float clamp,
-                                void* stream) {
+B200_API int b200_layer_act_fwd(const float* y, float* z, void* z_hi, void* z_lo, const float* bias, const float* noise,
+                                const float* strength, long noise_bs, int n, int hw, int c, int lrelu, float alpha, float gain,
+                                float clamp, void* stream) {
     const long total = (long)n * hw * c;
     if (total <= 0) return 0;
+    B200_REQUIRE(z || z_hi, "layer_act_fwd: no output requested");
+    B200_REQUIRE(!z_hi || c % 4 == 0, "layer_act_fwd: bf16 outputs need a channel count that is a multiple of 4");
     cudaStream_t st = (cudaStream_t)stream;
     if (c % 4 == 0) {
         const long t4 = total / 4;
         const int blocks = (int)((t4 + 255) / 256 < 148 * 16 ? (t4 + 255) / 256 : 148 * 16);
-        layer_act_fwd_kernel<<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, bias, noise, strength, noise_bs, t4, hw,
-                                                     c / 4, lrelu, alpha, gain, clamp);
+        layer_act_fwd_kernel<<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo, bias, noise, strength,
+                                                     noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp);
     } else {
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
         layer_act_fwd_kernel_s<<<blocks, 256, 0, st>>>(y, z, bias, noise, strength, noise_bs, total, hw, c, lrelu, alpha,
@@ -132,7 +145,8 @@ B200_API int b200_layer_act_fwd(const float* y, float* z, const float* bias, con
 // Also reduces dbias[c] += sum_pix dy, dstrength += sum dy*noise, dnoise[pix] += strength * sum_c dy.
 template <int R>
 __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ z,
-                                                            float* __restrict__ dy, float* __restrict__ dbias,
+                                                            float* __restrict__ dy, __nv_bfloat16* __restrict__ dyhi,
+                                                            __nv_bfloat16* __restrict__ dylo, float* __restrict__ dbias,
                                                             const float* __restrict__ noise, const float* __restrict__ strength,
                                                             long noise_bs, float* __restrict__ dstrength,
                                                             float* __restrict__ dnoise, long npix, int hw, int c, int lrelu,
@@ -151,7 +165,6 @@ __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restr
     for (long pix = (long)blockIdx.x * (blockDim.x >> 5) + wid; pix < npix; pix += nwarps) {
         const float* dzr = dz + pix * c;
         const float* zr = z + pix * c;
-        float* dyr = dy + pix * c;
         float row = 0.f;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
@@ -161,7 +174,12 @@ __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restr
                 float g = dzr[ch] * gain;
                 if (lrelu && !(zz > 0.f)) g *= alpha;
                 if (clamp >= 0.f && !(zz > -clamp && zz < clamp)) g = 0.f;
-                dyr[ch] = g;
+                if (dy) dy[pix * c + ch] = g;
+                if (dyhi) {
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(g);
+                    dyhi[pix * c + ch] = hh;
+                    if (dylo) dylo[pix * c + ch] = __float2bfloat16_rn(g - __bfloat162float(hh));
+                }
                 col[j] += g;
                 row += g;
             }
@@ -192,17 +210,18 @@ __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restr
     }
 }
 
-B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, float* dbias, const float* noise,
-                                const float* strength, long noise_bs, float* dstrength, float* dnoise, int n, int hw, int c,
-                                int lrelu, float alpha, float gain, float clamp, void* stream) {
+B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, void* dy_hi, void* dy_lo, float* dbias,
+                                const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise, int n,
+                                int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
     // dbias / dstrength / dnoise are ACCUMULATED into (callers zero them); any of them may be null.
     const long npix = (long)n * hw;
     if (npix <= 0 || c <= 0) return 0;
     B200_REQUIRE(c <= 512, "layer_act_bwd: at most 512 channels");
     cudaStream_t st = (cudaStream_t)stream;
     const int blocks = (int)((npix + 7) / 8 < 148 * 8 ? (npix + 7) / 8 : 148 * 8);
-#define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, dy, dbias, noise, strength, noise_bs, dstrength, \
-                                                                     dnoise, npix, hw, c, lrelu, alpha, gain, clamp)
+#define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, dy, (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, dbias, \
+                                                                     noise, strength, noise_bs, dstrength, dnoise, npix, hw, c, lrelu, \
+                                                                     alpha, gain, clamp)
     if (c <= 32) LAUNCH_R(1); else if (c <= 64) LAUNCH_R(2); else if (c <= 128) LAUNCH_R(4);
     else if (c <= 256) LAUNCH_R(8); else LAUNCH_R(16);
 #undef LAUNCH_R
@@ -216,15 +235,27 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, floa
 // g = gain * (flip ? f : reversed f)   -- the reference correlates with the reversed filter unless flip_filter.
 
 struct UpfirdnParams {
-    const float* x; const float* f; const float* add; float* y;
+    const float* x; const float* f; const float* add; float* y; uint2* yhi; uint2* ylo;
     int n, h, w, c, oh, ow, fh, fw, upx, upy, downx, downy, padx0, pady0, flip;
     float gain;
+    // optional SynthesisLayer epilogue applied to the filtered value (act != 0)
+    int act; const float* bias; const float* noise; const float* strength; long noise_bs; int lrelu; float alpha, act_gain, clamp;
 };
 
-template <int V>
+// V = channels per thread (4 or 1).  F > 0: square FxF filter with compile-time UP / DOWN (fully unrolled taps);
+// F == 0: generic run-time filter size and factors.
+template <int V, int F, int UP, int DOWN>
 __global__ void upfirdn2d_kernel(UpfirdnParams p) {
     const int cv = p.c / V;
     const long total = (long)p.n * p.oh * p.ow * cv;
+    const int fh = F > 0 ? F : p.fh, fw = F > 0 ? F : p.fw;
+    const int upx = F > 0 ? UP : p.upx, upy = F > 0 ? UP : p.upy, downx = F > 0 ? DOWN : p.downx, downy = F > 0 ? DOWN : p.downy;
+    float fr[F > 0 ? F * F : 1];
+    if (F > 0) {
+#pragma unroll
+        for (int i = 0; i < F * F; ++i) fr[i] = p.flip ? p.f[i] : p.f[F * F - 1 - i];
+    }
+    const float str = (p.act && p.noise && p.strength) ? *p.strength : 0.f;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
         const int cc = (int)(i % cv) * V;
         long r = i / cv;
@@ -234,55 +265,104 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0.f;
-        for (int a = 0; a < p.fh; ++a) {
-            const int uy = oy * p.downy + a - p.pady0;
-            if (uy < 0 || uy % p.upy != 0) continue;
-            const int iy = uy / p.upy;
-            if (iy >= p.h) continue;
-            for (int q = 0; q < p.fw; ++q) {
-                const int ux = ox * p.downx + q - p.padx0;
-                if (ux < 0 || ux % p.upx != 0) continue;
-                const int ix = ux / p.upx;
-                if (ix >= p.w) continue;
-                const float g = p.flip ? p.f[a * p.fw + q] : p.f[(p.fh - 1 - a) * p.fw + (p.fw - 1 - q)];
-                const float* src = p.x + (((long)b * p.h + iy) * p.w + ix) * p.c + cc;
-                if (V == 4) {
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-                    acc[0] = fmaf(g, v.x, acc[0]); acc[1] = fmaf(g, v.y, acc[1]);
-                    acc[2 % V] = fmaf(g, v.z, acc[2 % V]); acc[3 % V] = fmaf(g, v.w, acc[3 % V]);
-                } else {
-                    acc[0] = fmaf(g, __ldg(src), acc[0]);
-                }
+        const float* xb = p.x + (long)b * p.h * p.w * p.c + cc;
+        auto tap = [&](int a, int q, float g) {
+            const int uy = oy * downy + a - p.pady0, ux = ox * downx + q - p.padx0;
+            if (uy < 0 || ux < 0 || uy % upy != 0 || ux % upx != 0) return;
+            const int iy = uy / upy, ix = ux / upx;
+            if (iy >= p.h || ix >= p.w) return;
+            const float* src = xb + ((long)iy * p.w + ix) * p.c;
+            if (V == 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+                acc[0] = fmaf(g, v.x, acc[0]); acc[1 % V] = fmaf(g, v.y, acc[1 % V]);
+                acc[2 % V] = fmaf(g, v.z, acc[2 % V]); acc[3 % V] = fmaf(g, v.w, acc[3 % V]);
+            } else {
+                acc[0] = fmaf(g, __ldg(src), acc[0]);
+            }
+        };
+        if (F > 0) {
+#pragma unroll
+            for (int a = 0; a < F; ++a)
+#pragma unroll
+                for (int q = 0; q < F; ++q) tap(a, q, fr[a * (F > 0 ? F : 1) + q]);
+        } else {
+#pragma unroll 1
+            for (int a = 0; a < fh; ++a)
+#pragma unroll 1
+                for (int q = 0; q < fw; ++q) tap(a, q, p.flip ? p.f[a * fw + q] : p.f[(fh - 1 - a) * fw + (fw - 1 - q)]);
+        }
+        const long opix = ((long)b * p.oh + oy) * p.ow + ox;
+        const long o = opix * p.c + cc;
+        float out[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) out[j] = acc[j] * p.gain;
+        if (p.add) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) out[j] += p.add[o + j];
+        }
+        if (p.act) {
+            float nz = 0.f;
+            if (p.noise) nz = p.noise[(long)b * p.noise_bs + (long)oy * p.ow + ox] * str;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float t = out[j] + nz + (p.bias ? p.bias[cc + j] : 0.f);
+                if (p.lrelu) t = t > 0.f ? t : t * p.alpha;
+                t *= p.act_gain;
+                if (p.clamp >= 0.f) t = (t > -p.clamp && t < p.clamp) ? t : (t >= 0.f ? p.clamp : -p.clamp);
+                out[j] = t;
             }
         }
-        const long o = (((long)b * p.oh + oy) * p.ow + ox) * p.c + cc;
         if (V == 4) {
-            float4 out = make_float4(acc[0] * p.gain, acc[1] * p.gain, acc[2 % V] * p.gain, acc[3 % V] * p.gain);
-            if (p.add) { const float4 ad = *reinterpret_cast<const float4*>(p.add + o); out.x += ad.x; out.y += ad.y; out.z += ad.z; out.w += ad.w; }
-            *reinterpret_cast<float4*>(p.y + o) = out;
+            if (p.y) *reinterpret_cast<float4*>(p.y + o) = make_float4(out[0], out[1 % V], out[2 % V], out[3 % V]);
+            if (p.yhi) split4(out, p.yhi, p.ylo, o / 4);
         } else {
-            float out = acc[0] * p.gain;
-            if (p.add) out += p.add[o];
-            p.y[o] = out;
+            p.y[o] = out[0];
         }
     }
+}
+
+static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t st) {
+    B200_REQUIRE(p.upx >= 1 && p.upy >= 1 && p.downx >= 1 && p.downy >= 1, "upfirdn2d: up/down factors must be >= 1");
+    B200_REQUIRE(p.fh >= 1 && p.fw >= 1 && p.fh <= 64 && p.fw <= 64, "upfirdn2d: filter size must be in [1, 64]");
+    p.oh = (p.h * p.upy + p.pady0 + pady1 - p.fh + p.downy) / p.downy;
+    p.ow = (p.w * p.upx + p.padx0 + padx1 - p.fw + p.downx) / p.downx;
+    B200_REQUIRE(p.oh >= 1 && p.ow >= 1, "upfirdn2d: output would be empty");
+    const bool v4 = (p.c % 4 == 0);
+    B200_REQUIRE(v4 || (!p.yhi && p.y), "upfirdn2d: bf16 outputs need a channel count that is a multiple of 4");
+    B200_REQUIRE(p.y || p.yhi, "upfirdn2d: no output requested");
+    const long total = (long)p.n * p.oh * p.ow * (v4 ? p.c / 4 : p.c);
+    if (total <= 0) return 0;
+    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    const bool sq4 = p.fh == 4 && p.fw == 4 && p.upx == p.upy && p.downx == p.downy;
+    if (v4 && sq4 && p.upx == 1 && p.downx == 1) upfirdn2d_kernel<4, 4, 1, 1><<<blocks, 256, 0, st>>>(p);
+    else if (v4 && sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<4, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
+    else if (v4 && sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<4, 4, 1, 2><<<blocks, 256, 0, st>>>(p);
+    else if (v4) upfirdn2d_kernel<4, 0, 1, 1><<<blocks, 256, 0, st>>>(p);
+    else upfirdn2d_kernel<1, 0, 1, 1><<<blocks, 256, 0, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
 }
 
 B200_API int b200_upfirdn2d(const float* x, const float* f, const float* add, float* y, int n, int h, int w, int c, int fh,
                             int fw, int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1,
                             int flip, float gain, void* stream) {
-    B200_REQUIRE(upx >= 1 && upy >= 1 && downx >= 1 && downy >= 1, "upfirdn2d: up/down factors must be >= 1");
-    B200_REQUIRE(fh >= 1 && fw >= 1, "upfirdn2d: empty filter");
-    UpfirdnParams p{x, f, add, y, n, h, w, c, 0, 0, fh, fw, upx, upy, downx, downy, padx0, pady0, flip, gain};
-    p.oh = (h * upy + pady0 + pady1 - fh + downy) / downy;
-    p.ow = (w * upx + padx0 + padx1 - fw + downx) / downx;
-    B200_REQUIRE(p.oh >= 1 && p.ow >= 1, "upfirdn2d: output would be empty");
-    const bool v4 = (c % 4 == 0);
-    const long total = (long)n * p.oh * p.ow * (v4 ? c / 4 : c);
-    if (total <= 0) return 0;
-    const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
-    if (v4) upfirdn2d_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    else upfirdn2d_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
-    B200_CHECK_LAUNCH();
-    return 0;
+    UpfirdnParams p{};
+    p.x = x; p.f = f; p.add = add; p.y = y; p.n = n; p.h = h; p.w = w; p.c = c; p.fh = fh; p.fw = fw; p.upx = upx; p.upy = upy;
+    p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip; p.gain = gain;
+    return launch_upfirdn(p, padx1, pady1, (cudaStream_t)stream);
+}
+
+// upfirdn2d with fused consumers: optional SynthesisLayer epilogue (act != 0: + noise*strength + bias, lrelu, gain, clamp --
+// conv2d_resample.py:128 followed by networks_stylegan2.py:318-329 in one pass) and optional split-bf16 copies of the result
+// (y, y_hi/y_lo: at least one; the bf16 pair feeds the next tensor-core convolution).
+B200_API int b200_upfirdn2d_fused(const float* x, const float* f, const float* add, float* y, void* y_hi, void* y_lo, int n, int h,
+                                  int w, int c, int fh, int fw, int up, int down, int padx0, int padx1, int pady0, int pady1,
+                                  int flip, float gain, int act, const float* bias, const float* noise, const float* strength,
+                                  long noise_bs, int lrelu, float alpha, float act_gain, float clamp, void* stream) {
+    UpfirdnParams p{};
+    p.x = x; p.f = f; p.add = add; p.y = y; p.yhi = (uint2*)y_hi; p.ylo = (uint2*)y_lo; p.n = n; p.h = h; p.w = w; p.c = c;
+    p.fh = fh; p.fw = fw; p.upx = p.upy = up; p.downx = p.downy = down; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip; p.gain = gain;
+    p.act = act; p.bias = bias; p.noise = noise; p.strength = strength; p.noise_bs = noise_bs; p.lrelu = lrelu; p.alpha = alpha;
+    p.act_gain = act_gain; p.clamp = clamp;
+    return launch_upfirdn(p, padx1, pady1, (cudaStream_t)stream);
 }

@@ -1,6 +1,7 @@
 // Weight modulation / demodulation of modulated_conv2d (reference: training/networks_stylegan2.py:58-67)
 // and its backward, producing weights directly in the GEMM layout wmod[n][tap][cout][cin].
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
     v = warp_sum(v);
@@ -16,7 +17,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // grid (cout, n), block 256
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ W, const float* __restrict__ styles,
-                                                          float* __restrict__ wmod, float* __restrict__ dcoef,
+                                                          float* __restrict__ wmod, __nv_bfloat16* __restrict__ whi,
+                                                          __nv_bfloat16* __restrict__ wlo, float* __restrict__ dcoef,
                                                           int cout, int cin, int taps, int demod) {
     __shared__ float red[32];
     const int o = blockIdx.x, n = blockIdx.y;
@@ -33,10 +35,17 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
         d = rsqrtf(acc + 1e-8f);
         if (threadIdx.x == 0 && dcoef) dcoef[(long)n * cout + o] = d;
     }
-    float* out = wmod + (long)n * taps * cout * cin;
+    const long ob = (long)n * taps * cout * cin;
     for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
         const int t = idx / cin, i = idx % cin;
-        out[((long)t * cout + o) * cin + i] = Wo[i * taps + t] * s[i] * d;
+        const float v = Wo[i * taps + t] * s[i] * d;
+        const long oi = ob + ((long)t * cout + o) * cin + i;
+        if (wmod) wmod[oi] = v;
+        if (whi) {
+            const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+            whi[oi] = hh;
+            if (wlo) wlo[oi] = __float2bfloat16_rn(v - __bfloat162float(hh));
+        }
     }
 }
 
@@ -78,10 +87,12 @@ __global__ void __launch_bounds__(256) weight_prep_bwd_kernel(const float* __res
     }
 }
 
-B200_API int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod, float* dcoef,
+B200_API int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod, void* w_hi, void* w_lo, float* dcoef,
                                       int n, int cout, int cin, int taps, int demod, void* stream) {
     B200_REQUIRE(n > 0 && cout > 0 && cin > 0 && taps > 0, "weight_prep: bad shape");
-    weight_prep_kernel<<<dim3(cout, n), 256, 0, (cudaStream_t)stream>>>(W, styles, wmod, dcoef, cout, cin, taps, demod);
+    B200_REQUIRE(wmod || w_hi, "weight_prep: no output requested");
+    weight_prep_kernel<<<dim3(cout, n), 256, 0, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
+                                                                        dcoef, cout, cin, taps, demod);
     B200_CHECK_LAUNCH();
     return 0;
 }

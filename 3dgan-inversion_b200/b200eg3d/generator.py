@@ -127,7 +127,8 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None):
+        """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None."""
         assert noise_mode in ['random', 'const', 'none']
         styles = self.affine(w)
         noise = None
@@ -137,7 +138,7 @@ class SynthesisLayer(torch.nn.Module):
             noise = self.noise_const
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return ops.modconv_layer(x, self.weight, styles, self.bias, noise, self.noise_strength if noise is not None else None,
-                                 self.up, self.act_gain * gain, clamp)
+                                 self.up, self.act_gain * gain, clamp, x_split=x_split)
 
 
 class ToRGBLayer(torch.nn.Module):
@@ -153,9 +154,9 @@ class ToRGBLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
-    def forward(self, x, w, fused_modconv=True, img_prev=None):
+    def forward(self, x, w, fused_modconv=True, img_prev=None, x_split=None):
         styles = self.affine(w) * self.weight_gain
-        return ops.torgb_layer(x, self.weight, styles, self.bias, img_prev, self.conv_clamp)
+        return ops.torgb_layer(x, self.weight, styles, self.bias, img_prev, self.conv_clamp, x_split=x_split)
 
 
 class SynthesisBlock(torch.nn.Module):
@@ -185,14 +186,19 @@ class SynthesisBlock(torch.nn.Module):
         self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp)
         self.num_torgb += 1
 
-    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, **layer_kwargs):
+    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, x_split=None, return_split=False,
+                **layer_kwargs):
+        """x_split / return_split carry the split-bf16 copies of the activations between consecutive blocks."""
         w_iter = iter(ws.unbind(dim=1))
         if self.in_channels == 0:
             x = self.const.to(torch.float32).permute(1, 2, 0).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous()
+            sp = None
         else:
-            x = self.conv0(x, next(w_iter), **layer_kwargs)
-        x = self.conv1(x, next(w_iter), **layer_kwargs)
-        img = self.torgb(x, next(w_iter), img_prev=img)
+            x, sp = self.conv0(x, next(w_iter), x_split=x_split, **layer_kwargs)
+        x, sp = self.conv1(x, next(w_iter), x_split=sp, **layer_kwargs)
+        img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp)
+        if return_split:
+            return x, img, sp
         return x, img
 
 
@@ -226,9 +232,9 @@ class SynthesisNetwork(torch.nn.Module):
             block = getattr(self, f'b{res}')
             block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
             w_idx += block.num_conv
-        x = img = None
+        x = img = sp = None
         for res, cur_ws in zip(self.block_resolutions, block_ws):
-            x, img = getattr(self, f'b{res}')(x, img, cur_ws, **block_kwargs)
+            x, img, sp = getattr(self, f'b{res}')(x, img, cur_ws, x_split=sp, return_split=True, **block_kwargs)
         return img
 
     def forward(self, ws, c=None, **block_kwargs):
@@ -274,8 +280,8 @@ class SuperresolutionHybrid8X(torch.nn.Module):
             size = (self.input_resolution, self.input_resolution)
             x = _to_nhwc(F.interpolate(_to_nchw_view(x), size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias))
             rgb = _to_nhwc(F.interpolate(_to_nchw_view(rgb), size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias))
-        x, rgb = self.block0(x, rgb, ws, **block_kwargs)
-        x, rgb = self.block1(x, rgb, ws, **block_kwargs)
+        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, **block_kwargs)
+        x, rgb = self.block1(x, rgb, ws, x_split=sp, **block_kwargs)
         return rgb
 
     def forward(self, rgb, x, ws, **block_kwargs):

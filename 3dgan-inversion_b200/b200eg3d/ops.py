@@ -240,15 +240,41 @@ def fir_filter(device):
     return _FIR_CACHE[key]
 
 
+def _bf16_like(t):
+    return torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
+
+
+def _fir_fused(x, f2, up, down, pad, flip, gain, want_f32=True, want_split=False, need_lo=True, add=None, act=None):
+    """b200_upfirdn2d_fused on NHWC x.  act = (bias, noise, strength, noise_bs, act_gain, clamp) or None.
+    Returns (y fp32 | None, y_hi | None, y_lo | None)."""
+    n, h, w, c = x.shape
+    px0, px1, py0, py1 = pad
+    fh, fw = f2.shape
+    oh = (h * up + py0 + py1 - fh + down) // down
+    ow = (w * up + px0 + px1 - fw + down) // down
+    y = torch.empty([n, oh, ow, c], device=x.device, dtype=torch.float32) if want_f32 else None
+    yh = torch.empty([n, oh, ow, c], device=x.device, dtype=torch.bfloat16) if want_split else None
+    yl = torch.empty([n, oh, ow, c], device=x.device, dtype=torch.bfloat16) if (want_split and need_lo) else None
+    if act is None:
+        a = (0, None, None, None, 0, 0, 0.0, 1.0, -1.0)
+    else:
+        bias, noise, strength, nbs, act_gain, clamp = act
+        a = (1, ptr(bias), ptr(noise), ptr(strength), nbs, 1, 0.2, float(act_gain), float(clamp))
+    call('b200_upfirdn2d_fused', ptr(x), ptr(f2), ptr(add), ptr(y), ptr(yh), ptr(yl), n, h, w, c, fh, fw, up, down, px0, px1, py0, py1,
+         int(flip), float(gain), *a, stream())
+    return y, yh, yl
+
+
 class _ModConvLayer(torch.autograd.Function):
     """z = clamp(lrelu(modconv(x, W, styles) [-> FIR if up=2] + noise*strength + bias) * act_gain, +-clamp)
 
-    x [N,H,W,Cin] NHWC, weight [Cout,Cin,3,3], styles [N,Cin], noise [H',W'] or [N,1,H',W'] or None,
-    strength 0-dim tensor.  networks_stylegan2.py:311-330 + :34-91 (fused_modconv path).
+    x [N,H,W,Cin] NHWC (+ optional split-bf16 copies x_hi/x_lo made by the producing layer), weight [Cout,Cin,3,3],
+    styles [N,Cin], noise [H',W'] or [N,1,H',W'] or None, strength 0-dim tensor.
+    Returns (z, z_hi, z_lo); the bf16 pair is None on the exact-fp32 path.  networks_stylegan2.py:311-330 + :34-91.
     """
 
     @staticmethod
-    def forward(ctx, x, weight, styles, bias, noise, strength, up, act_gain, clamp):
+    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp):
         x = _f32c(x)
         n, h, w, cin = x.shape
         cout, _, k, _ = weight.shape
@@ -256,90 +282,148 @@ class _ModConvLayer(torch.autograd.Function):
         dev = x.device
         W = _f32c(weight)
         s = _f32c(styles)
-        wmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
-        dcoef = torch.empty([n, cout], device=dev, dtype=torch.float32)
-        call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), ptr(dcoef), n, cout, cin, taps, 1, stream())
-        if up == 1:
-            oh, ow = h, w
-            y = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
-            _conv_fwd(x, wmod, y, n, h, w, cin, cout, k, 1)
-        else:
-            oh, ow = 2 * h, 2 * w
-            zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
-            _conv_fwd(x, wmod, zt, n, h, w, cin, cout, k, 2)
-            y = _upfirdn_nhwc_raw(zt, fir_filter(dev), (1, 1), (1, 1), (1, 1, 1, 1), False, 4.0)
-        nz = None
+        b = _f32c(bias)
+        clampf = float(clamp if clamp is not None else -1)
+        oh, ow = h * up, w * up
+        nz = st = None
         nbs = 0
         if noise is not None:
             nz = _f32c(noise)
             nbs = oh * ow if nz.ndim == 4 else 0
-        b = _f32c(bias)
-        st = _f32c(strength) if noise is not None else None
-        z = torch.empty_like(y)
-        call('b200_layer_act_fwd', ptr(y), ptr(z), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
-             float(act_gain), float(clamp if clamp is not None else -1), stream())
-        ctx.cfg = (up, float(act_gain), float(clamp if clamp is not None else -1), k, nbs, noise is not None and noise.ndim)
-        ctx.save_for_backward(x, W, s, wmod, dcoef, z, nz, st)
-        return z
+            st = _f32c(strength)
+        tc = _tc_ok(0, h, w, cin, cout, k, up) and _tc_ok(1, h, w, cin, cout, k, up) and _tc_ok(2, h, w, cin, cout, k, up)
+        dcoef = torch.empty([n, cout], device=dev, dtype=torch.float32)
+        z = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
+        if tc:
+            fp = CONFIG['fwd_passes']
+            keep_lo = fp == 3 or CONFIG['dgrad_passes'] == 3
+            w_hi = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.bfloat16)
+            w_lo = torch.empty_like(w_hi) if keep_lo else None
+            call('b200_modconv_weight_prep', ptr(W), ptr(s), None, ptr(w_hi), ptr(w_lo), ptr(dcoef), n, cout, cin, taps, 1, stream())
+            if x_hi is None or (fp == 3 and x_lo is None):
+                x_hi, x_lo = _split(x, fp == 3)
+            z_hi, z_lo = _bf16_like(z), _bf16_like(z)
+            if up == 1:
+                y = torch.empty_like(z)
+                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cout, k, 1, fp, stream())
+                call('b200_layer_act_fwd', ptr(y), ptr(z), ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
+                     float(act_gain), clampf, stream())
+            else:
+                zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
+                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(zt), n, h, w, cin, cout, k, 2, fp, stream())
+                # 4x4 FIR (pad 1, gain 4) fused with the layer epilogue and the bf16 split for the next conv
+                call('b200_upfirdn2d_fused', ptr(zt), ptr(fir_filter(dev)), None, ptr(z), ptr(z_hi), ptr(z_lo), n, 2 * h + 1, 2 * w + 1,
+                     cout, 4, 4, 1, 1, 1, 1, 1, 1, 0, 4.0, 1, ptr(b), ptr(nz), ptr(st), nbs, 1, 0.2, float(act_gain), clampf, stream())
+            ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, dcoef, z, nz, st)
+            ctx.mark_non_differentiable(z_hi, z_lo)
+        else:
+            wmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
+            call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), None, None, ptr(dcoef), n, cout, cin, taps, 1, stream())
+            if up == 1:
+                y = torch.empty_like(z)
+                call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cout, k, 1, stream())
+            else:
+                zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
+                call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(zt), n, h, w, cin, cout, k, 2, stream())
+                y = _upfirdn_nhwc_raw(zt, fir_filter(dev), (1, 1), (1, 1), (1, 1, 1, 1), False, 4.0)
+            call('b200_layer_act_fwd', ptr(y), ptr(z), None, None, ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
+                 float(act_gain), clampf, stream())
+            z_hi = z_lo = None
+            ctx.save_for_backward(x, None, W, s, wmod, None, dcoef, z, nz, st)
+        ctx.cfg = (tc, up, float(act_gain), clampf, k, nbs, (n, h, w, cin, cout))
+        return z, z_hi, z_lo
 
     @staticmethod
-    def backward(ctx, dz):
-        x, W, s, wmod, dcoef, z, nz, st = ctx.saved_tensors
-        up, act_gain, clamp, k, nbs, noise_ndim = ctx.cfg
-        n, h, w, cin = x.shape
-        cout = W.shape[0]
+    def backward(ctx, dz, _dhi, _dlo):
+        xs, xs_lo, W, s, wm, wm_lo, dcoef, z, nz, st = ctx.saved_tensors
+        tc, up, act_gain, clamp, k, nbs, (n, h, w, cin, cout) = ctx.cfg
         taps = k * k
-        dev = x.device
+        dev = z.device
         oh, ow = z.shape[1:3]
         need = ctx.needs_input_grad
+        need_x, need_w = need[0], (need[3] or need[4])
         dzc = _f32c(dz)
-        dy = torch.empty_like(dzc)
         dbias = torch.zeros([cout], device=dev, dtype=torch.float32)
         has_noise = nz is not None
         dstr = torch.zeros([], device=dev, dtype=torch.float32) if has_noise else None
-        dnoise = torch.zeros_like(nz) if (has_noise and need[4]) else None
-        call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr), ptr(dnoise),
-             n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
-        if up == 2:
-            # adjoint of the 4x4 FIR (pad 1,1,1,1) back onto the (2h+1)x(2w+1) transposed-conv grid
-            dy = _upfirdn_nhwc_raw(dy, fir_filter(dev), (1, 1), (1, 1), (2, 2, 2, 2), True, 4.0)
-        dx = None
-        if need[0]:
-            dx = torch.empty_like(x)
-            _conv_dgrad(dy, wmod, dx, n, h, w, cin, cout, k, up)
+        dnoise = torch.zeros_like(nz) if (has_noise and need[6]) else None
+        dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
         dW = ds = None
-        if need[1] or need[2]:
-            dwmod = torch.empty_like(wmod)
-            _conv_wgrad(x, dy, dwmod, n, h, w, cin, cout, k, up)
+        if tc:
+            dp, wp = CONFIG['dgrad_passes'], CONFIG['wgrad_passes']
+            lo = (need_x and dp == 3) or (need_w and wp == 3)
+            if up == 1:
+                dy_hi, dy_lo = _bf16_like(dzc), (_bf16_like(dzc) if lo else None)
+                call('b200_layer_act_bwd', ptr(dzc), ptr(z), None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
+                     ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
+            else:
+                dy = torch.empty_like(dzc)
+                call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
+                     ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
+                # adjoint of the FIR (pad 2, flipped filter) straight to split bf16 on the (2h+1)x(2w+1) grid
+                _, dy_hi, dy_lo = _fir_fused(dy, fir_filter(dev), 1, 1, (2, 2, 2, 2), True, 4.0, want_f32=False, want_split=True, need_lo=lo)
+            if need_x:
+                call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cout, k, up, dp, stream())
+            if need_w:
+                dwmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
+                call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cout, k, up, wp, stream())
+        else:
+            dy = torch.empty_like(dzc)
+            call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr), ptr(dnoise),
+                 n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
+            if up == 2:
+                dy = _upfirdn_nhwc_raw(dy, fir_filter(dev), (1, 1), (1, 1), (2, 2, 2, 2), True, 4.0)
+            if need_x:
+                call('b200_conv_dgrad', ptr(dy), ptr(wm), ptr(dx), n, h, w, cin, cout, k, up, stream())
+            if need_w:
+                dwmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
+                call('b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cout, k, up, stream())
+        if need_w:
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
-            call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin,
-                 taps, 1, stream())
-        return dx, dW, ds, dbias, dnoise, dstr, None, None, None
+            call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin, taps, 1, stream())
+        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None
 
 
-def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp):
-    return _ModConvLayer.apply(x, weight, styles, bias, noise, strength, up, act_gain, clamp)
+def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None):
+    """Returns (z, (z_hi, z_lo) or None).  x_split: the producer's split-bf16 copies of x, if it made them."""
+    xh, xl = x_split if x_split is not None else (None, None)
+    z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
+    return z, ((zh, zl) if zh is not None else None)
 
 
 class _ToRGB(torch.autograd.Function):
     """img = [upsample2d(img_prev)] + clamp(conv1x1(x, W*styles) + bias, +-clamp)     (networks_stylegan2.py:353-357, 451-457)
 
-    x [N,H,W,Cin], weight [Cimg,Cin,1,1], styles [N,Cin] (already scaled by 1/sqrt(Cin)), img_prev [N,H/2,W/2,Cimg] or None.
+    x [N,H,W,Cin] (+ optional split copies), weight [Cimg,Cin,1,1], styles [N,Cin] (already scaled by 1/sqrt(Cin)),
+    img_prev [N,H/2,W/2,Cimg] or None.
     """
 
     @staticmethod
-    def forward(ctx, x, weight, styles, bias, img_prev, clamp):
+    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, img_prev, clamp):
         x = _f32c(x)
         n, h, w, cin = x.shape
         cimg = weight.shape[0]
         dev = x.device
         W = _f32c(weight)
         s = _f32c(styles)
-        wmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
-        call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), None, n, cimg, cin, 1, 0, stream())
+        tc_f = _tc_ok(0, h, w, cin, cimg, 1, 1)
+        tc_b = _tc_ok(1, h, w, cin, cimg, 1, 1) and _tc_ok(2, h, w, cin, cimg, 1, 1)
         y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
-        _conv_fwd(x, wmod, y, n, h, w, cin, cimg, 1, 1)
+        fp = CONFIG['fwd_passes']
+        wmod = w_hi = w_lo = None
+        if not (tc_f and tc_b):
+            wmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
+        if tc_f or tc_b:
+            w_hi = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.bfloat16)
+            w_lo = torch.empty_like(w_hi)
+        call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), ptr(w_hi), ptr(w_lo), None, n, cimg, cin, 1, 0, stream())
+        if (tc_f or tc_b) and (x_hi is None or x_lo is None):
+            x_hi, x_lo = _split(x, True)
+        if tc_f:
+            call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cimg, 1, 1, fp, stream())
+        else:
+            call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
         b = _f32c(bias)
         cl = float(clamp if clamp is not None else -1)
         call('b200_bias_act', ptr(y), ptr(b), None, None, None, ptr(y), 0, y.numel(), 1, cimg, 1, 0.0, 1.0, cl, stream())
@@ -347,42 +431,54 @@ class _ToRGB(torch.autograd.Function):
             img = _upfirdn_nhwc_raw(_f32c(img_prev), fir_filter(dev), (2, 2), (1, 1), (2, 1, 2, 1), False, 4.0, add=y)
         else:
             img = y
-        ctx.cfg = (cl, img_prev is not None)
-        ctx.save_for_backward(x, W, s, wmod, y)
+        ctx.cfg = (cl, img_prev is not None, tc_b, (n, h, w, cin, cimg))
+        if tc_b:
+            ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, y)
+        else:
+            ctx.save_for_backward(x, None, W, s, wmod, None, y)
         return img
 
     @staticmethod
     def backward(ctx, dimg):
-        x, W, s, wmod, y = ctx.saved_tensors
-        cl, has_prev = ctx.cfg
-        n, h, w, cin = x.shape
-        cimg = W.shape[0]
-        dev = x.device
+        xs, xs_lo, W, s, wm, wm_lo, y = ctx.saved_tensors
+        cl, has_prev, tc_b, (n, h, w, cin, cimg) = ctx.cfg
+        dev = y.device
         need = ctx.needs_input_grad
+        need_x, need_w = need[0], (need[3] or need[4])
         dimg = _f32c(dimg)
         dy = torch.empty_like(dimg)
         # gradient of bias+clamp uses the saved clamped output (bias_act.cu:143-145)
         call('b200_bias_act', ptr(dimg), None, None, ptr(y), None, ptr(dy), 1, dy.numel(), 1, 1, 1, 0.0, 1.0, cl, stream())
         dbias = dy.sum([0, 1, 2])
-        dx = None
-        if need[0]:
-            dx = torch.empty_like(x)
-            _conv_dgrad(dy, wmod, dx, n, h, w, cin, cimg, 1, 1)
+        dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
         dW = ds = None
-        if need[1] or need[2]:
-            dwmod = torch.empty_like(wmod)
-            _conv_wgrad(x, dy, dwmod, n, h, w, cin, cimg, 1, 1)
+        if need_w:
+            dwmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
+        if tc_b:
+            dp, wp = CONFIG['dgrad_passes'], CONFIG['wgrad_passes']
+            dy_hi, dy_lo = _split(dy, (need_x and dp == 3) or (need_w and wp == 3))
+            if need_x:
+                call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cimg, 1, 1, dp, stream())
+            if need_w:
+                call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, stream())
+        else:
+            if need_x:
+                call('b200_conv_dgrad', ptr(dy), ptr(wm), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
+            if need_w:
+                call('b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream())
+        if need_w:
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), None, ptr(dwmod), ptr(dW), ptr(ds), n, cimg, cin, 1, 0, stream())
         dprev = None
-        if has_prev and need[4]:
-            dprev = _upfirdn_nhwc_raw(dimg, fir_filter(dev), (1, 1), (2, 2), (1, 2, 1, 2), True, 4.0)
-        return dx, dW, ds, dbias, dprev, None
+        if has_prev and need[6]:
+            dprev = _upfirdn_nhwc_raw(dimg, fir_filter(dev), (1, 1), (2, 2), (1, 1, 1, 1), True, 4.0)
+        return dx, None, None, dW, ds, dbias, dprev, None
 
 
-def torgb_layer(x, weight, styles, bias, img_prev, clamp):
-    return _ToRGB.apply(x, weight, styles, bias, img_prev, clamp)
+def torgb_layer(x, weight, styles, bias, img_prev, clamp, x_split=None):
+    xh, xl = x_split if x_split is not None else (None, None)
+    return _ToRGB.apply(x, xh, xl, weight, styles, bias, img_prev, clamp)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -463,7 +559,8 @@ class _Render(torch.autograd.Function):
              *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), st)
         if density_noise > 0:
             sig_c += torch.randn_like(sig_c) * density_noise
-        minmax = torch.tensor([-1, 0], device=dev, dtype=torch.int32)
+        minmax = torch.zeros([2], device=dev, dtype=torch.int32)
+        minmax[:1].fill_(-1)                      # {0xFFFFFFFF, 0}: order-preserving uint encodings of +inf / -inf
         call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(minmax), st)
         t_f = rgb_f = sig_f = None
         if S2 > 0:

@@ -109,18 +109,31 @@ def run_b200(args):
     b200eg3d.ops.library_info()
     G, ws_h, c_h, t512_h, traw_h = make_problem(100 + rank if world > 1 else 0, dev)
     params = [p for n, p in G.named_parameters() if '.mapping.' not in n]
-    opt = torch.optim.Adam(params, lr=3e-4, fused=True)
+    opt = torch.optim.Adam(params, lr=3e-4, fused=True, capturable=not args.eager)
     host = [t.pin_memory() for t in (ws_h, c_h, t512_h, traw_h)]
     resident = [t.to(dev) for t in host]
 
-    def step(inputs):
-        ws, c, t512, traw = inputs
+    def eager_step(ws, c, t512, traw):
         out = G.synthesis(ws, c, noise_mode='const', force_fp32=True)
         loss = pti_loss(out, t512, traw)
-        opt.zero_grad(set_to_none=True)
+        if args.eager:
+            opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return loss
+
+    if args.eager:
+        def step(inputs):
+            return eager_step(*inputs)
+    else:
+        from b200eg3d.graphs import GraphedStep
+        graphed = GraphedStep(eager_step, resident, optimizer=opt, warmup=3)
+        _lib.LAUNCHES = 0
+        eager_step(*resident)                 # counts the C-ABI kernel calls one step makes (the graph replays exactly these)
+        calls_per_step = _lib.LAUNCHES
+
+        def step(inputs):
+            return graphed(*inputs)
 
     def barrier():
         if world > 1:
@@ -153,7 +166,7 @@ def run_b200(args):
         sampler.start()
     _lib.LAUNCHES = 0
     ms = timed(args.steps, e2e=False)
-    launches = _lib.LAUNCHES
+    launches = _lib.LAUNCHES if args.eager else calls_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(args.steps, e2e=True)
 
@@ -163,7 +176,8 @@ def run_b200(args):
     if rank == 0:
         _lib.PROFILE = {}
         for _ in range(2):
-            step(resident)
+            opt.zero_grad(set_to_none=True)
+            eager_step(*resident)
         torch.cuda.synchronize()
         prof = {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _lib.PROFILE.items()}
         _lib.PROFILE = None
@@ -187,7 +201,9 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
             'config': {'workload': WORKLOAD, 'parallelism': f'independent images x{world}',
                        'l2': 'per-step working set (>1 GB of activations and gradients) exceeds the 126 MB L2; no explicit flush',
-                       'loss': 'mse512 + mse128 + depth TV (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4 (fused)'},
+                       'loss': 'mse512 + mse128 + depth TV (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4 (fused)',
+                       'launch': 'eager (one Python-driven launch per kernel)' if args.eager else
+                                 'whole step captured once in a CUDA graph (b200eg3d.graphs.GraphedStep) and replayed'},
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
                     'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
@@ -254,6 +270,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     a = ap.parse_args()
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     if a.impl == 'reference':

@@ -26,7 +26,8 @@ const char* b200_last_error(void);      /* replaces TORCH_CHECK -> RuntimeError 
 
 /* w' = W * s; d = rsqrt(sum w'^2 + 1e-8); wmod = w' * d (demod != 0), written in GEMM layout.  networks_stylegan2.py:58-67.
  * W [cout][cin][taps], styles [n][cin], wmod [n][taps][cout][cin], dcoef [n][cout] (may be NULL when demod == 0). */
-int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod, float* dcoef,
+int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod /* fp32, may be NULL */,
+                             void* w_hi_bf16 /* may be NULL */, void* w_lo_bf16 /* may be NULL */, float* dcoef,
                              int n, int cout, int cin, int taps, int demod, void* stream);
 /* Backward of the above: dwmod -> dW [cout][cin][taps] (overwritten), dstyles [n][cin] (overwritten; may be NULL). */
 int b200_modconv_weight_prep_bwd(const float* W, const float* styles, const float* dcoef, const float* dwmod,
@@ -67,10 +68,12 @@ int b200_bias_act(const float* x, const float* b, const float* xref, const float
 /* SynthesisLayer epilogue on NHWC [n][hw][c]: z = clamp(lrelu(y + noise[pix]*strength + bias[c]) * gain, +-clamp)
  * (training/networks_stylegan2.py:318-329).  noise [hw] (noise_bs 0, shared 'const' buffer) or [n][hw] (noise_bs = hw) or NULL;
  * strength: device scalar; clamp < 0 disables clamping. */
-int b200_layer_act_fwd(const float* y, float* z, const float* bias, const float* noise, const float* strength, long noise_bs,
+int b200_layer_act_fwd(const float* y, float* z /* may be NULL */, void* z_hi_bf16 /* may be NULL */, void* z_lo_bf16,
+                       const float* bias, const float* noise, const float* strength, long noise_bs,
                        int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream);
 /* Backward from the saved OUTPUT z (bias_act.cu:73-77,143-145): dy, plus ACCUMULATED dbias[c], dstrength[1], dnoise (any NULL). */
-int b200_layer_act_bwd(const float* dz, const float* z, float* dy, float* dbias, const float* noise, const float* strength,
+int b200_layer_act_bwd(const float* dz, const float* z, float* dy /* may be NULL */, void* dy_hi_bf16 /* may be NULL */,
+                       void* dy_lo_bf16, float* dbias, const float* noise, const float* strength,
                        long noise_bs, float* dstrength, float* dnoise, int n, int hw, int c, int lrelu, float alpha, float gain,
                        float clamp, void* stream);
 
@@ -80,6 +83,14 @@ int b200_layer_act_bwd(const float* dz, const float* z, float* dy, float* dbias,
 int b200_upfirdn2d(const float* x, const float* f, const float* add, float* y, int n, int h, int w, int c, int fh, int fw,
                    int upx, int upy, int downx, int downy, int padx0, int padx1, int pady0, int pady1, int flip, float gain,
                    void* stream);
+
+/* Same filter geometry (square up / down factors) with fused consumers: act != 0 applies the SynthesisLayer epilogue
+ * (+ noise*strength + bias, lrelu, act_gain, clamp: conv2d_resample.py:128 followed by networks_stylegan2.py:318-329 in one pass);
+ * y (fp32) and y_hi / y_lo (split bf16 for the next tensor-core conv) are optional outputs, at least one is required. */
+int b200_upfirdn2d_fused(const float* x, const float* f, const float* add, float* y, void* y_hi_bf16, void* y_lo_bf16,
+                         int n, int h, int w, int c, int fh, int fw, int up, int down, int padx0, int padx1, int pady0, int pady1,
+                         int flip, float gain, int act, const float* bias, const float* noise, const float* strength,
+                         long noise_bs, int lrelu, float alpha, float act_gain, float clamp, void* stream);
 
 /* ---- fused tri-plane sampling + OSG decoder (renderer.py:39-66 sample_from_planes, triplane.py:124-136 OSGDecoder.forward) ---- */
 /* planes [n][hp][wp][96] (plane p = channels 32p..32p+31).  Points: coords [n][P][3], or (coords NULL) rays ray_o/ray_d

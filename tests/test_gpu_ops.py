@@ -71,7 +71,7 @@ def test_modconv_layer_fwd_bwd(b2, cin, cout, res, up, tc, monkeypatch):
 
     dev = 'cuda'
     cl = [t.detach().to(dev).requires_grad_(True) for t in (nhwc(x), W, s, b, noise, strength)]
-    z = b2.ops.modconv_layer(cl[0], cl[1], cl[2], cl[3], cl[4], cl[5], up, math.sqrt(2) * gain, clamp * gain)
+    z, _ = b2.ops.modconv_layer(cl[0], cl[1], cl[2], cl[3], cl[4], cl[5], up, math.sqrt(2) * gain, clamp * gain)
     z.backward(nhwc(dz).to(dev))
     assert maxdiff(nchw(z), z_ref) < 2e-4 * max(1.0, z_ref.abs().max().item())
     names = ['dx', 'dW', 'dstyles', 'dbias', 'dnoise', 'dstrength']
@@ -100,7 +100,7 @@ def test_modconv_layer_single_pass_backward(b2, monkeypatch):
         dzz = dz if up == 1 else torch.randn(n, cout, 2 * res, 2 * res, generator=g)
         z_ref.backward(dzz)
         cl = [t.detach().cuda().requires_grad_(True) for t in (nhwc(x), W, s)]
-        z = b2.ops.modconv_layer(cl[0], cl[1], cl[2], torch.zeros(cout, device='cuda'), None, None, up, math.sqrt(2), None)
+        z, _ = b2.ops.modconv_layer(cl[0], cl[1], cl[2], torch.zeros(cout, device='cuda'), None, None, up, math.sqrt(2), None)
         z.backward(nhwc(dzz).cuda())
         assert maxdiff(nchw(z), z_ref) < 2e-4 * z_ref.abs().max().item()
         for nm, a, r in zip(['dx', 'dW', 'ds'], cl, [nhwc(xr.grad), Wr.grad, sr.grad]):
