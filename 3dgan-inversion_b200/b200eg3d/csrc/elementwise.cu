@@ -210,6 +210,68 @@ __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restr
     }
 }
 
+// Vectorised variant for c % 4 == 0 and c <= 512: a group of G = c/4 (<= 128) threads owns one pixel, 4 channels per thread.
+// Per-thread column sums are kept in registers across the grid-stride loop (a thread always sees the same 4 channels).
+__global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __restrict__ dz, const float4* __restrict__ z,
+                                                                float4* __restrict__ dy, uint2* __restrict__ dyhi,
+                                                                uint2* __restrict__ dylo, float* __restrict__ dbias,
+                                                                const float* __restrict__ noise, const float* __restrict__ strength,
+                                                                long noise_bs, float* __restrict__ dstrength,
+                                                                float* __restrict__ dnoise, long npix, int hw, int c4, int lrelu,
+                                                                float alpha, float gain, float clamp) {
+    __shared__ float s_col[512];
+    __shared__ float s_row[256];
+    __shared__ float s_str;
+    const int ppb = blockDim.x / c4;                 // pixels per block iteration
+    const int sub = threadIdx.x / c4, cc = threadIdx.x % c4;
+    const bool active = sub < ppb;
+    for (int i = threadIdx.x; i < 4 * c4; i += blockDim.x) s_col[i] = 0.f;
+    if (threadIdx.x == 0) s_str = 0.f;
+    __syncthreads();
+    const float str = (noise && strength) ? *strength : 0.f;
+    float col[4] = {0.f, 0.f, 0.f, 0.f};
+    float sacc = 0.f;
+    for (long p0 = (long)blockIdx.x * ppb; p0 < npix; p0 += (long)gridDim.x * ppb) {
+        const long pix = p0 + sub;
+        float row = 0.f;
+        if (active && pix < npix) {
+            const long i = pix * c4 + cc;
+            const float4 zz = z[i], dd = dz[i];
+            float g[4] = {dd.x * gain, dd.y * gain, dd.z * gain, dd.w * gain};
+            const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (lrelu && !(zv[j] > 0.f)) g[j] *= alpha;
+                if (clamp >= 0.f && !(zv[j] > -clamp && zv[j] < clamp)) g[j] = 0.f;
+                col[j] += g[j];
+                row += g[j];
+            }
+            if (dy) dy[i] = make_float4(g[0], g[1], g[2], g[3]);
+            if (dyhi) split4(g, dyhi, dylo, i);
+        }
+        if (noise) {                                  // per-pixel sum over channels -> d noise, d strength
+            s_row[threadIdx.x] = row;
+            __syncthreads();
+            if (active && cc == 0 && pix < npix) {
+                float r = 0.f;
+                for (int k = 0; k < c4; ++k) r += s_row[sub * c4 + k];
+                const long nidx = (pix / hw) * noise_bs + pix % hw;
+                sacc += r * noise[nidx];
+                if (dnoise) atomicAdd(dnoise + nidx, r * str);
+            }
+            __syncthreads();
+        }
+    }
+    if (dbias && active) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(&s_col[cc * 4 + j], col[j]);
+    }
+    if (noise && dstrength && sacc != 0.f) atomicAdd(&s_str, sacc);
+    __syncthreads();
+    if (dbias) for (int i = threadIdx.x; i < 4 * c4; i += blockDim.x) atomicAdd(dbias + i, s_col[i]);
+    if (noise && dstrength && threadIdx.x == 0) atomicAdd(dstrength, s_str);
+}
+
 B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, void* dy_hi, void* dy_lo, float* dbias,
                                 const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise, int n,
                                 int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
@@ -218,6 +280,17 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, void
     if (npix <= 0 || c <= 0) return 0;
     B200_REQUIRE(c <= 512, "layer_act_bwd: at most 512 channels");
     cudaStream_t st = (cudaStream_t)stream;
+    if (c % 4 == 0) {
+        const int c4 = c / 4, ppb = 256 / c4;
+        const long nb = (npix + ppb - 1) / ppb;
+        const int blocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
+        layer_act_bwd_vec_kernel<<<blocks, 256, 0, st>>>((const float4*)dz, (const float4*)z, (float4*)dy, (uint2*)dy_hi, (uint2*)dy_lo,
+                                                         dbias, noise, strength, noise_bs, dstrength, dnoise, npix, hw, c4, lrelu,
+                                                         alpha, gain, clamp);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
+    B200_REQUIRE(!dy_hi, "layer_act_bwd: bf16 outputs need a channel count that is a multiple of 4");
     const int blocks = (int)((npix + 7) / 8 < 148 * 8 ? (npix + 7) / 8 : 148 * 8);
 #define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, dy, (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, dbias, \
                                                                      noise, strength, noise_bs, dstrength, dnoise, npix, hw, c, lrelu, \

@@ -15,48 +15,76 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return s;
 }
 
-// grid (cout, n), block 256
+// grid (cout, n), block 256, dynamic smem = cin*taps floats (the modulated row W[o]*s, staged once: the global read
+// is coalesced in the parameter layout [i][t], the writes are coalesced in the GEMM layout [t][i]).
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ W, const float* __restrict__ styles,
                                                           float* __restrict__ wmod, __nv_bfloat16* __restrict__ whi,
                                                           __nv_bfloat16* __restrict__ wlo, float* __restrict__ dcoef,
                                                           int cout, int cin, int taps, int demod) {
+    extern __shared__ float sW[];
     __shared__ float red[32];
     const int o = blockIdx.x, n = blockIdx.y;
     const float* Wo = W + (long)o * cin * taps;
     const float* s = styles + (long)n * cin;
+    float acc = 0.f;
+    for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
+        const float v = Wo[idx] * s[idx / taps];
+        sW[idx] = v;
+        acc = fmaf(v, v, acc);
+    }
     float d = 1.f;
     if (demod) {
-        float acc = 0.f;
-        for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
-            const float v = Wo[idx] * s[idx / taps];
-            acc = fmaf(v, v, acc);
-        }
         acc = block_sum(acc, red);
         d = rsqrtf(acc + 1e-8f);
         if (threadIdx.x == 0 && dcoef) dcoef[(long)n * cout + o] = d;
+    } else {
+        __syncthreads();
     }
     const long ob = (long)n * taps * cout * cin;
-    for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
-        const int t = idx / cin, i = idx % cin;
-        const float v = Wo[i * taps + t] * s[i] * d;
-        const long oi = ob + ((long)t * cout + o) * cin + i;
-        if (wmod) wmod[oi] = v;
-        if (whi) {
-            const __nv_bfloat16 hh = __float2bfloat16_rn(v);
-            whi[oi] = hh;
-            if (wlo) wlo[oi] = __float2bfloat16_rn(v - __bfloat162float(hh));
+    if ((cin & 1) == 0) {
+        const int half = cin >> 1;
+        for (int idx = threadIdx.x; idx < half * taps; idx += blockDim.x) {
+            const int t = idx / half, i = (idx % half) * 2;
+            const float v0 = sW[i * taps + t] * d, v1 = sW[(i + 1) * taps + t] * d;
+            const long oi = ob + ((long)t * cout + o) * cin + i;
+            if (wmod) *reinterpret_cast<float2*>(wmod + oi) = make_float2(v0, v1);
+            if (whi) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+                *reinterpret_cast<__nv_bfloat162*>(whi + oi) = hh;
+                if (wlo) *reinterpret_cast<__nv_bfloat162*>(wlo + oi) =
+                    __floats2bfloat162_rn(v0 - __low2float(hh), v1 - __high2float(hh));
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
+            const int t = idx / cin, i = idx % cin;
+            const float v = sW[i * taps + t] * d;
+            const long oi = ob + ((long)t * cout + o) * cin + i;
+            if (wmod) wmod[oi] = v;
+            if (whi) {
+                const __nv_bfloat16 hh = __float2bfloat16_rn(v);
+                whi[oi] = hh;
+                if (wlo) wlo[oi] = __float2bfloat16_rn(v - __bfloat162float(hh));
+            }
         }
     }
 }
 
-// grid (cout), block 256.  dW is written (not accumulated); dstyles must be zeroed by the caller (atomics).
+// grid (cout), block 256, dynamic smem = 2*cin*taps floats.  dW is written (not accumulated); dstyles must be zeroed by
+// the caller (atomics).  The parameter row W[o] and the outgoing dW[o] row are staged in shared memory so that every
+// global access is coalesced.
 __global__ void __launch_bounds__(256) weight_prep_bwd_kernel(const float* __restrict__ W, const float* __restrict__ styles,
                                                               const float* __restrict__ dcoef, const float* __restrict__ dwmod,
                                                               float* __restrict__ dW, float* __restrict__ dstyles,
                                                               int nb, int cout, int cin, int taps, int demod) {
+    extern __shared__ float sm[];
+    float* sW = sm;                       // W[o][i][t]
+    float* sD = sm + cin * taps;          // dW[o][i][t]
     __shared__ float red[32];
     const int o = blockIdx.x;
     const float* Wo = W + (long)o * cin * taps;
+    for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) { sW[idx] = Wo[idx]; sD[idx] = 0.f; }
+    __syncthreads();
     for (int n = 0; n < nb; ++n) {
         const float* s = styles + (long)n * cin;
         const float* G = dwmod + (long)n * taps * cout * cin;
@@ -66,7 +94,7 @@ __global__ void __launch_bounds__(256) weight_prep_bwd_kernel(const float* __res
             float acc = 0.f;
             for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
                 const int t = idx / cin, i = idx % cin;
-                acc = fmaf(G[((long)t * cout + o) * cin + i], Wo[i * taps + t] * s[i], acc);
+                acc = fmaf(G[((long)t * cout + o) * cin + i], sW[i * taps + t] * s[i], acc);
             }
             dot = block_sum(acc, red);
         }
@@ -75,24 +103,28 @@ __global__ void __launch_bounds__(256) weight_prep_bwd_kernel(const float* __res
             const float si = s[i];
             float ds = 0.f;
             for (int t = 0; t < taps; ++t) {
-                const float w = Wo[i * taps + t];
+                const float w = sW[i * taps + t];
                 float g = G[((long)t * cout + o) * cin + i] * d;
                 if (demod) g -= d3dot * w * si;
                 ds = fmaf(w, g, ds);
-                float* dst = dW + ((long)o * cin + i) * taps + t;
-                if (n == 0) *dst = si * g; else *dst += si * g;
+                sD[i * taps + t] += si * g;
             }
             if (dstyles) atomicAdd(dstyles + (long)n * cin + i, ds);
         }
     }
+    __syncthreads();
+    float* dWo = dW + (long)o * cin * taps;
+    for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) dWo[idx] = sD[idx];
 }
 
 B200_API int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod, void* w_hi, void* w_lo, float* dcoef,
                                       int n, int cout, int cin, int taps, int demod, void* stream) {
     B200_REQUIRE(n > 0 && cout > 0 && cin > 0 && taps > 0, "weight_prep: bad shape");
     B200_REQUIRE(wmod || w_hi, "weight_prep: no output requested");
-    weight_prep_kernel<<<dim3(cout, n), 256, 0, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
-                                                                        dcoef, cout, cin, taps, demod);
+    const size_t smem = sizeof(float) * (size_t)cin * taps;
+    B200_REQUIRE(smem <= 48 * 1024, "weight_prep: cin*taps too large for the staging tile");
+    weight_prep_kernel<<<dim3(cout, n), 256, smem, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
+                                                                           dcoef, cout, cin, taps, demod);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -103,7 +135,9 @@ B200_API int b200_modconv_weight_prep_bwd(const float* W, const float* styles, c
     B200_REQUIRE(n > 0 && cout > 0 && cin > 0 && taps > 0, "weight_prep_bwd: bad shape");
     B200_REQUIRE(!demod || dcoef, "weight_prep_bwd: demodulation needs the saved coefficients");
     if (dstyles) B200_CUDA(cudaMemsetAsync(dstyles, 0, sizeof(float) * (size_t)n * cin, (cudaStream_t)stream));
-    weight_prep_bwd_kernel<<<cout, 256, 0, (cudaStream_t)stream>>>(W, styles, dcoef, dwmod, dW, dstyles, n, cout, cin, taps, demod);
+    const size_t smem = 2 * sizeof(float) * (size_t)cin * taps;
+    B200_REQUIRE(smem <= 48 * 1024, "weight_prep_bwd: cin*taps too large for the staging tiles");
+    weight_prep_bwd_kernel<<<cout, 256, smem, (cudaStream_t)stream>>>(W, styles, dcoef, dwmod, dW, dstyles, n, cout, cin, taps, demod);
     B200_CHECK_LAUNCH();
     return 0;
 }
