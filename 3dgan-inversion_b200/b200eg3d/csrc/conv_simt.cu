@@ -222,6 +222,59 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(ConvWgradParams p) {
     }
 }
 
+// Thin 1x1 weight gradient (Cm <= 4 output channels, e.g. the 3-channel ToRGB of the super-resolution blocks):
+// dW[m][n] = sum_pixels dy[pixel][m] * x[pixel][n].  Pure streaming reduction over x (HBM-bound); a 128x128 GEMM tile
+// would waste 97% of its rows.
+__global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              float* __restrict__ dW, long npix, int cm, int cn, long x_bs,
+                                                              long dy_bs, long c_bs) {
+    __shared__ float red[4 * 512];
+    const int b = blockIdx.y;
+    x += (long)b * x_bs; dy += (long)b * dy_bs; dW += (long)b * c_bs;
+    const int c4 = cn >> 2, ppb = blockDim.x / c4;
+    const int sub = threadIdx.x / c4, cc = threadIdx.x % c4;
+    float acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+    if (sub < ppb) {
+        for (long pix = (long)blockIdx.x * ppb + sub; pix < npix; pix += (long)gridDim.x * ppb) {
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + pix * cn) + cc);
+            const float* d = dy + pix * cm;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                if (m < cm) {
+                    const float dv = __ldg(d + m);
+                    acc[m][0] = fmaf(dv, xv.x, acc[m][0]); acc[m][1] = fmaf(dv, xv.y, acc[m][1]);
+                    acc[m][2] = fmaf(dv, xv.z, acc[m][2]); acc[m][3] = fmaf(dv, xv.w, acc[m][3]);
+                }
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < 4 * cn; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    if (sub < ppb) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (m < cm)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(&red[m * cn + cc * 4 + j], acc[m][j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < cm * cn; i += blockDim.x) atomicAdd(dW + i, red[i]);
+}
+
+int launch_conv_wgrad_thin(const float* x, const float* dy, float* dW, int batch, long npix, int cm, int cn, cudaStream_t st) {
+    B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)batch * cm * cn, st));
+    const int ppb = 256 / (cn / 4);
+    const long nb = (npix + ppb - 1) / ppb;
+    dim3 grid((unsigned)(nb < 148 * 4 ? nb : 148 * 4), batch);
+    conv_wgrad_thin_kernel<<<grid, 256, 0, st>>>(x, dy, dW, npix, cm, cn, npix * cn, npix * cm, (long)cm * cn);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
 int launch_conv_pix_simt(const ConvPixParams& p, int batch, cudaStream_t st) {
     const int M = p.g.Hi * p.g.Wi;
     if (M <= 0 || p.N <= 0 || batch <= 0) return 0;

@@ -10,6 +10,7 @@
 //   MLP    : lane == point, weights broadcast from shared memory (LDS.128), activations in registers
 // The two phases are stitched with a per-warp shared-memory transpose.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 constexpr int C = 32, HID = 64, OUT = 33, PC = 96;
@@ -36,6 +37,7 @@ struct TriplaneParams {
     const float* d_rgb; const float* d_sigma;
     float* d_planes; float* d_coords;
     float* dW1; float* db1; float* dW2; float* db2;
+    int fwd_passes;                                         // 3: split-TF32 (default), 1: plain TF32 (experiments)
 };
 
 struct Bilin {
@@ -163,6 +165,7 @@ __device__ __forceinline__ void tex4_scatter(float* __restrict__ p, float bw, fl
 }
 
 // gather the 32-channel mean feature of the warp's 32 points into sf[q*SA + channel] (lane == channel)
+template <int STRIDE = SA>
 __device__ __forceinline__ void gather_features(const TriplaneParams& p, const float* __restrict__ pl, const float* ss, float* sf,
                                                 int lane) {
     const int rs = p.wp * PC;
@@ -171,7 +174,7 @@ __device__ __forceinline__ void gather_features(const TriplaneParams& p, const f
     for (int q = 0; q < 32; ++q) {
         const float4 s0 = *reinterpret_cast<const float4*>(&ss[q * SP]), s1 = *reinterpret_cast<const float4*>(&ss[q * SP + 4]);
         const float4 s2 = *reinterpret_cast<const float4*>(&ss[q * SP + 8]), s3 = *reinterpret_cast<const float4*>(&ss[q * SP + 12]);
-        sf[q * SA + lane] = tex4(pc, s0.x, s0.y, s0.z, s0.w, s1.x, rs) + tex4(pc, s1.y, s1.z, s1.w, s2.x, s2.y, rs) +
+        sf[q * STRIDE + lane] = tex4(pc, s0.x, s0.y, s0.z, s0.w, s1.x, rs) + tex4(pc, s1.y, s1.z, s1.w, s2.x, s2.y, rs) +
                             tex4(pc, s2.z, s2.w, s3.x, s3.y, s3.z, rs);
     }
 }
@@ -236,6 +239,163 @@ __global__ void __launch_bounds__(128) triplane_mlp_fwd_kernel(TriplaneParams p)
         const int cnt = (int)min((long)32, p.P - base);
         float* out = p.rgb + ((long)n * p.P + base) * C;
         for (int q = 0; q < cnt; ++q) out[q * C + lane] = sf[q * SA + lane];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core decoder: the two FC layers of a warp's 32 points as mma.sync.m16n8k8 TF32 tiles with split-float operands
+// (x = hi + lo, three MMAs per product: lo*hi + hi*lo + hi*hi, fp32 accumulate -> ~fp32 accuracy).
+//   layer 1: H[32x64] = F[32x32] * W1^T   (2 m-tiles x 8 n-tiles x 4 k-steps)
+//   layer 2: O[32x40] = H[32x64] * W2^T   (2 m-tiles x 5 n-tiles x 8 k-steps; rows 33..39 of W2 are zero padding)
+// Fragment layout (PTX ISA, m16n8k8 .tf32): g = lane/4, t = lane%4
+//   A: a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4)     B: b0 (k=t, n=g) b1 (k=t+4, n=g)     C: c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+// Shared-memory strides 36 / 68 (= 4 mod 32) make every fragment load bank-conflict free.
+// The hidden layer never touches shared memory: layer 1's C fragment gives lane (g,t) the hidden units {8*nt + 2t, 8*nt + 2t+1}
+// of rows g / g+8, and layer 2 consumes exactly these as its A fragment (a0 = c0, a1 = c2, a2 = c1, a3 = c3) when the k-slots
+// (t, t+4) of k-step nt are DEFINED to be those two units -- i.e. layer 2's B fragment reads W2[n][8*ks + 2t], W2[n][8*ks + 2t+1].
+constexpr int SF = 36, SW2 = 72, OUTP = 40;
+constexpr int FW_W = 2 * HID * SF + 2 * OUTP * SW2 + HID + OUTP;          // W1 hi|lo, W2 hi|lo, b1, b2 (floats)
+constexpr int FW_WARP = 32 * SF + 32 * SP;
+constexpr int FW_WARPS = 16;
+constexpr int FW_SMEM = (FW_W + FW_WARPS * FW_WARP) * 4;
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// W1 -> [64][SF] hi / lo (tf32 bit patterns), W2 -> [OUTP][SW2] hi / lo with zero rows 33..39, biases
+__device__ __forceinline__ void load_weights_split(const TriplaneParams& p, float* W1h, float* W1l, float* W2h, float* W2l,
+                                                   float* b1s, float* b2s) {
+    for (int i = threadIdx.x; i < HID * C; i += blockDim.x) {
+        uint32_t h, l;
+        tf32_split(p.W1[i] * p.w1g, h, l);
+        const int o = (i / C) * SF + (i % C);
+        W1h[o] = __uint_as_float(h); W1l[o] = __uint_as_float(l);
+    }
+    for (int i = threadIdx.x; i < OUTP * HID; i += blockDim.x) {
+        const int k = i / HID, j = i % HID;
+        uint32_t h = 0, l = 0;
+        if (k < OUT) tf32_split(p.W2[i] * p.w2g, h, l);
+        W2h[k * SW2 + j] = __uint_as_float(h); W2l[k * SW2 + j] = __uint_as_float(l);
+    }
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) b1s[i] = p.b1[i] * p.b1g;
+    for (int i = threadIdx.x; i < OUTP; i += blockDim.x) b2s[i] = i < OUT ? p.b2[i] * p.b2g : 0.f;
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(TriplaneParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* W1h = smem; float* W1l = W1h + HID * SF; float* W2h = W1l + HID * SF; float* W2l = W2h + OUTP * SW2;
+    float* b1s = W2l + OUTP * SW2; float* b2s = b1s + HID;
+    const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float* sF = smem + FW_W + wid * FW_WARP;     // [32][SF]  features, later the output staging tile
+    float* ss = sF + 32 * SF;                    // [32][SP]  bilinear set-up
+    load_weights_split(p, W1h, W1l, W2h, W2l, b1s, b2s);
+    __syncthreads();
+    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
+    for (long base = ((long)blockIdx.x * FW_WARPS + wid) * 32; base < p.P; base += (long)gridDim.x * (FW_WARPS * 32)) {
+        const long pi = base + lane;
+        float cx, cy, cz;
+        point_coords(p, n, pi, cx, cy, cz);
+        stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
+        __syncwarp();
+        gather_features<SF>(p, pl, ss, sF, lane);
+        __syncwarp();
+        // ---- layer 1: 16 independent accumulator tiles (2 m-tiles x 8 n-tiles), k-steps outermost
+        float c[2][8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float bv0 = b1s[8 * nt + 2 * t], bv1 = b1s[8 * nt + 2 * t + 1];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { c[mt][nt][0] = c[mt][nt][2] = bv0; c[mt][nt][1] = c[mt][nt][3] = bv1; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float* r0 = sF + (g + 16 * mt) * SF + t + 8 * ks;
+                tf32_split(r0[0], ah[mt][0], al[mt][0]);
+                tf32_split(r0[8 * SF], ah[mt][1], al[mt][1]);
+                tf32_split(r0[4], ah[mt][2], al[mt][2]);
+                tf32_split(r0[8 * SF + 4], ah[mt][3], al[mt][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int bo = (g + 8 * nt) * SF + t + 8 * ks;
+                const uint32_t bh0 = __float_as_uint(W1h[bo]), bh1 = __float_as_uint(W1h[bo + 4]);
+                const uint32_t bl0 = __float_as_uint(W1l[bo]), bl1 = __float_as_uint(W1l[bo + 4]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (p.fwd_passes == 3) {
+                        mma_tf32(c[mt][nt], al[mt], bh0, bh1);
+                        mma_tf32(c[mt][nt], ah[mt], bl0, bl1);
+                    }
+                    mma_tf32(c[mt][nt], ah[mt], bh0, bh1);
+                }
+            }
+        }
+        __syncwarp();                            // all lanes are done reading the feature tile
+        // ---- layer 2: A fragments come straight from layer 1's accumulators (see the note above)
+        float o[2][5][4];
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) {
+            const float bv0 = b2s[8 * nt + 2 * t], bv1 = b2s[8 * nt + 2 * t + 1];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { o[mt][nt][0] = o[mt][nt][2] = bv0; o[mt][nt][1] = o[mt][nt][3] = bv1; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t hh[2][4], hl[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                tf32_split(softplus_fast(c[mt][ks][0]), hh[mt][0], hl[mt][0]);     // (row g,   unit 8ks+2t)
+                tf32_split(softplus_fast(c[mt][ks][2]), hh[mt][1], hl[mt][1]);     // (row g+8, unit 8ks+2t)
+                tf32_split(softplus_fast(c[mt][ks][1]), hh[mt][2], hl[mt][2]);     // (row g,   unit 8ks+2t+1)
+                tf32_split(softplus_fast(c[mt][ks][3]), hh[mt][3], hl[mt][3]);     // (row g+8, unit 8ks+2t+1)
+            }
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                const int bo = (g + 8 * nt) * SW2 + 8 * ks + 2 * t;
+                const float2 bh = *reinterpret_cast<const float2*>(&W2h[bo]);
+                const float2 bl = *reinterpret_cast<const float2*>(&W2l[bo]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    if (p.fwd_passes == 3) {
+                        mma_tf32(o[mt][nt], hl[mt], __float_as_uint(bh.x), __float_as_uint(bh.y));
+                        mma_tf32(o[mt][nt], hh[mt], __float_as_uint(bl.x), __float_as_uint(bl.y));
+                    }
+                    mma_tf32(o[mt][nt], hh[mt], __float_as_uint(bh.x), __float_as_uint(bh.y));
+                }
+            }
+        }
+        // ---- epilogue: column 0 = sigma (linear), columns 1..32 = rgb = sigmoid(o)*1.002 - 0.001; staged in sF
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int row = g + 16 * mt + ((i & 2) ? 8 : 0), col = 8 * nt + 2 * t + (i & 1);
+                    if (col < OUT) sF[row * SF + col] = col == 0 ? o[mt][nt][i] : sigmoid_fast(o[mt][nt][i]) * 1.002f - 0.001f;
+                }
+        __syncwarp();
+        if (pi < p.P) p.sigma[(long)n * p.P + pi] = sF[lane * SF];
+        const int cnt = (int)min((long)32, p.P - base);
+        float* out = p.rgb + ((long)n * p.P + base) * C;
+        for (int q = 0; q < cnt; ++q) out[q * C + lane] = sF[q * SF + 1 + lane];
         __syncwarp();
     }
 }
@@ -438,6 +598,340 @@ __global__ void __launch_bounds__(128, 2) triplane_mlp_bwd_kernel(TriplaneParams
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core backward of the fused sampler + decoder (mma.sync m16n8k8 TF32, single pass: gradients need ~1e-3 relative
+// accuracy, the forward keeps the 3-pass split).  Per warp and 32 points:
+//   recompute   C1 = F W1^T (+b1), h = softplus(C1);  O = h W2^T (+b2)             [h feeds layer 2 from registers]
+//   d_out       dO = d_rgb * 1.002 * s(1-s) | d_sigma                               [C-fragment layout of O]
+//   chain       dh = dO W2  -> d_a = dh * (1 - exp(-h)) -> d_f = d_a W1             [A fragments straight from registers]
+//   parameters  dW2 += dO^T h, dW1 += d_a^T F (operands transposed through shared memory), db2, db1
+//   scatter     d_f (x bilinear weights, 1/3 folded in) -> red.global into the plane gradient
+constexpr int BSH = 72, BSO = 40, BM_WARPS = 8;
+constexpr int BM_W = HID * SF + OUTP * SW2 + HID + OUTP;                    // W1 [64][36], W2 [40][72], b1, b2
+constexpr int BM_WPAD = (BM_W + 3) / 4 * 4;
+constexpr int BM_WARP = 32 * SF + 32 * BSH + 32 * BSO + 16 + 32 * SP;       // f | h, d_a | d_out, d_f (+pad) | set-up
+constexpr int BM_SMEM = (BM_WPAD + BW_ACCPAD + BM_WARPS * BM_WARP) * 4;
+
+__global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(TriplaneParams p) {
+    extern __shared__ __align__(16) float smem[];
+    float* W1s = smem; float* W2s = W1s + HID * SF; float* b1s = W2s + OUTP * SW2; float* b2s = b1s + HID;
+    float* acc = smem + BM_WPAD;
+    float* aW1 = acc; float* ab1 = aW1 + HID * C; float* aW2 = ab1 + HID; float* ab2 = aW2 + OUT * HID;
+    const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    float* sF = smem + BM_WPAD + BW_ACCPAD + wid * BM_WARP;    // [32][SF]
+    float* sH = sF + 32 * SF;                                  // [32][BSH]
+    float* sO = sH + 32 * BSH;                                 // [32][BSO] (+16 pad)
+    float* ss = sO + 32 * BSO + 16;                            // [32][SP]
+    const bool wgrad = p.dW1 != nullptr;
+    for (int i = threadIdx.x; i < HID * C; i += blockDim.x) W1s[(i / C) * SF + (i % C)] = __uint_as_float(tf32_rna(p.W1[i] * p.w1g));
+    for (int i = threadIdx.x; i < OUTP * HID; i += blockDim.x) {
+        const int k = i / HID, j = i % HID;
+        W2s[k * SW2 + j] = k < OUT ? __uint_as_float(tf32_rna(p.W2[i] * p.w2g)) : 0.f;
+    }
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) b1s[i] = p.b1[i] * p.b1g;
+    for (int i = threadIdx.x; i < OUTP; i += blockDim.x) b2s[i] = i < OUT ? p.b2[i] * p.b2g : 0.f;
+    for (int i = threadIdx.x; i < BW_ACC; i += blockDim.x) acc[i] = 0.f;
+    if (lane < 16) sO[32 * BSO + lane] = 0.f;
+    __syncthreads();
+    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
+    float* dpl = p.d_planes ? p.d_planes + (long)n * p.hp * p.wp * PC : nullptr;
+
+    for (long base = ((long)blockIdx.x * BM_WARPS + wid) * 32; base < p.P; base += (long)gridDim.x * (BM_WARPS * 32)) {
+        const long pi = base + lane;
+        const bool valid = pi < p.P;
+        const int cnt = (int)min((long)32, p.P - base);
+        float cx, cy, cz;
+        point_coords(p, n, pi, cx, cy, cz);
+        stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
+        __syncwarp();
+        gather_features<SF>(p, pl, ss, sF, lane);
+        {   // incoming gradients -> sO[point][0] = d_sigma, [1..32] = d_rgb, [33..39] = 0
+            const float* gsrc = p.d_rgb + ((long)n * p.P + base) * C;
+            for (int q = 0; q < 32; ++q) {
+                sO[q * BSO + 1 + lane] = q < cnt ? gsrc[q * C + lane] : 0.f;
+                if (lane < 7) sO[q * BSO + 33 + lane] = 0.f;
+            }
+            sO[lane * BSO] = valid ? p.d_sigma[(long)n * p.P + pi] : 0.f;
+        }
+        __syncwarp();
+        // ---- layer 1 (recompute): c1 = b1 + F W1^T, then h = softplus(c1) kept in the accumulator registers
+        float c1[2][8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const float bv0 = b1s[8 * nt + 2 * t], bv1 = b1s[8 * nt + 2 * t + 1];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { c1[mt][nt][0] = c1[mt][nt][2] = bv0; c1[mt][nt][1] = c1[mt][nt][3] = bv1; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            uint32_t a[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float* r0 = sF + (g + 16 * mt) * SF + t + 8 * ks;
+                a[mt][0] = tf32_rna(r0[0]); a[mt][1] = tf32_rna(r0[8 * SF]); a[mt][2] = tf32_rna(r0[4]); a[mt][3] = tf32_rna(r0[8 * SF + 4]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int bo = (g + 8 * nt) * SF + t + 8 * ks;
+                const uint32_t b0 = __float_as_uint(W1s[bo]), b1 = __float_as_uint(W1s[bo + 4]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(c1[mt][nt], a[mt], b0, b1);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c1[mt][nt][i] = softplus_fast(c1[mt][nt][i]);
+                if (wgrad) {
+                    float* h0 = sH + (g + 16 * mt) * BSH + 8 * nt + 2 * t;
+                    *reinterpret_cast<float2*>(h0) = make_float2(c1[mt][nt][0], c1[mt][nt][1]);
+                    *reinterpret_cast<float2*>(h0 + 8 * BSH) = make_float2(c1[mt][nt][2], c1[mt][nt][3]);
+                }
+            }
+        // ---- layer 2 (recompute) from registers, then d_out in place
+        float o[2][5][4];
+#pragma unroll
+        for (int nt = 0; nt < 5; ++nt) {
+            const float bv0 = b2s[8 * nt + 2 * t], bv1 = b2s[8 * nt + 2 * t + 1];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) { o[mt][nt][0] = o[mt][nt][2] = bv0; o[mt][nt][1] = o[mt][nt][3] = bv1; }
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            uint32_t a[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                a[mt][0] = tf32_rna(c1[mt][ks][0]); a[mt][1] = tf32_rna(c1[mt][ks][2]);
+                a[mt][2] = tf32_rna(c1[mt][ks][1]); a[mt][3] = tf32_rna(c1[mt][ks][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                const float2 b = *reinterpret_cast<const float2*>(&W2s[(g + 8 * nt) * SW2 + 8 * ks + 2 * t]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][nt], a[mt], __float_as_uint(b.x), __float_as_uint(b.y));
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int row = g + 16 * mt + 8 * hh, col = 8 * nt + 2 * t;
+                    float2 d = *reinterpret_cast<const float2*>(&sO[row * BSO + col]);
+                    const float s0 = sigmoid_fast(o[mt][nt][2 * hh]), s1 = sigmoid_fast(o[mt][nt][2 * hh + 1]);
+                    d.x = col == 0 ? d.x : d.x * 1.002f * s0 * (1.f - s0);          // col 0 = sigma (linear)
+                    d.y = d.y * 1.002f * s1 * (1.f - s1);
+                    if (col + 1 >= OUT) d.y = 0.f;
+                    if (col >= OUT) d.x = 0.f;
+                    o[mt][nt][2 * hh] = d.x; o[mt][nt][2 * hh + 1] = d.y;
+                    if (wgrad) *reinterpret_cast<float2*>(&sO[row * BSO + col]) = d;
+                }
+        __syncwarp();
+        // ---- dW2[k][j] += sum_pt d_out[pt][k] h[pt][j]   (M = k: 3 m-tiles, N = j: 8 n-tiles, K = points: 4 k-steps), db2
+        if (wgrad) {
+            float cw[3][8][4];
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cw[mt][nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a[3][4];
+#pragma unroll
+                for (int mt = 0; mt < 3; ++mt) {
+                    const float* r0 = sO + (t + 8 * ks) * BSO + g + 16 * mt;
+                    a[mt][0] = tf32_rna(r0[0]); a[mt][1] = tf32_rna(r0[8]); a[mt][2] = tf32_rna(r0[4 * BSO]); a[mt][3] = tf32_rna(r0[4 * BSO + 8]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float* r0 = sH + (t + 8 * ks) * BSH + g + 8 * nt;
+                    const uint32_t b0 = tf32_rna(r0[0]), b1 = tf32_rna(r0[4 * BSH]);
+#pragma unroll
+                    for (int mt = 0; mt < 3; ++mt) mma_tf32(cw[mt][nt], a[mt], b0, b1);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int k = g + 16 * mt + ((i & 2) ? 8 : 0), j = 8 * nt + 2 * t + (i & 1);
+                        if (k < OUT) atomicAdd(&aW2[k * HID + j], cw[mt][nt][i]);
+                    }
+            float sb = 0.f, sb32 = 0.f;
+            for (int q = 0; q < 32; ++q) { sb += sO[q * BSO + lane]; sb32 += sO[q * BSO + 32]; }
+            atomicAdd(&ab2[lane], sb);
+            if (lane == 0) atomicAdd(&ab2[32], sb32);
+        }
+        // ---- dh = d_out W2 (K = 40: the 5 n-tiles of O are the k-steps), d_a = dh * (1 - exp(-h)) in place of h
+        {
+            float dh[2][8][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dh[mt][nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 5; ++ks) {
+                uint32_t a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    a[mt][0] = tf32_rna(o[mt][ks][0]); a[mt][1] = tf32_rna(o[mt][ks][2]);
+                    a[mt][2] = tf32_rna(o[mt][ks][1]); a[mt][3] = tf32_rna(o[mt][ks][3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const float* r0 = W2s + (8 * ks + 2 * t) * SW2 + g + 8 * nt;
+                    const uint32_t b0 = __float_as_uint(r0[0]), b1 = __float_as_uint(r0[SW2]);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) mma_tf32(dh[mt][nt], a[mt], b0, b1);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c1[mt][nt][i] = dh[mt][nt][i] * (1.f - __expf(-c1[mt][nt][i]));
+        }
+        // ---- dW1[j][c] += sum_pt d_a[pt][j] f[pt][c]   (M = j: 4 m-tiles, N = c: 4 n-tiles, K = points), db1
+        if (wgrad) {
+            __syncwarp();                         // every lane finished reading h from sH
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    float* h0 = sH + (g + 16 * mt) * BSH + 8 * nt + 2 * t;
+                    *reinterpret_cast<float2*>(h0) = make_float2(c1[mt][nt][0], c1[mt][nt][1]);
+                    *reinterpret_cast<float2*>(h0 + 8 * BSH) = make_float2(c1[mt][nt][2], c1[mt][nt][3]);
+                }
+            __syncwarp();
+            float cw[4][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) cw[mt][nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                uint32_t b[4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float* r0 = sF + (t + 8 * ks) * SF + g + 8 * nt;
+                    b[nt][0] = tf32_rna(r0[0]); b[nt][1] = tf32_rna(r0[4 * SF]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    const float* r0 = sH + (t + 8 * ks) * BSH + g + 16 * mt;
+                    uint32_t a[4] = {tf32_rna(r0[0]), tf32_rna(r0[8]), tf32_rna(r0[4 * BSH]), tf32_rna(r0[4 * BSH + 8])};
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma_tf32(cw[mt][nt], a, b[nt][0], b[nt][1]);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        atomicAdd(&aW1[(g + 16 * mt + ((i & 2) ? 8 : 0)) * C + 8 * nt + 2 * t + (i & 1)], cw[mt][nt][i]);
+            float s0 = 0.f, s1 = 0.f;
+            for (int q = 0; q < 32; ++q) { s0 += sH[q * BSH + lane]; s1 += sH[q * BSH + 32 + lane]; }
+            atomicAdd(&ab1[lane], s0); atomicAdd(&ab1[32 + lane], s1);
+        }
+        // ---- d_f = d_a W1 (K = 64: the 8 n-tiles of layer 1 are the k-steps) -> staging tile sO[point][channel]
+        {
+            float df[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) df[mt][nt][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                uint32_t a[2][4];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    a[mt][0] = tf32_rna(c1[mt][ks][0]); a[mt][1] = tf32_rna(c1[mt][ks][2]);
+                    a[mt][2] = tf32_rna(c1[mt][ks][1]); a[mt][3] = tf32_rna(c1[mt][ks][3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float* r0 = W1s + (8 * ks + 2 * t) * SF + g + 8 * nt;
+                    const uint32_t b0 = __float_as_uint(r0[0]), b1 = __float_as_uint(r0[SF]);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) mma_tf32(df[mt][nt], a[mt], b0, b1);
+                }
+            }
+            __syncwarp();                         // dW2 / db2 finished reading sO
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int row = g + 16 * mt + 8 * hh;
+                        const bool rv = base + row < p.P;
+                        *reinterpret_cast<float2*>(&sO[row * BSO + 8 * nt + 2 * t]) =
+                            rv ? make_float2(df[mt][nt][2 * hh], df[mt][nt][2 * hh + 1]) : make_float2(0.f, 0.f);
+                    }
+        }
+        __syncwarp();
+        // ---- scatter d_f (lane == channel; the 1/3 of the plane mean is folded into the staged weights)
+        if (dpl) {
+            const int rs = p.wp * PC;
+            float* dc = dpl + lane;
+#pragma unroll 2
+            for (int q = 0; q < cnt; ++q) {
+                const float4 s0 = *reinterpret_cast<const float4*>(&ss[q * SP]), s1 = *reinterpret_cast<const float4*>(&ss[q * SP + 4]);
+                const float4 s2 = *reinterpret_cast<const float4*>(&ss[q * SP + 8]), s3 = *reinterpret_cast<const float4*>(&ss[q * SP + 12]);
+                const float gq = sO[q * BSO + lane];
+                tex4_scatter(dc, s0.x, s0.y, s0.z, s0.w, s1.x, rs, gq);
+                tex4_scatter(dc, s1.y, s1.z, s1.w, s2.x, s2.y, rs, gq);
+                tex4_scatter(dc, s2.z, s2.w, s3.x, s3.y, s3.z, rs, gq);
+            }
+        }
+        if (p.d_coords) {
+            for (int q = 0; q < cnt; ++q) {
+                const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
+                const Bilin b0 = make_bilin(gx, gy, p.hp, p.wp), b1 = make_bilin(gx, gz, p.hp, p.wp), b2 = make_bilin(gz, gx, p.hp, p.wp);
+                const float gq = sO[q * BSO + lane] * (1.f / 3.f);
+                float ax, ay, bx, by, ex, ey;
+                bilin_dcoord(pl + lane, b0, p.wp, ax, ay);
+                bilin_dcoord(pl + C + lane, b1, p.wp, bx, by);
+                bilin_dcoord(pl + 2 * C + lane, b2, p.wp, ex, ey);
+                const float hx = 0.5f * p.wp, hy = 0.5f * p.hp;
+                float dx = gq * (ax * hx + bx * hx + ey * hy);
+                float dy = gq * (ay * hy);
+                float dz = gq * (by * hy + ex * hx);
+                dx = warp_sum(dx); dy = warp_sum(dy); dz = warp_sum(dz);
+                if (lane == 0) {
+                    float* dcq = p.d_coords + ((long)n * p.P + base + q) * 3;
+                    dcq[0] = dx * p.coord_scale; dcq[1] = dy * p.coord_scale; dcq[2] = dz * p.coord_scale;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (wgrad) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < HID * C; i += blockDim.x) atomicAdd(p.dW1 + i, aW1[i] * p.w1g);
+        for (int i = threadIdx.x; i < HID; i += blockDim.x) atomicAdd(p.db1 + i, ab1[i] * p.b1g);
+        for (int i = threadIdx.x; i < OUT * HID; i += blockDim.x) atomicAdd(p.dW2 + i, aW2[i] * p.w2g);
+        for (int i = threadIdx.x; i < OUT; i += blockDim.x) atomicAdd(p.db2 + i, ab2[i] * p.b2g);
+    }
+}
+
 int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                 const float* ray_d, const float* depths, int S, long P, float box_warp, const float* W1, const float* b1,
                 const float* W2, const float* b2, float lr_mul) {
@@ -465,7 +959,21 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     p.rgb = rgb; p.sigma = sigma;
     const long groups = (P + 127) / 128;
     dim3 grid((unsigned)(groups < 148 * 8 ? groups : 148 * 8), n);
-    triplane_mlp_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    static int use_mma = -1, passes = 3;
+    if (use_mma < 0) {
+        const char* e = getenv("B200EG3D_MLP");
+        use_mma = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+        const char* e2 = getenv("B200EG3D_MLP_PASSES");
+        if (e2 && strcmp(e2, "1") == 0) passes = 1;
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+    }
+    p.fwd_passes = passes;
+    if (use_mma) {
+        const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+        grid.x = (unsigned)(g512 < 148 ? g512 : 148);                  // persistent: one 16-warp CTA per SM
+        triplane_mlp_fwd_mma_kernel<<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
+    }
+    else triplane_mlp_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -484,14 +992,22 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     if (P == 0) return 0;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int use_mma = -1;
+    if (use_mma < 0) {
+        const char* e = getenv("B200EG3D_MLP");
+        use_mma = (e && strcmp(e, "simt") == 0) ? 0 : 1;
         B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
-        attr_set = true;
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
     }
-    const long groups = (P + 127) / 128;
-    dim3 grid((unsigned)(groups < 148 * 2 ? groups : 148 * 2), n);
-    triplane_mlp_bwd_kernel<<<grid, 128, BW_SMEM, (cudaStream_t)stream>>>(p);
+    if (use_mma) {
+        const long gb = (P + BM_WARPS * 32 - 1) / (BM_WARPS * 32);
+        dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                 // persistent: one 8-warp CTA per SM
+        triplane_mlp_bwd_mma_kernel<<<grid, BM_WARPS * 32, BM_SMEM, (cudaStream_t)stream>>>(p);
+    } else {
+        const long groups = (P + 127) / 128;
+        dim3 grid((unsigned)(groups < 148 * 2 ? groups : 148 * 2), n);
+        triplane_mlp_bwd_kernel<<<grid, 128, BW_SMEM, (cudaStream_t)stream>>>(p);
+    }
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -275,6 +275,7 @@ class _ModConvLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp):
+        ctx.set_materialize_grads(False)       # no zero-filled gradients for the non-differentiable bf16 outputs
         x = _f32c(x)
         n, h, w, cin = x.shape
         cout, _, k, _ = weight.shape
@@ -335,6 +336,8 @@ class _ModConvLayer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz, _dhi, _dlo):
+        if dz is None:
+            return (None,) * 11
         xs, xs_lo, W, s, wm, wm_lo, dcoef, z, nz, st = ctx.saved_tensors
         tc, up, act_gain, clamp, k, nbs, (n, h, w, cin, cout) = ctx.cfg
         taps = k * k
@@ -542,6 +545,7 @@ class _Render(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planes, ray_o, ray_d, W1, b1, W2, b2, lr_mul, box_warp, t_base, delta, u_strat, u_imp, white_back,
                 density_noise):
+        ctx.set_materialize_grads(False)
         pl = _f32c(planes)
         ro, rd = _f32c(ray_o), _f32c(ray_d)
         dev = pl.device
@@ -591,12 +595,15 @@ class _Render(torch.autograd.Function):
         dev = pl.device
         st = stream()
         need = ctx.needs_input_grad
+        if d_feat is None:
+            d_feat = torch.zeros([n, M, 32], device=dev, dtype=torch.float32)
         d_rgb_c = torch.empty_like(rgb_c)
         d_sig_c = torch.empty_like(sig_c)
         d_rgb_f = torch.empty_like(rgb_f) if S2 > 0 else None
         d_sig_f = torch.empty_like(sig_f) if S2 > 0 else None
         call('b200_ray_composite_bwd', ptr(t_c), ptr(sig_c), ptr(rgb_c), S, ptr(t_f), ptr(sig_f), ptr(rgb_f), S2, ptr(minmax),
-             white_back, n * M, ptr(_f32c(d_feat)), ptr(_f32c(d_depth)), ptr(_f32c(d_wsum)), ptr(d_rgb_c), ptr(d_sig_c),
+             white_back, n * M, ptr(_f32c(d_feat)), ptr(_f32c(d_depth) if d_depth is not None else None),
+             ptr(_f32c(d_wsum) if d_wsum is not None else None), ptr(d_rgb_c), ptr(d_sig_c),
              ptr(d_rgb_f), ptr(d_sig_f), st)
         d_planes = torch.zeros_like(pl) if need[0] else None
         want_rays = need[1] or need[2]

@@ -75,7 +75,7 @@ def test_gradients_match_reference(name, golden_dir):
         ssq = g.double().square().sum().item()
         ref = fx['grad_mom'][i][1]
         if g.numel() == 1:
-            assert abs(np.sqrt(ssq) - np.sqrt(ref)) <= TOL_GRAD * max(np.sqrt(ref), 1e-2 * scal), (str(n), ssq, ref)
+            assert abs(np.sqrt(ssq) - np.sqrt(ref)) <= TOL_GRAD * max(np.sqrt(ref), 5e-2 * scal), (str(n), ssq, ref)
             continue
         assert abs(ssq - ref) <= 2 * TOL_GRAD * max(ref, 1e-20), (str(n), ssq, ref)
         head = g.reshape(-1)[:16].cpu().numpy()

@@ -241,10 +241,11 @@ def test_run_model_fwd_bwd(b2, npts):
     assert maxdiff(out['rgb'], rgb_ref) < 2e-5
     assert maxdiff(out['sigma'], sig_ref) < 1e-4
     dpl_ref = pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)
-    assert relerr(pl.grad, dpl_ref) < 1e-4
-    assert relerr(cc.grad, cr.grad) < 1e-3
+    # the backward decoder GEMMs run single-pass TF32 on the tensor cores (the forward keeps the 3-pass split): ~5e-4 relative
+    assert relerr(pl.grad, dpl_ref) < 3e-3
+    assert relerr(cc.grad, cr.grad) < 3e-3
     for k, v in dec.named_parameters():
-        assert relerr(v.grad, Pr['decoder.' + k].grad) < 1e-4, k
+        assert relerr(v.grad, Pr['decoder.' + k].grad) < 3e-3, k
 
 
 @pytest.mark.parametrize('S,S2,white', [(12, 12, False), (16, 0, False), (8, 8, True), (48, 48, False)])
@@ -283,8 +284,8 @@ def test_render_fwd_bwd(b2, S, S2, white):
     assert maxdiff(f, f_ref) < 5e-5
     assert maxdiff(d, d_ref) < 5e-5
     assert maxdiff(w, w_ref) < 5e-5
-    assert relerr(pl.grad, pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)) < 2e-3
-    assert relerr(roc.grad, ror.grad) < 5e-3
-    assert relerr(rdc.grad, rdr.grad) < 5e-3
+    assert relerr(pl.grad, pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)) < 5e-3
+    assert relerr(roc.grad, ror.grad) < 1e-2
+    assert relerr(rdc.grad, rdr.grad) < 1e-2
     for k, v in dec.named_parameters():
-        assert relerr(v.grad, Pr['decoder.' + k].grad) < 2e-3, k
+        assert relerr(v.grad, Pr['decoder.' + k].grad) < 5e-3, k
