@@ -38,7 +38,12 @@ struct TcPixParams {
     int b_taps;                  // tap slices per sample in B
     int BN, N;
     float* C; long ldc, c_bs; int Wo, osy, osx, ooy, oox;
+    int ksplit;                  // > 1: the k-blocks of a tile are spread over ksplit CTAs, partial sums reduced with red.global.add
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 template <bool B_MN>
 __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_constant__ TcPixParams p) {
@@ -54,11 +59,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x;
+    const int tile = blockIdx.x / p.ksplit, ksi = blockIdx.x % p.ksplit;
     const int x0 = (tile % p.tiles_x) * p.tw, y0 = (tile / p.tiles_x) * p.th;
     const int n0 = blockIdx.y * p.BN;
     const int b = blockIdx.z;
-    const int nk = p.ntaps * p.kchunks;
+    const int nk_all = p.ntaps * p.kchunks;
+    const int per = (nk_all + p.ksplit - 1) / p.ksplit;
+    const int it0 = ksi * per;
+    const int nk = max(min(nk_all, it0 + per) - it0, 0);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -73,14 +81,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
 
-    if (warp == 0) {
+    if (nk == 0) {
+        // nothing to do for this k-slice (only possible when ksplit does not divide the k-blocks evenly)
+    } else if (warp == 0) {
         if (lane == 0) {
             const uint32_t bytes = (uint32_t)(A_BYTES + p.BN * TILE_K * 2) * (p.npass == 3 ? 2u : 1u);
             for (int it = 0; it < nk; ++it) {
                 const int s = it % STAGES, ph = (it / STAGES) & 1;
                 mbar_wait(empty(s), ph ^ 1);
                 mbar_arrive_expect_tx(full(s), bytes);
-                const int t = it / p.kchunks, c0 = (it % p.kchunks) * TILE_K;
+                const int t = (it0 + it) / p.kchunks, c0 = ((it0 + it) % p.kchunks) * TILE_K;
                 const uint32_t st = base + s * STAGE_BYTES;
                 const int ax = x0 * p.s + p.dx[t], ay = y0 * p.s + p.dy[t];
                 const int nh = p.npass == 3 ? 2 : 1;
@@ -137,12 +147,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
             if (valid) {
                 if (vec && n0 + c0 + 32 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; j += 4) {
+                        if (p.ksplit > 1) red_add_v4(crow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        else *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j < p.N) crow[c0 + j] = v[j];
+                        if (n0 + c0 + j < p.N) { if (p.ksplit > 1) atomicAdd(crow + c0 + j, v[j]); else crow[c0 + j] = v[j]; }
                 }
             }
         }
@@ -167,10 +179,6 @@ struct TcWgradParams {
     int BN, Cm, Cn;
     float* C; long c_bs;         // C[b][tap][Cm][Cn]
 };
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -346,6 +354,15 @@ void pick_tile(int Hi, int Wi, int& th, int& tw) {
     }
 }
 
+// Split-K factor for layers with too few output tiles to fill the GPU (the 4x4 .. 32x32 blocks stream 9.4 MB of weights
+// through a handful of CTAs otherwise): aim at ~one CTA per SM, keep at least 2 k-blocks per CTA.
+int pick_ksplit(int ctas, int nk) {
+    if (ctas >= 74 || nk < 4) return 1;
+    int ks = (148 + ctas - 1) / ctas;
+    if (ks > nk / 2) ks = nk / 2;
+    return ks < 1 ? 1 : ks;
+}
+
 int pick_bn(int n) {           // N tile of the K-major-B kernels (a multiple of 32, MMA N)
     if (n <= 32) return 32;
     if (n <= 64) return 64;
@@ -361,7 +378,7 @@ int launch_pix(const TcPixParams& p, int batch, cudaStream_t st) {
         attr = true;
     }
     const int tiles_y = (p.Hi + p.th - 1) / p.th;
-    dim3 grid(p.tiles_x * tiles_y, (p.N + p.BN - 1) / p.BN, batch);
+    dim3 grid(p.tiles_x * tiles_y * p.ksplit, (p.N + p.BN - 1) / p.BN, batch);
     conv_tc_pix_kernel<B_MN><<<grid, 192, SMEM_BYTES, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
@@ -409,9 +426,17 @@ B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_
         for (int t = 0; t < taps; ++t) { p.dy[t] = t / ksize - ksize / 2; p.dx[t] = t % ksize - ksize / 2; p.wt[t] = t; }
         for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
             if (int e = make_map_nhwc(&p.tmA[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
+        p.ksplit = pick_ksplit(p.tiles_x * ((h + p.th - 1) / p.th) * ((cout + p.BN - 1) / p.BN) * n, taps * p.kchunks);
+        if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * h * w * cout, st));
         return launch_pix<false>(p, n, st);
     }
     p.c_bs = (long)(2 * h + 1) * (2 * w + 1) * cout; p.Wo = 2 * w + 1; p.osy = p.osx = 2;
+    {   // split-K decided once for the four parity classes (the (0,0) class has the most tiles and taps)
+        int th0, tw0; pick_tile(h + 1, w + 1, th0, tw0);
+        const int ctas = ((w + 1 + tw0 - 1) / tw0) * ((h + 1 + th0 - 1) / th0) * ((cout + p.BN - 1) / p.BN) * n;
+        p.ksplit = pick_ksplit(ctas, p.kchunks);       // per class at least kchunks k-blocks (the (1,1) class has one tap)
+        if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * p.c_bs, st));
+    }
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
             p.Hi = h + 1 - py; p.Wi = w + 1 - px; pick_tile(p.Hi, p.Wi, p.th, p.tw); p.tiles_x = (p.Wi + p.tw - 1) / p.tw;
@@ -448,6 +473,8 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
         if (int e = make_map_nhwc(&p.tmA[i], i ? dy_lo : dy_hi, n, hs, ws, cout, p.tw, p.th, up)) return e;
         if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, 64)) return e;
     }
+    p.ksplit = pick_ksplit(p.tiles_x * ((h + p.th - 1) / p.th) * ((cin + p.BN - 1) / p.BN) * n, taps * p.kchunks);
+    if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)n * h * w * cin, st));
     return launch_pix<true>(p, n, st);
 }
 

@@ -58,6 +58,34 @@ __global__ void bias_act_kernel(const float* __restrict__ x, const float* __rest
     }
 }
 
+// Fast path of the two hot uses (ToRGB bias + clamp and its gradient): channel-last bias (stepB == 1), linear / lrelu,
+// 4 elements per thread, 32-bit index math.
+__global__ void bias_act_nhwc4_kernel(const float4* __restrict__ x, const float* __restrict__ b, const float4* __restrict__ yref,
+                                      float4* __restrict__ y, int grad, int n4, int c4, int lrelu, float alpha, float gain, float clamp) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 xv = x[i];
+        float v[4] = {xv.x, xv.y, xv.z, xv.w};
+        float yr[4] = {0.f, 0.f, 0.f, 0.f};
+        if (yref) { const float4 t = yref[i]; yr[0] = t.x; yr[1] = t.y; yr[2] = t.z; yr[3] = t.w; }
+        if (grad == 0 && b) {
+            const float4 bv = *reinterpret_cast<const float4*>(b + (i % c4) * 4);
+            v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float o = v[j];
+            if (lrelu) o = (grad == 0 ? (o > 0.f) : (yr[j] > 0.f)) ? o : o * alpha;      // sign(y/gain) == sign(y) for gain > 0
+            o *= gain;
+            if (clamp >= 0.f) {
+                if (grad == 0) o = (o > -clamp && o < clamp) ? o : (o >= 0.f ? clamp : -clamp);
+                else o = (yr[j] > -clamp && yr[j] < clamp) ? o : 0.f;
+            }
+            v[j] = o;
+        }
+        y[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 B200_API int b200_bias_act(const float* x, const float* b, const float* xref, const float* yref, const float* dy, float* y,
                            int grad, long sizeX, long stepB, int sizeB, int act, float alpha, float gain, float clamp,
                            void* stream) {
@@ -65,6 +93,16 @@ B200_API int b200_bias_act(const float* x, const float* b, const float* xref, co
     B200_REQUIRE(act >= 1 && act <= 9, "bias_act: unknown activation code");
     B200_REQUIRE(!b || (stepB > 0 && sizeB > 0), "bias_act: bad bias indexing");
     if (sizeX <= 0) return 0;
+    if ((act == 1 || act == 3) && !xref && !dy && gain > 0.f && sizeX % 4 == 0 && sizeX < (1L << 31) &&
+        (!b || (stepB == 1 && sizeB % 4 == 0 && sizeX % sizeB == 0)) && (grad == 0 || act == 1 || yref) &&
+        ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!yref || (uintptr_t)yref % 16 == 0) && (!b || (uintptr_t)b % 16 == 0)) {
+        const int n4 = (int)(sizeX / 4);
+        const int blocks4 = (n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16;
+        bias_act_nhwc4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>((const float4*)x, grad == 0 ? b : nullptr, (const float4*)yref,
+                                                                         (float4*)y, grad, n4, b ? sizeB / 4 : 1, act == 3, alpha, gain, clamp);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     const int blocks = (int)((sizeX + 255) / 256 < 148 * 16 ? (sizeX + 255) / 256 : 148 * 16);
     bias_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, b, xref, yref, dy, y, grad, sizeX, stepB > 0 ? stepB : 1,
                                                               sizeB > 0 ? sizeB : 1, act, alpha, gain, clamp);
@@ -411,6 +449,9 @@ static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t s
     else if (v4 && sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<4, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
     else if (v4 && sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<4, 4, 1, 2><<<blocks, 256, 0, st>>>(p);
     else if (v4) upfirdn2d_kernel<4, 0, 1, 1><<<blocks, 256, 0, st>>>(p);
+    else if (sq4 && p.upx == 1 && p.downx == 1) upfirdn2d_kernel<1, 4, 1, 1><<<blocks, 256, 0, st>>>(p);
+    else if (sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<1, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
+    else if (sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<1, 4, 1, 2><<<blocks, 256, 0, st>>>(p);
     else upfirdn2d_kernel<1, 0, 1, 1><<<blocks, 256, 0, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;

@@ -17,10 +17,12 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 
 // grid (cout, n), block 256, dynamic smem = cin*taps floats (the modulated row W[o]*s, staged once: the global read
 // is coalesced in the parameter layout [i][t], the writes are coalesced in the GEMM layout [t][i]).
+template <int TAPS>
 __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restrict__ W, const float* __restrict__ styles,
                                                           float* __restrict__ wmod, __nv_bfloat16* __restrict__ whi,
                                                           __nv_bfloat16* __restrict__ wlo, float* __restrict__ dcoef,
-                                                          int cout, int cin, int taps, int demod) {
+                                                          int cout, int cin, int taps_rt, int demod) {
+    const int taps = TAPS > 0 ? TAPS : taps_rt;
     extern __shared__ float sW[];
     __shared__ float red[32];
     const int o = blockIdx.x, n = blockIdx.y;
@@ -43,8 +45,9 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
     const long ob = (long)n * taps * cout * cin;
     if ((cin & 1) == 0) {
         const int half = cin >> 1;
-        for (int idx = threadIdx.x; idx < half * taps; idx += blockDim.x) {
-            const int t = idx / half, i = (idx % half) * 2;
+        for (int t = 0; t < taps; ++t)
+        for (int ih = threadIdx.x; ih < half; ih += blockDim.x) {
+            const int i = ih * 2;
             const float v0 = sW[i * taps + t] * d, v1 = sW[(i + 1) * taps + t] * d;
             const long oi = ob + ((long)t * cout + o) * cin + i;
             if (wmod) *reinterpret_cast<float2*>(wmod + oi) = make_float2(v0, v1);
@@ -73,10 +76,12 @@ __global__ void __launch_bounds__(256) weight_prep_kernel(const float* __restric
 // grid (cout), block 256, dynamic smem = 2*cin*taps floats.  dW is written (not accumulated); dstyles must be zeroed by
 // the caller (atomics).  The parameter row W[o] and the outgoing dW[o] row are staged in shared memory so that every
 // global access is coalesced.
+template <int TAPS>
 __global__ void __launch_bounds__(256) weight_prep_bwd_kernel(const float* __restrict__ W, const float* __restrict__ styles,
                                                               const float* __restrict__ dcoef, const float* __restrict__ dwmod,
                                                               float* __restrict__ dW, float* __restrict__ dstyles,
-                                                              int nb, int cout, int cin, int taps, int demod) {
+                                                              int nb, int cout, int cin, int taps_rt, int demod) {
+    const int taps = TAPS > 0 ? TAPS : taps_rt;
     extern __shared__ float sm[];
     float* sW = sm;                       // W[o][i][t]
     float* sD = sm + cin * taps;          // dW[o][i][t]
@@ -92,10 +97,9 @@ __global__ void __launch_bounds__(256) weight_prep_bwd_kernel(const float* __res
         if (demod) {
             d = dcoef[(long)n * cout + o];
             float acc = 0.f;
-            for (int idx = threadIdx.x; idx < cin * taps; idx += blockDim.x) {
-                const int t = idx / cin, i = idx % cin;
-                acc = fmaf(G[((long)t * cout + o) * cin + i], sW[i * taps + t] * s[i], acc);
-            }
+            for (int t = 0; t < taps; ++t)
+                for (int i = threadIdx.x; i < cin; i += blockDim.x)
+                    acc = fmaf(G[((long)t * cout + o) * cin + i], sW[i * taps + t] * s[i], acc);
             dot = block_sum(acc, red);
         }
         const float d3dot = d * d * d * dot;
@@ -123,8 +127,15 @@ B200_API int b200_modconv_weight_prep(const float* W, const float* styles, float
     B200_REQUIRE(wmod || w_hi, "weight_prep: no output requested");
     const size_t smem = sizeof(float) * (size_t)cin * taps;
     B200_REQUIRE(smem <= 48 * 1024, "weight_prep: cin*taps too large for the staging tile");
-    weight_prep_kernel<<<dim3(cout, n), 256, smem, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi, (__nv_bfloat16*)w_lo,
-                                                                           dcoef, cout, cin, taps, demod);
+    if (taps == 9)
+        weight_prep_kernel<9><<<dim3(cout, n), 256, smem, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi,
+                                                                                  (__nv_bfloat16*)w_lo, dcoef, cout, cin, taps, demod);
+    else if (taps == 1)
+        weight_prep_kernel<1><<<dim3(cout, n), 256, smem, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi,
+                                                                                  (__nv_bfloat16*)w_lo, dcoef, cout, cin, taps, demod);
+    else
+        weight_prep_kernel<0><<<dim3(cout, n), 256, smem, (cudaStream_t)stream>>>(W, styles, wmod, (__nv_bfloat16*)w_hi,
+                                                                                  (__nv_bfloat16*)w_lo, dcoef, cout, cin, taps, demod);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -137,7 +148,12 @@ B200_API int b200_modconv_weight_prep_bwd(const float* W, const float* styles, c
     if (dstyles) B200_CUDA(cudaMemsetAsync(dstyles, 0, sizeof(float) * (size_t)n * cin, (cudaStream_t)stream));
     const size_t smem = 2 * sizeof(float) * (size_t)cin * taps;
     B200_REQUIRE(smem <= 48 * 1024, "weight_prep_bwd: cin*taps too large for the staging tiles");
-    weight_prep_bwd_kernel<<<cout, 256, smem, (cudaStream_t)stream>>>(W, styles, dcoef, dwmod, dW, dstyles, n, cout, cin, taps, demod);
+    if (taps == 9)
+        weight_prep_bwd_kernel<9><<<cout, 256, smem, (cudaStream_t)stream>>>(W, styles, dcoef, dwmod, dW, dstyles, n, cout, cin, taps, demod);
+    else if (taps == 1)
+        weight_prep_bwd_kernel<1><<<cout, 256, smem, (cudaStream_t)stream>>>(W, styles, dcoef, dwmod, dW, dstyles, n, cout, cin, taps, demod);
+    else
+        weight_prep_bwd_kernel<0><<<cout, 256, smem, (cudaStream_t)stream>>>(W, styles, dcoef, dwmod, dW, dstyles, n, cout, cin, taps, demod);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
         for (int k = lane; k < S - 1; k += 32) { ws += w[k]; dn += w[k] * 0.5f * (ts[k] + ts[k + 1]); }
         ws = warp_sum(ws); dn = warp_sum(dn);
         float acc = 0.f;
+#pragma unroll 8
         for (int i = 0; i < S; ++i) {
             const int r = rk[i];
             const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
         const float g = 2.f * p.d_feat[ray * 32 + lane];        // through rgb*2-1
         const float gsum = p.white_back ? warp_sum(g) : 0.f;     // through + 1 - wsum
         // colours: d c_i = omega_rank(i) * g ; d omega_rank(i) = sum_lane g * c_i
+#pragma unroll 8
         for (int i = 0; i < S; ++i) {
             const int r = rk[i];
             const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));

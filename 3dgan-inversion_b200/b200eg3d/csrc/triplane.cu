@@ -165,12 +165,12 @@ __device__ __forceinline__ void tex4_scatter(float* __restrict__ p, float bw, fl
 }
 
 // gather the 32-channel mean feature of the warp's 32 points into sf[q*SA + channel] (lane == channel)
-template <int STRIDE = SA>
+template <int STRIDE = SA, int UNROLL = 4>
 __device__ __forceinline__ void gather_features(const TriplaneParams& p, const float* __restrict__ pl, const float* ss, float* sf,
                                                 int lane) {
     const int rs = p.wp * PC;
     const float* pc = pl + lane;
-#pragma unroll 4
+#pragma unroll UNROLL
     for (int q = 0; q < 32; ++q) {
         const float4 s0 = *reinterpret_cast<const float4*>(&ss[q * SP]), s1 = *reinterpret_cast<const float4*>(&ss[q * SP + 4]);
         const float4 s2 = *reinterpret_cast<const float4*>(&ss[q * SP + 8]), s3 = *reinterpret_cast<const float4*>(&ss[q * SP + 12]);
@@ -645,9 +645,10 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
         point_coords(p, n, pi, cx, cy, cz);
         stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
         __syncwarp();
-        gather_features<SF>(p, pl, ss, sF, lane);
+        gather_features<SF, 4>(p, pl, ss, sF, lane);
         {   // incoming gradients -> sO[point][0] = d_sigma, [1..32] = d_rgb, [33..39] = 0
             const float* gsrc = p.d_rgb + ((long)n * p.P + base) * C;
+#pragma unroll 16
             for (int q = 0; q < 32; ++q) {
                 sO[q * BSO + 1 + lane] = q < cnt ? gsrc[q * C + lane] : 0.f;
                 if (lane < 7) sO[q * BSO + 33 + lane] = 0.f;

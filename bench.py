@@ -161,6 +161,16 @@ def run_b200(args):
 
     for _ in range(max(args.warmup, 3)):
         step(resident)
+    if args.ncu_step:
+        # exactly one eager step between cudaProfilerStart/Stop:  ncu --profile-from-start off ... bench.py --eager --ncu-step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(resident)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -270,6 +280,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--ncu-step', action='store_true', help='profile exactly one step (cudaProfilerStart/Stop) and exit')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     a = ap.parse_args()
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
