@@ -6,23 +6,20 @@
 // one 128-byte line per texel and plane), so a warp gathers one texel with one coalesced request.
 //
 // Work decomposition: a warp owns 32 consecutive sample points.
-//   gather : lane == channel, the 12 texels of one point are 12 coalesced 128 B requests
-//   MLP    : lane == point, weights broadcast from shared memory (LDS.128), activations in registers
-// The two phases are stitched with a per-warp shared-memory transpose.
+//   gather / scatter : 8 lanes per point (4 channels each), one warp instruction touches four full 128 B texel lines
+//   decoder MLP      : mma.sync m16n8k8 TF32 tiles over the 32 points (see "Tensor-core decoder" below)
+// The phases are stitched through small per-warp shared-memory tiles.
 #include "common.cuh"
 #include <cstdlib>
 
 namespace {
 constexpr int C = 32, HID = 64, OUT = 33, PC = 96;
-constexpr int SP = 16;      // words per point of the bilinear set-up tile (3 planes x {offset|flags, 4 weights} + pad)
+constexpr int SP = 24;      // words per point of the bilinear set-up tile: 12 texel offsets + 12 weights
 
 // MUFU-based activations (ex2 / lg2 approximations): absolute error ~1e-6, far inside the 1e-3 parity budget, and
 // ~4x fewer instructions than expf / log1pf (the decoder evaluates 64 softplus + 32 sigmoid per sample point).
 __device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-constexpr int SA = 33;      // stride of the feature staging tile
-constexpr int SO = 36;      // stride of the d_out tile (16 B aligned rows for LDS.128 broadcasts)
-constexpr int SH = 68;      // stride of the hidden tile
 
 struct TriplaneParams {
     const float* planes; int n, hp, wp;
@@ -58,26 +55,6 @@ __device__ __forceinline__ Bilin make_bilin(float gx, float gy, int hp, int wp) 
     return b;
 }
 
-__device__ __forceinline__ float bilin_gather(const float* __restrict__ base, const Bilin& b, int wp) {
-    const float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
-    const float* r1 = r0 + (long)wp * PC;
-    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
-    if (b.yin0 && b.xin0) t00 = __ldg(r0);
-    if (b.yin0 && b.xin1) t01 = __ldg(r0 + PC);
-    if (b.yin1 && b.xin0) t10 = __ldg(r1);
-    if (b.yin1 && b.xin1) t11 = __ldg(r1 + PC);
-    return b.wy0 * (b.wx0 * t00 + b.wx1 * t01) + b.wy1 * (b.wx0 * t10 + b.wx1 * t11);
-}
-
-__device__ __forceinline__ void bilin_scatter(float* __restrict__ base, const Bilin& b, int wp, float g) {
-    float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
-    float* r1 = r0 + (long)wp * PC;
-    if (b.yin0 && b.xin0) atomicAdd(r0, g * b.wy0 * b.wx0);
-    if (b.yin0 && b.xin1) atomicAdd(r0 + PC, g * b.wy0 * b.wx1);
-    if (b.yin1 && b.xin0) atomicAdd(r1, g * b.wy1 * b.wx0);
-    if (b.yin1 && b.xin1) atomicAdd(r1 + PC, g * b.wy1 * b.wx1);
-}
-
 // per-channel partial derivatives of the bilinear value w.r.t. (ix, iy)
 __device__ __forceinline__ void bilin_dcoord(const float* __restrict__ base, const Bilin& b, int wp, float& dix, float& diy) {
     const float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
@@ -89,13 +66,6 @@ __device__ __forceinline__ void bilin_dcoord(const float* __restrict__ base, con
     if (b.yin1 && b.xin1) t11 = __ldg(r1 + PC);
     dix = b.wy0 * (t01 - t00) + b.wy1 * (t11 - t10);
     diy = b.wx0 * (t10 - t00) + b.wx1 * (t11 - t01);
-}
-
-__device__ __forceinline__ void load_weights(const TriplaneParams& p, float* W1s, float* b1s, float* W2s, float* b2s) {
-    for (int i = threadIdx.x; i < HID * C; i += blockDim.x) W1s[i] = p.W1[i] * p.w1g;
-    for (int i = threadIdx.x; i < HID; i += blockDim.x) b1s[i] = p.b1[i] * p.b1g;
-    for (int i = threadIdx.x; i < OUT * HID; i += blockDim.x) W2s[i] = p.W2[i] * p.w2g;
-    for (int i = threadIdx.x; i < OUT; i += blockDim.x) b2s[i] = p.b2[i] * p.b2g;
 }
 
 __device__ __forceinline__ void point_coords(const TriplaneParams& p, int n, long pi, float& cx, float& cy, float& cz) {
@@ -115,9 +85,9 @@ __device__ __forceinline__ void point_coords(const TriplaneParams& p, int n, lon
     cx *= p.coord_scale; cy *= p.coord_scale; cz *= p.coord_scale;
 }
 
-// Bilinear set-up of one plane for the lane's own point: {texel-00 offset | flags, w00, w01, w10, w11} with the plane mean
-// (1/3) folded into the weights, out-of-range texels given weight 0 and their address clamped onto a valid texel.
-__device__ __forceinline__ void plane_setup(float u, float v, int hp, int wp, int plane, float* out) {
+// Bilinear set-up of one plane for the lane's own point: 4 texel offsets (in floats, plane offset included) and 4 weights
+// with the plane mean (1/3) folded in; out-of-range texels get weight 0 and an address clamped onto a valid texel.
+__device__ __forceinline__ void plane_setup(float u, float v, int hp, int wp, int plane, float* off, float* wgt) {
     float ix = ((u + 1.f) * wp - 1.f) * 0.5f, iy = ((v + 1.f) * hp - 1.f) * 0.5f;
     ix = fminf(fmaxf(ix, -2.f), (float)wp + 1.f);
     iy = fminf(fmaxf(iy, -2.f), (float)hp + 1.f);
@@ -127,119 +97,74 @@ __device__ __forceinline__ void plane_setup(float u, float v, int hp, int wp, in
     const bool xi0 = x0 >= 0 && x0 < wp, xi1 = x0 + 1 >= 0 && x0 + 1 < wp, yi0 = y0 >= 0 && y0 < hp, yi1 = y0 + 1 >= 0 && y0 + 1 < hp;
     const int x0c = min(max(x0, 0), wp - 1), x1c = min(max(x0 + 1, 0), wp - 1);
     const int y0c = min(max(y0, 0), hp - 1), y1c = min(max(y0 + 1, 0), hp - 1);
-    const int base = (y0c * wp + x0c) * PC + plane * C;
-    const int flags = (x1c != x0c ? 1 : 0) | (y1c != y0c ? 2 : 0);
+    const int pc = plane * C;
     const float third = 1.f / 3.f;
-    out[0] = __int_as_float(base | flags);
-    out[1] = (yi0 && xi0) ? wy0 * wx0 * third : 0.f;
-    out[2] = (yi0 && xi1) ? wy0 * wx1 * third : 0.f;
-    out[3] = (yi1 && xi0) ? wy1 * wx0 * third : 0.f;
-    out[4] = (yi1 && xi1) ? wy1 * wx1 * third : 0.f;
+    off[0] = __int_as_float((y0c * wp + x0c) * PC + pc); wgt[0] = (yi0 && xi0) ? wy0 * wx0 * third : 0.f;
+    off[1] = __int_as_float((y0c * wp + x1c) * PC + pc); wgt[1] = (yi0 && xi1) ? wy0 * wx1 * third : 0.f;
+    off[2] = __int_as_float((y1c * wp + x0c) * PC + pc); wgt[2] = (yi1 && xi0) ? wy1 * wx0 * third : 0.f;
+    off[3] = __int_as_float((y1c * wp + x1c) * PC + pc); wgt[3] = (yi1 && xi1) ? wy1 * wx1 * third : 0.f;
 }
 
-// each lane stages the set-up of its own point: ss[lane*SP + 0..14]   (plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x))
+// each lane stages the set-up of its own point: ss[lane*SP + 0..11] = texel offsets, [12..23] = weights
+// (plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x): renderer.py:23-53)
 __device__ __forceinline__ void stage_setup(float* ss, int lane, float cx, float cy, float cz, int hp, int wp) {
     float t[SP];
-    plane_setup(cx, cy, hp, wp, 0, t);
-    plane_setup(cx, cz, hp, wp, 1, t + 5);
-    plane_setup(cz, cx, hp, wp, 2, t + 10);
-    t[15] = 0.f;
+    plane_setup(cx, cy, hp, wp, 0, t + 0, t + 12);
+    plane_setup(cx, cz, hp, wp, 1, t + 4, t + 16);
+    plane_setup(cz, cx, hp, wp, 2, t + 8, t + 20);
 #pragma unroll
     for (int j = 0; j < SP; j += 4) *reinterpret_cast<float4*>(&ss[lane * SP + j]) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
 }
 
-__device__ __forceinline__ float tex4(const float* __restrict__ p, float bw, float w00, float w01, float w10, float w11, int rowstride) {
-    const int b = __float_as_int(bw);
-    const int off = b & ~31, dx = (b & 1) ? PC : 0, dy = (b & 2) ? rowstride : 0;
-    return w00 * __ldg(p + off) + w01 * __ldg(p + off + dx) + w10 * __ldg(p + off + dy) + w11 * __ldg(p + off + dy + dx);
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
+    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
 }
 
-__device__ __forceinline__ void tex4_scatter(float* __restrict__ p, float bw, float w00, float w01, float w10, float w11, int rowstride,
-                                             float g) {
-    const int b = __float_as_int(bw);
-    const int off = b & ~31, dx = (b & 1) ? PC : 0, dy = (b & 2) ? rowstride : 0;
-    if (w00 != 0.f) atomicAdd(p + off, g * w00);
-    if (w01 != 0.f) atomicAdd(p + off + dx, g * w01);
-    if (w10 != 0.f) atomicAdd(p + off + dy, g * w10);
-    if (w11 != 0.f) atomicAdd(p + off + dy + dx, g * w11);
-}
-
-// gather the 32-channel mean feature of the warp's 32 points into sf[q*SA + channel] (lane == channel)
-template <int STRIDE = SA, int UNROLL = 4>
-__device__ __forceinline__ void gather_features(const TriplaneParams& p, const float* __restrict__ pl, const float* ss, float* sf,
-                                                int lane) {
-    const int rs = p.wp * PC;
-    const float* pc = pl + lane;
-#pragma unroll UNROLL
-    for (int q = 0; q < 32; ++q) {
-        const float4 s0 = *reinterpret_cast<const float4*>(&ss[q * SP]), s1 = *reinterpret_cast<const float4*>(&ss[q * SP + 4]);
-        const float4 s2 = *reinterpret_cast<const float4*>(&ss[q * SP + 8]), s3 = *reinterpret_cast<const float4*>(&ss[q * SP + 12]);
-        sf[q * STRIDE + lane] = tex4(pc, s0.x, s0.y, s0.z, s0.w, s1.x, rs) + tex4(pc, s1.y, s1.z, s1.w, s2.x, s2.y, rs) +
-                            tex4(pc, s2.z, s2.w, s3.x, s3.y, s3.z, rs);
-    }
-}
-
-__device__ __forceinline__ void mlp_hidden(const float* f, const float* W1s, const float* b1s, float* h) {
+// Gather the 32-channel mean feature of the warp's 32 points into sf[point*STRIDE + channel].  Eight lanes share a point
+// (4 channels each, one LDG.128 per texel), so one warp instruction fetches the same texel slot of FOUR points = four full
+// 128-byte lines; no cross-lane reduction is needed.
+template <int STRIDE>
+__device__ __forceinline__ void gather_features(const float* __restrict__ pl, const float* ss, float* sf, int lane) {
+    const int pt = lane >> 3, j4 = (lane & 7) * 4;
+    const float* pc = pl + j4;
+#pragma unroll 2
+    for (int q0 = 0; q0 < 32; q0 += 4) {
+        const float* s = ss + (q0 + pt) * SP;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < HID; ++j) {
-        float a = b1s[j];
-#pragma unroll
-        for (int c = 0; c < C; c += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(&W1s[j * C + c]);
-            a = fmaf(f[c], w.x, a); a = fmaf(f[c + 1], w.y, a); a = fmaf(f[c + 2], w.z, a); a = fmaf(f[c + 3], w.w, a);
+        for (int k = 0; k < 12; k += 4) {
+            const int4 o = *reinterpret_cast<const int4*>(s + k);
+            const float4 w = *reinterpret_cast<const float4*>(s + 12 + k);
+            fma4(acc, w.x, __ldg(reinterpret_cast<const float4*>(pc + o.x)));
+            fma4(acc, w.y, __ldg(reinterpret_cast<const float4*>(pc + o.y)));
+            fma4(acc, w.z, __ldg(reinterpret_cast<const float4*>(pc + o.z)));
+            fma4(acc, w.w, __ldg(reinterpret_cast<const float4*>(pc + o.w)));
         }
-        h[j] = softplus_fast(a);
+        *reinterpret_cast<float4*>(&sf[(q0 + pt) * STRIDE + j4]) = acc;
     }
 }
 
-__device__ __forceinline__ float mlp_out(const float* h, const float* W2s, const float* b2s, int k) {
-    float o = b2s[k];
-#pragma unroll
-    for (int j = 0; j < HID; j += 4) {
-        const float4 w = *reinterpret_cast<const float4*>(&W2s[k * HID + j]);
-        o = fmaf(h[j], w.x, o); o = fmaf(h[j + 1], w.y, o); o = fmaf(h[j + 2], w.z, o); o = fmaf(h[j + 3], w.w, o);
-    }
-    return o;
+__device__ __forceinline__ void red_add4(float* addr, float w, const float4& g) {
+    if (w != 0.f)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(w * g.x), "f"(w * g.y), "f"(w * g.z), "f"(w * g.w)
+                     : "memory");
 }
 
-__global__ void __launch_bounds__(128) triplane_mlp_fwd_kernel(TriplaneParams p) {
-    __shared__ __align__(16) float W1s[HID * C];
-    __shared__ __align__(16) float W2s[OUT * HID];
-    __shared__ float b1s[HID], b2s[OUT];
-    __shared__ float sfeat[4][32 * SA];
-    __shared__ __align__(16) float ssetup[4][32 * SP];
-    load_weights(p, W1s, b1s, W2s, b2s);
-    __syncthreads();
-    const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* sf = sfeat[wid];
-    float* ss = ssetup[wid];
-    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
-    for (long base = ((long)blockIdx.x * 4 + wid) * 32; base < p.P; base += (long)gridDim.x * 128) {
-        const long pi = base + lane;
-        float cx, cy, cz;
-        point_coords(p, n, pi, cx, cy, cz);
-        stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
-        __syncwarp();
-        gather_features(p, pl, ss, sf, lane);
-        __syncwarp();
-        float f[C];
+// Scatter d_f (sg[point*STRIDE + channel]) into the plane gradient with vector reductions, same lane mapping as the gather.
+template <int STRIDE>
+__device__ __forceinline__ void scatter_features(float* __restrict__ dpl, const float* ss, const float* sg, int lane, int cnt) {
+    const int pt = lane >> 3, j4 = (lane & 7) * 4;
+    float* pc = dpl + j4;
+    for (int q0 = 0; q0 < 32; q0 += 4) {
+        if (q0 + pt >= cnt) continue;
+        const float* s = ss + (q0 + pt) * SP;
+        const float4 g = *reinterpret_cast<const float4*>(&sg[(q0 + pt) * STRIDE + j4]);
 #pragma unroll
-        for (int c = 0; c < C; ++c) f[c] = sf[lane * SA + c];
-        __syncwarp();
-        float h[HID];
-        mlp_hidden(f, W1s, b1s, h);
-        const float sig = mlp_out(h, W2s, b2s, 0);
-        if (pi < p.P) p.sigma[(long)n * p.P + pi] = sig;
-#pragma unroll
-        for (int k = 1; k < OUT; ++k) {
-            const float o = mlp_out(h, W2s, b2s, k);
-            sf[lane * SA + k - 1] = sigmoid_fast(o) * 1.002f - 0.001f;
+        for (int k = 0; k < 12; k += 4) {
+            const int4 o = *reinterpret_cast<const int4*>(s + k);
+            const float4 w = *reinterpret_cast<const float4*>(s + 12 + k);
+            red_add4(pc + o.x, w.x, g); red_add4(pc + o.y, w.y, g); red_add4(pc + o.z, w.z, g); red_add4(pc + o.w, w.w, g);
         }
-        __syncwarp();
-        const int cnt = (int)min((long)32, p.P - base);
-        float* out = p.rgb + ((long)n * p.P + base) * C;
-        for (int q = 0; q < cnt; ++q) out[q * C + lane] = sf[q * SA + lane];
-        __syncwarp();
     }
 }
 
@@ -311,7 +236,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
         point_coords(p, n, pi, cx, cy, cz);
         stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
         __syncwarp();
-        gather_features<SF>(p, pl, ss, sF, lane);
+        gather_features<SF>(pl, ss, sF, lane);
         __syncwarp();
         // ---- layer 1: 16 independent accumulator tiles (2 m-tiles x 8 n-tiles), k-steps outermost
         float c[2][8][4];
@@ -400,204 +325,6 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
     }
 }
 
-// dynamic shared memory layout of the backward kernel (floats)
-constexpr int BW_W = HID * C + HID + OUT * HID + OUT + 3;            // weights, padded to a multiple of 4
-constexpr int BW_WPAD = (BW_W + 3) / 4 * 4;
-constexpr int BW_ACC = HID * C + HID + OUT * HID + OUT;              // block-level parameter-gradient accumulators
-constexpr int BW_ACCPAD = (BW_ACC + 3) / 4 * 4;
-constexpr int BW_WARP = 32 * SA + 32 * SH + 32 * SO + 32 * SP;       // per-warp staging
-constexpr int BW_SMEM = (BW_WPAD + BW_ACCPAD + 4 * BW_WARP) * 4;
-
-__global__ void __launch_bounds__(128, 2) triplane_mlp_bwd_kernel(TriplaneParams p) {
-    extern __shared__ __align__(16) float smem[];
-    float* W1s = smem;                       // [64][32]
-    float* W2s = W1s + HID * C;              // [33][64]
-    float* b1s = W2s + OUT * HID;
-    float* b2s = b1s + HID;
-    float* acc = smem + BW_WPAD;             // dW1 | db1 | dW2 | db2
-    float* aW1 = acc; float* ab1 = aW1 + HID * C; float* aW2 = ab1 + HID; float* ab2 = aW2 + OUT * HID;
-    const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* sA = smem + BW_WPAD + BW_ACCPAD + wid * BW_WARP;   // [32][SA] features f
-    float* sH = sA + 32 * SA;                                 // [32][SH] hidden h, later d_a
-    float* sO = sH + 32 * SH;                                 // [32][SO] d_rgb|d_sigma -> d_out -> d_f
-    float* ss = sO + 32 * SO;                                 // [32][SP] bilinear set-up (gather and scatter)
-    const bool wgrad = p.dW1 != nullptr;
-    load_weights(p, W1s, b1s, W2s, b2s);
-    for (int i = threadIdx.x; i < BW_ACC; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
-    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
-    float* dpl = p.d_planes ? p.d_planes + (long)n * p.hp * p.wp * PC : nullptr;
-
-    for (long base = ((long)blockIdx.x * 4 + wid) * 32; base < p.P; base += (long)gridDim.x * 128) {
-        const long pi = base + lane;
-        const bool valid = pi < p.P;
-        const int cnt = (int)min((long)32, p.P - base);
-        float cx, cy, cz;
-        point_coords(p, n, pi, cx, cy, cz);
-        // ---- 1. features (lane == channel) and incoming gradients, transposed through shared memory
-        stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
-        __syncwarp();
-        gather_features(p, pl, ss, sA, lane);
-        {
-            const float* g = p.d_rgb + ((long)n * p.P + base) * C;
-            for (int q = 0; q < 32; ++q) sO[q * SO + 1 + lane] = q < cnt ? g[q * C + lane] : 0.f;
-            sO[lane * SO] = valid ? p.d_sigma[(long)n * p.P + pi] : 0.f;
-        }
-        __syncwarp();
-        // ---- 2. forward recompute (lane == point): h -> sH, d_out -> sO (in place)
-        {
-            float h[HID];
-            {
-                float f[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) f[c] = sA[lane * SA + c];
-                mlp_hidden(f, W1s, b1s, h);
-            }
-#pragma unroll
-            for (int j = 0; j < HID; j += 4)
-                *reinterpret_cast<float4*>(&sH[lane * SH + j]) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
-#pragma unroll
-            for (int k = 1; k < OUT; ++k) {
-                const float sg = sigmoid_fast(mlp_out(h, W2s, b2s, k));       // rgb = sigmoid(o)*1.002 - 0.001
-                sO[lane * SO + k] *= 1.002f * sg * (1.f - sg);
-            }
-        }
-        __syncwarp();
-        // ---- 3. dW2[k][j] += sum_q d_out[q][k] * h[q][j]   (lane owns j = lane, lane + 32), db2
-        if (wgrad) {
-            float a0[OUT], a1[OUT];
-#pragma unroll
-            for (int k = 0; k < OUT; ++k) { a0[k] = 0.f; a1[k] = 0.f; }
-            for (int q = 0; q < 32; ++q) {
-                const float h0 = sH[q * SH + lane], h1 = sH[q * SH + 32 + lane];
-#pragma unroll
-                for (int k4 = 0; k4 < 32; k4 += 4) {
-                    const float4 d = *reinterpret_cast<const float4*>(&sO[q * SO + k4]);
-                    a0[k4] = fmaf(d.x, h0, a0[k4]); a1[k4] = fmaf(d.x, h1, a1[k4]);
-                    a0[k4 + 1] = fmaf(d.y, h0, a0[k4 + 1]); a1[k4 + 1] = fmaf(d.y, h1, a1[k4 + 1]);
-                    a0[k4 + 2] = fmaf(d.z, h0, a0[k4 + 2]); a1[k4 + 2] = fmaf(d.z, h1, a1[k4 + 2]);
-                    a0[k4 + 3] = fmaf(d.w, h0, a0[k4 + 3]); a1[k4 + 3] = fmaf(d.w, h1, a1[k4 + 3]);
-                }
-                const float d32 = sO[q * SO + 32];
-                a0[32] = fmaf(d32, h0, a0[32]); a1[32] = fmaf(d32, h1, a1[32]);
-            }
-#pragma unroll
-            for (int k = 0; k < OUT; ++k) {
-                atomicAdd(&aW2[k * HID + lane], a0[k]);
-                atomicAdd(&aW2[k * HID + 32 + lane], a1[k]);
-            }
-            float sb = 0.f, sb32 = 0.f;
-            for (int q = 0; q < 32; ++q) { sb += sO[q * SO + lane]; sb32 += sO[q * SO + 32]; }
-            atomicAdd(&ab2[lane], sb);
-            if (lane == 0) atomicAdd(&ab2[32], sb32);
-            __syncwarp();
-        }
-        // ---- 4. d_a = (W2^T d_out) * softplus'(a) with softplus'(a) = 1 - exp(-h);  d_f = W1^T d_a
-        {
-            float da[HID];
-#pragma unroll
-            for (int j = 0; j < HID; ++j) da[j] = 0.f;
-#pragma unroll
-            for (int k = 0; k < OUT; ++k) {
-                const float d = sO[lane * SO + k];
-#pragma unroll
-                for (int j = 0; j < HID; j += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(&W2s[k * HID + j]);
-                    da[j] = fmaf(d, w.x, da[j]); da[j + 1] = fmaf(d, w.y, da[j + 1]);
-                    da[j + 2] = fmaf(d, w.z, da[j + 2]); da[j + 3] = fmaf(d, w.w, da[j + 3]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < HID; j += 4) {
-                const float4 hv = *reinterpret_cast<const float4*>(&sH[lane * SH + j]);
-                da[j] *= 1.f - __expf(-hv.x); da[j + 1] *= 1.f - __expf(-hv.y);
-                da[j + 2] *= 1.f - __expf(-hv.z); da[j + 3] *= 1.f - __expf(-hv.w);
-                *reinterpret_cast<float4*>(&sH[lane * SH + j]) = make_float4(da[j], da[j + 1], da[j + 2], da[j + 3]);
-            }
-            float df[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) df[c] = 0.f;
-#pragma unroll
-            for (int j = 0; j < HID; ++j) {
-#pragma unroll
-                for (int c = 0; c < C; c += 4) {
-                    const float4 w = *reinterpret_cast<const float4*>(&W1s[j * C + c]);
-                    df[c] = fmaf(da[j], w.x, df[c]); df[c + 1] = fmaf(da[j], w.y, df[c + 1]);
-                    df[c + 2] = fmaf(da[j], w.z, df[c + 2]); df[c + 3] = fmaf(da[j], w.w, df[c + 3]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < C; c += 4)
-                *reinterpret_cast<float4*>(&sO[lane * SO + c]) =
-                    valid ? make_float4(df[c], df[c + 1], df[c + 2], df[c + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp();
-        // ---- 5. dW1[j][c] += sum_q d_a[q][j] * f[q][c]   (lane owns c = lane), db1
-        if (wgrad) {
-            float a[HID];
-#pragma unroll
-            for (int j = 0; j < HID; ++j) a[j] = 0.f;
-            for (int q = 0; q < 32; ++q) {
-                const float fq = sA[q * SA + lane];
-#pragma unroll
-                for (int j = 0; j < HID; j += 4) {
-                    const float4 d = *reinterpret_cast<const float4*>(&sH[q * SH + j]);
-                    a[j] = fmaf(d.x, fq, a[j]); a[j + 1] = fmaf(d.y, fq, a[j + 1]);
-                    a[j + 2] = fmaf(d.z, fq, a[j + 2]); a[j + 3] = fmaf(d.w, fq, a[j + 3]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < HID; ++j) atomicAdd(&aW1[j * C + lane], a[j]);
-            float s0 = 0.f, s1 = 0.f;
-            for (int q = 0; q < 32; ++q) { s0 += sH[q * SH + lane]; s1 += sH[q * SH + 32 + lane]; }
-            atomicAdd(&ab1[lane], s0); atomicAdd(&ab1[32 + lane], s1);
-        }
-        // ---- 6. scatter d_f (lane == channel) into the plane gradient (+ optional coordinate gradient)
-        if (dpl) {
-            const int rs = p.wp * PC;
-            float* dc = dpl + lane;
-#pragma unroll 2
-            for (int q = 0; q < cnt; ++q) {
-                const float4 s0 = *reinterpret_cast<const float4*>(&ss[q * SP]), s1 = *reinterpret_cast<const float4*>(&ss[q * SP + 4]);
-                const float4 s2 = *reinterpret_cast<const float4*>(&ss[q * SP + 8]), s3 = *reinterpret_cast<const float4*>(&ss[q * SP + 12]);
-                const float g = sO[q * SO + lane];             // the 1/3 of the plane mean is folded into the weights
-                tex4_scatter(dc, s0.x, s0.y, s0.z, s0.w, s1.x, rs, g);
-                tex4_scatter(dc, s1.y, s1.z, s1.w, s2.x, s2.y, rs, g);
-                tex4_scatter(dc, s2.z, s2.w, s3.x, s3.y, s3.z, rs, g);
-            }
-        }
-        if (p.d_coords) {
-            for (int q = 0; q < cnt; ++q) {
-                const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
-                const Bilin b0 = make_bilin(gx, gy, p.hp, p.wp), b1 = make_bilin(gx, gz, p.hp, p.wp), b2 = make_bilin(gz, gx, p.hp, p.wp);
-                const float g = sO[q * SO + lane] * (1.f / 3.f);
-                float ax, ay, bx, by, ex, ey;
-                bilin_dcoord(pl + lane, b0, p.wp, ax, ay);
-                bilin_dcoord(pl + C + lane, b1, p.wp, bx, by);
-                bilin_dcoord(pl + 2 * C + lane, b2, p.wp, ex, ey);
-                const float hx = 0.5f * p.wp, hy = 0.5f * p.hp;
-                // plane0 (x->W, y->H), plane1 (x->W, z->H), plane2 (z->W, x->H)
-                float dx = g * (ax * hx + bx * hx + ey * hy);
-                float dy = g * (ay * hy);
-                float dz = g * (by * hy + ex * hx);
-                dx = warp_sum(dx); dy = warp_sum(dy); dz = warp_sum(dz);
-                if (lane == 0) {
-                    float* dcq = p.d_coords + ((long)n * p.P + base + q) * 3;
-                    dcq[0] = dx * p.coord_scale; dcq[1] = dy * p.coord_scale; dcq[2] = dz * p.coord_scale;
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (wgrad) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < HID * C; i += blockDim.x) atomicAdd(p.dW1 + i, aW1[i] * p.w1g);
-        for (int i = threadIdx.x; i < HID; i += blockDim.x) atomicAdd(p.db1 + i, ab1[i] * p.b1g);
-        for (int i = threadIdx.x; i < OUT * HID; i += blockDim.x) atomicAdd(p.dW2 + i, aW2[i] * p.w2g);
-        for (int i = threadIdx.x; i < OUT; i += blockDim.x) atomicAdd(p.db2 + i, ab2[i] * p.b2g);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Tensor-core backward of the fused sampler + decoder (mma.sync m16n8k8 TF32, single pass: gradients need ~1e-3 relative
 // accuracy, the forward keeps the 3-pass split).  Per warp and 32 points:
@@ -607,6 +334,8 @@ __global__ void __launch_bounds__(128, 2) triplane_mlp_bwd_kernel(TriplaneParams
 //   parameters  dW2 += dO^T h, dW1 += d_a^T F (operands transposed through shared memory), db2, db1
 //   scatter     d_f (x bilinear weights, 1/3 folded in) -> red.global into the plane gradient
 constexpr int BSH = 72, BSO = 40, BM_WARPS = 8;
+constexpr int BW_ACC = HID * C + HID + OUT * HID + OUT;              // block-level parameter-gradient accumulators
+constexpr int BW_ACCPAD = (BW_ACC + 3) / 4 * 4;
 constexpr int BM_W = HID * SF + OUTP * SW2 + HID + OUTP;                    // W1 [64][36], W2 [40][72], b1, b2
 constexpr int BM_WPAD = (BM_W + 3) / 4 * 4;
 constexpr int BM_WARP = 32 * SF + 32 * BSH + 32 * BSO + 16 + 32 * SP;       // f | h, d_a | d_out, d_f (+pad) | set-up
@@ -645,7 +374,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
         point_coords(p, n, pi, cx, cy, cz);
         stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
         __syncwarp();
-        gather_features<SF, 4>(p, pl, ss, sF, lane);
+        gather_features<SF>(pl, ss, sF, lane);
         {   // incoming gradients -> sO[point][0] = d_sigma, [1..32] = d_rgb, [33..39] = 0
             const float* gsrc = p.d_rgb + ((long)n * p.P + base) * C;
 #pragma unroll 16
@@ -888,20 +617,8 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
                     }
         }
         __syncwarp();
-        // ---- scatter d_f (lane == channel; the 1/3 of the plane mean is folded into the staged weights)
-        if (dpl) {
-            const int rs = p.wp * PC;
-            float* dc = dpl + lane;
-#pragma unroll 2
-            for (int q = 0; q < cnt; ++q) {
-                const float4 s0 = *reinterpret_cast<const float4*>(&ss[q * SP]), s1 = *reinterpret_cast<const float4*>(&ss[q * SP + 4]);
-                const float4 s2 = *reinterpret_cast<const float4*>(&ss[q * SP + 8]), s3 = *reinterpret_cast<const float4*>(&ss[q * SP + 12]);
-                const float gq = sO[q * BSO + lane];
-                tex4_scatter(dc, s0.x, s0.y, s0.z, s0.w, s1.x, rs, gq);
-                tex4_scatter(dc, s1.y, s1.z, s1.w, s2.x, s2.y, rs, gq);
-                tex4_scatter(dc, s2.z, s2.w, s3.x, s3.y, s3.z, rs, gq);
-            }
-        }
+        // ---- scatter d_f (the 1/3 of the plane mean is folded into the staged weights)
+        if (dpl) scatter_features<BSO>(dpl, ss, sO, lane, cnt);
         if (p.d_coords) {
             for (int q = 0; q < cnt; ++q) {
                 const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
@@ -960,21 +677,16 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     p.rgb = rgb; p.sigma = sigma;
     const long groups = (P + 127) / 128;
     dim3 grid((unsigned)(groups < 148 * 8 ? groups : 148 * 8), n);
-    static int use_mma = -1, passes = 3;
-    if (use_mma < 0) {
-        const char* e = getenv("B200EG3D_MLP");
-        use_mma = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+    static int passes = 0;
+    if (passes == 0) {
         const char* e2 = getenv("B200EG3D_MLP_PASSES");
-        if (e2 && strcmp(e2, "1") == 0) passes = 1;
+        passes = (e2 && strcmp(e2, "1") == 0) ? 1 : 3;
         B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
     }
     p.fwd_passes = passes;
-    if (use_mma) {
-        const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
-        grid.x = (unsigned)(g512 < 148 ? g512 : 148);                  // persistent: one 16-warp CTA per SM
-        triplane_mlp_fwd_mma_kernel<<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
-    }
-    else triplane_mlp_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(p);
+    const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
+    grid.x = (unsigned)(g512 < 148 ? g512 : 148);                      // persistent: one 16-warp CTA per SM
+    triplane_mlp_fwd_mma_kernel<<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -993,22 +705,14 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     if (P == 0) return 0;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
-    static int use_mma = -1;
-    if (use_mma < 0) {
-        const char* e = getenv("B200EG3D_MLP");
-        use_mma = (e && strcmp(e, "simt") == 0) ? 0 : 1;
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM));
+    static bool attr_set = false;
+    if (!attr_set) {
         B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        attr_set = true;
     }
-    if (use_mma) {
-        const long gb = (P + BM_WARPS * 32 - 1) / (BM_WARPS * 32);
-        dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                 // persistent: one 8-warp CTA per SM
-        triplane_mlp_bwd_mma_kernel<<<grid, BM_WARPS * 32, BM_SMEM, (cudaStream_t)stream>>>(p);
-    } else {
-        const long groups = (P + 127) / 128;
-        dim3 grid((unsigned)(groups < 148 * 2 ? groups : 148 * 2), n);
-        triplane_mlp_bwd_kernel<<<grid, 128, BW_SMEM, (cudaStream_t)stream>>>(p);
-    }
+    const long gb = (P + BM_WARPS * 32 - 1) / (BM_WARPS * 32);
+    dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one 8-warp CTA per SM
+    triplane_mlp_bwd_mma_kernel<<<grid, BM_WARPS * 32, BM_SMEM, (cudaStream_t)stream>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
 }
