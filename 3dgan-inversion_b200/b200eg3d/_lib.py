@@ -17,6 +17,10 @@ SIGNATURES = {
     'b200_conv_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_dgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_wgrad': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_bank_styles_fwd': [_P, _I, _P, _I, _I, _I, _P],
+    'b200_bank_weights_fwd': [_P, _I, _I, _P],
+    'b200_bank_weights_bwd': [_P, _I, _I, _P],
+    'b200_bank_styles_bwd': [_P, _I, _P, _P, _I, _I, _I, _P],
     'b200_split_bf16': [_P, _P, _P, _L, _P],
     'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -36,6 +40,15 @@ SIGNATURES = {
     'b200_ray_composite_fwd': [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _L, _P, _P, _P, _P],
     'b200_ray_composite_bwd': [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _L, _P, _P, _P, _P, _P, _P, _P, _P],
 }
+
+
+
+class BankLayer(ctypes.Structure):
+    """B200BankLayer of include/b200eg3d.h."""
+    _fields_ = [(k, ctypes.c_void_p) for k in ('affine_w', 'affine_b', 'weight', 'styles', 'dcoef', 'wmod', 'w_hi', 'w_lo', 'dwmod',
+                                               'd_weight', 'd_styles', 'd_affine_w', 'd_affine_b')] + \
+               [(k, ctypes.c_int) for k in ('widx', 'cin', 'cout', 'taps', 'demod')] + [('post_scale', ctypes.c_float)]
+
 
 _lib = None
 

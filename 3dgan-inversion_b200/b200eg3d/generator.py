@@ -127,10 +127,11 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None):
-        """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None."""
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None, bank=None, lidx=-1):
+        """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None.
+        bank / lidx: styles and modulated weights come from a pre-computed ops.WeightBank entry (w is then unused)."""
         assert noise_mode in ['random', 'const', 'none']
-        styles = self.affine(w)
+        styles = self.affine(w) if bank is None else None
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device)
@@ -138,7 +139,7 @@ class SynthesisLayer(torch.nn.Module):
             noise = self.noise_const
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return ops.modconv_layer(x, self.weight, styles, self.bias, noise, self.noise_strength if noise is not None else None,
-                                 self.up, self.act_gain * gain, clamp, x_split=x_split)
+                                 self.up, self.act_gain * gain, clamp, x_split=x_split, bank=bank, lidx=lidx)
 
 
 class ToRGBLayer(torch.nn.Module):
@@ -154,9 +155,9 @@ class ToRGBLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
-    def forward(self, x, w, fused_modconv=True, img_prev=None, x_split=None):
-        styles = self.affine(w) * self.weight_gain
-        return ops.torgb_layer(x, self.weight, styles, self.bias, img_prev, self.conv_clamp, x_split=x_split)
+    def forward(self, x, w, fused_modconv=True, img_prev=None, x_split=None, bank=None, lidx=-1):
+        styles = self.affine(w) * self.weight_gain if bank is None else None
+        return ops.torgb_layer(x, self.weight, styles, self.bias, img_prev, self.conv_clamp, x_split=x_split, bank=bank, lidx=lidx)
 
 
 class SynthesisBlock(torch.nn.Module):
@@ -186,17 +187,30 @@ class SynthesisBlock(torch.nn.Module):
         self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp)
         self.num_torgb += 1
 
+    def bank_specs(self, w_base):
+        """ops.BankSpec of this block's layers, in execution order; w_base = index of the block's first latent."""
+        res, specs, wi = self.resolution, [], w_base
+        if self.in_channels != 0:
+            specs.append(ops.BankSpec(self.conv0.affine, self.conv0.weight, wi, True, 1.0, res // 2, res // 2, 2))
+            wi += 1
+        specs.append(ops.BankSpec(self.conv1.affine, self.conv1.weight, wi, True, 1.0, res, res, 1))
+        specs.append(ops.BankSpec(self.torgb.affine, self.torgb.weight, wi + 1, False, self.torgb.weight_gain, res, res, 1))
+        return specs
+
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, x_split=None, return_split=False,
-                **layer_kwargs):
-        """x_split / return_split carry the split-bf16 copies of the activations between consecutive blocks."""
+                bank=None, bank_base=0, **layer_kwargs):
+        """x_split / return_split carry the split-bf16 copies of the activations between consecutive blocks;
+        bank / bank_base: pre-computed styles + modulated weights (ops.WeightBank) and this block's first entry."""
         w_iter = iter(ws.unbind(dim=1))
+        li = bank_base
         if self.in_channels == 0:
             x = self.const.to(torch.float32).permute(1, 2, 0).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous()
             sp = None
         else:
-            x, sp = self.conv0(x, next(w_iter), x_split=x_split, **layer_kwargs)
-        x, sp = self.conv1(x, next(w_iter), x_split=sp, **layer_kwargs)
-        img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp)
+            x, sp = self.conv0(x, next(w_iter), x_split=x_split, bank=bank, lidx=li, **layer_kwargs)
+            li += 1
+        x, sp = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, **layer_kwargs)
+        img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
         if return_split:
             return x, img, sp
         return x, img
@@ -232,9 +246,19 @@ class SynthesisNetwork(torch.nn.Module):
             block = getattr(self, f'b{res}')
             block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
             w_idx += block.num_conv
+        bank, bases = None, [0] * len(self.block_resolutions)
+        if ops.CONFIG['bank']:
+            specs, w_idx = [], 0
+            for i, res in enumerate(self.block_resolutions):
+                block = getattr(self, f'b{res}')
+                bases[i] = len(specs)
+                specs += block.bank_specs(w_idx)
+                w_idx += block.num_conv
+            bank = ops.make_bank(ws, specs)
         x = img = sp = None
-        for res, cur_ws in zip(self.block_resolutions, block_ws):
-            x, img, sp = getattr(self, f'b{res}')(x, img, cur_ws, x_split=sp, return_split=True, **block_kwargs)
+        for i, (res, cur_ws) in enumerate(zip(self.block_resolutions, block_ws)):
+            x, img, sp = getattr(self, f'b{res}')(x, img, cur_ws, x_split=sp, return_split=True, bank=bank, bank_base=bases[i],
+                                                  **block_kwargs)
         return img
 
     def forward(self, ws, c=None, **block_kwargs):
@@ -280,8 +304,14 @@ class SuperresolutionHybrid8X(torch.nn.Module):
             size = (self.input_resolution, self.input_resolution)
             x = _to_nhwc(F.interpolate(_to_nchw_view(x), size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias))
             rgb = _to_nhwc(F.interpolate(_to_nchw_view(rgb), size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias))
-        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, **block_kwargs)
-        x, rgb = self.block1(x, rgb, ws, x_split=sp, **block_kwargs)
+        bank, base1 = None, 0
+        if ops.CONFIG['bank']:
+            specs = self.block0.bank_specs(0)
+            base1 = len(specs)
+            specs += self.block1.bank_specs(0)
+            bank = ops.make_bank(ws.contiguous(), specs)
+        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, bank=bank, bank_base=0, **block_kwargs)
+        x, rgb = self.block1(x, rgb, ws, x_split=sp, bank=bank, bank_base=base1, **block_kwargs)
         return rgb
 
     def forward(self, rgb, x, ws, **block_kwargs):

@@ -7,6 +7,7 @@ Public names mirror the reference's operator layer so that its call sites read t
 Internally the synthesis stack keeps activations NHWC ([N,H,W,C] fp32): one channel vector per pixel is the
 K-contiguous GEMM operand and the coalescing unit of every elementwise kernel.
 """
+import ctypes
 import math
 import os
 
@@ -27,6 +28,7 @@ _ACT_REF = {'linear': '', 'relu': 'y', 'lrelu': 'y', 'tanh': 'y', 'sigmoid': 'y'
 # (hi*hi + hi*lo + lo*hi, ~fp32 accuracy), 1 = plain bf16 operands.  B200EG3D_TC=0 forces the exact-fp32 SIMT kernels.
 CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           'fwd_passes': int(os.environ.get('B200EG3D_FWD_PASSES', '3')),
+          'bank': os.environ.get('B200EG3D_BANK', '1') != '0',       # batch styles + weight prep of all layers into one launch
           'dgrad_passes': int(os.environ.get('B200EG3D_DGRAD_PASSES', '3')),
           'wgrad_passes': int(os.environ.get('B200EG3D_WGRAD_PASSES', '1'))}
 
@@ -240,6 +242,117 @@ def fir_filter(device):
     return _FIR_CACHE[key]
 
 
+# ----------------------------------------------------------------------------------------------
+# Weight bank: styles + modulated weights of every layer of a synthesis network in one launch per stage
+
+class BankSpec:
+    """Static description of one modulated-conv layer for the bank (built by the generator modules)."""
+
+    def __init__(self, affine, weight, widx, demod, post_scale, h, w, up):
+        self.affine, self.weight, self.widx, self.demod, self.post_scale = affine, weight, widx, bool(demod), float(post_scale)
+        cout, cin, k, _ = weight.shape
+        self.cin, self.cout, self.k, self.taps, self.h, self.w, self.up = cin, cout, k, k * k, h, w, up
+        tc_f = _tc_ok(0, h, w, cin, cout, k, up)
+        tc_b = _tc_ok(1, h, w, cin, cout, k, up) and _tc_ok(2, h, w, cin, cout, k, up)
+        if demod:                       # 3x3 layers: all-or-nothing, as in _ModConvLayer
+            tc_f = tc_b = tc_f and tc_b
+        self.tc_f, self.tc_b = tc_f, tc_b
+
+
+class WeightBank:
+    """Per-forward container of the bank's outputs (and, during backward, of the per-layer d wmod)."""
+
+    def __init__(self, specs):
+        self.specs = specs
+        n = len(specs)
+        self.styles, self.dcoef, self.wmod, self.w_hi, self.w_lo = [None] * n, [None] * n, [None] * n, [None] * n, [None] * n
+        self.dwmod = [None] * n
+        self.need_wgrad = False
+        self.token = None
+
+
+def _bank_array(bank, n, dev, bwd=None):
+    arr = (_lib.BankLayer * len(bank.specs))()
+    for l, sp in enumerate(bank.specs):
+        e = arr[l]
+        e.affine_w, e.affine_b, e.weight = ptr(sp._aw), ptr(sp._ab), ptr(sp._W)
+        e.styles, e.dcoef, e.wmod, e.w_hi, e.w_lo = ptr(bank.styles[l]), ptr(bank.dcoef[l]), ptr(bank.wmod[l]), ptr(bank.w_hi[l]), ptr(bank.w_lo[l])
+        e.widx, e.cin, e.cout, e.taps, e.demod, e.post_scale = sp.widx, sp.cin, sp.cout, sp.taps, int(sp.demod), sp.post_scale
+        if bwd is not None:
+            e.dwmod, e.d_weight, e.d_styles, e.d_affine_w, e.d_affine_b = bwd[l]
+    return arr
+
+
+class _Bank(torch.autograd.Function):
+    """token = bank(ws, params...): fills `bank` (styles, dcoef, modulated weights of all layers).  The backward runs after
+    every layer's backward has stored its d wmod in bank.dwmod and turns them into parameter / latent gradients."""
+
+    @staticmethod
+    def forward(ctx, ws, bank, *params):
+        ws = _f32c(ws)
+        n, num_ws, w_dim = ws.shape
+        dev = ws.device
+        keep_lo = CONFIG['fwd_passes'] == 3 or CONFIG['dgrad_passes'] == 3
+        for l, sp in enumerate(bank.specs):
+            sp._aw, sp._ab, sp._W = _f32c(params[3 * l]), _f32c(params[3 * l + 1]), _f32c(params[3 * l + 2])
+            bank.styles[l] = torch.empty([n, sp.cin], device=dev, dtype=torch.float32)
+            bank.dcoef[l] = torch.empty([n, sp.cout], device=dev, dtype=torch.float32) if sp.demod else None
+            shape = [n, sp.taps, sp.cout, sp.cin]
+            if not (sp.tc_f and sp.tc_b):
+                bank.wmod[l] = torch.empty(shape, device=dev, dtype=torch.float32)
+            if sp.tc_f or sp.tc_b:
+                bank.w_hi[l] = torch.empty(shape, device=dev, dtype=torch.bfloat16)
+                bank.w_lo[l] = torch.empty(shape, device=dev, dtype=torch.bfloat16) if keep_lo else None
+        arr = _bank_array(bank, n, dev)
+        call('b200_bank_styles_fwd', ctypes.addressof(arr), len(bank.specs), ptr(ws), n, num_ws, w_dim, stream())
+        call('b200_bank_weights_fwd', ctypes.addressof(arr), len(bank.specs), n, stream())
+        ctx.bank = bank
+        ctx.save_for_backward(ws)
+        bank.need_wgrad = any(ctx.needs_input_grad)
+        return torch.zeros([1], device=dev, dtype=torch.float32)
+
+    @staticmethod
+    def backward(ctx, _dtok):
+        bank = ctx.bank
+        (ws,) = ctx.saved_tensors
+        n, num_ws, w_dim = ws.shape
+        dev = ws.device
+        need = ctx.needs_input_grad
+        specs = bank.specs
+        d_ws = torch.zeros_like(ws) if need[0] else None
+        total_cin = sum(sp.cin for sp in specs)
+        ds_all = torch.zeros([total_cin * n], device=dev, dtype=torch.float32)
+        grads, bwd, off = [], [], 0
+        for l, sp in enumerate(specs):
+            gaw = torch.empty_like(sp._aw) if need[2 + 3 * l] else None
+            gab = torch.empty_like(sp._ab) if need[3 + 3 * l] else None
+            gW = torch.empty_like(sp._W) if need[4 + 3 * l] else None
+            dw = bank.dwmod[l]
+            if dw is None:                                   # layer not reached by the backward pass: zero gradients
+                gaw = torch.zeros_like(sp._aw) if gaw is not None else None
+                gab = torch.zeros_like(sp._ab) if gab is not None else None
+                gW = torch.zeros_like(sp._W) if gW is not None else None
+            ds = ds_all[off:off + n * sp.cin]
+            off += n * sp.cin
+            bwd.append((ptr(dw), ptr(gW), ptr(ds), ptr(gaw), ptr(gab)))
+            grads += [gaw, gab, gW]
+        arr = _bank_array(bank, n, dev, bwd)
+        call('b200_bank_weights_bwd', ctypes.addressof(arr), len(specs), n, stream())
+        call('b200_bank_styles_bwd', ctypes.addressof(arr), len(specs), ptr(ws), ptr(d_ws), n, num_ws, w_dim, stream())
+        bank.dwmod = [None] * len(specs)
+        return (d_ws, None, *grads)
+
+
+def make_bank(ws, specs):
+    """Run the bank for `specs` on latents ws [N, num_ws, w_dim]; returns the filled WeightBank."""
+    bank = WeightBank(specs)
+    params = []
+    for sp in specs:
+        params += [sp.affine.weight, sp.affine.bias, sp.weight]
+    bank.token = _Bank.apply(ws, bank, *params)
+    return bank
+
+
 def _bf16_like(t):
     return torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
 
@@ -274,15 +387,20 @@ class _ModConvLayer(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp):
+    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp, token=None, bank=None, lidx=-1):
         ctx.set_materialize_grads(False)       # no zero-filled gradients for the non-differentiable bf16 outputs
         x = _f32c(x)
         n, h, w, cin = x.shape
-        cout, _, k, _ = weight.shape
+        if bank is not None:
+            sp = bank.specs[lidx]
+            cout, k = sp.cout, sp.k
+            W, s = sp._W, bank.styles[lidx]
+        else:
+            cout, _, k, _ = weight.shape
+            W = _f32c(weight)
+            s = _f32c(styles)
         taps = k * k
         dev = x.device
-        W = _f32c(weight)
-        s = _f32c(styles)
         b = _f32c(bias)
         clampf = float(clamp if clamp is not None else -1)
         oh, ow = h * up, w * up
@@ -292,15 +410,22 @@ class _ModConvLayer(torch.autograd.Function):
             nz = _f32c(noise)
             nbs = oh * ow if nz.ndim == 4 else 0
             st = _f32c(strength)
-        tc = _tc_ok(0, h, w, cin, cout, k, up) and _tc_ok(1, h, w, cin, cout, k, up) and _tc_ok(2, h, w, cin, cout, k, up)
-        dcoef = torch.empty([n, cout], device=dev, dtype=torch.float32)
+        if bank is not None:
+            tc = sp.tc_f
+            dcoef = bank.dcoef[lidx]
+        else:
+            tc = _tc_ok(0, h, w, cin, cout, k, up) and _tc_ok(1, h, w, cin, cout, k, up) and _tc_ok(2, h, w, cin, cout, k, up)
+            dcoef = torch.empty([n, cout], device=dev, dtype=torch.float32)
         z = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
         if tc:
             fp = CONFIG['fwd_passes']
             keep_lo = fp == 3 or CONFIG['dgrad_passes'] == 3
-            w_hi = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.bfloat16)
-            w_lo = torch.empty_like(w_hi) if keep_lo else None
-            call('b200_modconv_weight_prep', ptr(W), ptr(s), None, ptr(w_hi), ptr(w_lo), ptr(dcoef), n, cout, cin, taps, 1, stream())
+            if bank is not None:
+                w_hi, w_lo = bank.w_hi[lidx], bank.w_lo[lidx]
+            else:
+                w_hi = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.bfloat16)
+                w_lo = torch.empty_like(w_hi) if keep_lo else None
+                call('b200_modconv_weight_prep', ptr(W), ptr(s), None, ptr(w_hi), ptr(w_lo), ptr(dcoef), n, cout, cin, taps, 1, stream())
             if x_hi is None or (fp == 3 and x_lo is None):
                 x_hi, x_lo = _split(x, fp == 3)
             z_hi, z_lo = _bf16_like(z), _bf16_like(z)
@@ -318,8 +443,11 @@ class _ModConvLayer(torch.autograd.Function):
             ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, dcoef, z, nz, st)
             ctx.mark_non_differentiable(z_hi, z_lo)
         else:
-            wmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
-            call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), None, None, ptr(dcoef), n, cout, cin, taps, 1, stream())
+            if bank is not None:
+                wmod = bank.wmod[lidx]
+            else:
+                wmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
+                call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), None, None, ptr(dcoef), n, cout, cin, taps, 1, stream())
             if up == 1:
                 y = torch.empty_like(z)
                 call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cout, k, 1, stream())
@@ -332,19 +460,21 @@ class _ModConvLayer(torch.autograd.Function):
             z_hi = z_lo = None
             ctx.save_for_backward(x, None, W, s, wmod, None, dcoef, z, nz, st)
         ctx.cfg = (tc, up, float(act_gain), clampf, k, nbs, (n, h, w, cin, cout))
+        ctx.bank, ctx.lidx = bank, lidx
         return z, z_hi, z_lo
 
     @staticmethod
     def backward(ctx, dz, _dhi, _dlo):
         if dz is None:
-            return (None,) * 11
+            return (None,) * 14
         xs, xs_lo, W, s, wm, wm_lo, dcoef, z, nz, st = ctx.saved_tensors
         tc, up, act_gain, clamp, k, nbs, (n, h, w, cin, cout) = ctx.cfg
+        bank, lidx = ctx.bank, ctx.lidx
         taps = k * k
         dev = z.device
         oh, ow = z.shape[1:3]
         need = ctx.needs_input_grad
-        need_x, need_w = need[0], (need[3] or need[4])
+        need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dzc = _f32c(dz)
         dbias = torch.zeros([cout], device=dev, dtype=torch.float32)
         has_noise = nz is not None
@@ -381,17 +511,26 @@ class _ModConvLayer(torch.autograd.Function):
             if need_w:
                 dwmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
                 call('b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cout, k, up, stream())
-        if need_w:
+        dtok = None
+        if need_w and bank is not None:
+            bank.dwmod[lidx] = dwmod                    # consumed by _Bank.backward (runs after every layer's backward)
+            if lidx == 0:
+                dtok = torch.zeros([1], device=dev, dtype=torch.float32)
+        elif need_w:
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin, taps, 1, stream())
-        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None
+        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None, dtok, None, None
 
 
-def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None):
-    """Returns (z, (z_hi, z_lo) or None).  x_split: the producer's split-bf16 copies of x, if it made them."""
+def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None, bank=None, lidx=-1):
+    """Returns (z, (z_hi, z_lo) or None).  x_split: the producer's split-bf16 copies of x, if it made them.
+    bank / lidx: take styles and modulated weights from a WeightBank entry instead of (weight, styles)."""
     xh, xl = x_split if x_split is not None else (None, None)
-    z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
+    if bank is not None:
+        z, zh, zl = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank, lidx)
+    else:
+        z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
     return z, ((zh, zl) if zh is not None else None)
 
 
@@ -403,24 +542,31 @@ class _ToRGB(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, img_prev, clamp):
+    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, img_prev, clamp, token=None, bank=None, lidx=-1):
+        ctx.set_materialize_grads(False)
         x = _f32c(x)
         n, h, w, cin = x.shape
-        cimg = weight.shape[0]
         dev = x.device
-        W = _f32c(weight)
-        s = _f32c(styles)
-        tc_f = _tc_ok(0, h, w, cin, cimg, 1, 1)
-        tc_b = _tc_ok(1, h, w, cin, cimg, 1, 1) and _tc_ok(2, h, w, cin, cimg, 1, 1)
-        y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
         fp = CONFIG['fwd_passes']
-        wmod = w_hi = w_lo = None
-        if not (tc_f and tc_b):
-            wmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
-        if tc_f or tc_b:
-            w_hi = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.bfloat16)
-            w_lo = torch.empty_like(w_hi)
-        call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), ptr(w_hi), ptr(w_lo), None, n, cimg, cin, 1, 0, stream())
+        if bank is not None:
+            sp = bank.specs[lidx]
+            cimg, W, s = sp.cout, sp._W, bank.styles[lidx]
+            tc_f, tc_b = sp.tc_f, sp.tc_b
+            wmod, w_hi, w_lo = bank.wmod[lidx], bank.w_hi[lidx], bank.w_lo[lidx]
+        else:
+            cimg = weight.shape[0]
+            W = _f32c(weight)
+            s = _f32c(styles)
+            tc_f = _tc_ok(0, h, w, cin, cimg, 1, 1)
+            tc_b = _tc_ok(1, h, w, cin, cimg, 1, 1) and _tc_ok(2, h, w, cin, cimg, 1, 1)
+            wmod = w_hi = w_lo = None
+            if not (tc_f and tc_b):
+                wmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
+            if tc_f or tc_b:
+                w_hi = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.bfloat16)
+                w_lo = torch.empty_like(w_hi)
+            call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), ptr(w_hi), ptr(w_lo), None, n, cimg, cin, 1, 0, stream())
+        y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
         if (tc_f or tc_b) and (x_hi is None or x_lo is None):
             x_hi, x_lo = _split(x, True)
         if tc_f:
@@ -435,6 +581,7 @@ class _ToRGB(torch.autograd.Function):
         else:
             img = y
         ctx.cfg = (cl, img_prev is not None, tc_b, (n, h, w, cin, cimg))
+        ctx.bank, ctx.lidx = bank, lidx
         if tc_b:
             ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, y)
         else:
@@ -443,11 +590,14 @@ class _ToRGB(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dimg):
+        if dimg is None:
+            return (None,) * 11
         xs, xs_lo, W, s, wm, wm_lo, y = ctx.saved_tensors
         cl, has_prev, tc_b, (n, h, w, cin, cimg) = ctx.cfg
+        bank, lidx = ctx.bank, ctx.lidx
         dev = y.device
         need = ctx.needs_input_grad
-        need_x, need_w = need[0], (need[3] or need[4])
+        need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dimg = _f32c(dimg)
         dy = torch.empty_like(dimg)
         # gradient of bias+clamp uses the saved clamped output (bias_act.cu:143-145)
@@ -469,18 +619,22 @@ class _ToRGB(torch.autograd.Function):
                 call('b200_conv_dgrad', ptr(dy), ptr(wm), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
             if need_w:
                 call('b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream())
-        if need_w:
+        if need_w and bank is not None:
+            bank.dwmod[lidx] = dwmod
+        elif need_w:
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), None, ptr(dwmod), ptr(dW), ptr(ds), n, cimg, cin, 1, 0, stream())
         dprev = None
         if has_prev and need[6]:
             dprev = _upfirdn_nhwc_raw(dimg, fir_filter(dev), (1, 1), (2, 2), (1, 1, 1, 1), True, 4.0)
-        return dx, None, None, dW, ds, dbias, dprev, None
+        return dx, None, None, dW, ds, dbias, dprev, None, None, None, None
 
 
-def torgb_layer(x, weight, styles, bias, img_prev, clamp, x_split=None):
+def torgb_layer(x, weight, styles, bias, img_prev, clamp, x_split=None, bank=None, lidx=-1):
     xh, xl = x_split if x_split is not None else (None, None)
+    if bank is not None:
+        return _ToRGB.apply(x, xh, xl, None, None, bias, img_prev, clamp, bank.token, bank, lidx)
     return _ToRGB.apply(x, xh, xl, weight, styles, bias, img_prev, clamp)
 
 

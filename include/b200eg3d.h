@@ -33,6 +33,33 @@ int b200_modconv_weight_prep(const float* W, const float* styles, float* wmod /*
 int b200_modconv_weight_prep_bwd(const float* W, const float* styles, const float* dcoef, const float* dwmod,
                                  float* dW, float* dstyles, int n, int cout, int cin, int taps, int demod, void* stream);
 
+/* Grouped ("bank") style + weight preparation: every modulated-conv layer of a synthesis network in one launch per stage.
+ * Replaces the per-layer `styles = self.affine(w)` (networks_stylegan2.py:312,354) and the weight modulation of :58-67 for
+ * up to 32 layers at once.  `layers` is a HOST array (copied into the kernel parameters); all pointers inside are device
+ * pointers.  post_scale multiplies the affine output (ToRGB's weight_gain, networks_stylegan2.py:354); demod selects :65-67. */
+#define B200_BANK_MAX_LAYERS 32
+typedef struct {
+    const float* affine_w;      /* [cin][w_dim] */
+    const float* affine_b;      /* [cin] */
+    const float* weight;        /* [cout][cin][taps] */
+    float* styles;              /* out [n][cin] (post-scaled) */
+    float* dcoef;               /* out [n][cout], demod only */
+    float* wmod;                /* out fp32 [n][taps][cout][cin] or NULL */
+    void* w_hi; void* w_lo;     /* out split bf16, same layout, or NULL */
+    const float* dwmod;         /* backward in: gradient w.r.t. wmod, or NULL (layer skipped) */
+    float* d_weight;            /* backward out [cout][cin][taps] or NULL */
+    float* d_styles;            /* backward scratch [n][cin], zeroed by the caller, or NULL */
+    float* d_affine_w; float* d_affine_b;   /* backward out or NULL */
+    int widx, cin, cout, taps, demod;
+    float post_scale;
+} B200BankLayer;
+int b200_bank_styles_fwd(const B200BankLayer* layers, int n_layers, const float* ws /* [n][num_ws][w_dim] */, int n, int num_ws,
+                         int w_dim, void* stream);
+int b200_bank_weights_fwd(const B200BankLayer* layers, int n_layers, int n, void* stream);
+int b200_bank_weights_bwd(const B200BankLayer* layers, int n_layers, int n, void* stream);
+int b200_bank_styles_bwd(const B200BankLayer* layers, int n_layers, const float* ws, float* d_ws /* accumulated, may be NULL */,
+                         int n, int num_ws, int w_dim, void* stream);
+
 /* Exact-fp32 gather-GEMM convolutions (any channel count).  Replace F.conv2d / F.conv_transpose2d reached through
  * torch_utils/ops/conv2d_gradfix.py:37-45 from torch_utils/ops/conv2d_resample.py:113-136, and their autograd.
  * ksize in {1,3}; up == 1: 'same' correlation (padding ksize/2); up == 2 (ksize 3): stride-2 transposed convolution whose
