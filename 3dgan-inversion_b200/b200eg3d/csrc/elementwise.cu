@@ -114,14 +114,16 @@ B200_API int b200_bias_act(const float* x, const float* b, const float* xref, co
 // SynthesisLayer epilogue on NHWC [n][hw][c]:  z = clamp(act(y + noise[pix]*strength + bias[c]) * gain, +-clamp)
 // noise may be null; noise_bs = per-sample stride of the noise map (0 for the shared 'const' buffer).
 
+template <typename idx_t>
 __global__ void layer_act_fwd_kernel(const float4* __restrict__ y, float4* __restrict__ z, uint2* __restrict__ zhi,
                                      uint2* __restrict__ zlo, const float* __restrict__ bias,
                                      const float* __restrict__ noise, const float* __restrict__ strength, long noise_bs,
-                                     long total4, int hw, int c4, int lrelu, float alpha, float gain, float clamp) {
+                                     long total4_, int hw_, int c4_, int lrelu, float alpha, float gain, float clamp) {
     const float str = (noise && strength) ? *strength : 0.f;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const idx_t total4 = (idx_t)total4_, c4 = (idx_t)c4_, hw = (idx_t)hw_;
+    for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (idx_t)gridDim.x * blockDim.x) {
         const int cc = (int)(i % c4);
-        const long pix = i / c4;
+        const idx_t pix = i / c4;
         float4 v = y[i];
         float add = 0.f;
         if (noise) add = noise[(pix / hw) * noise_bs + pix % hw] * str;
@@ -168,8 +170,12 @@ B200_API int b200_layer_act_fwd(const float* y, float* z, void* z_hi, void* z_lo
     if (c % 4 == 0) {
         const long t4 = total / 4;
         const int blocks = (int)((t4 + 255) / 256 < 148 * 16 ? (t4 + 255) / 256 : 148 * 16);
-        layer_act_fwd_kernel<<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo, bias, noise, strength,
-                                                     noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp);
+        if (t4 < (1L << 31))
+            layer_act_fwd_kernel<unsigned><<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo, bias, noise,
+                                                                   strength, noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp);
+        else
+            layer_act_fwd_kernel<long><<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo, bias, noise,
+                                                               strength, noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp);
     } else {
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
         layer_act_fwd_kernel_s<<<blocks, 256, 0, st>>>(y, z, bias, noise, strength, noise_bs, total, hw, c, lrelu, alpha,
@@ -357,8 +363,8 @@ struct UpfirdnParams {
 // F == 0: generic run-time filter size and factors.
 template <int V, int F, int UP, int DOWN>
 __global__ void upfirdn2d_kernel(UpfirdnParams p) {
-    const int cv = p.c / V;
-    const long total = (long)p.n * p.oh * p.ow * cv;
+    const unsigned cv = p.c / V;
+    const unsigned total = (unsigned)((long)p.n * p.oh * p.ow * cv);      // launch_upfirdn() guarantees < 2^31 outputs
     const int fh = F > 0 ? F : p.fh, fw = F > 0 ? F : p.fw;
     const int upx = F > 0 ? UP : p.upx, upy = F > 0 ? UP : p.upy, downx = F > 0 ? DOWN : p.downx, downy = F > 0 ? DOWN : p.downy;
     float fr[F > 0 ? F * F : 1];
@@ -367,12 +373,12 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
         for (int i = 0; i < F * F; ++i) fr[i] = p.flip ? p.f[i] : p.f[F * F - 1 - i];
     }
     const float str = (p.act && p.noise && p.strength) ? *p.strength : 0.f;
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int cc = (int)(i % cv) * V;
-        long r = i / cv;
-        const int ox = (int)(r % p.ow); r /= p.ow;
-        const int oy = (int)(r % p.oh);
-        const int b = (int)(r / p.oh);
+        unsigned r = i / cv;
+        const int ox = (int)(r % (unsigned)p.ow); r /= (unsigned)p.ow;
+        const int oy = (int)(r % (unsigned)p.oh);
+        const int b = (int)(r / (unsigned)p.oh);
         float acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = 0.f;
@@ -432,6 +438,86 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
     }
 }
 
+// Register-blocked 4x4 FIR at unit rate (the filter after every up=2 convolution and its adjoint): one thread produces a
+// 2 x 4 patch of outputs for 4 channels from a 5 x 7 input window, i.e. 4.4 vector loads per output instead of 16.
+__global__ void __launch_bounds__(256) fir4_strip_kernel(UpfirdnParams p) {
+    const unsigned cv = p.c >> 2;
+    const unsigned sxn = (p.ow + 3) >> 2, syn = (p.oh + 1) >> 1;
+    const unsigned total = (unsigned)p.n * syn * sxn * cv;
+    float fr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fr[i] = (p.flip ? p.f[i] : p.f[15 - i]) * p.gain;
+    const float str = (p.act && p.noise && p.strength) ? *p.strength : 0.f;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cc = (int)(i % cv) * 4;
+        unsigned r = i / cv;
+        const int ox0 = (int)(r % sxn) * 4; r /= sxn;
+        const int oy0 = (int)(r % syn) * 2;
+        const int b = (int)(r / syn);
+        float4 acc[2][4];
+#pragma unroll
+        for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx) acc[yy][xx] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* xb = p.x + (long)b * p.h * p.w * p.c + cc;
+#pragma unroll
+        for (int ry = 0; ry < 5; ++ry) {
+            const int iy = oy0 + ry - p.pady0;
+            if (iy < 0 || iy >= p.h) continue;
+            float4 row[7];
+#pragma unroll
+            for (int rx = 0; rx < 7; ++rx) {
+                const int ix = ox0 + rx - p.padx0;
+                row[rx] = (ix >= 0 && ix < p.w) ? __ldg(reinterpret_cast<const float4*>(xb + ((long)iy * p.w + ix) * p.c))
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int yy = 0; yy < 2; ++yy) {
+                const int a = ry - yy;                      // filter row applied to this input row
+                if (a < 0 || a > 3) continue;
+#pragma unroll
+                for (int xx = 0; xx < 4; ++xx)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float g = fr[a * 4 + q];
+                        const float4 v = row[xx + q];
+                        acc[yy][xx].x = fmaf(g, v.x, acc[yy][xx].x); acc[yy][xx].y = fmaf(g, v.y, acc[yy][xx].y);
+                        acc[yy][xx].z = fmaf(g, v.z, acc[yy][xx].z); acc[yy][xx].w = fmaf(g, v.w, acc[yy][xx].w);
+                    }
+            }
+        }
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.act && p.bias) bv = *reinterpret_cast<const float4*>(p.bias + cc);
+#pragma unroll
+        for (int yy = 0; yy < 2; ++yy) {
+            const int oy = oy0 + yy;
+            if (oy >= p.oh) continue;
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx) {
+                const int ox = ox0 + xx;
+                if (ox >= p.ow) continue;
+                const long o = (((long)b * p.oh + oy) * p.ow + ox) * p.c + cc;
+                float out[4] = {acc[yy][xx].x, acc[yy][xx].y, acc[yy][xx].z, acc[yy][xx].w};
+                if (p.add) { const float4 ad = *reinterpret_cast<const float4*>(p.add + o); out[0] += ad.x; out[1] += ad.y; out[2] += ad.z; out[3] += ad.w; }
+                if (p.act) {
+                    const float nz = p.noise ? p.noise[(long)b * p.noise_bs + (long)oy * p.ow + ox] * str : 0.f;
+                    const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = out[j] + nz + bb[j];
+                        if (p.lrelu) t = t > 0.f ? t : t * p.alpha;
+                        t *= p.act_gain;
+                        if (p.clamp >= 0.f) t = (t > -p.clamp && t < p.clamp) ? t : (t >= 0.f ? p.clamp : -p.clamp);
+                        out[j] = t;
+                    }
+                }
+                if (p.y) *reinterpret_cast<float4*>(p.y + o) = make_float4(out[0], out[1], out[2], out[3]);
+                if (p.yhi) split4(out, p.yhi, p.ylo, o / 4);
+            }
+        }
+    }
+}
+
 static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t st) {
     B200_REQUIRE(p.upx >= 1 && p.upy >= 1 && p.downx >= 1 && p.downy >= 1, "upfirdn2d: up/down factors must be >= 1");
     B200_REQUIRE(p.fh >= 1 && p.fw >= 1 && p.fh <= 64 && p.fw <= 64, "upfirdn2d: filter size must be in [1, 64]");
@@ -443,9 +529,14 @@ static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t s
     B200_REQUIRE(p.y || p.yhi, "upfirdn2d: no output requested");
     const long total = (long)p.n * p.oh * p.ow * (v4 ? p.c / 4 : p.c);
     if (total <= 0) return 0;
+    B200_REQUIRE(total < (1L << 31) && (long)p.n * p.h * p.w * p.c < (1L << 31), "upfirdn2d: tensor too large (>= 2^31 elements)");
     const int blocks = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
     const bool sq4 = p.fh == 4 && p.fw == 4 && p.upx == p.upy && p.downx == p.downy;
-    if (v4 && sq4 && p.upx == 1 && p.downx == 1) upfirdn2d_kernel<4, 4, 1, 1><<<blocks, 256, 0, st>>>(p);
+    if (v4 && sq4 && p.upx == 1 && p.downx == 1) {
+        const long strips = (long)p.n * ((p.oh + 1) / 2) * ((p.ow + 3) / 4) * (p.c / 4);
+        const int sb = (int)((strips + 255) / 256 < 148 * 32 ? (strips + 255) / 256 : 148 * 32);
+        fir4_strip_kernel<<<sb, 256, 0, st>>>(p);
+    }
     else if (v4 && sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<4, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
     else if (v4 && sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<4, 4, 1, 2><<<blocks, 256, 0, st>>>(p);
     else if (v4) upfirdn2d_kernel<4, 0, 1, 1><<<blocks, 256, 0, st>>>(p);

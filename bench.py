@@ -37,37 +37,51 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """SM clock and throttle reasons sampled DURING the timed region (NVML in a background thread, 5 ms period;
+    falls back to polling nvidia-smi when the NVML python binding is unavailable)."""
+    REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.samples, self.mask, self.max_mhz, self.run, self.th, self.how = index, [], 0, None, False, None, 'nvml'
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv, self.how = None, 'nvidia-smi'
+
+    def _loop(self):
+        while self.run:
+            try:
+                if self.nv is not None:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    self.mask |= self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    time.sleep(0.005)
+                else:
+                    out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=clocks.sm,clocks.max.sm,'
+                                          'clocks_event_reasons.active', '--format=csv,noheader,nounits'],
+                                         capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                    self.samples.append(int(out[0]))
+                    self.max_mhz = int(out[1])
+                    self.mask |= int(out[2].strip(), 16)
+            except Exception:
+                time.sleep(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([v.strip() for v in line.split(',')])
+        self.run = True
+        self.th = threading.Thread(target=self._loop, daemon=True)
+        self.th.start()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        self.proc.terminate()
-        self.th.join(timeout=2)
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith('Active') for r in self.rows)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
-                'samples': len(sm)}
+        self.run = False
+        if self.th is not None:
+            self.th.join(timeout=6)
+        sm = sorted(self.samples)
+        reasons = [n for n, bit in self.REASONS.items() if self.mask & bit]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons, 'samples': len(sm),
+                'source': self.how}
 
 
 def conv_flops_per_step():
@@ -276,7 +290,7 @@ def run_reference(args):
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
