@@ -47,9 +47,22 @@ __device__ __forceinline__ void march_weights(const float* ts, const float* ss, 
         alpha[k] = 1.f - expf(-sp * delta);
     }
     __syncwarp();
-    if (lane == 0) {
-        float T = 1.f;
-        for (int k = 0; k < S - 1; ++k) { trans[k] = T; w[k] = alpha[k] * T; T *= (1.f - alpha[k] + 1e-10f); }
+    // exclusive running product of (1 - alpha + 1e-10): warp-wide multiplicative scan, 32 intervals per round
+    float carry = 1.f;
+    for (int k0 = 0; k0 < S - 1; k0 += 32) {
+        const int k = k0 + lane;
+        const float a = k < S - 1 ? alpha[k] : 0.f;
+        float incl = k < S - 1 ? (1.f - a + 1e-10f) : 1.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl *= up;
+        }
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float T = carry * excl;
+        if (k < S - 1) { trans[k] = T; w[k] = a * T; }
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
 }

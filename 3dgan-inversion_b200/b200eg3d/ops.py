@@ -599,22 +599,26 @@ class _ToRGB(torch.autograd.Function):
         need = ctx.needs_input_grad
         need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dimg = _f32c(dimg)
-        dy = torch.empty_like(dimg)
-        # gradient of bias+clamp uses the saved clamped output (bias_act.cu:143-145)
-        call('b200_bias_act', ptr(dimg), None, None, ptr(y), None, ptr(dy), 1, dy.numel(), 1, 1, 1, 0.0, 1.0, cl, stream())
-        dbias = dy.sum([0, 1, 2])
+        dbias = torch.zeros([cimg], device=dev, dtype=torch.float32)
         dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
         dW = ds = None
         if need_w:
             dwmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
+        # gradient of bias + clamp from the saved clamped output (bias_act.cu:143-145), d bias reduced in the same pass
         if tc_b:
             dp, wp = CONFIG['dgrad_passes'], CONFIG['wgrad_passes']
-            dy_hi, dy_lo = _split(dy, (need_x and dp == 3) or (need_w and wp == 3))
+            lo = (need_x and dp == 3) or (need_w and wp == 3)
+            dy_hi, dy_lo = _bf16_like(dimg), (_bf16_like(dimg) if lo else None)
+            call('b200_layer_act_bwd', ptr(dimg), ptr(y), None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), None, None, 0, None, None,
+                 n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
                 call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cimg, 1, 1, dp, stream())
             if need_w:
                 call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, stream())
         else:
+            dy = torch.empty_like(dimg)
+            call('b200_layer_act_bwd', ptr(dimg), ptr(y), ptr(dy), None, None, ptr(dbias), None, None, 0, None, None,
+                 n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
                 call('b200_conv_dgrad', ptr(dy), ptr(wm), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
             if need_w:
