@@ -25,7 +25,7 @@ import torch  # noqa: E402
 
 METRIC = 'PTI steps/sec (fwd+bwd) 512px out, 128px neural render, 48+48 depth samples'
 WORKLOAD = 'ffhqrebalanced512-128 EG3D (random-init), single-image PTI step, R=128, 48+48 samples, batch 1 per GPU'
-R, S, S_IMP = 128, 48, 48
+R, S, S_IMP = 128, 48, 48          # BASELINE config[1]; --render-res / --depth-samples select the config[4] stress shape
 
 
 def peaks():
@@ -294,9 +294,15 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--render-res', type=int, default=None, help='neural rendering resolution (default 128; 256 = BASELINE config 5)')
+    ap.add_argument('--depth-samples', type=int, default=None, help='coarse = fine depth samples per ray (default 48; 96 = config 5)')
     ap.add_argument('--ncu-step', action='store_true', help='profile exactly one step (cudaProfilerStart/Stop) and exit')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
     a = ap.parse_args()
+    if a.render_res or a.depth_samples:
+        R = a.render_res or R
+        S = S_IMP = a.depth_samples or S
+        WORKLOAD = f'ffhqrebalanced512-128 EG3D (random-init), single-image PTI step, R={R}, {S}+{S_IMP} samples, batch 1 per GPU (non-default shape)'
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     if a.impl == 'reference':
         run_reference(a)
