@@ -33,7 +33,7 @@ SIGNATURES = {
     'b200_upfirdn2d': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'b200_upfirdn2d_fused': [_P] * 6 + [_I] * 13 + [_F, _I, _P, _P, _P, _L, _I, _F, _F, _F, _P],
     'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P],
-    'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
     'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],
     'b200_depth_minmax': [_P, _L, _P, _P],
     'b200_ray_importance': [_P, _P, _P, _P, _L, _I, _I, _P],
@@ -70,6 +70,8 @@ def load():
     lib.b200_version.restype = ctypes.c_int
     lib.b200_version.argtypes = []
     lib.b200_conv_tc_supported.restype = ctypes.c_int
+    lib.b200_triplane_bwd_workspace_bytes.restype = ctypes.c_long
+    lib.b200_triplane_bwd_workspace_bytes.argtypes = [_I, _L]
     lib.b200_conv_tc_supported.argtypes = [_I] * 7
     _lib = lib
     return lib

@@ -11,6 +11,7 @@
 // The phases are stitched through small per-warp shared-memory tiles.
 #include "common.cuh"
 #include <cstdlib>
+#include <cuda_bf16.h>
 
 namespace {
 constexpr int C = 32, HID = 64, OUT = 33, PC = 96;
@@ -34,6 +35,7 @@ struct TriplaneParams {
     const float* d_rgb; const float* d_sigma;
     float* d_planes; float* d_coords;
     float* dW1; float* db1; float* dW2; float* db2;
+    __nv_bfloat16* x_f; __nv_bfloat16* x_h; __nv_bfloat16* x_do; __nv_bfloat16* x_da;   // bf16 exports for the dW1 / dW2 GEMMs
     int fwd_passes;                                         // 3: split-TF32 (default), 1: plain TF32 (experiments)
 };
 
@@ -331,60 +333,68 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
 //   recompute   C1 = F W1^T (+b1), h = softplus(C1);  O = h W2^T (+b2)             [h feeds layer 2 from registers]
 //   d_out       dO = d_rgb * 1.002 * s(1-s) | d_sigma                               [C-fragment layout of O]
 //   chain       dh = dO W2  -> d_a = dh * (1 - exp(-h)) -> d_f = d_a W1             [A fragments straight from registers]
-//   parameters  dW2 += dO^T h, dW1 += d_a^T F (operands transposed through shared memory), db2, db1
-//   scatter     d_f (x bilinear weights, 1/3 folded in) -> red.global into the plane gradient
-constexpr int BSH = 72, BSO = 40, BM_WARPS = 8;
-constexpr int BW_ACC = HID * C + HID + OUT * HID + OUT;              // block-level parameter-gradient accumulators
-constexpr int BW_ACCPAD = (BW_ACC + 3) / 4 * 4;
-constexpr int BM_W = HID * SF + OUTP * SW2 + HID + OUTP;                    // W1 [64][36], W2 [40][72], b1, b2
+//   scatter     d_f (x bilinear weights, 1/3 folded in) -> red.global.add.v4 into the plane gradient
+//   parameters  db1 / db2 reduced here; for dW1 = d_a^T F and dW2 = dO^T h the four operands are exported as bf16 [P][.]
+//               tensors and contracted over the point dimension by the tcgen05 weight-gradient kernel (conv_tc.cu), which
+//               keeps this kernel free of shared-memory transposes and lets 16 warps share an SM.
+constexpr int BM_WARPS = 16;
+constexpr int BM_W = HID * SF + OUTP * SW2 + HID + OUTP + HID + OUTP;       // W1 [64][36], W2 [40][72], b1, b2, db1, db2
 constexpr int BM_WPAD = (BM_W + 3) / 4 * 4;
-constexpr int BM_WARP = 32 * SF + 32 * BSH + 32 * BSO + 16 + 32 * SP;       // f | h, d_a | d_out, d_f (+pad) | set-up
-constexpr int BM_SMEM = (BM_WPAD + BW_ACCPAD + BM_WARPS * BM_WARP) * 4;
+constexpr int BM_WARP = 32 * SF + 32 * SP;                                  // f (later d_f) | set-up
+constexpr int BM_SMEM = (BM_WPAD + BM_WARPS * BM_WARP) * 4;
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// sum over the 8 row-groups (lane bits 2..4) of a C-fragment register; result valid in lanes with g == 0
+__device__ __forceinline__ float sum_over_g(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
 
 __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(TriplaneParams p) {
     extern __shared__ __align__(16) float smem[];
     float* W1s = smem; float* W2s = W1s + HID * SF; float* b1s = W2s + OUTP * SW2; float* b2s = b1s + HID;
-    float* acc = smem + BM_WPAD;
-    float* aW1 = acc; float* ab1 = aW1 + HID * C; float* aW2 = ab1 + HID; float* ab2 = aW2 + OUT * HID;
+    float* ab1 = b2s + OUTP; float* ab2 = ab1 + HID;
     const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    float* sF = smem + BM_WPAD + BW_ACCPAD + wid * BM_WARP;    // [32][SF]
-    float* sH = sF + 32 * SF;                                  // [32][BSH]
-    float* sO = sH + 32 * BSH;                                 // [32][BSO] (+16 pad)
-    float* ss = sO + 32 * BSO + 16;                            // [32][SP]
-    const bool wgrad = p.dW1 != nullptr;
+    float* sF = smem + BM_WPAD + wid * BM_WARP;                // [32][SF]
+    float* ss = sF + 32 * SF;                                  // [32][SP]
+    const bool wgrad = p.db1 != nullptr;
     for (int i = threadIdx.x; i < HID * C; i += blockDim.x) W1s[(i / C) * SF + (i % C)] = __uint_as_float(tf32_rna(p.W1[i] * p.w1g));
     for (int i = threadIdx.x; i < OUTP * HID; i += blockDim.x) {
         const int k = i / HID, j = i % HID;
         W2s[k * SW2 + j] = k < OUT ? __uint_as_float(tf32_rna(p.W2[i] * p.w2g)) : 0.f;
     }
-    for (int i = threadIdx.x; i < HID; i += blockDim.x) b1s[i] = p.b1[i] * p.b1g;
-    for (int i = threadIdx.x; i < OUTP; i += blockDim.x) b2s[i] = i < OUT ? p.b2[i] * p.b2g : 0.f;
-    for (int i = threadIdx.x; i < BW_ACC; i += blockDim.x) acc[i] = 0.f;
-    if (lane < 16) sO[32 * BSO + lane] = 0.f;
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) { b1s[i] = p.b1[i] * p.b1g; ab1[i] = 0.f; }
+    for (int i = threadIdx.x; i < OUTP; i += blockDim.x) { b2s[i] = i < OUT ? p.b2[i] * p.b2g : 0.f; ab2[i] = 0.f; }
     __syncthreads();
     const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
     float* dpl = p.d_planes ? p.d_planes + (long)n * p.hp * p.wp * PC : nullptr;
+    const long row0 = (long)n * p.P;
 
     for (long base = ((long)blockIdx.x * BM_WARPS + wid) * 32; base < p.P; base += (long)gridDim.x * (BM_WARPS * 32)) {
         const long pi = base + lane;
-        const bool valid = pi < p.P;
         const int cnt = (int)min((long)32, p.P - base);
         float cx, cy, cz;
         point_coords(p, n, pi, cx, cy, cz);
         stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
         __syncwarp();
         gather_features<SF>(pl, ss, sF, lane);
-        {   // incoming gradients -> sO[point][0] = d_sigma, [1..32] = d_rgb, [33..39] = 0
-            const float* gsrc = p.d_rgb + ((long)n * p.P + base) * C;
-#pragma unroll 16
-            for (int q = 0; q < 32; ++q) {
-                sO[q * BSO + 1 + lane] = q < cnt ? gsrc[q * C + lane] : 0.f;
-                if (lane < 7) sO[q * BSO + 33 + lane] = 0.f;
-            }
-            sO[lane * BSO] = valid ? p.d_sigma[(long)n * p.P + pi] : 0.f;
-        }
         __syncwarp();
+        if (p.x_f) {       // features as bf16 [P][32] (operand of dW1)
+            const int pt = lane >> 3, j4 = (lane & 7) * 4;
+#pragma unroll
+            for (int q0 = 0; q0 < 32; q0 += 4)
+                if (q0 + pt < cnt) {
+                    const float4 v = *reinterpret_cast<const float4*>(&sF[(q0 + pt) * SF + j4]);
+                    *reinterpret_cast<uint2*>(p.x_f + (row0 + base + q0 + pt) * C + j4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+                }
+        }
         // ---- layer 1 (recompute): c1 = b1 + F W1^T, then h = softplus(c1) kept in the accumulator registers
         float c1[2][8][4];
 #pragma unroll
@@ -415,13 +425,17 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
             for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) c1[mt][nt][i] = softplus_fast(c1[mt][nt][i]);
-                if (wgrad) {
-                    float* h0 = sH + (g + 16 * mt) * BSH + 8 * nt + 2 * t;
-                    *reinterpret_cast<float2*>(h0) = make_float2(c1[mt][nt][0], c1[mt][nt][1]);
-                    *reinterpret_cast<float2*>(h0 + 8 * BSH) = make_float2(c1[mt][nt][2], c1[mt][nt][3]);
+                if (p.x_h) {       // h as bf16 [P][64] (operand of dW2)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int row = g + 16 * mt + 8 * hh;
+                        if (row < cnt)
+                            *reinterpret_cast<uint32_t*>(p.x_h + (row0 + base + row) * HID + 8 * nt + 2 * t) =
+                                pack_bf16(c1[mt][nt][2 * hh], c1[mt][nt][2 * hh + 1]);
+                    }
                 }
             }
-        // ---- layer 2 (recompute) from registers, then d_out in place
+        // ---- layer 2 (recompute) from registers
         float o[2][5][4];
 #pragma unroll
         for (int nt = 0; nt < 5; ++nt) {
@@ -444,6 +458,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
                 for (int mt = 0; mt < 2; ++mt) mma_tf32(o[mt][nt], a[mt], __float_as_uint(b.x), __float_as_uint(b.y));
             }
         }
+        // ---- d_out in the C-fragment layout: column 0 = sigma (linear), columns 1..32 = rgb = sigmoid(o)*1.002 - 0.001
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -451,134 +466,84 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int row = g + 16 * mt + 8 * hh, col = 8 * nt + 2 * t;
-                    float2 d = *reinterpret_cast<const float2*>(&sO[row * BSO + col]);
-                    const float s0 = sigmoid_fast(o[mt][nt][2 * hh]), s1 = sigmoid_fast(o[mt][nt][2 * hh + 1]);
-                    d.x = col == 0 ? d.x : d.x * 1.002f * s0 * (1.f - s0);          // col 0 = sigma (linear)
-                    d.y = d.y * 1.002f * s1 * (1.f - s1);
-                    if (col + 1 >= OUT) d.y = 0.f;
-                    if (col >= OUT) d.x = 0.f;
-                    o[mt][nt][2 * hh] = d.x; o[mt][nt][2 * hh + 1] = d.y;
-                    if (wgrad) *reinterpret_cast<float2*>(&sO[row * BSO + col]) = d;
-                }
-        __syncwarp();
-        // ---- dW2[k][j] += sum_pt d_out[pt][k] h[pt][j]   (M = k: 3 m-tiles, N = j: 8 n-tiles, K = points: 4 k-steps), db2
-        if (wgrad) {
-            float cw[3][8][4];
-#pragma unroll
-            for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) cw[mt][nt][i] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t a[3][4];
-#pragma unroll
-                for (int mt = 0; mt < 3; ++mt) {
-                    const float* r0 = sO + (t + 8 * ks) * BSO + g + 16 * mt;
-                    a[mt][0] = tf32_rna(r0[0]); a[mt][1] = tf32_rna(r0[8]); a[mt][2] = tf32_rna(r0[4 * BSO]); a[mt][3] = tf32_rna(r0[4 * BSO + 8]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    const float* r0 = sH + (t + 8 * ks) * BSH + g + 8 * nt;
-                    const uint32_t b0 = tf32_rna(r0[0]), b1 = tf32_rna(r0[4 * BSH]);
-#pragma unroll
-                    for (int mt = 0; mt < 3; ++mt) mma_tf32(cw[mt][nt], a[mt], b0, b1);
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < 3; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int k = g + 16 * mt + ((i & 2) ? 8 : 0), j = 8 * nt + 2 * t + (i & 1);
-                        if (k < OUT) atomicAdd(&aW2[k * HID + j], cw[mt][nt][i]);
+                    const bool rv = row < cnt;
+                    const long prow = row0 + base + row;
+                    float d0 = 0.f, d1 = 0.f;
+                    if (rv) {
+                        if (col == 0) d0 = __ldg(p.d_sigma + prow);
+                        else if (col < OUT) d0 = __ldg(p.d_rgb + prow * C + col - 1);
+                        if (col + 1 < OUT) d1 = __ldg(p.d_rgb + prow * C + col);
                     }
-            float sb = 0.f, sb32 = 0.f;
-            for (int q = 0; q < 32; ++q) { sb += sO[q * BSO + lane]; sb32 += sO[q * BSO + 32]; }
-            atomicAdd(&ab2[lane], sb);
-            if (lane == 0) atomicAdd(&ab2[32], sb32);
+                    const float s0 = sigmoid_fast(o[mt][nt][2 * hh]), s1 = sigmoid_fast(o[mt][nt][2 * hh + 1]);
+                    if (col != 0) d0 *= 1.002f * s0 * (1.f - s0);
+                    d1 *= 1.002f * s1 * (1.f - s1);
+                    o[mt][nt][2 * hh] = d0; o[mt][nt][2 * hh + 1] = d1;
+                    if (p.x_do && rv) *reinterpret_cast<uint32_t*>(p.x_do + prow * OUTP + col) = pack_bf16(d0, d1);
+                }
+        if (wgrad) {       // db2[k] += sum over the warp's rows
+#pragma unroll
+            for (int nt = 0; nt < 5; ++nt) {
+                const float s0 = sum_over_g(o[0][nt][0] + o[0][nt][2] + o[1][nt][0] + o[1][nt][2]);
+                const float s1 = sum_over_g(o[0][nt][1] + o[0][nt][3] + o[1][nt][1] + o[1][nt][3]);
+                if (g == 0) { atomicAdd(&ab2[8 * nt + 2 * t], s0); atomicAdd(&ab2[8 * nt + 2 * t + 1], s1); }
+            }
         }
-        // ---- dh = d_out W2 (K = 40: the 5 n-tiles of O are the k-steps), d_a = dh * (1 - exp(-h)) in place of h
-        {
-            float dh[2][8][4];
+        // ---- dh = d_out W2 (K = 40: the 5 n-tiles of O are the k-steps), two n-tiles at a time; d_a = dh * (1 - exp(-h)) replaces h
+        uint32_t ao[2][5][4];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) dh[mt][nt][i] = 0.f;
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
             for (int ks = 0; ks < 5; ++ks) {
-                uint32_t a[2][4];
+                ao[mt][ks][0] = tf32_rna(o[mt][ks][0]); ao[mt][ks][1] = tf32_rna(o[mt][ks][2]);
+                ao[mt][ks][2] = tf32_rna(o[mt][ks][1]); ao[mt][ks][3] = tf32_rna(o[mt][ks][3]);
+            }
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    a[mt][0] = tf32_rna(o[mt][ks][0]); a[mt][1] = tf32_rna(o[mt][ks][2]);
-                    a[mt][2] = tf32_rna(o[mt][ks][1]); a[mt][3] = tf32_rna(o[mt][ks][3]);
-                }
+        for (int nt0 = 0; nt0 < 8; nt0 += 2) {
+            float dh[2][2][4];
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    const float* r0 = W2s + (8 * ks + 2 * t) * SW2 + g + 8 * nt;
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dh[mt][u][i] = 0.f;
+#pragma unroll
+            for (int ks = 0; ks < 5; ++ks)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const float* r0 = W2s + (8 * ks + 2 * t) * SW2 + g + 8 * (nt0 + u);
                     const uint32_t b0 = __float_as_uint(r0[0]), b1 = __float_as_uint(r0[SW2]);
 #pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) mma_tf32(dh[mt][nt], a[mt], b0, b1);
+                    for (int mt = 0; mt < 2; ++mt) mma_tf32(dh[mt][u], ao[mt][ks], b0, b1);
                 }
-            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c1[mt][nt0 + u][i] = dh[mt][u][i] * (1.f - __expf(-c1[mt][nt0 + u][i]));
+        }
+        if (p.x_da) {      // d_a as bf16 [P][64] (operand of dW1)
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) c1[mt][nt][i] = dh[mt][nt][i] * (1.f - __expf(-c1[mt][nt][i]));
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int row = g + 16 * mt + 8 * hh;
+                        if (row < cnt)
+                            *reinterpret_cast<uint32_t*>(p.x_da + (row0 + base + row) * HID + 8 * nt + 2 * t) =
+                                pack_bf16(c1[mt][nt][2 * hh], c1[mt][nt][2 * hh + 1]);
+                    }
         }
-        // ---- dW1[j][c] += sum_pt d_a[pt][j] f[pt][c]   (M = j: 4 m-tiles, N = c: 4 n-tiles, K = points), db1
-        if (wgrad) {
-            __syncwarp();                         // every lane finished reading h from sH
+        if (wgrad) {       // db1[j] += sum over the warp's rows
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    float* h0 = sH + (g + 16 * mt) * BSH + 8 * nt + 2 * t;
-                    *reinterpret_cast<float2*>(h0) = make_float2(c1[mt][nt][0], c1[mt][nt][1]);
-                    *reinterpret_cast<float2*>(h0 + 8 * BSH) = make_float2(c1[mt][nt][2], c1[mt][nt][3]);
-                }
-            __syncwarp();
-            float cw[4][4][4];
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) cw[mt][nt][i] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                uint32_t b[4][2];
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const float* r0 = sF + (t + 8 * ks) * SF + g + 8 * nt;
-                    b[nt][0] = tf32_rna(r0[0]); b[nt][1] = tf32_rna(r0[4 * SF]);
-                }
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt) {
-                    const float* r0 = sH + (t + 8 * ks) * BSH + g + 16 * mt;
-                    uint32_t a[4] = {tf32_rna(r0[0]), tf32_rna(r0[8]), tf32_rna(r0[4 * BSH]), tf32_rna(r0[4 * BSH + 8])};
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma_tf32(cw[mt][nt], a, b[nt][0], b[nt][1]);
-                }
+            for (int nt = 0; nt < 8; ++nt) {
+                const float s0 = sum_over_g(c1[0][nt][0] + c1[0][nt][2] + c1[1][nt][0] + c1[1][nt][2]);
+                const float s1 = sum_over_g(c1[0][nt][1] + c1[0][nt][3] + c1[1][nt][1] + c1[1][nt][3]);
+                if (g == 0) { atomicAdd(&ab1[8 * nt + 2 * t], s0); atomicAdd(&ab1[8 * nt + 2 * t + 1], s1); }
             }
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        atomicAdd(&aW1[(g + 16 * mt + ((i & 2) ? 8 : 0)) * C + 8 * nt + 2 * t + (i & 1)], cw[mt][nt][i]);
-            float s0 = 0.f, s1 = 0.f;
-            for (int q = 0; q < 32; ++q) { s0 += sH[q * BSH + lane]; s1 += sH[q * BSH + 32 + lane]; }
-            atomicAdd(&ab1[lane], s0); atomicAdd(&ab1[32 + lane], s1);
         }
-        // ---- d_f = d_a W1 (K = 64: the 8 n-tiles of layer 1 are the k-steps) -> staging tile sO[point][channel]
+        // ---- d_f = d_a W1 (K = 64: the 8 n-tiles of layer 1 are the k-steps) -> staging tile sF[point][channel]
         {
             float df[2][4][4];
 #pragma unroll
@@ -603,27 +568,24 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
                     for (int mt = 0; mt < 2; ++mt) mma_tf32(df[mt][nt], a[mt], b0, b1);
                 }
             }
-            __syncwarp();                         // dW2 / db2 finished reading sO
+            __syncwarp();                         // every lane is done with the feature tile (A fragments, bf16 export)
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int row = g + 16 * mt + 8 * hh;
-                        const bool rv = base + row < p.P;
-                        *reinterpret_cast<float2*>(&sO[row * BSO + 8 * nt + 2 * t]) =
-                            rv ? make_float2(df[mt][nt][2 * hh], df[mt][nt][2 * hh + 1]) : make_float2(0.f, 0.f);
-                    }
+                    for (int hh = 0; hh < 2; ++hh)
+                        *reinterpret_cast<float2*>(&sF[(g + 16 * mt + 8 * hh) * SF + 8 * nt + 2 * t]) =
+                            make_float2(df[mt][nt][2 * hh], df[mt][nt][2 * hh + 1]);      // rows >= cnt carry exact zeros (d_out == 0)
         }
         __syncwarp();
         // ---- scatter d_f (the 1/3 of the plane mean is folded into the staged weights)
-        if (dpl) scatter_features<BSO>(dpl, ss, sO, lane, cnt);
+        if (dpl) scatter_features<SF>(dpl, ss, sF, lane, cnt);
         if (p.d_coords) {
             for (int q = 0; q < cnt; ++q) {
                 const float gx = __shfl_sync(0xffffffffu, cx, q), gy = __shfl_sync(0xffffffffu, cy, q), gz = __shfl_sync(0xffffffffu, cz, q);
                 const Bilin b0 = make_bilin(gx, gy, p.hp, p.wp), b1 = make_bilin(gx, gz, p.hp, p.wp), b2 = make_bilin(gz, gx, p.hp, p.wp);
-                const float gq = sO[q * BSO + lane] * (1.f / 3.f);
+                const float gq = sF[q * SF + lane] * (1.f / 3.f);
                 float ax, ay, bx, by, ex, ey;
                 bilin_dcoord(pl + lane, b0, p.wp, ax, ay);
                 bilin_dcoord(pl + C + lane, b1, p.wp, bx, by);
@@ -643,9 +605,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
     }
     if (wgrad) {
         __syncthreads();
-        for (int i = threadIdx.x; i < HID * C; i += blockDim.x) atomicAdd(p.dW1 + i, aW1[i] * p.w1g);
         for (int i = threadIdx.x; i < HID; i += blockDim.x) atomicAdd(p.db1 + i, ab1[i] * p.b1g);
-        for (int i = threadIdx.x; i < OUT * HID; i += blockDim.x) atomicAdd(p.dW2 + i, aW2[i] * p.w2g);
         for (int i = threadIdx.x; i < OUT; i += blockDim.x) atomicAdd(p.db2 + i, ab2[i] * p.b2g);
     }
 }
@@ -691,28 +651,72 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     return 0;
 }
 
+static __global__ void decoder_wgrad_finalize_kernel(const float* __restrict__ t1, const float* __restrict__ t2, float* __restrict__ dW1,
+                                              float* __restrict__ dW2, float w1g, float w2g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < HID * C) dW1[i] += t1[i] * w1g;                 // t1 = d_a^T F  [64][32]
+    if (i < OUT * HID) dW2[i] += t2[i] * w2g;               // t2 = dO^T h   [40][64], rows >= 33 are padding
+}
+
+extern "C" int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod, int n,
+                                  int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+
+// Workspace of b200_triplane_mlp_bwd when decoder-parameter gradients are requested: four bf16 [rows][.] operand tensors
+// (rows = n*P rounded up to 64) + two fp32 partial-result tiles.
+B200_API long b200_triplane_bwd_workspace_bytes(int n, long P) {
+    const long rows = ((long)n * P + 63) / 64 * 64;
+    return rows * (C + HID + OUTP + HID) * 2 + (long)(HID * C + OUTP * HID) * 4;
+}
+
 // d_planes [n][hp][wp][96] is ACCUMULATED into (zero it first); d_coords [n][P][3] is written (may be null);
-// dW1/db1/dW2/db2 are ACCUMULATED into (all four null => parameter gradients skipped).
+// dW1/db1/dW2/db2 are ACCUMULATED into (all four null => parameter gradients skipped; otherwise `workspace` of at least
+// b200_triplane_bwd_workspace_bytes(n, P) bytes is required: dW1 = d_a^T F and dW2 = dO^T h are contracted over the points by
+// the tcgen05 weight-gradient kernel from bf16 operands this kernel exports).
 B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                                    const float* ray_d, const float* depths, int S, long P, float box_warp,
                                    const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
                                    const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
-                                   float* dW1, float* db1, float* dW2, float* db2, void* stream) {
+                                   float* dW1, float* db1, float* dW2, float* db2, void* workspace, long workspace_bytes,
+                                   void* stream) {
     TriplaneParams p{};
     if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
     B200_REQUIRE(d_rgb && d_sigma, "triplane_bwd: null incoming gradient");
     B200_REQUIRE((dW1 && db1 && dW2 && db2) || (!dW1 && !db1 && !dW2 && !db2), "triplane_bwd: pass all four parameter gradients or none");
     if (P == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
+    const long rows = (long)n * P, rows_pad = (rows + 63) / 64 * 64;
+    float* t1 = nullptr; float* t2 = nullptr;
+    if (dW1) {
+        B200_REQUIRE(workspace && workspace_bytes >= b200_triplane_bwd_workspace_bytes(n, P), "triplane_bwd: workspace missing or too small");
+        B200_REQUIRE(rows_pad / 64 < (1L << 31), "triplane_bwd: too many points");
+        __nv_bfloat16* ws = (__nv_bfloat16*)workspace;
+        p.x_f = ws; p.x_h = p.x_f + rows_pad * C; p.x_do = p.x_h + rows_pad * HID; p.x_da = p.x_do + rows_pad * OUTP;
+        t1 = (float*)(p.x_da + rows_pad * HID); t2 = t1 + HID * C;
+        if (rows_pad > rows) {                       // padding rows must read as zeros in the GEMMs
+            B200_CUDA(cudaMemsetAsync(p.x_f + rows * C, 0, (rows_pad - rows) * C * 2, st));
+            B200_CUDA(cudaMemsetAsync(p.x_h + rows * HID, 0, (rows_pad - rows) * HID * 2, st));
+            B200_CUDA(cudaMemsetAsync(p.x_do + rows * OUTP, 0, (rows_pad - rows) * OUTP * 2, st));
+            B200_CUDA(cudaMemsetAsync(p.x_da + rows * HID, 0, (rows_pad - rows) * HID * 2, st));
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
         attr_set = true;
     }
     const long gb = (P + BM_WARPS * 32 - 1) / (BM_WARPS * 32);
-    dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one 8-warp CTA per SM
-    triplane_mlp_bwd_mma_kernel<<<grid, BM_WARPS * 32, BM_SMEM, (cudaStream_t)stream>>>(p);
+    dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one 16-warp CTA per SM
+    triplane_mlp_bwd_mma_kernel<<<grid, BM_WARPS * 32, BM_SMEM, st>>>(p);
     B200_CHECK_LAUNCH();
+    if (dW1) {
+        const int hh = (int)(rows_pad / 64);
+        // dW1[j][c] = sum_p d_a[p][j] F[p][c]   and   dW2[k][j] = sum_p dO[p][k] h[p][j]   (1x1 "convolutions" over the point axis)
+        if (int e = b200_conv_wgrad_tc(p.x_f, nullptr, p.x_da, nullptr, t1, 1, hh, 64, C, HID, 1, 1, 1, stream)) return e;
+        if (int e = b200_conv_wgrad_tc(p.x_h, nullptr, p.x_do, nullptr, t2, 1, hh, 64, HID, OUTP, 1, 1, 1, stream)) return e;
+        decoder_wgrad_finalize_kernel<<<(OUTP * HID + 255) / 256, 256, 0, st>>>(t1, t2, dW1, dW2, p.w1g, p.w2g);
+        B200_CHECK_LAUNCH();
+    }
     return 0;
 }

@@ -127,12 +127,15 @@ int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const floa
                           const float* ray_d, const float* depths, int S, long P, float box_warp,
                           const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
                           float* rgb, float* sigma, void* stream);
-/* d_planes is ACCUMULATED (zero it first; may be NULL); d_coords [n][P][3] written (may be NULL); dW1..db2 ACCUMULATED (all or none). */
+/* d_planes is ACCUMULATED (zero it first; may be NULL); d_coords [n][P][3] written (may be NULL); dW1..db2 ACCUMULATED (all or
+ * none).  With parameter gradients, `workspace` (>= b200_triplane_bwd_workspace_bytes(n, P) bytes of device memory) receives the
+ * bf16 operands of dW1 = d_a^T F and dW2 = d_out^T h, which the tcgen05 weight-gradient kernel contracts over the points. */
+long b200_triplane_bwd_workspace_bytes(int n, long P);
 int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                           const float* ray_d, const float* depths, int S, long P, float box_warp,
                           const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
                           const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
-                          float* dW1, float* db1, float* dW2, float* db2, void* stream);
+                          float* dW1, float* db1, float* dW2, float* db2, void* workspace, long workspace_bytes, void* stream);
 
 /* ---- per-ray kernels (renderer.py:143-308 ImportanceRenderer, ray_marcher.py:25-57 MipRayMarcher2) ---------------- */
 /* t[ray][s] = t_base[s] + u[ray][s] * delta          (renderer.py:224-247 sample_stratified, numeric ray_start/ray_end) */
