@@ -191,19 +191,34 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
         const bool d_pass = (D == D) && D >= dmin && D <= dmax;
         const float gD = (d_pass && p.d_depth) ? p.d_depth[ray] : 0.f;
         const float gW = p.d_wsum ? p.d_wsum[ray] : 0.f;
-        const float g = 2.f * p.d_feat[ray * 32 + lane];        // through rgb*2-1
-        const float gsum = p.white_back ? warp_sum(g) : 0.f;     // through + 1 - wsum
-        // colours: d c_i = omega_rank(i) * g ; d omega_rank(i) = sum_lane g * c_i
-#pragma unroll 8
-        for (int i = 0; i < S; ++i) {
+        // through rgb*2-1: every lane keeps the ray's 32 channel gradients in registers
+        float gv[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p.d_feat + ray * 32) + q);
+            gv[4 * q] = 2.f * v.x; gv[4 * q + 1] = 2.f * v.y; gv[4 * q + 2] = 2.f * v.z; gv[4 * q + 3] = 2.f * v.w;
+        }
+        float gsum = 0.f;                                        // through + 1 - wsum
+        if (p.white_back) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) gsum += gv[q];
+        }
+        // colours, lane == sample: d c_i = omega_rank(i) * g ; d omega_rank(i) = sum_ch g[ch] * c_i[ch]   (no cross-lane reduction)
+        for (int i = lane; i < S; i += 32) {
             const int r = rk[i];
             const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
             const bool co = i < p.S1;
-            const long idx = co ? (ray * p.S1 + i) * 32 + lane : (ray * p.S2 + i - p.S1) * 32 + lane;
-            const float c = co ? p.rgb_c[idx] : p.rgb_f[idx];
-            (co ? p.d_rgb_c : p.d_rgb_f)[idx] = om * g;
-            const float t = warp_sum(g * c);
-            if (lane == 0) dom[r] = t;
+            const long row = co ? (ray * p.S1 + i) * 32 : (ray * p.S2 + i - p.S1) * 32;
+            const float4* crow = reinterpret_cast<const float4*>((co ? p.rgb_c : p.rgb_f) + row);
+            float4* drow = reinterpret_cast<float4*>((co ? p.d_rgb_c : p.d_rgb_f) + row);
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 c = __ldg(crow + q);
+                t = fmaf(gv[4 * q], c.x, t); t = fmaf(gv[4 * q + 1], c.y, t); t = fmaf(gv[4 * q + 2], c.z, t); t = fmaf(gv[4 * q + 3], c.w, t);
+                drow[q] = make_float4(om * gv[4 * q], om * gv[4 * q + 1], om * gv[4 * q + 2], om * gv[4 * q + 3]);
+            }
+            dom[r] = t;
         }
         __syncwarp();
         // d w_k, stored in dsb[]
