@@ -26,18 +26,25 @@ constexpr int B_BYTES = MAX_BN * TILE_K * 2;              // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // hi + lo of both operands
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-struct TcPixParams {
-    CUtensorMap tmA[2];          // hi, lo : 4-D {C, W, H, N}
-    CUtensorMap tmB[2];          // hi, lo : 2-D {inner, rows}
-    int th, tw, tiles_x;
-    int Hi, Wi;
-    int kchunks, ntaps, npass;
+// One "class" = one iteration grid with its tap list.  Plain convolutions have a single class; the stride-2 transposed
+// convolution has four (output parities), merged into ONE launch so that their CTAs fill the GPU together.
+struct TcClass {
+    int th, tw, tiles_x, Hi, Wi, ntaps, ooy, oox;
     int dy[9], dx[9], wt[9];
+};
+
+struct TcPixParams {
+    CUtensorMap tmA[4][2];       // per class: hi, lo : 4-D {C, W, H, N}  (the box depends on the class's tile shape)
+    CUtensorMap tmB[2];          // hi, lo : 2-D {inner, rows}
+    TcClass c[4];
+    int cta_start[5];            // prefix sums of (tiles * ksplit) per class
+    int ncls;
+    int kchunks, npass;
     int s;                       // source pixel = iteration pixel * s + (dy, dx)
     int b_rows_per_tap;          // K-major B: total N; MN-major B: total K per tap
     int b_taps;                  // tap slices per sample in B
     int BN, N;
-    float* C; long ldc, c_bs; int Wo, osy, osx, ooy, oox;
+    float* C; long ldc, c_bs; int Wo, osy, osx;
     int ksplit;                  // > 1: the k-blocks of a tile are spread over ksplit CTAs, partial sums reduced with red.global.add
 };
 
@@ -59,11 +66,15 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x / p.ksplit, ksi = blockIdx.x % p.ksplit;
-    const int x0 = (tile % p.tiles_x) * p.tw, y0 = (tile / p.tiles_x) * p.th;
+    int cls = 0;
+    while (cls + 1 < p.ncls && (int)blockIdx.x >= p.cta_start[cls + 1]) ++cls;
+    const TcClass& kc = p.c[cls];
+    const int local = blockIdx.x - p.cta_start[cls];
+    const int tile = local / p.ksplit, ksi = local % p.ksplit;
+    const int x0 = (tile % kc.tiles_x) * kc.tw, y0 = (tile / kc.tiles_x) * kc.th;
     const int n0 = blockIdx.y * p.BN;
     const int b = blockIdx.z;
-    const int nk_all = p.ntaps * p.kchunks;
+    const int nk_all = kc.ntaps * p.kchunks;
     const int per = (nk_all + p.ksplit - 1) / p.ksplit;
     const int it0 = ksi * per;
     const int nk = max(min(nk_all, it0 + per) - it0, 0);
@@ -72,8 +83,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
-        tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
-        if (p.npass == 3) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmB[1]); }
+        tma_prefetch_desc(&p.tmA[cls][0]); tma_prefetch_desc(&p.tmB[0]);
+        if (p.npass == 3) { tma_prefetch_desc(&p.tmA[cls][1]); tma_prefetch_desc(&p.tmB[1]); }
     }
     if (warp == 1) tmem_alloc(tmem_slot, 128);
     tc_fence_before();
@@ -92,15 +103,15 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
                 mbar_arrive_expect_tx(full(s), bytes);
                 const int t = (it0 + it) / p.kchunks, c0 = ((it0 + it) % p.kchunks) * TILE_K;
                 const uint32_t st = base + s * STAGE_BYTES;
-                const int ax = x0 * p.s + p.dx[t], ay = y0 * p.s + p.dy[t];
+                const int ax = x0 * p.s + kc.dx[t], ay = y0 * p.s + kc.dy[t];
                 const int nh = p.npass == 3 ? 2 : 1;
                 for (int h = 0; h < nh; ++h) {
-                    tma_load_4d(st + h * A_BYTES, &p.tmA[h], full(s), c0, ax, ay, b);
+                    tma_load_4d(st + h * A_BYTES, &p.tmA[cls][h], full(s), c0, ax, ay, b);
                     const uint32_t bdst = st + 2 * A_BYTES + h * B_BYTES;
                     if (!B_MN) {
-                        tma_load_2d(bdst, &p.tmB[h], full(s), c0, (b * p.b_taps + p.wt[t]) * p.b_rows_per_tap + n0);
+                        tma_load_2d(bdst, &p.tmB[h], full(s), c0, (b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + n0);
                     } else {
-                        const int krow = (b * p.b_taps + p.wt[t]) * p.b_rows_per_tap + c0;
+                        const int krow = (b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + c0;
                         for (int j = 0; j < p.BN / 64; ++j) tma_load_2d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), n0 + j * 64, krow);
                     }
                 }
@@ -136,9 +147,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int m = q * 32 + lane;
-        const int iy = y0 + m / p.tw, ix = x0 + m % p.tw;
-        const bool valid = iy < p.Hi && ix < p.Wi;
-        const long opix = (long)(iy * p.osy + p.ooy) * p.Wo + (ix * p.osx + p.oox);
+        const int iy = y0 + m / kc.tw, ix = x0 + m % kc.tw;
+        const bool valid = iy < kc.Hi && ix < kc.Wi;
+        const long opix = (long)(iy * p.osy + kc.ooy) * p.Wo + (ix * p.osx + kc.oox);
         float* crow = p.C + (long)b * p.c_bs + opix * p.ldc + n0;
         const bool vec = (p.N & 3) == 0;
         for (int c0 = 0; c0 < p.BN; c0 += 32) {
@@ -377,8 +388,7 @@ int launch_pix(const TcPixParams& p, int batch, cudaStream_t st) {
         B200_CUDA(cudaFuncSetAttribute(conv_tc_pix_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    const int tiles_y = (p.Hi + p.th - 1) / p.th;
-    dim3 grid(p.tiles_x * tiles_y * p.ksplit, (p.N + p.BN - 1) / p.BN, batch);
+    dim3 grid(p.cta_start[p.ncls], (p.N + p.BN - 1) / p.BN, batch);
     conv_tc_pix_kernel<B_MN><<<grid, 192, SMEM_BYTES, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
@@ -418,38 +428,46 @@ B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_
     TcPixParams p{};
     p.kchunks = (cin + 63) / 64; p.npass = npass; p.s = 1; p.b_rows_per_tap = cout; p.b_taps = taps;
     p.BN = pick_bn(cout); p.N = cout; p.C = y; p.ldc = cout;
+    const int ntn = (cout + p.BN - 1) / p.BN;
     for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
         if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, p.BN)) return e;
+    int tiles[4];
     if (up == 1) {
-        p.Hi = h; p.Wi = w; pick_tile(h, w, p.th, p.tw); p.tiles_x = (w + p.tw - 1) / p.tw;
-        p.ntaps = taps; p.c_bs = (long)h * w * cout; p.Wo = w; p.osy = p.osx = 1; p.ooy = p.oox = 0;
-        for (int t = 0; t < taps; ++t) { p.dy[t] = t / ksize - ksize / 2; p.dx[t] = t % ksize - ksize / 2; p.wt[t] = t; }
+        p.ncls = 1;
+        TcClass& c = p.c[0];
+        c.Hi = h; c.Wi = w; pick_tile(h, w, c.th, c.tw); c.tiles_x = (w + c.tw - 1) / c.tw;
+        c.ntaps = taps; c.ooy = c.oox = 0;
+        for (int t = 0; t < taps; ++t) { c.dy[t] = t / ksize - ksize / 2; c.dx[t] = t % ksize - ksize / 2; c.wt[t] = t; }
+        p.c_bs = (long)h * w * cout; p.Wo = w; p.osy = p.osx = 1;
+        tiles[0] = c.tiles_x * ((h + c.th - 1) / c.th);
+        p.ksplit = pick_ksplit(tiles[0] * ntn * n, taps * p.kchunks);
+    } else {
+        // stride-2 transposed convolution: four output-parity classes (4, 2, 2, 1 taps), one launch
+        p.ncls = 4;
+        p.c_bs = (long)(2 * h + 1) * (2 * w + 1) * cout; p.Wo = 2 * w + 1; p.osy = p.osx = 2;
+        int total = 0;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                TcClass& c = p.c[py * 2 + px];
+                c.Hi = h + 1 - py; c.Wi = w + 1 - px; pick_tile(c.Hi, c.Wi, c.th, c.tw); c.tiles_x = (c.Wi + c.tw - 1) / c.tw;
+                c.ooy = py; c.oox = px;
+                int t = 0;
+                for (int kh = py; kh < 3; kh += 2)
+                    for (int kw = px; kw < 3; kw += 2) { c.dy[t] = -(kh >> 1); c.dx[t] = -(kw >> 1); c.wt[t] = kh * 3 + kw; ++t; }
+                c.ntaps = t;
+                tiles[py * 2 + px] = c.tiles_x * ((c.Hi + c.th - 1) / c.th);
+                total += tiles[py * 2 + px];
+            }
+        p.ksplit = pick_ksplit(total * ntn * n, p.kchunks);      // the (1,1) class has a single tap: at least kchunks k-blocks
+    }
+    p.cta_start[0] = 0;
+    for (int k = 0; k < p.ncls; ++k) {
+        p.cta_start[k + 1] = p.cta_start[k] + tiles[k] * p.ksplit;
         for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
-            if (int e = make_map_nhwc(&p.tmA[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
-        p.ksplit = pick_ksplit(p.tiles_x * ((h + p.th - 1) / p.th) * ((cout + p.BN - 1) / p.BN) * n, taps * p.kchunks);
-        if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * h * w * cout, st));
-        return launch_pix<false>(p, n, st);
+            if (int e = make_map_nhwc(&p.tmA[k][i], i ? x_lo : x_hi, n, h, w, cin, p.c[k].tw, p.c[k].th, 1)) return e;
     }
-    p.c_bs = (long)(2 * h + 1) * (2 * w + 1) * cout; p.Wo = 2 * w + 1; p.osy = p.osx = 2;
-    {   // split-K decided once for the four parity classes (the (0,0) class has the most tiles and taps)
-        int th0, tw0; pick_tile(h + 1, w + 1, th0, tw0);
-        const int ctas = ((w + 1 + tw0 - 1) / tw0) * ((h + 1 + th0 - 1) / th0) * ((cout + p.BN - 1) / p.BN) * n;
-        p.ksplit = pick_ksplit(ctas, p.kchunks);       // per class at least kchunks k-blocks (the (1,1) class has one tap)
-        if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * p.c_bs, st));
-    }
-    for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) {
-            p.Hi = h + 1 - py; p.Wi = w + 1 - px; pick_tile(p.Hi, p.Wi, p.th, p.tw); p.tiles_x = (p.Wi + p.tw - 1) / p.tw;
-            p.ooy = py; p.oox = px;
-            int t = 0;
-            for (int kh = py; kh < 3; kh += 2)
-                for (int kw = px; kw < 3; kw += 2) { p.dy[t] = -(kh >> 1); p.dx[t] = -(kw >> 1); p.wt[t] = kh * 3 + kw; ++t; }
-            p.ntaps = t;
-            for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
-                if (int e = make_map_nhwc(&p.tmA[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
-            if (int e = launch_pix<false>(p, n, st)) return e;
-        }
-    return 0;
+    if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * p.c_bs, st));
+    return launch_pix<false>(p, n, st);
 }
 
 // dgrad on split-bf16 operands.  dy_* bf16 ([h][w][cout], or the (2h+1)x(2w+1) grid when up == 2), w_* as above, dx fp32.
@@ -463,17 +481,21 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
     TcPixParams p{};
     p.kchunks = (cout + 63) / 64; p.npass = npass; p.s = up; p.b_rows_per_tap = cout; p.b_taps = taps;
     p.BN = cin > 64 ? 128 : 64; p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin;
-    p.Hi = h; p.Wi = w; pick_tile(h, w, p.th, p.tw); p.tiles_x = (w + p.tw - 1) / p.tw;
-    p.ntaps = taps; p.Wo = w; p.osy = p.osx = 1; p.ooy = p.oox = 0;
+    p.ncls = 1;
+    TcClass& c = p.c[0];
+    c.Hi = h; c.Wi = w; pick_tile(h, w, c.th, c.tw); c.tiles_x = (w + c.tw - 1) / c.tw;
+    c.ntaps = taps; p.Wo = w; p.osy = p.osx = 1; c.ooy = c.oox = 0;
     for (int t = 0; t < taps; ++t) {
         const int kh = t / ksize, kw = t % ksize;
-        p.dy[t] = up == 1 ? ksize / 2 - kh : kh; p.dx[t] = up == 1 ? ksize / 2 - kw : kw; p.wt[t] = t;
+        c.dy[t] = up == 1 ? ksize / 2 - kh : kh; c.dx[t] = up == 1 ? ksize / 2 - kw : kw; c.wt[t] = t;
     }
     for (int i = 0; i < (npass == 3 ? 2 : 1); ++i) {
-        if (int e = make_map_nhwc(&p.tmA[i], i ? dy_lo : dy_hi, n, hs, ws, cout, p.tw, p.th, up)) return e;
+        if (int e = make_map_nhwc(&p.tmA[0][i], i ? dy_lo : dy_hi, n, hs, ws, cout, c.tw, c.th, up)) return e;
         if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, 64)) return e;
     }
-    p.ksplit = pick_ksplit(p.tiles_x * ((h + p.th - 1) / p.th) * ((cin + p.BN - 1) / p.BN) * n, taps * p.kchunks);
+    const int tiles0 = c.tiles_x * ((h + c.th - 1) / c.th);
+    p.ksplit = pick_ksplit(tiles0 * ((cin + p.BN - 1) / p.BN) * n, taps * p.kchunks);
+    p.cta_start[0] = 0; p.cta_start[1] = tiles0 * p.ksplit;
     if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)n * h * w * cin, st));
     return launch_pix<true>(p, n, st);
 }
