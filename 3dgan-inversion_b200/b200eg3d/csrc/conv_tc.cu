@@ -189,6 +189,8 @@ struct TcWgradParams {
     int ntaps, ksplit, npass;
     int BN, Cm, Cn;
     float* C; long c_bs;         // C[b][tap][Cm][Cn]
+    int tg;                      // taps per CTA (single-pass only): the operand that does not move with the tap is loaded once
+    int shared_a;                // 1: A (dy) is common to the taps of a group, B (x) shifts (up == 1); 0: the reverse (up == 2)
 };
 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
@@ -205,13 +207,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TILE_M, n0 = blockIdx.y * p.BN;
+    const int ngroups = p.ntaps / p.tg;
     int z = blockIdx.z;
     const int ks = z % p.ksplit; z /= p.ksplit;
-    const int t = z % p.ntaps;
-    const int b = z / p.ntaps;
+    const int t0 = (z % ngroups) * p.tg;          // first tap of this CTA's group
+    const int b = z / ngroups;
     const int per = (p.ntiles + p.ksplit - 1) / p.ksplit;
     const int kb0 = ks * per, kb1 = min(p.ntiles, kb0 + per);
     const int nk = max(kb1 - kb0, 0);
+    const uint32_t tcols = p.tg * p.BN <= 128 ? 128u : (p.tg * p.BN <= 256 ? 256u : 512u);
+    const uint32_t b_tile = (uint32_t)p.BN * TILE_K * 2;      // bytes of one B tile (N-side), A tile is A_BYTES
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -219,17 +224,23 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
         fence_barrier_init();
         tma_prefetch_desc(&p.tmA[0]); tma_prefetch_desc(&p.tmB[0]);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    if (warp == 1) tmem_alloc(tmem_slot, tcols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
 
+    // Stage layout.  tg == 1 (any npass): A_hi | A_lo | B_hi | B_lo as in the pixel-GEMM kernel.
+    // tg  > 1 (single pass, hi only): shared tile first, then the tg shifted tiles.
+    auto a_addr = [&](uint32_t st, int j, int h) { return p.tg == 1 ? st + h * A_BYTES : (p.shared_a ? st : st + b_tile + j * A_BYTES); };
+    auto b_addr = [&](uint32_t st, int j, int h) { return p.tg == 1 ? st + 2 * A_BYTES + h * B_BYTES : (p.shared_a ? st + A_BYTES + j * b_tile : st); };
+
     if (nk > 0) {
         if (warp == 0) {
             if (lane == 0) {
                 const int nh = p.npass == 3 ? 2 : 1;
-                const uint32_t bytes = (uint32_t)(A_BYTES + p.BN * TILE_K * 2) * nh;
+                const uint32_t bytes = p.tg == 1 ? (A_BYTES + b_tile) * nh
+                                                 : (p.shared_a ? A_BYTES + p.tg * b_tile : p.tg * A_BYTES + b_tile);
                 for (int it = 0; it < nk; ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(empty(s), ph ^ 1);
@@ -237,13 +248,18 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
                     const int tile = kb0 + it;
                     const int x0 = (tile % p.tiles_x) * p.tw, y0 = (tile / p.tiles_x) * p.th;
                     const uint32_t st = base + s * STAGE_BYTES;
-                    for (int h = 0; h < nh; ++h) {
-                        const uint32_t adst = st + h * A_BYTES, bdst = st + 2 * A_BYTES + h * B_BYTES;
-                        for (int j = 0; j < 2; ++j)
-                            tma_load_4d(adst + j * (TILE_K * 128), &p.tmA[h], full(s), m0 + j * 64, x0 * p.sA + p.dAx[t], y0 * p.sA + p.dAy[t], b);
-                        for (int j = 0; j < p.BN / 64; ++j)
-                            tma_load_4d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), n0 + j * 64, x0 * p.sB + p.dBx[t], y0 * p.sB + p.dBy[t], b);
-                    }
+                    for (int h = 0; h < nh; ++h)
+                        for (int j = 0; j < p.tg; ++j) {
+                            const int t = t0 + j;
+                            if (j == 0 || !p.shared_a)
+                                for (int q = 0; q < 2; ++q)
+                                    tma_load_4d(a_addr(st, j, h) + q * (TILE_K * 128), &p.tmA[h], full(s), m0 + q * 64,
+                                                x0 * p.sA + p.dAx[t], y0 * p.sA + p.dAy[t], b);
+                            if (j == 0 || p.shared_a)
+                                for (int q = 0; q < p.BN / 64; ++q)
+                                    tma_load_4d(b_addr(st, j, h) + q * (TILE_K * 128), &p.tmB[h], full(s), n0 + q * 64,
+                                                x0 * p.sB + p.dBx[t], y0 * p.sB + p.dBy[t], b);
+                        }
                 }
             }
         } else if (warp == 1) {
@@ -254,16 +270,19 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
                     mbar_wait(full(s), ph);
                     tc_fence_after();
                     const uint32_t st = base + s * STAGE_BYTES;
-                    const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                    for (int j = 0; j < p.tg; ++j) {
+                        const uint32_t a_hi = a_addr(st, j, 0), b_hi = b_addr(st, j, 0);
+                        const uint32_t d = tmem + (uint32_t)(j * p.BN);
 #pragma unroll
-                    for (int k = 0; k < TILE_K / 16; ++k) {
-                        const uint32_t o = k * 2048, lbo = TILE_K * 128;
-                        const uint64_t dah = smem_desc(a_hi + o, lbo, 1024), dbh = smem_desc(b_hi + o, lbo, 1024);
-                        umma_bf16(tmem, dah, dbh, idesc, (it | k) != 0);
-                        if (p.npass == 3) {
-                            const uint64_t dal = smem_desc(a_lo + o, lbo, 1024), dbl = smem_desc(b_lo + o, lbo, 1024);
-                            umma_bf16(tmem, dah, dbl, idesc, 1);
-                            umma_bf16(tmem, dal, dbh, idesc, 1);
+                        for (int k = 0; k < TILE_K / 16; ++k) {
+                            const uint32_t o = k * 2048, lbo = TILE_K * 128;
+                            const uint64_t dah = smem_desc(a_hi + o, lbo, 1024), dbh = smem_desc(b_hi + o, lbo, 1024);
+                            umma_bf16(d, dah, dbh, idesc, (it | k) != 0);
+                            if (p.npass == 3) {
+                                const uint64_t dal = smem_desc(a_addr(st, j, 1) + o, lbo, 1024), dbl = smem_desc(b_addr(st, j, 1) + o, lbo, 1024);
+                                umma_bf16(d, dah, dbl, idesc, 1);
+                                umma_bf16(d, dal, dbh, idesc, 1);
+                            }
                         }
                     }
                     umma_commit(empty(s));
@@ -275,19 +294,21 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
             mbar_wait(accum_bar, 0);
             tc_fence_after();
             const int m = m0 + q * 32 + lane;
-            float* crow = p.C + (long)b * p.c_bs + ((long)t * p.Cm + m) * p.Cn + n0;
             const bool vec = (p.Cn & 3) == 0;
-            for (int c0 = 0; c0 < p.BN; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                if (m < p.Cm) {
-                    if (vec && n0 + c0 + 32 <= p.Cn) {
+            for (int j = 0; j < p.tg; ++j) {
+                float* crow = p.C + (long)b * p.c_bs + ((long)(t0 + j) * p.Cm + m) * p.Cn + n0;
+                for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.BN + c0), v);
+                    if (m < p.Cm) {
+                        if (vec && n0 + c0 + 32 <= p.Cn) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) red_add_v4(crow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
+                            for (int jj = 0; jj < 32; jj += 4) red_add_v4(crow + c0 + jj, v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (n0 + c0 + j < p.Cn) atomicAdd(crow + c0 + j, v[j]);
+                            for (int jj = 0; jj < 32; ++jj)
+                                if (n0 + c0 + jj < p.Cn) atomicAdd(crow + c0 + jj, v[jj]);
+                        }
                     }
                 }
             }
@@ -295,7 +316,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 128);
+    if (warp == 1) tmem_dealloc(tmem, tcols);
 }
 
 __global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, long n4) {
@@ -366,10 +387,10 @@ void pick_tile(int Hi, int Wi, int& th, int& tw) {
 }
 
 // Split-K factor for layers with too few output tiles to fill the GPU (the 4x4 .. 32x32 blocks stream 9.4 MB of weights
-// through a handful of CTAs otherwise): aim at ~one CTA per SM, keep at least 2 k-blocks per CTA.
+// through a handful of CTAs otherwise): aim at one CTA per SM (a single wave), keep at least 2 k-blocks per CTA.
 int pick_ksplit(int ctas, int nk) {
     if (ctas >= 74 || nk < 4) return 1;
-    int ks = (148 + ctas - 1) / ctas;
+    int ks = 148 / ctas;                 // floor: one wave, never 148 + a few stragglers
     if (ks > nk / 2) ks = nk / 2;
     return ks < 1 ? 1 : ks;
 }
@@ -526,8 +547,12 @@ B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
         if (int e = make_map_nhwc(&p.tmB[i], i ? x_lo : x_hi, n, h, w, cin, p.tw, p.th, 1)) return e;
     }
     const int mt = (cout + TILE_M - 1) / TILE_M, nt = (cin + p.BN - 1) / p.BN;
-    const int base_ctas = mt * nt * taps * n;
-    int ksplit = (296 + base_ctas - 1) / base_ctas;
+    // single-pass 3x3: one kernel row (3 taps) per CTA -- the operand that does not shift with the tap is fetched once
+    p.tg = (npass == 1 && taps == 9) ? 3 : 1;
+    p.shared_a = up == 1;
+    const int base_ctas = mt * nt * (taps / p.tg) * n;
+    const int target = p.tg > 1 ? 148 : 296;      // fewer, heavier CTAs when a CTA owns three taps: less split-K atomic traffic
+    int ksplit = p.tg > 1 ? target / base_ctas : (target + base_ctas - 1) / base_ctas;   // tg > 1: stay within one wave
     if (ksplit > p.ntiles) ksplit = p.ntiles;
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
@@ -537,7 +562,7 @@ B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
         B200_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    dim3 grid(mt, nt, n * taps * ksplit);
+    dim3 grid(mt, nt, n * (taps / p.tg) * ksplit);
     conv_tc_wgrad_kernel<<<grid, 192, SMEM_BYTES, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
