@@ -20,11 +20,12 @@ using namespace tc;
 
 namespace {
 
-constexpr int TILE_M = 128, TILE_K = 64, MAX_BN = 128, STAGES = 3;
+constexpr int TILE_M = 128, TILE_K = 64, MAX_BN = 128, STAGES = 3, MAX_ST = 8;
 constexpr int A_BYTES = TILE_M * TILE_K * 2;              // 16 KB
 constexpr int B_BYTES = MAX_BN * TILE_K * 2;              // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;    // hi + lo of both operands
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;         // 192 KB operand ring (the pixel-GEMM kernel cuts it into 3..8 stages)
+constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 // One "class" = one iteration grid with its tap list.  Plain convolutions have a single class; the stride-2 transposed
 // convolution has four (output parities), merged into ONE launch so that their CTAs fill the GPU together.
@@ -46,73 +47,94 @@ struct TcPixParams {
     int BN, N;
     float* C; long ldc, c_bs; int Wo, osy, osx;
     int ksplit;                  // > 1: the k-blocks of a tile are spread over ksplit CTAs, partial sums reduced with red.global.add
+    int ntn, nwork;              // N tiles; work items = cta_start[ncls] * ntn * batch
+    int stage_bytes, nstages;    // ring geometry: bytes one k-block really needs, and how many fit in RING_BYTES
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Persistent: one CTA per SM walks the work list (pixel tile x k-slice x N tile x sample) with a stride of gridDim.x.  The
+// shared-memory ring keeps running across work items (the producer prefetches the next tile while the MMAs of the current
+// one drain) and the accumulator is double-buffered in TMEM, so the epilogue of item i overlaps the main loop of item i+1.
 template <bool B_MN>
 __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_constant__ TcPixParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base - raw);
-    const uint32_t bars = base + STAGES * STAGE_BYTES;                 // full[3], empty[3], accum, then tmem slot
+    const uint32_t bars = base + STAGES * STAGE_BYTES;                 // full[MAX_ST], empty[MAX_ST], tfull[2], tempty[2], tmem slot
     auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
-    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
-    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+    auto empty = [&](int s) { return bars + 8u * (MAX_ST + s); };
+    auto tfull = [&](int a) { return bars + 8u * (2 * MAX_ST + a); };
+    auto tempty = [&](int a) { return bars + 8u * (2 * MAX_ST + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * MAX_ST + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem + STAGES * STAGE_BYTES + 8 * (2 * MAX_ST + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int cls = 0;
-    while (cls + 1 < p.ncls && (int)blockIdx.x >= p.cta_start[cls + 1]) ++cls;
-    const TcClass& kc = p.c[cls];
-    const int local = blockIdx.x - p.cta_start[cls];
-    const int tile = local / p.ksplit, ksi = local % p.ksplit;
-    const int x0 = (tile % kc.tiles_x) * kc.tw, y0 = (tile / kc.tiles_x) * kc.th;
-    const int n0 = blockIdx.y * p.BN;
-    const int b = blockIdx.z;
-    const int nk_all = kc.ntaps * p.kchunks;
-    const int per = (nk_all + p.ksplit - 1) / p.ksplit;
-    const int it0 = ksi * per;
-    const int nk = max(min(nk_all, it0 + per) - it0, 0);
+    const int nst = p.nstages;
+    const uint32_t b_tile = (uint32_t)p.BN * TILE_K * 2;
+    const uint32_t a_lo_off = A_BYTES, b_hi_off = p.npass == 3 ? 2 * A_BYTES : A_BYTES, b_lo_off = b_hi_off + b_tile;
+    const uint32_t tcols = 2 * p.BN <= 128 ? 128u : 256u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int s = 0; s < nst; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
         fence_barrier_init();
-        tma_prefetch_desc(&p.tmA[cls][0]); tma_prefetch_desc(&p.tmB[0]);
-        if (p.npass == 3) { tma_prefetch_desc(&p.tmA[cls][1]); tma_prefetch_desc(&p.tmB[1]); }
+        for (int k = 0; k < p.ncls; ++k) { tma_prefetch_desc(&p.tmA[k][0]); if (p.npass == 3) tma_prefetch_desc(&p.tmA[k][1]); }
+        tma_prefetch_desc(&p.tmB[0]);
+        if (p.npass == 3) tma_prefetch_desc(&p.tmB[1]);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    if (warp == 1) tmem_alloc(tmem_slot, tcols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
 
-    if (nk == 0) {
-        // nothing to do for this k-slice (only possible when ksplit does not divide the k-blocks evenly)
-    } else if (warp == 0) {
+    // work item -> (class, tile, k-slice, N tile, sample); every role decodes the same list
+    struct Item { int cls, x0, y0, n0, b, it0, nk; };
+    const int per_x = p.cta_start[p.ncls];
+    auto decode = [&](int w, Item& o) {
+        const int lx = w % per_x; int r = w / per_x;
+        o.n0 = (r % p.ntn) * p.BN; o.b = r / p.ntn;
+        int cls = 0;
+        while (cls + 1 < p.ncls && lx >= p.cta_start[cls + 1]) ++cls;
+        o.cls = cls;
+        const TcClass& kc = p.c[cls];
+        const int local = lx - p.cta_start[cls];
+        const int tile = local / p.ksplit, ksi = local % p.ksplit;
+        o.x0 = (tile % kc.tiles_x) * kc.tw; o.y0 = (tile / kc.tiles_x) * kc.th;
+        const int nk_all = kc.ntaps * p.kchunks;
+        const int per = (nk_all + p.ksplit - 1) / p.ksplit;
+        o.it0 = ksi * per;
+        o.nk = max(min(nk_all, o.it0 + per) - o.it0, 0);      // 0: nothing to do for this k-slice (ksplit does not divide evenly)
+    };
+
+    if (warp == 0) {
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)(A_BYTES + p.BN * TILE_K * 2) * (p.npass == 3 ? 2u : 1u);
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(empty(s), ph ^ 1);
-                mbar_arrive_expect_tx(full(s), bytes);
-                const int t = (it0 + it) / p.kchunks, c0 = ((it0 + it) % p.kchunks) * TILE_K;
-                const uint32_t st = base + s * STAGE_BYTES;
-                const int ax = x0 * p.s + kc.dx[t], ay = y0 * p.s + kc.dy[t];
-                const int nh = p.npass == 3 ? 2 : 1;
-                for (int h = 0; h < nh; ++h) {
-                    tma_load_4d(st + h * A_BYTES, &p.tmA[cls][h], full(s), c0, ax, ay, b);
-                    const uint32_t bdst = st + 2 * A_BYTES + h * B_BYTES;
-                    if (!B_MN) {
-                        tma_load_2d(bdst, &p.tmB[h], full(s), c0, (b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + n0);
-                    } else {
-                        const int krow = (b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + c0;
-                        for (int j = 0; j < p.BN / 64; ++j) tma_load_2d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), n0 + j * 64, krow);
+            const int nh = p.npass == 3 ? 2 : 1;
+            const uint32_t bytes = (uint32_t)(A_BYTES + b_tile) * nh;
+            int g = 0;                                             // running k-block counter: ring position and phase
+            for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+                Item o; decode(w, o);
+                const TcClass& kc = p.c[o.cls];
+                for (int it = 0; it < o.nk; ++it, ++g) {
+                    const int s = g % nst, ph = (g / nst) & 1;
+                    mbar_wait(empty(s), ph ^ 1);
+                    mbar_arrive_expect_tx(full(s), bytes);
+                    const int t = (o.it0 + it) / p.kchunks, c0 = ((o.it0 + it) % p.kchunks) * TILE_K;
+                    const uint32_t st = base + s * p.stage_bytes;
+                    const int ax = o.x0 * p.s + kc.dx[t], ay = o.y0 * p.s + kc.dy[t];
+                    for (int h = 0; h < nh; ++h) {
+                        tma_load_4d(st + h * a_lo_off, &p.tmA[o.cls][h], full(s), c0, ax, ay, o.b);
+                        const uint32_t bdst = st + (h ? b_lo_off : b_hi_off);
+                        if (!B_MN) {
+                            tma_load_2d(bdst, &p.tmB[h], full(s), c0, (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + o.n0);
+                        } else {
+                            const int krow = (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + c0;
+                            for (int j = 0; j < p.BN / 64; ++j) tma_load_2d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), o.n0 + j * 64, krow);
+                        }
                     }
                 }
             }
@@ -120,59 +142,82 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = instr_desc_bf16(TILE_M, p.BN, 0, B_MN ? 1 : 0);
-            for (int it = 0; it < nk; ++it) {
-                const int s = it % STAGES, ph = (it / STAGES) & 1;
-                mbar_wait(full(s), ph);
+            int g = 0, li = 0;
+            for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+                Item o; decode(w, o);
+                if (o.nk == 0) continue;
+                const int acc = li & 1;
+                mbar_wait(tempty(acc), ((li >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t st = base + s * STAGE_BYTES;
-                const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+                const uint32_t d = tmem + (uint32_t)(acc * p.BN);
+                for (int it = 0; it < o.nk; ++it, ++g) {
+                    const int s = g % nst, ph = (g / nst) & 1;
+                    mbar_wait(full(s), ph);
+                    tc_fence_after();
+                    const uint32_t st = base + s * p.stage_bytes;
+                    const uint32_t a_hi = st, a_lo = st + a_lo_off, b_hi = st + b_hi_off, b_lo = st + b_lo_off;
 #pragma unroll
-                for (int k = 0; k < TILE_K / 16; ++k) {
-                    const uint32_t ao = k * 32, bo = B_MN ? k * 2048 : k * 32;
-                    const uint32_t blbo = B_MN ? TILE_K * 128 : 0;
-                    const uint64_t dah = smem_desc(a_hi + ao, 0, 1024), dbh = smem_desc(b_hi + bo, blbo, 1024);
-                    umma_bf16(tmem, dah, dbh, idesc, (it | k) != 0);
-                    if (p.npass == 3) {
-                        const uint64_t dal = smem_desc(a_lo + ao, 0, 1024), dbl = smem_desc(b_lo + bo, blbo, 1024);
-                        umma_bf16(tmem, dah, dbl, idesc, 1);
-                        umma_bf16(tmem, dal, dbh, idesc, 1);
+                    for (int k = 0; k < TILE_K / 16; ++k) {
+                        const uint32_t ao = k * 32, bo = B_MN ? k * 2048 : k * 32;
+                        const uint32_t blbo = B_MN ? TILE_K * 128 : 0;
+                        const uint64_t dah = smem_desc(a_hi + ao, 0, 1024), dbh = smem_desc(b_hi + bo, blbo, 1024);
+                        umma_bf16(d, dah, dbh, idesc, (it | k) != 0);
+                        if (p.npass == 3) {
+                            const uint64_t dal = smem_desc(a_lo + ao, 0, 1024), dbl = smem_desc(b_lo + bo, blbo, 1024);
+                            umma_bf16(d, dah, dbl, idesc, 1);
+                            umma_bf16(d, dal, dbh, idesc, 1);
+                        }
                     }
+                    umma_commit(empty(s));
                 }
-                umma_commit(empty(s));
+                umma_commit(tfull(acc));
+                ++li;
             }
-            umma_commit(accum_bar);
         }
     } else {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
-        const int m = q * 32 + lane;
-        const int iy = y0 + m / kc.tw, ix = x0 + m % kc.tw;
-        const bool valid = iy < kc.Hi && ix < kc.Wi;
-        const long opix = (long)(iy * p.osy + kc.ooy) * p.Wo + (ix * p.osx + kc.oox);
-        float* crow = p.C + (long)b * p.c_bs + opix * p.ldc + n0;
         const bool vec = (p.N & 3) == 0;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (valid) {
-                if (vec && n0 + c0 + 32 <= p.N) {
+        int li = 0;
+        for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+            Item o; decode(w, o);
+            if (o.nk == 0) continue;
+            const TcClass& kc = p.c[o.cls];
+            const int acc = li & 1;
+            mbar_wait(tfull(acc), (li >> 1) & 1);
+            tc_fence_after();
+            const int m = q * 32 + lane;
+            const int iy = o.y0 + m / kc.tw, ix = o.x0 + m % kc.tw;
+            const bool valid = iy < kc.Hi && ix < kc.Wi;
+            const long opix = (long)(iy * p.osy + kc.ooy) * p.Wo + (ix * p.osx + kc.oox);
+            float* crow = p.C + (long)o.b * p.c_bs + opix * p.ldc + o.n0;
+            for (int c0 = 0; c0 < p.BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c0), v);
+                if (c0 + 32 >= p.BN) {                 // last read of this accumulator: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty(acc));
+                }
+                if (valid) {
+                    if (vec && o.n0 + c0 + 32 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (p.ksplit > 1) red_add_v4(crow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        else *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; j += 4) {
+                            if (p.ksplit > 1) red_add_v4(crow + c0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            else *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (o.n0 + c0 + j < p.N) { if (p.ksplit > 1) atomicAdd(crow + c0 + j, v[j]); else crow[c0 + j] = v[j]; }
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + c0 + j < p.N) { if (p.ksplit > 1) atomicAdd(crow + c0 + j, v[j]); else crow[c0 + j] = v[j]; }
                 }
             }
+            ++li;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 128);
+    if (warp == 1) tmem_dealloc(tmem, tcols);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -403,13 +448,19 @@ int pick_bn(int n) {           // N tile of the K-major-B kernels (a multiple of
 }
 
 template <bool B_MN>
-int launch_pix(const TcPixParams& p, int batch, cudaStream_t st) {
+int launch_pix(TcPixParams& p, int batch, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         B200_CUDA(cudaFuncSetAttribute(conv_tc_pix_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr = true;
     }
-    dim3 grid(p.cta_start[p.ncls], (p.N + p.BN - 1) / p.BN, batch);
+    p.ntn = (p.N + p.BN - 1) / p.BN;
+    p.nwork = p.cta_start[p.ncls] * p.ntn * batch;
+    p.stage_bytes = (A_BYTES + p.BN * TILE_K * 2) * (p.npass == 3 ? 2 : 1);
+    p.nstages = RING_BYTES / p.stage_bytes < MAX_ST ? RING_BYTES / p.stage_bytes : MAX_ST;
+    static int sms = 0;
+    if (!sms) { int dev = 0; B200_CUDA(cudaGetDevice(&dev)); B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+    const int grid = p.nwork < sms ? p.nwork : sms;
     conv_tc_pix_kernel<B_MN><<<grid, 192, SMEM_BYTES, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
