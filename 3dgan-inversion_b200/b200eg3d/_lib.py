@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libb200eg3d.so')
+LIB_PATH = os.environ.get('B200EG3D_LIB') or os.path.join(_HERE, 'libb200eg3d.so')     # env override: kernel-tuning variants
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 

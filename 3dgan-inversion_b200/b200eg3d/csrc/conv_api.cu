@@ -90,4 +90,4 @@ B200_API int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int 
 }
 
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 100; }
+B200_API int b200_version() { return 101; }

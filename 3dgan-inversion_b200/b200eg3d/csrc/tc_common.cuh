@@ -91,6 +91,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// zero 32 lanes x 16 consecutive fp32 columns (accumulator initialisation when several threads issue accumulating MMAs)
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100): start address, leading / stride byte offsets.
 //   K-major  tile [rows][64 bf16]: rows are 128 B apart, 8-row groups SBO = 1024 B apart (LBO unused)
 //   MN-major tile [k rows][64 bf16]: 8-row k groups SBO = 1024 B apart, 64-element MN blocks LBO apart

@@ -10,6 +10,7 @@
 //   decoder MLP      : mma.sync m16n8k8 TF32 tiles over the 32 points (see "Tensor-core decoder" below)
 // The phases are stitched through small per-warp shared-memory tiles.
 #include "common.cuh"
+#include "tc_common.cuh"
 #include <cstdlib>
 #include <cuda_bf16.h>
 
@@ -35,7 +36,6 @@ struct TriplaneParams {
     const float* d_rgb; const float* d_sigma;
     float* d_planes; float* d_coords;
     float* dW1; float* db1; float* dW2; float* db2;
-    __nv_bfloat16* x_f; __nv_bfloat16* x_h; __nv_bfloat16* x_do; __nv_bfloat16* x_da;   // bf16 exports for the dW1 / dW2 GEMMs
     int fwd_passes;                                         // 3: split-TF32 (default), 1: plain TF32 (experiments)
 };
 
@@ -184,7 +184,10 @@ __device__ __forceinline__ void scatter_features(float* __restrict__ dpl, const 
 constexpr int SF = 36, SW2 = 72, OUTP = 40;
 constexpr int FW_W = 2 * HID * SF + 2 * OUTP * SW2 + HID + OUTP;          // W1 hi|lo, W2 hi|lo, b1, b2 (floats)
 constexpr int FW_WARP = 32 * SF + 32 * SP;
-constexpr int FW_WARPS = 16;
+#ifndef B200_FW_WARPS
+#define B200_FW_WARPS 16
+#endif
+constexpr int FW_WARPS = B200_FW_WARPS;
 constexpr int FW_SMEM = (FW_W + FW_WARPS * FW_WARP) * 4;
 
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
@@ -334,14 +337,24 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
 //   d_out       dO = d_rgb * 1.002 * s(1-s) | d_sigma                               [C-fragment layout of O]
 //   chain       dh = dO W2  -> d_a = dh * (1 - exp(-h)) -> d_f = d_a W1             [A fragments straight from registers]
 //   scatter     d_f (x bilinear weights, 1/3 folded in) -> red.global.add.v4 into the plane gradient
-//   parameters  db1 / db2 reduced here; for dW1 = d_a^T F and dW2 = dO^T h the four operands are exported as bf16 [P][.]
-//               tensors and contracted over the point dimension by the tcgen05 weight-gradient kernel (conv_tc.cu), which
-//               keeps this kernel free of shared-memory transposes and lets 16 warps share an SM.
-constexpr int BM_WARPS = 16;
+//   parameters  db1 / db2 reduced here.  dW1 = d_a^T F and dW2 = dO^T h are contractions over the POINT axis: every warp
+//               stages its 32-point operand tiles as bf16 in shared memory (MN-major, 128-byte swizzle, the layout the
+//               tcgen05 weight-gradient kernel of conv_tc.cu gets from TMA) and one lane issues tcgen05.mma into a
+//               CTA-wide fp32 accumulator in TMEM -- D[j][0:48] += h^T dO, D[j][48:80] += d_a^T F -- so the reduction over
+//               all points of the CTA costs no registers, no atomics and no HBM round trip.  The accumulator is drained
+//               once at the end of the kernel (148 x 4160 global atomics).
+// Two instantiations: with decoder-parameter gradients (PTI: 12 warps, the operand tiles take 8 KB per warp) and without
+// (w-projection: 16 warps, no operand tiles, more shared memory left to the L1).
+#ifndef B200_BM_WARPS
+#define B200_BM_WARPS 12
+#endif
+constexpr int BM_WARPS_WG = B200_BM_WARPS, BM_WARPS_NOWG = 16;
 constexpr int BM_W = HID * SF + OUTP * SW2 + HID + OUTP + HID + OUTP;       // W1 [64][36], W2 [40][72], b1, b2, db1, db2
 constexpr int BM_WPAD = (BM_W + 3) / 4 * 4;
 constexpr int BM_WARP = 32 * SF + 32 * SP;                                  // f (later d_f) | set-up
-constexpr int BM_SMEM = (BM_WPAD + BM_WARPS * BM_WARP) * 4;
+constexpr int BM_OPER = 8192;                                               // per warp: A tile [32 pts][64] bf16 | B tile [32 pts][<=64] bf16
+constexpr int bm_smem(int warps, bool wg) { return (wg ? 1024 + warps * BM_OPER + 8 * warps + 16 : 0) + (BM_WPAD + warps * BM_WARP) * 4; }
+constexpr int DW2_COLS = 48, DW1_COL0 = 48, DW_TCOLS = 128;                 // TMEM columns: [0,48) dW2^T, [48,80) dW1
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -356,15 +369,45 @@ __device__ __forceinline__ float sum_over_g(float v) {
     return v;
 }
 
+template <int BM_WARPS, bool WGRAD>
 __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(TriplaneParams p) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t raw = tc::smem_u32(smem_raw);
+    uint8_t* smem_al = smem_raw + (WGRAD ? ((raw + 1023u) & ~1023u) - raw : 0u);   // swizzle-128B operand tiles need 1024-byte alignment
+    float* smem = reinterpret_cast<float*>(smem_al + (WGRAD ? BM_WARPS * BM_OPER : 0));
     float* W1s = smem; float* W2s = W1s + HID * SF; float* b1s = W2s + OUTP * SW2; float* b2s = b1s + HID;
     float* ab1 = b2s + OUTP; float* ab2 = ab1 + HID;
     const int n = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     float* sF = smem + BM_WPAD + wid * BM_WARP;                // [32][SF]
     float* ss = sF + 32 * SF;                                  // [32][SP]
-    const bool wgrad = p.db1 != nullptr;
+    constexpr bool wgrad = WGRAD;
+    // decoder weight gradients: per-warp operand tiles, one mbarrier per warp, CTA-wide TMEM accumulator
+    uint8_t* opA = smem_al + wid * BM_OPER;                    // [32 pts][64] bf16: h, later d_a          (M side)
+    uint8_t* opB = opA + 4096;                                 // [32 pts][64] bf16: dO (48 used), later F (N side)
+    const uint32_t opA_u = tc::smem_u32(opA), opB_u = opA_u + 4096;
+    uint8_t* bar_base = reinterpret_cast<uint8_t*>(smem + BM_WPAD + BM_WARPS * BM_WARP);
+    const uint32_t mybar = tc::smem_u32(bar_base) + 8u * wid;
+    const uint32_t tmem_slot = tc::smem_u32(bar_base) + 8u * BM_WARPS;
+    uint32_t ncommit = 0;                                      // tcgen05.commit count of this warp (mbarrier phase bookkeeping)
+    uint32_t tmem = 0;
+    if (wgrad) {
+        if (threadIdx.x == 0) {
+            for (int w = 0; w < BM_WARPS; ++w) tc::mbar_init(tc::smem_u32(bar_base) + 8u * w, 1);
+            tc::fence_barrier_init();
+        }
+        for (int i = lane; i < 4096 / 16; i += 32) reinterpret_cast<uint4*>(opB)[i] = make_uint4(0u, 0u, 0u, 0u);   // dO columns 40..47 stay zero
+        if (wid == 0) tc::tmem_alloc(tmem_slot, DW_TCOLS);
+        tc::tc_fence_before();
+        __syncthreads();
+        tc::tc_fence_after();
+        tmem = *reinterpret_cast<volatile uint32_t*>(bar_base + 8 * BM_WARPS);
+        if (wid < 2) {                                         // zero rows 0..63 (TMEM lanes of warps 0, 1) of the 80 accumulator columns
+            for (int c0 = 0; c0 < 80; c0 += 16) tc::tmem_st16_zero(tmem + ((uint32_t)(wid * 32) << 16) + (uint32_t)c0);
+            tc::tmem_wait_st();
+        }
+        tc::tc_fence_before();
+    }
     for (int i = threadIdx.x; i < HID * C; i += blockDim.x) W1s[(i / C) * SF + (i % C)] = __uint_as_float(tf32_rna(p.W1[i] * p.w1g));
     for (int i = threadIdx.x; i < OUTP * HID; i += blockDim.x) {
         const int k = i / HID, j = i % HID;
@@ -386,15 +429,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
         __syncwarp();
         gather_features<SF>(pl, ss, sF, lane);
         __syncwarp();
-        if (p.x_f) {       // features as bf16 [P][32] (operand of dW1)
-            const int pt = lane >> 3, j4 = (lane & 7) * 4;
-#pragma unroll
-            for (int q0 = 0; q0 < 32; q0 += 4)
-                if (q0 + pt < cnt) {
-                    const float4 v = *reinterpret_cast<const float4*>(&sF[(q0 + pt) * SF + j4]);
-                    *reinterpret_cast<uint2*>(p.x_f + (row0 + base + q0 + pt) * C + j4) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-                }
-        }
+        if (wgrad && ncommit) tc::mbar_wait(mybar, (ncommit - 1) & 1);      // last iteration's dW1 MMAs have consumed the operand tiles
         // ---- layer 1 (recompute): c1 = b1 + F W1^T, then h = softplus(c1) kept in the accumulator registers
         float c1[2][8][4];
 #pragma unroll
@@ -425,13 +460,11 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
             for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) c1[mt][nt][i] = softplus_fast(c1[mt][nt][i]);
-                if (p.x_h) {       // h as bf16 [P][64] (operand of dW2)
+                if (wgrad) {       // h as bf16 into the A tile: element (point, unit) at point*128 + ((unit/8 ^ point%8) * 16) + (unit%8)*2
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int row = g + 16 * mt + 8 * hh;
-                        if (row < cnt)
-                            *reinterpret_cast<uint32_t*>(p.x_h + (row0 + base + row) * HID + 8 * nt + 2 * t) =
-                                pack_bf16(c1[mt][nt][2 * hh], c1[mt][nt][2 * hh + 1]);
+                        *reinterpret_cast<uint32_t*>(opA + row * 128 + ((nt ^ g) << 4) + 4 * t) = pack_bf16(c1[mt][nt][2 * hh], c1[mt][nt][2 * hh + 1]);
                     }
                 }
             }
@@ -478,8 +511,21 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
                     if (col != 0) d0 *= 1.002f * s0 * (1.f - s0);
                     d1 *= 1.002f * s1 * (1.f - s1);
                     o[mt][nt][2 * hh] = d0; o[mt][nt][2 * hh + 1] = d1;
-                    if (p.x_do && rv) *reinterpret_cast<uint32_t*>(p.x_do + prow * OUTP + col) = pack_bf16(d0, d1);
+                    if (wgrad) *reinterpret_cast<uint32_t*>(opB + row * 128 + ((nt ^ g) << 4) + 4 * t) = pack_bf16(d0, d1);
                 }
+        if (wgrad) {       // dW2^T[j][k] += sum_p h[p][j] dO[p][k]: two k16 steps over the warp's 32 points
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tc::tc_fence_after();
+                const uint32_t idesc = tc::instr_desc_bf16(128, DW2_COLS, 1, 1);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    tc::umma_bf16(tmem, tc::smem_desc(opA_u + k * 2048, 4096, 1024), tc::smem_desc(opB_u + k * 2048, 4096, 1024), idesc, 1);
+                tc::umma_commit(mybar);
+            }
+            ++ncommit;
+        }
         if (wgrad) {       // db2[k] += sum over the warp's rows
 #pragma unroll
             for (int nt = 0; nt < 5; ++nt) {
@@ -522,7 +568,8 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
 #pragma unroll
                     for (int i = 0; i < 4; ++i) c1[mt][nt0 + u][i] = dh[mt][u][i] * (1.f - __expf(-c1[mt][nt0 + u][i]));
         }
-        if (p.x_da) {      // d_a as bf16 [P][64] (operand of dW1)
+        if (wgrad) {       // dW1[j][c] += sum_p d_a[p][j] F[p][c]: d_a replaces h in the A tile, F (bf16) replaces dO in the B tile
+            tc::mbar_wait(mybar, (ncommit - 1) & 1);                           // the dW2 MMAs have read both tiles
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -530,10 +577,26 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int row = g + 16 * mt + 8 * hh;
-                        if (row < cnt)
-                            *reinterpret_cast<uint32_t*>(p.x_da + (row0 + base + row) * HID + 8 * nt + 2 * t) =
-                                pack_bf16(c1[mt][nt][2 * hh], c1[mt][nt][2 * hh + 1]);
+                        *reinterpret_cast<uint32_t*>(opA + row * 128 + ((nt ^ g) << 4) + 4 * t) = pack_bf16(c1[mt][nt][2 * hh], c1[mt][nt][2 * hh + 1]);
                     }
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {                                    // lane = point: 32 channels = four 16-byte chunks
+                const float4 v0 = *reinterpret_cast<const float4*>(&sF[lane * SF + 8 * ch]);
+                const float4 v1 = *reinterpret_cast<const float4*>(&sF[lane * SF + 8 * ch + 4]);
+                *reinterpret_cast<uint4*>(opB + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+                    make_uint4(pack_bf16(v0.x, v0.y), pack_bf16(v0.z, v0.w), pack_bf16(v1.x, v1.y), pack_bf16(v1.z, v1.w));
+            }
+            tc::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                tc::tc_fence_after();
+                const uint32_t idesc = tc::instr_desc_bf16(128, C, 1, 1);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    tc::umma_bf16(tmem + DW1_COL0, tc::smem_desc(opA_u + k * 2048, 4096, 1024), tc::smem_desc(opB_u + k * 2048, 4096, 1024), idesc, 1);
+                tc::umma_commit(mybar);
+            }
+            ++ncommit;
         }
         if (wgrad) {       // db1[j] += sum over the warp's rows
 #pragma unroll
@@ -604,9 +667,29 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
         __syncwarp();
     }
     if (wgrad) {
+        if (ncommit) tc::mbar_wait(mybar, (ncommit - 1) & 1);                  // this warp's MMAs have retired
+        tc::tc_fence_before();
         __syncthreads();
+        tc::tc_fence_after();
         for (int i = threadIdx.x; i < HID; i += blockDim.x) atomicAdd(p.db1 + i, ab1[i] * p.b1g);
         for (int i = threadIdx.x; i < OUT; i += blockDim.x) atomicAdd(p.db2 + i, ab2[i] * p.b2g);
+        if (wid < 2) {                                         // drain: TMEM lane j = hidden unit j
+            const int j = wid * 32 + lane;
+            float v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(wid * 32) << 16), v);             // dW2^T[j][0..31]
+#pragma unroll
+            for (int k = 0; k < 32; ++k) atomicAdd(p.dW2 + k * HID + j, v[k] * p.w2g);
+            tc::tmem_ld32(tmem + ((uint32_t)(wid * 32) << 16) + 32u, v);       // dW2^T[j][32..47] | dW1[j][0..15]
+            atomicAdd(p.dW2 + 32 * HID + j, v[0] * p.w2g);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) atomicAdd(p.dW1 + j * C + c, v[16 + c] * p.w1g);
+            tc::tmem_ld32(tmem + ((uint32_t)(wid * 32) << 16) + 64u, v);       // dW1[j][16..31] | unused
+#pragma unroll
+            for (int c = 0; c < 16; ++c) atomicAdd(p.dW1 + j * C + 16 + c, v[c] * p.w1g);
+        }
+        tc::tc_fence_before();
+        __syncthreads();
+        if (wid == 0) tc::tmem_dealloc(tmem, DW_TCOLS);
     }
 }
 
@@ -651,27 +734,15 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     return 0;
 }
 
-static __global__ void decoder_wgrad_finalize_kernel(const float* __restrict__ t1, const float* __restrict__ t2, float* __restrict__ dW1,
-                                              float* __restrict__ dW2, float w1g, float w2g) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < HID * C) dW1[i] += t1[i] * w1g;                 // t1 = d_a^T F  [64][32]
-    if (i < OUT * HID) dW2[i] += t2[i] * w2g;               // t2 = dO^T h   [40][64], rows >= 33 are padding
-}
-
-extern "C" int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod, int n,
-                                  int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
-
-// Workspace of b200_triplane_mlp_bwd when decoder-parameter gradients are requested: four bf16 [rows][.] operand tensors
-// (rows = n*P rounded up to 64) + two fp32 partial-result tiles.
+// Kept for ABI stability: the decoder-parameter gradients are accumulated in tensor memory inside the kernel and need
+// no workspace any more.
 B200_API long b200_triplane_bwd_workspace_bytes(int n, long P) {
-    const long rows = ((long)n * P + 63) / 64 * 64;
-    return rows * (C + HID + OUTP + HID) * 2 + (long)(HID * C + OUTP * HID) * 4;
+    (void)n; (void)P;
+    return 0;
 }
 
 // d_planes [n][hp][wp][96] is ACCUMULATED into (zero it first); d_coords [n][P][3] is written (may be null);
-// dW1/db1/dW2/db2 are ACCUMULATED into (all four null => parameter gradients skipped; otherwise `workspace` of at least
-// b200_triplane_bwd_workspace_bytes(n, P) bytes is required: dW1 = d_a^T F and dW2 = dO^T h are contracted over the points by
-// the tcgen05 weight-gradient kernel from bf16 operands this kernel exports).
+// dW1/db1/dW2/db2 are ACCUMULATED into (all four null => parameter gradients skipped).  `workspace` is unused (may be null).
 B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                                    const float* ray_d, const float* depths, int S, long P, float box_warp,
                                    const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
@@ -686,37 +757,20 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     cudaStream_t st = (cudaStream_t)stream;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
-    const long rows = (long)n * P, rows_pad = (rows + 63) / 64 * 64;
-    float* t1 = nullptr; float* t2 = nullptr;
-    if (dW1) {
-        B200_REQUIRE(workspace && workspace_bytes >= b200_triplane_bwd_workspace_bytes(n, P), "triplane_bwd: workspace missing or too small");
-        B200_REQUIRE(rows_pad / 64 < (1L << 31), "triplane_bwd: too many points");
-        __nv_bfloat16* ws = (__nv_bfloat16*)workspace;
-        p.x_f = ws; p.x_h = p.x_f + rows_pad * C; p.x_do = p.x_h + rows_pad * HID; p.x_da = p.x_do + rows_pad * OUTP;
-        t1 = (float*)(p.x_da + rows_pad * HID); t2 = t1 + HID * C;
-        if (rows_pad > rows) {                       // padding rows must read as zeros in the GEMMs
-            B200_CUDA(cudaMemsetAsync(p.x_f + rows * C, 0, (rows_pad - rows) * C * 2, st));
-            B200_CUDA(cudaMemsetAsync(p.x_h + rows * HID, 0, (rows_pad - rows) * HID * 2, st));
-            B200_CUDA(cudaMemsetAsync(p.x_do + rows * OUTP, 0, (rows_pad - rows) * OUTP * 2, st));
-            B200_CUDA(cudaMemsetAsync(p.x_da + rows * HID, 0, (rows_pad - rows) * HID * 2, st));
-        }
-    }
+    (void)workspace; (void)workspace_bytes;
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BM_SMEM));
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel<BM_WARPS_WG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       bm_smem(BM_WARPS_WG, true)));
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel<BM_WARPS_NOWG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       bm_smem(BM_WARPS_NOWG, false)));
         attr_set = true;
     }
-    const long gb = (P + BM_WARPS * 32 - 1) / (BM_WARPS * 32);
-    dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one 16-warp CTA per SM
-    triplane_mlp_bwd_mma_kernel<<<grid, BM_WARPS * 32, BM_SMEM, st>>>(p);
+    const int warps = dW1 ? BM_WARPS_WG : BM_WARPS_NOWG;
+    const long gb = (P + warps * 32 - 1) / (warps * 32);
+    dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one CTA per SM
+    if (dW1) triplane_mlp_bwd_mma_kernel<BM_WARPS_WG, true><<<grid, warps * 32, bm_smem(BM_WARPS_WG, true), st>>>(p);
+    else triplane_mlp_bwd_mma_kernel<BM_WARPS_NOWG, false><<<grid, warps * 32, bm_smem(BM_WARPS_NOWG, false), st>>>(p);
     B200_CHECK_LAUNCH();
-    if (dW1) {
-        const int hh = (int)(rows_pad / 64);
-        // dW1[j][c] = sum_p d_a[p][j] F[p][c]   and   dW2[k][j] = sum_p dO[p][k] h[p][j]   (1x1 "convolutions" over the point axis)
-        if (int e = b200_conv_wgrad_tc(p.x_f, nullptr, p.x_da, nullptr, t1, 1, hh, 64, C, HID, 1, 1, 1, stream)) return e;
-        if (int e = b200_conv_wgrad_tc(p.x_h, nullptr, p.x_do, nullptr, t2, 1, hh, 64, HID, OUTP, 1, 1, 1, stream)) return e;
-        decoder_wgrad_finalize_kernel<<<(OUTP * HID + 255) / 256, 256, 0, st>>>(t1, t2, dW1, dW2, p.w1g, p.w2g);
-        B200_CHECK_LAUNCH();
-    }
     return 0;
 }

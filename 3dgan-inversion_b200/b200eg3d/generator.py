@@ -341,7 +341,7 @@ class OSGDecoder(torch.nn.Module):
 class RaySampler(torch.nn.Module):
     """training/volumetric_rendering/ray_sampler.py:24-73 (device follows the inputs; the reference hard-codes .cuda())."""
 
-    def forward(self, cam2world_matrix, intrinsics, resolution):
+    def forward(self, cam2world_matrix, intrinsics, resolution, need_cam_space=False):
         N, M = cam2world_matrix.shape[0], resolution ** 2
         dev = cam2world_matrix.device
         cam_locs_world = cam2world_matrix[:, :3, 3]
@@ -356,16 +356,24 @@ class RaySampler(torch.nn.Module):
                   - sk.unsqueeze(-1) * y_cam / fy.unsqueeze(-1)) / fx.unsqueeze(-1) * z_cam
         y_lift = (y_cam - cy.unsqueeze(-1)) / fy.unsqueeze(-1) * z_cam
         cam_rel_points = torch.stack((x_lift, y_lift, z_cam, torch.ones_like(z_cam)), dim=-1)
+        if need_cam_space:                                   # ray_sampler.py:61-70
+            return torch.zeros_like(cam_locs_world), F.normalize(cam_rel_points[:, :, :3], dim=2), uv
         world_rel_points = torch.bmm(cam2world_matrix, cam_rel_points.permute(0, 2, 1)).permute(0, 2, 1)[:, :, :3]
         ray_dirs = F.normalize(world_rel_points - cam_locs_world[:, None, :], dim=2)
         ray_origins = cam_locs_world.unsqueeze(1).repeat(1, ray_dirs.shape[1], 1)
         return ray_origins, ray_dirs
 
-    def calculate_xyz_of_depth(self, cam2world_matrix, intrinsics, resolution, depth):
-        """ray_sampler.py:75-93: world xyz of a rendered depth map [N,1,R,R] (used by the warping loss)."""
-        ray_origins, ray_dirs = self.forward(cam2world_matrix, intrinsics, resolution)
-        d = depth.reshape(depth.shape[0], -1, 1)
-        return ray_origins + ray_dirs * d
+    def calculate_xyz_of_depth(self, ray_origin, ray_dirs, depth):
+        """ray_sampler.py:75-93: homogeneous world xyz [4, res*res] of a rendered depth map [1,res,res] / [1,1,res,res]
+        along rays [1,res*res,3] (or [3,res,res]); used by the warping loss (warping_loss.py:21)."""
+        res = depth.shape[-1]
+        if ray_origin.shape[0] == 1 and ray_origin.shape[1] == res ** 2:
+            ray_origin = ray_origin.squeeze(0).reshape(res, res, 3).permute(2, 0, 1)
+        if ray_dirs.shape[0] == 1 and ray_dirs.shape[1] == res ** 2:
+            ray_dirs = ray_dirs.squeeze(0).reshape(res, res, 3).permute(2, 0, 1)
+        xyz = ray_origin + ray_dirs * depth.squeeze(0)
+        ones = torch.ones(1, xyz.shape[1], xyz.shape[2], device=ray_origin.device)
+        return torch.cat([xyz, ones], dim=0).reshape(4, res * res)
 
 
 class ImportanceRenderer(torch.nn.Module):

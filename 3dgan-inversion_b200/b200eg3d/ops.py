@@ -645,12 +645,6 @@ def torgb_layer(x, weight, styles, bias, img_prev, clamp, x_split=None, bank=Non
 # ----------------------------------------------------------------------------------------------
 # Renderer: fused tri-plane sampling + decoder, per-ray hierarchical sampling and compositing
 
-def _decoder_ws(n, P, dev):
-    """Workspace of b200_triplane_mlp_bwd for the decoder-parameter gradients (bf16 operands of the two point-axis GEMMs)."""
-    nbytes = _lib.load().b200_triplane_bwd_workspace_bytes(n, P)
-    return torch.empty([nbytes], device=dev, dtype=torch.uint8), nbytes
-
-
 def _decoder_params(decoder):
     fc0, fc1 = decoder.net[0], decoder.net[2]
     return fc0.weight, fc0.bias, fc1.weight, fc1.bias, float(fc0.lr_multiplier)
@@ -688,9 +682,8 @@ class _RunModel(torch.autograd.Function):
         d_coords = torch.empty_like(co) if need[1] else None
         wg = any(need[2:6])
         dws = [torch.zeros_like(t) for t in (W1, b1, W2, b2)] if wg else [None] * 4
-        wsp, wsb = _decoder_ws(n, P, pl.device) if wg else (None, 0)
         call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, P, box_warp, ptr(W1), ptr(b1), ptr(W2),
-             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(d_planes), ptr(d_coords), *map(ptr, dws), ptr(wsp), wsb,
+             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(d_planes), ptr(d_coords), *map(ptr, dws), None, 0,
              stream())
         return (d_planes, d_coords, *dws, None, None)
 
@@ -783,9 +776,8 @@ class _Render(torch.autograd.Function):
             if s == 0:
                 continue
             d_pts = torch.empty([n, M, s, 3], device=dev, dtype=torch.float32) if want_rays else None
-            wsp, wsb = _decoder_ws(n, M * s, dev) if wg else (None, 0)
             call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t), s, M * s, box_warp, ptr(W1),
-                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(d_planes), ptr(d_pts), *map(ptr, dws), ptr(wsp), wsb, st)
+                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(d_planes), ptr(d_pts), *map(ptr, dws), None, 0, st)
             if want_rays:                      # point = o + t*d  (renderer.py:161,178)
                 d_ro += d_pts.sum(2)
                 d_rd += (d_pts * t.unsqueeze(-1)).sum(2)

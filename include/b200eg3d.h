@@ -128,8 +128,8 @@ int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const floa
                           const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
                           float* rgb, float* sigma, void* stream);
 /* d_planes is ACCUMULATED (zero it first; may be NULL); d_coords [n][P][3] written (may be NULL); dW1..db2 ACCUMULATED (all or
- * none).  With parameter gradients, `workspace` (>= b200_triplane_bwd_workspace_bytes(n, P) bytes of device memory) receives the
- * bf16 operands of dW1 = d_a^T F and dW2 = d_out^T h, which the tcgen05 weight-gradient kernel contracts over the points. */
+ * none).  dW1 = d_a^T F and dW2 = d_out^T h are contracted over the points inside the kernel (tcgen05.mma into a tensor-memory
+ * accumulator); `workspace` is unused since version 101 (pass NULL / 0; b200_triplane_bwd_workspace_bytes returns 0). */
 long b200_triplane_bwd_workspace_bytes(int n, long P);
 int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                           const float* ray_d, const float* depths, int S, long P, float box_warp,

@@ -22,8 +22,8 @@ d_rgb = torch.randn_like(rgb); d_sig = torch.randn_like(sig)
 dpl = torch.zeros_like(planes); dpts = torch.empty(n, M * S, 3, device=dev)
 dW = [torch.zeros_like(x) for x in (W1, b1, W2, b2)]
 from b200eg3d import _lib
-wsb = _lib.load().b200_triplane_bwd_workspace_bytes(n, M * S)
-wsp = torch.empty(wsb, device=dev, dtype=torch.uint8)
+
+
 
 def timeit(fn, name, iters=5):
     fn(); torch.cuda.synchronize()
@@ -36,7 +36,7 @@ def timeit(fn, name, iters=5):
 fwd = lambda: call('b200_triplane_mlp_fwd', ptr(planes), n, 256, 256, None, ptr(ro), ptr(rd), ptr(t), S, M * S, 1.0, ptr(W1), ptr(b1), ptr(W2), ptr(b2), 1.0, ptr(rgb), ptr(sig), stream())
 def bwd(dp, dc, wg):
     return lambda: call('b200_triplane_mlp_bwd', ptr(planes), n, 256, 256, None, ptr(ro), ptr(rd), ptr(t), S, M * S, 1.0, ptr(W1), ptr(b1), ptr(W2), ptr(b2), 1.0,
-                        ptr(d_rgb), ptr(d_sig), ptr(dpl) if dp else None, ptr(dpts) if dc else None, *[(ptr(x) if wg else None) for x in dW], ptr(wsp) if wg else None, wsb if wg else 0, stream())
+                        ptr(d_rgb), ptr(d_sig), ptr(dpl) if dp else None, ptr(dpts) if dc else None, *[(ptr(x) if wg else None) for x in dW], None, 0, stream())
 timeit(fwd, 'fwd 786k pts')
 timeit(bwd(True, False, True), 'bwd planes+wgrad (PTI)')
 timeit(bwd(True, False, False), 'bwd planes only')
