@@ -4,11 +4,13 @@ Public surface (mirrors the reference's generator API, see generator.py):
     TriPlaneGenerator, ImportanceRenderer, RaySampler, OSGDecoder, SuperresolutionHybrid8X
     ops.bias_act / ops.upfirdn2d / ops.upsample2d / ops.setup_filter      (torch_utils.ops equivalents)
     seam.convert_generator / seam.load_old_G                               (drop-in replacement of utils/models_utils.py:21-25)
+    losses.pti_loss / losses.compute_tv_norm                               (base_coach.py:101-126,294-305 as fused reductions)
 """
 from . import ops  # noqa: F401
 from .generator import (FullyConnectedLayer, Generator, ImportanceRenderer, MappingNetwork, OSGDecoder, RaySampler,  # noqa: F401
                         SuperresolutionHybrid8X, SynthesisBlock, SynthesisLayer, SynthesisNetwork, ToRGBLayer,
                         TriPlaneGenerator)
 from . import seam  # noqa: F401
+from . import losses  # noqa: F401
 
 __version__ = '0.1.0'

@@ -34,6 +34,8 @@ SIGNATURES = {
     'b200_upfirdn2d_fused': [_P] * 6 + [_I] * 13 + [_F, _I, _P, _P, _P, _L, _I, _F, _F, _F, _P],
     'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P],
     'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
+    'b200_pti_loss_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P],
+    'b200_pti_loss_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],
     'b200_depth_minmax': [_P, _L, _P, _P],
     'b200_ray_importance': [_P, _P, _P, _P, _L, _I, _I, _P],

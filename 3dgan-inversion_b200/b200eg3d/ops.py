@@ -269,6 +269,13 @@ class WeightBank:
         self.dwmod = [None] * n
         self.need_wgrad = False
         self.token = None
+        self.zpool = None          # one zero-filled buffer for the small backward accumulators (d bias, d noise_strength) of all layers
+        self.zoff = []
+
+    def zeros(self, lidx, cout):
+        """(d bias [cout], d strength []) views into the pool: one fill per network and pass instead of two per layer."""
+        o = self.zoff[lidx]
+        return self.zpool[o:o + cout], self.zpool[o + cout]
 
 
 def _bank_array(bank, n, dev, bwd=None):
@@ -303,6 +310,11 @@ class _Bank(torch.autograd.Function):
             if sp.tc_f or sp.tc_b:
                 bank.w_hi[l] = torch.empty(shape, device=dev, dtype=torch.bfloat16)
                 bank.w_lo[l] = torch.empty(shape, device=dev, dtype=torch.bfloat16) if keep_lo else None
+        bank.zoff, tot = [], 0
+        for sp in bank.specs:
+            bank.zoff.append(tot)
+            tot += (sp.cout + 1 + 3) // 4 * 4
+        bank.zpool = torch.zeros([tot], device=dev, dtype=torch.float32)
         arr = _bank_array(bank, n, dev)
         call('b200_bank_styles_fwd', ctypes.addressof(arr), len(bank.specs), ptr(ws), n, num_ws, w_dim, stream())
         call('b200_bank_weights_fwd', ctypes.addressof(arr), len(bank.specs), n, stream())
@@ -476,9 +488,13 @@ class _ModConvLayer(torch.autograd.Function):
         need = ctx.needs_input_grad
         need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dzc = _f32c(dz)
-        dbias = torch.zeros([cout], device=dev, dtype=torch.float32)
         has_noise = nz is not None
-        dstr = torch.zeros([], device=dev, dtype=torch.float32) if has_noise else None
+        if bank is not None:
+            dbias, dstr = bank.zeros(lidx, cout)
+            dstr = dstr if has_noise else None
+        else:
+            dbias = torch.zeros([cout], device=dev, dtype=torch.float32)
+            dstr = torch.zeros([], device=dev, dtype=torch.float32) if has_noise else None
         dnoise = torch.zeros_like(nz) if (has_noise and need[6]) else None
         dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
         dW = ds = None
@@ -599,7 +615,7 @@ class _ToRGB(torch.autograd.Function):
         need = ctx.needs_input_grad
         need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dimg = _f32c(dimg)
-        dbias = torch.zeros([cimg], device=dev, dtype=torch.float32)
+        dbias = bank.zeros(lidx, cimg)[0] if bank is not None else torch.zeros([cimg], device=dev, dtype=torch.float32)
         dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
         dW = ds = None
         if need_w:

@@ -104,9 +104,10 @@ def make_problem(seed, device):
     return G, ws, c, t512.contiguous(), t_raw.contiguous()
 
 
-def pti_loss(out, t512, t_raw):
-    import eg3d_oracle as oracle       # loss definition only (caller-side code, shared with the parity tests)
-    return oracle.pti_loss(out, t512, t_raw)
+def pti_loss(out, t512):
+    """calc_loss of base_coach.py:101-126 without LPIPS, as the fused CUDA reduction (t_raw = area(t512) is formed in the kernel)."""
+    from b200eg3d import losses
+    return losses.pti_loss(out, t512)
 
 
 def run_b200(args):
@@ -124,12 +125,12 @@ def run_b200(args):
     G, ws_h, c_h, t512_h, traw_h = make_problem(100 + rank if world > 1 else 0, dev)
     params = [p for n, p in G.named_parameters() if '.mapping.' not in n]
     opt = torch.optim.Adam(params, lr=3e-4, fused=True, capturable=not args.eager)
-    host = [t.pin_memory() for t in (ws_h, c_h, t512_h, traw_h)]
+    host = [t.pin_memory() for t in (ws_h, c_h, t512_h)]       # the raw-resolution target is derived from t512 inside the loss kernel
     resident = [t.to(dev) for t in host]
 
-    def eager_step(ws, c, t512, traw):
+    def eager_step(ws, c, t512):
         out = G.synthesis(ws, c, noise_mode='const', force_fp32=True)
-        loss = pti_loss(out, t512, traw)
+        loss = pti_loss(out, t512)
         if args.eager:
             opt.zero_grad(set_to_none=True)
         loss.backward()
@@ -248,7 +249,7 @@ def run_b200(args):
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
             'config': {'workload': WORKLOAD, 'parallelism': f'independent images x{world}',
                        'l2': 'per-step working set (>1 GB of activations and gradients) exceeds the 126 MB L2; no explicit flush',
-                       'loss': 'mse512 + mse128 + depth TV (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4 (fused)',
+                       'loss': 'mse512 + mse128 + depth TV, fused kernel b200eg3d.losses.pti_loss (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4 (fused)',
                        'launch': 'eager (one Python-driven launch per kernel)' if args.eager else
                                  'whole step captured once in a CUDA graph (b200eg3d.graphs.GraphedStep) and replayed'},
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,

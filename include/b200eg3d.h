@@ -154,6 +154,19 @@ int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, const float* 
                            long n_rays, const float* d_feat, const float* d_depth, const float* d_wsum, float* d_rgb_c,
                            float* d_sigma_c, float* d_rgb_f, float* d_sigma_f, void* stream);
 
+/* ---- caller-side losses: training/coaches/base_coach.py:101-126 calc_loss (without LPIPS), :294-305 tv ---- */
+/* loss[4] (ACCUMULATED; zero first) = {l2_lambda*(mse_image+mse_raw) + tv_lambda*tv, mse(image, real), mse(raw, area_R(real)), tv(depth)}.
+ * image [n][C][H][W] and raw [n][C][R][R] are addressed through HOST arrays of 4 element strides {n, c, h, w} (NCHW views of NHWC
+ * memory need no copy); depth [n][R][R] and real [n][C][H][W] contiguous.  image, raw and depth may each be NULL. */
+int b200_pti_loss_fwd(const float* image, const long* image_strides, const float* raw, const long* raw_strides, const float* depth,
+                      const float* real, int n, int C, int H, int W, int R, float l2_lambda, float tv_lambda, float* loss,
+                      void* stream);
+/* gradients of loss[0] scaled by the device scalar *dloss; written (not accumulated) with the given element strides. */
+int b200_pti_loss_bwd(const float* image, const long* image_strides, const float* raw, const long* raw_strides, const float* depth,
+                      const float* real, int n, int C, int H, int W, int R, float l2_lambda, float tv_lambda, const float* dloss,
+                      float* d_image, const long* d_image_strides, float* d_raw, const long* d_raw_strides, float* d_depth,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -362,3 +362,13 @@ def tv_norm(depth):
 
 def pti_loss(out, target512, target_raw):
     return F.mse_loss(out['image'], target512) + F.mse_loss(out['image_raw'], target_raw) + tv_norm(out['image_depth'])
+
+
+def calc_loss(out, real_images, pt_l2_lambda=1.0, depth_tv_lambda=1.0):
+    """base_coach.py:101-126 (calc_loss) restated without the LPIPS term: the raw-resolution target is the area-resized
+    real image (:103), both MSE terms are weighted by pt_l2_lambda (:105-109), the depth TV term is added last (:123-124).
+    Returns (loss, [mse_image, mse_raw, tv])."""
+    r = out['image_raw'].shape[-1]
+    real_r = F.interpolate(real_images, size=(r, r), mode='area')
+    a, b, t = F.mse_loss(out['image'], real_images), F.mse_loss(out['image_raw'], real_r), tv_norm(out['image_depth'])
+    return pt_l2_lambda * (a + b) + depth_tv_lambda * t, [a, b, t]

@@ -291,3 +291,33 @@ def test_render_fwd_bwd(b2, S, S2, white):
     assert relerr(rdc.grad, rdr.grad) < 1e-2
     for k, v in dec.named_parameters():
         assert relerr(v.grad, Pr['decoder.' + k].grad) < 1e-2, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,h,r', [(1, 512, 128), (2, 16, 8), (1, 12, 12), (3, 24, 4)])
+def test_pti_loss_fwd_bwd(b2, n, h, r):
+    """Fused calc_loss (base_coach.py:101-126 without LPIPS) against the oracle, on the layouts the generator produces:
+    image = NCHW view of NHWC memory, image_raw = 3-channel slice of the NHWC feature image, depth contiguous."""
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    img_nhwc = torch.randn(n, h, h, 3, generator=g)
+    feat_nhwc = torch.randn(n, r, r, 32, generator=g)
+    depth = torch.rand(n, 1, r, r, generator=g) + 2.5
+    real = torch.rand(n, 3, h, h, generator=g) * 2 - 1
+    ref_in = [t.clone().requires_grad_(True) for t in (img_nhwc, feat_nhwc, depth)]
+    out_ref = {'image': ref_in[0].permute(0, 3, 1, 2), 'image_raw': ref_in[1].permute(0, 3, 1, 2)[:, :3], 'image_depth': ref_in[2]}
+    loss_ref, parts_ref = oracle.calc_loss(out_ref, real, 0.7, 1.3)
+    (loss_ref * 1.5).backward()
+    dev_in = [t.clone().cuda().requires_grad_(True) for t in (img_nhwc, feat_nhwc, depth)]
+    out = {'image': dev_in[0].permute(0, 3, 1, 2), 'image_raw': dev_in[1].permute(0, 3, 1, 2)[:, :3], 'image_depth': dev_in[2]}
+    loss, parts = b2.losses.pti_loss(out, real.cuda(), 0.7, 1.3, return_parts=True)
+    (loss * 1.5).backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-5 * max(1.0, abs(loss_ref.item()))
+    for a, b in zip(parts[1:].tolist(), parts_ref):
+        assert abs(a - b.item()) <= 1e-5 * max(1.0, abs(b.item()))
+    for a, b in zip(dev_in, ref_in):
+        assert relerr(a.grad, b.grad) < 1e-5
+    tv = b2.losses.compute_tv_norm(depth.cuda())
+    assert abs(tv.item() - oracle.tv_norm(depth).item()) <= 1e-6 + 1e-5 * oracle.tv_norm(depth).item()
+    with pytest.raises(RuntimeError, match='divide'):
+        b2.losses.pti_loss({'image': dev_in[0].permute(0, 3, 1, 2), 'image_raw': torch.zeros(n, 3, 5, 5, device='cuda'), 'image_depth': None},
+                           real.cuda())
