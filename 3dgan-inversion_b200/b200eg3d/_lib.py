@@ -36,6 +36,11 @@ SIGNATURES = {
     'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
     'b200_pti_loss_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P],
     'b200_pti_loss_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P],
+    'b200_warp_uv_fwd': [_P, _P, _P, _P, _P, _I, _P, _P, _P],
+    'b200_warp_uv_bwd': [_P, _P, _P, _P, _P, _I, _P, _P, _P, _P],
+    'b200_noise_pyramid_fwd': [_I, _P, _P, _P, _P, _P, _P, _P],
+    'b200_noise_pyramid_bwd': [_I, _P, _P, _P, _P, _P, _P, _P, _P],
+    'b200_noise_normalize': [_I, _P, _P, _P, _P],
     'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],
     'b200_depth_minmax': [_P, _L, _P, _P],
     'b200_ray_importance': [_P, _P, _P, _P, _L, _I, _I, _P],
@@ -75,6 +80,8 @@ def load():
     lib.b200_triplane_bwd_workspace_bytes.restype = ctypes.c_long
     lib.b200_triplane_bwd_workspace_bytes.argtypes = [_I, _L]
     lib.b200_conv_tc_supported.argtypes = [_I] * 7
+    lib.b200_noise_pyramid_work_floats.restype = ctypes.c_long
+    lib.b200_noise_pyramid_work_floats.argtypes = [_I, _P]
     _lib = lib
     return lib
 

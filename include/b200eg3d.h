@@ -167,6 +167,30 @@ int b200_pti_loss_bwd(const float* image, const long* image_strides, const float
                       float* d_image, const long* d_image_strides, float* d_raw, const long* d_raw_strides, float* d_depth,
                       void* stream);
 
+/* ---- stage-1 (w-projection) caller-side kernels ------------------------------------------------- */
+/* training/warping_loss.py:18-43 fused: rays of the predicted camera `ext` (ray_sampler.py:24-73), surface point o + d*depth
+ * (:75-93), line-plane intersection with the canonical image plane (warping_loss.py:58-72), projection through w2c =
+ * inverse(init_ext) and the intrinsics K -> uv [R*R][2] in [-1, 1].  ext / init_ext / w2c: device [16]; K: device [9]; depth:
+ * device [R*R].  min_ndotu (device scalar, initialise to a large float; may be NULL) receives min |n.v| for the reference's
+ * "no intersection" check. */
+int b200_warp_uv_fwd(const float* ext, const float* init_ext, const float* w2c, const float* K, const float* depth, int R,
+                     float* uv, float* min_ndotu, void* stream);
+/* d_ext [16] ACCUMULATED (zero first), d_depth [R*R] written. */
+int b200_warp_uv_bwd(const float* ext, const float* init_ext, const float* w2c, const float* K, const float* depth, int R,
+                     const float* d_uv, float* d_ext, float* d_depth, void* stream);
+/* Noise regulariser of w_projector.py:221-237 over nbuf square buffers (side sizes[b], powers of two): for every level of the 2x2
+ * average-pool pyramid down to 8x8, (mean(n*roll(n,1,x)))^2 + (mean(n*roll(n,1,y)))^2, summed into *reg (ACCUMULATED).
+ * bufs / dbufs: HOST arrays of device pointers; sizes: HOST array; sizes_dev: the same on the device; work / gwork: device
+ * workspaces of b200_noise_pyramid_work_floats(nbuf, sizes) floats; sums: device [nbuf][8][2], ZEROED by the caller and
+ * passed unchanged to the backward, which writes (*dreg) * d reg / d buffer into dbufs. */
+long b200_noise_pyramid_work_floats(int nbuf, const int* sizes);
+int b200_noise_pyramid_fwd(int nbuf, const float* const* bufs, const int* sizes, const int* sizes_dev, float* work, float* sums,
+                           float* reg, void* stream);
+int b200_noise_pyramid_bwd(int nbuf, const float* const* bufs, const int* sizes, const float* work, const float* sums,
+                           const float* dreg, float* const* dbufs, float* gwork, void* stream);
+/* w_projector.py:262-268 in place: buf <- (buf - mean) * rsqrt(mean((buf - mean)^2)); stats: device [nbuf][2], ZEROED by the caller. */
+int b200_noise_normalize(int nbuf, float* const* bufs, const int* sizes, float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

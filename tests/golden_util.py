@@ -78,3 +78,37 @@ def build_param_dict(case, requires_grad=False):
         for v in P.values():
             v.requires_grad_(True)
     return P
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# stage-1 (w-projection) fixtures: shared by oracle/make_goldens_stage1.py and the tests
+
+def stage1_feature_net(seed=11):
+    """Seeded stand-in for torchvision VGG16.features (same child layout: conv/relu pairs, max-pools after children 3, 8, 15;
+    pretrained weights are not available offline).  get_features(..., '14') returns the activation after child 14."""
+    import torch.nn as nn
+    chans = [(3, 8), (8, 8), None, (8, 16), (16, 16), None, (16, 32), (32, 32), (32, 32), None, (32, 32), (32, 32), (32, 32)]
+    layers = []
+    for c in chans:
+        if c is None:
+            layers.append(nn.MaxPool2d(2))
+        else:
+            layers += [nn.Conv2d(c[0], c[1], 3, padding=1), nn.ReLU(inplace=False)]
+    net = nn.Sequential(*layers)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.3 if p.ndim > 1 else 0.05))
+    return net.eval().requires_grad_(False)
+
+
+def stage1_inputs(name, R, H):
+    seed = {'a': 21, 'b': 22}[name]
+    g = torch.Generator().manual_seed(seed)
+    c0, c1 = sp.camera(0.0, 0.0), sp.camera(0.25, -0.15)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, R), torch.linspace(-1, 1, R), indexing='ij')
+    depth = 2.75 - 0.35 * torch.exp(-(xx ** 2 + yy ** 2) * 3) + 0.01 * torch.randn(R, R, generator=g)
+    can = torch.nn.functional.interpolate(torch.rand(1, 3, H // 8, H // 8, generator=g) * 2 - 1, size=(H, H), mode='bilinear')
+    return {'init_ext': c0[:, :16].reshape(1, 4, 4).clone(), 'extrinsic': c1[:, :16].reshape(1, 4, 4).clone(),
+            'intrinsic': c0[0, 16:25].clone(), 'depth': depth.reshape(1, 1, R, R).contiguous(), 'can_image': can.contiguous(),
+            'target': torch.rand(1, 3, 256, 256, generator=g) * 2 - 1}

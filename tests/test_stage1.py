@@ -1,0 +1,138 @@
+"""Stage-1 (w-projection) caller-side pieces: the oracle against the fixtures generated from the reference's own
+calc_warping_loss (CPU), and the CUDA kernels against the oracle / fixtures (GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import stage1_oracle as s1
+from golden_util import stage1_feature_net, stage1_inputs
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'stage1_warp.npz')
+CASES = {'a': (32, 64), 'b': (128, 512)}
+
+
+def relerr(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('name', ['a', 'b'])
+def test_oracle_matches_reference_fixture(name):
+    fx = np.load(GOLD)
+    R, H = CASES[name]
+    inp = stage1_inputs(name, R, H)
+    ext = inp['extrinsic'].clone().requires_grad_(True)
+    depth = inp['depth'].clone().requires_grad_(True)
+    loss, warped = s1.warping_loss(inp['can_image'], ext, inp['init_ext'], inp['intrinsic'], depth, inp['target'], stage1_feature_net(), '14')
+    loss.backward()
+    assert abs(loss.item() - float(fx[f'{name}_loss'])) <= 2e-6 * abs(float(fx[f'{name}_loss']))
+    assert np.abs(warped.detach()[:, :, ::4, ::4].numpy() - fx[f'{name}_warped_sub']).max() < 1e-4
+    assert relerr(ext.grad, torch.from_numpy(fx[f'{name}_d_ext'])) < 1e-4
+    assert relerr(depth.grad[:, :, ::4, ::4], torch.from_numpy(fx[f'{name}_d_depth_sub'])) < 1e-4
+    uv, _ = s1.warp_uv(inp['extrinsic'], inp['init_ext'], inp['intrinsic'], inp['depth'])
+    assert np.abs(uv.reshape(R, R, 2)[::4, ::4].numpy() - fx[f'{name}_uv_sub']).max() < 1e-5
+
+
+def test_oracle_noise_regulariser_fixture():
+    g = torch.Generator().manual_seed(5)
+    bufs = [torch.randn(r, r, generator=g) for r in [4, 8, 8, 16, 16, 32, 64, 128, 256]]
+    assert abs(float(s1.noise_regularizer(bufs)) - float(np.load(GOLD)['noise_reg'])) < 1e-6
+
+
+@pytest.fixture(scope='module')
+def b2():
+    import b200eg3d
+    assert torch.cuda.is_available()
+    b200eg3d.ops.library_info()
+    return b200eg3d
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['a', 'b'])
+def test_warp_uv_fwd_bwd(b2, name):
+    R, H = CASES[name]
+    inp = stage1_inputs(name, R, H)
+    g = torch.Generator().manual_seed(3)
+    up = torch.randn(R * R, 2, generator=g)
+    ext = inp['extrinsic'].clone().requires_grad_(True)
+    depth = inp['depth'].clone().requires_grad_(True)
+    uv_ref, _ = s1.warp_uv(ext, inp['init_ext'], inp['intrinsic'], depth)
+    (uv_ref * up).sum().backward()
+    ext_d = inp['extrinsic'].clone().cuda().requires_grad_(True)
+    depth_d = inp['depth'].clone().cuda().requires_grad_(True)
+    uv = b2.projector.warp_uv(ext_d, inp['init_ext'].cuda(), inp['intrinsic'].cuda(), depth_d)
+    (uv * up.cuda()).sum().backward()
+    assert (uv.cpu() - uv_ref).abs().max().item() < 2e-5            # fp32, uv in [-1, 1]
+    assert relerr(depth_d.grad, depth.grad) < 1e-4
+    assert relerr(ext_d.grad, ext.grad) < 1e-4
+    assert ext_d.grad.shape == ext.grad.shape and float(ext_d.grad[0, 3].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_warp_uv_reports_degenerate_intersection(b2):
+    inp = stage1_inputs('a', 32, 64)
+    # a depth map that puts the surface points in the plane through the canonical origin orthogonal to its normal: n . v == 0
+    ext = inp['init_ext'].clone().cuda()
+    depth = torch.zeros(1, 1, 32, 32, device='cuda')                # surface point == predicted camera origin == canonical origin
+    with pytest.raises(RuntimeError, match='no intersection'):
+        b2.projector.warp_uv(ext, inp['init_ext'].cuda(), inp['intrinsic'].cuda(), depth)
+    uv = b2.projector.warp_uv(ext, inp['init_ext'].cuda(), inp['intrinsic'].cuda(), depth, check_intersection=False)
+    assert uv.shape == (32 * 32, 2)
+
+
+class _StubG:
+    def __init__(self, img):
+        self.img = img
+
+    def synthesis(self, ws, c, **kw):
+        return {'image': self.img}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['a', 'b'])
+def test_calc_warping_loss_against_reference_fixture(b2, name):
+    """Same call as training/warping_loss.py:calc_warping_loss (stub G returning the fixture's canonical image)."""
+    fx = np.load(GOLD)
+    R, H = CASES[name]
+    inp = {k: v.cuda() for k, v in stage1_inputs(name, R, H).items()}
+    ext = inp['extrinsic'].clone().requires_grad_(True)
+    depth = inp['depth'].clone().requires_grad_(True)
+    vgg = stage1_feature_net().cuda()
+    torch.backends.cudnn.allow_tf32 = False          # the stand-in feature net must run in fp32 like the CPU reference (|.| and ReLU kinks)
+    loss, warped = b2.projector.calc_warping_loss(torch.zeros(1, 14, 512, device='cuda'), torch.zeros(1, 25, device='cuda'), ext,
+                                                  inp['init_ext'], inp['intrinsic'], depth, inp['target'], _StubG(inp['can_image']), vgg,
+                                                  b2.RaySampler(), layers='14')
+    loss.backward()
+    assert abs(loss.item() - float(fx[f'{name}_loss'])) <= 1e-3 * abs(float(fx[f'{name}_loss']))     # cuDNN convs of the stand-in feature net
+    assert np.abs(warped.detach()[:, :, ::4, ::4].cpu().numpy() - fx[f'{name}_warped_sub']).max() < 1e-3
+    assert relerr(ext.grad, torch.from_numpy(fx[f'{name}_d_ext'])) < 1e-2
+    assert relerr(depth.grad[:, :, ::4, ::4], torch.from_numpy(fx[f'{name}_d_depth_sub'])) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('sizes', [[4], [8, 16], [4, 8, 8, 16, 16, 32, 32, 64, 64, 128, 128, 256, 256, 256, 256, 512, 512], [1024, 4]])
+def test_noise_regulariser_fwd_bwd(b2, sizes):
+    g = torch.Generator().manual_seed(len(sizes))
+    bufs = [torch.randn(r, r, generator=g) for r in sizes]
+    ref_in = [b.clone().double().requires_grad_(True) for b in bufs]
+    ref = s1.noise_regularizer(ref_in)
+    (ref * 1e5).backward()
+    dev_in = [b.clone().cuda().requires_grad_(True) for b in bufs]
+    reg = b2.projector.noise_regularizer(dev_in)
+    (reg * 1e5).backward()
+    assert abs(reg.item() - ref.item()) <= 1e-4 * abs(ref.item()) + 1e-9
+    for a, b in zip(dev_in, ref_in):
+        assert relerr(a.grad, b.grad) < 1e-3, a.shape
+
+
+@pytest.mark.gpu
+def test_normalize_noise_in_place(b2):
+    g = torch.Generator().manual_seed(9)
+    bufs = [torch.randn(r, r, generator=g) * (1 + i) + 0.3 * i for i, r in enumerate([4, 8, 64, 512])]
+    ref = s1.normalize_noise(bufs)
+    dev = {f'b{i}': b.clone().cuda() for i, b in enumerate(bufs)}
+    b2.projector.normalize_noise_(dev)
+    for a, b in zip(dev.values(), ref):
+        assert (a.cpu() - b).abs().max().item() < 1e-4
