@@ -29,7 +29,7 @@ class _WarpUV(torch.autograd.Function):
     """pred_uv [R*R, 2] of warping_loss.py:18-43 from (extrinsic, init_ext, intrinsic, depth); gradients to extrinsic and depth."""
 
     @staticmethod
-    def forward(ctx, extrinsic, init_ext, intrinsic, depth):
+    def forward(ctx, extrinsic, init_ext, intrinsic, depth, w2c):
         ext = _f32c(extrinsic).reshape(16)
         ini = _f32c(init_ext).reshape(16)
         K = _f32c(intrinsic).reshape(9)
@@ -37,7 +37,8 @@ class _WarpUV(torch.autograd.Function):
         R = dep.shape[-1]
         if dep.numel() != R * R:
             raise ValueError('warp_uv handles one depth map [1, 1, R, R] (the reference path is batch 1)')
-        w2c = torch.linalg.inv(ini.reshape(4, 4)).contiguous()               # warping_loss.py:38
+        # warping_loss.py:38; torch.linalg.inv synchronises, so callers that capture CUDA graphs pass the (constant) inverse in
+        w2c = torch.linalg.inv(ini.reshape(4, 4)).contiguous() if w2c is None else _f32c(w2c).reshape(4, 4)
         uv = torch.empty([R * R, 2], device=dep.device, dtype=torch.float32)
         mn = torch.full([1], _BIG, device=dep.device, dtype=torch.float32)
         call('b200_warp_uv_fwd', ptr(ext), ptr(ini), ptr(w2c), ptr(K), ptr(dep), R, ptr(uv), ptr(mn), stream())
@@ -54,13 +55,13 @@ class _WarpUV(torch.autograd.Function):
         d_dep = torch.empty_like(dep)
         call('b200_warp_uv_bwd', ptr(ext), ptr(ini), ptr(w2c), ptr(K), ptr(dep), ctx.R, ptr(_f32c(d_uv)), ptr(d_ext), ptr(d_dep), stream())
         es, ds = ctx.shapes
-        return d_ext.reshape(es), None, None, d_dep.reshape(ds)
+        return d_ext.reshape(es), None, None, d_dep.reshape(ds), None
 
 
-def warp_uv(extrinsic, init_ext, intrinsic, depth, check_intersection=True, epsilon=1e-6):
+def warp_uv(extrinsic, init_ext, intrinsic, depth, check_intersection=True, epsilon=1e-6, w2c=None):
     """Canonical-view uv in [-1, 1] of every pixel's surface point.  check_intersection reproduces the reference's
     RuntimeError (warping_loss.py:66-67); it synchronises, so switch it off inside CUDA-graph capture."""
-    uv, mn = _WarpUV.apply(extrinsic, init_ext, intrinsic, depth)
+    uv, mn = _WarpUV.apply(extrinsic, init_ext, intrinsic, depth, w2c)
     if check_intersection and mn.item() < epsilon:
         raise RuntimeError('no intersection or line is within plane')
     return uv
@@ -95,7 +96,7 @@ def photometric_reconstruction_loss(tgt_img, ref_img, depth_mask, explainability
 
 
 def calc_warping_loss(ws, canonical_cam, extrinsic, init_ext, intrinsic, depth, target_images, G, torch_vgg, ray_generator=None,
-                      layers='14', check_intersection=True):
+                      layers='14', check_intersection=True, w2c=None):
     """training/warping_loss.py:6-56 with the same arguments.  Returns (loss, warped canonical image)."""
     canonical_dict = G.synthesis(ws, canonical_cam, noise_mode='const', force_fp32=True)
     can_images = canonical_dict['image']
@@ -103,7 +104,7 @@ def calc_warping_loss(ws, canonical_cam, extrinsic, init_ext, intrinsic, depth, 
         can_images = F.interpolate(can_images, size=(256, 256), mode='area')
     depth_mean = torch.mean(depth)
     masked_depths = torch.where(depth < depth_mean, torch.ones_like(depth_mean), torch.zeros_like(depth_mean))   # foreground only
-    pred_uv = warp_uv(extrinsic, init_ext, intrinsic, depth, check_intersection=check_intersection)
+    pred_uv = warp_uv(extrinsic, init_ext, intrinsic, depth, check_intersection=check_intersection, w2c=w2c)
     torch_target_features = get_features(target_images, torch_vgg, layers)
     torch_synth_features = get_features(can_images, torch_vgg, layers)
     res = depth.shape[-1]
@@ -196,3 +197,51 @@ def normalize_noise_(noise_bufs):
         tab, tab_p = _ptr_table(bufs)
         stats = torch.zeros([2 * len(bufs)], device=bufs[0].device, dtype=torch.float32)
         call('b200_noise_normalize', len(bufs), tab_p, sizes_p, ptr(stats), stream())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one iteration of the w-projection loop (w_projector.py:160-260) around a pose given as a rotation matrix
+
+def rot6d_to_rotmat(x):
+    """utils/camera_utils.py:259-273 (6-D rotation representation -> [B, 3, 3])."""
+    x = x.view(-1, 2, 3) + 1e-4
+    a1, a2 = x[:, 0, :], x[:, 1, :]
+    b1 = F.normalize(a1)
+    b2 = F.normalize(a2 - torch.einsum('bi,bi->b', b1, a2).unsqueeze(-1) * b1)
+    b3 = torch.cross(b1, b2, dim=-1)
+    return torch.stack((b1, b2, b3), dim=-1)
+
+
+def assemble_extrinsic(pred_rotmat, translation_opt, radius=2.7):
+    """w_projector.py:160-171: cam2world from the predicted rotation and the optimisable translation, radius renormalised."""
+    dev = pred_rotmat.device
+    pred_translation = -radius * pred_rotmat[:, :3, 2]
+    translation_opt_world = -torch.bmm(pred_rotmat, translation_opt.unsqueeze(-1)) * 2.7
+    tmp_translation = translation_opt_world.squeeze(-1) + pred_translation
+    tmp_translation = tmp_translation / torch.norm(tmp_translation, dim=-1) * 2.7
+    bottom = F.pad(torch.ones([pred_rotmat.shape[0], 1, 1], device=dev), (3, 0))          # [0, 0, 0, 1] without a host->device copy
+    return torch.cat([torch.cat([pred_rotmat, tmp_translation.unsqueeze(-1)], dim=2), bottom], dim=1)
+
+
+def projection_step_loss(G, w_opt, pred_rotmat, translation_opt, init_ext, intrinsic, target_images, target_features, feature_fn,
+                         torch_vgg, noise_bufs, noise_bufs2, w_noise=None, regularize_noise_weight=1e5, layers='14',
+                         check_intersection=False, w2c=None):
+    """Loss of one w-projection iteration (w_projector.py:160-240): synthesis at the predicted camera, warping loss through a
+    second synthesis at the canonical camera, feature distance and noise regulariser.
+
+    target_images: [1, 3, H, W] in [-1, 1] (the reference's target_images_contiguous); target_features = feature_fn of the
+    0..255 target at <= 256 px; feature_fn / torch_vgg are the caller's (pretrained) feature networks."""
+    pred_ext = assemble_extrinsic(pred_rotmat, translation_opt)
+    pred_cam = torch.cat([pred_ext.reshape(-1, 16), intrinsic.reshape(1, 9)], dim=-1)
+    canonical_cam = torch.cat([init_ext.reshape(-1, 16), intrinsic.reshape(1, 9)], dim=-1)
+    ws_expand = (w_opt if w_noise is None else w_opt + w_noise).repeat(1, G.backbone.num_ws, 1)
+    pred_dict = G.synthesis(ws_expand, pred_cam, noise_mode='const', force_fp32=True)
+    pred_images = pred_dict['image'] * 127.5 + 128
+    warp_loss, _ = calc_warping_loss(ws_expand.clone().detach(), canonical_cam.clone().detach(), pred_ext, init_ext, intrinsic,
+                                     pred_dict['image_depth'], target_images, G, torch_vgg, None, layers=layers,
+                                     check_intersection=check_intersection, w2c=w2c)
+    if pred_images.shape[2] > 256:
+        pred_images = F.interpolate(pred_images, size=(256, 256), mode='area')
+    dist = (target_features - feature_fn(pred_images)).square().sum()
+    reg_loss = noise_regularizer(list(noise_bufs.values()) + list(noise_bufs2.values()))
+    return dist + reg_loss * regularize_noise_weight + warp_loss, {'dist': dist.detach(), 'warp': warp_loss.detach(), 'reg': reg_loss.detach()}

@@ -262,6 +262,102 @@ def run_b200(args):
         torch.distributed.destroy_process_group()
 
 
+def run_stage1(args):
+    """Secondary measurement: one w-projection iteration (w_projector.py:145-270) -- two synthesis calls
+    (predicted + canonical camera), warping loss, feature distance, noise regulariser, backward to w / noise buffers / pose,
+    three Adam steps, noise normalisation.  The feature networks are seeded stand-ins (VGG16 weights are unavailable offline);
+    the pose is a 6-D rotation leaf instead of the camera encoder.  Same JSON contract, different workload name."""
+    import b200eg3d
+    from b200eg3d import projector
+    from b200eg3d.graphs import GraphedStep
+    import synth_params as sp
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=rk, **sp.G_KWARGS_FULL).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), 7)
+    G = G.to(dev).float().requires_grad_(False)
+    G.neural_rendering_resolution = R
+    g = torch.Generator().manual_seed(3)
+    nb = {n: b for n, b in G.backbone.synthesis.named_buffers() if 'noise_const' in n}
+    nb2 = {n: b for n, b in G.superresolution.named_buffers() if 'noise_const' in n}
+    for b in list(nb.values()) + list(nb2.values()):
+        b.copy_(torch.randn(b.shape, generator=g))
+        b.requires_grad = True
+    for m in G.modules():                                   # noise enters only where noise_strength != 0
+        if hasattr(m, 'noise_strength'):
+            m.noise_strength.data.fill_(0.05)
+
+    def feat_net(seed):
+        chans = [(3, 16), (16, 16), None, (16, 32), (32, 32), None, (32, 64), (64, 64), (64, 64), None, (64, 64), (64, 64), (64, 64)]
+        layers = []
+        for c in chans:
+            layers += [torch.nn.MaxPool2d(2)] if c is None else [torch.nn.Conv2d(c[0], c[1], 3, padding=1), torch.nn.ReLU()]
+        net = torch.nn.Sequential(*layers)
+        gg = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.copy_(torch.randn(p_.shape, generator=gg) * (0.1 if p_.ndim > 1 else 0.01))
+        return net.to(dev).eval().requires_grad_(False)
+
+    vgg_feat, torch_vgg = feat_net(1), feat_net(2)
+    c0 = sp.camera(0.0, 0.0).to(dev)
+    init_ext, intrinsic = c0[:, :16].reshape(1, 4, 4).contiguous(), c0[0, 16:25].contiguous()
+    w2c = torch.linalg.inv(init_ext[0]).contiguous()          # constant over the loop; linalg.inv cannot be graph-captured
+    target = (torch.rand(1, 3, 512, 512, generator=g) * 2 - 1).to(dev)
+    target_255 = torch.nn.functional.interpolate((target + 1) / 2 * 255, size=(256, 256), mode='area')
+    with torch.no_grad():
+        target_features = vgg_feat(target_255)
+    w_opt = sp.latent_ws(1)[:, :1].to(dev).clone().requires_grad_(True)
+    pose6d = torch.tensor([[1.0, 0.05, 0.0, 0.02, -1.0, 0.03]], device=dev, requires_grad=True)
+    trans = torch.zeros(1, 3, device=dev, requires_grad=True)
+    opt = torch.optim.Adam([w_opt] + list(nb.values()) + list(nb2.values()), lr=5e-3, fused=True, capturable=True)
+    opt_cam = torch.optim.Adam([pose6d], lr=1e-4, fused=True, capturable=True)
+    opt_tr = torch.optim.Adam([trans], lr=1e-4, fused=True, capturable=True)
+
+    class Opts:
+        def zero_grad(self, set_to_none=True):
+            for o in (opt, opt_cam, opt_tr):
+                o.zero_grad(set_to_none=set_to_none)
+
+    def step(w_noise):
+        loss, _ = projector.projection_step_loss(G, w_opt, projector.rot6d_to_rotmat(pose6d), trans, init_ext, intrinsic, target,
+                                                 target_features, vgg_feat, torch_vgg, nb, nb2, w_noise=w_noise, w2c=w2c)
+        loss.backward()
+        opt_cam.step(); opt.step(); opt_tr.step()
+        projector.normalize_noise_(list(nb.values()) + list(nb2.values()))
+        return loss
+
+    noise = torch.randn(1, 1, 512, device=dev) * 0.01
+    graphed = GraphedStep(step, [noise], optimizer=Opts(), warmup=3)
+    for _ in range(max(args.warmup, 3)):
+        graphed(noise)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graphed(noise)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    h_noise = noise.cpu().pin_memory()
+    e0.record()
+    for _ in range(args.steps):
+        graphed(h_noise.to(dev, non_blocking=True)).item()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    line = {'metric': 'w-projection steps/sec (2 synthesis calls fwd+bwd + warping loss + noise regulariser) 512px out, 128px neural render, 48+48 depth samples',
+            'value': round(args.steps / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic (random-init generator, random target, seeded stand-in feature networks)',
+            'config': {'workload': 'stage-1 w-projection iteration (w_projector.py:145-270) at R=%d, %d+%d samples; secondary measurement, not BASELINE.json\'s metric' % (R, S, S_IMP),
+                       'launch': 'whole iteration captured in a CUDA graph'},
+            'e2e': {'value': round(args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': 2048, 'd2h_bytes_per_step': 4},
+            'loss': float(graphed.loss.item())}
+    print(json.dumps(line), flush=True)
+
+
 def cpu_baseline(warm, steps):
     """The oracle port (CPU restatement of the reference path) timed on this host's cores: full PTI steps."""
     import eg3d_oracle as oracle
@@ -323,6 +419,7 @@ if __name__ == '__main__':
     ap.add_argument('--depth-samples', type=int, default=None, help='coarse = fine depth samples per ray (default 48; 96 = config 5)')
     ap.add_argument('--ncu-step', action='store_true', help='profile exactly one step (cudaProfilerStart/Stop) and exit')
     ap.add_argument('--eager', action='store_true', help='launch every kernel from Python instead of replaying a CUDA graph')
+    ap.add_argument('--stage', default='pti', choices=['pti', 'w_projection'], help="pti = BASELINE.json's metric (default); w_projection = stage-1 iteration (secondary)")
     a = ap.parse_args()
     if a.render_res or a.depth_samples:
         R = a.render_res or R
@@ -331,5 +428,7 @@ if __name__ == '__main__':
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     if a.impl == 'reference':
         run_reference(a)
+    elif a.stage == 'w_projection':
+        run_stage1(a)
     else:
         run_b200(a)
