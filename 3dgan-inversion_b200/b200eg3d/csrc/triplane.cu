@@ -224,7 +224,10 @@ __device__ __forceinline__ void load_weights_split(const TriplaneParams& p, floa
     for (int i = threadIdx.x; i < OUTP; i += blockDim.x) b2s[i] = i < OUT ? p.b2[i] * p.b2g : 0.f;
 }
 
+// SIGMA_ONLY: density queries on voxel grids (single_id_coach.py:118-140) need column 0 of the second layer only.
+template <bool SIGMA_ONLY>
 __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(TriplaneParams p) {
+    constexpr int NT2 = SIGMA_ONLY ? 1 : 5;
     extern __shared__ __align__(16) float smem[];
     float* W1h = smem; float* W1l = W1h + HID * SF; float* W2h = W1l + HID * SF; float* W2l = W2h + OUTP * SW2;
     float* b1s = W2l + OUTP * SW2; float* b2s = b1s + HID;
@@ -279,9 +282,9 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
         }
         __syncwarp();                            // all lanes are done reading the feature tile
         // ---- layer 2: A fragments come straight from layer 1's accumulators (see the note above)
-        float o[2][5][4];
+        float o[2][NT2][4];
 #pragma unroll
-        for (int nt = 0; nt < 5; ++nt) {
+        for (int nt = 0; nt < NT2; ++nt) {
             const float bv0 = b2s[8 * nt + 2 * t], bv1 = b2s[8 * nt + 2 * t + 1];
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) { o[mt][nt][0] = o[mt][nt][2] = bv0; o[mt][nt][1] = o[mt][nt][3] = bv1; }
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
                 tf32_split(softplus_fast(c[mt][ks][3]), hh[mt][3], hl[mt][3]);     // (row g+8, unit 8ks+2t+1)
             }
 #pragma unroll
-            for (int nt = 0; nt < 5; ++nt) {
+            for (int nt = 0; nt < NT2; ++nt) {
                 const int bo = (g + 8 * nt) * SW2 + 8 * ks + 2 * t;
                 const float2 bh = *reinterpret_cast<const float2*>(&W2h[bo]);
                 const float2 bl = *reinterpret_cast<const float2*>(&W2l[bo]);
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-            for (int nt = 0; nt < 5; ++nt)
+            for (int nt = 0; nt < NT2; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int row = g + 16 * mt + ((i & 2) ? 8 : 0), col = 8 * nt + 2 * t + (i & 1);
@@ -323,9 +326,11 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
                 }
         __syncwarp();
         if (pi < p.P) p.sigma[(long)n * p.P + pi] = sF[lane * SF];
-        const int cnt = (int)min((long)32, p.P - base);
-        float* out = p.rgb + ((long)n * p.P + base) * C;
-        for (int q = 0; q < cnt; ++q) out[q * C + lane] = sF[q * SF + 1 + lane];
+        if (!SIGMA_ONLY) {
+            const int cnt = (int)min((long)32, p.P - base);
+            float* out = p.rgb + ((long)n * p.P + base) * C;
+            for (int q = 0; q < cnt; ++q) out[q * C + lane] = sF[q * SF + 1 + lane];
+        }
         __syncwarp();
     }
 }
@@ -715,7 +720,7 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
                                    float* rgb, float* sigma, void* stream) {
     TriplaneParams p{};
     if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
-    B200_REQUIRE(rgb && sigma, "triplane_fwd: null output");
+    B200_REQUIRE(sigma, "triplane_fwd: null output");        // rgb == NULL: density-only query
     if (P == 0) return 0;
     p.rgb = rgb; p.sigma = sigma;
     const long groups = (P + 127) / 128;
@@ -724,12 +729,14 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     if (passes == 0) {
         const char* e2 = getenv("B200EG3D_MLP_PASSES");
         passes = (e2 && strcmp(e2, "1") == 0) ? 1 : 3;
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
     }
     p.fwd_passes = passes;
     const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
     grid.x = (unsigned)(g512 < 148 ? g512 : 148);                      // persistent: one 16-warp CTA per SM
-    triplane_mlp_fwd_mma_kernel<<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
+    if (rgb) triplane_mlp_fwd_mma_kernel<false><<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
+    else triplane_mlp_fwd_mma_kernel<true><<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -85,6 +85,17 @@ def main():
     a, b = literal_noise_reg(bufs), s1.noise_regularizer(list(bufs.values()))
     print('noise reg', float(a), float(b))
     out['noise_reg'] = np.float64(float(a))
+    # create_samples: run the reference function's own source (single_id_coach.py imports lpips / mrcfile, absent here)
+    import ast
+    src = open(os.path.join(REF, 'training', 'coaches', 'single_id_coach.py')).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'create_samples'][0]
+    ns = {'np': np, 'torch': torch}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), 'single_id_coach.py', 'exec'), ns)
+    for N in (16, 256):
+        ref_s, _, _ = ns['create_samples'](N=N, voxel_origin=[0, 0, 0], cube_length=1.0)
+        mine, _, _ = s1.create_samples(N=N, voxel_origin=[0, 0, 0], cube_length=1.0)
+        print('create_samples', N, 'max diff vs oracle', (ref_s - mine).abs().max().item())
+        out[f'samples_n{N}'] = ref_s[0, ::(1 if N == 16 else 4099)].numpy().astype(np.float32)
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'stage1_warp.npz'), **out)
     print('wrote stage1_warp.npz')
 

@@ -63,6 +63,23 @@ def warping_loss(can_images, extrinsic, init_ext, intrinsic, depth, target_image
     return ((wf - ft) * mask).abs().mean(), wi
 
 
+def create_samples(N=256, voxel_origin=(0, 0, 0), cube_length=2.0):
+    """training/coaches/single_id_coach.py:165-188 restated on CPU (fp32 index arithmetic kept as written there).
+    Pinned by make_goldens_stage1.py, which executes the reference function's own source (extracted with ast)."""
+    import numpy as np
+    origin = np.array(voxel_origin) - cube_length / 2
+    size = cube_length / (N - 1)
+    idx = torch.arange(0, N ** 3, 1, dtype=torch.long)
+    s = torch.zeros(N ** 3, 3)
+    s[:, 2] = idx % N
+    s[:, 1] = (idx.float() / N) % N
+    s[:, 0] = ((idx.float() / N) / N) % N
+    s[:, 0] = (s[:, 0] * size) + origin[2]
+    s[:, 1] = (s[:, 1] * size) + origin[1]
+    s[:, 2] = (s[:, 2] * size) + origin[0]
+    return s.unsqueeze(0), origin, size
+
+
 def noise_regularizer(bufs):
     """w_projector.py:221-237."""
     reg = 0.0
