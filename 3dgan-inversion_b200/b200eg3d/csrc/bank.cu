@@ -195,6 +195,201 @@ __global__ void __launch_bounds__(256) bank_styles_bwd_kernel(const __grid_const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Vectorised weight kernels for the shapes every EG3D layer has (cin a multiple of 8 and <= 2048, 1 or 9 taps): one thread owns
+// 8 consecutive input channels x all taps of ONE output channel -- TAPS*8 contiguous floats of W, read with 16-byte loads and
+// kept in registers across the demodulation reduction -- and writes, per tap, one 16-byte bf16x8 vector each to w_hi / w_lo
+// (cin-contiguous GEMM layout).  A cout's cin/8 threads form one reduction group; a 256-thread block holds 256/(cin/8) couts.
+// sum over the `gs` consecutive threads of a group (gs a power of two; groups never straddle a block)
+__device__ __forceinline__ float group_sum(float v, int gs, float* red) {
+    if (gs <= 32) {
+        for (int o = gs >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    v = warp_sum(v);
+    const int wid = threadIdx.x >> 5, wpg = gs >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[wid] = v;
+    __syncthreads();
+    float s = 0.f;
+    const int w0 = (wid / wpg) * wpg;
+    for (int i = 0; i < wpg; ++i) s += red[w0 + i];
+    return s;
+}
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    return make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
+                      *reinterpret_cast<uint32_t*>(&d));
+}
+
+template <int TAPS>
+__device__ __forceinline__ void weights_fwd_vec(const B200BankLayer& L, int blk, int n, float* red) {
+    const int cin = L.cin, cout = L.cout, gs = cin >> 3, cpb = 256 / gs;     // gs: power of two for every EG3D layer; else fall back
+    const int o = blk * cpb + (int)threadIdx.x / gs, i0 = ((int)threadIdx.x % gs) * 8;
+    const bool live = o < cout && (int)threadIdx.x < cpb * gs;
+    float w[TAPS * 8];
+    if (live) {
+        const float4* src = reinterpret_cast<const float4*>(L.weight + ((long)o * cin + i0) * TAPS);
+#pragma unroll
+        for (int q = 0; q < TAPS * 2; ++q) { const float4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+    }
+    __nv_bfloat16* whi = (__nv_bfloat16*)L.w_hi;
+    __nv_bfloat16* wlo = (__nv_bfloat16*)L.w_lo;
+    for (int b = 0; b < n; ++b) {
+        float v[TAPS * 8];
+        float acc = 0.f;
+        if (live) {
+            const float4 s0 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0), s1 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0 + 4);
+            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int tp = 0; tp < TAPS; ++tp) { v[j * TAPS + tp] = w[j * TAPS + tp] * s[j]; acc = fmaf(v[j * TAPS + tp], v[j * TAPS + tp], acc); }
+        }
+        float d = 1.f;
+        if (L.demod) {
+            acc = group_sum(acc, gs, red);
+            d = rsqrtf(acc + 1e-8f);
+            if (live && i0 == 0) L.dcoef[(long)b * cout + o] = d;
+        }
+        if (live) {
+            const long ob = (long)b * TAPS * cout * cin;
+#pragma unroll
+            for (int tp = 0; tp < TAPS; ++tp) {
+                float x[8], lo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = v[j * TAPS + tp] * d;
+                const long oi = ob + ((long)tp * cout + o) * cin + i0;
+                if (L.wmod) {
+                    *reinterpret_cast<float4*>(L.wmod + oi) = make_float4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<float4*>(L.wmod + oi + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                }
+                if (whi) {
+                    const uint4 h = pack8_bf16(x);
+                    *reinterpret_cast<uint4*>(whi + oi) = h;
+                    if (wlo) {
+                        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) lo[j] = x[j] - __bfloat162float(hb[j]);
+                        *reinterpret_cast<uint4*>(wlo + oi) = pack8_bf16(lo);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bank_weights_fwd_vec_kernel(const __grid_constant__ BankTable t, int n) {
+    __shared__ float red[8];
+    const int l = find_layer(t, blockIdx.x);
+    const B200BankLayer& L = t.l[l];
+    if (L.taps == 9) weights_fwd_vec<9>(L, blockIdx.x - t.start[l], n, red);
+    else weights_fwd_vec<1>(L, blockIdx.x - t.start[l], n, red);
+}
+
+template <int TAPS>
+__device__ __forceinline__ void weights_bwd_vec(const B200BankLayer& L, int blk, int n, float* red, float* sds) {
+    const int cin = L.cin, cout = L.cout, gs = cin >> 3, cpb = 256 / gs;
+    const int o = blk * cpb + (int)threadIdx.x / gs, i0 = ((int)threadIdx.x % gs) * 8;
+    const bool live = o < cout && (int)threadIdx.x < cpb * gs;
+    float w[TAPS * 8], dW[TAPS * 8];
+#pragma unroll
+    for (int q = 0; q < TAPS * 8; ++q) { w[q] = 0.f; dW[q] = 0.f; }
+    if (live) {
+        const float4* src = reinterpret_cast<const float4*>(L.weight + ((long)o * cin + i0) * TAPS);
+#pragma unroll
+        for (int q = 0; q < TAPS * 2; ++q) { const float4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+    }
+    for (int b = 0; b < n; ++b) {
+        float s[8], g[TAPS * 8];
+        float d = 1.f, acc = 0.f;
+        if (live) {
+            const float4 s0 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0), s1 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0 + 4);
+            s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+            const float* G = L.dwmod + (long)b * TAPS * cout * cin;
+#pragma unroll
+            for (int tp = 0; tp < TAPS; ++tp) {
+                const float4 g0 = *reinterpret_cast<const float4*>(G + ((long)tp * cout + o) * cin + i0);
+                const float4 g1 = *reinterpret_cast<const float4*>(G + ((long)tp * cout + o) * cin + i0 + 4);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { g[j * TAPS + tp] = gg[j]; acc = fmaf(gg[j], w[j * TAPS + tp] * s[j], acc); }
+            }
+        }
+        float d3dot = 0.f;
+        if (L.demod) {
+            const float dot = group_sum(acc, gs, red);
+            if (live) d = L.dcoef[(long)b * cout + o];
+            d3dot = d * d * d * dot;
+        }
+        float dsv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dsv[j] = 0.f;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int tp = 0; tp < TAPS; ++tp) {
+                    float gv = g[j * TAPS + tp] * d;
+                    if (L.demod) gv -= d3dot * w[j * TAPS + tp] * s[j];
+                    dsv[j] = fmaf(w[j * TAPS + tp], gv, dsv[j]);
+                    dW[j * TAPS + tp] += s[j] * gv;
+                }
+            }
+        }
+        if (L.d_styles) {       // d styles: sum the block's couts in shared memory, then one coalesced atomic per input channel
+            __syncthreads();
+            *reinterpret_cast<float4*>(sds + threadIdx.x * 8) = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
+            *reinterpret_cast<float4*>(sds + threadIdx.x * 8 + 4) = make_float4(dsv[4], dsv[5], dsv[6], dsv[7]);
+            __syncthreads();
+            for (int i = threadIdx.x; i < cin; i += 256) {
+                float a = 0.f;
+                for (int c = 0; c < cpb; ++c) a += sds[c * cin + i];
+                atomicAdd(L.d_styles + (long)b * cin + i, a);
+            }
+        }
+    }
+    if (live && L.d_weight) {
+        float4* dst = reinterpret_cast<float4*>(L.d_weight + ((long)o * cin + i0) * TAPS);
+#pragma unroll
+        for (int q = 0; q < TAPS * 2; ++q) dst[q] = make_float4(dW[4 * q], dW[4 * q + 1], dW[4 * q + 2], dW[4 * q + 3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) bank_weights_bwd_vec_kernel(const __grid_constant__ BankTable t, int n) {
+    __shared__ float red[8];
+    __shared__ __align__(16) float sds[256 * 8];
+    const int l = find_layer(t, blockIdx.x);
+    const B200BankLayer& L = t.l[l];
+    if (!L.dwmod) return;
+    if (L.taps == 9) weights_bwd_vec<9>(L, blockIdx.x - t.start[l], n, red, sds);
+    else weights_bwd_vec<1>(L, blockIdx.x - t.start[l], n, red, sds);
+}
+
+bool host_vec_ok(const B200BankLayer& L) {
+    const int gs = L.cin >> 3;
+    return (L.taps == 9 || L.taps == 1) && (L.cin & 7) == 0 && L.cin <= 2048 && (gs & (gs - 1)) == 0;
+}
+
+// block table of the vectorised kernels: ceil(cout / (256 / (cin/8))) blocks per layer
+int fill_table_vec(BankTable& t, const B200BankLayer* layers, int n_layers, bool& all_vec) {
+    B200_REQUIRE(layers && n_layers > 0 && n_layers <= MAXL, "bank: between 1 and 32 layers");
+    t.n_layers = n_layers;
+    t.start[0] = 0;
+    all_vec = true;
+    for (int l = 0; l < n_layers; ++l) {
+        t.l[l] = layers[l];
+        B200_REQUIRE(layers[l].cin > 0 && layers[l].cout > 0 && layers[l].taps > 0, "bank: bad layer shape");
+        if (!host_vec_ok(layers[l])) { all_vec = false; break; }
+        const int cpb = 256 / (layers[l].cin >> 3);
+        t.start[l + 1] = t.start[l] + (layers[l].cout + cpb - 1) / cpb;
+    }
+    return 0;
+}
+
 int fill_table(BankTable& t, const B200BankLayer* layers, int n_layers, bool per_row8) {
     B200_REQUIRE(layers && n_layers > 0 && n_layers <= MAXL, "bank: between 1 and 32 layers");
     t.n_layers = n_layers;
@@ -230,6 +425,13 @@ B200_API int b200_bank_styles_fwd(const B200BankLayer* layers, int n_layers, con
 
 B200_API int b200_bank_weights_fwd(const B200BankLayer* layers, int n_layers, int n, void* stream) {
     BankTable t;
+    bool all_vec = false;
+    if (int e = fill_table_vec(t, layers, n_layers, all_vec)) return e;
+    if (all_vec) {
+        bank_weights_fwd_vec_kernel<<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     if (int e = fill_table(t, layers, n_layers, false)) return e;
     const size_t smem = max_smem(layers, n_layers, 1);
     B200_REQUIRE(smem <= 48 * 1024, "bank: cin*taps too large for the staging tile");
@@ -240,6 +442,13 @@ B200_API int b200_bank_weights_fwd(const B200BankLayer* layers, int n_layers, in
 
 B200_API int b200_bank_weights_bwd(const B200BankLayer* layers, int n_layers, int n, void* stream) {
     BankTable t;
+    bool all_vec = false;
+    if (int e = fill_table_vec(t, layers, n_layers, all_vec)) return e;
+    if (all_vec) {
+        bank_weights_bwd_vec_kernel<<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     if (int e = fill_table(t, layers, n_layers, false)) return e;
     const size_t smem = max_smem(layers, n_layers, 2);
     B200_REQUIRE(smem <= 48 * 1024, "bank: cin*taps too large for the staging tiles");

@@ -40,3 +40,24 @@ def load_old_G(path, device='cuda'):
     with open(path, 'rb') as f:
         G_ref = pickle.load(f)['G_ema'].eval().float()
     return convert_generator(G_ref, device=device).float()
+
+
+def save_tuned_G(G, path):
+    """Checkpoint of a (PTI-tuned) generator: constructor arguments + state_dict + the attributes callers set after loading.
+    The reference never saves the tuned generator (single_id_coach.py:117 is commented out); this is the `state_dict` route
+    SURVEY.md 8 f4 asks for.  Plain torch.save of tensors and python scalars -- no pickled code."""
+    torch.save({'format': 'b200eg3d.tuned_G.v1', 'init_args': tuple(G.init_args), 'init_kwargs': copy.deepcopy(dict(G.init_kwargs)),
+                'state_dict': {k: v.detach().cpu() for k, v in G.state_dict().items()},
+                'neural_rendering_resolution': int(G.neural_rendering_resolution),
+                'rendering_kwargs': copy.deepcopy(dict(G.rendering_kwargs))}, path)
+
+
+def load_tuned_G(path, device='cuda'):
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    if ck.get('format') != 'b200eg3d.tuned_G.v1':
+        raise ValueError(f'{path} is not a b200eg3d tuned-generator checkpoint')
+    G = TriPlaneGenerator(*ck['init_args'], **ck['init_kwargs']).eval().requires_grad_(False)
+    G.load_state_dict(ck['state_dict'], strict=True)
+    G.neural_rendering_resolution = ck['neural_rendering_resolution']
+    G.rendering_kwargs = ck['rendering_kwargs']
+    return G.to(device)

@@ -118,3 +118,20 @@ def test_gloo_world_size_2_reduction():
     res = out.get(timeout=120)
     [p.join(timeout=60) for p in procs]
     assert res == (50, 150.0, 10.0)
+
+
+def test_tuned_generator_checkpoint_roundtrip(tmp_path):
+    import b200eg3d
+    import synth_params as sp
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=sp.rendering_kwargs(), **sp.G_KWARGS_TINY)
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), 5)
+    G.neural_rendering_resolution = 128
+    path = str(tmp_path / 'tuned.pt')
+    b200eg3d.seam.save_tuned_G(G, path)
+    G2 = b200eg3d.seam.load_tuned_G(path, device='cpu')
+    assert G2.neural_rendering_resolution == 128 and G2.rendering_kwargs == G.rendering_kwargs
+    for (n1, p1), (n2, p2) in zip(sorted(G.state_dict().items()), sorted(G2.state_dict().items())):
+        assert n1 == n2 and torch.equal(p1, p2)
+    torch.save({'format': 'other'}, path)
+    with pytest.raises(ValueError):
+        b200eg3d.seam.load_tuned_G(path, device='cpu')
