@@ -69,10 +69,10 @@ __device__ __forceinline__ void march_weights(const float* ts, const float* ss, 
 
 __global__ void __launch_bounds__(128) ray_importance_kernel(const float* __restrict__ t_c, const float* __restrict__ sigma_c,
                                                              const float* __restrict__ u, float* __restrict__ t_f,
-                                                             long n_rays, int S, int S_imp) {
-    __shared__ float sm[4][5 * MAXS];
+                                                             long n_rays, int S, int S_imp, int SP) {
+    extern __shared__ float dyn[];                 // per warp: 5 arrays of SP floats (SP = samples rounded up): more resident warps than a fixed 256
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* ts = sm[wid]; float* ss = ts + MAXS; float* alpha = ss + MAXS; float* trans = alpha + MAXS; float* w = trans + MAXS;
+    float* ts = dyn + wid * 5 * SP; float* ss = ts + SP; float* alpha = ss + SP; float* trans = alpha + SP; float* w = trans + SP;
     for (long ray = (long)blockIdx.x * 4 + wid; ray < n_rays; ray += (long)gridDim.x * 4) {
         for (int k = lane; k < S; k += 32) { ts[k] = t_c[ray * S + k]; ss[k] = sigma_c[ray * S + k]; }
         __syncwarp();
@@ -121,44 +121,89 @@ struct CompositeParams {
 
 // Loads one ray, ranks the merged samples by depth (ties broken by original index) and fills
 // ts/ss (sorted depth, density) and rk[i] = sorted position of original sample i.
+// Fast path (the renderer's case): the coarse depths are already non-decreasing (stratified sampling), so only the fine
+// samples are ranked against each other (S2^2 compares) and the two sorted lists are merged by binary search:
+//   rank(coarse i) = i + #{fine < t_i}            rank(fine j) = rank_in_fine(j) + #{coarse <= t_j}
+// -- exactly the order a stable sort of [coarse..., fine...] produces (torch.sort in renderer.py:218).  Unsorted coarse
+// depths fall back to the all-pairs ranking.  `scratch` holds S2 floats (the sorted fine depths).
 __device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray, float* traw, float* ts, float* ss, int* rk,
-                                              int lane) {
-    const int S = p.S1 + p.S2;
-    for (int i = lane; i < S; i += 32) traw[i] = i < p.S1 ? p.t_c[ray * p.S1 + i] : p.t_f[ray * p.S2 + i - p.S1];
+                                              float* scratch, int lane) {
+    const int S1 = p.S1, S2 = p.S2, S = S1 + S2;
+    for (int i = lane; i < S; i += 32) traw[i] = i < S1 ? p.t_c[ray * S1 + i] : p.t_f[ray * S2 + i - S1];
     __syncwarp();
-    for (int i = lane; i < S; i += 32) {
-        const float ti = traw[i];
-        int r = 0;
-        for (int j = 0; j < S; ++j) { const float tj = traw[j]; r += (tj < ti) || (tj == ti && j < i); }
-        rk[i] = r;
-        ts[r] = ti;
-        ss[r] = i < p.S1 ? p.sigma_c[ray * p.S1 + i] : p.sigma_f[ray * p.S2 + i - p.S1];
+    bool sorted = true;
+    for (int i = lane; i + 1 < S1; i += 32) sorted = sorted && (traw[i] <= traw[i + 1]);
+    sorted = __all_sync(0xffffffffu, sorted);
+    if (sorted) {
+        const float* tf = traw + S1;
+        for (int j = lane; j < S2; j += 32) {                 // rank among the fine samples
+            const float tj = tf[j];
+            int r = 0;
+            for (int k = 0; k < S2; ++k) { const float tk = tf[k]; r += (tk < tj) || (tk == tj && k < j); }
+            rk[S1 + j] = r;
+            scratch[r] = tj;
+        }
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) {
+            const float ti = traw[i];
+            int r;
+            if (i < S1) {                                      // lower_bound in the sorted fine depths
+                int lo = 0, hi = S2;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (scratch[mid] < ti) lo = mid + 1; else hi = mid; }
+                r = i + lo;
+            } else {                                           // upper_bound in the coarse depths
+                int lo = 0, hi = S1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (traw[mid] <= ti) lo = mid + 1; else hi = mid; }
+                r = rk[i] + lo;
+            }
+            rk[i] = r;
+            ts[r] = ti;
+            ss[r] = i < S1 ? p.sigma_c[ray * S1 + i] : p.sigma_f[ray * S2 + i - S1];
+        }
+    } else {
+        for (int i = lane; i < S; i += 32) {
+            const float ti = traw[i];
+            int r = 0;
+            for (int j = 0; j < S; ++j) { const float tj = traw[j]; r += (tj < ti) || (tj == ti && j < i); }
+            rk[i] = r;
+            ts[r] = ti;
+            ss[r] = i < S1 ? p.sigma_c[ray * S1 + i] : p.sigma_f[ray * S2 + i - S1];
+        }
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams p) {
-    __shared__ float sm[4][6 * MAXS];
+__global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams p, int SP) {
+    extern __shared__ float dyn[];                 // per warp: 6 float arrays + the rank array, SP entries each
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* traw = sm[wid]; float* ts = traw + MAXS; float* ss = ts + MAXS; float* alpha = ss + MAXS;
-    float* trans = alpha + MAXS; float* w = trans + MAXS;
-    __shared__ int srk[4][MAXS];
-    int* rk = srk[wid];
+    float* traw = dyn + wid * 7 * SP; float* ts = traw + SP; float* ss = ts + SP; float* alpha = ss + SP;
+    float* trans = alpha + SP; float* w = trans + SP;
+    int* rk = reinterpret_cast<int*>(w + SP);
     const int S = p.S1 + p.S2;
     const float dmin = ord2f(p.minmax[0]), dmax = ord2f(p.minmax[1]);
     for (long ray = (long)blockIdx.x * 4 + wid; ray < p.n_rays; ray += (long)gridDim.x * 4) {
-        load_and_rank(p, ray, traw, ts, ss, rk, lane);
+        load_and_rank(p, ray, traw, ts, ss, rk, alpha, lane);
         march_weights(ts, ss, S, alpha, trans, w, lane);
         float ws = 0.f, dn = 0.f;
         for (int k = lane; k < S - 1; k += 32) { ws += w[k]; dn += w[k] * 0.5f * (ts[k] + ts[k + 1]); }
         ws = warp_sum(ws); dn = warp_sum(dn);
         float acc = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < S; ++i) {
-            const int r = rk[i];
-            const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
-            const float c = i < p.S1 ? p.rgb_c[(ray * p.S1 + i) * 32 + lane] : p.rgb_f[(ray * p.S2 + i - p.S1) * 32 + lane];
-            acc = fmaf(om, c, acc);
+        for (int i0 = 0; i0 < S; i0 += 16) {          // 16 colour rows (128 B each, lane = channel) in flight per warp
+            float c[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = i0 + j;
+                c[j] = i >= S ? 0.f : (i < p.S1 ? __ldg(p.rgb_c + (ray * p.S1 + i) * 32 + lane) : __ldg(p.rgb_f + (ray * p.S2 + i - p.S1) * 32 + lane));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int i = i0 + j;
+                if (i < S) {
+                    const int r = rk[i];
+                    const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+                    acc = fmaf(om, c[j], acc);
+                }
+            }
         }
         if (p.white_back) acc += 1.f - ws;
         p.feat[ray * 32 + lane] = acc * 2.f - 1.f;
@@ -172,17 +217,16 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
     }
 }
 
-__global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams p) {
-    __shared__ float sm[4][8 * MAXS];
+__global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams p, int SP) {
+    extern __shared__ float dyn[];                 // per warp: 8 float arrays + the rank array, SP entries each
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    float* traw = sm[wid]; float* ts = traw + MAXS; float* ss = ts + MAXS; float* alpha = ss + MAXS;
-    float* trans = alpha + MAXS; float* w = trans + MAXS; float* dom = w + MAXS; float* dsb = dom + MAXS;
-    __shared__ int srk[4][MAXS];
-    int* rk = srk[wid];
+    float* traw = dyn + wid * 9 * SP; float* ts = traw + SP; float* ss = ts + SP; float* alpha = ss + SP;
+    float* trans = alpha + SP; float* w = trans + SP; float* dom = w + SP; float* dsb = dom + SP;
+    int* rk = reinterpret_cast<int*>(dsb + SP);
     const int S = p.S1 + p.S2;
     const float dmin = ord2f(p.minmax[0]), dmax = ord2f(p.minmax[1]);
     for (long ray = (long)blockIdx.x * 4 + wid; ray < p.n_rays; ray += (long)gridDim.x * 4) {
-        load_and_rank(p, ray, traw, ts, ss, rk, lane);
+        load_and_rank(p, ray, traw, ts, ss, rk, alpha, lane);
         march_weights(ts, ss, S, alpha, trans, w, lane);
         float ws = 0.f, dn = 0.f;
         for (int k = lane; k < S - 1; k += 32) { ws += w[k]; dn += w[k] * 0.5f * (ts[k] + ts[k + 1]); }
@@ -280,8 +324,9 @@ B200_API int b200_ray_importance(const float* t_c, const float* sigma_c, const f
                                  int S_imp, void* stream) {
     B200_REQUIRE(S >= 4 && S <= MAXS, "ray_importance: need 4 <= depth_resolution <= 256");
     if (n_rays <= 0 || S_imp <= 0) return 0;
-    const int blocks = (int)((n_rays + 3) / 4 < 148 * 8 ? (n_rays + 3) / 4 : 148 * 8);
-    ray_importance_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(t_c, sigma_c, u, t_f, n_rays, S, S_imp);
+    const int SP = (S + 3) & ~3;
+    const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
+    ray_importance_kernel<<<blocks, 128, 4 * 5 * SP * sizeof(float), (cudaStream_t)stream>>>(t_c, sigma_c, u, t_f, n_rays, S, S_imp, SP);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -294,8 +339,9 @@ B200_API int b200_ray_composite_fwd(const float* t_c, const float* sigma_c, cons
     CompositeParams p{};
     p.t_c = t_c; p.sigma_c = sigma_c; p.rgb_c = rgb_c; p.S1 = S1; p.t_f = t_f; p.sigma_f = sigma_f; p.rgb_f = rgb_f; p.S2 = S2;
     p.minmax = minmax; p.white_back = white_back; p.n_rays = n_rays; p.feat = feat; p.depth = depth; p.wsum = wsum;
-    const int blocks = (int)((n_rays + 3) / 4 < 148 * 8 ? (n_rays + 3) / 4 : 148 * 8);
-    ray_composite_fwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+    const int SP = (S1 + S2 + 3) & ~3;
+    const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
+    ray_composite_fwd_kernel<<<blocks, 128, 4 * 7 * SP * sizeof(float), (cudaStream_t)stream>>>(p, SP);
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -313,8 +359,9 @@ B200_API int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, cons
     p.minmax = minmax; p.white_back = white_back; p.n_rays = n_rays;
     p.d_feat = d_feat; p.d_depth = d_depth; p.d_wsum = d_wsum;
     p.d_rgb_c = d_rgb_c; p.d_sigma_c = d_sigma_c; p.d_rgb_f = d_rgb_f; p.d_sigma_f = d_sigma_f;
-    const int blocks = (int)((n_rays + 3) / 4 < 148 * 8 ? (n_rays + 3) / 4 : 148 * 8);
-    ray_composite_bwd_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(p);
+    const int SP = (S1 + S2 + 3) & ~3;
+    const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
+    ray_composite_bwd_kernel<<<blocks, 128, 4 * 9 * SP * sizeof(float), (cudaStream_t)stream>>>(p, SP);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -321,3 +321,52 @@ def test_pti_loss_fwd_bwd(b2, n, h, r):
     with pytest.raises(RuntimeError, match='divide'):
         b2.losses.pti_loss({'image': dev_in[0].permute(0, 3, 1, 2), 'image_raw': torch.zeros(n, 3, 5, 5, device='cuda'), 'image_depth': None},
                            real.cuda())
+
+
+@pytest.mark.parametrize('mode', ['sorted', 'unsorted', 'ties'])
+@pytest.mark.parametrize('S1,S2', [(48, 48), (7, 13), (16, 0), (96, 96)])
+def test_ray_composite_merge_orders(b2, mode, S1, S2):
+    """The merge of coarse + fine samples (renderer.py:212-222): sorted coarse depths take the binary-search merge, unsorted
+    ones the all-pairs ranking; ties resolve like a stable sort of [coarse..., fine...].  Forward and backward vs the oracle."""
+    from b200eg3d._lib import call, ptr, stream
+    M = 40
+    g = gen(S1 * 100 + S2 + len(mode))
+    t_c = torch.rand(1, M, S1, 1, generator=g) + 2.0
+    if mode != 'unsorted':
+        t_c = t_c.sort(dim=2).values
+    t_f = torch.rand(1, M, max(S2, 1), 1, generator=g)[:, :, :S2] + 2.0
+    if mode == 'ties' and S2 > 0:
+        k = min(S1, S2)
+        t_f[:, :, :k:3] = t_c[:, :, :k:3]                                            # fine samples that coincide with coarse ones
+        if S2 > 4:
+            t_f[:, :, 1] = t_f[:, :, 4]                                              # and a tie inside the fine list
+    rgb = torch.rand(1, M, S1 + S2, 32, generator=g)
+    sig = torch.randn(1, M, S1 + S2, 1, generator=g) * 3
+    d_feat, d_depth = torch.randn(1, M, 32, generator=g), torch.randn(1, M, 1, generator=g)
+    # oracle: stable sort of the concatenation, then the mid-point marcher
+    rr, sr = rgb.clone().requires_grad_(True), sig.clone().requires_grad_(True)
+    t_all = torch.cat([t_c, t_f], 2)
+    order = torch.sort(t_all, dim=2, stable=True).indices
+    feat_ref, depth_ref, w_ref = oracle.ray_march(torch.gather(rr, 2, order.expand(-1, -1, -1, 32)), torch.gather(sr, 2, order),
+                                                  torch.gather(t_all, 2, order))
+    ((feat_ref * d_feat).sum() + (depth_ref * d_depth).sum()).backward()
+    dev = lambda t: t.contiguous().cuda()
+    tc, tf = dev(t_c.reshape(M, S1)), (dev(t_f.reshape(M, S2)) if S2 else None)
+    rc, rf = dev(rgb[0, :, :S1]), (dev(rgb[0, :, S1:]) if S2 else None)
+    sc, sf = dev(sig[0, :, :S1, 0]), (dev(sig[0, :, S1:, 0]) if S2 else None)
+    mm = torch.zeros(2, dtype=torch.int32, device='cuda'); mm[:1].fill_(-1)
+    call('b200_depth_minmax', ptr(tc), tc.numel(), ptr(mm), stream())
+    if S2:
+        call('b200_depth_minmax', ptr(tf), tf.numel(), ptr(mm), stream())
+    feat, depth, wsum = torch.empty(M, 32, device='cuda'), torch.empty(M, device='cuda'), torch.empty(M, device='cuda')
+    call('b200_ray_composite_fwd', ptr(tc), ptr(sc), ptr(rc), S1, ptr(tf), ptr(sf), ptr(rf), S2, ptr(mm), 0, M, ptr(feat), ptr(depth), ptr(wsum), stream())
+    assert maxdiff(feat, feat_ref[0]) < 2e-5 and maxdiff(depth, depth_ref[0, :, 0]) < 2e-5
+    assert maxdiff(wsum, w_ref.sum(2)[0, :, 0]) < 2e-5
+    d_rc, d_sc = torch.empty_like(rc), torch.empty_like(sc)
+    d_rf, d_sf = (torch.empty_like(rf), torch.empty_like(sf)) if S2 else (None, None)
+    g_feat, g_depth = dev(d_feat[0]), dev(d_depth[0, :, 0])        # keep the device copies alive across the asynchronous launch
+    call('b200_ray_composite_bwd', ptr(tc), ptr(sc), ptr(rc), S1, ptr(tf), ptr(sf), ptr(rf), S2, ptr(mm), 0, M, ptr(g_feat),
+         ptr(g_depth), None, ptr(d_rc), ptr(d_sc), ptr(d_rf), ptr(d_sf), stream())
+    assert relerr(d_rc, rr.grad[0, :, :S1]) < 1e-4 and relerr(d_sc, sr.grad[0, :, :S1, 0]) < 1e-4
+    if S2:
+        assert relerr(d_rf, rr.grad[0, :, S1:]) < 1e-4 and relerr(d_sf, sr.grad[0, :, S1:, 0]) < 1e-4
