@@ -13,8 +13,13 @@ def bf(*shape):
     return (torch.randn(*shape, device=dev) * 0.5).to(torch.bfloat16).contiguous()
 
 
+ONCE = '--once' in sys.argv          # ncu captures: launch every kernel exactly once
+
+
 def timeit(fn, name, flops, iters=10):
     fn(); torch.cuda.synchronize()
+    if ONCE:
+        return
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
