@@ -49,6 +49,8 @@ B200_API int b200_conv_dgrad(const float* dy, const float* wmod, float* dx, int 
     B200_REQUIRE(up == 1 || (up == 2 && ksize == 3), "conv_dgrad: up must be 1, or 2 with ksize 3");
     cudaStream_t st = (cudaStream_t)stream;
     const int taps = ksize * ksize;
+    if (ksize == 1 && up == 1 && cout <= 4 && cin % 4 == 0 && cin <= 512)
+        return launch_conv_dgrad_thin(dy, wmod, dx, n, (long)h * w, cout, cin, st);
     ConvPixParams p{};
     const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
     p.A = dy; p.a_bs = (long)hs * ws * cout;

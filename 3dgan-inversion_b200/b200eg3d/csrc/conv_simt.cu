@@ -275,6 +275,42 @@ int launch_conv_wgrad_thin(const float* x, const float* dy, float* dW, int batch
     return 0;
 }
 
+// Thin data gradient of a 1x1 convolution with <= 4 output channels (the ToRGB layers of the super-resolution blocks):
+// dx[pix][ci] = sum_o dy[pix][o] * w[o][ci] is a streaming write of the cin-wide activation gradient -- one thread per
+// (pixel, 4 input channels), weights in shared memory.
+__global__ void __launch_bounds__(256) conv_dgrad_thin_kernel(const float* __restrict__ dy, const float* __restrict__ w,
+                                                              float* __restrict__ dx, long npix, int cm, int cn, long w_bs) {
+    __shared__ float sw[4 * 512];
+    const int b = blockIdx.y;
+    dy += (long)b * npix * cm; dx += (long)b * npix * cn; w += (long)b * w_bs;
+    for (int i = threadIdx.x; i < cm * cn; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    const int c4 = cn >> 2;
+    const long total = npix * c4;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long pix = i / c4;
+        const int cc = (int)(i - pix * c4) * 4;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (m < cm) {
+                const float d = __ldg(dy + pix * cm + m);
+                const float4 wv = *reinterpret_cast<const float4*>(&sw[m * cn + cc]);
+                acc.x = fmaf(d, wv.x, acc.x); acc.y = fmaf(d, wv.y, acc.y); acc.z = fmaf(d, wv.z, acc.z); acc.w = fmaf(d, wv.w, acc.w);
+            }
+        *reinterpret_cast<float4*>(dx + pix * cn + cc) = acc;
+    }
+}
+
+int launch_conv_dgrad_thin(const float* dy, const float* w, float* dx, int batch, long npix, int cm, int cn, cudaStream_t st) {
+    if (npix <= 0 || batch <= 0) return 0;
+    const long nb = (npix * (cn / 4) + 255) / 256;
+    dim3 grid((unsigned)(nb < 148 * 16 ? nb : 148 * 16), batch);
+    conv_dgrad_thin_kernel<<<grid, 256, 0, st>>>(dy, w, dx, npix, cm, cn, (long)cm * cn);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
 int launch_conv_pix_simt(const ConvPixParams& p, int batch, cudaStream_t st) {
     const int M = p.g.Hi * p.g.Wi;
     if (M <= 0 || p.N <= 0 || batch <= 0) return 0;

@@ -534,8 +534,17 @@ static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t s
     const bool sq4 = p.fh == 4 && p.fw == 4 && p.upx == p.upy && p.downx == p.downy;
     if (v4 && sq4 && p.upx == 1 && p.downx == 1) {
         const long strips = (long)p.n * ((p.oh + 1) / 2) * ((p.ow + 3) / 4) * (p.c / 4);
-        const int sb = (int)((strips + 255) / 256 < 148 * 32 ? (strips + 255) / 256 : 148 * 32);
-        fir4_strip_kernel<<<sb, 256, 0, st>>>(p);
+        // The register-blocked kernel needs enough strips to fill the GPU; below that the one-output-per-thread kernel has
+        // 8x the parallelism and finishes sooner (these launches are latency-bound, not bandwidth-bound).
+#ifndef B200_FIR_STRIP_MIN
+#define B200_FIR_STRIP_MIN (148L * 256)
+#endif
+        if (strips >= B200_FIR_STRIP_MIN) {
+            const int sb = (int)((strips + 255) / 256 < 148 * 32 ? (strips + 255) / 256 : 148 * 32);
+            fir4_strip_kernel<<<sb, 256, 0, st>>>(p);
+        } else {
+            upfirdn2d_kernel<4, 4, 1, 1><<<blocks, 256, 0, st>>>(p);
+        }
     }
     else if (v4 && sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<4, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
     else if (v4 && sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<4, 4, 1, 2><<<blocks, 256, 0, st>>>(p);

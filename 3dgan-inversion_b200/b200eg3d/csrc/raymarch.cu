@@ -235,34 +235,32 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
         const bool d_pass = (D == D) && D >= dmin && D <= dmax;
         const float gD = (d_pass && p.d_depth) ? p.d_depth[ray] : 0.f;
         const float gW = p.d_wsum ? p.d_wsum[ray] : 0.f;
-        // through rgb*2-1: every lane keeps the ray's 32 channel gradients in registers
-        float gv[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(p.d_feat + ray * 32) + q);
-            gv[4 * q] = 2.f * v.x; gv[4 * q + 1] = 2.f * v.y; gv[4 * q + 2] = 2.f * v.z; gv[4 * q + 3] = 2.f * v.w;
-        }
+        // through rgb*2-1.  Eight lanes share one sample row (4 channels each): every warp instruction reads / writes four full
+        // 128-byte colour rows; d omega_rank(i) = sum_ch g[ch] * c_i[ch] is reduced over the 8 lanes with three shuffles.
+        const int sub = lane >> 3, j4 = lane & 7;
+        float4 g4 = __ldg(reinterpret_cast<const float4*>(p.d_feat + ray * 32) + j4);
+        g4.x *= 2.f; g4.y *= 2.f; g4.z *= 2.f; g4.w *= 2.f;
         float gsum = 0.f;                                        // through + 1 - wsum
         if (p.white_back) {
-#pragma unroll
-            for (int q = 0; q < 32; ++q) gsum += gv[q];
+            gsum = g4.x + g4.y + g4.z + g4.w;
+            gsum += __shfl_xor_sync(0xffffffffu, gsum, 1); gsum += __shfl_xor_sync(0xffffffffu, gsum, 2); gsum += __shfl_xor_sync(0xffffffffu, gsum, 4);
         }
-        // colours, lane == sample: d c_i = omega_rank(i) * g ; d omega_rank(i) = sum_ch g[ch] * c_i[ch]   (no cross-lane reduction)
-        for (int i = lane; i < S; i += 32) {
-            const int r = rk[i];
+#pragma unroll 4
+        for (int i0 = 0; i0 < S; i0 += 4) {
+            const int i = i0 + sub;
+            const bool v = i < S;
+            const int r = v ? rk[i] : 0;
             const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
             const bool co = i < p.S1;
             const long row = co ? (ray * p.S1 + i) * 32 : (ray * p.S2 + i - p.S1) * 32;
-            const float4* crow = reinterpret_cast<const float4*>((co ? p.rgb_c : p.rgb_f) + row);
-            float4* drow = reinterpret_cast<float4*>((co ? p.d_rgb_c : p.d_rgb_f) + row);
             float t = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 c = __ldg(crow + q);
-                t = fmaf(gv[4 * q], c.x, t); t = fmaf(gv[4 * q + 1], c.y, t); t = fmaf(gv[4 * q + 2], c.z, t); t = fmaf(gv[4 * q + 3], c.w, t);
-                drow[q] = make_float4(om * gv[4 * q], om * gv[4 * q + 1], om * gv[4 * q + 2], om * gv[4 * q + 3]);
+            if (v) {
+                const float4 c = __ldg(reinterpret_cast<const float4*>((co ? p.rgb_c : p.rgb_f) + row) + j4);
+                t = g4.x * c.x + g4.y * c.y + g4.z * c.z + g4.w * c.w;
+                reinterpret_cast<float4*>((co ? p.d_rgb_c : p.d_rgb_f) + row)[j4] = make_float4(om * g4.x, om * g4.y, om * g4.z, om * g4.w);
             }
-            dom[r] = t;
+            t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+            if (v && j4 == 0) dom[r] = t;
         }
         __syncwarp();
         // d w_k, stored in dsb[]
