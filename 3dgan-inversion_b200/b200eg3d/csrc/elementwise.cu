@@ -414,8 +414,13 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
 #pragma unroll
         for (int j = 0; j < V; ++j) out[j] = acc[j] * p.gain;
         if (p.add) {
+            if (V == 4) {
+                const float4 ad = __ldg(reinterpret_cast<const float4*>(p.add + o));
+                out[0] += ad.x; out[1 % V] += ad.y; out[2 % V] += ad.z; out[3 % V] += ad.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < V; ++j) out[j] += p.add[o + j];
+                for (int j = 0; j < V; ++j) out[j] += p.add[o + j];
+            }
         }
         if (p.act) {
             float nz = 0.f;

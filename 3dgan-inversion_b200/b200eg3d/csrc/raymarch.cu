@@ -187,6 +187,12 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
         float ws = 0.f, dn = 0.f;
         for (int k = lane; k < S - 1; k += 32) { ws += w[k]; dn += w[k] * 0.5f * (ts[k] + ts[k + 1]); }
         ws = warp_sum(ws); dn = warp_sum(dn);
+        // omega_i = (w[rank(i) - 1] + w[rank(i)]) / 2 per ORIGINAL sample, computed once (lane-parallel) into traw[] (free now)
+        for (int i = lane; i < S; i += 32) {
+            const int r = rk[i];
+            traw[i] = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+        }
+        __syncwarp();
         float acc = 0.f;
         for (int i0 = 0; i0 < S; i0 += 16) {          // 16 colour rows (128 B each, lane = channel) in flight per warp
             float c[16];
@@ -196,14 +202,8 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
                 c[j] = i >= S ? 0.f : (i < p.S1 ? __ldg(p.rgb_c + (ray * p.S1 + i) * 32 + lane) : __ldg(p.rgb_f + (ray * p.S2 + i - p.S1) * 32 + lane));
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = i0 + j;
-                if (i < S) {
-                    const int r = rk[i];
-                    const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
-                    acc = fmaf(om, c[j], acc);
-                }
-            }
+            for (int j = 0; j < 16; ++j)
+                if (i0 + j < S) acc = fmaf(traw[i0 + j], c[j], acc);
         }
         if (p.white_back) acc += 1.f - ws;
         p.feat[ray * 32 + lane] = acc * 2.f - 1.f;
