@@ -198,7 +198,7 @@ class SynthesisBlock(torch.nn.Module):
         return specs
 
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, x_split=None, return_split=False,
-                bank=None, bank_base=0, **layer_kwargs):
+                bank=None, bank_base=0, side=None, **layer_kwargs):
         """x_split / return_split carry the split-bf16 copies of the activations between consecutive blocks;
         bank / bank_base: pre-computed styles + modulated weights (ops.WeightBank) and this block's first entry."""
         w_iter = iter(ws.unbind(dim=1))
@@ -210,7 +210,18 @@ class SynthesisBlock(torch.nn.Module):
             x, sp = self.conv0(x, next(w_iter), x_split=x_split, bank=bank, lidx=li, **layer_kwargs)
             li += 1
         x, sp = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, **layer_kwargs)
-        img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
+        if side is None:
+            img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
+        else:
+            # ToRGB + skip upsample on the second stream: they depend on this block's x only, the next block's convolutions
+            # do not depend on them.  Tensors that cross streams are registered with the allocator (record_stream).
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
+            for t in (x,) + (tuple(sp) if sp is not None else ()):
+                if t is not None:
+                    t.record_stream(side)
         if return_split:
             return x, img, sp
         return x, img
@@ -256,9 +267,18 @@ class SynthesisNetwork(torch.nn.Module):
                 w_idx += block.num_conv
             bank = ops.make_bank(ws, specs)
         x = img = sp = None
+        side = ops.side_stream(ws.device) if (ops.CONFIG['overlap'] and bank is not None and ws.is_cuda) else None
+        if side is not None:
+            bank.side = side
+            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool]:
+                if t is not None:
+                    t.record_stream(side)
         for i, (res, cur_ws) in enumerate(zip(self.block_resolutions, block_ws)):
             x, img, sp = getattr(self, f'b{res}')(x, img, cur_ws, x_split=sp, return_split=True, bank=bank, bank_base=bases[i],
-                                                  **block_kwargs)
+                                                  side=side, **block_kwargs)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            img.record_stream(torch.cuda.current_stream())
         return img
 
     def forward(self, ws, c=None, **block_kwargs):
@@ -310,8 +330,18 @@ class SuperresolutionHybrid8X(torch.nn.Module):
             base1 = len(specs)
             specs += self.block1.bank_specs(0)
             bank = ops.make_bank(ws.contiguous(), specs)
-        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, bank=bank, bank_base=0, **block_kwargs)
-        x, rgb = self.block1(x, rgb, ws, x_split=sp, bank=bank, bank_base=base1, **block_kwargs)
+        side = ops.side_stream(ws.device) if (ops.CONFIG['overlap'] and bank is not None and ws.is_cuda) else None
+        if side is not None:
+            bank.side = side
+            side.wait_stream(torch.cuda.current_stream())           # rgb (skip input) and the bank were produced on the main stream
+            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool, rgb]:
+                if t is not None:
+                    t.record_stream(side)
+        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, bank=bank, bank_base=0, side=side, **block_kwargs)
+        x, rgb = self.block1(x, rgb, ws, x_split=sp, bank=bank, bank_base=base1, side=side, **block_kwargs)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+            rgb.record_stream(torch.cuda.current_stream())
         return rgb
 
     def forward(self, rgb, x, ws, **block_kwargs):

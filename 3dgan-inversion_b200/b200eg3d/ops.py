@@ -30,7 +30,9 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           'fwd_passes': int(os.environ.get('B200EG3D_FWD_PASSES', '3')),
           'bank': os.environ.get('B200EG3D_BANK', '1') != '0',       # batch styles + weight prep of all layers into one launch
           'dgrad_passes': int(os.environ.get('B200EG3D_DGRAD_PASSES', '3')),
-          'wgrad_passes': int(os.environ.get('B200EG3D_WGRAD_PASSES', '1'))}
+          'wgrad_passes': int(os.environ.get('B200EG3D_WGRAD_PASSES', '1')),
+          # run the ToRGB / skip-upsample chain on a second stream, concurrently with the next block's convolutions
+          'overlap': os.environ.get('B200EG3D_OVERLAP', '1') != '0'}
 
 
 def _f32c(t):
@@ -271,6 +273,7 @@ class WeightBank:
         self.token = None
         self.zpool = None          # one zero-filled buffer for the small backward accumulators (d bias, d noise_strength) of all layers
         self.zoff = []
+        self.side = None           # second stream some layers ran on (CONFIG['overlap']); the bank's backward joins it
 
     def zeros(self, lidx, cout):
         """(d bias [cout], d strength []) views into the pool: one fill per network and pass instead of two per layer."""
@@ -331,6 +334,8 @@ class _Bank(torch.autograd.Function):
         dev = ws.device
         need = ctx.needs_input_grad
         specs = bank.specs
+        if bank.side is not None:                   # d wmod of the side-stream layers carries no autograd edge: join explicitly
+            torch.cuda.current_stream().wait_stream(bank.side)
         d_ws = torch.zeros_like(ws) if need[0] else None
         total_cin = sum(sp.cin for sp in specs)
         ds_all = torch.zeros([total_cin * n], device=dev, dtype=torch.float32)
@@ -353,6 +358,17 @@ class _Bank(torch.autograd.Function):
         call('b200_bank_styles_bwd', ctypes.addressof(arr), len(specs), ptr(ws), ptr(d_ws), n, num_ws, w_dim, stream())
         bank.dwmod = [None] * len(specs)
         return (d_ws, None, *grads)
+
+
+_SIDE = {}
+
+
+def side_stream(device):
+    """The per-device second stream of CONFIG['overlap'] (created on first use)."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
 
 
 def make_bank(ws, specs):

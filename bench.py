@@ -194,6 +194,7 @@ def run_b200(args):
     launches = _lib.LAUNCHES if args.eager else calls_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(args.steps, e2e=True)
+    final_loss = float(step(resident).item())        # sanity value: the optimisation must behave the same in every launch mode
 
     # per-kernel device time of the same step, instrumented with CUDA events on the launching stream (separate steps)
     roof = roof_conv = per_call = None
@@ -258,7 +259,7 @@ def run_b200(args):
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
                     'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_conv_stack': roof_conv if rank == 0 else None,
-            'per_call_ms': per_call if rank == 0 else None, 'cpu_baseline': cpu,
+            'per_call_ms': per_call if rank == 0 else None, 'cpu_baseline': cpu, 'final_loss': round(final_loss, 6),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
