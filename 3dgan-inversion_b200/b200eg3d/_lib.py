@@ -41,6 +41,8 @@ SIGNATURES = {
     'b200_noise_pyramid_fwd': [_I, _P, _P, _P, _P, _P, _P, _P],
     'b200_noise_pyramid_bwd': [_I, _P, _P, _P, _P, _P, _P, _P, _P],
     'b200_noise_normalize': [_I, _P, _P, _P, _P],
+    'b200_ray_sampler_fwd': [_P, _P, _I, _I, _P, _P, _P],
+    'b200_ray_sampler_bwd': [_P, _P, _I, _I, _P, _P, _P, _P],
     'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],
     'b200_depth_minmax': [_P, _L, _P, _P],
     'b200_ray_importance': [_P, _P, _P, _P, _L, _I, _I, _P],

@@ -297,6 +297,60 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
         __syncwarp();
     }
 }
+// ---------------------------------------------------------------------------------------------------------------------
+// RaySampler.forward (training/volumetric_rendering/ray_sampler.py:24-73): pixel-centre uv, unprojection through the
+// intrinsics, rotation into world space, normalisation.  One thread per ray; the backward reduces the 12 cam2world
+// gradients per sample (w-projection optimises the pose through them).
+template <bool BWD>
+__global__ void ray_sampler_kernel(const float* __restrict__ c2w, const float* __restrict__ K, int R, float* __restrict__ ray_o,
+                                   float* __restrict__ ray_d, const float* __restrict__ d_o, const float* __restrict__ d_d,
+                                   float* __restrict__ d_c2w) {
+    __shared__ float red[32];
+    const int b = blockIdx.y, M = R * R;
+    const float* E = c2w + b * 16;
+    const float* Kb = K + b * 9;
+    const float fx = Kb[0], sk = Kb[1], cx = Kb[2], fy = Kb[4], cy = Kb[5];
+    float acc[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+        const float xc = (float)(i % R) * (1.f / R) + 0.5f / R, yc = (float)(i / R) * (1.f / R) + 0.5f / R;
+        const float xl = (xc - cx + cy * sk / fy - sk * yc / fy) / fx, yl = (yc - cy) / fy;
+        float q[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) q[j] = (E[4 * j] * xl + E[4 * j + 1] * yl + E[4 * j + 2] + E[4 * j + 3]) - E[4 * j + 3];
+        const float qn = fmaxf(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), 1e-12f);
+        const long o = ((long)b * M + i) * 3;
+        if (!BWD) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { ray_o[o + j] = E[4 * j + 3]; ray_d[o + j] = q[j] / qn; }
+        } else {
+            float dd[3] = {0.f, 0.f, 0.f}, dot = 0.f, dir[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { dir[j] = q[j] / qn; if (d_d) dd[j] = d_d[o + j]; dot += dir[j] * dd[j]; }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const float dq = (dd[j] - dir[j] * dot) / qn;
+                acc[4 * j] += dq * xl; acc[4 * j + 1] += dq * yl; acc[4 * j + 2] += dq;
+                if (d_o) acc[4 * j + 3] += d_o[o + j];
+            }
+        }
+    }
+    if (BWD) {
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            float v = warp_sum(acc[j]);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+                v = warp_sum(v);
+                if (threadIdx.x == 0) atomicAdd(d_c2w + b * 16 + j, v);
+            }
+        }
+    }
+}
 }  // namespace
 
 B200_API int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta,
@@ -360,6 +414,25 @@ B200_API int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, cons
     const int SP = (S1 + S2 + 3) & ~3;
     const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
     ray_composite_bwd_kernel<<<blocks, 128, 4 * 9 * SP * sizeof(float), (cudaStream_t)stream>>>(p, SP);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// RaySampler.forward: cam2world [n][16], intrinsics [n][9] -> ray_o, ray_d [n][R*R][3] (ray m = i*R + j at pixel centre ((j+.5)/R, (i+.5)/R)).
+B200_API int b200_ray_sampler_fwd(const float* cam2world, const float* intrinsics, int n, int R, float* ray_o, float* ray_d, void* stream) {
+    B200_REQUIRE(cam2world && intrinsics && ray_o && ray_d && n > 0 && R > 0, "ray_sampler_fwd: null pointer or bad shape");
+    const int bx = (R * R + 255) / 256 < 148 ? (R * R + 255) / 256 : 148;
+    ray_sampler_kernel<false><<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(cam2world, intrinsics, R, ray_o, ray_d, nullptr, nullptr, nullptr);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+// d_cam2world [n][16] is ACCUMULATED into (zero it first; row 3 stays zero); d_ray_o / d_ray_d may each be NULL.
+B200_API int b200_ray_sampler_bwd(const float* cam2world, const float* intrinsics, int n, int R, const float* d_ray_o,
+                                  const float* d_ray_d, float* d_cam2world, void* stream) {
+    B200_REQUIRE(cam2world && intrinsics && d_cam2world && n > 0 && R > 0, "ray_sampler_bwd: null pointer or bad shape");
+    const int bx = (R * R + 255) / 256 < 148 ? (R * R + 255) / 256 : 148;
+    ray_sampler_kernel<true><<<dim3(bx, n), 256, 0, (cudaStream_t)stream>>>(cam2world, intrinsics, R, nullptr, nullptr, d_ray_o, d_ray_d, d_cam2world);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -372,6 +372,12 @@ class RaySampler(torch.nn.Module):
     """training/volumetric_rendering/ray_sampler.py:24-73 (device follows the inputs; the reference hard-codes .cuda())."""
 
     def forward(self, cam2world_matrix, intrinsics, resolution, need_cam_space=False):
+        if cam2world_matrix.is_cuda and not need_cam_space and not intrinsics.requires_grad:
+            return ops.ray_sampler(cam2world_matrix, intrinsics, resolution)      # one kernel instead of ~15 small launches
+        return self.forward_torch(cam2world_matrix, intrinsics, resolution, need_cam_space)
+
+    def forward_torch(self, cam2world_matrix, intrinsics, resolution, need_cam_space=False):
+        """The same statements as device-agnostic torch ops (camera-space rays, intrinsics that require a gradient)."""
         N, M = cam2world_matrix.shape[0], resolution ** 2
         dev = cam2world_matrix.device
         cam_locs_world = cam2world_matrix[:, :3, 3]

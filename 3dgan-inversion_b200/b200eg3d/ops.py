@@ -822,6 +822,34 @@ def render(planes_nhwc, decoder, ray_o, ray_d, box_warp, t_base, delta, u_strat,
                          white_back, density_noise)
 
 
+class _RaySampler(torch.autograd.Function):
+    """RaySampler.forward (ray_sampler.py:24-73) as one kernel; gradient to cam2world (the w-projection optimises the pose)."""
+
+    @staticmethod
+    def forward(ctx, cam2world, intrinsics, resolution):
+        c2w = _f32c(cam2world).reshape(-1, 16)
+        K = _f32c(intrinsics).reshape(-1, 9)
+        n, M = c2w.shape[0], resolution * resolution
+        ray_o = torch.empty([n, M, 3], device=c2w.device, dtype=torch.float32)
+        ray_d = torch.empty_like(ray_o)
+        call('b200_ray_sampler_fwd', ptr(c2w), ptr(K), n, resolution, ptr(ray_o), ptr(ray_d), stream())
+        ctx.res, ctx.shape = resolution, cam2world.shape
+        ctx.save_for_backward(c2w, K)
+        return ray_o, ray_d
+
+    @staticmethod
+    def backward(ctx, d_o, d_d):
+        c2w, K = ctx.saved_tensors
+        g = torch.zeros_like(c2w)
+        call('b200_ray_sampler_bwd', ptr(c2w), ptr(K), c2w.shape[0], ctx.res, ptr(_f32c(d_o) if d_o is not None else None),
+             ptr(_f32c(d_d) if d_d is not None else None), ptr(g), stream())
+        return g.reshape(ctx.shape), None, None
+
+
+def ray_sampler(cam2world, intrinsics, resolution):
+    return _RaySampler.apply(cam2world, intrinsics, resolution)
+
+
 def library_info():
     lib = _lib.load()
     return {'path': _lib.LIB_PATH, 'version': lib.b200_version()}

@@ -138,6 +138,11 @@ int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const floa
                           float* dW1, float* db1, float* dW2, float* db2, void* workspace, long workspace_bytes, void* stream);
 
 /* ---- per-ray kernels (renderer.py:143-308 ImportanceRenderer, ray_marcher.py:25-57 MipRayMarcher2) ---------------- */
+/* RaySampler.forward (ray_sampler.py:24-73): cam2world [n][16], intrinsics [n][9] -> ray_o, ray_d [n][R*R][3]; the backward
+ * ACCUMULATES d cam2world [n][16] (zero it first) from d ray_o / d ray_d (either may be NULL). */
+int b200_ray_sampler_fwd(const float* cam2world, const float* intrinsics, int n, int R, float* ray_o, float* ray_d, void* stream);
+int b200_ray_sampler_bwd(const float* cam2world, const float* intrinsics, int n, int R, const float* d_ray_o, const float* d_ray_d,
+                         float* d_cam2world, void* stream);
 /* t[ray][s] = t_base[s] + u[ray][s] * delta          (renderer.py:224-247 sample_stratified, numeric ray_start/ray_end) */
 int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta, void* stream);
 /* global min / max of depths for the clamp of ray_marcher.py:50; minmax: 2 x uint32 (order-preserving), initialised {~0u, 0} */

@@ -370,3 +370,25 @@ def test_ray_composite_merge_orders(b2, mode, S1, S2):
     assert relerr(d_rc, rr.grad[0, :, :S1]) < 1e-4 and relerr(d_sc, sr.grad[0, :, :S1, 0]) < 1e-4
     if S2:
         assert relerr(d_rf, rr.grad[0, :, S1:]) < 1e-4 and relerr(d_sf, sr.grad[0, :, S1:, 0]) < 1e-4
+
+
+@pytest.mark.parametrize('n,R', [(1, 128), (2, 16), (3, 5)])
+def test_ray_sampler_kernel(b2, n, R):
+    """RaySampler.forward kernel + its cam2world gradient against the oracle (ray_sampler.py:24-73)."""
+    import synth_params as sp
+    c = torch.cat([sp.camera(0.3 - 0.2 * i, -0.2 + 0.15 * i) for i in range(n)], 0)
+    c[:, 17] = 0.02                                                   # non-zero skew exercises the full unprojection
+    g = gen(R)
+    u_o, u_d = torch.randn(n, R * R, 3, generator=g), torch.randn(n, R * R, 3, generator=g)
+    cr = c[:, :16].reshape(n, 4, 4).clone().requires_grad_(True)
+    o_ref, d_ref = oracle.ray_sampler(cr, c[:, 16:].reshape(n, 3, 3), R)
+    ((o_ref * u_o).sum() + (d_ref * u_d).sum()).backward()
+    cd = c[:, :16].reshape(n, 4, 4).clone().cuda().requires_grad_(True)
+    o, d = b2.RaySampler()(cd, c[:, 16:].reshape(n, 3, 3).cuda(), R)
+    ((o * u_o.cuda()).sum() + (d * u_d.cuda()).sum()).backward()
+    assert maxdiff(o, o_ref) == 0.0 and maxdiff(d, d_ref) < 1e-6
+    assert relerr(cd.grad[:, :3], cr.grad[:, :3]) < 1e-4 and float(cd.grad[:, 3].abs().max()) == 0.0
+    o2, d2 = b2.RaySampler().forward_torch(cd.detach(), c[:, 16:].reshape(n, 3, 3).cuda(), R)
+    assert maxdiff(o2, o) == 0.0 and maxdiff(d2, d) < 1e-6
+    _, dcam, uv = b2.RaySampler()(cd.detach(), c[:, 16:].reshape(n, 3, 3).cuda(), R, need_cam_space=True)
+    assert dcam.shape == (n, R * R, 3) and uv.shape == (n, R * R, 2)
