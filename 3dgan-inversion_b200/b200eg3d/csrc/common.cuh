@@ -29,6 +29,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// (a0, a1) += g * (v0, v1) as one sm_100 packed-FP32 instruction (fma.rn.f32x2 -> FFMA2)
+__device__ __forceinline__ void fma2(float& a0, float& a1, float g, float v0, float v1) {
+    unsigned long long acc, gg, vv;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(acc) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(gg) : "f"(g));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v0), "f"(v1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(gg), "l"(vv));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(acc));
+}
+
 __device__ __forceinline__ float softplus_f(float x) {          // torch softplus, beta=1, threshold=20
     return x > 20.f ? x : log1pf(expf(x));
 }

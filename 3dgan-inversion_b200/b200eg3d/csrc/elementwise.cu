@@ -483,11 +483,11 @@ __global__ void __launch_bounds__(256) fir4_strip_kernel(UpfirdnParams p) {
 #pragma unroll
                 for (int xx = 0; xx < 4; ++xx)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
+                    for (int q = 0; q < 4; ++q) {          // packed FP32 FMA (FFMA2): two channels per instruction
                         const float g = fr[a * 4 + q];
                         const float4 v = row[xx + q];
-                        acc[yy][xx].x = fmaf(g, v.x, acc[yy][xx].x); acc[yy][xx].y = fmaf(g, v.y, acc[yy][xx].y);
-                        acc[yy][xx].z = fmaf(g, v.z, acc[yy][xx].z); acc[yy][xx].w = fmaf(g, v.w, acc[yy][xx].w);
+                        fma2(acc[yy][xx].x, acc[yy][xx].y, g, v.x, v.y);
+                        fma2(acc[yy][xx].z, acc[yy][xx].w, g, v.z, v.w);
                     }
             }
         }

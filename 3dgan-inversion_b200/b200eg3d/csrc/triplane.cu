@@ -118,8 +118,8 @@ __device__ __forceinline__ void stage_setup(float* ss, int lane, float cx, float
     for (int j = 0; j < SP; j += 4) *reinterpret_cast<float4*>(&ss[lane * SP + j]) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
 }
 
-__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
-    a.x = fmaf(w, v.x, a.x); a.y = fmaf(w, v.y, a.y); a.z = fmaf(w, v.z, a.z); a.w = fmaf(w, v.w, a.w);
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {          // two packed FP32 FMAs (FFMA2)
+    fma2(a.x, a.y, w, v.x, v.y); fma2(a.z, a.w, w, v.z, v.w);
 }
 
 // Gather the 32-channel mean feature of the warp's 32 points into sf[point*STRIDE + channel].  Eight lanes share a point
