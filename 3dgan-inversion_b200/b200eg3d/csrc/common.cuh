@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <utility>
 
 #define B200_API extern "C" __attribute__((visibility("default")))
 
@@ -22,6 +24,33 @@ static inline int b200_fail(const char* file, int line, const char* msg) {
     if (e_ != cudaSuccess) return b200_fail(__FILE__, __LINE__, cudaGetErrorString(e_)); } while (0)
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may be
+// scheduled while its predecessor in the stream is still draining; it must execute pdl_wait() (griddepcontrol.wait: all
+// prerequisite grids complete and their memory visible) before touching global memory.  The step is ~250 dependent launches,
+// most of them short: overlapping launch latency / prologue with the previous kernel's tail is worth several percent.
+// B200EG3D_PDL=0 disables the attribute (the wait then returns immediately).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Let the next PDL kernel of the stream be scheduled as soon as every CTA of this one has started (it still blocks in its
+// own pdl_wait() until this grid has completed): its CTAs then sit ready on the SMs when our last CTA retires.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool b200_pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("B200EG3D_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on == 1;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

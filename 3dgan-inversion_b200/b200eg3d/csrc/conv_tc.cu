@@ -60,6 +60,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // one drain) and the accumulator is double-buffered in TMEM, so the epilogue of item i overlaps the main loop of item i+1.
 template <bool B_MN>
 __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_constant__ TcPixParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
+    pdl_wait();                       // barriers, descriptors and TMEM are set up while the previous kernel drains
 
     // work item -> (class, tile, k-slice, N tile, sample); every role decodes the same list
     struct Item { int cls, x0, y0, n0, b, it0, nk; };
@@ -239,6 +241,7 @@ struct TcWgradParams {
 };
 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
+    pdl_wait();
 
     // Stage layout.  tg == 1 (any npass): A_hi | A_lo | B_hi | B_lo as in the pixel-GEMM kernel.
     // tg  > 1 (single pass, hi only): shared tile first, then the tg shifted tiles.
@@ -461,7 +465,7 @@ int launch_pix(TcPixParams& p, int batch, cudaStream_t st) {
     static int sms = 0;
     if (!sms) { int dev = 0; B200_CUDA(cudaGetDevice(&dev)); B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
     const int grid = p.nwork < sms ? p.nwork : sms;
-    conv_tc_pix_kernel<B_MN><<<grid, 192, SMEM_BYTES, st>>>(p);
+    B200_CUDA(launch_pdl(conv_tc_pix_kernel<B_MN>, dim3(grid), dim3(192), SMEM_BYTES, st, p));
     B200_CHECK_LAUNCH();
     return 0;
 }
@@ -614,7 +618,7 @@ B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
         attr = true;
     }
     dim3 grid(mt, nt, n * (taps / p.tg) * ksplit);
-    conv_tc_wgrad_kernel<<<grid, 192, SMEM_BYTES, st>>>(p);
+    B200_CUDA(launch_pdl(conv_tc_wgrad_kernel, grid, dim3(192), SMEM_BYTES, st, p));
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -62,6 +62,8 @@ __global__ void bias_act_kernel(const float* __restrict__ x, const float* __rest
 // 4 elements per thread, 32-bit index math.
 __global__ void bias_act_nhwc4_kernel(const float4* __restrict__ x, const float* __restrict__ b, const float4* __restrict__ yref,
                                       float4* __restrict__ y, int grad, int n4, int c4, int lrelu, float alpha, float gain, float clamp) {
+    pdl_trigger();
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
         const float4 xv = x[i];
         float v[4] = {xv.x, xv.y, xv.z, xv.w};
@@ -98,9 +100,8 @@ B200_API int b200_bias_act(const float* x, const float* b, const float* xref, co
         ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && (!yref || (uintptr_t)yref % 16 == 0) && (!b || (uintptr_t)b % 16 == 0)) {
         const int n4 = (int)(sizeX / 4);
         const int blocks4 = (n4 + 255) / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16;
-        bias_act_nhwc4_kernel<<<blocks4, 256, 0, (cudaStream_t)stream>>>((const float4*)x, grad == 0 ? b : nullptr, (const float4*)yref,
-                                                                         (float4*)y, grad, n4, b ? sizeB / 4 : 1, act == 3, alpha, gain, clamp);
-        B200_CHECK_LAUNCH();
+        B200_CUDA(launch_pdl(bias_act_nhwc4_kernel, dim3(blocks4), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, grad == 0 ? b : (const float*)nullptr,
+                             (const float4*)yref, (float4*)y, grad, n4, (int)(b ? sizeB / 4 : 1), (int)(act == 3), alpha, gain, clamp));
         return 0;
     }
     const int blocks = (int)((sizeX + 255) / 256 < 148 * 16 ? (sizeX + 255) / 256 : 148 * 16);
@@ -119,6 +120,8 @@ __global__ void layer_act_fwd_kernel(const float4* __restrict__ y, float4* __res
                                      uint2* __restrict__ zlo, const float* __restrict__ bias,
                                      const float* __restrict__ noise, const float* __restrict__ strength, long noise_bs,
                                      long total4_, int hw_, int c4_, int lrelu, float alpha, float gain, float clamp) {
+    pdl_trigger();
+    pdl_wait();
     const float str = (noise && strength) ? *strength : 0.f;
     const idx_t total4 = (idx_t)total4_, c4 = (idx_t)c4_, hw = (idx_t)hw_;
     for (idx_t i = (idx_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (idx_t)gridDim.x * blockDim.x) {
@@ -171,11 +174,11 @@ B200_API int b200_layer_act_fwd(const float* y, float* z, void* z_hi, void* z_lo
         const long t4 = total / 4;
         const int blocks = (int)((t4 + 255) / 256 < 148 * 16 ? (t4 + 255) / 256 : 148 * 16);
         if (t4 < (1L << 31))
-            layer_act_fwd_kernel<unsigned><<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo, bias, noise,
-                                                                   strength, noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp);
+            B200_CUDA(launch_pdl(layer_act_fwd_kernel<unsigned>, dim3(blocks), dim3(256), 0, st, (const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo,
+                                 bias, noise, strength, noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp));
         else
-            layer_act_fwd_kernel<long><<<blocks, 256, 0, st>>>((const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo, bias, noise,
-                                                               strength, noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp);
+            B200_CUDA(launch_pdl(layer_act_fwd_kernel<long>, dim3(blocks), dim3(256), 0, st, (const float4*)y, (float4*)z, (uint2*)z_hi, (uint2*)z_lo,
+                                 bias, noise, strength, noise_bs, t4, hw, c / 4, lrelu, alpha, gain, clamp));
     } else {
         const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
         layer_act_fwd_kernel_s<<<blocks, 256, 0, st>>>(y, z, bias, noise, strength, noise_bs, total, hw, c, lrelu, alpha,
@@ -266,6 +269,8 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
     __shared__ float s_col[512];
     __shared__ float s_row[256];
     __shared__ float s_str;
+    pdl_trigger();
+    pdl_wait();
     const int ppb = blockDim.x / c4;                 // pixels per block iteration
     const int sub = threadIdx.x / c4, cc = threadIdx.x % c4;
     const bool active = sub < ppb;
@@ -328,10 +333,8 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, void
         const int c4 = c / 4, ppb = 256 / c4;
         const long nb = (npix + ppb - 1) / ppb;
         const int blocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
-        layer_act_bwd_vec_kernel<<<blocks, 256, 0, st>>>((const float4*)dz, (const float4*)z, (float4*)dy, (uint2*)dy_hi, (uint2*)dy_lo,
-                                                         dbias, noise, strength, noise_bs, dstrength, dnoise, npix, hw, c4, lrelu,
-                                                         alpha, gain, clamp);
-        B200_CHECK_LAUNCH();
+        B200_CUDA(launch_pdl(layer_act_bwd_vec_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)dz, (const float4*)z, (float4*)dy, (uint2*)dy_hi,
+                             (uint2*)dy_lo, dbias, noise, strength, noise_bs, dstrength, dnoise, npix, hw, c4, lrelu, alpha, gain, clamp));
         return 0;
     }
     B200_REQUIRE(!dy_hi, "layer_act_bwd: bf16 outputs need a channel count that is a multiple of 4");
@@ -363,6 +366,8 @@ struct UpfirdnParams {
 // F == 0: generic run-time filter size and factors.
 template <int V, int F, int UP, int DOWN>
 __global__ void upfirdn2d_kernel(UpfirdnParams p) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned cv = p.c / V;
     const unsigned total = (unsigned)((long)p.n * p.oh * p.ow * cv);      // launch_upfirdn() guarantees < 2^31 outputs
     const int fh = F > 0 ? F : p.fh, fw = F > 0 ? F : p.fw;
@@ -446,6 +451,8 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
 // Register-blocked 4x4 FIR at unit rate (the filter after every up=2 convolution and its adjoint): one thread produces a
 // 2 x 4 patch of outputs for 4 channels from a 5 x 7 input window, i.e. 4.4 vector loads per output instead of 16.
 __global__ void __launch_bounds__(256) fir4_strip_kernel(UpfirdnParams p) {
+    pdl_trigger();
+    pdl_wait();
     const unsigned cv = p.c >> 2;
     const unsigned sxn = (p.ow + 3) >> 2, syn = (p.oh + 1) >> 1;
     const unsigned total = (unsigned)p.n * syn * sxn * cv;
@@ -546,18 +553,18 @@ static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t s
 #endif
         if (strips >= B200_FIR_STRIP_MIN) {
             const int sb = (int)((strips + 255) / 256 < 148 * 32 ? (strips + 255) / 256 : 148 * 32);
-            fir4_strip_kernel<<<sb, 256, 0, st>>>(p);
+            B200_CUDA(launch_pdl(fir4_strip_kernel, dim3(sb), dim3(256), 0, st, p));
         } else {
-            upfirdn2d_kernel<4, 4, 1, 1><<<blocks, 256, 0, st>>>(p);
+            B200_CUDA(launch_pdl(upfirdn2d_kernel<4, 4, 1, 1>, dim3(blocks), dim3(256), 0, st, p));
         }
     }
-    else if (v4 && sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<4, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
-    else if (v4 && sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<4, 4, 1, 2><<<blocks, 256, 0, st>>>(p);
-    else if (v4) upfirdn2d_kernel<4, 0, 1, 1><<<blocks, 256, 0, st>>>(p);
-    else if (sq4 && p.upx == 1 && p.downx == 1) upfirdn2d_kernel<1, 4, 1, 1><<<blocks, 256, 0, st>>>(p);
-    else if (sq4 && p.upx == 2 && p.downx == 1) upfirdn2d_kernel<1, 4, 2, 1><<<blocks, 256, 0, st>>>(p);
-    else if (sq4 && p.upx == 1 && p.downx == 2) upfirdn2d_kernel<1, 4, 1, 2><<<blocks, 256, 0, st>>>(p);
-    else upfirdn2d_kernel<1, 0, 1, 1><<<blocks, 256, 0, st>>>(p);
+    else if (v4 && sq4 && p.upx == 2 && p.downx == 1) B200_CUDA(launch_pdl(upfirdn2d_kernel<4, 4, 2, 1>, dim3(blocks), dim3(256), 0, st, p));
+    else if (v4 && sq4 && p.upx == 1 && p.downx == 2) B200_CUDA(launch_pdl(upfirdn2d_kernel<4, 4, 1, 2>, dim3(blocks), dim3(256), 0, st, p));
+    else if (v4) B200_CUDA(launch_pdl(upfirdn2d_kernel<4, 0, 1, 1>, dim3(blocks), dim3(256), 0, st, p));
+    else if (sq4 && p.upx == 1 && p.downx == 1) B200_CUDA(launch_pdl(upfirdn2d_kernel<1, 4, 1, 1>, dim3(blocks), dim3(256), 0, st, p));
+    else if (sq4 && p.upx == 2 && p.downx == 1) B200_CUDA(launch_pdl(upfirdn2d_kernel<1, 4, 2, 1>, dim3(blocks), dim3(256), 0, st, p));
+    else if (sq4 && p.upx == 1 && p.downx == 2) B200_CUDA(launch_pdl(upfirdn2d_kernel<1, 4, 1, 2>, dim3(blocks), dim3(256), 0, st, p));
+    else B200_CUDA(launch_pdl(upfirdn2d_kernel<1, 0, 1, 1>, dim3(blocks), dim3(256), 0, st, p));
     B200_CHECK_LAUNCH();
     return 0;
 }
