@@ -112,6 +112,9 @@ def call(name, *args):
     lib = load()
     LAUNCHES += 1
     if PROFILE is not None:
+        # per-kernel timing leg of bench.py: drain the device first so that the events bracket this call's kernels only
+        # (no overlap with earlier asynchronous work, no second-stream branch running beside it)
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib, name)(*args)

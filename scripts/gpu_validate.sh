@@ -6,3 +6,4 @@ timeout 600 python bench.py > gpurun_out/bench_$1.log 2>&1
 tail -1 gpurun_out/bench_$1.log | cut -c1-400
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$1.csv python bench.py --steps 1 --warmup 3 --no-cpu --eager --ncu-step > gpurun_out/ncu_l_$1.log 2>&1
 ls -la gpurun_out | tail -4
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$1.log 2>&1; tail -2 gpurun_out/smoke_$1.log
