@@ -208,6 +208,14 @@ def run_b200(args):
         torch.cuda.synchronize()
         prof = {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in _lib.PROFILE.items()}
         _lib.PROFILE = None
+        try:
+            def one_step():
+                opt.zero_grad(set_to_none=True)
+                eager_step(*resident)
+            kt = cupti_kernel_times(one_step)
+        except Exception as e:                        # CUPTI unavailable: keep the event brackets only
+            kt = None
+            print(f'[bench] CUPTI kernel trace unavailable ({type(e).__name__}: {e}); conv-stack time from CUDA-event brackets', file=sys.stderr)
         pk, how = peaks()
         nprof = 2
         per_call = {k: round(v[0] / nprof, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
@@ -231,18 +239,27 @@ def run_b200(args):
                 'traffic': traffic.get('triplane_mlp_bwd_mma_kernel', {}).get('bytes'), 'peak_source': how,
                 'algorithmic_bytes_per_launch': bwd_bytes, 'launch_ms': round(bwd_launch_ms, 4), 'launches_per_step': bwd_n / nprof,
                 'launch_ms_eager_bracket': round(bwd_eager_ms, 4),
-                'share_of_kernel_time': round(bwd_ms / nprof / tot_ms, 3),
+                'share_of_kernel_time': round(bwd_launch_ms * (bwd_n / nprof) / (sum(v[0] for v in kt.values()) if kt else tot_ms), 3),
                 'note': 'HBM-bound only by the compulsory-byte definition: DRAM traffic equals the algorithmic bytes (no re-reads); '
                         'the kernel is limited by the L2 gather + vector-atomic scatter of 2 x 1.2 GB of texel lines (L2 35 %) and by instruction issue '
                         '(SM 35 %, 12 warps/SM); decoder weight gradients accumulate in tensor memory (tcgen05.mma) and add no DRAM traffic'}
         # (2) the conv stack (all tcgen05 / SIMT conv launches of the step) against the tensor roofline
         conv_ms = sum(prof[k][0] for k in prof if k.startswith('b200_conv_')) / nprof
         n_conv = sum(prof[k][1] for k in prof if k.startswith('b200_conv_')) / nprof
+        conv_bracket_ms, conv_timing = conv_ms, 'CUDA-event brackets around the C-ABI calls (include launch latency)'
+        kernel_ms = None
+        if kt:
+            is_conv = lambda k: k.startswith(('conv_tc_', 'conv_pix_kernel', 'conv_wgrad', 'conv_dgrad'))
+            conv_ms = sum(v[0] for k, v in kt.items() if is_conv(k))
+            tot_ms = sum(v[0] for v in kt.values())
+            conv_timing = 'CUPTI kernel trace of eager steps (kernel device time)'
+            kernel_ms = {k: round(v[0], 3) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][0])[:30]}
         achieved = conv_flops_per_step() / (conv_ms * 1e-3) / 1e12
         peak = pk['bf16_tflops_sustained']
         roof_conv = {'kernel': 'modulated-conv stack (b200_conv_fwd/dgrad/wgrad[_tc])', 'bound': 'tensor', 'achieved': round(achieved, 2),
                      'peak': peak, 'unit': 'TFLOP/s', 'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': how,
                      'launches_per_step': n_conv, 'ms_per_step_in_kernel': round(conv_ms, 3), 'share_of_kernel_time': round(conv_ms / tot_ms, 3),
+                     'timing': conv_timing, 'ms_per_step_event_brackets': round(conv_bracket_ms, 3),
                      'issued_tflops': round(achieved * 7 / 3, 1), 'issued_frac': round(achieved * 7 / 3 / peak, 4),
                      'note': 'algorithmic FLOPs (fwd+dgrad+wgrad = 428.3 GFLOP); forward and dgrad issue 3 MMAs per product (split-bf16 parity mode), '
                              'wgrad 1: the tensor pipe executes 7/3 of the algorithmic FLOPs (issued_*)'}
@@ -262,11 +279,31 @@ def run_b200(args):
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
                     'd2h_bytes_per_step': 4},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_conv_stack': roof_conv if rank == 0 else None,
-            'per_call_ms': per_call if rank == 0 else None, 'cpu_baseline': cpu, 'final_loss': round(final_loss, 6),
+            'kernel_ms': kernel_ms if rank == 0 else None, 'per_call_ms_event_brackets': per_call if rank == 0 else None, 'cpu_baseline': cpu, 'final_loss': round(final_loss, 6),
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def cupti_kernel_times(fn, nsteps=2):
+    """kernel name -> (ms per step, launches per step) from a CUPTI trace (torch.profiler) of `nsteps` eager steps.  Eager steps
+    are CPU-bound, so kernels never overlap and the traced durations are the kernels' own device times (the CUDA-event
+    brackets around the C-ABI calls additionally contain ~9 us of launch latency per call)."""
+    import collections
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        for _ in range(nsteps):
+            fn()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0.0, 0])
+    for e in prof.events():
+        if e.device_type != torch.autograd.DeviceType.CUDA:
+            continue
+        name = e.name.replace('(anonymous namespace)::', '').replace('void ', '').split('(')[0][:60]
+        agg[name][0] += (e.device_time if hasattr(e, 'device_time') else e.cuda_time) / 1e3
+        agg[name][1] += 1
+    return {k: (v[0] / nsteps, v[1] / nsteps) for k, v in agg.items()}
 
 
 def time_triplane_bwd(G, resident, dev, iters=10):
