@@ -125,11 +125,11 @@ __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {     
 // Gather the 32-channel mean feature of the warp's 32 points into sf[point*STRIDE + channel].  Eight lanes share a point
 // (4 channels each, one LDG.128 per texel), so one warp instruction fetches the same texel slot of FOUR points = four full
 // 128-byte lines; no cross-lane reduction is needed.
-template <int STRIDE>
+template <int STRIDE, int UNROLL = 2>
 __device__ __forceinline__ void gather_features(const float* __restrict__ pl, const float* ss, float* sf, int lane) {
     const int pt = lane >> 3, j4 = (lane & 7) * 4;
     const float* pc = pl + j4;
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int q0 = 0; q0 < 32; q0 += 4) {
         const float* s = ss + (q0 + pt) * SP;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) triplane_mlp_fwd_mma_kernel(
 #ifndef B200_BM_WARPS
 #define B200_BM_WARPS 12
 #endif
+#ifndef B200_BWD_GATHER_UNROLL
+#define B200_BWD_GATHER_UNROLL 2      // texel loads in flight per lane = 12 x this
+#endif
 constexpr int BM_WARPS_WG = B200_BM_WARPS, BM_WARPS_NOWG = 16;
 constexpr int BM_W = HID * SF + OUTP * SW2 + HID + OUTP + HID + OUTP;       // W1 [64][36], W2 [40][72], b1, b2, db1, db2
 constexpr int BM_WPAD = (BM_W + 3) / 4 * 4;
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
         point_coords(p, n, pi, cx, cy, cz);
         stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
         __syncwarp();
-        gather_features<SF>(pl, ss, sF, lane);
+        gather_features<SF, B200_BWD_GATHER_UNROLL>(pl, ss, sF, lane);
         __syncwarp();
         if (wgrad && ncommit) tc::mbar_wait(mybar, (ncommit - 1) & 1);      // last iteration's dW1 MMAs have consumed the operand tiles
         // ---- layer 1 (recompute): c1 = b1 + F W1^T, then h = softplus(c1) kept in the accumulator registers
