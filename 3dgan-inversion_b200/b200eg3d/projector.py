@@ -203,7 +203,9 @@ def normalize_noise_(noise_bufs):
 # one iteration of the w-projection loop (w_projector.py:160-260) around a pose given as a rotation matrix
 
 def rot6d_to_rotmat(x):
-    """utils/camera_utils.py:259-273 (6-D rotation representation -> [B, 3, 3])."""
+    """utils/camera_utils.py:259-273 (6-D rotation representation -> [B, 3, 3]).  The cross product is taken along the last
+    dimension; the reference calls torch.cross without `dim` (legacy: first dimension of size 3), identical for every batch
+    size but 3."""
     x = x.view(-1, 2, 3) + 1e-4
     a1, a2 = x[:, 0, :], x[:, 1, :]
     b1 = F.normalize(a1)

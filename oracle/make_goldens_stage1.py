@@ -96,6 +96,32 @@ def main():
         mine, _, _ = s1.create_samples(N=N, voxel_origin=[0, 0, 0], cube_length=1.0)
         print('create_samples', N, 'max diff vs oracle', (ref_s - mine).abs().max().item())
         out[f'samples_n{N}'] = ref_s[0, ::(1 if N == 16 else 4099)].numpy().astype(np.float32)
+    # pose helpers: the reference's own rot6d_to_rotmat (utils/camera_utils.py:259-273) and LinePlaneCollision
+    # (training/warping_loss.py:58-72) on seeded inputs; the extrinsic assembly of w_projector.py:160-171 is inline code,
+    # transcribed literally below (the .cuda() calls are identities under the shim)
+    from utils.camera_utils import rot6d_to_rotmat
+    from training.warping_loss import LinePlaneCollision
+    g = torch.Generator().manual_seed(8)
+    x6 = torch.randn(2, 6, generator=g)          # not 3 rows: the reference calls torch.cross without dim (first size-3 dimension)
+    out['rot6d_in'] = x6.numpy()
+    out['rot6d_out'] = rot6d_to_rotmat(x6.clone()).numpy()
+    n_, pp_, rd_, rp_ = [torch.randn(50, 3, generator=g) for _ in range(4)]
+    out['lpc_in'] = torch.stack([n_, pp_, rd_, rp_]).numpy()
+    out['lpc_out'] = LinePlaneCollision(n_, pp_, rd_, rp_).numpy()
+    pred_rotmat = rot6d_to_rotmat(x6[:1].clone())
+    translation_opt = torch.tensor([[0.02, -0.01, 0.03]])
+    radius = 2.7
+    pred_ext_tmp = torch.eye(4).unsqueeze(0).repeat(pred_rotmat.shape[0], 1, 1).cuda()
+    pred_translation = -radius * pred_rotmat[:, :3, 2]
+    pred_ext_tmp[:, :3, :3] = pred_rotmat
+    translation_opt_world = -torch.bmm(pred_ext_tmp[:, :3, :3], translation_opt.unsqueeze(-1)) * 2.7
+    tmp_translation = translation_opt_world.squeeze(-1) + pred_translation
+    tmp_translation = tmp_translation / torch.norm(tmp_translation, dim=-1) * 2.7
+    pred_ext = torch.eye(4).unsqueeze(0).cuda()
+    pred_ext[:, :3, 3] = tmp_translation
+    pred_ext[:, :3, :3] = pred_ext_tmp[:, :3, :3]
+    out['ext_translation'] = translation_opt.numpy()
+    out['ext_out'] = pred_ext.numpy()
     np.savez_compressed(os.path.join(ROOT, 'tests', 'golden', 'stage1_warp.npz'), **out)
     print('wrote stage1_warp.npz')
 

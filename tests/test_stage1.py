@@ -136,3 +136,22 @@ def test_normalize_noise_in_place(b2):
     b2.projector.normalize_noise_(dev)
     for a, b in zip(dev.values(), ref):
         assert (a.cpu() - b).abs().max().item() < 1e-4
+
+
+def test_pose_helpers_match_reference_fixture():
+    """Device-agnostic host helpers of projector.py against outputs of the reference's own functions (CPU)."""
+    from b200eg3d import projector
+    fx = np.load(GOLD)
+    r = projector.rot6d_to_rotmat(torch.from_numpy(fx['rot6d_in']))
+    assert np.abs(r.numpy() - fx['rot6d_out']).max() < 1e-6
+    n_, pp_, rd_, rp_ = [torch.from_numpy(a) for a in fx['lpc_in']]
+    assert np.abs(projector.LinePlaneCollision(n_, pp_, rd_, rp_).numpy() - fx['lpc_out']).max() < 1e-5
+    ext = projector.assemble_extrinsic(projector.rot6d_to_rotmat(torch.from_numpy(fx['rot6d_in'][:1])), torch.from_numpy(fx['ext_translation']))
+    assert ext.shape == (1, 4, 4) and np.abs(ext.numpy() - fx['ext_out']).max() < 1e-6
+    with pytest.raises(RuntimeError, match='no intersection'):
+        projector.LinePlaneCollision(torch.tensor([[0., 0., 1.]]), torch.zeros(1, 3), torch.tensor([[1., 0., 0.]]), torch.zeros(1, 3))
+    net = stage1_feature_net()
+    x = torch.rand(1, 3, 32, 32)
+    assert torch.equal(projector.get_features(x, net, '14'), s1.get_features(x, net, '14'))
+    with pytest.raises(ValueError):
+        projector.get_features(x, net, '5')
