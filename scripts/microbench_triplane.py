@@ -21,7 +21,6 @@ rgb = torch.empty(n, M * S, 32, device=dev); sig = torch.empty(n, M * S, device=
 d_rgb = torch.randn_like(rgb); d_sig = torch.randn_like(sig)
 dpl = torch.zeros_like(planes); dpts = torch.empty(n, M * S, 3, device=dev)
 dW = [torch.zeros_like(x) for x in (W1, b1, W2, b2)]
-from b200eg3d import _lib
 
 
 

@@ -1,6 +1,6 @@
 """Per-kernel device times of the GRAPH-REPLAYED PTI step from a CUPTI trace (torch.profiler): what each kernel really costs
 inside the step (warm caches, two-branch graph), next to ncu's serialised cold-cache launch list."""
-import collections, json, os, sys
+import collections, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, '3dgan-inversion_b200')); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
 import torch
