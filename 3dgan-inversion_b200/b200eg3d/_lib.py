@@ -23,6 +23,7 @@ SIGNATURES = {
     'b200_bank_styles_bwd': [_P, _I, _P, _P, _I, _I, _I, _P],
     'b200_split_bf16': [_P, _P, _P, _L, _P],
     'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_fwd_tc_act': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_wgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_modconv_weight_prep': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -82,6 +83,8 @@ def load():
     lib.b200_triplane_bwd_workspace_bytes.restype = ctypes.c_long
     lib.b200_triplane_bwd_workspace_bytes.argtypes = [_I, _L]
     lib.b200_conv_tc_supported.argtypes = [_I] * 7
+    lib.b200_conv_tc_act_fusable.restype = ctypes.c_int
+    lib.b200_conv_tc_act_fusable.argtypes = [_I] * 6
     lib.b200_noise_pyramid_work_floats.restype = ctypes.c_long
     lib.b200_noise_pyramid_work_floats.argtypes = [_I, _P]
     _lib = lib

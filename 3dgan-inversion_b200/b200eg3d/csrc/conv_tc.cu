@@ -49,7 +49,20 @@ struct TcPixParams {
     int ksplit;                  // > 1: the k-blocks of a tile are spread over ksplit CTAs, partial sums reduced with red.global.add
     int ntn, nwork;              // N tiles; work items = cta_start[ncls] * ntn * batch
     int stage_bytes, nstages;    // ring geometry: bytes one k-block really needs, and how many fit in RING_BYTES
+    // Optional fused SynthesisLayer epilogue (up == 1 forward, no split-K, N a multiple of 32; networks_stylegan2.py:318-329):
+    // z = clamp(lrelu(acc + noise * strength + bias) * act_gain), written as fp32 (C) and as the split-bf16 pair of the next conv.
+    int act;
+    const float* bias; const float* noise; const float* strength; long noise_bs;
+    float alpha, act_gain, clamp;
+    __nv_bfloat16* z_hi; __nv_bfloat16* z_lo;
 };
+
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    return make_uint4(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
+                      *reinterpret_cast<uint32_t*>(&d));
+}
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -200,7 +213,37 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty(acc));
                 }
-                if (valid) {
+                if (valid && p.act) {                  // fused layer epilogue (launch code guarantees ksplit == 1, N % 32 == 0, plain output grid)
+                    const float nz = p.noise ? __ldg(p.noise + (long)o.b * p.noise_bs + (long)iy * kc.Wi + ix) * __ldg(p.strength) : 0.f;
+                    const float4* bsrc = reinterpret_cast<const float4*>(p.bias + o.n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bv = __ldg(bsrc + (j >> 2));
+                        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float t = v[j + q] + nz + bb[q];
+                            t = t > 0.f ? t : t * p.alpha;
+                            t *= p.act_gain;
+                            if (p.clamp >= 0.f) t = (t > -p.clamp && t < p.clamp) ? t : (t >= 0.f ? p.clamp : -p.clamp);
+                            v[j + q] = t;
+                        }
+                        *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    const long eo = (long)o.b * p.c_bs + opix * p.ldc + o.n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 h = pack8_bf16(v + j);
+                        *reinterpret_cast<uint4*>(p.z_hi + eo + j) = h;
+                        if (p.z_lo) {
+                            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
+                            float lo[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) lo[q] = v[j + q] - __bfloat162float(hb[q]);
+                            *reinterpret_cast<uint4*>(p.z_lo + eo + j) = pack8_bf16(lo);
+                        }
+                    }
+                } else if (valid) {
                     if (vec && o.n0 + c0 + 32 <= p.N) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -495,8 +538,19 @@ B200_API int b200_split_bf16(const float* x, void* hi, void* lo, long count, voi
 
 // Forward conv on split-bf16 operands.  x_* [n][h][w][cin] bf16, w_* [n][taps][cout][cin] bf16, y fp32 NHWC
 // (up == 2: y is the (2h+1)x(2w+1) transposed-conv grid, as in b200_conv_fwd).  npass: 1 (hi*hi) or 3.
-B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int n, int h,
-                              int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+struct FwdEpilogue {
+    const float* bias; const float* noise; const float* strength; long noise_bs; float alpha, act_gain, clamp; void* z_hi; void* z_lo;
+};
+
+static int fwd_ksplit(int n, int h, int w, int cin, int cout, int ksize) {       // split-K factor of an up == 1 forward launch
+    int th, tw;
+    pick_tile(h, w, th, tw);
+    const int tiles = ((w + tw - 1) / tw) * ((h + th - 1) / th), bn = pick_bn(cout);
+    return pick_ksplit(tiles * ((cout + bn - 1) / bn) * n, ksize * ksize * ((cin + 63) / 64));
+}
+
+static int conv_fwd_tc_impl(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int n, int h,
+                            int w, int cin, int cout, int ksize, int up, int npass, const FwdEpilogue* ep, void* stream) {
     B200_REQUIRE(b200_conv_tc_supported(0, h, w, cin, cout, ksize, up), "conv_fwd_tc: unsupported shape");
     B200_REQUIRE(npass == 1 || (npass == 3 && x_lo && w_lo), "conv_fwd_tc: npass must be 1, or 3 with lo operands");
     cudaStream_t st = (cudaStream_t)stream;
@@ -542,8 +596,41 @@ B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_
         for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
             if (int e = make_map_nhwc(&p.tmA[k][i], i ? x_lo : x_hi, n, h, w, cin, p.c[k].tw, p.c[k].th, 1)) return e;
     }
+    if (ep) {
+        B200_REQUIRE(up == 1 && p.ksplit == 1 && cout % 32 == 0 && ep->bias && ep->z_hi && (!ep->noise || ep->strength),
+                     "conv_fwd_tc_act: epilogue fusion needs up == 1, no split-K, cout % 32 == 0 (ask b200_conv_tc_act_fusable first)");
+        p.act = 1; p.bias = ep->bias; p.noise = ep->noise; p.strength = ep->strength; p.noise_bs = ep->noise_bs;
+        p.alpha = ep->alpha; p.act_gain = ep->act_gain; p.clamp = ep->clamp;
+        p.z_hi = (__nv_bfloat16*)ep->z_hi; p.z_lo = (__nv_bfloat16*)ep->z_lo;
+    }
     if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * p.c_bs, st));
     return launch_pix<false>(p, n, st);
+}
+
+B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int n, int h,
+                              int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+    return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, y, n, h, w, cin, cout, ksize, up, npass, nullptr, stream);
+}
+
+// 1 when b200_conv_fwd_tc_act can fuse the SynthesisLayer epilogue into the convolution's TMEM drain for this shape.
+B200_API int b200_conv_tc_act_fusable(int n, int h, int w, int cin, int cout, int ksize) {
+    if (!b200_conv_tc_supported(0, h, w, cin, cout, ksize, 1) || cout % 32 != 0) return 0;
+    // The epilogue of tile i runs under the main loop of tile i+1: that hides it only when a tile has enough k-blocks.  Measured:
+    // with 9 / 18 k-blocks per tile (64- / 128-channel layers) the fused kernel loses what the separate epilogue launch cost.
+    if (ksize * ksize * ((cin + 63) / 64) < 36) return 0;
+    return fwd_ksplit(n, h, w, cin, cout, ksize) == 1;
+}
+
+// up == 1 forward convolution with the layer epilogue applied while the accumulator leaves tensor memory:
+//   z = clamp(lrelu_alpha(conv + noise[pix] * *strength + bias[c]) * act_gain, +-clamp)   (networks_stylegan2.py:318-329)
+// written as fp32 z and as split-bf16 z_hi / z_lo (z_lo may be NULL).  noise: [h*w] (noise_bs == 0) or [n][h*w]; may be NULL.
+B200_API int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, void* z_hi,
+                                  void* z_lo, const float* bias, const float* noise, const float* strength, long noise_bs, int n,
+                                  int h, int w, int cin, int cout, int ksize, int npass, float alpha, float act_gain, float clamp,
+                                  void* stream) {
+    B200_REQUIRE(z, "conv_fwd_tc_act: null output");
+    FwdEpilogue ep{bias, noise, strength, noise_bs, alpha, act_gain, clamp, z_hi, z_lo};
+    return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, z, n, h, w, cin, cout, ksize, 1, npass, &ep, stream);
 }
 
 // dgrad on split-bf16 operands.  dy_* bf16 ([h][w][cout], or the (2h+1)x(2w+1) grid when up == 2), w_* as above, dx fp32.

@@ -457,7 +457,11 @@ class _ModConvLayer(torch.autograd.Function):
             if x_hi is None or (fp == 3 and x_lo is None):
                 x_hi, x_lo = _split(x, fp == 3)
             z_hi, z_lo = _bf16_like(z), _bf16_like(z)
-            if up == 1:
+            if up == 1 and _lib.load().b200_conv_tc_act_fusable(n, h, w, cin, cout, k) == 1:
+                # epilogue applied while the accumulator leaves tensor memory: no fp32 round trip of the raw conv output
+                call('b200_conv_fwd_tc_act', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(z), ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st),
+                     nbs, n, h, w, cin, cout, k, fp, 0.2, float(act_gain), clampf, stream())
+            elif up == 1:
                 y = torch.empty_like(z)
                 call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cout, k, 1, fp, stream())
                 call('b200_layer_act_fwd', ptr(y), ptr(z), ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,

@@ -79,6 +79,14 @@ int b200_conv_tc_supported(int kind, int h, int w, int cin, int cout, int ksize,
 int b200_split_bf16(const float* x, void* hi_bf16, void* lo_bf16 /* may be NULL */, long count, void* stream);
 int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y,
                      int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+/* up == 1 forward convolution with the SynthesisLayer epilogue (networks_stylegan2.py:318-329) applied while the accumulator
+ * leaves tensor memory: z = clamp(lrelu_alpha(conv + noise[pix] * *strength + bias[c]) * act_gain, +-clamp), written as fp32 z and
+ * as the split-bf16 pair z_hi / z_lo (z_lo may be NULL) that feeds the next convolution.  noise [h*w] (noise_bs 0) or [n][h*w]
+ * (noise_bs h*w), may be NULL.  Only for shapes b200_conv_tc_act_fusable reports 1 (no split-K, cout % 32 == 0). */
+int b200_conv_tc_act_fusable(int n, int h, int w, int cin, int cout, int ksize);
+int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, void* z_hi, void* z_lo,
+                         const float* bias, const float* noise, const float* strength, long noise_bs, int n, int h, int w, int cin,
+                         int cout, int ksize, int npass, float alpha, float act_gain, float clamp, void* stream);
 int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx,
                        int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
 int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod,

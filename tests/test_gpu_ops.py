@@ -392,3 +392,34 @@ def test_ray_sampler_kernel(b2, n, R):
     assert maxdiff(o2, o) == 0.0 and maxdiff(d2, d) < 1e-6
     _, dcam, uv = b2.RaySampler()(cd.detach(), c[:, 16:].reshape(n, 3, 3).cuda(), R, need_cam_space=True)
     assert dcam.shape == (n, R * R, 3) and uv.shape == (n, R * R, 2)
+
+
+@pytest.mark.parametrize('noise_mode', ['const', 'batch', 'none'])
+def test_conv_fwd_tc_fused_epilogue_matches_two_kernel_path(b2, noise_mode):
+    """b200_conv_fwd_tc_act (layer epilogue applied in the TMEM drain) == b200_conv_fwd_tc followed by b200_layer_act_fwd."""
+    from b200eg3d._lib import call, ptr, stream, load
+    n, h, w, cin, cout = 2, 96, 128, 256, 64
+    assert load().b200_conv_tc_act_fusable(n, h, w, cin, cout, 3) == 1
+    assert load().b200_conv_tc_act_fusable(n, 8, 8, cin, cout, 3) == 0          # split-K layer: not fusable
+    g = gen(17)
+    x = torch.randn(n, h, w, cin, generator=g).cuda()
+    wm = (torch.randn(n, 9, cout, cin, generator=g) * 0.05).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    strength = torch.full([], 0.3).cuda()
+    noise, nbs = None, 0
+    if noise_mode == 'const':
+        noise = torch.randn(h, w, generator=g).cuda()
+    elif noise_mode == 'batch':
+        noise, nbs = torch.randn(n, 1, h, w, generator=g).cuda(), h * w
+    xh, xl = b2.ops._split(x, True)
+    wh, wl = b2.ops._split(wm, True)
+    y = torch.empty(n, h, w, cout, device='cuda')
+    z0, z1 = torch.empty_like(y), torch.empty_like(y)
+    h0, l0, h1, l1 = [torch.empty(n, h, w, cout, device='cuda', dtype=torch.bfloat16) for _ in range(4)]
+    call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, 3, 1, 3, stream())
+    call('b200_layer_act_fwd', ptr(y), ptr(z0), ptr(h0), ptr(l0), ptr(bias), ptr(noise), ptr(strength) if noise is not None else None, nbs,
+         n, h * w, cout, 1, 0.2, math.sqrt(2), 1.5, stream())
+    call('b200_conv_fwd_tc_act', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(z1), ptr(h1), ptr(l1), ptr(bias), ptr(noise),
+         ptr(strength) if noise is not None else None, nbs, n, h, w, cin, cout, 3, 3, 0.2, math.sqrt(2), 1.5, stream())
+    assert float(z0.abs().max()) == 1.5                                          # the clamp is active
+    assert maxdiff(z1, z0) < 1e-6 and maxdiff(h1.float(), h0.float()) < 1e-2 and maxdiff((h1.float() + l1.float()), z0) < 1e-4
