@@ -155,15 +155,49 @@ def run_b200(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    copy_stream = torch.cuda.Stream()
+    stage = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    ready, consumed, loss_ev = ([torch.cuda.Event() for _ in range(2)] for _ in range(3))
+    for ev in consumed:
+        ev.record()
+    loss_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    e2e_losses = []
+
     def timed(n_steps, e2e):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n_steps):
-            if e2e:
-                loss = step([t.to(dev, non_blocking=True) for t in host])
-                loss.item()                                   # device -> host read of the step's result
-            else:
+        if e2e:
+            # Every step: host->device copy of its inputs from pinned memory and a device->host read of its loss.  Double-buffered:
+            # the copy for step i+1 runs on a second stream under step i's kernels, and step i's loss is read on the host while
+            # step i+1 is already queued (one step of lag), so neither the PCIe transfer nor the host sync sits on the critical path.
+            main = torch.cuda.current_stream()
+            for i in range(n_steps):
+                b = i & 1
+                if i == 0:
+                    with torch.cuda.stream(copy_stream):
+                        for dst, src in zip(stage[0], host):
+                            dst.copy_(src, non_blocking=True)
+                        ready[0].record(copy_stream)
+                main.wait_event(ready[b])
+                loss = step(stage[b])
+                consumed[b].record(main)
+                loss_host[b].copy_(loss.detach().reshape(1), non_blocking=True)
+                loss_ev[b].record(main)
+                if i + 1 < n_steps:
+                    nb = b ^ 1
+                    copy_stream.wait_event(consumed[nb])
+                    with torch.cuda.stream(copy_stream):
+                        for dst, src in zip(stage[nb], host):
+                            dst.copy_(src, non_blocking=True)
+                        ready[nb].record(copy_stream)
+                if i >= 1:
+                    loss_ev[b ^ 1].synchronize()
+                    e2e_losses.append(float(loss_host[b ^ 1]))
+            loss_ev[(n_steps - 1) & 1].synchronize()
+            e2e_losses.append(float(loss_host[(n_steps - 1) & 1]))
+        else:
+            for _ in range(n_steps):
                 step(resident)
         e1.record()
         barrier()
@@ -277,7 +311,8 @@ def run_b200(args):
                        'launch': 'eager (one Python-driven launch per kernel)' if args.eager else
                                  'whole step captured once in a CUDA graph (b200eg3d.graphs.GraphedStep) and replayed'},
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
-                    'd2h_bytes_per_step': 4},
+                    'd2h_bytes_per_step': 4, 'host_reads': len(e2e_losses),
+                    'pipelining': 'double-buffered: H2D of step i+1 on a copy stream under step i, loss of step i read on the host one step later'},
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_conv_stack': roof_conv if rank == 0 else None,
             'kernel_ms': kernel_ms if rank == 0 else None, 'per_call_ms_event_brackets': per_call if rank == 0 else None, 'cpu_baseline': cpu, 'final_loss': round(final_loss, 6),
         }
