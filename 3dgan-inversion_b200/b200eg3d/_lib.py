@@ -79,6 +79,8 @@ def load():
     lib.b200_last_error.argtypes = []
     lib.b200_version.restype = ctypes.c_int
     lib.b200_version.argtypes = []
+    lib.b200_set_pdl.restype = ctypes.c_int
+    lib.b200_set_pdl.argtypes = [_I]
     lib.b200_conv_tc_supported.restype = ctypes.c_int
     lib.b200_triplane_bwd_workspace_bytes.restype = ctypes.c_long
     lib.b200_triplane_bwd_workspace_bytes.argtypes = [_I, _L]

@@ -35,10 +35,10 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // own pdl_wait() until this grid has completed): its CTAs then sit ready on the SMs when our last CTA retires.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+extern int g_b200_pdl;            // -1: take B200EG3D_PDL from the environment on first use; 0 / 1: set by b200_set_pdl()
 static inline bool b200_pdl_enabled() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("B200EG3D_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
-    return on == 1;
+    if (g_b200_pdl < 0) { const char* e = getenv("B200EG3D_PDL"); g_b200_pdl = (e && e[0] == '0') ? 0 : 1; }
+    return g_b200_pdl == 1;
 }
 
 template <typename... KArgs, typename... Args>

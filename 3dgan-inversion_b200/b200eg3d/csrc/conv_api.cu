@@ -7,6 +7,7 @@
 #include "conv_geom.h"
 
 thread_local char g_b200_err[512] = "";
+int g_b200_pdl = -1;
 
 static void plain_out(ConvGeom& g, int wo) { g.Wo = wo; g.osy = g.osx = 1; g.ooy = g.oox = 0; }
 
@@ -92,4 +93,12 @@ B200_API int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int 
 }
 
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 101; }
+B200_API int b200_version() { return 102; }
+
+// Programmatic dependent launch on (1) / off (0) for subsequent launches; returns the previous setting.  Profiling aid: with PDL a
+// traced kernel duration includes the time it waits for its predecessor.
+B200_API int b200_set_pdl(int on) {
+    const int prev = b200_pdl_enabled() ? 1 : 0;
+    g_b200_pdl = on ? 1 : 0;
+    return prev;
+}

@@ -246,7 +246,11 @@ def run_b200(args):
             def one_step():
                 opt.zero_grad(set_to_none=True)
                 eager_step(*resident)
-            kt = cupti_kernel_times(one_step)
+            pdl_prev = _lib.load().b200_set_pdl(0)        # with PDL a traced duration would include the wait for the predecessor
+            try:
+                kt = cupti_kernel_times(one_step)
+            finally:
+                _lib.load().b200_set_pdl(pdl_prev)
         except Exception as e:                        # CUPTI unavailable: keep the event brackets only
             kt = None
             print(f'[bench] CUPTI kernel trace unavailable ({type(e).__name__}: {e}); conv-stack time from CUDA-event brackets', file=sys.stderr)

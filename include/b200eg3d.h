@@ -21,6 +21,8 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int b200_version(void);                 /* replaces the plugin identity of torch_utils/custom_ops.py:61 get_plugin() */
 const char* b200_last_error(void);      /* replaces TORCH_CHECK -> RuntimeError text, torch_utils/ops/bias_act.cpp:39-55 */
+int b200_set_pdl(int on);               /* programmatic dependent launch of the conv / epilogue / FIR kernels on (default; env
+                                           B200EG3D_PDL=0 disables) or off; returns the previous setting.  Profiling aid. */
 
 /* ---- modulated convolution (training/networks_stylegan2.py:34-91 modulated_conv2d, fused path) ---------------- */
 

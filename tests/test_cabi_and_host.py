@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_table_matches_header():
     from b200eg3d import _lib
     syms = set(declared_symbols())
-    bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes',
+    bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes',
                                         'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable'}
     assert syms == bound, (sorted(syms - bound), sorted(bound - syms))
     src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
@@ -52,6 +52,8 @@ def test_shape_support_query_needs_no_gpu():
     assert lib.b200_conv_tc_supported(0, 64, 64, 12, 20, 3, 1) == 0        # channel count not a multiple of 8 -> fp32 path
     assert lib.b200_conv_tc_supported(1, 64, 64, 64, 3, 1, 1) == 0
     assert lib.b200_conv_tc_supported(0, 8, 8, 64, 64, 5, 1) == 0
+    prev = lib.b200_set_pdl(0)
+    assert lib.b200_set_pdl(prev) == 0 and lib.b200_set_pdl(prev) == prev
 
 
 def test_module_tree_mirrors_reference_names():
