@@ -302,7 +302,7 @@ def run_b200(args):
                      'note': 'algorithmic FLOPs (fwd+dgrad+wgrad = 428.3 GFLOP); forward and dgrad issue 3 MMAs per product (split-bf16 parity mode), '
                              'wgrad 1: the tensor pipe executes 7/3 of the algorithmic FLOPs (issued_*)'}
         if world == 1 and not args.no_cpu:
-            cpu = cpu_baseline(1, 1)
+            cpu = cpu_baseline(1, 5)          # ~10-12 s of host work on the GPU box (1 warm-up + 5 timed PTI steps)
     if rank == 0:
         n_in = sum(t.numel() * t.element_size() for t in host)
         line = {
