@@ -519,14 +519,14 @@ def run_reference(args):
         return
     first = cpu_baseline(0, 1)
     per = first['seconds_per_step']
-    budget = 150.0
+    budget = 90.0
     k = max(1, min(args.steps, int(budget / per) - 1))
     w = 1
     res = cpu_baseline(0, k) if k > 0 else first
     line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'steps/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
             'steps': k, 'warmup': w, 'ms_per_step': round(1e3 / res['value'], 1), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
-            'config': {'workload': WORKLOAD, 'note': 'reference CPU path restated by the oracle port, all host threads; steps bounded to ~150 s'},
+            'config': {'workload': WORKLOAD, 'note': 'reference CPU path restated by the oracle port, all host threads; steps bounded to ~90 s'},
             'cpu_baseline': dict(res, value=res['value']),
             'e2e': {'value': res['value'], 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
