@@ -277,6 +277,7 @@ def run_b200(args):
                 'traffic': traffic.get('triplane_mlp_bwd_mma_kernel', {}).get('bytes'), 'peak_source': how,
                 'algorithmic_bytes_per_launch': bwd_bytes, 'launch_ms': round(bwd_launch_ms, 4), 'launches_per_step': bwd_n / nprof,
                 'launch_ms_eager_bracket': round(bwd_eager_ms, 4),
+                'l2_gather_scatter_gbs': round(2 * P1 * 1536 / (bwd_launch_ms * 1e-3) / 1e9, 1) if bwd_launch_ms > 0 else None,
                 'share_of_kernel_time': round(bwd_launch_ms * (bwd_n / nprof) / (sum(v[0] for v in kt.values()) if kt else tot_ms), 3),
                 'note': 'HBM-bound only by the compulsory-byte definition: DRAM traffic equals the algorithmic bytes (no re-reads); '
                         'the kernel is limited by the L2 gather + vector-atomic scatter of 2 x 1.2 GB of texel lines (L2 35 %) and by instruction issue '
