@@ -12,6 +12,10 @@ LIB_PATH = os.environ.get('B200EG3D_LIB') or os.path.join(_HERE, 'libb200eg3d.so
 
 _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 
+# b200_version() this binding table was written for.  Bumped together with csrc/conv_api.cu whenever a prototype changes: a
+# stale or variant .so (B200EG3D_LIB) with other argument lists would otherwise be called with the wrong stack layout.
+EXPECTED_VERSION = 200
+
 # name -> argument ctypes (every function returns int status; 0 = ok)
 SIGNATURES = {
     'b200_conv_fwd': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
@@ -71,6 +75,11 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f'{LIB_PATH} is missing: run `python __graft_entry__.py build` (no CPU/PyTorch fallback exists)')
     lib = ctypes.CDLL(LIB_PATH)
+    lib.b200_version.restype = ctypes.c_int
+    lib.b200_version.argtypes = []
+    if lib.b200_version() != EXPECTED_VERSION:
+        raise RuntimeError(f'{LIB_PATH} reports version {lib.b200_version()}, this binding expects {EXPECTED_VERSION}: '
+                           'rebuild with `python __graft_entry__.py build`')
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args
@@ -81,6 +90,8 @@ def load():
     lib.b200_version.argtypes = []
     lib.b200_set_pdl.restype = ctypes.c_int
     lib.b200_set_pdl.argtypes = [_I]
+    lib.b200_set_mlp_passes.restype = ctypes.c_int
+    lib.b200_set_mlp_passes.argtypes = [_I]
     lib.b200_conv_tc_supported.restype = ctypes.c_int
     lib.b200_triplane_bwd_workspace_bytes.restype = ctypes.c_long
     lib.b200_triplane_bwd_workspace_bytes.argtypes = [_I, _L]
@@ -104,8 +115,49 @@ def ptr(t):
     return t.data_ptr()
 
 
-def stream():
-    return torch.cuda.current_stream().cuda_stream
+def stream(device=None):
+    """Raw handle of torch's current stream on `device` (default: the current device)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class on_device:
+    """Make the device of `t` current for the enclosed C-ABI calls and restore the previous one afterwards (the reference's
+    plugins do this with OptionalCUDAGuard(device_of(x)), bias_act.cpp:58).  A no-op when it already is current."""
+
+    def __init__(self, t):
+        self.idx = t.device.index if (t is not None and t.is_cuda) else None
+        self.prev = None
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def device_guard(fn):
+    """Decorator for autograd.Function.forward / backward: run with the device of the first CUDA tensor argument current, so
+    that kernels, torch.empty(...) allocations and stream() all refer to the tensors' device even when another one is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        t = next((a for a in args if isinstance(a, torch.Tensor) and a.is_cuda), None)
+        if t is None and args and hasattr(args[0], 'saved_tensors'):
+            try:
+                t = next((a for a in args[0].saved_tensors if isinstance(a, torch.Tensor) and a.is_cuda), None)
+            except Exception:
+                t = None
+        with on_device(t):
+            return fn(*args, **kwargs)
+    return wrapper
 
 
 LAUNCHES = 0        # number of C-ABI kernel calls made (bench.py reads it for `gpu_launches`)

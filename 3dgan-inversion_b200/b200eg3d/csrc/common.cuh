@@ -25,6 +25,26 @@ static inline int b200_fail(const char* file, int line, const char* msg) {
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Per-device one-time state.  cudaFuncSetAttribute and the SM count are properties of a DEVICE, so nothing here may be cached
+// in a process-wide flag: a second GPU used from the same process would otherwise launch with the default 48 KB shared-memory
+// limit.  Benign race: two threads may both run the set-up for a device, which is idempotent.
+constexpr int B200_MAX_DEVICES = 64;
+static inline int b200_current_device() { int d = 0; return cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < B200_MAX_DEVICES ? d : 0; }
+struct B200PerDeviceFlag {
+    volatile unsigned char done[B200_MAX_DEVICES];
+    bool test(int dev) const { return done[dev] != 0; }
+    void set(int dev) { done[dev] = 1; }
+};
+// set `attr` of kernel `fn` to `value` once per device
+#define B200_FUNC_ATTR_ONCE(fn, attr, value) do { static B200PerDeviceFlag flag_ = {}; const int dev_ = b200_current_device(); \
+    if (!flag_.test(dev_)) { B200_CUDA(cudaFuncSetAttribute(fn, attr, value)); flag_.set(dev_); } } while (0)
+static inline int b200_sm_count() {
+    static int sms[B200_MAX_DEVICES] = {};
+    const int dev = b200_current_device();
+    if (!sms[dev]) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148; sms[dev] = v; }
+    return sms[dev];
+}
+
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may be
 // scheduled while its predecessor in the stream is still draining; it must execute pdl_wait() (griddepcontrol.wait: all
 // prerequisite grids complete and their memory visible) before touching global memory.  The step is ~250 dependent launches,

@@ -496,17 +496,12 @@ int pick_bn(int n) {           // N tile of the K-major-B kernels (a multiple of
 
 template <bool B_MN>
 int launch_pix(TcPixParams& p, int batch, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(conv_tc_pix_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr = true;
-    }
+    B200_FUNC_ATTR_ONCE(conv_tc_pix_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     p.ntn = (p.N + p.BN - 1) / p.BN;
     p.nwork = p.cta_start[p.ncls] * p.ntn * batch;
     p.stage_bytes = (A_BYTES + p.BN * TILE_K * 2) * (p.npass == 3 ? 2 : 1);
     p.nstages = RING_BYTES / p.stage_bytes < MAX_ST ? RING_BYTES / p.stage_bytes : MAX_ST;
-    static int sms = 0;
-    if (!sms) { int dev = 0; B200_CUDA(cudaGetDevice(&dev)); B200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)); }
+    const int sms = b200_sm_count();
     const int grid = p.nwork < sms ? p.nwork : sms;
     B200_CUDA(launch_pdl(conv_tc_pix_kernel<B_MN>, dim3(grid), dim3(192), SMEM_BYTES, st, p));
     B200_CHECK_LAUNCH();
@@ -699,11 +694,7 @@ B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
     B200_CUDA(cudaMemsetAsync(dwmod, 0, sizeof(float) * (size_t)n * taps * cout * cin, st));
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr = true;
-    }
+    B200_FUNC_ATTR_ONCE(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     dim3 grid(mt, nt, n * (taps / p.tg) * ksplit);
     B200_CUDA(launch_pdl(conv_tc_wgrad_kernel, grid, dim3(192), SMEM_BYTES, st, p));
     B200_CHECK_LAUNCH();

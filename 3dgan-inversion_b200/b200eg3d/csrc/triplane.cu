@@ -701,6 +701,9 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
     }
 }
 
+}  // namespace
+int g_b200_mlp_passes = 0;        // 0: take B200EG3D_MLP_PASSES from the environment on first use; 1 / 3: set by b200_set_mlp_passes()
+namespace {
 int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                 const float* ray_d, const float* depths, int S, long P, float box_warp, const float* W1, const float* b1,
                 const float* W2, const float* b2, float lr_mul) {
@@ -728,20 +731,27 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     p.rgb = rgb; p.sigma = sigma;
     const long groups = (P + 127) / 128;
     dim3 grid((unsigned)(groups < 148 * 8 ? groups : 148 * 8), n);
-    static int passes = 0;
-    if (passes == 0) {
+    if (g_b200_mlp_passes == 0) {
         const char* e2 = getenv("B200EG3D_MLP_PASSES");
-        passes = (e2 && strcmp(e2, "1") == 0) ? 1 : 3;
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM));
+        g_b200_mlp_passes = (e2 && strcmp(e2, "1") == 0) ? 1 : 3;
     }
-    p.fwd_passes = passes;
+    B200_FUNC_ATTR_ONCE(triplane_mlp_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+    B200_FUNC_ATTR_ONCE(triplane_mlp_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+    p.fwd_passes = g_b200_mlp_passes;
     const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
     grid.x = (unsigned)(g512 < 148 ? g512 : 148);                      // persistent: one 16-warp CTA per SM
     if (rgb) triplane_mlp_fwd_mma_kernel<false><<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
     else triplane_mlp_fwd_mma_kernel<true><<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
+}
+
+// Operand passes of the decoder forward: 3 = split operands (fp32-equivalent, the parity default), 1 = single pass (the
+// non-parity "fast mode" reported separately by bench.py).  Returns the previous value.
+B200_API int b200_set_mlp_passes(int passes) {
+    const int prev = g_b200_mlp_passes == 0 ? 3 : g_b200_mlp_passes;
+    g_b200_mlp_passes = passes == 1 ? 1 : 3;
+    return prev;
 }
 
 // Kept for ABI stability: the decoder-parameter gradients are accumulated in tensor memory inside the kernel and need
@@ -768,14 +778,8 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
     (void)workspace; (void)workspace_bytes;
-    static bool attr_set = false;
-    if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel<BM_WARPS_WG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       bm_smem(BM_WARPS_WG, true)));
-        B200_CUDA(cudaFuncSetAttribute(triplane_mlp_bwd_mma_kernel<BM_WARPS_NOWG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       bm_smem(BM_WARPS_NOWG, false)));
-        attr_set = true;
-    }
+    B200_FUNC_ATTR_ONCE((triplane_mlp_bwd_mma_kernel<BM_WARPS_WG, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bm_smem(BM_WARPS_WG, true));
+    B200_FUNC_ATTR_ONCE((triplane_mlp_bwd_mma_kernel<BM_WARPS_NOWG, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bm_smem(BM_WARPS_NOWG, false));
     const int warps = dW1 ? BM_WARPS_WG : BM_WARPS_NOWG;
     const long gb = (P + warps * 32 - 1) / (warps * 32);
     dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one CTA per SM

@@ -17,6 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from ._lib import on_device
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -250,6 +251,10 @@ class SynthesisNetwork(torch.nn.Module):
             setattr(self, f'b{res}', block)
 
     def forward_nhwc(self, ws, **block_kwargs):
+        with on_device(ws):                     # streams, events and allocations below refer to the latents' device
+            return self._forward_nhwc(ws, **block_kwargs)
+
+    def _forward_nhwc(self, ws, **block_kwargs):
         block_ws = []
         ws = ws.to(torch.float32)
         w_idx = 0
@@ -319,6 +324,10 @@ class SuperresolutionHybrid8X(torch.nn.Module):
         self.register_buffer('resample_filter', ops.setup_filter([1, 3, 3, 1]))
 
     def forward_nhwc(self, rgb, x, ws, **block_kwargs):
+        with on_device(ws):
+            return self._forward_nhwc(rgb, x, ws, **block_kwargs)
+
+    def _forward_nhwc(self, rgb, x, ws, **block_kwargs):
         ws = ws[:, -1:, :].repeat(1, 3, 1)
         if x.shape[1] != self.input_resolution:
             size = (self.input_resolution, self.input_resolution)
@@ -426,20 +435,34 @@ class ImportanceRenderer(torch.nn.Module):
             return planes.permute(0, 3, 4, 1, 2).reshape(n, h, w, p * c).contiguous()
         return planes                   # already [N,H,W,96]
 
+    @staticmethod
+    def ray_limits_box(rays_o, rays_d, box_side_length):
+        """math_utils.py:46-98 (get_ray_limits_box): slab test of every ray against the cube of side box_side_length about the
+        origin; returns (t_near, t_far) [N,M,1], (-1, -2) for rays that miss.  No gradient (the reference detaches the rays)."""
+        o, d = rays_o.detach().reshape(-1, 3), rays_d.detach().reshape(-1, 3)
+        half = box_side_length / 2
+        inv = 1 / d
+        neg = inv < 0
+        t_in = (torch.where(neg, half, -half) - o) * inv          # entry / exit distance through each pair of faces
+        t_out = (torch.where(neg, -half, half) - o) * inv
+        tmin, tmax = t_in[:, 0], t_out[:, 0]
+        hit = ~((tmin > t_out[:, 1]) | (t_in[:, 1] > tmax))
+        tmin, tmax = torch.maximum(tmin, t_in[:, 1]), torch.minimum(tmax, t_out[:, 1])
+        hit &= ~((tmin > t_out[:, 2]) | (t_in[:, 2] > tmax))
+        tmin, tmax = torch.maximum(tmin, t_in[:, 2]), torch.minimum(tmax, t_out[:, 2])
+        tmin = torch.where(hit, tmin, -torch.ones_like(tmin))
+        tmax = torch.where(hit, tmax, -2 * torch.ones_like(tmax))
+        return tmin.reshape(*rays_o.shape[:-1], 1), tmax.reshape(*rays_o.shape[:-1], 1)
+
     def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options):
-        if rendering_options['ray_start'] == rendering_options['ray_end'] == 'auto':
-            raise NotImplementedError("ray_start='auto' (math_utils.get_ray_limits_box) is not implemented in b200eg3d")
-        if rendering_options.get('disparity_space_sampling', False):
-            raise NotImplementedError('disparity_space_sampling is not implemented in b200eg3d')
         assert rendering_options.get('clamp_mode', 'softplus') == 'softplus'
         pl = self._planes_nhwc(planes)
         dev = pl.device
         N, M, _ = ray_origins.shape
         S = int(rendering_options['depth_resolution'])
         S2 = int(rendering_options['depth_resolution_importance'])
-        ray_start, ray_end = float(rendering_options['ray_start']), float(rendering_options['ray_end'])
-        t_base = torch.linspace(ray_start, ray_end, S, device=dev)
-        delta = (ray_end - ray_start) / (S - 1)
+        auto = rendering_options['ray_start'] == rendering_options['ray_end'] == 'auto'
+        disparity = bool(rendering_options.get('disparity_space_sampling', False))
         if self.fixed_noise is not None:
             u_strat, u_imp = self.fixed_noise
             u_strat = u_strat.to(dev)
@@ -447,9 +470,32 @@ class ImportanceRenderer(torch.nn.Module):
         else:
             u_strat = torch.rand([N, M, S, 1], device=dev)                        # renderer.py:245
             u_imp = torch.rand([N * M, S2], device=dev) if S2 > 0 else None       # renderer.py:292
+        t_base, delta, t_coarse = None, 0.0, None
+        if auto:                                                                  # renderer.py:146-152, sample_stratified :238-242
+            ray_start, ray_end = self.ray_limits_box(ray_origins, ray_directions, rendering_options['box_warp'])
+            ok = ray_end > ray_start
+            lo, hi = torch.where(ok, ray_start, float('inf')).min(), torch.where(ok, ray_start, -float('inf')).max()
+            any_ok = ok.any()                                                     # stays on the device: no host sync (the reference calls .item())
+            ray_start = torch.where(ok | ~any_ok, ray_start, lo)
+            ray_end = torch.where(ok | ~any_ok, ray_end, hi)
+            steps = (torch.arange(S, dtype=torch.float32, device=dev) / (S - 1)).reshape(1, 1, S, 1)
+            if disparity:
+                t = steps + u_strat * (1.0 / (S - 1))
+                t_coarse = 1. / (1. / ray_start.unsqueeze(2) * (1. - t) + 1. / ray_end.unsqueeze(2) * t)
+            else:
+                t_coarse = ray_start.unsqueeze(2) + steps * (ray_end - ray_start).unsqueeze(2) \
+                    + u_strat * ((ray_end - ray_start) / (S - 1)).unsqueeze(-1)
+        elif disparity:                                                           # renderer.py:230-237
+            ray_start, ray_end = float(rendering_options['ray_start']), float(rendering_options['ray_end'])
+            t = torch.linspace(0, 1, S, device=dev).reshape(1, 1, S, 1) + u_strat * (1.0 / (S - 1))
+            t_coarse = 1. / (1. / ray_start * (1. - t) + 1. / ray_end * t)
+        else:
+            ray_start, ray_end = float(rendering_options['ray_start']), float(rendering_options['ray_end'])
+            t_base = torch.linspace(ray_start, ray_end, S, device=dev)
+            delta = (ray_end - ray_start) / (S - 1)
         return ops.render(pl, decoder, ray_origins, ray_directions, rendering_options['box_warp'], t_base, delta, u_strat,
                           u_imp, white_back=rendering_options.get('white_back', False),
-                          density_noise=rendering_options.get('density_noise', 0))
+                          density_noise=rendering_options.get('density_noise', 0), t_coarse=t_coarse)
 
     def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
         pl = self._planes_nhwc(planes)
@@ -494,6 +540,12 @@ class TriPlaneGenerator(torch.nn.Module):
 
     def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
                   use_cached_backbone=False, **synthesis_kwargs):
+        with on_device(ws):
+            return self._synthesis(ws, c, neural_rendering_resolution, update_emas, cache_backbone, use_cached_backbone,
+                                   **synthesis_kwargs)
+
+    def _synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
+                   use_cached_backbone=False, **synthesis_kwargs):
         cam2world_matrix = c[:, :16].view(-1, 4, 4)
         intrinsics = c[:, 16:25].view(-1, 3, 3)
         if neural_rendering_resolution is None:

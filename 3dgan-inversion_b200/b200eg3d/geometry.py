@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import ops
-from ._lib import call, ptr, stream
+from ._lib import call, on_device, ptr, stream
 
 
 def create_samples(N=256, voxel_origin=[0, 0, 0], cube_length=2.0, device='cuda'):
@@ -35,6 +35,11 @@ def create_samples(N=256, voxel_origin=[0, 0, 0], cube_length=2.0, device='cuda'
 @torch.no_grad()
 def query_sigma(G, ws, samples, max_batch=1 << 24, planes=None):
     """sigma [N, P, 1] of sample_mixed(samples, ., ws, noise_mode='const') for all P points; the backbone runs once."""
+    with on_device(ws):
+        return _query_sigma(G, ws, samples, max_batch, planes)
+
+
+def _query_sigma(G, ws, samples, max_batch, planes):
     if planes is None:
         planes = G.backbone.synthesis(ws, update_emas=False, noise_mode='const')
     pl = G.renderer._planes_nhwc(planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1]))

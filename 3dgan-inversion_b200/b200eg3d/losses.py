@@ -10,7 +10,7 @@ import ctypes
 
 import torch
 
-from ._lib import call, ptr, stream
+from ._lib import call, device_guard, ptr, stream
 
 
 def _strides(t):
@@ -26,6 +26,7 @@ def _dense_like_nchw(t):
 
 class _PTILoss(torch.autograd.Function):
     @staticmethod
+    @device_guard
     def forward(ctx, image, image_raw, image_depth, real, l2_lambda, tv_lambda):
         real = real.detach().to(torch.float32).contiguous()
         n, c, h, w = real.shape
@@ -49,6 +50,7 @@ class _PTILoss(torch.autograd.Function):
         return out[0].clone(), out
 
     @staticmethod
+    @device_guard
     def backward(ctx, dloss, _dparts):
         img, raw, dep, real = ctx.saved_tensors
         n, c, h, w, r, l2, tv = ctx.cfg

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import call, ptr, stream
+from ._lib import call, device_guard, ptr, stream
 
 _ACT = {'linear': (1, 0.0, 1.0), 'relu': (2, 0.0, math.sqrt(2)), 'lrelu': (3, 0.2, math.sqrt(2)), 'tanh': (4, 0.0, 1.0),
         'sigmoid': (5, 0.0, 1.0), 'elu': (6, 0.0, 1.0), 'selu': (7, 0.0, 1.0), 'softplus': (8, 0.0, 1.0),
@@ -86,6 +86,7 @@ def _conv_wgrad(x, dy, dwmod, n, h, w, cin, cout, k, up):
 
 class _BiasAct(torch.autograd.Function):
     @staticmethod
+    @device_guard
     def forward(ctx, x, b, dim, act, alpha, gain, clamp):
         code = _ACT[act][0]
         xc = _f32c(x)
@@ -100,6 +101,7 @@ class _BiasAct(torch.autograd.Function):
         return y
 
     @staticmethod
+    @device_guard
     def backward(ctx, dy):
         dim, act, alpha, gain, clamp, step, has_b = ctx.cfg
         xref, bref, yref = ctx.saved_tensors
@@ -184,6 +186,7 @@ def _upfirdn_nhwc_raw(x, f2, up, down, pad, flip, gain, add=None):
 
 class _UpfirdnNHWC(torch.autograd.Function):
     @staticmethod
+    @device_guard
     def forward(ctx, x, f2, up, down, pad, flip, gain):
         xc = _f32c(x)
         ctx.cfg = (up, down, pad, flip, gain, xc.shape)
@@ -191,6 +194,7 @@ class _UpfirdnNHWC(torch.autograd.Function):
         return _upfirdn_nhwc_raw(xc, f2, up, down, pad, flip, gain)
 
     @staticmethod
+    @device_guard
     def backward(ctx, dy):
         (f2,) = ctx.saved_tensors
         up, down, pad, flip, gain, xs = ctx.cfg
@@ -298,6 +302,7 @@ class _Bank(torch.autograd.Function):
     every layer's backward has stored its d wmod in bank.dwmod and turns them into parameter / latent gradients."""
 
     @staticmethod
+    @device_guard
     def forward(ctx, ws, bank, *params):
         ws = _f32c(ws)
         n, num_ws, w_dim = ws.shape
@@ -327,6 +332,7 @@ class _Bank(torch.autograd.Function):
         return torch.zeros([1], device=dev, dtype=torch.float32)
 
     @staticmethod
+    @device_guard
     def backward(ctx, _dtok):
         bank = ctx.bank
         (ws,) = ctx.saved_tensors
@@ -415,6 +421,7 @@ class _ModConvLayer(torch.autograd.Function):
     """
 
     @staticmethod
+    @device_guard
     def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp, token=None, bank=None, lidx=-1):
         ctx.set_materialize_grads(False)       # no zero-filled gradients for the non-differentiable bf16 outputs
         x = _f32c(x)
@@ -496,6 +503,7 @@ class _ModConvLayer(torch.autograd.Function):
         return z, z_hi, z_lo
 
     @staticmethod
+    @device_guard
     def backward(ctx, dz, _dhi, _dlo):
         if dz is None:
             return (None,) * 14
@@ -578,6 +586,7 @@ class _ToRGB(torch.autograd.Function):
     """
 
     @staticmethod
+    @device_guard
     def forward(ctx, x, x_hi, x_lo, weight, styles, bias, img_prev, clamp, token=None, bank=None, lidx=-1):
         ctx.set_materialize_grads(False)
         x = _f32c(x)
@@ -625,6 +634,7 @@ class _ToRGB(torch.autograd.Function):
         return img
 
     @staticmethod
+    @device_guard
     def backward(ctx, dimg):
         if dimg is None:
             return (None,) * 11
@@ -693,6 +703,7 @@ class _RunModel(torch.autograd.Function):
     """
 
     @staticmethod
+    @device_guard
     def forward(ctx, planes, coords, W1, b1, W2, b2, lr_mul, box_warp):
         pl = _f32c(planes)
         co = _f32c(coords)
@@ -708,6 +719,7 @@ class _RunModel(torch.autograd.Function):
         return rgb, sigma
 
     @staticmethod
+    @device_guard
     def backward(ctx, d_rgb, d_sigma):
         pl, co, W1, b1, W2, b2 = ctx.saved_tensors
         lr_mul, box_warp = ctx.cfg
@@ -738,26 +750,30 @@ class _Render(torch.autograd.Function):
     """
 
     @staticmethod
+    @device_guard
     def forward(ctx, planes, ray_o, ray_d, W1, b1, W2, b2, lr_mul, box_warp, t_base, delta, u_strat, u_imp, white_back,
-                density_noise):
+                density_noise, t_coarse=None):
         ctx.set_materialize_grads(False)
         pl = _f32c(planes)
         ro, rd = _f32c(ray_o), _f32c(ray_d)
         dev = pl.device
         n, hp, wp, _ = pl.shape
         M = ro.shape[1]
-        S = t_base.numel()
+        S = t_base.numel() if t_coarse is None else t_coarse.shape[2]
         S2 = 0 if u_imp is None else u_imp.shape[1]
         w = [_f32c(t) for t in (W1, b1, W2, b2)]
         st = stream()
-        t_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
-        call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), st)
+        if t_coarse is not None:          # per-ray limits / disparity sampling: depths prepared by the caller (renderer.py:230-242)
+            t_c = _f32c(t_coarse).reshape(n, M, S)
+        else:
+            t_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
+            call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), st)
         rgb_c = torch.empty([n, M, S, 32], device=dev, dtype=torch.float32)
         sig_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
         call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_c), S, M * S, float(box_warp),
              *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), st)
         if density_noise > 0:
-            sig_c += torch.randn_like(sig_c) * density_noise
+            sig_c += (torch.randn_like(sig_c.view(n, M * S, 1)) * density_noise).view(n, M, S)      # renderer.py:201-202 (same draw shape)
         minmax = torch.zeros([2], device=dev, dtype=torch.int32)
         minmax[:1].fill_(-1)                      # {0xFFFFFFFF, 0}: order-preserving uint encodings of +inf / -inf
         call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(minmax), st)
@@ -770,7 +786,7 @@ class _Render(torch.autograd.Function):
             call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_f), S2, M * S2, float(box_warp),
                  *map(ptr, w), float(lr_mul), ptr(rgb_f), ptr(sig_f), st)
             if density_noise > 0:
-                sig_f += torch.randn_like(sig_f) * density_noise
+                sig_f += (torch.randn_like(sig_f.view(n, M * S2, 1)) * density_noise).view(n, M, S2)
             call('b200_depth_minmax', ptr(t_f), t_f.numel(), ptr(minmax), st)
         feat = torch.empty([n, M, 32], device=dev, dtype=torch.float32)
         depth = torch.empty([n, M, 1], device=dev, dtype=torch.float32)
@@ -782,6 +798,7 @@ class _Render(torch.autograd.Function):
         return feat, depth, wsum
 
     @staticmethod
+    @device_guard
     def backward(ctx, d_feat, d_depth, d_wsum):
         pl, ro, rd, W1, b1, W2, b2, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax = ctx.saved_tensors
         lr_mul, box_warp, white_back, S, S2 = ctx.cfg
@@ -817,19 +834,21 @@ class _Render(torch.autograd.Function):
             if want_rays:                      # point = o + t*d  (renderer.py:161,178)
                 d_ro += d_pts.sum(2)
                 d_rd += (d_pts * t.unsqueeze(-1)).sum(2)
-        return (d_planes, d_ro, d_rd, *dws, None, None, None, None, None, None, None, None)
+        return (d_planes, d_ro, d_rd, *dws, None, None, None, None, None, None, None, None, None)
 
 
-def render(planes_nhwc, decoder, ray_o, ray_d, box_warp, t_base, delta, u_strat, u_imp, white_back=False, density_noise=0.0):
+def render(planes_nhwc, decoder, ray_o, ray_d, box_warp, t_base, delta, u_strat, u_imp, white_back=False, density_noise=0.0,
+           t_coarse=None):
     W1, b1, W2, b2, lr_mul = _decoder_params(decoder)
     return _Render.apply(planes_nhwc, ray_o, ray_d, W1, b1, W2, b2, lr_mul, box_warp, t_base, delta, u_strat, u_imp,
-                         white_back, density_noise)
+                         white_back, density_noise, t_coarse)
 
 
 class _RaySampler(torch.autograd.Function):
     """RaySampler.forward (ray_sampler.py:24-73) as one kernel; gradient to cam2world (the w-projection optimises the pose)."""
 
     @staticmethod
+    @device_guard
     def forward(ctx, cam2world, intrinsics, resolution):
         c2w = _f32c(cam2world).reshape(-1, 16)
         K = _f32c(intrinsics).reshape(-1, 9)
@@ -842,6 +861,7 @@ class _RaySampler(torch.autograd.Function):
         return ray_o, ray_d
 
     @staticmethod
+    @device_guard
     def backward(ctx, d_o, d_d):
         c2w, K = ctx.saved_tensors
         g = torch.zeros_like(c2w)

@@ -16,7 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import call, ptr, stream
+from ._lib import call, device_guard, ptr, stream
 
 _BIG = 3.0e38
 
@@ -29,6 +29,7 @@ class _WarpUV(torch.autograd.Function):
     """pred_uv [R*R, 2] of warping_loss.py:18-43 from (extrinsic, init_ext, intrinsic, depth); gradients to extrinsic and depth."""
 
     @staticmethod
+    @device_guard
     def forward(ctx, extrinsic, init_ext, intrinsic, depth, w2c):
         ext = _f32c(extrinsic).reshape(16)
         ini = _f32c(init_ext).reshape(16)
@@ -49,6 +50,7 @@ class _WarpUV(torch.autograd.Function):
         return uv, mn
 
     @staticmethod
+    @device_guard
     def backward(ctx, d_uv, _dmn):
         ext, ini, w2c, K, dep = ctx.saved_tensors
         d_ext = torch.zeros([16], device=dep.device, dtype=torch.float32)
@@ -146,6 +148,7 @@ def _sizes_dev(bufs):
 
 class _NoiseReg(torch.autograd.Function):
     @staticmethod
+    @device_guard
     def forward(ctx, *bufs):
         bs = [_f32c(b) for b in bufs]
         dev = bs[0].device
@@ -163,6 +166,7 @@ class _NoiseReg(torch.autograd.Function):
         return reg
 
     @staticmethod
+    @device_guard
     def backward(ctx, dreg):
         work, sums, *bs = ctx.saved_tensors
         sizes, sizes_p = _size_table(bs)
@@ -188,7 +192,7 @@ def normalize_noise_(noise_bufs):
     bufs = list(noise_bufs.values()) if isinstance(noise_bufs, dict) else list(noise_bufs)
     if not bufs:
         return
-    with torch.no_grad():
+    with torch.no_grad(), _lib.on_device(bufs[0]):
         for b in bufs:
             if b.dtype != torch.float32 or not b.is_contiguous():
                 raise RuntimeError('normalize_noise_: buffers must be contiguous fp32 (they are updated in place)')

@@ -42,21 +42,41 @@ def load_old_G(path, device='cuda'):
     return convert_generator(G_ref, device=device).float()
 
 
+def _plain(obj):
+    """Recursively turn dict subclasses (dnnlib.EasyDict), tuples and numpy scalars into plain dict / list / python scalars,
+    so that the checkpoint holds no class references and loads with torch.load(weights_only=True)."""
+    if isinstance(obj, dict):
+        return {str(k): _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().cpu()
+    if hasattr(obj, 'item') and not isinstance(obj, (str, bytes)):
+        try:
+            return obj.item()
+        except Exception:
+            pass
+    if obj is None or isinstance(obj, (bool, int, float, str)):
+        return obj
+    raise TypeError(f'cannot store {type(obj).__name__} in a tuned-generator checkpoint')
+
+
 def save_tuned_G(G, path):
     """Checkpoint of a (PTI-tuned) generator: constructor arguments + state_dict + the attributes callers set after loading.
     The reference never saves the tuned generator (single_id_coach.py:117 is commented out); this is the `state_dict` route
     SURVEY.md 8 f4 asks for.  Plain torch.save of tensors and python scalars -- no pickled code."""
-    torch.save({'format': 'b200eg3d.tuned_G.v1', 'init_args': tuple(G.init_args), 'init_kwargs': copy.deepcopy(dict(G.init_kwargs)),
+    torch.save({'format': 'b200eg3d.tuned_G.v1', 'init_args': _plain(list(G.init_args)), 'init_kwargs': _plain(dict(G.init_kwargs)),
                 'state_dict': {k: v.detach().cpu() for k, v in G.state_dict().items()},
                 'neural_rendering_resolution': int(G.neural_rendering_resolution),
-                'rendering_kwargs': copy.deepcopy(dict(G.rendering_kwargs))}, path)
+                'rendering_kwargs': _plain(dict(G.rendering_kwargs))}, path)
 
 
 def load_tuned_G(path, device='cuda'):
-    ck = torch.load(path, map_location='cpu', weights_only=False)
+    ck = torch.load(path, map_location='cpu', weights_only=True)         # tensors + plain containers only: no pickled code runs
     if ck.get('format') != 'b200eg3d.tuned_G.v1':
         raise ValueError(f'{path} is not a b200eg3d tuned-generator checkpoint')
     G = TriPlaneGenerator(*ck['init_args'], **ck['init_kwargs']).eval().requires_grad_(False)
+    G.init_kwargs['rendering_kwargs'] = ck['rendering_kwargs']
     G.load_state_dict(ck['state_dict'], strict=True)
     G.neural_rendering_resolution = ck['neural_rendering_resolution']
     G.rendering_kwargs = ck['rendering_kwargs']

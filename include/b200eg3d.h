@@ -3,7 +3,10 @@
  *
  * Conventions (every entry point):
  *   - plain pointers and sizes only; all pointers are DEVICE pointers of the current CUDA device unless noted
- *   - nothing is allocated, nothing synchronises, no global state: the caller owns inputs, outputs and workspaces
+ *   - nothing is allocated, nothing synchronises: the caller owns inputs, outputs and workspaces.  The only process-wide
+ *     state are the three tuning switches below (b200_set_*) and per-DEVICE one-time launch attributes / SM counts (keyed by
+ *     cudaGetDevice(), so several GPUs can be driven from one process); entry points are re-entrant across streams and devices
+ *   - the CALLER makes the pointers' device current (cudaSetDevice) before the call -- the Python wrapper does so per call
  *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and the call returns immediately
  *   - returns 0 on success; non-zero on error, with a message available from b200_last_error() (thread-local)
  *   - activations are NHWC fp32: x[n][h][w][c]; modulated weights are wmod[n][tap][cout][cin], tap = kh*ksize + kw
@@ -23,6 +26,10 @@ int b200_version(void);                 /* replaces the plugin identity of torch
 const char* b200_last_error(void);      /* replaces TORCH_CHECK -> RuntimeError text, torch_utils/ops/bias_act.cpp:39-55 */
 int b200_set_pdl(int on);               /* programmatic dependent launch of the conv / epilogue / FIR kernels on (default; env
                                            B200EG3D_PDL=0 disables) or off; returns the previous setting.  Profiling aid. */
+
+int b200_set_mlp_passes(int passes);    /* operand passes of the fused decoder MLP forward: 3 = split operands, fp32-equivalent (default;
+                                           env B200EG3D_MLP_PASSES=1 selects 1), 1 = single pass ("fast mode", non-parity).
+                                           Returns the previous setting. */
 
 /* ---- modulated convolution (training/networks_stylegan2.py:34-91 modulated_conv2d, fused path) ---------------- */
 

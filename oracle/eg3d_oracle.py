@@ -233,10 +233,15 @@ def osg_decoder(P, feats, lr_mul=1.0, pre='decoder.net.'):
     return rgb, o[..., 0:1]
 
 
-def run_model(P, planes, coords, rk):
-    """renderer.py:197-203 (density_noise == 0)."""
+def run_model(P, planes, coords, rk, density_draw=None):
+    """renderer.py:197-203.  density_draw: the standard-normal tensor the reference draws with randn_like(sigma) when
+    rendering_kwargs['density_noise'] > 0 (:201-202); None = no density noise."""
     feats = sample_triplane_features(planes, coords, rk['box_warp'])
-    return osg_decoder(P, feats, rk.get('decoder_lr_mul', 1))
+    rgb, sigma = osg_decoder(P, feats, rk.get('decoder_lr_mul', 1))
+    if rk.get('density_noise', 0) > 0:
+        assert density_draw is not None, 'density_noise > 0 needs the randn_like draw'
+        sigma = sigma + density_draw.reshape(sigma.shape).to(sigma.dtype) * rk['density_noise']
+    return rgb, sigma
 
 
 # ----------------------------------------------------------------------------
@@ -260,10 +265,38 @@ def ray_march(colors, densities, depths, white_back=False):
     return rgb * 2 - 1, depth, weights
 
 
-def stratified_depths(n, m, s, ray_start, ray_end, u, dtype):
-    """renderer.py:224-247, non-disparity, scalar limits: linspace + U[0,1)*delta."""
+def ray_limits_box(ray_o, ray_d, box_side_length):
+    """math_utils.py:46-98 (get_ray_limits_box): slab intersection of every ray with the cube of side box_side_length about
+    the origin; (-1, -2) marks a miss.  Restated with where() instead of index_select / masked assignment."""
+    o, d = ray_o.detach().reshape(-1, 3), ray_d.detach().reshape(-1, 3)
+    half = box_side_length / 2
+    inv = 1 / d
+    neg = inv < 0
+    lo = torch.where(neg, torch.full_like(o, half), torch.full_like(o, -half))       # bounds[sign]
+    hi = torch.where(neg, torch.full_like(o, -half), torch.full_like(o, half))       # bounds[1 - sign]
+    t0, t1 = (lo - o) * inv, (hi - o) * inv
+    tmin, tmax = t0[:, 0], t1[:, 0]
+    valid = ~((tmin > t1[:, 1]) | (t0[:, 1] > tmax))
+    tmin, tmax = torch.max(tmin, t0[:, 1]), torch.min(tmax, t1[:, 1])
+    valid = valid & ~((tmin > t1[:, 2]) | (t0[:, 2] > tmax))
+    tmin, tmax = torch.max(tmin, t0[:, 2]), torch.min(tmax, t1[:, 2])
+    tmin = torch.where(valid, tmin, torch.full_like(tmin, -1))
+    tmax = torch.where(valid, tmax, torch.full_like(tmax, -2))
+    return tmin.reshape(*ray_o.shape[:-1], 1), tmax.reshape(*ray_o.shape[:-1], 1)
+
+
+def stratified_depths(n, m, s, ray_start, ray_end, u, dtype, disparity=False):
+    """renderer.py:224-247 (sample_stratified): scalar limits, per-ray tensor limits ('auto'), or disparity-space sampling."""
+    u = u.to(dtype)
+    if disparity:
+        t = torch.linspace(0, 1, s).to(dtype).reshape(1, 1, s, 1).repeat(n, m, 1, 1) + u * (1 / (s - 1))
+        return 1. / (1. / ray_start * (1. - t) + 1. / ray_end * t)
+    if isinstance(ray_start, torch.Tensor):                                          # [N,M,1] each
+        steps = (torch.arange(s, dtype=torch.float32) / (s - 1)).to(dtype).reshape(1, 1, s, 1)
+        t = ray_start.unsqueeze(2) + steps * (ray_end - ray_start).unsqueeze(2)
+        return t + u * ((ray_end - ray_start) / (s - 1)).unsqueeze(-1)
     t = torch.linspace(ray_start, ray_end, s).to(dtype).reshape(1, 1, s, 1).repeat(n, m, 1, 1)
-    return t + u.to(dtype) * ((ray_end - ray_start) / (s - 1))
+    return t + u * ((ray_end - ray_start) / (s - 1))
 
 
 def importance_depths(depths, weights, n_imp, u, eps=1e-5):
@@ -290,13 +323,20 @@ def importance_depths(depths, weights, n_imp, u, eps=1e-5):
         return t.reshape(n, m, n_imp, 1)
 
 
-def render(P, planes, ray_o, ray_d, rk, u_strat, u_imp):
-    """renderer.py:143-195 (ImportanceRenderer.forward) for numeric ray_start/ray_end."""
+def render(P, planes, ray_o, ray_d, rk, u_strat, u_imp, density_draws=(None, None)):
+    """renderer.py:143-195 (ImportanceRenderer.forward).  density_draws: the (coarse, fine) randn_like draws of :201-202."""
     n, m, _ = ray_o.shape
     s = rk['depth_resolution']
-    t_c = stratified_depths(n, m, s, rk['ray_start'], rk['ray_end'], u_strat, ray_o.dtype)
+    ray_start, ray_end = rk['ray_start'], rk['ray_end']
+    if ray_start == 'auto' and ray_end == 'auto':                                    # renderer.py:146-152
+        ray_start, ray_end = ray_limits_box(ray_o, ray_d, rk['box_warp'])
+        ok = ray_end > ray_start
+        if bool(ok.any()):
+            ray_start = torch.where(ok, ray_start, ray_start[ok].min())
+            ray_end = torch.where(ok, ray_end, ray_start[ok].max())
+    t_c = stratified_depths(n, m, s, ray_start, ray_end, u_strat, ray_o.dtype, rk.get('disparity_space_sampling', False))
     pts = (ray_o.unsqueeze(-2) + t_c * ray_d.unsqueeze(-2)).reshape(n, -1, 3)
-    rgb_c, sig_c = run_model(P, planes, pts, rk)
+    rgb_c, sig_c = run_model(P, planes, pts, rk, density_draws[0])
     rgb_c = rgb_c.reshape(n, m, s, -1)
     sig_c = sig_c.reshape(n, m, s, 1)
     n_imp = rk['depth_resolution_importance']
@@ -305,7 +345,7 @@ def render(P, planes, ray_o, ray_d, rk, u_strat, u_imp):
         _, _, w_c = ray_march(rgb_c, sig_c, t_c, wb)
         t_f = importance_depths(t_c, w_c, n_imp, u_imp)
         pts = (ray_o.unsqueeze(-2) + t_f * ray_d.unsqueeze(-2)).reshape(n, -1, 3)
-        rgb_f, sig_f = run_model(P, planes, pts, rk)
+        rgb_f, sig_f = run_model(P, planes, pts, rk, density_draws[1])
         rgb_f = rgb_f.reshape(n, m, n_imp, -1)
         sig_f = sig_f.reshape(n, m, n_imp, 1)
         t_all = torch.cat([t_c, t_f], -2)
@@ -322,23 +362,30 @@ def render(P, planes, ray_o, ray_d, rk, u_strat, u_imp):
 # ----------------------------------------------------------------------------
 # Whole generator (training/triplane.py:53-90)
 
-def draw_depth_noise(seed, n, m, s, s_imp):
-    """The two RNG draws the renderer makes, in order (renderer.py:245 rand_like [N,M,S,1]; :292 rand [N*M,S_imp])."""
+def draw_depth_noise(seed, n, m, s, s_imp, tensor_limits=False):
+    """The two RNG draws the renderer makes, in order (renderer.py:245 rand_like [N,M,S,1]; :292 rand [N*M,S_imp]).
+    tensor_limits ('auto' ray limits, renderer.py:240-242): depths_coarse is a permuted view of a [S,N,M,1] tensor there and
+    rand_like preserves that memory layout, so the draws fill [S,N,M,1] order and are read as [N,M,S,1]."""
     g = torch.Generator().manual_seed(seed)
-    return torch.rand(n, m, s, 1, generator=g), torch.rand(n * m, s_imp, generator=g)
+    if tensor_limits:
+        u1 = torch.rand(s, n, m, 1, generator=g).permute(1, 2, 0, 3).contiguous()
+    else:
+        u1 = torch.rand(n, m, s, 1, generator=g)
+    return u1, torch.rand(n * m, s_imp, generator=g)
 
 
 def synthesis(P, ws, c, rk, neural_rendering_resolution, u_strat, u_imp, noise_mode='const',
-              conv_clamp=256, return_planes=False):
-    """TriPlaneGenerator.synthesis (triplane.py:53-90) with force_fp32=True semantics."""
+              conv_clamp=256, return_planes=False, noise_random=None, density_draws=(None, None)):
+    """TriPlaneGenerator.synthesis (triplane.py:53-90) with force_fp32=True semantics.
+    noise_random: {layer prefix -> [N,1,res,res] standard-normal draw} for noise_mode='random' (networks_stylegan2.py:319)."""
     n = ws.shape[0]
     r = neural_rendering_resolution
     cam2world = c[:, :16].reshape(-1, 4, 4)
     intr = c[:, 16:25].reshape(-1, 3, 3)
     ray_o, ray_d = ray_sampler(cam2world, intr, r)
-    planes96 = backbone_synthesis(P, ws, noise_mode=noise_mode, conv_clamp=conv_clamp)
+    planes96 = backbone_synthesis(P, ws, noise_mode=noise_mode, conv_clamp=conv_clamp, noise_random=noise_random)
     planes = planes96.reshape(n, 3, 32, planes96.shape[-2], planes96.shape[-1])
-    feat, depth, _ = render(P, planes, ray_o, ray_d, rk, u_strat, u_imp)
+    feat, depth, _ = render(P, planes, ray_o, ray_d, rk, u_strat, u_imp, density_draws)
     feat_img = feat.permute(0, 2, 1).reshape(n, feat.shape[-1], r, r)
     depth_img = depth.permute(0, 2, 1).reshape(n, 1, r, r)
     rgb = feat_img[:, :3]

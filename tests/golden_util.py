@@ -8,15 +8,15 @@ import torch
 import eg3d_oracle as oracle
 import synth_params as sp
 
-# must mirror oracle/make_goldens.py CASES (G kwargs, rendering overrides)
-CASE_CFG = {
-    'tiny_r64_s16': (sp.G_KWARGS_TINY, {}),
-    'tiny_r32_s8_n2_white': (sp.G_KWARGS_TINY, {'white_back': True}),
-    'tiny_r64_s12_noimp': (sp.G_KWARGS_TINY, {}),
-    'full_r64_s16': (sp.G_KWARGS_FULL, {}),
-    'full_r128_s48': (sp.G_KWARGS_FULL, {}),
-    'full_r256_s96': (sp.G_KWARGS_FULL, {}),
-}
+CASE_CFG = sp.GOLDEN_CASES          # shared with oracle/make_goldens.py
+
+
+def manifest(arch, golden_dir=None):
+    """name -> shape of every parameter and buffer of the REAL reference TriPlaneGenerator (recorded by make_goldens.py)."""
+    import json
+    golden_dir = golden_dir or os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+    with open(os.path.join(golden_dir, f'manifest_{arch}.json')) as f:
+        return json.load(f)
 
 
 def param_shapes(gk):
@@ -58,17 +58,74 @@ def load_case(golden_dir, name):
     fx = dict(np.load(os.path.join(golden_dir, name + '.npz'), allow_pickle=False))
     R, S, S_imp, N, yaw, pitch, pseed, wseed, nseed, tseed = fx['meta']
     R, S, S_imp, N = int(R), int(S), int(S_imp), int(N)
-    gk, over = CASE_CFG[name]
-    case = types.SimpleNamespace(name=name, fx=fx, R=R, S=S, S_imp=S_imp, N=N, gk=gk, param_seed=int(pseed))
+    cfg = CASE_CFG[name]
+    gk, over = sp.G_KWARGS[cfg['arch']], cfg.get('rk', {})
+    assert (R, S, S_imp, N) == (cfg['R'], cfg['S'], cfg['S_imp'], cfg['N']), 'fixture and case table disagree'
+    case = types.SimpleNamespace(name=name, fx=fx, R=R, S=S, S_imp=S_imp, N=N, gk=gk, arch=cfg['arch'], param_seed=int(pseed),
+                                 noise_mode=cfg.get('noise_mode', 'const'), has_grads=bool(cfg['bwd']))
     case.rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_imp, **over)
     case.ws = sp.latent_ws(int(wseed), n=N)
-    case.c = sp.camera(yaw, pitch, n=N)
-    if N > 1:
-        case.c[1] = sp.camera(-yaw, pitch * 0.5)[0]
-    case.u_strat, case.u_imp = oracle.draw_depth_noise(int(nseed), N, R * R, S, max(S_imp, 1))
+    case.c = sp.case_camera(cfg)
+    case.u_strat, case.u_imp = oracle.draw_depth_noise(int(nseed), N, R * R, S, max(S_imp, 1),
+                                                       tensor_limits=(case.rk['ray_start'] == 'auto'))
     t512, t_raw = sp.targets(int(tseed), R)
     case.t512, case.t_raw = t512.expand(N, -1, -1, -1), t_raw.expand(N, -1, -1, -1)
+    import json
+    case.randn_seed = int(fx['randn_seed'][0])
+    case.randn_shapes = json.loads(str(fx['randn_shapes']))
     return case
+
+
+def oracle_noise_args(case):
+    """(noise_random, density_draws) for oracle.synthesis on this case (None, (None, None) for the const-noise cases)."""
+    return sp.replay_normal_draws(case.randn_seed, case.randn_shapes, case.gk)
+
+
+def check_image(img, fx, tol):
+    """Compare a full [N,3,512,512] image with the fixture: every second pixel at `tol` and ALL pixels through 16x16 tile sums."""
+    img = img.detach().double().cpu()
+    d_sub = float((img[..., ::2, ::2].float().numpy() - fx['image_sub2']).__abs__().max())
+    n, c, h, w = img.shape
+    tiles = img.reshape(n, c, h // 16, 16, w // 16, 16).sum(dim=(3, 5)).numpy()
+    d_tile = float(np.abs(tiles - fx['image_tile16']).max()) / 256.0          # mean abs deviation per pixel of the worst tile
+    return d_sub, d_tile
+
+
+def check_param_grads(named_grads, fx, tol, scalar_floor=5e-2):
+    """Per-parameter comparison against the fixture's channel-resolved summaries.  Returns the worst relative deviations
+    (per-output-channel norms, per-input-channel norms, strided samples) and asserts each is within `tol`.
+    0-dim gradients (noise_strength: single cancellation-dominated sums over a whole activation map) are compared on the
+    scale of the largest such scalar in the network."""
+    names = [str(n) for n in fx['grad_names']]
+    off = fx['grad_off']
+    o0 = i0 = s0 = 0
+    worst = {'oc': 0.0, 'ic': 0.0, 'samp': 0.0}
+    scal = max([float(np.sqrt(fx['grad_mom'][k][1])) for k, n in enumerate(names) if off[k][0] == 1 and off[k][1] == 0 and off[k][2] == 1] + [0.0])
+    for k, n in enumerate(names):
+        no, ni, ns = (int(v) for v in off[k])
+        ref_oc, ref_ic, ref_s = fx['grad_oc'][o0:o0 + no], fx['grad_ic'][i0:i0 + ni], fx['grad_samp'][s0:s0 + ns].astype(np.float64)
+        o0, i0, s0 = o0 + no, i0 + ni, s0 + ns
+        g = named_grads[n]
+        assert g is not None, f'{n}: no gradient'
+        oc, ic, smp = sp.grad_slices(g)
+        assert oc.shape == ref_oc.shape and ic.shape == ref_ic.shape and smp.shape == ref_s.shape, n
+        if g.ndim == 0:
+            assert abs(oc[0] - ref_oc[0]) <= tol * max(ref_oc[0], scalar_floor * scal), (n, oc[0], ref_oc[0])
+            continue
+        rms = float(np.sqrt(fx['grad_mom'][k][1] / max(g.numel(), 1)))
+        # channel norms: relative to the channel's own norm, floored at 20 % of the tensor's typical channel norm
+        for key, a, b in (('oc', oc, ref_oc), ('ic', ic, ref_ic)):
+            if b.size == 0:
+                continue
+            floor = 0.2 * float(np.sqrt((b ** 2).mean()))
+            dev = float(np.max(np.abs(a - b) / np.maximum(b, max(floor, 1e-30))))
+            worst[key] = max(worst[key], dev)
+            assert dev <= 2 * tol, (n, key, dev)
+        # strided sample: rel-L2 over the sample (element-wise agreement, not just norms)
+        dev = float(np.linalg.norm(smp - ref_s) / max(np.linalg.norm(ref_s), 1e-30 + rms * 1e-6))
+        worst['samp'] = max(worst['samp'], dev)
+        assert dev <= 2 * tol, (n, 'samp', dev)
+    return worst
 
 
 def build_param_dict(case, requires_grad=False):

@@ -29,13 +29,13 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 20
     for s in syms:
         assert hasattr(lib, s), f'{s} declared in include/b200eg3d.h but not exported'
-    assert lib.b200_version() >= 100
+    assert lib.b200_version() == _lib.EXPECTED_VERSION
 
 
 def test_ctypes_table_matches_header():
     from b200eg3d import _lib
     syms = set(declared_symbols())
-    bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes',
+    bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_set_mlp_passes', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes',
                                         'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable'}
     assert syms == bound, (sorted(syms - bound), sorted(bound - syms))
     src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
@@ -56,14 +56,23 @@ def test_shape_support_query_needs_no_gpu():
     assert lib.b200_set_pdl(prev) == 0 and lib.b200_set_pdl(prev) == prev
 
 
-def test_module_tree_mirrors_reference_names():
+@pytest.mark.parametrize('arch', ['tiny', 'full'])
+def test_module_tree_mirrors_reference_names(arch):
+    """Names and shapes of EVERY parameter and buffer (incl. backbone.mapping.*) equal the manifest recorded from the real
+    reference class by oracle/make_goldens.py; the hand-written mirror used by the oracle agrees with it too."""
     import b200eg3d
     import synth_params as sp
-    from golden_util import param_shapes
-    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=sp.rendering_kwargs(), **sp.G_KWARGS_TINY)
-    mine = {k: tuple(v.shape) for k, v in list(G.named_parameters()) + list(G.named_buffers())}
-    for k, shp in param_shapes(sp.G_KWARGS_TINY).items():
-        assert mine.get(k) == tuple(shp), (k, shp, mine.get(k))
+    from golden_util import manifest, param_shapes
+    man = manifest(arch)
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=sp.rendering_kwargs(), **sp.G_KWARGS[arch])
+    assert {k: list(v.shape) for k, v in G.named_parameters()} == man['parameters']
+    assert {k: list(v.shape) for k, v in G.named_buffers()} == man['buffers']
+    assert G.backbone.num_ws == man['num_ws']
+    ref = dict(man['parameters'], **man['buffers'])
+    for k, shp in param_shapes(sp.G_KWARGS[arch]).items():
+        assert ref.get(k) == list(shp), (k, shp, ref.get(k))
+    if arch == 'full':
+        return
     assert [n for n, _ in G.named_children()] == ['renderer', 'ray_sampler', 'backbone', 'superresolution', 'decoder']
     assert G.backbone.num_ws == 14 and G.init_kwargs['img_resolution'] == 512
     noise = [n for n, _ in G.backbone.synthesis.named_buffers() if 'noise_const' in n]       # w_projector.py:103-104
@@ -80,16 +89,90 @@ def test_no_cpu_fallback():
         G.synthesis(sp.latent_ws(1), sp.camera())
 
 
+class _ManifestModule(torch.nn.Module):
+    """Stand-in for an un-pickled reference generator: exposes exactly the manifest's named parameters / buffers plus
+    init_args / init_kwargs / rendering_kwargs -- everything seam.convert_generator reads (gen_samples.py:146-152)."""
+
+    def __init__(self, man, gk, rk):
+        super().__init__()
+        self.init_args, self.init_kwargs = (), dict(gk, rendering_kwargs=rk)
+        self.rendering_kwargs, self.neural_rendering_resolution = rk, 96
+        for kind, reg in (('parameters', self._reg_p), ('buffers', self._reg_b)):
+            for name, shape in man[kind].items():
+                reg(name, torch.zeros(shape))
+
+    def _leaf(self, name):
+        mod = self
+        *path, leaf = name.split('.')
+        for p in path:
+            if not hasattr(mod, p):
+                mod.add_module(p, torch.nn.Module())
+            mod = getattr(mod, p)
+        return mod, leaf
+
+    def _reg_p(self, name, t):
+        mod, leaf = self._leaf(name)
+        mod.register_parameter(leaf, torch.nn.Parameter(t))
+
+    def _reg_b(self, name, t):
+        mod, leaf = self._leaf(name)
+        mod.register_buffer(leaf, t)
+
+
 def test_seam_copies_by_name():
+    """convert_generator against a module carrying the REAL reference's name/shape manifest (incl. backbone.mapping.*)."""
     import b200eg3d
     import synth_params as sp
-    src = b200eg3d.TriPlaneGenerator(rendering_kwargs=sp.rendering_kwargs(), **sp.G_KWARGS_TINY)
+    from golden_util import manifest
+    rk = sp.rendering_kwargs()
+    src = _ManifestModule(manifest('tiny'), sp.G_KWARGS_TINY, rk)
     sp.fill_params_(dict(list(src.named_parameters()) + list(src.named_buffers())), 3)
-    src.neural_rendering_resolution = 96
+    with torch.no_grad():
+        src.backbone.mapping.w_avg.normal_()
     dst = b200eg3d.seam.convert_generator(src, device='cpu')
-    for (n1, p1), (n2, p2) in zip(sorted(src.state_dict().items()), sorted(dst.state_dict().items())):
-        assert n1 == n2 and torch.equal(p1, p2)
+    a, b = src.state_dict(), dst.state_dict()
+    assert sorted(a) == sorted(b)
+    for n in a:
+        assert torch.equal(a[n], b[n]), n
     assert dst.neural_rendering_resolution == 96 and dst.rendering_kwargs is src.rendering_kwargs
+    # a source lacking a tensor the destination has must fail loudly (misc.copy_params_and_buffers(require_all=True))
+    man = manifest('tiny')
+    man['parameters'].pop('decoder.net.2.bias')
+    with pytest.raises(KeyError):
+        b200eg3d.seam.convert_generator(_ManifestModule(man, sp.G_KWARGS_TINY, rk), device='cpu')
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/training'), reason='the reference tree only exists in the build container')
+def test_seam_converts_the_real_reference_class():
+    """Build container only: the unmodified reference TriPlaneGenerator -> b200eg3d, misc.copy_params_and_buffers semantics."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path[:0] = [%r, %r, '/root/reference'];"
+        "import synth_params as sp; import b200eg3d;"
+        "from training.triplane import TriPlaneGenerator as Ref;"
+        "import dnnlib;"
+        "rk = dnnlib.EasyDict(sp.rendering_kwargs());"
+        "G = Ref(rendering_kwargs=rk, **sp.G_KWARGS_TINY).eval();"
+        "sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), 3);"
+        "G.neural_rendering_resolution = 128;"
+        "D = b200eg3d.seam.convert_generator(G, device='cpu');"
+        "a, b = G.state_dict(), D.state_dict();"
+        "assert sorted(a) == sorted(b), 'names differ';"
+        "assert all(torch.equal(a[k], b[k]) for k in a);"
+        "b200eg3d.seam.save_tuned_G(D, sys.argv[1]);"
+        "print('converted', len(a))"
+    ) % (os.path.join(ROOT, '3dgan-inversion_b200'), os.path.join(ROOT, 'oracle'))
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'g.pt')
+        r = subprocess.run([sys.executable, '-c', code, path], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        assert 'converted' in r.stdout
+        # the checkpoint written from an EasyDict-carrying generator loads WITHOUT dnnlib importable and with weights_only=True
+        import b200eg3d
+        G2 = b200eg3d.seam.load_tuned_G(path, device='cpu')
+        assert G2.neural_rendering_resolution == 128 and type(G2.rendering_kwargs) is dict
 
 
 def test_shard_indices():

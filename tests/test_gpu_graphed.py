@@ -1,0 +1,113 @@
+"""The execution mode bench.py times -- the whole optimisation step replayed as a CUDA graph (graphs.GraphedStep: two stream
+branches, programmatic dependent launch, capturable fused Adam) -- against the plain eager loop from the same state:
+loss trajectory and EVERY parameter after three steps.  A stale static input, a missed cross-stream edge or a gradient that
+is accumulated instead of overwritten on replay would show up here.
+
+Tolerances: the two modes run the same kernels on the same data; split-K and scatter reductions use floating-point atomics,
+so single steps agree to ~1e-6 relative, and Adam's m / sqrt(v) turns a sign flip of a near-zero gradient into a 2*lr
+difference of that element -- compared as relative L2 per tensor (1e-4), not element-wise."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import synth_params as sp
+from golden_util import load_case, stage1_feature_net
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _build(case):
+    import b200eg3d
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=case.rk, **case.gk).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), case.param_seed)
+    G = G.cuda().float()
+    G.neural_rendering_resolution = case.R
+    G.renderer.fixed_noise = (case.u_strat.cuda(), case.u_imp.cuda())
+    return G
+
+
+@pytest.mark.parametrize('name', ['tiny_r64_s16', 'full_r64_s16'])
+def test_graphed_pti_step_equals_eager(name, golden_dir):
+    from b200eg3d.coach import PTIStep
+    case = load_case(golden_dir, name)
+    Ga = _build(case)
+    Gb = copy.deepcopy(Ga)
+    ws, c, real = case.ws.cuda(), case.c.cuda(), case.t512.cuda().contiguous()
+    eager = PTIStep(Ga, graphed=False)
+    graph = PTIStep(Gb, graphed=True, example=(ws, c, real))
+    # the graph's warm-up ran optimizer steps on Gb: restore the common start state (parameters and Adam moments)
+    with torch.no_grad():
+        for pa, pb in zip(eager.params, graph.params):
+            pb.copy_(pa)
+    for st in graph.opt.state.values():
+        st['exp_avg'].zero_(); st['exp_avg_sq'].zero_(); st['step'].zero_()
+    la, lb = [], []
+    for i in range(3):
+        # a different latent every step: a replay that kept reading a stale static input would diverge immediately
+        wsi = ws + 0.05 * i
+        la.append(eager.step(wsi, c, real).item())
+        lb.append(graph.step(wsi, c, real).item())
+    print(name, 'loss eager', la, 'graph', lb)
+    assert la[0] != la[1]
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-4 * abs(a), (la, lb)
+    worst = max(_rel(pb, pa) for pa, pb in zip(eager.params, graph.params))
+    moved = max((pa - p0).abs().max().item() for pa, p0 in zip(eager.params, [p for n, p in _build(case).named_parameters() if '.mapping.' not in n]))
+    print(name, 'worst parameter rel-L2 after 3 steps', worst, 'largest update', moved)
+    assert moved > 1e-4                       # the optimiser really moved the weights
+    assert worst < 1e-4
+
+
+def test_graphed_projection_step_equals_eager(golden_dir):
+    """Stage-1 iteration (w_projector.py:160-268) in both launch modes: loss trajectory, latent, pose, translation and all
+    17 noise buffers after three iterations."""
+    import b200eg3d
+    from b200eg3d import projector
+    from b200eg3d.coach import ProjectionStep, projection_schedule
+    case = load_case(golden_dir, 'tiny_r64_s16')
+
+    def make(graphed):
+        G = _build(case)
+        G.renderer.fixed_noise = (case.u_strat.cuda(), case.u_imp.cuda())
+        for m in G.modules():
+            if hasattr(m, 'noise_strength'):
+                m.noise_strength.data.fill_(0.05)
+        pose6d = torch.tensor([[1.0, 0.05, 0.0, 0.02, -1.0, 0.03]], device='cuda', requires_grad=True)
+        c0 = sp.camera(0.0, 0.0).cuda()
+        vgg, tv = stage1_feature_net(11).cuda(), stage1_feature_net(12).cuda()
+        target = (torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(4)) * 2 - 1).cuda()
+        st = ProjectionStep(G, sp.latent_ws(1)[:, :1].cuda(), [pose6d], lambda: projector.rot6d_to_rotmat(pose6d),
+                            c0[:, :16].reshape(1, 4, 4).contiguous(), c0[0, 16:25].contiguous(), target, vgg, tv, graphed=graphed, seed=3)
+        return st, pose6d
+
+    a, pa = make(False)
+    b, pb = make(True)
+    # common start state after the graph's warm-up iterations
+    with torch.no_grad():
+        b.w_opt.copy_(a.w_opt); b.translation_opt.copy_(a.translation_opt); pb.copy_(pa)
+        for (na, ba), (nb, bb) in zip(list(a.noise_bufs.items()) + list(a.noise_bufs2.items()), list(b.noise_bufs.items()) + list(b.noise_bufs2.items())):
+            bb.copy_(ba)
+    for o in (b.optimizer, b.cam_optimizer, b.translation_optimizer):
+        for st in o.state.values():
+            st['exp_avg'].zero_(); st['exp_avg_sq'].zero_(); st['step'].zero_()
+    la, lb = [], []
+    g = torch.Generator().manual_seed(9)
+    for i in range(3):
+        lr, scale = projection_schedule(i + 20, 400, 1.0)
+        noise = (torch.randn(1, 1, 512, generator=g) * scale).cuda()
+        la.append(a.step(noise, lr=lr).item())
+        lb.append(b.step(noise, lr=lr).item())
+    print('stage-1 loss eager', la, 'graph', lb)
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 1e-4 * abs(x)
+    assert _rel(b.w_opt, a.w_opt) < 1e-4 and _rel(pb, pa) < 1e-4
+    assert (b.translation_opt - a.translation_opt).abs().max().item() < 1e-6
+    for (n, ba), bb in zip(list(a.noise_bufs.items()) + list(a.noise_bufs2.items()), list(b.noise_bufs.values()) + list(b.noise_bufs2.values())):
+        assert _rel(bb, ba) < 1e-4, n
