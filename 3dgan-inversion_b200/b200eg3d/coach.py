@@ -102,6 +102,7 @@ class ProjectionStep:
             self.target_features = feature_fn(t255)
         self.feature_fn, self.torch_vgg, self.reg_w = feature_fn, torch_vgg, regularize_noise_weight
         self.parts = None
+        self.graph = None              # _eager runs during the warm-up / capture below
         self.graph = GraphedStep(self._eager, [torch.zeros_like(self.w_opt)], optimizer=self, warmup=3) if graphed else None
 
     def zero_grad(self, set_to_none=True):

@@ -91,15 +91,27 @@ def check_image(img, fx, tol):
     return d_sub, d_tile
 
 
-def check_param_grads(named_grads, fx, tol, scalar_floor=5e-2):
-    """Per-parameter comparison against the fixture's channel-resolved summaries.  Returns the worst relative deviations
-    (per-output-channel norms, per-input-channel norms, strided samples) and asserts each is within `tol`.
+def check_param_grads(named_grads, fx, tol, scalar_floor=0.1, do_assert=True):
+    """Per-parameter comparison against the fixture's channel-resolved summaries.  For every gradient tensor:
+      'oc' / 'ic'  relative L2 of the vector of per-output-channel (per-input-channel) norms            <= tol
+      'chan'       worst single channel norm, relative to max(its reference, 20 % of the typical one)   <= 10 tol
+                   (structural check: a permuted / dropped channel block deviates by O(1))
+      'samp'       relative L2 over the strided element sample (element-wise agreement)                  <= 2 tol
     0-dim gradients (noise_strength: single cancellation-dominated sums over a whole activation map) are compared on the
-    scale of the largest such scalar in the network."""
+    scale of the largest such scalar in the network.  Returns {metric: (worst value, parameter name)}."""
     names = [str(n) for n in fx['grad_names']]
     off = fx['grad_off']
     o0 = i0 = s0 = 0
-    worst = {'oc': 0.0, 'ic': 0.0, 'samp': 0.0}
+    worst = {'oc': (0.0, ''), 'ic': (0.0, ''), 'chan': (0.0, ''), 'samp': (0.0, '')}
+    limit = {'oc': tol, 'ic': tol, 'chan': 10 * tol, 'samp': 2 * tol}
+    fails = []
+
+    def note(key, dev, n):
+        if dev > worst[key][0]:
+            worst[key] = (dev, n)
+        if dev > limit[key]:
+            fails.append((n, key, dev))
+
     scal = max([float(np.sqrt(fx['grad_mom'][k][1])) for k, n in enumerate(names) if off[k][0] == 1 and off[k][1] == 0 and off[k][2] == 1] + [0.0])
     for k, n in enumerate(names):
         no, ni, ns = (int(v) for v in off[k])
@@ -110,21 +122,19 @@ def check_param_grads(named_grads, fx, tol, scalar_floor=5e-2):
         oc, ic, smp = sp.grad_slices(g)
         assert oc.shape == ref_oc.shape and ic.shape == ref_ic.shape and smp.shape == ref_s.shape, n
         if g.ndim == 0:
-            assert abs(oc[0] - ref_oc[0]) <= tol * max(ref_oc[0], scalar_floor * scal), (n, oc[0], ref_oc[0])
+            if abs(oc[0] - ref_oc[0]) > tol * max(ref_oc[0], scalar_floor * scal):
+                fails.append((n, 'scalar', abs(oc[0] - ref_oc[0]) / max(ref_oc[0], scalar_floor * scal)))
             continue
-        rms = float(np.sqrt(fx['grad_mom'][k][1] / max(g.numel(), 1)))
-        # channel norms: relative to the channel's own norm, floored at 20 % of the tensor's typical channel norm
         for key, a, b in (('oc', oc, ref_oc), ('ic', ic, ref_ic)):
             if b.size == 0:
                 continue
+            if g.ndim >= 2:                     # 1-D tensors: a "channel norm" is a single element, covered by 'samp'
+                note(key, float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)), n)
             floor = 0.2 * float(np.sqrt((b ** 2).mean()))
-            dev = float(np.max(np.abs(a - b) / np.maximum(b, max(floor, 1e-30))))
-            worst[key] = max(worst[key], dev)
-            assert dev <= 2 * tol, (n, key, dev)
-        # strided sample: rel-L2 over the sample (element-wise agreement, not just norms)
-        dev = float(np.linalg.norm(smp - ref_s) / max(np.linalg.norm(ref_s), 1e-30 + rms * 1e-6))
-        worst['samp'] = max(worst['samp'], dev)
-        assert dev <= 2 * tol, (n, 'samp', dev)
+            note('chan', float(np.max(np.abs(a - b) / np.maximum(b, max(floor, 1e-30)))), n)
+        note('samp', float(np.linalg.norm(smp - ref_s) / max(np.linalg.norm(ref_s), 1e-30)), n)
+    if do_assert:
+        assert not fails, sorted(fails, key=lambda f: -f[2])[:8]
     return worst
 
 
