@@ -14,162 +14,9 @@
 #include <cstdlib>
 #include <cuda_bf16.h>
 
+#include "triplane_common.cuh"
 namespace {
-constexpr int C = 32, HID = 64, OUT = 33, PC = 96;
-constexpr int SP = 24;      // words per point of the bilinear set-up tile: 12 texel offsets + 12 weights
-
-// MUFU-based activations (ex2 / lg2 approximations): absolute error ~1e-6, far inside the 1e-3 parity budget, and
-// ~4x fewer instructions than expf / log1pf (the decoder evaluates 64 softplus + 32 sigmoid per sample point).
-__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-
-struct TriplaneParams {
-    const float* planes; int n, hp, wp;
-    const float* coords;                                   // [n][P][3] or null (ray mode)
-    const float* ray_o; const float* ray_d; const float* depths; int S;   // ray mode: point p belongs to ray p / S
-    long P;
-    float coord_scale;                                     // 2 / box_warp
-    const float* W1; const float* b1; const float* W2; const float* b2;
-    float w1g, b1g, w2g, b2g;
-    float* rgb; float* sigma;
-    // backward only
-    const float* d_rgb; const float* d_sigma;
-    float* d_planes; float* d_coords;
-    float* dW1; float* db1; float* dW2; float* db2;
-    int fwd_passes;                                         // 3: split-TF32 (default), 1: plain TF32 (experiments)
-};
-
-struct Bilin {
-    int x0, y0; float wx0, wx1, wy0, wy1; bool xin0, xin1, yin0, yin1;
-};
-
-__device__ __forceinline__ Bilin make_bilin(float gx, float gy, int hp, int wp) {
-    // grid_sample unnormalise, align_corners=False: ix = ((x+1)*W - 1)/2 ; zeros padding
-    float ix = ((gx + 1.f) * wp - 1.f) * 0.5f, iy = ((gy + 1.f) * hp - 1.f) * 0.5f;
-    ix = fminf(fmaxf(ix, -2.f), (float)wp + 1.f);
-    iy = fminf(fmaxf(iy, -2.f), (float)hp + 1.f);
-    const float fx = floorf(ix), fy = floorf(iy);
-    Bilin b;
-    b.x0 = (int)fx; b.y0 = (int)fy;
-    b.wx1 = ix - fx; b.wx0 = 1.f - b.wx1; b.wy1 = iy - fy; b.wy0 = 1.f - b.wy1;
-    b.xin0 = b.x0 >= 0 && b.x0 < wp; b.xin1 = b.x0 + 1 >= 0 && b.x0 + 1 < wp;
-    b.yin0 = b.y0 >= 0 && b.y0 < hp; b.yin1 = b.y0 + 1 >= 0 && b.y0 + 1 < hp;
-    return b;
-}
-
-// per-channel partial derivatives of the bilinear value w.r.t. (ix, iy)
-__device__ __forceinline__ void bilin_dcoord(const float* __restrict__ base, const Bilin& b, int wp, float& dix, float& diy) {
-    const float* r0 = base + ((long)b.y0 * wp + b.x0) * PC;
-    const float* r1 = r0 + (long)wp * PC;
-    float t00 = 0.f, t01 = 0.f, t10 = 0.f, t11 = 0.f;
-    if (b.yin0 && b.xin0) t00 = __ldg(r0);
-    if (b.yin0 && b.xin1) t01 = __ldg(r0 + PC);
-    if (b.yin1 && b.xin0) t10 = __ldg(r1);
-    if (b.yin1 && b.xin1) t11 = __ldg(r1 + PC);
-    dix = b.wy0 * (t01 - t00) + b.wy1 * (t11 - t10);
-    diy = b.wx0 * (t10 - t00) + b.wx1 * (t11 - t01);
-}
-
-__device__ __forceinline__ void point_coords(const TriplaneParams& p, int n, long pi, float& cx, float& cy, float& cz) {
-    cx = cy = cz = 0.f;
-    if (pi >= p.P) return;
-    if (p.coords) {
-        const float* c = p.coords + ((long)n * p.P + pi) * 3;
-        cx = c[0]; cy = c[1]; cz = c[2];
-    } else {
-        const long M = p.P / p.S;
-        const long ray = pi / p.S;
-        const float t = p.depths[(long)n * p.P + pi];
-        const float* o = p.ray_o + ((long)n * M + ray) * 3;
-        const float* d = p.ray_d + ((long)n * M + ray) * 3;
-        cx = o[0] + t * d[0]; cy = o[1] + t * d[1]; cz = o[2] + t * d[2];
-    }
-    cx *= p.coord_scale; cy *= p.coord_scale; cz *= p.coord_scale;
-}
-
-// Bilinear set-up of one plane for the lane's own point: 4 texel offsets (in floats, plane offset included) and 4 weights
-// with the plane mean (1/3) folded in; out-of-range texels get weight 0 and an address clamped onto a valid texel.
-__device__ __forceinline__ void plane_setup(float u, float v, int hp, int wp, int plane, float* off, float* wgt) {
-    float ix = ((u + 1.f) * wp - 1.f) * 0.5f, iy = ((v + 1.f) * hp - 1.f) * 0.5f;
-    ix = fminf(fmaxf(ix, -2.f), (float)wp + 1.f);
-    iy = fminf(fmaxf(iy, -2.f), (float)hp + 1.f);
-    const float fx = floorf(ix), fy = floorf(iy);
-    const int x0 = (int)fx, y0 = (int)fy;
-    const float wx1 = ix - fx, wx0 = 1.f - wx1, wy1 = iy - fy, wy0 = 1.f - wy1;
-    const bool xi0 = x0 >= 0 && x0 < wp, xi1 = x0 + 1 >= 0 && x0 + 1 < wp, yi0 = y0 >= 0 && y0 < hp, yi1 = y0 + 1 >= 0 && y0 + 1 < hp;
-    const int x0c = min(max(x0, 0), wp - 1), x1c = min(max(x0 + 1, 0), wp - 1);
-    const int y0c = min(max(y0, 0), hp - 1), y1c = min(max(y0 + 1, 0), hp - 1);
-    const int pc = plane * C;
-    const float third = 1.f / 3.f;
-    off[0] = __int_as_float((y0c * wp + x0c) * PC + pc); wgt[0] = (yi0 && xi0) ? wy0 * wx0 * third : 0.f;
-    off[1] = __int_as_float((y0c * wp + x1c) * PC + pc); wgt[1] = (yi0 && xi1) ? wy0 * wx1 * third : 0.f;
-    off[2] = __int_as_float((y1c * wp + x0c) * PC + pc); wgt[2] = (yi1 && xi0) ? wy1 * wx0 * third : 0.f;
-    off[3] = __int_as_float((y1c * wp + x1c) * PC + pc); wgt[3] = (yi1 && xi1) ? wy1 * wx1 * third : 0.f;
-}
-
-// each lane stages the set-up of its own point: ss[lane*SP + 0..11] = texel offsets, [12..23] = weights
-// (plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x): renderer.py:23-53)
-__device__ __forceinline__ void stage_setup(float* ss, int lane, float cx, float cy, float cz, int hp, int wp) {
-    float t[SP];
-    plane_setup(cx, cy, hp, wp, 0, t + 0, t + 12);
-    plane_setup(cx, cz, hp, wp, 1, t + 4, t + 16);
-    plane_setup(cz, cx, hp, wp, 2, t + 8, t + 20);
-#pragma unroll
-    for (int j = 0; j < SP; j += 4) *reinterpret_cast<float4*>(&ss[lane * SP + j]) = make_float4(t[j], t[j + 1], t[j + 2], t[j + 3]);
-}
-
-__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {          // two packed FP32 FMAs (FFMA2)
-    fma2(a.x, a.y, w, v.x, v.y); fma2(a.z, a.w, w, v.z, v.w);
-}
-
-// Gather the 32-channel mean feature of the warp's 32 points into sf[point*STRIDE + channel].  Eight lanes share a point
-// (4 channels each, one LDG.128 per texel), so one warp instruction fetches the same texel slot of FOUR points = four full
-// 128-byte lines; no cross-lane reduction is needed.
-template <int STRIDE, int UNROLL = 2>
-__device__ __forceinline__ void gather_features(const float* __restrict__ pl, const float* ss, float* sf, int lane) {
-    const int pt = lane >> 3, j4 = (lane & 7) * 4;
-    const float* pc = pl + j4;
-#pragma unroll UNROLL
-    for (int q0 = 0; q0 < 32; q0 += 4) {
-        const float* s = ss + (q0 + pt) * SP;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int k = 0; k < 12; k += 4) {
-            const int4 o = *reinterpret_cast<const int4*>(s + k);
-            const float4 w = *reinterpret_cast<const float4*>(s + 12 + k);
-            fma4(acc, w.x, __ldg(reinterpret_cast<const float4*>(pc + o.x)));
-            fma4(acc, w.y, __ldg(reinterpret_cast<const float4*>(pc + o.y)));
-            fma4(acc, w.z, __ldg(reinterpret_cast<const float4*>(pc + o.z)));
-            fma4(acc, w.w, __ldg(reinterpret_cast<const float4*>(pc + o.w)));
-        }
-        *reinterpret_cast<float4*>(&sf[(q0 + pt) * STRIDE + j4]) = acc;
-    }
-}
-
-__device__ __forceinline__ void red_add4(float* addr, float w, const float4& g) {
-    if (w != 0.f)
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(w * g.x), "f"(w * g.y), "f"(w * g.z), "f"(w * g.w)
-                     : "memory");
-}
-
-// Scatter d_f (sg[point*STRIDE + channel]) into the plane gradient with vector reductions, same lane mapping as the gather.
-template <int STRIDE>
-__device__ __forceinline__ void scatter_features(float* __restrict__ dpl, const float* ss, const float* sg, int lane, int cnt) {
-    const int pt = lane >> 3, j4 = (lane & 7) * 4;
-    float* pc = dpl + j4;
-    for (int q0 = 0; q0 < 32; q0 += 4) {
-        if (q0 + pt >= cnt) continue;
-        const float* s = ss + (q0 + pt) * SP;
-        const float4 g = *reinterpret_cast<const float4*>(&sg[(q0 + pt) * STRIDE + j4]);
-#pragma unroll
-        for (int k = 0; k < 12; k += 4) {
-            const int4 o = *reinterpret_cast<const int4*>(s + k);
-            const float4 w = *reinterpret_cast<const float4*>(s + 12 + k);
-            red_add4(pc + o.x, w.x, g); red_add4(pc + o.y, w.y, g); red_add4(pc + o.z, w.z, g); red_add4(pc + o.w, w.w, g);
-        }
-    }
-}
-
+using namespace tri;
 // ---------------------------------------------------------------------------------------------------------------------
 // Tensor-core decoder: the two FC layers of a warp's 32 points as mma.sync.m16n8k8 TF32 tiles with split-float operands
 // (x = hi + lo, three MMAs per product: lo*hi + hi*lo + hi*hi, fp32 accumulate -> ~fp32 accuracy).
@@ -702,16 +549,25 @@ __global__ void __launch_bounds__(BM_WARPS * 32, 1) triplane_mlp_bwd_mma_kernel(
 }
 
 }  // namespace
+int triplane_fwd_tc_launch(tri::TriplaneParams& p, bool sigma_only, cudaStream_t st);          // triplane_tc.cu
+int triplane_bwd_tc_launch(tri::TriplaneParams& p, cudaStream_t st);
+int g_b200_triplane_impl = -1;    // -1: take B200EG3D_TRIPLANE_IMPL from the environment on first use; 0: mma.sync kernels, 1: tcgen05 kernels
+static inline int triplane_impl() {
+    if (g_b200_triplane_impl < 0) { const char* e = getenv("B200EG3D_TRIPLANE_IMPL"); g_b200_triplane_impl = (e && e[0] == '0') ? 0 : 1; }
+    return g_b200_triplane_impl;
+}
 int g_b200_mlp_passes = 0;        // 0: take B200EG3D_MLP_PASSES from the environment on first use; 1 / 3: set by b200_set_mlp_passes()
 namespace {
 int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
-                const float* ray_d, const float* depths, int S, long P, float box_warp, const float* W1, const float* b1,
+                const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp, const float* W1, const float* b1,
                 const float* W2, const float* b2, float lr_mul) {
     B200_REQUIRE(planes && W1 && b1 && W2 && b2, "triplane: null plane/weight pointer");
     B200_REQUIRE(coords || (ray_o && ray_d && depths && S > 0 && P % S == 0), "triplane: need coords or (ray_o, ray_d, depths, S)");
     B200_REQUIRE(n > 0 && hp > 0 && wp > 0 && P >= 0 && box_warp != 0.f, "triplane: bad shape");
     p.planes = planes; p.n = n; p.hp = hp; p.wp = wp; p.coords = coords; p.ray_o = ray_o; p.ray_d = ray_d; p.depths = depths;
-    p.S = S; p.P = P; p.coord_scale = 2.f / box_warp; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+    B200_REQUIRE(ray_w >= 0 && (ray_w == 0 || coords || (P / S) % ray_w == 0), "triplane: ray_w must divide the ray count");
+    p.S = S; p.ray_w = coords ? 0 : ray_w; p.P = P; p.coord_scale = 2.f / box_warp;
+    p.M = coords ? 0 : P / S; p.ray_h = p.ray_w > 0 ? (int)(p.M / p.ray_w) : 0; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
     p.w1g = lr_mul / sqrtf((float)C); p.b1g = lr_mul; p.w2g = lr_mul / sqrtf((float)HID); p.b2g = lr_mul;
     return 0;
 }
@@ -721,11 +577,11 @@ int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, c
 // W1 [64][32], b1 [64], W2 [33][64], b2 [33] are the raw decoder parameters (gains lr_mul/sqrt(fan_in) applied here,
 // training/networks_stylegan2.py:111-112).  Outputs rgb [n][P][32], sigma [n][P].
 B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
-                                   const float* ray_d, const float* depths, int S, long P, float box_warp,
+                                   const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp,
                                    const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
                                    float* rgb, float* sigma, void* stream) {
     TriplaneParams p{};
-    if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
+    if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, ray_w, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
     B200_REQUIRE(sigma, "triplane_fwd: null output");        // rgb == NULL: density-only query
     if (P == 0) return 0;
     p.rgb = rgb; p.sigma = sigma;
@@ -738,6 +594,7 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     B200_FUNC_ATTR_ONCE(triplane_mlp_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
     B200_FUNC_ATTR_ONCE(triplane_mlp_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
     p.fwd_passes = g_b200_mlp_passes;
+    if (triplane_impl() == 1 && P < (1L << 31)) return triplane_fwd_tc_launch(p, rgb == nullptr, (cudaStream_t)stream);
     const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
     grid.x = (unsigned)(g512 < 148 ? g512 : 148);                      // persistent: one 16-warp CTA per SM
     if (rgb) triplane_mlp_fwd_mma_kernel<false><<<grid, FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(p);
@@ -748,43 +605,89 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
 
 // Operand passes of the decoder forward: 3 = split operands (fp32-equivalent, the parity default), 1 = single pass (the
 // non-parity "fast mode" reported separately by bench.py).  Returns the previous value.
+// Implementation of the fused sampler + decoder: 1 = tcgen05 pipeline (default), 0 = the mma.sync kernels of round 1 (kept as
+// the on-GPU cross-check; env B200EG3D_TRIPLANE_IMPL=0).  Returns the previous setting.
+B200_API int b200_set_triplane_impl(int impl) {
+    const int prev = triplane_impl();
+    g_b200_triplane_impl = impl ? 1 : 0;
+    return prev;
+}
+
 B200_API int b200_set_mlp_passes(int passes) {
     const int prev = g_b200_mlp_passes == 0 ? 3 : g_b200_mlp_passes;
     g_b200_mlp_passes = passes == 1 ? 1 : 3;
     return prev;
 }
 
-// Kept for ABI stability: the decoder-parameter gradients are accumulated in tensor memory inside the kernel and need
-// no workspace any more.
+// Scratch the backward may need: the per-point coordinate gradients (12 B / point, when per-ray sums are requested without
+// d_coords) and the per-point feature gradients handed from the decoder pass to the plane-scatter pass (64 B / point, tcgen05
+// implementation).  The caller allocates it once and passes it to b200_triplane_mlp_bwd.
 B200_API long b200_triplane_bwd_workspace_bytes(int n, long P) {
-    (void)n; (void)P;
-    return 0;
+    return (long)n * P * (12 + 64) + 1024;
 }
 
+namespace {
+// d ray_o[m] += sum_k d point[m][k],  d ray_d[m] += sum_k t[m][k] * d point[m][k]      (point = o + t * d, renderer.py:161,178)
+__global__ void ray_reduce_dpoints_kernel(const float* __restrict__ d_pts, const float* __restrict__ depths, long rays, int S,
+                                          float* __restrict__ d_ro, float* __restrict__ d_rd) {
+    const int lane = threadIdx.x & 31;
+    const long ray = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ray >= rays) return;
+    float so[3] = {0.f, 0.f, 0.f}, sd[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < S; k += 32) {
+        const float t = depths[ray * S + k];
+        const float* g = d_pts + (ray * S + k) * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { so[a] += g[a]; sd[a] += t * g[a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { so[a] = warp_sum(so[a]); sd[a] = warp_sum(sd[a]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { d_ro[ray * 3 + a] += so[a]; d_rd[ray * 3 + a] += sd[a]; }
+    }
+}
+}  // namespace
+
 // d_planes [n][hp][wp][96] is ACCUMULATED into (zero it first); d_coords [n][P][3] is written (may be null);
-// dW1/db1/dW2/db2 are ACCUMULATED into (all four null => parameter gradients skipped).  `workspace` is unused (may be null).
+// d_ray_o / d_ray_d [n][P/S][3] (ray mode; both or neither; may be null) are ACCUMULATED into: the per-ray sums of d point and
+// t * d point, i.e. the gradients of the ray origins / directions;  dW1/db1/dW2/db2 are ACCUMULATED into (all four null =>
+// parameter gradients skipped).  `workspace`: b200_triplane_bwd_workspace_bytes(n, P) bytes of scratch (may be null when neither
+// d_ray_o nor the tcgen05 implementation needs it).
 B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
-                                   const float* ray_d, const float* depths, int S, long P, float box_warp,
+                                   const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp,
                                    const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
                                    const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
+                                   float* d_ray_o, float* d_ray_d,
                                    float* dW1, float* db1, float* dW2, float* db2, void* workspace, long workspace_bytes,
                                    void* stream) {
     TriplaneParams p{};
-    if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
+    if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, ray_w, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
     B200_REQUIRE(d_rgb && d_sigma, "triplane_bwd: null incoming gradient");
     B200_REQUIRE((dW1 && db1 && dW2 && db2) || (!dW1 && !db1 && !dW2 && !db2), "triplane_bwd: pass all four parameter gradients or none");
+    B200_REQUIRE((d_ray_o != nullptr) == (d_ray_d != nullptr), "triplane_bwd: pass both ray gradients or neither");
+    B200_REQUIRE(!d_ray_o || !coords, "triplane_bwd: ray gradients need ray mode");
     if (P == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
-    (void)workspace; (void)workspace_bytes;
+    if (d_ray_o && !d_coords) {          // per-point coordinate gradients staged in the workspace, reduced per ray below
+        B200_REQUIRE(workspace && workspace_bytes >= (long)n * P * 12, "triplane_bwd: workspace too small for the ray gradients");
+        p.d_coords = static_cast<float*>(workspace);
+    }
     B200_FUNC_ATTR_ONCE((triplane_mlp_bwd_mma_kernel<BM_WARPS_WG, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, bm_smem(BM_WARPS_WG, true));
     B200_FUNC_ATTR_ONCE((triplane_mlp_bwd_mma_kernel<BM_WARPS_NOWG, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, bm_smem(BM_WARPS_NOWG, false));
     const int warps = dW1 ? BM_WARPS_WG : BM_WARPS_NOWG;
     const long gb = (P + warps * 32 - 1) / (warps * 32);
-    dim3 grid((unsigned)(gb < 148 ? gb : 148), n);                     // persistent: one CTA per SM
+    const int sms = b200_sm_count();
+    dim3 grid((unsigned)(gb < sms ? gb : sms), n);                     // persistent: one CTA per SM
     if (dW1) triplane_mlp_bwd_mma_kernel<BM_WARPS_WG, true><<<grid, warps * 32, bm_smem(BM_WARPS_WG, true), st>>>(p);
     else triplane_mlp_bwd_mma_kernel<BM_WARPS_NOWG, false><<<grid, warps * 32, bm_smem(BM_WARPS_NOWG, false), st>>>(p);
     B200_CHECK_LAUNCH();
+    if (d_ray_o) {
+        const long rays = (long)n * (P / S);
+        ray_reduce_dpoints_kernel<<<(unsigned)((rays + 7) / 8), 256, 0, st>>>(p.d_coords, depths, rays, S, d_ray_o, d_ray_d);
+        B200_CHECK_LAUNCH();
+    }
     return 0;
 }

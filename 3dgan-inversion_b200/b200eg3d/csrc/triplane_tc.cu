@@ -1,0 +1,349 @@
+// Fused tri-plane sampling + OSG decoder, tcgen05 generation (sm_100a).
+//
+// Same math as triplane.cu (renderer.py:39-66 sample_from_planes, triplane.py:124-136 OSGDecoder), re-organised as a
+// warp-specialised pipeline over tiles of 128 sample points so that the decoder runs on the 5th-generation tensor cores with
+// its accumulators in tensor memory and the texel gather never waits for it:
+//
+//   gather warps (8)     point -> 3 plane coordinates -> 12 texel lines (LDG.128, 8 lanes per point) -> mean feature, written
+//                        as split bf16 (hi | lo in one 128-byte row) straight into the swizzled K-major A tile of layer 1
+//   MMA warp (1 lane)    layer 1: D1[128 x 64] = [F_hi F_lo][W1_hi W1_hi]^T + F_hi W1_lo^T    (6 tcgen05.mma, K = 16 each)
+//                        layer 2: D2[128 x 48] = h_hi W2_hi^T + h_hi W2_lo^T + h_lo W2_hi^T     (12 tcgen05.mma)
+//   consumer warps (2x4) thread = point = TMEM lane: tcgen05.ld D1 -> +b1 -> softplus -> split bf16 -> A tile of layer 2;
+//                        tcgen05.ld D2 -> +b2 -> sigmoid -> staged through shared memory -> coalesced stores
+//
+// Two tiles are in flight per stage (the two consumer sets alternate), every hand-off is an mbarrier, tensor-core completion is
+// signalled with tcgen05.commit.  Split-bf16 operands (x = hi + lo, three products, fp32 accumulate) keep the decoder at
+// fp32-equivalent accuracy, like the convolution stack.
+//
+// Work order: in ray mode the rays are walked column by column and every CTA owns a contiguous range of tiles, see
+// tri::map_point (the XZ / ZX texel lines of a pixel column stay in that SM's L1).
+#include "triplane_common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+using namespace tri;
+using namespace tc;
+
+constexpr int TILE = 128, OUTP = 48;
+constexpr int NCONS = 8, MMA_WARP = 8, GATHER0 = 9, NGRP = 3, NG = 4 * NGRP;   // 3 gather groups of 4 warps = 3 tiles being gathered
+constexpr int FW_THREADS = (NCONS + 1 + NG) * 32;              // 672
+
+// shared-memory map (bytes from a 1024-aligned base)
+constexpr int OFF_A1 = 0;                                      // NGRP stages x [128 rows][hi 32 ch | lo 32 ch] bf16
+constexpr int OFF_A2 = OFF_A1 + NGRP * 16384;                  // 2 sets x ([128][64] hi | [128][64] lo) bf16
+constexpr int OFF_W1A = OFF_A2 + 2 * 32768;                    // [64 units][W1_hi | W1_hi]
+constexpr int OFF_W1B = OFF_W1A + 8192;                        // [64 units][W1_lo | 0]
+constexpr int OFF_W2H = OFF_W1B + 8192;                        // [48 outputs][64 units] hi (rows 33..47 zero)
+constexpr int OFF_W2L = OFF_W2H + 6144;
+constexpr int OFF_SS = OFF_W2L + 6144;                         // per gather warp: bilinear set-up [32][SP] words
+constexpr int OFF_BIAS = OFF_SS + NG * 32 * SP * 4;            // b1[64] | b2[48]
+constexpr int OFF_BAR = OFF_BIAS + 512;                        // mbarriers (see bar_*) + TMEM slot
+constexpr int FW_SMEM = OFF_BAR + 128 + 1024;                  // + alignment slack
+constexpr int TM_COLS = 256;                                   // per set: D1 at +0 (64 columns), D2 at +64 (48 columns)
+
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// 8 floats -> 8 bf16 (hi) and the bf16 of the remainders (lo)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        h[i] = pack2(v[2 * i], v[2 * i + 1]);
+        l[i] = pack2(v[2 * i] - bf_lo(h[i]), v[2 * i + 1] - bf_hi(h[i]));
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Activations in base 2 (MUFU.EX2 / LG2 / RCP are the native special functions); the conversion factors live in the weights:
+//   layer 1 is staged as W1 log2(e), b1 log2(e), so the tensor core delivers y = u log2(e) and
+//       softplus(u) = ln2 * lg2(1 + 2^y)          -> the kernel keeps h' = lg2(1 + 2^y), ln2 is folded into W2
+//   the colour rows of layer 2 are staged as -W2 (= -log2(e) * ln2 * W2), -log2(e) b2, so the tensor core delivers z = -o log2(e) and
+//       sigmoid(o) = 1 / (1 + 2^z)
+// Equal to torch's softplus (threshold 20) / sigmoid to ~1e-7 absolute.  y is clamped below 2^126 so that huge pre-activations
+// stay finite (lg2(1 + 2^y) = y exactly there).
+__device__ __forceinline__ float softplus2(float y) { return __log2f(1.f + exp2f(fminf(y, 126.f))); }
+__device__ __forceinline__ float sigmoid2(float z) { return __fdividef(1.f, 1.f + exp2f(fminf(z, 126.f))); }
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Decoder weights -> swizzled K-major bf16 B tiles (gains folded in; networks_stylegan2.py:111-112), biases -> fp32.
+__device__ void stage_decoder_weights(const TriplaneParams& p, uint8_t* sm) {
+    for (int i = threadIdx.x; i < HID * 64; i += blockDim.x) {
+        const int j = i >> 6, e = i & 63, c = e & 31;
+        const float w = p.W1[j * C + c] * (p.w1g * LOG2E);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const uint32_t o = sw128(j, e >> 3) + (e & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(sm + OFF_W1A + o) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(sm + OFF_W1B + o) = e < 32 ? lo : __float2bfloat16_rn(0.f);
+    }
+    for (int i = threadIdx.x; i < OUTP * 64; i += blockDim.x) {
+        const int k = i >> 6, j = i & 63;
+        const float w = k < OUT ? p.W2[k * HID + j] * (k == 0 ? p.w2g * LN2 : -p.w2g) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+        const uint32_t o = sw128(k, j >> 3) + (j & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(sm + OFF_W2H + o) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(sm + OFF_W2L + o) = lo;
+    }
+    float* bias = reinterpret_cast<float*>(sm + OFF_BIAS);
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) bias[i] = p.b1[i] * (p.b1g * LOG2E);
+    for (int i = threadIdx.x; i < OUTP; i += blockDim.x) bias[HID + i] = i < OUT ? p.b2[i] * (i == 0 ? p.b2g : -p.b2g * LOG2E) : 0.f;
+}
+
+// Gather the mean feature of 32 points (rows row0 .. row0+31 of the tile) into the layer-1 A tile as split bf16.
+// Eight lanes share a point (4 channels each, one LDG.128 per texel): one warp instruction fetches the same texel slot of four
+// points = four full 128-byte lines.  Row layout: chunks 0-3 = hi channels 0..31, chunks 4-7 = lo channels 0..31.
+__device__ __forceinline__ void gather_to_tile(const float* __restrict__ pl, const float* ss, uint8_t* a1, int row0, int lane) {
+    const int pt = lane >> 3, l8 = lane & 7;
+    const float* pc = pl + l8 * 4;
+#pragma unroll 2
+    for (int q0 = 0; q0 < 32; q0 += 4) {
+        const float* s = ss + (q0 + pt) * SP;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 12; k += 4) {
+            const int4 o = *reinterpret_cast<const int4*>(s + k);
+            const float4 w = *reinterpret_cast<const float4*>(s + 12 + k);
+            fma4(acc, w.x, __ldg(reinterpret_cast<const float4*>(pc + o.x)));
+            fma4(acc, w.y, __ldg(reinterpret_cast<const float4*>(pc + o.y)));
+            fma4(acc, w.z, __ldg(reinterpret_cast<const float4*>(pc + o.z)));
+            fma4(acc, w.w, __ldg(reinterpret_cast<const float4*>(pc + o.w)));
+        }
+        const int row = row0 + q0 + pt;
+        const uint32_t h01 = pack2(acc.x, acc.y), h23 = pack2(acc.z, acc.w);
+        const uint32_t l01 = pack2(acc.x - bf_lo(h01), acc.y - bf_hi(h01)), l23 = pack2(acc.z - bf_lo(h23), acc.w - bf_hi(h23));
+        // lane pair (2c, 2c+1) holds channels 8c..8c+7: the even lane collects the 16-byte hi chunk, the odd lane the lo chunk, so
+        // every lane issues ONE conflict-free STS.128 (the 8 lanes of a point cover its whole 128-byte row)
+        const bool odd = l8 & 1;
+        const uint32_t rx = __shfl_xor_sync(0xffffffffu, odd ? h01 : l01, 1), ry = __shfl_xor_sync(0xffffffffu, odd ? h23 : l23, 1);
+        const uint4 v = odd ? make_uint4(rx, ry, l01, l23) : make_uint4(h01, h23, rx, ry);
+        *reinterpret_cast<uint4*>(a1 + sw128(row, (odd ? 4 : 0) + (l8 >> 1))) = v;
+    }
+}
+
+
+// mbarrier addresses (8 bytes each) relative to OFF_BAR; plain arithmetic so that runtime stage indices stay in registers
+__device__ __forceinline__ uint32_t bar_a1_full(uint32_t b, int s) { return b + 8u * s; }               // NGRP, count 4
+__device__ __forceinline__ uint32_t bar_a1_empty(uint32_t b, int s) { return b + 8u * (NGRP + s); }      // NGRP, count 1 (tcgen05.commit)
+__device__ __forceinline__ uint32_t bar_d1_full(uint32_t b, int s) { return b + 8u * (2 * NGRP + s); }   // 2
+__device__ __forceinline__ uint32_t bar_a2_full(uint32_t b, int s) { return b + 8u * (2 * NGRP + 2 + s); }   // 2, count 4
+__device__ __forceinline__ uint32_t bar_d2_full(uint32_t b, int s) { return b + 8u * (2 * NGRP + 4 + s); }   // 2
+constexpr int BAR_TMEM_SLOT = 8 * (2 * NGRP + 6);
+
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {          // non-blocking probe
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// SIGMA_ONLY: density queries on voxel grids (single_id_coach.py:118-140) write column 0 of the second layer only.
+template <bool SIGMA_ONLY>
+__global__ void __launch_bounds__(FW_THREADS, 1) triplane_fwd_tc_kernel(TriplaneParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const uint32_t sm_u = smem_u32(sm);
+    const uint32_t B = sm_u + OFF_BAR;
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NGRP; ++i) { mbar_init(bar_a1_full(B, i), 4); mbar_init(bar_a1_empty(B, i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_d1_full(B, i), 1); mbar_init(bar_a2_full(B, i), 4); mbar_init(bar_d2_full(B, i), 1); }
+        fence_barrier_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(B + BAR_TMEM_SLOT, TM_COLS);
+    stage_decoder_weights(p, sm);
+    fence_proxy_async();                       // the weight tiles were written through the generic proxy; tcgen05.mma reads via the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + BAR_TMEM_SLOT);
+
+    const long ntiles = (p.P + TILE - 1) / TILE;
+    const long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long t0 = (long)blockIdx.x * per;
+    const int nloc = (int)max(0L, min(ntiles, t0 + per) - t0);
+    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
+
+    if (warp >= GATHER0) {
+        // ------------------------------------------------------------------ gather: tiles lt = group, group + NGRP, ...
+        const int g = warp - GATHER0, group = g >> 2, gq = g & 3;
+        float* ss = reinterpret_cast<float*>(sm + OFF_SS) + g * 32 * SP;
+        uint8_t* a1 = sm + OFF_A1 + group * 16384;
+        int it = 0;
+        for (int lt = group; lt < nloc; lt += NGRP, ++it) {
+            float cx, cy, cz;
+            point_coords32(p, n, map_point(p, (unsigned)((t0 + lt) * TILE + gq * 32 + lane)), cx, cy, cz);
+            stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
+            mbar_wait(bar_a1_empty(B, group), (it & 1) ^ 1);           // layer 1 of the tile NGRP back has consumed this stage
+            __syncwarp();
+            gather_to_tile(pl, ss, a1, gq * 32, lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a1_full(B, group));
+        }
+    } else if (warp == MMA_WARP) {
+        // ------------------------------------------------------------------ tensor-core issue (one lane)
+        // Two cursors: n1 = next tile whose layer 1 is to be issued, n2 = next tile whose layer 2 is to be issued.  Whichever
+        // operand tile is ready first goes first, so a slow activation stage never holds back the next tile's layer 1.
+        // D1[s] / D2[s] (s = tile parity) are free again once layer 2 of the tile two back has been issued: its a2_full arrival
+        // follows the consumer's last read of both.
+        if (lane == 0) {
+            const uint32_t id1 = instr_desc_bf16(128, HID, 0, 0), id2 = instr_desc_bf16(128, OUTP, 0, 0);
+            int n1 = 0, n2 = 0;
+            while (n2 < nloc) {
+                bool did = false;
+                if (n1 < nloc && n1 - n2 < 2) {
+                    const int st = n1 % NGRP, it = n1 / NGRP, s = n1 & 1;
+                    if (mbar_test(bar_a1_full(B, st), it & 1)) {
+                        tc_fence_after();
+                        const uint32_t a = sm_u + OFF_A1 + st * 16384, d1 = tmem + (uint32_t)(s * 128);
+                        const int nk = p.fwd_passes == 3 ? 4 : 2;
+                        for (int k = 0; k < nk; ++k)           // [F_hi F_lo] x [W1_hi W1_hi]   (single pass: F_hi x W1_hi only)
+                            umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + OFF_W1A + k * 32, 0, 1024), id1, k != 0);
+                        if (p.fwd_passes == 3) {
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)        // F_hi x W1_lo
+                                umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + OFF_W1B + k * 32, 0, 1024), id1, 1);
+                        }
+                        umma_commit(bar_a1_empty(B, st));
+                        umma_commit(bar_d1_full(B, s));
+                        ++n1;
+                        did = true;
+                    }
+                }
+                if (n2 < n1) {
+                    const int s = n2 & 1, it = n2 >> 1;
+                    if (mbar_test(bar_a2_full(B, s), it & 1)) {
+                        tc_fence_after();
+                        const uint32_t ah = sm_u + OFF_A2 + s * 32768, al = ah + 16384, d2 = tmem + (uint32_t)(s * 128 + 64);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t dah = smem_desc(ah + k * 32, 0, 1024), dbh = smem_desc(sm_u + OFF_W2H + k * 32, 0, 1024);
+                            umma_bf16(d2, dah, dbh, id2, k != 0);
+                            if (p.fwd_passes == 3) {
+                                umma_bf16(d2, dah, smem_desc(sm_u + OFF_W2L + k * 32, 0, 1024), id2, 1);
+                                umma_bf16(d2, smem_desc(al + k * 32, 0, 1024), dbh, id2, 1);
+                            }
+                        }
+                        umma_commit(bar_d2_full(B, s));
+                        ++n2;
+                        did = true;
+                    }
+                }
+                if (!did) __nanosleep(32);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers: set = tile parity, thread = point = TMEM lane
+        const int set = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 128);
+        uint8_t* a2h = sm + OFF_A2 + set * 32768;
+        uint8_t* a2l = a2h + 16384;
+        const float* b1s = reinterpret_cast<const float*>(sm + OFF_BIAS);
+        const float* b2s = b1s + HID;
+        // output staging, 36-float rows (conflict-free for row-per-thread writes and for row-contiguous reads), carved out of the
+        // A2 rows this warp itself owns: rows 0..15 in its hi rows, 16..31 in its lo rows
+        auto stage_row = [&](int r) -> float* {
+            return reinterpret_cast<float*>((r < 16 ? a2h : a2l) + q * 4096 + (r & 15) * 144);
+        };
+        for (int lt = set; lt < nloc; lt += 2) {
+            const int it = lt >> 1;
+            const unsigned pp0 = (unsigned)((t0 + lt) * TILE + q * 32);   // first work point of this warp's 32 rows
+            mbar_wait(bar_d1_full(B, set), it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tmem_ld32(tq + half * 32, v);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(b1s + half * 32 + c8 * 8 + e);
+                        h[e] = softplus2(v[c8 * 8 + e] + bv.x); h[e + 1] = softplus2(v[c8 * 8 + e + 1] + bv.y);
+                        h[e + 2] = softplus2(v[c8 * 8 + e + 2] + bv.z); h[e + 3] = softplus2(v[c8 * 8 + e + 3] + bv.w);
+                    }
+                    uint4 hi, lo;
+                    split8(h, hi, lo);
+                    const uint32_t o = sw128(row, half * 4 + c8);
+                    *reinterpret_cast<uint4*>(a2h + o) = hi;
+                    *reinterpret_cast<uint4*>(a2l + o) = lo;
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a2_full(B, set));
+            // ---- layer 2 result
+            mbar_wait(bar_d2_full(B, set), it & 1);
+            tc_fence_after();
+            float o[32], o32[8];
+            tmem_ld32(tq + 64, o);
+            if (!SIGMA_ONLY) tmem_ld8(tq + 96, o32);
+            tc_fence_before();
+            const int pi = map_point(p, pp0 + lane);
+            if (pi >= 0) p.sigma[(long)n * p.P + pi] = o[0] + b2s[0];
+            if (!SIGMA_ONLY) {
+                // rgb = sigmoid(o[1..32]) * 1.002 - 0.001, staged so that the global stores are full 128-byte rows
+                float* mine = stage_row(lane);
+#pragma unroll
+                for (int c4 = 0; c4 < 32; c4 += 4) {
+                    float r[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = c4 + e + 1;
+                        const float x = (col < 32 ? o[col] : o32[0]) + b2s[col];
+                        r[e] = sigmoid2(x) * 1.002f - 0.001f;
+                    }
+                    *reinterpret_cast<float4*>(mine + c4) = make_float4(r[0], r[1], r[2], r[3]);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = i * 4 + (lane >> 3);
+                    const int pr = __shfl_sync(0xffffffffu, pi, r);
+                    const float4 val = *reinterpret_cast<const float4*>(stage_row(r) + (lane & 7) * 4);
+                    if (pr >= 0) *reinterpret_cast<float4*>(p.rgb + ((long)n * p.P + pr) * C + (lane & 7) * 4) = val;
+                }
+                __syncwarp();                       // staging rows are overwritten by the next tile's hidden activations
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem, TM_COLS);
+}
+}  // namespace
+
+extern int g_b200_mlp_passes;
+
+// Launch helper used by b200_triplane_mlp_fwd (triplane.cu) when the tcgen05 implementation is selected.
+int triplane_fwd_tc_launch(tri::TriplaneParams& p, bool sigma_only, cudaStream_t st) {
+    B200_FUNC_ATTR_ONCE(triplane_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+    B200_FUNC_ATTR_ONCE(triplane_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+    const long ntiles = (p.P + TILE - 1) / TILE;
+    const int sms = b200_sm_count();
+    dim3 grid((unsigned)(ntiles < sms ? ntiles : sms), p.n);              // persistent: one CTA per SM, contiguous tile ranges
+    if (sigma_only) triplane_fwd_tc_kernel<true><<<grid, FW_THREADS, FW_SMEM, st>>>(p);
+    else triplane_fwd_tc_kernel<false><<<grid, FW_THREADS, FW_SMEM, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}

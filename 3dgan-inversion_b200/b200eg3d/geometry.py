@@ -58,11 +58,11 @@ def _query_sigma(G, ws, samples, max_batch, planes):
         while head < P:
             cnt = min(max_batch, P - head)
             c = co[:, head:head + cnt].contiguous()
-            call('b200_triplane_mlp_fwd', ptr(pl), 1, hp, wp, ptr(c), None, None, None, 0, cnt, box, *map(ptr, w), float(lr_mul),
+            call('b200_triplane_mlp_fwd', ptr(pl), 1, hp, wp, ptr(c), None, None, None, 0, 0, cnt, box, *map(ptr, w), float(lr_mul),
                  None, ptr(sigmas[:, head:head + cnt]), stream())
             head += cnt
     else:
-        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co.contiguous()), None, None, None, 0, P, box, *map(ptr, w), float(lr_mul),
+        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co.contiguous()), None, None, None, 0, 0, P, box, *map(ptr, w), float(lr_mul),
              None, ptr(sigmas), stream())
     return sigmas
 

@@ -712,7 +712,7 @@ class _RunModel(torch.autograd.Function):
         rgb = torch.empty([n, P, 32], device=pl.device, dtype=torch.float32)
         sigma = torch.empty([n, P, 1], device=pl.device, dtype=torch.float32)
         w = [_f32c(t) for t in (W1, b1, W2, b2)]
-        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, P, float(box_warp), *map(ptr, w),
+        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, 0, P, float(box_warp), *map(ptr, w),
              float(lr_mul), ptr(rgb), ptr(sigma), stream())
         ctx.cfg = (float(lr_mul), float(box_warp))
         ctx.save_for_backward(pl, co, *w)
@@ -730,9 +730,11 @@ class _RunModel(torch.autograd.Function):
         d_coords = torch.empty_like(co) if need[1] else None
         wg = any(need[2:6])
         dws = [torch.zeros_like(t) for t in (W1, b1, W2, b2)] if wg else [None] * 4
-        call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, P, box_warp, ptr(W1), ptr(b1), ptr(W2),
-             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(d_planes), ptr(d_coords), *map(ptr, dws), None, 0,
-             stream())
+        ws_bytes = _lib.load().b200_triplane_bwd_workspace_bytes(n, P)
+        work = torch.empty([ws_bytes], device=pl.device, dtype=torch.uint8)
+        call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, 0, P, box_warp, ptr(W1), ptr(b1), ptr(W2),
+             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(d_planes), ptr(d_coords), None, None, *map(ptr, dws),
+             ptr(work), ws_bytes, stream())
         return (d_planes, d_coords, *dws, None, None)
 
 
@@ -770,7 +772,8 @@ class _Render(torch.autograd.Function):
             call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), st)
         rgb_c = torch.empty([n, M, S, 32], device=dev, dtype=torch.float32)
         sig_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
-        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_c), S, M * S, float(box_warp),
+        rw = int(round(math.sqrt(M))) if int(round(math.sqrt(M))) ** 2 == M else 0       # square ray image: column-major work order
+        call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_c), S, rw, M * S, float(box_warp),
              *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), st)
         if density_noise > 0:
             sig_c += (torch.randn_like(sig_c.view(n, M * S, 1)) * density_noise).view(n, M, S)      # renderer.py:201-202 (same draw shape)
@@ -783,7 +786,7 @@ class _Render(torch.autograd.Function):
             call('b200_ray_importance', ptr(t_c), ptr(sig_c), ptr(_f32c(u_imp)), ptr(t_f), n * M, S, S2, st)
             rgb_f = torch.empty([n, M, S2, 32], device=dev, dtype=torch.float32)
             sig_f = torch.empty([n, M, S2], device=dev, dtype=torch.float32)
-            call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_f), S2, M * S2, float(box_warp),
+            call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_f), S2, rw, M * S2, float(box_warp),
                  *map(ptr, w), float(lr_mul), ptr(rgb_f), ptr(sig_f), st)
             if density_noise > 0:
                 sig_f += (torch.randn_like(sig_f.view(n, M * S2, 1)) * density_noise).view(n, M, S2)
@@ -793,7 +796,7 @@ class _Render(torch.autograd.Function):
         wsum = torch.empty([n, M, 1], device=dev, dtype=torch.float32)
         call('b200_ray_composite_fwd', ptr(t_c), ptr(sig_c), ptr(rgb_c), S, ptr(t_f), ptr(sig_f), ptr(rgb_f), S2, ptr(minmax),
              int(bool(white_back)), n * M, ptr(feat), ptr(depth), ptr(wsum), st)
-        ctx.cfg = (float(lr_mul), float(box_warp), int(bool(white_back)), S, S2)
+        ctx.cfg = (float(lr_mul), float(box_warp), int(bool(white_back)), S, S2, rw)
         ctx.save_for_backward(pl, ro, rd, *w, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax)
         return feat, depth, wsum
 
@@ -801,7 +804,7 @@ class _Render(torch.autograd.Function):
     @device_guard
     def backward(ctx, d_feat, d_depth, d_wsum):
         pl, ro, rd, W1, b1, W2, b2, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax = ctx.saved_tensors
-        lr_mul, box_warp, white_back, S, S2 = ctx.cfg
+        lr_mul, box_warp, white_back, S, S2, rw = ctx.cfg
         n, hp, wp, _ = pl.shape
         M = ro.shape[1]
         dev = pl.device
@@ -825,15 +828,16 @@ class _Render(torch.autograd.Function):
         if want_rays:
             d_ro = torch.zeros_like(ro)
             d_rd = torch.zeros_like(rd)
+        ws_bytes = _lib.load().b200_triplane_bwd_workspace_bytes(n, M * max(S, S2))
+        work = torch.empty([ws_bytes], device=dev, dtype=torch.uint8)
         for t, d_rgb, d_sig, s in ((t_c, d_rgb_c, d_sig_c, S), (t_f, d_rgb_f, d_sig_f, S2)):
             if s == 0:
                 continue
-            d_pts = torch.empty([n, M, s, 3], device=dev, dtype=torch.float32) if want_rays else None
-            call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t), s, M * s, box_warp, ptr(W1),
-                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(d_planes), ptr(d_pts), *map(ptr, dws), None, 0, st)
-            if want_rays:                      # point = o + t*d  (renderer.py:161,178)
-                d_ro += d_pts.sum(2)
-                d_rd += (d_pts * t.unsqueeze(-1)).sum(2)
+            # the per-ray sums d ray_o = sum_k d point, d ray_d = sum_k t_k * d point (point = o + t*d, renderer.py:161,178) are
+            # reduced inside the C-ABI call
+            call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t), s, rw, M * s, box_warp, ptr(W1),
+                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(d_planes), None, ptr(d_ro), ptr(d_rd),
+                 *map(ptr, dws), ptr(work), ws_bytes, st)
         return (d_planes, d_ro, d_rd, *dws, None, None, None, None, None, None, None, None, None)
 
 

@@ -346,6 +346,10 @@ def cupti_kernel_times(fn, nsteps=2):
     return {k: (v[0] / nsteps, v[1] / nsteps) for k, v in agg.items()}
 
 
+def b200eg3d_lib_mod():
+    return __import__('b200eg3d')._lib
+
+
 def time_triplane_bwd(G, resident, dev, iters=10):
     """Average duration of the dominant kernel (backward of the fused tri-plane sampler + decoder, with decoder-parameter
     gradients) launched on its own stream position: the step's real planes, rays and coarse depths, CUDA events around
@@ -367,10 +371,12 @@ def time_triplane_bwd(G, resident, dev, iters=10):
     d_rgb, d_sig = torch.randn(1, P, 32, device=dev) * 1e-3, torch.randn(1, P, device=dev) * 1e-3
     d_pl = torch.zeros_like(pl)
     dws = [torch.zeros_like(x) for x in w]
+    work = torch.empty([b200eg3d_lib_mod().load().b200_triplane_bwd_workspace_bytes(1, P)], device=dev, dtype=torch.uint8)
 
     def launch():
-        call('b200_triplane_mlp_bwd', ptr(pl), 1, pl.shape[1], pl.shape[2], None, ptr(ro.contiguous()), ptr(rd.contiguous()), ptr(t), S, P,
-             float(rk['box_warp']), *map(ptr, w), float(lr_mul), ptr(d_rgb), ptr(d_sig), ptr(d_pl), None, *map(ptr, dws), None, 0, stream())
+        call('b200_triplane_mlp_bwd', ptr(pl), 1, pl.shape[1], pl.shape[2], None, ptr(ro.contiguous()), ptr(rd.contiguous()), ptr(t), S, R, P,
+             float(rk['box_warp']), *map(ptr, w), float(lr_mul), ptr(d_rgb), ptr(d_sig), ptr(d_pl), None, None, None, *map(ptr, dws),
+             ptr(work), work.numel(), stream())
 
     saved, b200eg3d_lib = None, __import__('b200eg3d')._lib
     saved, b200eg3d_lib.PROFILE = b200eg3d_lib.PROFILE, None

@@ -216,8 +216,17 @@ def _decoder(b2, seed):
     return dec, P
 
 
-@pytest.mark.parametrize('npts', [1, 31, 32, 1000])
-def test_run_model_fwd_bwd(b2, npts):
+@pytest.fixture(params=[1, 0], ids=['tcgen05', 'mma_sync'])
+def triplane_impl(request):
+    """Both generations of the fused sampler + decoder stay under test: the tcgen05 pipeline (default) and the mma.sync kernels."""
+    from b200eg3d import _lib
+    prev = _lib.load().b200_set_triplane_impl(request.param)
+    yield request.param
+    _lib.load().b200_set_triplane_impl(prev)
+
+
+@pytest.mark.parametrize('npts', [1, 31, 32, 1000, 5000])
+def test_run_model_fwd_bwd(b2, npts, triplane_impl):
     n, res = 2, 16
     g = gen(npts)
     planes = torch.randn(n, 3, 32, res, res, generator=g)
@@ -251,7 +260,7 @@ def test_run_model_fwd_bwd(b2, npts):
 
 
 @pytest.mark.parametrize('S,S2,white', [(12, 12, False), (16, 0, False), (8, 8, True), (48, 48, False)])
-def test_render_fwd_bwd(b2, S, S2, white):
+def test_render_fwd_bwd(b2, S, S2, white, triplane_impl):
     n, res, R = 1, 32, 12
     M = R * R
     g = gen(S * 7 + S2)
