@@ -671,6 +671,7 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     cudaStream_t st = (cudaStream_t)stream;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
+    if (triplane_impl() == 1 && !d_coords && !d_ray_o && P < (1L << 31)) return triplane_bwd_tc_launch(p, st);
     if (d_ray_o && !d_coords) {          // per-point coordinate gradients staged in the workspace, reduced per ray below
         B200_REQUIRE(workspace && workspace_bytes >= (long)n * P * 12, "triplane_bwd: workspace too small for the ray gradients");
         p.d_coords = static_cast<float*>(workspace);

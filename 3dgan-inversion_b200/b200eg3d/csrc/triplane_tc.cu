@@ -331,6 +331,416 @@ __global__ void __launch_bounds__(FW_THREADS, 1) triplane_fwd_tc_kernel(Triplane
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem, TM_COLS);
 }
+
+// =====================================================================================================================
+// Backward.  Per tile of 128 points the tensor core runs four phases, the consumer threads (thread = point) the steps between:
+//
+//   gather            F (split bf16, as in the forward) -> A1[stage];  bilinear set-up -> SS[stage] (kept for the scatter)
+//   P1  D1 = F W1'^T                    S1  h' = lg2(1 + 2^(D1 + b1'))                    -> A2hi | A2lo (split bf16)
+//   P2  D2 = h' W2'^T                   S2  s = 1/(1 + 2^(D2 + b2')), dO = d_rgb 1.002 s(1-s) | d_sigma   -> A3 (bf16; = A2lo)
+//   P3  D3 = dO W2                      S3  d_a = D3 * 2^y / (1 + 2^y),  y = D1 + b1'  (D1 re-read from TMEM)  -> A2hi (bf16)
+//       ACC2 += [h' ; 1]^T dO                                                         (dW2^T rows 0..63, db2 in rows 64..127)
+//   P4  D4 = d_a W1                     S4  d_f = D4 -> staging (= A2lo) for the scatter warps
+//       ACC1 += [F_hi ; F_lo ; 1]^T d_a                                               (dW1^T rows 0..63, db1 in rows 64..127)
+//   scatter           d_f x bilinear weights -> red.global.add.v4.f32 into the plane gradient
+//
+// The weight / bias gradients are contractions over ALL points: the activation tiles that already sit in shared memory for the
+// chain are read a second time as MN-major operands (K = the 128 points of the tile) and accumulated in two CTA-wide TMEM
+// accumulators for the whole kernel.  The M = 128 instruction reads a second 64-row block at the descriptor's leading-dimension
+// offset; it is pointed at a constant tile of ones, so rows 64..127 of the accumulators are the bias gradients (sum over
+// points) at no extra cost.  One drain per CTA at the end (148 x ~5.3 k global atomics).
+//
+// Gradient operands (dO, d_a) are single bf16 (their rounding errors are independent per point and average out in every
+// consumer: plane texels, weight sums); weights are split bf16 everywhere, the forward recompute is the forward's 3-pass.
+constexpr int BW_NCONS = 8, BW_MMA_WARP = 8, BW_GATHER0 = 9, BW_NGATHER = 8, BW_SCATTER0 = 17, BW_NSCATTER = 4;
+constexpr int BW_THREADS = (BW_NCONS + 1 + BW_NGATHER + BW_NSCATTER) * 32;     // 672
+constexpr int BW_ST = 3;                                       // stages of A1 / SS (tile lt uses stage lt % 3)
+
+constexpr int BO_A1 = 0;                                       // BW_ST x 16384
+constexpr int BO_A2 = BO_A1 + BW_ST * 16384;                   // 2 sets x (hi 16384 | lo 16384); lo doubles as A3 (dO) and as the d_rgb / d_f staging
+constexpr int BO_ONES = BO_A2 + 2 * 32768;                     // [128][64] bf16 ones (second MN block of the weight-gradient A operands)
+constexpr int BO_W1A = BO_ONES + 16384;
+constexpr int BO_W1B = BO_W1A + 8192;
+constexpr int BO_W2H = BO_W1B + 8192;
+constexpr int BO_W2L = BO_W2H + 6144;
+constexpr int BO_W2TH = BO_W2L + 6144;                         // [64 units][64 (k < 33 used)] true W2^T, hi / lo
+constexpr int BO_W2TL = BO_W2TH + 8192;
+constexpr int BO_W1TH = BO_W2TL + 8192;                        // [32 channels][64 units] true W1^T, hi / lo
+constexpr int BO_W1TL = BO_W1TH + 4096;
+constexpr int BO_SS = BO_W1TL + 4096;                          // BW_ST x [128][SP] words
+constexpr int BO_BIAS = BO_SS + BW_ST * TILE * SP * 4;         // b1'[64] | b2'[48]
+constexpr int BO_BAR = BO_BIAS + 512;
+constexpr int BW_SMEM = BO_BAR + 256 + 1024;
+constexpr int BW_TM_COLS = 512;                                // set s at 192 s: D1 +0 (64), D2/D4 +64 (48), D3 +128 (64); ACC2 at 384 (48), ACC1 at 432 (64)
+constexpr int TM_ACC2 = 384, TM_ACC1 = 432;
+
+__device__ __forceinline__ uint32_t bb_a1_full(uint32_t b, int s) { return b + 8u * s; }                  // BW_ST, count 4
+__device__ __forceinline__ uint32_t bb_a1_free(uint32_t b, int s) { return b + 8u * (BW_ST + s); }         // BW_ST, count 1 + BW_NSCATTER
+__device__ __forceinline__ uint32_t bb_set(uint32_t b, int which, int s) { return b + 8u * (2 * BW_ST + 2 * which + s); }
+enum { BB_D1 = 0, BB_A2, BB_D2, BB_A3, BB_D3, BB_A4, BB_D4, BB_DF_FULL, BB_DF_FREE, BB_NSET };
+constexpr int BB_ACC_DONE = 8 * (2 * BW_ST + 2 * BB_NSET), BB_TMEM_SLOT = BB_ACC_DONE + 8;
+
+__device__ void stage_decoder_weights_bwd(const TriplaneParams& p, uint8_t* sm) {
+    for (int i = threadIdx.x; i < HID * 64; i += blockDim.x) {
+        const int j = i >> 6, e = i & 63, c = e & 31;
+        const float w = p.W1[j * C + c] * (p.w1g * LOG2E);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const uint32_t o = sw128(j, e >> 3) + (e & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1A + o) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1B + o) = e < 32 ? __float2bfloat16_rn(w - __bfloat162float(hi)) : __float2bfloat16_rn(0.f);
+        // true W2^T: row j (unit), column k = e (output)
+        const float wt = e < OUT ? p.W2[e * HID + j] * p.w2g : 0.f;
+        const __nv_bfloat16 th = __float2bfloat16_rn(wt);
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W2TH + o) = th;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W2TL + o) = __float2bfloat16_rn(wt - __bfloat162float(th));
+    }
+    for (int i = threadIdx.x; i < OUTP * 64; i += blockDim.x) {
+        const int k = i >> 6, j = i & 63;
+        const float w = k < OUT ? p.W2[k * HID + j] * (k == 0 ? p.w2g * LN2 : -p.w2g) : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const uint32_t o = sw128(k, j >> 3) + (j & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W2H + o) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W2L + o) = __float2bfloat16_rn(w - __bfloat162float(hi));
+    }
+    for (int i = threadIdx.x; i < C * 64; i += blockDim.x) {            // true W1^T: row c (channel), column j (unit)
+        const int c = i >> 6, j = i & 63;
+        const float w = p.W1[j * C + c] * p.w1g;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+        const uint32_t o = sw128(c, j >> 3) + (j & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1TH + o) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1TL + o) = __float2bfloat16_rn(w - __bfloat162float(hi));
+    }
+    for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + BO_ONES)[i] = 0x3f803f80u;   // bf16 1.0 pairs
+    float* bias = reinterpret_cast<float*>(sm + BO_BIAS);
+    for (int i = threadIdx.x; i < HID; i += blockDim.x) bias[i] = p.b1[i] * (p.b1g * LOG2E);
+    for (int i = threadIdx.x; i < OUTP; i += blockDim.x) bias[HID + i] = i < OUT ? p.b2[i] * (i == 0 ? p.b2g : -p.b2g * LOG2E) : 0.f;
+}
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+}
+
+// WGRAD: accumulate the decoder weight / bias gradients (PTI); false = frozen decoder (w-projection).
+template <bool WGRAD>
+__global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(TriplaneParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* sm = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const uint32_t sm_u = smem_u32(sm);
+    const uint32_t B = sm_u + BO_BAR;
+    const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < BW_ST; ++i) { mbar_init(bb_a1_full(B, i), 4); mbar_init(bb_a1_free(B, i), 1 + BW_NSCATTER); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bb_set(B, BB_D1, s), 1); mbar_init(bb_set(B, BB_A2, s), 4); mbar_init(bb_set(B, BB_D2, s), 1);
+            mbar_init(bb_set(B, BB_A3, s), 4); mbar_init(bb_set(B, BB_D3, s), 1); mbar_init(bb_set(B, BB_A4, s), 4);
+            mbar_init(bb_set(B, BB_D4, s), 1); mbar_init(bb_set(B, BB_DF_FULL, s), 4); mbar_init(bb_set(B, BB_DF_FREE, s), BW_NSCATTER);
+        }
+        mbar_init(B + BB_ACC_DONE, 1);
+        fence_barrier_init();
+    }
+    if (warp == BW_MMA_WARP) tmem_alloc(B + BB_TMEM_SLOT, BW_TM_COLS);
+    stage_decoder_weights_bwd(p, sm);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sm + BO_BAR + BB_TMEM_SLOT);
+
+    const long ntiles = (p.P + TILE - 1) / TILE;
+    const long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long t0 = (long)blockIdx.x * per;
+    const int nloc = (int)max(0L, min(ntiles, t0 + per) - t0);
+    const float* pl = p.planes + (long)n * p.hp * p.wp * PC;
+    float* dpl = p.d_planes ? p.d_planes + (long)n * p.hp * p.wp * PC : nullptr;
+    const long row0 = (long)n * p.P;
+
+    if (warp >= BW_SCATTER0) {
+        // ------------------------------------------------------------------ scatter: every tile, rows 32 w .. 32 w + 31
+        const int w = warp - BW_SCATTER0, pt = lane >> 3, l8 = lane & 7;
+        for (int lt = 0; lt < nloc; ++lt) {
+            const int set = lt & 1, st = lt % BW_ST;
+            const uint8_t* stg = sm + BO_A2 + set * 32768 + 16384;               // d_f staging = A2lo[set], fp32 rows, 128-byte swizzle
+            const float* ss = reinterpret_cast<const float*>(sm + BO_SS) + (st * TILE + w * 32) * SP;
+            mbar_wait(bb_set(B, BB_DF_FULL, set), (lt >> 1) & 1);
+            float4 g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = *reinterpret_cast<const float4*>(stg + sw128(w * 32 + i * 4 + pt, l8));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_set(B, BB_DF_FREE, set));              // the staging rows are in registers now
+            if (dpl) {
+                float* pc = dpl + l8 * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float* s = ss + (i * 4 + pt) * SP;
+#pragma unroll
+                    for (int k = 0; k < 12; k += 4) {
+                        const int4 o = *reinterpret_cast<const int4*>(s + k);
+                        const float4 wv = *reinterpret_cast<const float4*>(s + 12 + k);
+                        red_add4(pc + o.x, wv.x, g[i]); red_add4(pc + o.y, wv.y, g[i]); red_add4(pc + o.z, wv.z, g[i]); red_add4(pc + o.w, wv.w, g[i]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_a1_free(B, st));                       // SS[stage] may be rewritten
+        }
+    } else if (warp >= BW_GATHER0) {
+        // ------------------------------------------------------------------ gather: group = tile parity
+        const int g = warp - BW_GATHER0, group = g >> 2, gq = g & 3;
+        for (int lt = group; lt < nloc; lt += 2) {
+            const int st = lt % BW_ST, use = lt / BW_ST;
+            float* ss = reinterpret_cast<float*>(sm + BO_SS) + (st * TILE + gq * 32) * SP;
+            uint8_t* a1 = sm + BO_A1 + st * 16384;
+            float cx, cy, cz;
+            point_coords32(p, n, map_point(p, (unsigned)((t0 + lt) * TILE + gq * 32 + lane)), cx, cy, cz);
+            mbar_wait(bb_a1_free(B, st), (use & 1) ^ 1);          // weight-gradient MMAs and scatter of the tile BW_ST back are done with this stage
+            stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
+            __syncwarp();
+            gather_to_tile(pl, ss, a1, gq * 32, lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_a1_full(B, st));
+        }
+    } else if (warp == BW_MMA_WARP) {
+        // ------------------------------------------------------------------ tensor-core issue (one lane), four cursors
+        if (lane == 0) {
+            const uint32_t id1 = instr_desc_bf16(128, HID, 0, 0), id2 = instr_desc_bf16(128, OUTP, 0, 0);
+            const uint32_t id3 = instr_desc_bf16(128, HID, 0, 0), id4 = instr_desc_bf16(128, C, 0, 0);
+            const uint32_t idw2 = instr_desc_bf16(128, OUTP, 1, 1), idw1 = instr_desc_bf16(128, HID, 1, 1);
+            int n1 = 0, n2 = 0, n3 = 0, n4 = 0;
+            while (n4 < nloc) {
+                bool did = false;
+                if (n4 < n3 && mbar_test(bb_set(B, BB_A4, n4 & 1), (n4 >> 1) & 1)) {          // P4: d_f and dW1
+                    tc_fence_after();
+                    const int s = n4 & 1, st = n4 % BW_ST;
+                    const uint32_t da = sm_u + BO_A2 + s * 32768, d4 = tmem + (uint32_t)(s * 192 + 64);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t a = smem_desc(da + k * 32, 0, 1024);
+                        umma_bf16(d4, a, smem_desc(sm_u + BO_W1TH + k * 32, 0, 1024), id4, k != 0);
+                        umma_bf16(d4, a, smem_desc(sm_u + BO_W1TL + k * 32, 0, 1024), id4, 1);
+                    }
+                    if (WGRAD) {
+                        const uint32_t f = sm_u + BO_A1 + st * 16384, lbo = sm_u + BO_ONES - f;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(tmem + TM_ACC1, smem_desc(f + k * 2048, lbo, 1024), smem_desc(da + k * 2048, 0, 1024), idw1, (n4 | k) != 0);
+                    }
+                    umma_commit(bb_set(B, BB_D4, s));
+                    umma_commit(bb_a1_free(B, st));
+                    ++n4; did = true;
+                }
+                if (n3 < n2 && mbar_test(bb_set(B, BB_A3, n3 & 1), (n3 >> 1) & 1)) {          // P3: dh and dW2
+                    tc_fence_after();
+                    const int s = n3 & 1;
+                    const uint32_t hh = sm_u + BO_A2 + s * 32768, dO = hh + 16384, d3 = tmem + (uint32_t)(s * 192 + 128);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint64_t a = smem_desc(dO + k * 32, 0, 1024);
+                        umma_bf16(d3, a, smem_desc(sm_u + BO_W2TH + k * 32, 0, 1024), id3, k != 0);
+                        umma_bf16(d3, a, smem_desc(sm_u + BO_W2TL + k * 32, 0, 1024), id3, 1);
+                    }
+                    if (WGRAD) {
+                        const uint32_t lbo = sm_u + BO_ONES - hh;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16(tmem + TM_ACC2, smem_desc(hh + k * 2048, lbo, 1024), smem_desc(dO + k * 2048, 0, 1024), idw2, (n3 | k) != 0);
+                    }
+                    umma_commit(bb_set(B, BB_D3, s));
+                    ++n3; did = true;
+                }
+                if (n2 < n1 && mbar_test(bb_set(B, BB_A2, n2 & 1), (n2 >> 1) & 1)) {          // P2: layer 2 (recompute)
+                    tc_fence_after();
+                    const int s = n2 & 1;
+                    const uint32_t ah = sm_u + BO_A2 + s * 32768, al = ah + 16384, d2 = tmem + (uint32_t)(s * 192 + 64);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t dah = smem_desc(ah + k * 32, 0, 1024), dbh = smem_desc(sm_u + BO_W2H + k * 32, 0, 1024);
+                        umma_bf16(d2, dah, dbh, id2, k != 0);
+                        umma_bf16(d2, dah, smem_desc(sm_u + BO_W2L + k * 32, 0, 1024), id2, 1);
+                        umma_bf16(d2, smem_desc(al + k * 32, 0, 1024), dbh, id2, 1);
+                    }
+                    umma_commit(bb_set(B, BB_D2, s));
+                    ++n2; did = true;
+                }
+                if (n1 < nloc && n1 - n4 < 2 && mbar_test(bb_a1_full(B, n1 % BW_ST), (n1 / BW_ST) & 1)) {   // P1: layer 1 (recompute)
+                    tc_fence_after();
+                    const int s = n1 & 1;
+                    const uint32_t a = sm_u + BO_A1 + (n1 % BW_ST) * 16384, d1 = tmem + (uint32_t)(s * 192);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + BO_W1A + k * 32, 0, 1024), id1, k != 0);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + BO_W1B + k * 32, 0, 1024), id1, 1);
+                    umma_commit(bb_set(B, BB_D1, s));
+                    ++n1; did = true;
+                }
+                if (!did) __nanosleep(32);
+            }
+            umma_commit(B + BB_ACC_DONE);
+        }
+    } else {
+        // ------------------------------------------------------------------ consumers: set = tile parity, thread = point = TMEM lane
+        const int set = warp >> 2, q = warp & 3, row = q * 32 + lane;
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 192);
+        uint8_t* a2h = sm + BO_A2 + set * 32768;
+        uint8_t* a2l = a2h + 16384;
+        const float* b1s = reinterpret_cast<const float*>(sm + BO_BIAS);
+        const float* b2s = b1s + HID;
+        int it = 0;
+        for (int lt = set; lt < nloc; lt += 2, ++it) {
+            const unsigned pp0 = (unsigned)((t0 + lt) * TILE + q * 32);
+            const int pi = map_point(p, pp0 + lane);
+            // ---- S1: h' = lg2(1 + 2^y)
+            mbar_wait(bb_set(B, BB_D1, set), it & 1);
+            tc_fence_after();
+            if (it > 0) mbar_wait(bb_set(B, BB_DF_FREE, set), (it - 1) & 1);       // the scatter warps have taken the previous d_f out of A2lo
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tmem_ld32(tq + half * 32, v);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(b1s + half * 32 + c8 * 8 + e);
+                        h[e] = softplus2(v[c8 * 8 + e] + bv.x); h[e + 1] = softplus2(v[c8 * 8 + e + 1] + bv.y);
+                        h[e + 2] = softplus2(v[c8 * 8 + e + 2] + bv.z); h[e + 3] = softplus2(v[c8 * 8 + e + 3] + bv.w);
+                    }
+                    uint4 hi, lo;
+                    split8(h, hi, lo);
+                    const uint32_t o = sw128(row, half * 4 + c8);
+                    *reinterpret_cast<uint4*>(a2h + o) = hi;
+                    *reinterpret_cast<uint4*>(a2l + o) = lo;
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_set(B, BB_A2, set));
+            // ---- S2: dO (A2lo is free once layer 2 has read h' lo).  The incoming gradients of this warp's 32 rows are loaded
+            // coalesced (8 lanes per 128-byte row) while layer 2 runs, and exchanged through the staging rows.
+            float4 dr[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int pr = __shfl_sync(0xffffffffu, pi, i * 4 + (lane >> 3));
+                dr[i] = pr >= 0 ? __ldg(reinterpret_cast<const float4*>(p.d_rgb + (row0 + pr) * C + (lane & 7) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float dsig = pi >= 0 ? __ldg(p.d_sigma + row0 + pi) : 0.f;
+            mbar_wait(bb_set(B, BB_D2, set), it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(a2l + sw128(q * 32 + i * 4 + (lane >> 3), lane & 7)) = dr[i];
+            __syncwarp();
+            {
+                float z[32], z32[8], dO[48];
+                tmem_ld32(tq + 64, z);
+                tmem_ld8(tq + 96, z32);
+                dO[0] = dsig;
+#pragma unroll
+                for (int c4 = 0; c4 < 32; c4 += 4) {
+                    const float4 g4 = *reinterpret_cast<const float4*>(a2l + sw128(row, c4 >> 2));      // own row: d_rgb[c4 .. c4+3]
+                    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int col = c4 + e + 1;
+                        const float s = sigmoid2((col < 32 ? z[col] : z32[0]) + b2s[col]);
+                        dO[col] = gg[e] * 1.002f * s * (1.f - s);
+                    }
+                }
+#pragma unroll
+                for (int k = 33; k < 48; ++k) dO[k] = 0.f;
+                __syncwarp();                                           // every lane has read its staged d_rgb row
+#pragma unroll
+                for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4*>(a2l + sw128(row, c)) = pack8(dO + 8 * c);
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_set(B, BB_A3, set));
+            // ---- S3: d_a = dh * softplus'(u) = dh * 2^y / (1 + 2^y), y re-read from D1
+            mbar_wait(bb_set(B, BB_D3, set), it & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float y[32], dh[32];
+                tmem_ld32(tq + half * 32, y);
+                tmem_ld32(tq + 128 + half * 32, dh);
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float da[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(b1s + half * 32 + c8 * 8 + e);
+                        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float e2 = exp2f(fminf(y[c8 * 8 + e + u] + bb[u], 126.f));
+                            da[e + u] = dh[c8 * 8 + e + u] * __fdividef(e2, 1.f + e2);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(a2h + sw128(row, half * 4 + c8)) = pack8(da);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_set(B, BB_A4, set));
+            // ---- S4: d_f -> staging for the scatter warps
+            mbar_wait(bb_set(B, BB_D4, set), it & 1);
+            tc_fence_after();
+            {
+                float df[32];
+                tmem_ld32(tq + 64, df);
+                tc_fence_before();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4*>(a2l + sw128(row, c)) = make_float4(df[4 * c], df[4 * c + 1], df[4 * c + 2], df[4 * c + 3]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bb_set(B, BB_DF_FULL, set));
+        }
+        // ---- drain of the weight / bias gradient accumulators (set 0's four warps cover the 128 TMEM lanes)
+        if (WGRAD && set == 0 && nloc > 0) {
+            mbar_wait(B + BB_ACC_DONE, 0);
+            tc_fence_after();
+            const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+            float v[32];
+            if (q < 2) {                                    // lanes 0..63: dW2^T[j][k] (h' = h / ln2) and dW1^T[c | 32 + c][j] (hi | lo part of F)
+                const int j = q * 32 + lane;
+                tmem_ld32(tl + TM_ACC2, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) atomicAdd(p.dW2 + k * HID + j, v[k] * (LN2 * p.w2g));
+                tmem_ld32(tl + TM_ACC2 + 32, v);            // columns 32..47 of ACC2, then 16 columns of ACC1
+                atomicAdd(p.dW2 + 32 * HID + j, v[0] * (LN2 * p.w2g));
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld32(tl + TM_ACC1 + half * 32, v);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) atomicAdd(p.dW1 + (half * 32 + jj) * C + lane, v[jj] * p.w1g);
+                }
+            } else if (q == 2) {                            // lane 64 (first lane of this warp): the ones row = bias gradients
+                tmem_ld32(tl + TM_ACC2, v);                 // tcgen05.ld is warp-collective: all lanes load, lane 0 publishes
+                if (lane == 0)
+                    for (int k = 0; k < 32; ++k) atomicAdd(p.db2 + k, v[k] * p.b2g);
+                tmem_ld32(tl + TM_ACC2 + 32, v);
+                if (lane == 0) atomicAdd(p.db2 + 32, v[0] * p.b2g);
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld32(tl + TM_ACC1 + half * 32, v);
+                    if (lane == 0)
+                        for (int jj = 0; jj < 32; ++jj) atomicAdd(p.db1 + half * 32 + jj, v[jj] * p.b1g);
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == BW_MMA_WARP) tmem_dealloc(tmem, BW_TM_COLS);
+}
 }  // namespace
 
 extern int g_b200_mlp_passes;
@@ -344,6 +754,18 @@ int triplane_fwd_tc_launch(tri::TriplaneParams& p, bool sigma_only, cudaStream_t
     dim3 grid((unsigned)(ntiles < sms ? ntiles : sms), p.n);              // persistent: one CTA per SM, contiguous tile ranges
     if (sigma_only) triplane_fwd_tc_kernel<true><<<grid, FW_THREADS, FW_SMEM, st>>>(p);
     else triplane_fwd_tc_kernel<false><<<grid, FW_THREADS, FW_SMEM, st>>>(p);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
+int triplane_bwd_tc_launch(tri::TriplaneParams& p, cudaStream_t st) {
+    B200_FUNC_ATTR_ONCE(triplane_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    B200_FUNC_ATTR_ONCE(triplane_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    const long ntiles = (p.P + TILE - 1) / TILE;
+    const int sms = b200_sm_count();
+    dim3 grid((unsigned)(ntiles < sms ? ntiles : sms), p.n);
+    if (p.dW1) triplane_bwd_tc_kernel<true><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
+    else triplane_bwd_tc_kernel<false><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
 }

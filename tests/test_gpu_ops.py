@@ -225,8 +225,9 @@ def triplane_impl(request):
     _lib.load().b200_set_triplane_impl(prev)
 
 
+@pytest.mark.parametrize('coord_grad', [True, False], ids=['dcoords', 'nodcoords'])
 @pytest.mark.parametrize('npts', [1, 31, 32, 1000, 5000])
-def test_run_model_fwd_bwd(b2, npts, triplane_impl):
+def test_run_model_fwd_bwd(b2, npts, triplane_impl, coord_grad):
     n, res = 2, 16
     g = gen(npts)
     planes = torch.randn(n, 3, 32, res, res, generator=g)
@@ -244,7 +245,7 @@ def test_run_model_fwd_bwd(b2, npts, triplane_impl):
     for p in dec.parameters():
         p.requires_grad_(True)
     pl = planes.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96).contiguous().cuda().requires_grad_(True)
-    cc = coords.cuda().requires_grad_(True)
+    cc = coords.cuda().requires_grad_(coord_grad)        # without coordinate gradients the tcgen05 backward is taken (PTI shape)
     out = b2.ImportanceRenderer().run_model(pl, dec, cc, None, rk)
     (out['rgb'] * d_rgb.cuda()).sum().add((out['sigma'] * d_sig.cuda()).sum()).backward()
     assert maxdiff(out['rgb'], rgb_ref) < 2e-5
@@ -252,7 +253,8 @@ def test_run_model_fwd_bwd(b2, npts, triplane_impl):
     dpl_ref = pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)
     # the backward decoder GEMMs run single-pass TF32 on the tensor cores (the forward keeps the 3-pass split): ~5e-4 relative
     assert relerr(pl.grad, dpl_ref) < 3e-3
-    assert relerr(cc.grad, cr.grad) < 3e-3
+    if coord_grad:
+        assert relerr(cc.grad, cr.grad) < 3e-3
     for k, v in dec.named_parameters():
         # dW1 / dW2 are contracted over the points from bf16 operands: rounding averages out over the ~1e6 points of a real
         # pass, with a handful of points it is ~4e-3
@@ -260,7 +262,8 @@ def test_run_model_fwd_bwd(b2, npts, triplane_impl):
 
 
 @pytest.mark.parametrize('S,S2,white', [(12, 12, False), (16, 0, False), (8, 8, True), (48, 48, False)])
-def test_render_fwd_bwd(b2, S, S2, white, triplane_impl):
+@pytest.mark.parametrize('ray_grad', [True, False], ids=['drays', 'nodrays'])
+def test_render_fwd_bwd(b2, S, S2, white, triplane_impl, ray_grad):
     n, res, R = 1, 32, 12
     M = R * R
     g = gen(S * 7 + S2)
@@ -289,15 +292,16 @@ def test_render_fwd_bwd(b2, S, S2, white, triplane_impl):
     ren = b2.ImportanceRenderer()
     ren.fixed_noise = (u1, u2)
     pl = planes.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96).contiguous().cuda().requires_grad_(True)
-    roc, rdc = ro.cuda().requires_grad_(True), rd.cuda().requires_grad_(True)
+    roc, rdc = ro.cuda().requires_grad_(ray_grad), rd.cuda().requires_grad_(ray_grad)
     f, d, w = ren(pl, dec, roc, rdc, rk)
     ((f * dfeat.cuda()).sum() + (d * ddepth.cuda()).sum() + (w * dws.cuda()).sum()).backward()
     assert maxdiff(f, f_ref) < 5e-5
     assert maxdiff(d, d_ref) < 5e-5
     assert maxdiff(w, w_ref) < 5e-5
     assert relerr(pl.grad, pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)) < 5e-3
-    assert relerr(roc.grad, ror.grad) < 1e-2
-    assert relerr(rdc.grad, rdr.grad) < 1e-2
+    if ray_grad:
+        assert relerr(roc.grad, ror.grad) < 1e-2
+        assert relerr(rdc.grad, rdr.grad) < 1e-2
     for k, v in dec.named_parameters():
         assert relerr(v.grad, Pr['decoder.' + k].grad) < 1e-2, k
 
