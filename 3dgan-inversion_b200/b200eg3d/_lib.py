@@ -37,8 +37,8 @@ SIGNATURES = {
     'b200_layer_act_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_upfirdn2d': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'b200_upfirdn2d_fused': [_P] * 6 + [_I] * 13 + [_F, _I, _P, _P, _P, _L, _I, _F, _F, _F, _P],
-    'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P],
-    'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
+    'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P],
+    'b200_triplane_mlp_bwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
     'b200_pti_loss_fwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P],
     'b200_pti_loss_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P, _P],
     'b200_warp_uv_fwd': [_P, _P, _P, _P, _P, _I, _P, _P, _P],
@@ -97,6 +97,8 @@ def load():
     lib.b200_conv_tc_supported.restype = ctypes.c_int
     lib.b200_triplane_bwd_workspace_bytes.restype = ctypes.c_long
     lib.b200_triplane_bwd_workspace_bytes.argtypes = [_I, _L]
+    lib.b200_triplane_fsave_bytes.restype = ctypes.c_long
+    lib.b200_triplane_fsave_bytes.argtypes = [_I, _L]
     lib.b200_conv_tc_supported.argtypes = [_I] * 7
     lib.b200_conv_tc_act_fusable.restype = ctypes.c_int
     lib.b200_conv_tc_act_fusable.argtypes = [_I] * 6

@@ -567,7 +567,9 @@ int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, c
     p.planes = planes; p.n = n; p.hp = hp; p.wp = wp; p.coords = coords; p.ray_o = ray_o; p.ray_d = ray_d; p.depths = depths;
     B200_REQUIRE(ray_w >= 0 && (ray_w == 0 || coords || (P / S) % ray_w == 0), "triplane: ray_w must divide the ray count");
     p.S = S; p.ray_w = coords ? 0 : ray_w; p.P = P; p.coord_scale = 2.f / box_warp;
-    p.M = coords ? 0 : P / S; p.ray_h = p.ray_w > 0 ? (int)(p.M / p.ray_w) : 0; p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
+    p.M = coords ? 0 : P / S; p.ray_h = p.ray_w > 0 ? (int)(p.M / p.ray_w) : 0;
+    if (p.ray_w > 0 && (p.ray_w % 8 != 0 || p.ray_h % 16 != 0)) p.ray_w = p.ray_h = 0;      // patch order needs whole 8 x 16 patches
+    p.W1 = W1; p.b1 = b1; p.W2 = W2; p.b2 = b2;
     p.w1g = lr_mul / sqrtf((float)C); p.b1g = lr_mul; p.w2g = lr_mul / sqrtf((float)HID); p.b2g = lr_mul;
     return 0;
 }
@@ -579,7 +581,7 @@ int fill_common(TriplaneParams& p, const float* planes, int n, int hp, int wp, c
 B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                                    const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp,
                                    const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
-                                   float* rgb, float* sigma, void* stream) {
+                                   float* rgb, float* sigma, void* f_save, void* stream) {
     TriplaneParams p{};
     if (int e = fill_common(p, planes, n, hp, wp, coords, ray_o, ray_d, depths, S, ray_w, P, box_warp, W1, b1, W2, b2, lr_mul)) return e;
     B200_REQUIRE(sigma, "triplane_fwd: null output");        // rgb == NULL: density-only query
@@ -594,6 +596,7 @@ B200_API int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, c
     B200_FUNC_ATTR_ONCE(triplane_mlp_fwd_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
     B200_FUNC_ATTR_ONCE(triplane_mlp_fwd_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
     p.fwd_passes = g_b200_mlp_passes;
+    p.f_save = triplane_impl() == 1 ? static_cast<uint8_t*>(f_save) : nullptr;      // only the tcgen05 kernels produce / consume it
     if (triplane_impl() == 1 && P < (1L << 31)) return triplane_fwd_tc_launch(p, rgb == nullptr, (cudaStream_t)stream);
     const long g512 = (P + FW_WARPS * 32 - 1) / (FW_WARPS * 32);
     grid.x = (unsigned)(g512 < 148 ? g512 : 148);                      // persistent: one 16-warp CTA per SM
@@ -617,6 +620,13 @@ B200_API int b200_set_mlp_passes(int passes) {
     const int prev = g_b200_mlp_passes == 0 ? 3 : g_b200_mlp_passes;
     g_b200_mlp_passes = passes == 1 ? 1 : 3;
     return prev;
+}
+
+// Size of the optional forward -> backward hand-off buffer: every 128-point tile's mean features as the finished layer-1
+// tensor-core operand (split bf16, 128 bytes per point).  With it the backward reloads the features with one bulk copy per tile
+// instead of gathering the 12 texel lines per point a second time (the kernels are L2-bandwidth bound on exactly that gather).
+B200_API long b200_triplane_fsave_bytes(int n, long P) {
+    return (long)n * ((P + 127) / 128) * 16384;
 }
 
 // Scratch the backward may need: the per-point coordinate gradients (12 B / point, when per-ray sums are requested without
@@ -652,12 +662,13 @@ __global__ void ray_reduce_dpoints_kernel(const float* __restrict__ d_pts, const
 // d_planes [n][hp][wp][96] is ACCUMULATED into (zero it first); d_coords [n][P][3] is written (may be null);
 // d_ray_o / d_ray_d [n][P/S][3] (ray mode; both or neither; may be null) are ACCUMULATED into: the per-ray sums of d point and
 // t * d point, i.e. the gradients of the ray origins / directions;  dW1/db1/dW2/db2 are ACCUMULATED into (all four null =>
-// parameter gradients skipped).  `workspace`: b200_triplane_bwd_workspace_bytes(n, P) bytes of scratch (may be null when neither
+// parameter gradients skipped).  f_saved: the buffer the forward filled through its f_save argument for the SAME points, ray_w and
+// implementation setting (may be null: the features are then gathered again).  `workspace`: b200_triplane_bwd_workspace_bytes(n, P) bytes of scratch (may be null when neither
 // d_ray_o nor the tcgen05 implementation needs it).
 B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                                    const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp,
                                    const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
-                                   const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
+                                   const float* d_rgb, const float* d_sigma, const void* f_saved, float* d_planes, float* d_coords,
                                    float* d_ray_o, float* d_ray_d,
                                    float* dW1, float* db1, float* dW2, float* db2, void* workspace, long workspace_bytes,
                                    void* stream) {
@@ -671,7 +682,9 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     cudaStream_t st = (cudaStream_t)stream;
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
-    if (triplane_impl() == 1 && !d_coords && !d_ray_o && P < (1L << 31)) return triplane_bwd_tc_launch(p, st);
+    p.f_saved = static_cast<const uint8_t*>(f_saved);
+    // tcgen05 pipeline: needs the forward's feature tiles; coordinate / ray gradients (w-projection) take the mma.sync kernel
+    if (triplane_impl() == 1 && f_saved && !d_coords && !d_ray_o && P < (1L << 31)) return triplane_bwd_tc_launch(p, st);
     if (d_ray_o && !d_coords) {          // per-point coordinate gradients staged in the workspace, reduced per ray below
         B200_REQUIRE(workspace && workspace_bytes >= (long)n * P * 12, "triplane_bwd: workspace too small for the ray gradients");
         p.d_coords = static_cast<float*>(workspace);

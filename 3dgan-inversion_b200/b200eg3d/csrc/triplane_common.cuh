@@ -30,19 +30,28 @@ struct TriplaneParams {
     int ray_w, ray_h;                                       // ray mode: ray image width / height for the column-major work order (0: linear order)
     long M;                                                 // ray mode: rays per sample = P / S
     float* d_ray_o; float* d_ray_d;                         // backward, ray mode: per-ray sums of d point and t * d point (may be null)
-    __nv_bfloat16* df_out;                                  // backward: d feature per point as bf16 [n][P][32] for the plane pass (may be null)
+    uint8_t* f_save;                                        // forward: [n][ceil(P/128)][16384] image of every tile's layer-1 operand (may be null)
+    const uint8_t* f_saved;                                 // backward: the same buffer
 };
 
-// Work order of the tcgen05 kernels.  In ray mode with a known image width the rays can be walked COLUMN by column
-// (work ray r' = j * Rh + i  <->  stored ray m = i * Rw + j).  Returns the stored point index of work point pp, or -1 past
-// the end.  32-bit arithmetic: the launch code guarantees P < 2^31 (64-bit divisions cost ~100 instructions each).
+// Work order of the tcgen05 kernels.  The kernels are bound by L2 bandwidth (12 texel lines gathered per point), so the order
+// in which a CTA walks its points decides how much of that traffic its L1 absorbs.  In ray mode with a known image size a tile
+// of 128 work points is a PATCH of 8 x 16 neighbouring pixels at ONE depth index (tile T = patch * S + k; the tiles of a CTA are
+// consecutive, i.e. it marches one patch front to back): on all three planes the 128 points fall into a compact window of
+// texels (neighbouring rays are ~1.3 texels apart), most of which the next depth index touches again.
+// ray_w <= 0, or an image that is not a multiple of 8 x 16: linear order.
+// Returns the stored point index of work point pp, or -1 past the end.  32-bit arithmetic: the launch code guarantees
+// P < 2^31 (64-bit divisions cost ~100 instructions each).
 __device__ __forceinline__ int map_point(const TriplaneParams& p, unsigned pp) {
     if (pp >= (unsigned)p.P) return -1;
     if (p.coords || p.ray_w <= 0) return (int)pp;
-    const unsigned S = (unsigned)p.S, Rh = (unsigned)p.ray_h;
-    const unsigned r = pp / S, k = pp - r * S;
-    const unsigned j = r / Rh, i = r - j * Rh;
-    return (int)((i * (unsigned)p.ray_w + j) * S + k);
+    const unsigned S = (unsigned)p.S, Rw = (unsigned)p.ray_w;
+    const unsigned T = pp >> 7, r = pp & 127u;
+    const unsigned patch = T / S, k = T - patch * S;
+    const unsigned ppr = Rw >> 3;                               // patches per image row
+    const unsigned pr = patch / ppr, pc = patch - pr * ppr;
+    const unsigned i = pr * 16u + (r >> 3), j = pc * 8u + (r & 7u);
+    return (int)((i * Rw + j) * S + k);
 }
 
 // coordinates (grid units) of stored point pi of sample n (pi < 0: zeros); 32-bit index arithmetic

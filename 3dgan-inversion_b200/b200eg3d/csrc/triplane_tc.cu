@@ -108,7 +108,10 @@ __device__ void stage_decoder_weights(const TriplaneParams& p, uint8_t* sm) {
 // Gather the mean feature of 32 points (rows row0 .. row0+31 of the tile) into the layer-1 A tile as split bf16.
 // Eight lanes share a point (4 channels each, one LDG.128 per texel): one warp instruction fetches the same texel slot of four
 // points = four full 128-byte lines.  Row layout: chunks 0-3 = hi channels 0..31, chunks 4-7 = lo channels 0..31.
-__device__ __forceinline__ void gather_to_tile(const float* __restrict__ pl, const float* ss, uint8_t* a1, int row0, int lane) {
+// fsave (may be null): global image of the tile (same swizzled layout) kept for the backward, which then reloads the features
+// with one bulk copy per tile instead of gathering the 12 texel lines per point again.
+__device__ __forceinline__ void gather_to_tile(const float* __restrict__ pl, const float* ss, uint8_t* a1, int row0, int lane,
+                                               uint8_t* __restrict__ fsave = nullptr) {
     const int pt = lane >> 3, l8 = lane & 7;
     const float* pc = pl + l8 * 4;
 #pragma unroll 2
@@ -132,7 +135,9 @@ __device__ __forceinline__ void gather_to_tile(const float* __restrict__ pl, con
         const bool odd = l8 & 1;
         const uint32_t rx = __shfl_xor_sync(0xffffffffu, odd ? h01 : l01, 1), ry = __shfl_xor_sync(0xffffffffu, odd ? h23 : l23, 1);
         const uint4 v = odd ? make_uint4(rx, ry, l01, l23) : make_uint4(h01, h23, rx, ry);
-        *reinterpret_cast<uint4*>(a1 + sw128(row, (odd ? 4 : 0) + (l8 >> 1))) = v;
+        const uint32_t off = sw128(row, (odd ? 4 : 0) + (l8 >> 1));
+        *reinterpret_cast<uint4*>(a1 + off) = v;
+        if (fsave) *reinterpret_cast<uint4*>(fsave + off) = v;         // the 8 lanes of a point write one full 128-byte line
     }
 }
 
@@ -144,6 +149,22 @@ __device__ __forceinline__ uint32_t bar_d1_full(uint32_t b, int s) { return b + 
 __device__ __forceinline__ uint32_t bar_a2_full(uint32_t b, int s) { return b + 8u * (2 * NGRP + 2 + s); }   // 2, count 4
 __device__ __forceinline__ uint32_t bar_d2_full(uint32_t b, int s) { return b + 8u * (2 * NGRP + 4 + s); }   // 2
 constexpr int BAR_TMEM_SLOT = 8 * (2 * NGRP + 6);
+
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// Wait that is expected to be long (a producer several pipeline stages away): back off between probes so that the spinning
+// warp does not take issue slots from the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok) __nanosleep(64);
+    } while (!ok);
+}
 
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {          // non-blocking probe
     uint32_t ok;
@@ -193,7 +214,7 @@ __global__ void __launch_bounds__(FW_THREADS, 1) triplane_fwd_tc_kernel(Triplane
             stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
             mbar_wait(bar_a1_empty(B, group), (it & 1) ^ 1);           // layer 1 of the tile NGRP back has consumed this stage
             __syncwarp();
-            gather_to_tile(pl, ss, a1, gq * 32, lane);
+            gather_to_tile(pl, ss, a1, gq * 32, lane, p.f_save ? p.f_save + ((long)n * ntiles + t0 + lt) * 16384 : nullptr);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_a1_full(B, group));
@@ -352,30 +373,30 @@ __global__ void __launch_bounds__(FW_THREADS, 1) triplane_fwd_tc_kernel(Triplane
 //
 // Gradient operands (dO, d_a) are single bf16 (their rounding errors are independent per point and average out in every
 // consumer: plane texels, weight sums); weights are split bf16 everywhere, the forward recompute is the forward's 3-pass.
-constexpr int BW_NCONS = 8, BW_MMA_WARP = 8, BW_GATHER0 = 9, BW_NGATHER = 8, BW_SCATTER0 = 17, BW_NSCATTER = 4;
-constexpr int BW_THREADS = (BW_NCONS + 1 + BW_NGATHER + BW_NSCATTER) * 32;     // 672
-constexpr int BW_ST = 3;                                       // stages of A1 / SS (tile lt uses stage lt % 3)
+constexpr int BW_NCONS = 8, BW_MMA_WARP = 8, BW_LOAD_WARP = 9, BW_SCATTER0 = 10, BW_NSCATTER = 8;
+constexpr int BW_THREADS = (BW_NCONS + 2 + BW_NSCATTER) * 32;                   // 576
+constexpr int BW_ST = 3;                                       // stages of A1 (tile lt uses stage lt % 3); recycled as soon as S1 has copied F out
 
 constexpr int BO_A1 = 0;                                       // BW_ST x 16384
-constexpr int BO_A2 = BO_A1 + BW_ST * 16384;                   // 2 sets x (hi 16384 | lo 16384); lo doubles as A3 (dO) and as the d_rgb / d_f staging
-constexpr int BO_ONES = BO_A2 + 2 * 32768;                     // [128][64] bf16 ones (second MN block of the weight-gradient A operands)
-constexpr int BO_W1A = BO_ONES + 16384;
-constexpr int BO_W1B = BO_W1A + 8192;
-constexpr int BO_W2H = BO_W1B + 8192;
-constexpr int BO_W2L = BO_W2H + 6144;
-constexpr int BO_W2TH = BO_W2L + 6144;                         // [64 units][64 (k < 33 used)] true W2^T, hi / lo
+constexpr int BO_FC = BO_A1 + BW_ST * 16384;                   // 2 sets x [128][64] bf16: copy of the tile's F (hi half used) for the dW1 contraction
+constexpr int BO_A2 = BO_FC + 2 * 16384;                       // 2 sets x (hi 16384 | lo 16384); lo doubles as A3 (dO) and as the d_rgb / d_f staging
+constexpr int BO_W1A = BO_A2 + 2 * 32768;                      // [64][W1'_hi | W1'_hi]   (recompute: activations split, weights hi)
+constexpr int BO_W2H = BO_W1A + 8192;                          // [48][64] W2'_hi
+constexpr int BO_W2TH = BO_W2H + 6144;                         // [64 units][64 (k < 33 used)] true W2^T, hi / lo
 constexpr int BO_W2TL = BO_W2TH + 8192;
 constexpr int BO_W1TH = BO_W2TL + 8192;                        // [32 channels][64 units] true W1^T, hi / lo
 constexpr int BO_W1TL = BO_W1TH + 4096;
-constexpr int BO_SS = BO_W1TL + 4096;                          // BW_ST x [128][SP] words
-constexpr int BO_BIAS = BO_SS + BW_ST * TILE * SP * 4;         // b1'[64] | b2'[48]
+constexpr int BO_ONES = BO_W1TL + 4096;                        // [16][64] bf16 ones: second MN block of every k-step of the weight-gradient A operands
+constexpr int BO_SS = BO_ONES + 2048;                          // private set-up tiles of the scatter warps, [32][SP] words each
+constexpr int BO_BIAS = BO_SS + BW_NSCATTER * 32 * SP * 4;      // b1'[64] | b2'[48]
 constexpr int BO_BAR = BO_BIAS + 512;
 constexpr int BW_SMEM = BO_BAR + 256 + 1024;
 constexpr int BW_TM_COLS = 512;                                // set s at 192 s: D1 +0 (64), D2/D4 +64 (48), D3 +128 (64); ACC2 at 384 (48), ACC1 at 432 (64)
 constexpr int TM_ACC2 = 384, TM_ACC1 = 432;
+static_assert(BW_SMEM <= 227 * 1024, "backward kernel shared memory");
 
 __device__ __forceinline__ uint32_t bb_a1_full(uint32_t b, int s) { return b + 8u * s; }                  // BW_ST, count 4
-__device__ __forceinline__ uint32_t bb_a1_free(uint32_t b, int s) { return b + 8u * (BW_ST + s); }         // BW_ST, count 1 + BW_NSCATTER
+__device__ __forceinline__ uint32_t bb_a1_free(uint32_t b, int s) { return b + 8u * (BW_ST + s); }         // BW_ST, count 4 (consumer warps after copying F)
 __device__ __forceinline__ uint32_t bb_set(uint32_t b, int which, int s) { return b + 8u * (2 * BW_ST + 2 * which + s); }
 enum { BB_D1 = 0, BB_A2, BB_D2, BB_A3, BB_D3, BB_A4, BB_D4, BB_DF_FULL, BB_DF_FREE, BB_NSET };
 constexpr int BB_ACC_DONE = 8 * (2 * BW_ST + 2 * BB_NSET), BB_TMEM_SLOT = BB_ACC_DONE + 8;
@@ -387,7 +408,6 @@ __device__ void stage_decoder_weights_bwd(const TriplaneParams& p, uint8_t* sm) 
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const uint32_t o = sw128(j, e >> 3) + (e & 7) * 2;
         *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1A + o) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1B + o) = e < 32 ? __float2bfloat16_rn(w - __bfloat162float(hi)) : __float2bfloat16_rn(0.f);
         // true W2^T: row j (unit), column k = e (output)
         const float wt = e < OUT ? p.W2[e * HID + j] * p.w2g : 0.f;
         const __nv_bfloat16 th = __float2bfloat16_rn(wt);
@@ -400,7 +420,6 @@ __device__ void stage_decoder_weights_bwd(const TriplaneParams& p, uint8_t* sm) 
         const __nv_bfloat16 hi = __float2bfloat16_rn(w);
         const uint32_t o = sw128(k, j >> 3) + (j & 7) * 2;
         *reinterpret_cast<__nv_bfloat16*>(sm + BO_W2H + o) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(sm + BO_W2L + o) = __float2bfloat16_rn(w - __bfloat162float(hi));
     }
     for (int i = threadIdx.x; i < C * 64; i += blockDim.x) {            // true W1^T: row c (channel), column j (unit)
         const int c = i >> 6, j = i & 63;
@@ -410,7 +429,7 @@ __device__ void stage_decoder_weights_bwd(const TriplaneParams& p, uint8_t* sm) 
         *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1TH + o) = hi;
         *reinterpret_cast<__nv_bfloat16*>(sm + BO_W1TL + o) = __float2bfloat16_rn(w - __bfloat162float(hi));
     }
-    for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + BO_ONES)[i] = 0x3f803f80u;   // bf16 1.0 pairs
+    for (int i = threadIdx.x; i < 2048 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm + BO_ONES)[i] = 0x3f803f80u;    // bf16 1.0 pairs
     float* bias = reinterpret_cast<float*>(sm + BO_BIAS);
     for (int i = threadIdx.x; i < HID; i += blockDim.x) bias[i] = p.b1[i] * (p.b1g * LOG2E);
     for (int i = threadIdx.x; i < OUTP; i += blockDim.x) bias[HID + i] = i < OUT ? p.b2[i] * (i == 0 ? p.b2g : -p.b2g * LOG2E) : 0.f;
@@ -431,11 +450,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
     const int n = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < BW_ST; ++i) { mbar_init(bb_a1_full(B, i), 4); mbar_init(bb_a1_free(B, i), 1 + BW_NSCATTER); }
+        for (int i = 0; i < BW_ST; ++i) { mbar_init(bb_a1_full(B, i), 1); mbar_init(bb_a1_free(B, i), 4); }
         for (int s = 0; s < 2; ++s) {
             mbar_init(bb_set(B, BB_D1, s), 1); mbar_init(bb_set(B, BB_A2, s), 4); mbar_init(bb_set(B, BB_D2, s), 1);
             mbar_init(bb_set(B, BB_A3, s), 4); mbar_init(bb_set(B, BB_D3, s), 1); mbar_init(bb_set(B, BB_A4, s), 4);
-            mbar_init(bb_set(B, BB_D4, s), 1); mbar_init(bb_set(B, BB_DF_FULL, s), 4); mbar_init(bb_set(B, BB_DF_FREE, s), BW_NSCATTER);
+            mbar_init(bb_set(B, BB_D4, s), 1); mbar_init(bb_set(B, BB_DF_FULL, s), 4); mbar_init(bb_set(B, BB_DF_FREE, s), 4);
         }
         mbar_init(B + BB_ACC_DONE, 1);
         fence_barrier_init();
@@ -458,17 +477,23 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
 
     if (warp >= BW_SCATTER0) {
         // ------------------------------------------------------------------ scatter: every tile, rows 32 w .. 32 w + 31
-        const int w = warp - BW_SCATTER0, pt = lane >> 3, l8 = lane & 7;
-        for (int lt = 0; lt < nloc; ++lt) {
-            const int set = lt & 1, st = lt % BW_ST;
-            const uint8_t* stg = sm + BO_A2 + set * 32768 + 16384;               // d_f staging = A2lo[set], fp32 rows, 128-byte swizzle
-            const float* ss = reinterpret_cast<const float*>(sm + BO_SS) + (st * TILE + w * 32) * SP;
-            mbar_wait(bb_set(B, BB_DF_FULL, set), (lt >> 1) & 1);
+        // The bilinear set-up (12 texel offsets + 12 weights per point) is recomputed here from the point's coordinates rather than
+        // kept from the gather: that would tie a 12 KB buffer per tile to the whole length of the chain.
+        // Eight warps: group sg = (warp - BW_SCATTER0) / 4 serves the tiles of consumer set sg.
+        const int sw = warp - BW_SCATTER0, sg = sw >> 2, w = sw & 3, pt = lane >> 3, l8 = lane & 7;
+        float* ss = reinterpret_cast<float*>(sm + BO_SS) + sw * 32 * SP;
+        const uint8_t* stg = sm + BO_A2 + sg * 32768 + 16384;                    // d_f staging = A2lo[set], fp32 rows, 128-byte swizzle
+        int it = 0;
+        for (int lt = sg; lt < nloc; lt += 2, ++it) {
+            float cx, cy, cz;
+            point_coords32(p, n, map_point(p, (unsigned)((t0 + lt) * TILE + w * 32 + lane)), cx, cy, cz);
+            stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
+            mbar_wait_sleep(bb_set(B, BB_DF_FULL, sg), it & 1);
             float4 g[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i] = *reinterpret_cast<const float4*>(stg + sw128(w * 32 + i * 4 + pt, l8));
             __syncwarp();
-            if (lane == 0) mbar_arrive(bb_set(B, BB_DF_FREE, set));              // the staging rows are in registers now
+            if (lane == 0) mbar_arrive(bb_set(B, BB_DF_FREE, sg));               // the staging rows are in registers now
             if (dpl) {
                 float* pc = dpl + l8 * 4;
 #pragma unroll
@@ -483,24 +508,18 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bb_a1_free(B, st));                       // SS[stage] may be rewritten
         }
-    } else if (warp >= BW_GATHER0) {
-        // ------------------------------------------------------------------ gather: group = tile parity
-        const int g = warp - BW_GATHER0, group = g >> 2, gq = g & 3;
-        for (int lt = group; lt < nloc; lt += 2) {
-            const int st = lt % BW_ST, use = lt / BW_ST;
-            float* ss = reinterpret_cast<float*>(sm + BO_SS) + (st * TILE + gq * 32) * SP;
-            uint8_t* a1 = sm + BO_A1 + st * 16384;
-            float cx, cy, cz;
-            point_coords32(p, n, map_point(p, (unsigned)((t0 + lt) * TILE + gq * 32 + lane)), cx, cy, cz);
-            mbar_wait(bb_a1_free(B, st), (use & 1) ^ 1);          // weight-gradient MMAs and scatter of the tile BW_ST back are done with this stage
-            stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
-            __syncwarp();
-            gather_to_tile(pl, ss, a1, gq * 32, lane);
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bb_a1_full(B, st));
+    } else if (warp == BW_LOAD_WARP) {
+        // ------------------------------------------------------------------ loader: the forward kept every tile's features as the
+        // finished layer-1 operand (split bf16, swizzled): one 16 KB bulk copy per tile, completion counted on the stage's mbarrier
+        if (lane == 0) {
+            const uint8_t* src = p.f_saved + ((long)n * ntiles + t0) * 16384;
+            for (int lt = 0; lt < nloc; ++lt) {
+                const int st = lt % BW_ST, use = lt / BW_ST;
+                mbar_wait_sleep(bb_a1_free(B, st), (use & 1) ^ 1);    // layer 1 of the tile BW_ST back is done and its F has been copied out
+                mbar_arrive_expect_tx(bb_a1_full(B, st), 16384);
+                bulk_load(sm_u + BO_A1 + st * 16384, src + (long)lt * 16384, 16384, bb_a1_full(B, st));
+            }
         }
     } else if (warp == BW_MMA_WARP) {
         // ------------------------------------------------------------------ tensor-core issue (one lane), four cursors
@@ -513,7 +532,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                 bool did = false;
                 if (n4 < n3 && mbar_test(bb_set(B, BB_A4, n4 & 1), (n4 >> 1) & 1)) {          // P4: d_f and dW1
                     tc_fence_after();
-                    const int s = n4 & 1, st = n4 % BW_ST;
+                    const int s = n4 & 1;
                     const uint32_t da = sm_u + BO_A2 + s * 32768, d4 = tmem + (uint32_t)(s * 192 + 64);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -522,13 +541,13 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                         umma_bf16(d4, a, smem_desc(sm_u + BO_W1TL + k * 32, 0, 1024), id4, 1);
                     }
                     if (WGRAD) {
-                        const uint32_t f = sm_u + BO_A1 + st * 16384, lbo = sm_u + BO_ONES - f;
+                        const uint32_t f = sm_u + BO_FC + s * 16384;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            umma_bf16(tmem + TM_ACC1, smem_desc(f + k * 2048, lbo, 1024), smem_desc(da + k * 2048, 0, 1024), idw1, (n4 | k) != 0);
+                        for (int k = 0; k < 8; ++k)            // rows 64..127 of the M = 128 operand: the 16 x 64 ones block, for every k-step
+                            umma_bf16(tmem + TM_ACC1, smem_desc(f + k * 2048, sm_u + BO_ONES - (f + k * 2048), 1024), smem_desc(da + k * 2048, 0, 1024),
+                                      idw1, (n4 | k) != 0);
                     }
                     umma_commit(bb_set(B, BB_D4, s));
-                    umma_commit(bb_a1_free(B, st));
                     ++n4; did = true;
                 }
                 if (n3 < n2 && mbar_test(bb_set(B, BB_A3, n3 & 1), (n3 >> 1) & 1)) {          // P3: dh and dW2
@@ -542,10 +561,10 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                         umma_bf16(d3, a, smem_desc(sm_u + BO_W2TL + k * 32, 0, 1024), id3, 1);
                     }
                     if (WGRAD) {
-                        const uint32_t lbo = sm_u + BO_ONES - hh;
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            umma_bf16(tmem + TM_ACC2, smem_desc(hh + k * 2048, lbo, 1024), smem_desc(dO + k * 2048, 0, 1024), idw2, (n3 | k) != 0);
+                            umma_bf16(tmem + TM_ACC2, smem_desc(hh + k * 2048, sm_u + BO_ONES - (hh + k * 2048), 1024), smem_desc(dO + k * 2048, 0, 1024),
+                                      idw2, (n3 | k) != 0);
                     }
                     umma_commit(bb_set(B, BB_D3, s));
                     ++n3; did = true;
@@ -558,22 +577,18 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t dah = smem_desc(ah + k * 32, 0, 1024), dbh = smem_desc(sm_u + BO_W2H + k * 32, 0, 1024);
                         umma_bf16(d2, dah, dbh, id2, k != 0);
-                        umma_bf16(d2, dah, smem_desc(sm_u + BO_W2L + k * 32, 0, 1024), id2, 1);
                         umma_bf16(d2, smem_desc(al + k * 32, 0, 1024), dbh, id2, 1);
                     }
                     umma_commit(bb_set(B, BB_D2, s));
                     ++n2; did = true;
                 }
-                if (n1 < nloc && n1 - n4 < 2 && mbar_test(bb_a1_full(B, n1 % BW_ST), (n1 / BW_ST) & 1)) {   // P1: layer 1 (recompute)
+                if (n1 < nloc && n1 - n4 < 2 && mbar_test(bb_a1_full(B, n1 % BW_ST), (n1 / BW_ST) & 1)) {   // P1: layer 1 (recompute); D1[s] is free after S3 of tile n1 - 2
                     tc_fence_after();
                     const int s = n1 & 1;
                     const uint32_t a = sm_u + BO_A1 + (n1 % BW_ST) * 16384, d1 = tmem + (uint32_t)(s * 192);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + BO_W1A + k * 32, 0, 1024), id1, k != 0);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + BO_W1B + k * 32, 0, 1024), id1, 1);
                     umma_commit(bb_set(B, BB_D1, s));
                     ++n1; did = true;
                 }
@@ -597,6 +612,14 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
             mbar_wait(bb_set(B, BB_D1, set), it & 1);
             tc_fence_after();
             if (it > 0) mbar_wait(bb_set(B, BB_DF_FREE, set), (it - 1) & 1);       // the scatter warps have taken the previous d_f out of A2lo
+            {   // keep this tile's F (hi half: chunks 0..3 of the row) for the dW1 contraction at the end of the chain; the stage goes back to the gather
+                const uint8_t* a1 = sm + BO_A1 + (lt % BW_ST) * 16384;
+                uint8_t* fc = sm + BO_FC + set * 16384;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(fc + sw128(row, c)) = *reinterpret_cast<const uint4*>(a1 + sw128(row, c));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bb_a1_free(B, lt % BW_ST));
+            }
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 float v[32];
@@ -709,7 +732,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
             tc_fence_after();
             const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
             float v[32];
-            if (q < 2) {                                    // lanes 0..63: dW2^T[j][k] (h' = h / ln2) and dW1^T[c | 32 + c][j] (hi | lo part of F)
+            if (q < 2) {                                    // lanes 0..63: dW2^T[j][k] (h' = h / ln2); lanes 0..31: dW1^T[c][j]
                 const int j = q * 32 + lane;
                 tmem_ld32(tl + TM_ACC2, v);
 #pragma unroll
@@ -717,10 +740,12 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                 tmem_ld32(tl + TM_ACC2 + 32, v);            // columns 32..47 of ACC2, then 16 columns of ACC1
                 atomicAdd(p.dW2 + 32 * HID + j, v[0] * (LN2 * p.w2g));
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 2; ++half) {      // ACC1 rows 0..31 = channels (F hi); rows 32..63 multiply the uncopied lo half: ignored
                     tmem_ld32(tl + TM_ACC1 + half * 32, v);
+                    if (q == 0) {
 #pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) atomicAdd(p.dW1 + (half * 32 + jj) * C + lane, v[jj] * p.w1g);
+                        for (int jj = 0; jj < 32; ++jj) atomicAdd(p.dW1 + (half * 32 + jj) * C + lane, v[jj] * p.w1g);
+                    }
                 }
             } else if (q == 2) {                            // lane 64 (first lane of this warp): the ones row = bias gradients
                 tmem_ld32(tl + TM_ACC2, v);                 // tcgen05.ld is warp-collective: all lanes load, lane 0 publishes

@@ -59,11 +59,11 @@ def _query_sigma(G, ws, samples, max_batch, planes):
             cnt = min(max_batch, P - head)
             c = co[:, head:head + cnt].contiguous()
             call('b200_triplane_mlp_fwd', ptr(pl), 1, hp, wp, ptr(c), None, None, None, 0, 0, cnt, box, *map(ptr, w), float(lr_mul),
-                 None, ptr(sigmas[:, head:head + cnt]), stream())
+                 None, ptr(sigmas[:, head:head + cnt]), None, stream())
             head += cnt
     else:
         call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co.contiguous()), None, None, None, 0, 0, P, box, *map(ptr, w), float(lr_mul),
-             None, ptr(sigmas), stream())
+             None, ptr(sigmas), None, stream())
     return sigmas
 
 

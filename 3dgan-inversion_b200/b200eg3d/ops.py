@@ -32,7 +32,9 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           'dgrad_passes': int(os.environ.get('B200EG3D_DGRAD_PASSES', '3')),
           'wgrad_passes': int(os.environ.get('B200EG3D_WGRAD_PASSES', '1')),
           # run the ToRGB / skip-upsample chain on a second stream, concurrently with the next block's convolutions
-          'overlap': os.environ.get('B200EG3D_OVERLAP', '1') != '0'}
+          'overlap': os.environ.get('B200EG3D_OVERLAP', '1') != '0',
+          # walk 8x16-pixel ray patches front to back in the tri-plane kernels instead of ray after ray (measured slower: see DESIGN.md)
+          'ray_patch_order': os.environ.get('B200EG3D_RAY_PATCH_ORDER', '0') != '0'}
 
 
 def _f32c(t):
@@ -712,16 +714,17 @@ class _RunModel(torch.autograd.Function):
         rgb = torch.empty([n, P, 32], device=pl.device, dtype=torch.float32)
         sigma = torch.empty([n, P, 1], device=pl.device, dtype=torch.float32)
         w = [_f32c(t) for t in (W1, b1, W2, b2)]
+        fs = _fsave(n, P, pl.device) if any(ctx.needs_input_grad) else None
         call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, 0, P, float(box_warp), *map(ptr, w),
-             float(lr_mul), ptr(rgb), ptr(sigma), stream())
+             float(lr_mul), ptr(rgb), ptr(sigma), ptr(fs), stream())
         ctx.cfg = (float(lr_mul), float(box_warp))
-        ctx.save_for_backward(pl, co, *w)
+        ctx.save_for_backward(pl, co, *w, fs)
         return rgb, sigma
 
     @staticmethod
     @device_guard
     def backward(ctx, d_rgb, d_sigma):
-        pl, co, W1, b1, W2, b2 = ctx.saved_tensors
+        pl, co, W1, b1, W2, b2, fs = ctx.saved_tensors
         lr_mul, box_warp = ctx.cfg
         n, hp, wp, _ = pl.shape
         P = co.shape[1]
@@ -733,9 +736,14 @@ class _RunModel(torch.autograd.Function):
         ws_bytes = _lib.load().b200_triplane_bwd_workspace_bytes(n, P)
         work = torch.empty([ws_bytes], device=pl.device, dtype=torch.uint8)
         call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, ptr(co), None, None, None, 0, 0, P, box_warp, ptr(W1), ptr(b1), ptr(W2),
-             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(d_planes), ptr(d_coords), None, None, *map(ptr, dws),
+             ptr(b2), lr_mul, ptr(_f32c(d_rgb)), ptr(_f32c(d_sigma)), ptr(fs), ptr(d_planes), ptr(d_coords), None, None, *map(ptr, dws),
              ptr(work), ws_bytes, stream())
         return (d_planes, d_coords, *dws, None, None)
+
+
+def _fsave(n, P, device):
+    """Forward -> backward hand-off buffer of the fused sampler + decoder (b200_triplane_fsave_bytes)."""
+    return torch.empty([_lib.load().b200_triplane_fsave_bytes(n, P)], device=device, dtype=torch.uint8)
 
 
 def run_model_nhwc(planes_nhwc, decoder, coords, box_warp):
@@ -772,22 +780,27 @@ class _Render(torch.autograd.Function):
             call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), st)
         rgb_c = torch.empty([n, M, S, 32], device=dev, dtype=torch.float32)
         sig_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
-        rw = int(round(math.sqrt(M))) if int(round(math.sqrt(M))) ** 2 == M else 0       # square ray image: column-major work order
+        rw = 0
+        if CONFIG['ray_patch_order'] and int(round(math.sqrt(M))) ** 2 == M:
+            rw = int(round(math.sqrt(M)))
+        want_grad = any(ctx.needs_input_grad)
+        fs_c = _fsave(n, M * S, dev) if want_grad else None          # features of every point, kept for the backward
         call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_c), S, rw, M * S, float(box_warp),
-             *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), st)
+             *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), ptr(fs_c), st)
         if density_noise > 0:
             sig_c += (torch.randn_like(sig_c.view(n, M * S, 1)) * density_noise).view(n, M, S)      # renderer.py:201-202 (same draw shape)
         minmax = torch.zeros([2], device=dev, dtype=torch.int32)
         minmax[:1].fill_(-1)                      # {0xFFFFFFFF, 0}: order-preserving uint encodings of +inf / -inf
         call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(minmax), st)
-        t_f = rgb_f = sig_f = None
+        t_f = rgb_f = sig_f = fs_f = None
         if S2 > 0:
             t_f = torch.empty([n, M, S2], device=dev, dtype=torch.float32)
             call('b200_ray_importance', ptr(t_c), ptr(sig_c), ptr(_f32c(u_imp)), ptr(t_f), n * M, S, S2, st)
             rgb_f = torch.empty([n, M, S2, 32], device=dev, dtype=torch.float32)
             sig_f = torch.empty([n, M, S2], device=dev, dtype=torch.float32)
+            fs_f = _fsave(n, M * S2, dev) if want_grad else None
             call('b200_triplane_mlp_fwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t_f), S2, rw, M * S2, float(box_warp),
-                 *map(ptr, w), float(lr_mul), ptr(rgb_f), ptr(sig_f), st)
+                 *map(ptr, w), float(lr_mul), ptr(rgb_f), ptr(sig_f), ptr(fs_f), st)
             if density_noise > 0:
                 sig_f += (torch.randn_like(sig_f.view(n, M * S2, 1)) * density_noise).view(n, M, S2)
             call('b200_depth_minmax', ptr(t_f), t_f.numel(), ptr(minmax), st)
@@ -797,13 +810,13 @@ class _Render(torch.autograd.Function):
         call('b200_ray_composite_fwd', ptr(t_c), ptr(sig_c), ptr(rgb_c), S, ptr(t_f), ptr(sig_f), ptr(rgb_f), S2, ptr(minmax),
              int(bool(white_back)), n * M, ptr(feat), ptr(depth), ptr(wsum), st)
         ctx.cfg = (float(lr_mul), float(box_warp), int(bool(white_back)), S, S2, rw)
-        ctx.save_for_backward(pl, ro, rd, *w, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax)
+        ctx.save_for_backward(pl, ro, rd, *w, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax, fs_c, fs_f)
         return feat, depth, wsum
 
     @staticmethod
     @device_guard
     def backward(ctx, d_feat, d_depth, d_wsum):
-        pl, ro, rd, W1, b1, W2, b2, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax = ctx.saved_tensors
+        pl, ro, rd, W1, b1, W2, b2, t_c, sig_c, rgb_c, t_f, sig_f, rgb_f, minmax, fs_c, fs_f = ctx.saved_tensors
         lr_mul, box_warp, white_back, S, S2, rw = ctx.cfg
         n, hp, wp, _ = pl.shape
         M = ro.shape[1]
@@ -830,13 +843,13 @@ class _Render(torch.autograd.Function):
             d_rd = torch.zeros_like(rd)
         ws_bytes = _lib.load().b200_triplane_bwd_workspace_bytes(n, M * max(S, S2))
         work = torch.empty([ws_bytes], device=dev, dtype=torch.uint8)
-        for t, d_rgb, d_sig, s in ((t_c, d_rgb_c, d_sig_c, S), (t_f, d_rgb_f, d_sig_f, S2)):
+        for t, d_rgb, d_sig, s, fs in ((t_c, d_rgb_c, d_sig_c, S, fs_c), (t_f, d_rgb_f, d_sig_f, S2, fs_f)):
             if s == 0:
                 continue
             # the per-ray sums d ray_o = sum_k d point, d ray_d = sum_k t_k * d point (point = o + t*d, renderer.py:161,178) are
             # reduced inside the C-ABI call
             call('b200_triplane_mlp_bwd', ptr(pl), n, hp, wp, None, ptr(ro), ptr(rd), ptr(t), s, rw, M * s, box_warp, ptr(W1),
-                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(d_planes), None, ptr(d_ro), ptr(d_rd),
+                 ptr(b1), ptr(W2), ptr(b2), lr_mul, ptr(d_rgb), ptr(d_sig), ptr(fs), ptr(d_planes), None, ptr(d_ro), ptr(d_rd),
                  *map(ptr, dws), ptr(work), ws_bytes, st)
         return (d_planes, d_ro, d_rd, *dws, None, None, None, None, None, None, None, None, None)
 

@@ -371,11 +371,16 @@ def time_triplane_bwd(G, resident, dev, iters=10):
     d_rgb, d_sig = torch.randn(1, P, 32, device=dev) * 1e-3, torch.randn(1, P, device=dev) * 1e-3
     d_pl = torch.zeros_like(pl)
     dws = [torch.zeros_like(x) for x in w]
-    work = torch.empty([b200eg3d_lib_mod().load().b200_triplane_bwd_workspace_bytes(1, P)], device=dev, dtype=torch.uint8)
+    lib = b200eg3d_lib_mod().load()
+    work = torch.empty([lib.b200_triplane_bwd_workspace_bytes(1, P)], device=dev, dtype=torch.uint8)
+    fsave = torch.empty([lib.b200_triplane_fsave_bytes(1, P)], device=dev, dtype=torch.uint8)
+    rgb, sig = torch.empty(1, P, 32, device=dev), torch.empty(1, P, device=dev)
+    call('b200_triplane_mlp_fwd', ptr(pl), 1, pl.shape[1], pl.shape[2], None, ptr(ro.contiguous()), ptr(rd.contiguous()), ptr(t), S, 0, P,
+         float(rk['box_warp']), *map(ptr, w), float(lr_mul), ptr(rgb), ptr(sig), ptr(fsave), stream())     # the forward leaves its feature tiles for the backward
 
     def launch():
-        call('b200_triplane_mlp_bwd', ptr(pl), 1, pl.shape[1], pl.shape[2], None, ptr(ro.contiguous()), ptr(rd.contiguous()), ptr(t), S, R, P,
-             float(rk['box_warp']), *map(ptr, w), float(lr_mul), ptr(d_rgb), ptr(d_sig), ptr(d_pl), None, None, None, *map(ptr, dws),
+        call('b200_triplane_mlp_bwd', ptr(pl), 1, pl.shape[1], pl.shape[2], None, ptr(ro.contiguous()), ptr(rd.contiguous()), ptr(t), S, 0, P,
+             float(rk['box_warp']), *map(ptr, w), float(lr_mul), ptr(d_rgb), ptr(d_sig), ptr(fsave), ptr(d_pl), None, None, None, *map(ptr, dws),
              ptr(work), work.numel(), stream())
 
     saved, b200eg3d_lib = None, __import__('b200eg3d')._lib

@@ -138,14 +138,18 @@ int b200_upfirdn2d_fused(const float* x, const float* f, const float* add, float
 
 /* ---- fused tri-plane sampling + OSG decoder (renderer.py:39-66 sample_from_planes, triplane.py:124-136 OSGDecoder.forward) ---- */
 /* planes [n][hp][wp][96] (plane p = channels 32p..32p+31).  Points: coords [n][P][3], or (coords NULL) rays ray_o/ray_d
- * [n][P/S][3] with depths [n][P] (point p on ray p / S).  ray_w (ray mode; 0 = unknown): width of the ray image -- the kernels
- * then walk the rays column by column, which keeps the XZ / ZX texel lines of a pixel column in one SM's L1; results do not
- * depend on it.  W1 [64][32], b1 [64], W2 [33][64], b2 [33] raw parameters (gains lr_mul/sqrt(fan_in),
- * networks_stylegan2.py:111-112, applied inside).  Out: rgb [n][P][32] (NULL: density-only query), sigma [n][P]. */
+ * [n][P/S][3] with depths [n][P] (point p on ray p / S).  ray_w (ray mode; 0 = linear order): width of the ray image -- the
+ * tcgen05 kernels then walk 8 x 16-pixel patches front to back (experimental, see tri::map_point; results do not depend on it;
+ * a forward and the backward that consumes its f_save must use the same value).  W1 [64][32], b1 [64], W2 [33][64], b2 [33]
+ * raw parameters (gains lr_mul/sqrt(fan_in), networks_stylegan2.py:111-112, applied inside).  Out: rgb [n][P][32] (NULL:
+ * density-only query), sigma [n][P].
+ * f_save (may be NULL): b200_triplane_fsave_bytes(n, P) bytes that receive every 128-point tile's mean features as the finished
+ * layer-1 tensor-core operand; handing it to the backward (f_saved) saves the second gather of 12 texel lines per point. */
+long b200_triplane_fsave_bytes(int n, long P);
 int b200_triplane_mlp_fwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                           const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp,
                           const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
-                          float* rgb, float* sigma, void* stream);
+                          float* rgb, float* sigma, void* f_save, void* stream);
 /* d_planes is ACCUMULATED (zero it first; may be NULL); d_coords [n][P][3] written (may be NULL); d_ray_o / d_ray_d
  * [n][P/S][3] ACCUMULATED (ray mode; both or neither): the sums over a ray's samples of d point and t * d point, i.e. the
  * gradients of `ray_origins + t * ray_directions` (renderer.py:161,178) w.r.t. origins and directions; dW1..db2 ACCUMULATED
@@ -155,8 +159,8 @@ long b200_triplane_bwd_workspace_bytes(int n, long P);
 int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, const float* coords, const float* ray_o,
                           const float* ray_d, const float* depths, int S, int ray_w, long P, float box_warp,
                           const float* W1, const float* b1, const float* W2, const float* b2, float lr_mul,
-                          const float* d_rgb, const float* d_sigma, float* d_planes, float* d_coords,
-                          float* d_ray_o, float* d_ray_d,
+                          const float* d_rgb, const float* d_sigma, const void* f_saved /* from the forward, may be NULL */,
+                          float* d_planes, float* d_coords, float* d_ray_o, float* d_ray_d,
                           float* dW1, float* db1, float* dW2, float* db2, void* workspace, long workspace_bytes, void* stream);
 /* Implementation switch of the two entry points above: 1 = tcgen05 pipeline (default), 0 = the mma.sync kernels kept as the
  * on-GPU cross-check (env B200EG3D_TRIPLANE_IMPL=0).  Returns the previous setting. */

@@ -44,21 +44,25 @@ def timeit(fn, name, iters=5):
     print(f'{name:48s} {tot / iters:8.3f} ms', flush=True)
 
 
-def fwd(rw):
+fsave = torch.empty(_lib.load().b200_triplane_fsave_bytes(n, M * S), device=dev, dtype=torch.uint8)
+
+
+def fwd(rw, save=False):
     return lambda: call('b200_triplane_mlp_fwd', ptr(planes), n, 256, 256, None, ptr(ro), ptr(rd), ptr(t), S, rw, M * S, 1.0, ptr(W1), ptr(b1),
-                        ptr(W2), ptr(b2), 1.0, ptr(rgb), ptr(sig), stream())
+                        ptr(W2), ptr(b2), 1.0, ptr(rgb), ptr(sig), ptr(fsave) if save else None, stream())
 
 
-def bwd(dp, dc, wg, rays=False, rw=R):
+def bwd(dp, dc, wg, rays=False, rw=0):
     return lambda: call('b200_triplane_mlp_bwd', ptr(planes), n, 256, 256, None, ptr(ro), ptr(rd), ptr(t), S, rw, M * S, 1.0, ptr(W1), ptr(b1), ptr(W2),
-                        ptr(b2), 1.0, ptr(d_rgb), ptr(d_sig), ptr(dpl) if dp else None, ptr(dpts) if dc else None,
+                        ptr(b2), 1.0, ptr(d_rgb), ptr(d_sig), ptr(fsave), ptr(dpl) if dp else None, ptr(dpts) if dc else None,
                         ptr(dro) if rays else None, ptr(drd) if rays else None, *[(ptr(x) if wg else None) for x in dW], ptr(work), work.numel(), stream())
 
 
 for impl, name in ((1, 'tcgen05'), (0, 'mma.sync')):
     _lib.load().b200_set_triplane_impl(impl)
-    timeit(fwd(R), f'[{name}] fwd 786k pts, column-major rays')
+    timeit(fwd(R), f'[{name}] fwd 786k pts, 8x16 patch order')
     timeit(fwd(0), f'[{name}] fwd 786k pts, linear ray order')
+    timeit(fwd(0, save=True), f'[{name}] fwd 786k pts, linear, saving features')
     timeit(bwd(True, False, True), f'[{name}] bwd planes+wgrad (PTI)')
     timeit(bwd(True, False, False), f'[{name}] bwd planes only')
     timeit(bwd(False, False, True), f'[{name}] bwd wgrad only')

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_table_matches_header():
     from b200eg3d import _lib
     syms = set(declared_symbols())
-    bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_set_mlp_passes', 'b200_set_triplane_impl', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes',
+    bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_set_mlp_passes', 'b200_set_triplane_impl', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes', 'b200_triplane_fsave_bytes',
                                         'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable'}
     assert syms == bound, (sorted(syms - bound), sorted(bound - syms))
     src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
