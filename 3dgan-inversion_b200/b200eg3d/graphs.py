@@ -6,6 +6,8 @@ kernel sequence of one eager step once (same kernels, same numerics) and replays
 Inputs are copied into static device buffers before each replay; `rendering_kwargs` and shapes must stay fixed while a
 graph is alive (re-capture after changing them).
 """
+import gc
+
 import torch
 
 
@@ -27,8 +29,17 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         if optimizer is not None:
             optimizer.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
-            self.loss = step_fn(*self.static_inputs)
+        # No cyclic garbage collection while capturing: finalising an older CUDA graph (or freeing its private pool) from inside the
+        # capture is a prohibited call that silently invalidates it ("operation failed due to a previous error during capture").
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = step_fn(*self.static_inputs)
+        finally:
+            if gc_was_on:
+                gc.enable()
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_inputs, inputs):

@@ -89,19 +89,205 @@ def conv_flops_per_step():
     return 3 * 2 * 71.387e9
 
 
-def make_problem(seed, device):
+def make_problem(seed, device, r=None, s=None):
     import synth_params as sp
     import b200eg3d
-    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
+    r, s = r or R, s or S
+    rk = sp.rendering_kwargs(depth_resolution=s, depth_resolution_importance=s)
     G = b200eg3d.TriPlaneGenerator(rendering_kwargs=rk, **sp.G_KWARGS_FULL).eval()
     named = dict(list(G.named_parameters()) + list(G.named_buffers()))
     sp.fill_params_(named, 7 + seed)
     G = G.to(device).float().requires_grad_(True)
-    G.neural_rendering_resolution = R
+    G.neural_rendering_resolution = r
     ws = sp.latent_ws(1 + seed)
     c = sp.camera(0.3, -0.2)
-    t512, t_raw = sp.targets(2 + seed, R)
+    t512, t_raw = sp.targets(2 + seed, r)
     return G, ws, c, t512.contiguous(), t_raw.contiguous()
+
+
+def stats_ms(times):
+    """median / mean / p10 / p90 of a list of per-step milliseconds."""
+    t = sorted(times)
+    n = len(t)
+    return {'steps': n, 'median_ms': round(t[n // 2], 4), 'mean_ms': round(sum(t) / n, 4), 'p10_ms': round(t[n // 10], 4),
+            'p90_ms': round(t[(9 * n) // 10], 4)}
+
+
+def per_step_times(fn, n_steps, warm=3):
+    """Per-step device times of fn() from CUDA event pairs on the current stream."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_steps + 1)]
+    evs[0].record()
+    for i in range(n_steps):
+        fn()
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    return [evs[i].elapsed_time(evs[i + 1]) for i in range(n_steps)]
+
+
+def rank_max(ms, world, dev):
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = t.item()
+    return ms
+
+
+def extra_render_only(G, resident, world, dev, steps=100):
+    """Forward only (eval / preview calls: single_id_coach.py:90, base_coach.py:137): G.synthesis under no_grad, replayed as a graph."""
+    ws, c = resident[0], resident[1]
+    with torch.no_grad():
+        for _ in range(3):
+            G.synthesis(ws, c, noise_mode='const', force_fp32=True)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = G.synthesis(ws, c, noise_mode='const', force_fp32=True)
+    t = per_step_times(g.replay, steps)
+    ms = rank_max(sorted(t)[len(t) // 2], world, dev)
+    return {'metric': 'render-only (forward) images/sec, same shape', 'value': round(world / (ms * 1e-3), 2), 'unit': 'images/s', 'median_ms': round(ms, 4),
+            'steps': steps, 'image_sum': round(float(out['image'].double().sum()), 3)}
+
+
+def extra_cfg5(rank, world, dev, steps=30):
+    """BASELINE config 5: R = 256, 96 + 96 samples (SR input antialias-resized 256 -> 128), the same PTI step."""
+    from b200eg3d.coach import PTIStep
+    G, ws, c, t512, _ = make_problem(100 + rank if world > 1 else 0, dev, 256, 96)
+    inputs = [t.to(dev) for t in (ws, c, t512)]
+    st = PTIStep(G, graphed=True, example=inputs)
+    t = per_step_times(lambda: st.step(*inputs), steps)
+    ms = rank_max(sorted(t)[len(t) // 2], world, dev)
+    res = {'workload': 'PTI step at R=256, 96+96 samples (BASELINE config 5)', 'value': round(world / (ms * 1e-3), 2), 'unit': 'steps/s',
+           'median_ms': round(ms, 3), 'steps': steps, 'loss': round(float(st.step(*inputs)), 5)}
+    del st, G
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def extra_stage1(rank, world, dev, steps=50):
+    """One w-projection iteration (w_projector.py:160-268; BASELINE config 4 shape: pose + latent + noise optimised, warping loss)."""
+    st, noise = make_stage1(dev, graphed=True, seed=rank)
+    t = per_step_times(lambda: st.step(noise), steps)
+    ms = rank_max(sorted(t)[len(t) // 2], world, dev)
+    res = {'workload': 'stage-1 w-projection iteration: 2 synthesis calls fwd+bwd (grads to w, 17 noise buffers, pose), warping loss, noise regulariser; '
+                       'seeded stand-in feature networks', 'value': round(world / (ms * 1e-3), 2), 'unit': 'steps/s', 'median_ms': round(ms, 3),
+           'steps': steps, 'loss': float(st.step(noise))}
+    del st
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return res
+
+
+def make_stage1(dev, graphed=True, seed=0):
+    """ProjectionStep (b200eg3d.coach) on a random-init generator with seeded stand-in feature networks (VGG16 weights are unavailable
+    offline) and a 6-D rotation leaf instead of the camera encoder."""
+    import b200eg3d
+    from b200eg3d import projector
+    from b200eg3d.coach import ProjectionStep
+    import synth_params as sp
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
+    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=rk, **sp.G_KWARGS_FULL).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), 7 + seed)
+    G = G.to(dev).float().requires_grad_(False)
+    G.neural_rendering_resolution = R
+    for m in G.modules():                                   # noise enters only where noise_strength != 0
+        if hasattr(m, 'noise_strength'):
+            m.noise_strength.data.fill_(0.05)
+
+    def feat_net(sd):
+        chans = [(3, 16), (16, 16), None, (16, 32), (32, 32), None, (32, 64), (64, 64), (64, 64), None, (64, 64), (64, 64), (64, 64)]
+        layers = []
+        for c in chans:
+            layers += [torch.nn.MaxPool2d(2)] if c is None else [torch.nn.Conv2d(c[0], c[1], 3, padding=1), torch.nn.ReLU()]
+        net = torch.nn.Sequential(*layers)
+        gg = torch.Generator().manual_seed(sd)
+        with torch.no_grad():
+            for p_ in net.parameters():
+                p_.copy_(torch.randn(p_.shape, generator=gg) * (0.1 if p_.ndim > 1 else 0.01))
+        return net.to(dev).eval().requires_grad_(False)
+
+    g = torch.Generator().manual_seed(3 + seed)
+    c0 = sp.camera(0.0, 0.0).to(dev)
+    target = (torch.rand(1, 3, 512, 512, generator=g) * 2 - 1).to(dev)
+    pose6d = torch.tensor([[1.0, 0.05, 0.0, 0.02, -1.0, 0.03]], device=dev, requires_grad=True)
+    st = ProjectionStep(G, sp.latent_ws(1 + seed)[:, :1].to(dev), [pose6d], lambda: projector.rot6d_to_rotmat(pose6d),
+                        c0[:, :16].reshape(1, 4, 4).contiguous(), c0[0, 16:25].contiguous(), target, feat_net(1), feat_net(2), graphed=graphed, seed=3 + seed)
+    st.pose6d = pose6d
+    return st, torch.randn(1, 1, 512, device=dev) * 0.01
+
+
+def gpu_aten_baseline(dev, steps=20):
+    """The comparator the reference itself would be on this GPU: the same PTI step through plain ATen / cuDNN ops --
+    the oracle port (oracle/eg3d_oracle.py, a statement-by-statement restatement of the reference's PyTorch path) with every tensor on
+    the B200.  Two figures: strict fp32 (TF32 off, the numerics of force_fp32=True) and TF32 allowed (PyTorch's conv default)."""
+    import eg3d_oracle as oracle
+    import synth_params as sp
+    from golden_util import param_shapes
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
+    out = {'what': 'same PTI step via ATen/cuDNN ops on this GPU (oracle port on cuda), eager, median of per-step CUDA-event times'}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    for tag, tf32 in (('fp32', False), ('tf32', True)):
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = tf32
+        P = {k: torch.zeros(v) for k, v in param_shapes(sp.G_KWARGS_FULL).items()}
+        sp.fill_params_(P, 7)
+        P = {k: v.to(dev).requires_grad_(True) for k, v in P.items()}
+        opt = torch.optim.Adam(list(P.values()), lr=3e-4, fused=True)
+        ws, c = sp.latent_ws(1).to(dev), sp.camera(0.3, -0.2).to(dev)
+        t512, traw = (t.to(dev) for t in sp.targets(2, R))
+
+        def step():
+            u1, u2 = torch.rand(1, R * R, S, 1, device=dev), torch.rand(R * R, S_IMP, device=dev)
+            o = oracle.synthesis(P, ws, c, rk, R, u1, u2)
+            loss = oracle.pti_loss(o, t512, traw)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        t = per_step_times(step, steps, warm=3)
+        st = stats_ms(t)
+        out[tag] = {'value': round(1e3 / st['median_ms'], 3), 'unit': 'steps/s', **st}
+        del P, opt
+        torch.cuda.empty_cache()
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
+def fast_mode(G, resident, dev, steps=50):
+    """Non-parity single-pass mode (bf16 operands once instead of the split-bf16 3-pass scheme; the counterpart of the reference's own
+    fp16 blocks, networks_stylegan2.py:421-423): throughput and its measured deviation from the parity mode on the same generator."""
+    import copy
+    from b200eg3d import ops, _lib
+    from b200eg3d.coach import PTIStep
+    Gf = copy.deepcopy(G)
+    ws, c, t512 = resident
+    keys = ('fwd_passes', 'dgrad_passes')
+    saved = {k: ops.CONFIG[k] for k in keys}
+    with torch.no_grad():
+        ref = Gf.synthesis(ws, c, noise_mode='const', force_fp32=True)
+        ref = {k: v.clone() for k, v in ref.items()}
+    prev = _lib.load().b200_set_mlp_passes(1)
+    try:
+        for k in keys:
+            ops.CONFIG[k] = 1
+        with torch.no_grad():
+            out = Gf.synthesis(ws, c, noise_mode='const', force_fp32=True)
+        dev_abs = {k: round(float((out[k] - ref[k]).abs().max()), 6) for k in ref}
+        st = PTIStep(Gf, graphed=True, example=list(resident))
+        t = per_step_times(lambda: st.step(*resident), steps)
+        res = {'what': 'single-pass operands (B200EG3D_FWD_PASSES=1, DGRAD_PASSES=1, MLP_PASSES=1): NOT parity mode', 'unit': 'steps/s',
+               'value': round(1e3 / sorted(t)[len(t) // 2], 2), **stats_ms(t), 'max_abs_vs_parity_mode': dev_abs}
+        del st
+    finally:
+        for k in keys:
+            ops.CONFIG[k] = saved[k]
+        _lib.load().b200_set_mlp_passes(prev)
+    del Gf
+    torch.cuda.empty_cache()
+    return res
 
 
 def pti_loss(out, t512):
@@ -201,11 +387,10 @@ def run_b200(args):
                 step(resident)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms = t.item()
+        # whole-job time = slowest rank (b200eg3d.shard.reduce_run_stats: SUM of steps, MAX of elapsed time over NCCL)
+        from b200eg3d.shard import reduce_run_stats
+        total_steps, ms, _ = reduce_run_stats(n_steps, e0.elapsed_time(e1), 0.0, device=dev)
+        assert total_steps == n_steps * world
         return ms
 
     for _ in range(max(args.warmup, 3)):
@@ -230,9 +415,31 @@ def run_b200(args):
     ms_e2e = timed(args.steps, e2e=True)
     final_loss = float(step(resident).item())        # sanity value: the optimisation must behave the same in every launch mode
 
+    # long run: >= 400 steps (>= ~1.7 s of device time) with one CUDA-event pair per step -> median / spread next to the K-step mean
+    long_t = per_step_times(lambda: step(resident), max(400, args.steps), warm=0)
+    long_run = stats_ms(long_t)
+    long_run['median_ms'] = round(rank_max(long_run['median_ms'], world, dev), 4)
+    long_run['seconds'] = round(sum(long_t) * 1e-3, 3)
+    long_run['value_from_median'] = round(world / (long_run['median_ms'] * 1e-3), 3)
+
+    # secondary workloads, measured on every rank (whole-job value = world / slowest rank's median step)
+    extra = {}
+    if not args.no_extra:
+        for name, fn in (('render_only', lambda: extra_render_only(G, resident, world, dev)),
+                         ('stage1', lambda: extra_stage1(rank, world, dev)),
+                         ('cfg5', lambda: extra_cfg5(rank, world, dev))):
+            try:
+                extra[name] = fn()
+            except Exception as e:                      # a secondary leg must never cost the headline number
+                import traceback
+                traceback.print_exc()
+                extra[name] = {'error': f'{type(e).__name__}: {e}'[:300]}
+                if world > 1:
+                    raise
+
     # per-kernel device time of the same step, instrumented with CUDA events on the launching stream (separate steps)
     roof = roof_conv = per_call = None
-    cpu = None
+    cpu = aten = fast = None
     if rank == 0:
         _lib.PROFILE = {}
         b200eg3d.ops.CONFIG['overlap'] = False        # per-kernel times are taken with the two graph branches serialised (one stream)
@@ -271,17 +478,23 @@ def run_b200(args):
         bwd_ms, bwd_n = prof.get('b200_triplane_mlp_bwd', (0.0, 1))
         bwd_eager_ms = bwd_ms / max(bwd_n, 1)
         bwd_launch_ms = time_triplane_bwd(G, resident, dev)
+        bwd_key = next((k for k in (kt or {}) if k.startswith('triplane_bwd_tc_kernel') or k.startswith('triplane_mlp_bwd')), None)
         ach = bwd_bytes / (bwd_launch_ms * 1e-3) / 1e9 if bwd_launch_ms > 0 else 0.0
-        roof = {'kernel': 'triplane_mlp_bwd_mma_kernel (fused tri-plane sample + OSG decoder, backward)', 'bound': 'hbm',
+        roof = {'kernel': 'triplane_bwd_tc_kernel (fused tri-plane sample + OSG decoder, backward; tcgen05)', 'bound': 'hbm',
                 'achieved': round(ach, 1), 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': round(ach / pk['hbm_gbs'], 4),
-                'traffic': traffic.get('triplane_mlp_bwd_mma_kernel', {}).get('bytes'), 'peak_source': how,
+                'traffic': traffic.get('triplane_bwd_tc_kernel', {}).get('bytes'), 'peak_source': how,
                 'algorithmic_bytes_per_launch': bwd_bytes, 'launch_ms': round(bwd_launch_ms, 4), 'launches_per_step': bwd_n / nprof,
+                'launch_ms_is': 'microbenchmark: 10 back-to-back launches of the kernel alone on the step\'s planes / rays, CUDA events',
+                'launch_ms_in_step_cupti': round(kt[bwd_key][0] / max(kt[bwd_key][1], 1), 4) if (kt and bwd_key) else None,
                 'launch_ms_eager_bracket': round(bwd_eager_ms, 4),
-                'l2_gather_scatter_gbs': round(2 * P1 * 1536 / (bwd_launch_ms * 1e-3) / 1e9, 1) if bwd_launch_ms > 0 else None,
+                'l2_scatter_gbs': round(P1 * 1536 / (bwd_launch_ms * 1e-3) / 1e9, 1) if bwd_launch_ms > 0 else None,
+                'l2_atomic_peak_gbs': 6300.0,
                 'share_of_kernel_time': round(bwd_launch_ms * (bwd_n / nprof) / (sum(v[0] for v in kt.values()) if kt else tot_ms), 3),
-                'note': 'HBM-bound only by the compulsory-byte definition: DRAM traffic equals the algorithmic bytes (no re-reads); '
-                        'the kernel is limited by the L2 gather + vector-atomic scatter of 2 x 1.2 GB of texel lines (L2 35 %) and by instruction issue '
-                        '(SM 35 %, 12 warps/SM); decoder weight gradients accumulate in tensor memory (tcgen05.mma) and add no DRAM traffic'}
+                'note': 'HBM-bound only by the compulsory-byte definition.  The binding limit is L2: every point adds 12 weighted 128-byte texel lines '
+                        'into the plane gradient (1.2 GB of red.global.add.v4 per launch) and the measured L2 atomic throughput of this part is '
+                        '~6.3 TB/s (scripts/microbench_red.cu: red.v4, scalar red and cp.reduce.async.bulk all saturate there) -> >= 0.19 ms per launch; '
+                        'l2_scatter_gbs / l2_atomic_peak_gbs is the fraction of THAT roofline.  The features are not gathered again: the forward '
+                        'leaves them as finished tensor-core operand tiles (100 MB, bulk-copied back); decoder weight gradients accumulate in tensor memory'}
         # (2) the conv stack (all tcgen05 / SIMT conv launches of the step) against the tensor roofline
         conv_ms = sum(prof[k][0] for k in prof if k.startswith('b200_conv_')) / nprof
         n_conv = sum(prof[k][1] for k in prof if k.startswith('b200_conv_')) / nprof
@@ -302,6 +515,17 @@ def run_b200(args):
                      'issued_tflops': round(achieved * 7 / 3, 1), 'issued_frac': round(achieved * 7 / 3 / peak, 4),
                      'note': 'algorithmic FLOPs (fwd+dgrad+wgrad = 428.3 GFLOP); forward and dgrad issue 3 MMAs per product (split-bf16 parity mode), '
                              'wgrad 1: the tensor pipe executes 7/3 of the algorithmic FLOPs (issued_*)'}
+        b200eg3d.ops.CONFIG['overlap'] = True
+        if world == 1 and not args.no_extra:
+            for name, fn in (('aten', lambda: gpu_aten_baseline(dev)), ('fast', lambda: fast_mode(G, resident, dev))):
+                try:
+                    res = fn()
+                except Exception as e:
+                    res = {'error': f'{type(e).__name__}: {e}'[:300]}
+                if name == 'aten':
+                    aten = res
+                else:
+                    fast = res
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(1, 5)          # ~10-12 s of host work on the GPU box (1 warm-up + 5 timed PTI steps)
     if rank == 0:
@@ -318,6 +542,7 @@ def run_b200(args):
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
                     'd2h_bytes_per_step': 4, 'host_reads': len(e2e_losses),
                     'pipelining': 'double-buffered: H2D of step i+1 on a copy stream under step i, loss of step i read on the host one step later'},
+            'timed_region_s': round(ms * 1e-3, 4), 'long_run': long_run, 'extra': extra, 'gpu_aten_baseline': aten, 'fast_mode': fast,
             'gpu_launches': launches, 'clocks': clocks, 'roofline': roof, 'roofline_conv_stack': roof_conv if rank == 0 else None,
             'kernel_ms': kernel_ms if rank == 0 else None, 'per_call_ms_event_brackets': per_call if rank == 0 else None, 'cpu_baseline': cpu, 'final_loss': round(final_loss, 6),
         }
@@ -401,96 +626,29 @@ def time_triplane_bwd(G, resident, dev, iters=10):
 def run_stage1(args):
     """Secondary measurement: one w-projection iteration (w_projector.py:145-270) -- two synthesis calls
     (predicted + canonical camera), warping loss, feature distance, noise regulariser, backward to w / noise buffers / pose,
-    three Adam steps, noise normalisation.  The feature networks are seeded stand-ins (VGG16 weights are unavailable offline);
-    the pose is a 6-D rotation leaf instead of the camera encoder.  Same JSON contract, different workload name."""
-    import b200eg3d
-    from b200eg3d import projector
-    from b200eg3d.graphs import GraphedStep
-    import synth_params as sp
+    three Adam steps, noise normalisation.  Same JSON contract, different workload name.  The default run reports the same
+    measurement as extra.stage1."""
     torch.cuda.set_device(0)
     dev = torch.device('cuda', 0)
-    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S_IMP)
-    G = b200eg3d.TriPlaneGenerator(rendering_kwargs=rk, **sp.G_KWARGS_FULL).eval()
-    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), 7)
-    G = G.to(dev).float().requires_grad_(False)
-    G.neural_rendering_resolution = R
-    g = torch.Generator().manual_seed(3)
-    nb = {n: b for n, b in G.backbone.synthesis.named_buffers() if 'noise_const' in n}
-    nb2 = {n: b for n, b in G.superresolution.named_buffers() if 'noise_const' in n}
-    for b in list(nb.values()) + list(nb2.values()):
-        b.copy_(torch.randn(b.shape, generator=g))
-        b.requires_grad = True
-    for m in G.modules():                                   # noise enters only where noise_strength != 0
-        if hasattr(m, 'noise_strength'):
-            m.noise_strength.data.fill_(0.05)
-
-    def feat_net(seed):
-        chans = [(3, 16), (16, 16), None, (16, 32), (32, 32), None, (32, 64), (64, 64), (64, 64), None, (64, 64), (64, 64), (64, 64)]
-        layers = []
-        for c in chans:
-            layers += [torch.nn.MaxPool2d(2)] if c is None else [torch.nn.Conv2d(c[0], c[1], 3, padding=1), torch.nn.ReLU()]
-        net = torch.nn.Sequential(*layers)
-        gg = torch.Generator().manual_seed(seed)
-        with torch.no_grad():
-            for p_ in net.parameters():
-                p_.copy_(torch.randn(p_.shape, generator=gg) * (0.1 if p_.ndim > 1 else 0.01))
-        return net.to(dev).eval().requires_grad_(False)
-
-    vgg_feat, torch_vgg = feat_net(1), feat_net(2)
-    c0 = sp.camera(0.0, 0.0).to(dev)
-    init_ext, intrinsic = c0[:, :16].reshape(1, 4, 4).contiguous(), c0[0, 16:25].contiguous()
-    w2c = torch.linalg.inv(init_ext[0]).contiguous()          # constant over the loop; linalg.inv cannot be graph-captured
-    target = (torch.rand(1, 3, 512, 512, generator=g) * 2 - 1).to(dev)
-    target_255 = torch.nn.functional.interpolate((target + 1) / 2 * 255, size=(256, 256), mode='area')
-    with torch.no_grad():
-        target_features = vgg_feat(target_255)
-    w_opt = sp.latent_ws(1)[:, :1].to(dev).clone().requires_grad_(True)
-    pose6d = torch.tensor([[1.0, 0.05, 0.0, 0.02, -1.0, 0.03]], device=dev, requires_grad=True)
-    trans = torch.zeros(1, 3, device=dev, requires_grad=True)
-    opt = torch.optim.Adam([w_opt] + list(nb.values()) + list(nb2.values()), lr=5e-3, fused=True, capturable=True)
-    opt_cam = torch.optim.Adam([pose6d], lr=1e-4, fused=True, capturable=True)
-    opt_tr = torch.optim.Adam([trans], lr=1e-4, fused=True, capturable=True)
-
-    class Opts:
-        def zero_grad(self, set_to_none=True):
-            for o in (opt, opt_cam, opt_tr):
-                o.zero_grad(set_to_none=set_to_none)
-
-    def step(w_noise):
-        loss, _ = projector.projection_step_loss(G, w_opt, projector.rot6d_to_rotmat(pose6d), trans, init_ext, intrinsic, target,
-                                                 target_features, vgg_feat, torch_vgg, nb, nb2, w_noise=w_noise, w2c=w2c)
-        loss.backward()
-        opt_cam.step(); opt.step(); opt_tr.step()
-        projector.normalize_noise_(list(nb.values()) + list(nb2.values()))
-        return loss
-
-    noise = torch.randn(1, 1, 512, device=dev) * 0.01
-    graphed = GraphedStep(step, [noise], optimizer=Opts(), warmup=3)
-    for _ in range(max(args.warmup, 3)):
-        graphed(noise)
-    torch.cuda.synchronize()
+    st, noise = make_stage1(dev, graphed=True)
+    t = per_step_times(lambda: st.step(noise), args.steps, warm=max(args.warmup, 3))
+    ms = sum(t)
+    h_noise = noise.cpu().pin_memory()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        graphed(noise)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    h_noise = noise.cpu().pin_memory()
-    e0.record()
-    for _ in range(args.steps):
-        graphed(h_noise.to(dev, non_blocking=True)).item()
+        st.step(h_noise.to(dev, non_blocking=True)).item()
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
     line = {'metric': 'w-projection steps/sec (2 synthesis calls fwd+bwd + warping loss + noise regulariser) 512px out, 128px neural render, 48+48 depth samples',
             'value': round(args.steps / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'ms_per_step': round(ms / args.steps, 3), 'median_ms': stats_ms(t)['median_ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic (random-init generator, random target, seeded stand-in feature networks)',
             'config': {'workload': 'stage-1 w-projection iteration (w_projector.py:145-270) at R=%d, %d+%d samples; secondary measurement, not BASELINE.json\'s metric' % (R, S, S_IMP),
                        'launch': 'whole iteration captured in a CUDA graph'},
             'e2e': {'value': round(args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': 2048, 'd2h_bytes_per_step': 4},
-            'loss': float(graphed.loss.item())}
+            'loss': float(st.step(noise).item())}
     print(json.dumps(line), flush=True)
 
 
@@ -551,6 +709,7 @@ if __name__ == '__main__':
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary legs (render-only, stage 1, config 5, ATen-on-GPU comparator, fast mode)')
     ap.add_argument('--render-res', type=int, default=None, help='neural rendering resolution (default 128; 256 = BASELINE config 5)')
     ap.add_argument('--depth-samples', type=int, default=None, help='coarse = fine depth samples per ray (default 48; 96 = config 5)')
     ap.add_argument('--ncu-step', action='store_true', help='profile exactly one step (cudaProfilerStart/Stop) and exit')

@@ -163,7 +163,7 @@ def synthesis_block(P, pre, x, img, ws, res, first, noise_mode, conv_clamp, f, n
 def backbone_synthesis(P, ws, noise_mode='const', conv_clamp=256, img_resolution=256, noise_random=None, pre='backbone.synthesis.'):
     """training/networks_stylegan2.py:503-518 (SynthesisNetwork.forward): blocks 4..img_resolution,
     block k reads ws[:, idx : idx+num_conv+num_torgb], idx += num_conv."""
-    f = fir_1331(ws.dtype)
+    f = fir_1331(ws.dtype).to(ws.device)
     x = img = None
     w_idx = 0
     res = 4
@@ -179,7 +179,7 @@ def backbone_synthesis(P, ws, noise_mode='const', conv_clamp=256, img_resolution
 
 def superresolution_8x(P, rgb, x, ws, noise_mode='none', sr_antialias=True, noise_random=None, pre='superresolution.'):
     """training/superresolution.py:45-56 (SuperresolutionHybrid8X.forward); conv_clamp 256 because sr_num_fp16_res>0 (:36-42)."""
-    f = fir_1331(ws.dtype)
+    f = fir_1331(ws.dtype).to(ws.device)
     w3 = ws[:, -1:, :].repeat(1, 3, 1)
     if x.shape[-1] != 128:
         x = F.interpolate(x, size=(128, 128), mode='bilinear', align_corners=False, antialias=sr_antialias)
@@ -197,7 +197,7 @@ def ray_sampler(cam2world, intrinsics, resolution):
     dt = cam2world.dtype
     fx, fy = intrinsics[:, 0, 0], intrinsics[:, 1, 1]
     cx, cy, sk = intrinsics[:, 0, 2], intrinsics[:, 1, 2], intrinsics[:, 0, 1]
-    idx = (torch.arange(resolution, dtype=torch.float32) * (1.0 / resolution) + (0.5 / resolution)).to(dt)
+    idx = (torch.arange(resolution, dtype=torch.float32, device=cam2world.device) * (1.0 / resolution) + (0.5 / resolution)).to(dt)
     # flat ray m = i*R + j  ->  x = (j+.5)/R, y = (i+.5)/R        (ray_sampler.py:45-51)
     y_cam = idx.repeat_interleave(resolution)[None].expand(n, -1)
     x_cam = idx.repeat(resolution)[None].expand(n, -1)
@@ -289,13 +289,13 @@ def stratified_depths(n, m, s, ray_start, ray_end, u, dtype, disparity=False):
     """renderer.py:224-247 (sample_stratified): scalar limits, per-ray tensor limits ('auto'), or disparity-space sampling."""
     u = u.to(dtype)
     if disparity:
-        t = torch.linspace(0, 1, s).to(dtype).reshape(1, 1, s, 1).repeat(n, m, 1, 1) + u * (1 / (s - 1))
+        t = torch.linspace(0, 1, s, device=u.device).to(dtype).reshape(1, 1, s, 1).repeat(n, m, 1, 1) + u * (1 / (s - 1))
         return 1. / (1. / ray_start * (1. - t) + 1. / ray_end * t)
     if isinstance(ray_start, torch.Tensor):                                          # [N,M,1] each
-        steps = (torch.arange(s, dtype=torch.float32) / (s - 1)).to(dtype).reshape(1, 1, s, 1)
+        steps = (torch.arange(s, dtype=torch.float32, device=u.device) / (s - 1)).to(dtype).reshape(1, 1, s, 1)
         t = ray_start.unsqueeze(2) + steps * (ray_end - ray_start).unsqueeze(2)
         return t + u * ((ray_end - ray_start) / (s - 1)).unsqueeze(-1)
-    t = torch.linspace(ray_start, ray_end, s).to(dtype).reshape(1, 1, s, 1).repeat(n, m, 1, 1)
+    t = torch.linspace(ray_start, ray_end, s, device=u.device).to(dtype).reshape(1, 1, s, 1).repeat(n, m, 1, 1)
     return t + u * ((ray_end - ray_start) / (s - 1))
 
 
