@@ -683,8 +683,10 @@ B200_API int b200_triplane_mlp_bwd(const float* planes, int n, int hp, int wp, c
     p.d_rgb = d_rgb; p.d_sigma = d_sigma; p.d_planes = d_planes; p.d_coords = d_coords;
     p.dW1 = dW1; p.db1 = db1; p.dW2 = dW2; p.db2 = db2;
     p.f_saved = static_cast<const uint8_t*>(f_saved);
-    // tcgen05 pipeline: needs the forward's feature tiles; coordinate / ray gradients (w-projection) take the mma.sync kernel
-    if (triplane_impl() == 1 && f_saved && !d_coords && !d_ray_o && P < (1L << 31)) return triplane_bwd_tc_launch(p, st);
+    p.d_ray_o = d_ray_o; p.d_ray_d = d_ray_d;
+    // tcgen05 pipeline: needs the forward's feature tiles (otherwise the mma.sync kernel gathers the features again)
+    if (triplane_impl() == 1 && f_saved && P < (1L << 31)) return triplane_bwd_tc_launch(p, st);
+    p.d_ray_o = p.d_ray_d = nullptr;
     if (d_ray_o && !d_coords) {          // per-point coordinate gradients staged in the workspace, reduced per ray below
         B200_REQUIRE(workspace && workspace_bytes >= (long)n * P * 12, "triplane_bwd: workspace too small for the ray gradients");
         p.d_coords = static_cast<float*>(workspace);

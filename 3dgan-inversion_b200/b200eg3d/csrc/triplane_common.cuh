@@ -140,6 +140,19 @@ __device__ __forceinline__ void plane_setup(float u, float v, int hp, int wp, in
     off[3] = __int_as_float((y1c * wp + x1c) * PC + pc); wgt[3] = (yi1 && xi1) ? wy1 * wx1 * third : 0.f;
 }
 
+// Extra set-up for the coordinate gradient: fractional weights (wx1, wy1) of one plane and a validity mask of its four texels
+// (bit 0: (y0,x0), 1: (y0,x1), 2: (y1,x0), 3: (y1,x1)), same unnormalisation as plane_setup.
+__device__ __forceinline__ void plane_setup_frac(float u, float v, int hp, int wp, float& wx1, float& wy1, int& mask) {
+    float ix = ((u + 1.f) * wp - 1.f) * 0.5f, iy = ((v + 1.f) * hp - 1.f) * 0.5f;
+    ix = fminf(fmaxf(ix, -2.f), (float)wp + 1.f);
+    iy = fminf(fmaxf(iy, -2.f), (float)hp + 1.f);
+    const float fx = floorf(ix), fy = floorf(iy);
+    const int x0 = (int)fx, y0 = (int)fy;
+    wx1 = ix - fx; wy1 = iy - fy;
+    const bool xi0 = x0 >= 0 && x0 < wp, xi1 = x0 + 1 >= 0 && x0 + 1 < wp, yi0 = y0 >= 0 && y0 < hp, yi1 = y0 + 1 >= 0 && y0 + 1 < hp;
+    mask = (yi0 && xi0 ? 1 : 0) | (yi0 && xi1 ? 2 : 0) | (yi1 && xi0 ? 4 : 0) | (yi1 && xi1 ? 8 : 0);
+}
+
 // each lane stages the set-up of its own point: ss[lane*SP + 0..11] = texel offsets, [12..23] = weights
 // (plane 0 <- (x,y), plane 1 <- (x,z), plane 2 <- (z,x): renderer.py:23-53)
 __device__ __forceinline__ void stage_setup(float* ss, int lane, float cx, float cy, float cz, int hp, int wp) {

@@ -388,7 +388,8 @@ constexpr int BO_W1TH = BO_W2TL + 8192;                        // [32 channels][
 constexpr int BO_W1TL = BO_W1TH + 4096;
 constexpr int BO_ONES = BO_W1TL + 4096;                        // [16][64] bf16 ones: second MN block of every k-step of the weight-gradient A operands
 constexpr int BO_SS = BO_ONES + 2048;                          // private set-up tiles of the scatter warps, [32][SP] words each
-constexpr int BO_BIAS = BO_SS + BW_NSCATTER * 32 * SP * 4;      // b1'[64] | b2'[48]
+constexpr int SPX = 8;                                         // extra set-up words per point for the coordinate gradient
+constexpr int BO_BIAS = BO_SS + BW_NSCATTER * 32 * (SP + SPX) * 4;   // b1'[64] | b2'[48]
 constexpr int BO_BAR = BO_BIAS + 512;
 constexpr int BW_SMEM = BO_BAR + 256 + 1024;
 constexpr int BW_TM_COLS = 512;                                // set s at 192 s: D1 +0 (64), D2/D4 +64 (48), D3 +128 (64); ACC2 at 384 (48), ACC1 at 432 (64)
@@ -440,7 +441,9 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 }
 
 // WGRAD: accumulate the decoder weight / bias gradients (PTI); false = frozen decoder (w-projection).
-template <bool WGRAD>
+// COORDS: also produce the gradient w.r.t. the sample coordinates (d_coords) and / or its per-ray sums (d_ray_o, d_ray_d): the
+// scatter warps then fetch the 12 texel lines of every point once more (the bilinear derivative needs the texel values).
+template <bool WGRAD, bool COORDS>
 __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(TriplaneParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -481,13 +484,26 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
         // kept from the gather: that would tie a 12 KB buffer per tile to the whole length of the chain.
         // Eight warps: group sg = (warp - BW_SCATTER0) / 4 serves the tiles of consumer set sg.
         const int sw = warp - BW_SCATTER0, sg = sw >> 2, w = sw & 3, pt = lane >> 3, l8 = lane & 7;
-        float* ss = reinterpret_cast<float*>(sm + BO_SS) + sw * 32 * SP;
+        float* ss = reinterpret_cast<float*>(sm + BO_SS) + sw * 32 * (SP + SPX);
+        float* sx = ss + 32 * SP;                                                // [32][SPX]: wx1, wy1 per plane, validity mask
         const uint8_t* stg = sm + BO_A2 + sg * 32768 + 16384;                    // d_f staging = A2lo[set], fp32 rows, 128-byte swizzle
         int it = 0;
         for (int lt = sg; lt < nloc; lt += 2, ++it) {
             float cx, cy, cz;
-            point_coords32(p, n, map_point(p, (unsigned)((t0 + lt) * TILE + w * 32 + lane)), cx, cy, cz);
+            const int pi = map_point(p, (unsigned)((t0 + lt) * TILE + w * 32 + lane));
+            point_coords32(p, n, pi, cx, cy, cz);
             stage_setup(ss, lane, cx, cy, cz, p.hp, p.wp);
+            float tdepth = 0.f;
+            if (COORDS) {
+                int m0, m1, m2;
+                float f[6];
+                plane_setup_frac(cx, cy, p.hp, p.wp, f[0], f[1], m0);
+                plane_setup_frac(cx, cz, p.hp, p.wp, f[2], f[3], m1);
+                plane_setup_frac(cz, cx, p.hp, p.wp, f[4], f[5], m2);
+                *reinterpret_cast<float4*>(sx + lane * SPX) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(sx + lane * SPX + 4) = make_float4(f[4], f[5], __int_as_float(m0 | (m1 << 4) | (m2 << 8)), 0.f);
+                if (pi >= 0 && !p.coords) tdepth = p.depths[row0 + pi];
+            }
             mbar_wait_sleep(bb_set(B, BB_DF_FULL, sg), it & 1);
             float4 g[8];
 #pragma unroll
@@ -504,6 +520,54 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                         const int4 o = *reinterpret_cast<const int4*>(s + k);
                         const float4 wv = *reinterpret_cast<const float4*>(s + 12 + k);
                         red_add4(pc + o.x, wv.x, g[i]); red_add4(pc + o.y, wv.y, g[i]); red_add4(pc + o.z, wv.z, g[i]); red_add4(pc + o.w, wv.w, g[i]);
+                    }
+                }
+            }
+            if (COORDS) {
+                // d point = sum over channels of d_f * d(bilinear)/d(coordinate), all three planes (ATen grid_sampler_2d_backward
+                // semantics: out-of-range texels count as zeros).  Lane (pt, l8) covers channels 4 l8 .. 4 l8 + 3 of point 4 i + pt.
+                const float* pc = pl + l8 * 4;
+                const float hx = 0.5f * p.wp * (1.f / 3.f) * p.coord_scale, hy = 0.5f * p.hp * (1.f / 3.f) * p.coord_scale;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int q = i * 4 + pt;
+                    const float* s = ss + q * SP;
+                    const float4 fa = *reinterpret_cast<const float4*>(sx + q * SPX), fb = *reinterpret_cast<const float4*>(sx + q * SPX + 4);
+                    const int mask = __float_as_int(fb.z);
+                    const float wx1[3] = {fa.x, fa.z, fb.x}, wy1[3] = {fa.y, fa.w, fb.y};
+                    float dix[3], diy[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const int4 o = *reinterpret_cast<const int4*>(s + 4 * k);
+                        const int mk = mask >> (4 * k);
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 t00 = (mk & 1) ? __ldg(reinterpret_cast<const float4*>(pc + o.x)) : z4;
+                        const float4 t01 = (mk & 2) ? __ldg(reinterpret_cast<const float4*>(pc + o.y)) : z4;
+                        const float4 t10 = (mk & 4) ? __ldg(reinterpret_cast<const float4*>(pc + o.z)) : z4;
+                        const float4 t11 = (mk & 8) ? __ldg(reinterpret_cast<const float4*>(pc + o.w)) : z4;
+                        auto dot = [&](const float4& a) { return g[i].x * a.x + g[i].y * a.y + g[i].z * a.z + g[i].w * a.w; };
+                        const float s00 = dot(t00), s01 = dot(t01), s10 = dot(t10), s11 = dot(t11);
+                        dix[k] = (1.f - wy1[k]) * (s01 - s00) + wy1[k] * (s11 - s10);
+                        diy[k] = (1.f - wx1[k]) * (s10 - s00) + wx1[k] * (s11 - s01);
+                    }
+                    // planes: 0 <- (x, y), 1 <- (x, z), 2 <- (z, x)
+                    float dx = (dix[0] + dix[1]) * hx + diy[2] * hy, dy = diy[0] * hy, dz = diy[1] * hy + dix[2] * hx;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        dx += __shfl_xor_sync(0xffffffffu, dx, o); dy += __shfl_xor_sync(0xffffffffu, dy, o); dz += __shfl_xor_sync(0xffffffffu, dz, o);
+                    }
+                    const int pq = __shfl_sync(0xffffffffu, pi, q);
+                    const float tq = __shfl_sync(0xffffffffu, tdepth, q);
+                    if (l8 == 0 && pq >= 0) {
+                        if (p.d_coords) {
+                            float* dc = p.d_coords + (row0 + pq) * 3;
+                            dc[0] = dx; dc[1] = dy; dc[2] = dz;
+                        }
+                        if (p.d_ray_o) {
+                            const long r3 = ((long)n * p.M + (unsigned)pq / (unsigned)p.S) * 3;
+                            atomicAdd(p.d_ray_o + r3, dx); atomicAdd(p.d_ray_o + r3 + 1, dy); atomicAdd(p.d_ray_o + r3 + 2, dz);
+                            atomicAdd(p.d_ray_d + r3, tq * dx); atomicAdd(p.d_ray_d + r3 + 1, tq * dy); atomicAdd(p.d_ray_d + r3 + 2, tq * dz);
+                        }
                     }
                 }
             }
@@ -784,13 +848,18 @@ int triplane_fwd_tc_launch(tri::TriplaneParams& p, bool sigma_only, cudaStream_t
 }
 
 int triplane_bwd_tc_launch(tri::TriplaneParams& p, cudaStream_t st) {
-    B200_FUNC_ATTR_ONCE(triplane_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
-    B200_FUNC_ATTR_ONCE(triplane_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    B200_FUNC_ATTR_ONCE((triplane_bwd_tc_kernel<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    B200_FUNC_ATTR_ONCE((triplane_bwd_tc_kernel<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    B200_FUNC_ATTR_ONCE((triplane_bwd_tc_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+    B200_FUNC_ATTR_ONCE((triplane_bwd_tc_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
     const long ntiles = (p.P + TILE - 1) / TILE;
     const int sms = b200_sm_count();
     dim3 grid((unsigned)(ntiles < sms ? ntiles : sms), p.n);
-    if (p.dW1) triplane_bwd_tc_kernel<true><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
-    else triplane_bwd_tc_kernel<false><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
+    const bool coords = p.d_coords || p.d_ray_o;
+    if (p.dW1 && coords) triplane_bwd_tc_kernel<true, true><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
+    else if (p.dW1) triplane_bwd_tc_kernel<true, false><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
+    else if (coords) triplane_bwd_tc_kernel<false, true><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
+    else triplane_bwd_tc_kernel<false, false><<<grid, BW_THREADS, BW_SMEM, st>>>(p);
     B200_CHECK_LAUNCH();
     return 0;
 }

