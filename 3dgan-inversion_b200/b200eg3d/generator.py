@@ -132,6 +132,8 @@ class SynthesisLayer(torch.nn.Module):
         """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None.
         bank / lidx: styles and modulated weights come from a pre-computed ops.WeightBank entry (w is then unused)."""
         assert noise_mode in ['random', 'const', 'none']
+        if not fused_modconv:
+            return self._forward_unfused(x, w, noise_mode, gain), None
         styles = self.affine(w) if bank is None else None
         noise = None
         if self.use_noise and noise_mode == 'random':
@@ -141,6 +143,32 @@ class SynthesisLayer(torch.nn.Module):
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return ops.modconv_layer(x, self.weight, styles, self.bias, noise, self.noise_strength if noise is not None else None,
                                  self.up, self.act_gain * gain, clamp, x_split=x_split, bank=bank, lidx=lidx)
+
+
+    def _forward_unfused(self, x, w, noise_mode, gain):
+        """fused_modconv=False (networks_stylegan2.py:70-79): scale the activations by the styles, convolve with the SHARED weight,
+        scale by the demodulation coefficients afterwards.  Algebraically the same layer; it runs on the op-level look-alikes
+        (shims.ops_modules: conv2d_resample, fma, bias_act) and is the cross-check of the fused kernels, not a fast path."""
+        from .shims import ops_modules as om
+        styles = self.affine(w)
+        xn = _to_nchw_view(x)
+        n = xn.shape[0]
+        wt = self.weight.to(torch.float32)
+        dcoefs = ((wt.unsqueeze(0) * styles.reshape(n, 1, -1, 1, 1)).square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()
+        noise = None
+        if self.use_noise and noise_mode == 'random':
+            noise = torch.randn([n, 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
+        if self.use_noise and noise_mode == 'const':
+            noise = self.noise_const * self.noise_strength
+        y = xn * styles.reshape(n, -1, 1, 1)
+        y = om.conv2d_resample(y, wt, f=self.resample_filter, up=self.up, padding=self.padding, flip_weight=(self.up == 1))
+        if noise is not None:
+            y = om.fma(y, dcoefs.reshape(n, -1, 1, 1), noise)
+        else:
+            y = y * dcoefs.reshape(n, -1, 1, 1)
+        clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        y = ops.bias_act(y, self.bias, act=self.activation, gain=self.act_gain * gain, clamp=clamp)
+        return _to_nhwc(y)
 
 
 class ToRGBLayer(torch.nn.Module):
@@ -157,6 +185,15 @@ class ToRGBLayer(torch.nn.Module):
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
     def forward(self, x, w, fused_modconv=True, img_prev=None, x_split=None, bank=None, lidx=-1):
+        if not fused_modconv:                               # networks_stylegan2.py:70-79 with demodulate=False, then the skip add of :451-457
+            from .shims import ops_modules as om
+            styles = self.affine(w) * self.weight_gain
+            xn = _to_nchw_view(x)
+            y = om.conv2d_resample(xn * styles.reshape(xn.shape[0], -1, 1, 1), self.weight.to(torch.float32), padding=0, flip_weight=True)
+            y = ops.bias_act(y, self.bias, clamp=self.conv_clamp)
+            if img_prev is not None:
+                y = y + ops.upsample2d(_to_nchw_view(img_prev), ops.fir_filter(x.device))
+            return _to_nhwc(y)
         styles = self.affine(w) * self.weight_gain if bank is None else None
         return ops.torgb_layer(x, self.weight, styles, self.bias, img_prev, self.conv_clamp, x_split=x_split, bank=bank, lidx=lidx)
 
@@ -204,6 +241,13 @@ class SynthesisBlock(torch.nn.Module):
         bank / bank_base: pre-computed styles + modulated weights (ops.WeightBank) and this block's first entry."""
         w_iter = iter(ws.unbind(dim=1))
         li = bank_base
+        if fused_modconv is None:                           # networks_stylegan2.py:425-428
+            fused_modconv = self.fused_modconv_default
+        if fused_modconv == 'inference_only':
+            fused_modconv = not self.training
+        layer_kwargs = dict(layer_kwargs, fused_modconv=bool(fused_modconv))
+        if not fused_modconv:
+            side = None                                     # the cross-check path is plain stream-ordered torch code
         if self.in_channels == 0:
             x = self.const.to(torch.float32).permute(1, 2, 0).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous()
             sp = None
@@ -212,7 +256,7 @@ class SynthesisBlock(torch.nn.Module):
             li += 1
         x, sp = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, **layer_kwargs)
         if side is None:
-            img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
+            img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1, fused_modconv=bool(fused_modconv))
         else:
             # ToRGB + skip upsample on the second stream: they depend on this block's x only, the next block's convolutions
             # do not depend on them.  Tensors that cross streams are registered with the allocator (record_stream).
