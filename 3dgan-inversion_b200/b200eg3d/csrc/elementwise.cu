@@ -17,46 +17,75 @@ __device__ __forceinline__ void split4(const float* o, uint2* hi, uint2* lo, lon
 }
 
 // ---------------------------------------------------------------------------------------------
-// Generic bias_act.  act codes follow the reference table (bias_act.py:20-30): 1 linear, 2 relu, 3 lrelu,
-// 4 tanh, 5 sigmoid, 6 elu, 7 selu, 8 softplus, 9 swish.  grad: 0 forward, 1 first-order gradient.
+// Generic bias_act (mapping network, odd activations; the synthesis layers use the fused epilogues below).
+// act codes follow the reference table (bias_act.py:20-30): 1 linear, 2 relu, 3 lrelu, 4 tanh, 5 sigmoid, 6 elu, 7 selu,
+// 8 softplus, 9 swish.  Each activation is a small functor:
+//     value(u)          the activation of the biased input u
+//     slope(u_ref, a)   its derivative, expressed through what the forward SAVED for it -- the un-gained output a = y / gain for
+//                       every activation that can be inverted from its output, the biased input u_ref for swish (the only one
+//                       that cannot; bias_act.py:20-30 column 'ref')
+// and the kernel is instantiated per (activation, direction), so the element loop carries no switch:
+//     forward   y  = clamp(value(x + b) * gain)
+//     gradient  dx = dy * slope * gain, zeroed where the saved output sits on the clamp
+namespace bact {
+constexpr float kBig = 80.f;            // exp() saturation guard of the reference kernel (bias_act.cu:92-131): keeps 1/(1+e^-u) etc. finite
+struct Linear   { float alpha; __device__ float value(float u) const { return u; }
+                  __device__ float slope(float, float) const { return 1.f; } };
+struct Relu     { float alpha; __device__ float value(float u) const { return fmaxf(u, 0.f); }
+                  __device__ float slope(float, float a) const { return a > 0.f ? 1.f : 0.f; } };
+struct LRelu    { float alpha; __device__ float value(float u) const { return u > 0.f ? u : u * alpha; }
+                  __device__ float slope(float, float a) const { return a > 0.f ? 1.f : alpha; } };
+struct Tanh     { float alpha; __device__ float value(float u) const { return fabsf(u) > kBig ? copysignf(1.f, u) : tanhf(u); }
+                  __device__ float slope(float, float a) const { return 1.f - a * a; } };
+struct Sigmoid  { float alpha; __device__ float value(float u) const { return u < -kBig ? 0.f : 1.f / (1.f + expf(-u)); }
+                  __device__ float slope(float, float a) const { return a * (1.f - a); } };
+struct Elu      { float alpha; __device__ float value(float u) const { return u >= 0.f ? u : expm1f(u); }
+                  __device__ float slope(float, float a) const { return a >= 0.f ? 1.f : a + 1.f; } };
+struct Selu     { float alpha; static constexpr float S = 1.0507009873554804934f, A = 1.6732632423543772848f;
+                  __device__ float value(float u) const { return u >= 0.f ? S * u : S * A * expm1f(u); }
+                  __device__ float slope(float, float a) const { return a >= 0.f ? S : a + S * A; } };
+struct Softplus { float alpha; __device__ float value(float u) const { return u > kBig ? u : log1pf(expf(u)); }
+                  __device__ float slope(float, float a) const { return -expm1f(-a); } };           // 1 - e^-softplus = sigmoid(u)
+struct Swish    { float alpha; __device__ float value(float u) const { return u < -kBig ? 0.f : u / (1.f + expf(-u)); }
+                  __device__ float slope(float u, float) const {                                     // s + u s (1 - s), s = sigmoid(u)
+                      if (u > 0.5f * kBig) return 1.f;
+                      const float s = u < -kBig ? 0.f : 1.f / (1.f + expf(-u));
+                      return s * (1.f + u * (1.f - s)); } };
 
-__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ xref,
-                                const float* __restrict__ yref, const float* __restrict__ dy, float* __restrict__ y,
-                                int grad, long sizeX, long stepB, int sizeB, int act, float alpha, float gain, float clamp) {
-    const float seluScale = 1.0507009873554804934193349852946f, seluAlpha = 1.6732632423543772848170429916717f;
-    for (long xi = (long)blockIdx.x * blockDim.x + threadIdx.x; xi < sizeX; xi += (long)gridDim.x * blockDim.x) {
-        float xv = x[xi];
-        const float bv = b ? b[(xi / stepB) % sizeB] : 0.f;
-        float xr = xref ? xref[xi] : 0.f;
-        float yr = yref ? yref[xi] : 0.f;
-        const float dyv = dy ? dy[xi] : 1.f;
-        const float yy = gain != 0.f ? yr / gain : 0.f;
-        float out = 0.f;
-        if (grad == 0) xv += bv; else xr += bv;
-        switch (act) {
-            case 1: out = xv; break;
-            case 2: out = grad == 0 ? (xv > 0.f ? xv : 0.f) : (yy > 0.f ? xv : 0.f); break;
-            case 3: out = grad == 0 ? (xv > 0.f ? xv : xv * alpha) : (yy > 0.f ? xv : xv * alpha); break;
-            case 4: if (grad == 0) { float c = expf(xv), d = 1.f / c; out = xv < -80.f ? -1.f : xv > 80.f ? 1.f : (c - d) / (c + d); }
-                    else out = xv * (1.f - yy * yy); break;
-            case 5: out = grad == 0 ? (xv < -80.f ? 0.f : 1.f / (expf(-xv) + 1.f)) : xv * yy * (1.f - yy); break;
-            case 6: out = grad == 0 ? (xv >= 0.f ? xv : expf(xv) - 1.f) : (yy >= 0.f ? xv : xv * (yy + 1.f)); break;
-            case 7: out = grad == 0 ? (xv >= 0.f ? seluScale * xv : seluScale * seluAlpha * (expf(xv) - 1.f))
-                                    : (yy >= 0.f ? xv * seluScale : xv * (yy + seluScale * seluAlpha)); break;
-            case 8: out = grad == 0 ? (xv > 80.f ? xv : logf(expf(xv) + 1.f)) : xv * (1.f - expf(-yy)); break;
-            case 9: if (grad == 0) out = xv < -80.f ? 0.f : xv / (expf(-xv) + 1.f);
-                    else { float c = expf(xr), d = c + 1.f; out = xr > 40.f ? xv : xv * c * (xr + d) / (d * d);
-                           yr = xr < -80.f ? 0.f : xr / (expf(-xr) + 1.f) * gain; } break;
-            default: break;
+template <typename Act, bool GRAD>
+__global__ void bias_act_generic_kernel(const float* __restrict__ x, const float* __restrict__ b, const float* __restrict__ xref,
+                                        const float* __restrict__ yref, const float* __restrict__ dy, float* __restrict__ y, long total,
+                                        long stepB, int sizeB, Act act, float gain, float clamp) {
+    const float inv_gain = gain != 0.f ? 1.f / gain : 0.f;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const float bias = b ? b[(i / stepB) % sizeB] : 0.f;
+        const float scale = gain * (dy ? dy[i] : 1.f);
+        float out;
+        if (!GRAD) {
+            out = act.value(x[i] + bias) * scale;
+            if (clamp >= 0.f) out = fminf(fmaxf(out, -clamp), clamp);
+        } else {
+            const float u_ref = (xref ? xref[i] : 0.f) + bias;                       // only swish reads it
+            float y_saved = yref ? yref[i] : 0.f;
+            if (!yref && xref) y_saved = act.value(u_ref) * gain;                    // swish: the clamp test needs the output, rebuilt from the input
+            out = x[i] * act.slope(u_ref, y_saved * inv_gain) * scale;
+            if (clamp >= 0.f && !(y_saved > -clamp && y_saved < clamp)) out = 0.f;
         }
-        out *= gain * dyv;
-        if (clamp >= 0.f) {
-            if (grad == 0) out = (out > -clamp && out < clamp) ? out : (out >= 0.f ? clamp : -clamp);
-            else out = (yr > -clamp && yr < clamp) ? out : 0.f;
-        }
-        y[xi] = out;
+        y[i] = out;
     }
 }
+
+template <typename Act>
+static int launch_bias_act(bool grad, const float* x, const float* b, const float* xref, const float* yref, const float* dy, float* y, long total,
+                           long stepB, int sizeB, float alpha, float gain, float clamp, cudaStream_t st) {
+    const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    const Act act{alpha};
+    if (grad) bias_act_generic_kernel<Act, true><<<blocks, 256, 0, st>>>(x, b, xref, yref, dy, y, total, stepB, sizeB, act, gain, clamp);
+    else bias_act_generic_kernel<Act, false><<<blocks, 256, 0, st>>>(x, b, xref, yref, dy, y, total, stepB, sizeB, act, gain, clamp);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+}  // namespace bact
 
 // Fast path of the two hot uses (ToRGB bias + clamp and its gradient): channel-last bias (stepB == 1), linear / lrelu,
 // 4 elements per thread, 32-bit index math.
@@ -104,11 +133,21 @@ B200_API int b200_bias_act(const float* x, const float* b, const float* xref, co
                              (const float4*)yref, (float4*)y, grad, n4, (int)(b ? sizeB / 4 : 1), (int)(act == 3), alpha, gain, clamp));
         return 0;
     }
-    const int blocks = (int)((sizeX + 255) / 256 < 148 * 16 ? (sizeX + 255) / 256 : 148 * 16);
-    bias_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, b, xref, yref, dy, y, grad, sizeX, stepB > 0 ? stepB : 1,
-                                                              sizeB > 0 ? sizeB : 1, act, alpha, gain, clamp);
-    B200_CHECK_LAUNCH();
-    return 0;
+    const long sb = stepB > 0 ? stepB : 1;
+    const int nb = sizeB > 0 ? sizeB : 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    using namespace bact;
+    switch (act) {
+        case 1: return launch_bias_act<Linear>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 2: return launch_bias_act<Relu>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 3: return launch_bias_act<LRelu>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 4: return launch_bias_act<Tanh>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 5: return launch_bias_act<Sigmoid>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 6: return launch_bias_act<Elu>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 7: return launch_bias_act<Selu>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        case 8: return launch_bias_act<Softplus>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+        default: return launch_bias_act<Swish>(grad, x, b, xref, yref, dy, y, sizeX, sb, nb, alpha, gain, clamp, st);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

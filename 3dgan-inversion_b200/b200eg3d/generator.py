@@ -89,22 +89,26 @@ class MappingNetwork(torch.nn.Module):
 
     def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False):
         x = None
-        if self.z_dim > 0:
-            x = normalize_2nd_moment(z.to(torch.float32))
-        if self.c_dim > 0:
-            y = normalize_2nd_moment(self.embed(c.to(torch.float32)))
-            x = torch.cat([x, y], dim=1) if x is not None else y
+        with ops.prof_range('input'):
+            if self.z_dim > 0:
+                x = normalize_2nd_moment(z.to(torch.float32))
+            if self.c_dim > 0:
+                y = normalize_2nd_moment(self.embed(c.to(torch.float32)))
+                x = torch.cat([x, y], dim=1) if x is not None else y
         for idx in range(self.num_layers):
             x = getattr(self, f'fc{idx}')(x)
         if update_emas and self.w_avg_beta is not None:
-            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+            with ops.prof_range('update_w_avg'):
+                self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
         if self.num_ws is not None:
-            x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+            with ops.prof_range('broadcast'):
+                x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
         if truncation_psi != 1:
-            if self.num_ws is None or truncation_cutoff is None:
-                x = self.w_avg.lerp(x, truncation_psi)
-            else:
-                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+            with ops.prof_range('truncate'):
+                if self.num_ws is None or truncation_cutoff is None:
+                    x = self.w_avg.lerp(x, truncation_psi)
+                else:
+                    x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
         return x
 
 
@@ -300,12 +304,13 @@ class SynthesisNetwork(torch.nn.Module):
 
     def _forward_nhwc(self, ws, **block_kwargs):
         block_ws = []
-        ws = ws.to(torch.float32)
-        w_idx = 0
-        for res in self.block_resolutions:
-            block = getattr(self, f'b{res}')
-            block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
-            w_idx += block.num_conv
+        with ops.prof_range('split_ws'):
+            ws = ws.to(torch.float32)
+            w_idx = 0
+            for res in self.block_resolutions:
+                block = getattr(self, f'b{res}')
+                block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
+                w_idx += block.num_conv
         bank, bases = None, [0] * len(self.block_resolutions)
         if ops.CONFIG['bank']:
             specs, w_idx = [], 0

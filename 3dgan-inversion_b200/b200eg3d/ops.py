@@ -26,6 +26,10 @@ _ACT_REF = {'linear': '', 'relu': 'y', 'lrelu': 'y', 'tanh': 'y', 'sigmoid': 'y'
 
 # Numerics of the convolution stack.  tc: use the tcgen05 kernels when the shape allows; *_passes: 3 = split-bf16
 # (hi*hi + hi*lo + lo*hi, ~fp32 accuracy), 1 = plain bf16 operands.  B200EG3D_TC=0 forces the exact-fp32 SIMT kernels.
+# Defaults: forward and dgrad 3-pass (their errors would compound through 17 layers and fail the 1e-3 bar), wgrad 1-pass: a weight
+# gradient is a sum over all pixels of products whose bf16 rounding errors (2^-9 relative, zero-mean) are independent, so the sum
+# keeps ~1e-3 relative accuracy -- measured per parameter by tests/test_gpu_golden.py (channel norms and strided samples of every
+# gradient tensor, worst 2.7e-3 against the 1e-2 bar).  B200EG3D_WGRAD_PASSES=3 buys fp32-equivalent weight gradients for ~0.5 ms.
 CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           'fwd_passes': int(os.environ.get('B200EG3D_FWD_PASSES', '3')),
           'bank': os.environ.get('B200EG3D_BANK', '1') != '0',       # batch styles + weight prep of all layers into one launch
@@ -34,11 +38,33 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           # run the ToRGB / skip-upsample chain on a second stream, concurrently with the next block's convolutions
           'overlap': os.environ.get('B200EG3D_OVERLAP', '1') != '0',
           # walk 8x16-pixel ray patches front to back in the tri-plane kernels instead of ray after ray (measured slower: see DESIGN.md)
-          'ray_patch_order': os.environ.get('B200EG3D_RAY_PATCH_ORDER', '0') != '0'}
+          'ray_patch_order': os.environ.get('B200EG3D_RAY_PATCH_ORDER', '0') != '0',
+          'ranges': os.environ.get('B200EG3D_RANGES', '0') != '0'}
 
 
 def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
+
+
+class _NullRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_RANGE = _NullRange()
+
+
+def prof_range(name):
+    """torch.autograd.profiler.record_function(name) with the range names the reference emits (misc.profiled_function,
+    torch_utils/misc.py:102-107: 'modulated_conv2d', 'conv2d_resample', ...; networks_stylegan2.py:236-262,505: 'input',
+    'broadcast', 'truncate', 'split_ws'), so traces of the two implementations line up.  Free when no profiler is recording
+    (and in graph replay, where no Python runs at all); B200EG3D_RANGES=1 forces the ranges on (NVTX via emit_nvtx)."""
+    if CONFIG['ranges'] or torch.autograd.profiler._is_profiler_enabled:
+        return torch.autograd.profiler.record_function(name)
+    return _NULL_RANGE
 
 
 def _tc_ok(kind, h, w, cin, cout, k, up):
@@ -125,7 +151,8 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
     clamp = float(clamp if clamp is not None else -1)
     if b is not None and (b.ndim != 1 or b.shape[0] != x.shape[dim]):
         raise ValueError('bias must be a vector matching x.shape[dim]')
-    return _BiasAct.apply(x, b, dim, act, alpha, gain, clamp)
+    with prof_range('bias_act'):
+        return _BiasAct.apply(x, b, dim, act, alpha, gain, clamp)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -218,7 +245,8 @@ def upfirdn2d_nhwc(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1):
 def upfirdn2d(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda'):
     """NCHW front-end with the reference's signature (upfirdn2d.py:120): every (n, c) image is one single-channel map."""
     n, c, h, w = x.shape
-    y = upfirdn2d_nhwc(x.reshape(n * c, h, w, 1), f, up, down, padding, flip_filter, gain)
+    with prof_range('upfirdn2d'):
+        y = upfirdn2d_nhwc(x.reshape(n * c, h, w, 1), f, up, down, padding, flip_filter, gain)
     return y.reshape(n, c, y.shape[1], y.shape[2])
 
 
@@ -277,12 +305,21 @@ class WeightBank:
         self.dwmod = [None] * n
         self.need_wgrad = False
         self.token = None
+        self.ztotal = 0
         self.zpool = None          # one zero-filled buffer for the small backward accumulators (d bias, d noise_strength) of all layers
         self.zoff = []
         self.side = None           # second stream some layers ran on (CONFIG['overlap']); the bank's backward joins it
 
     def zeros(self, lidx, cout):
-        """(d bias [cout], d strength []) views into the pool: one fill per network and pass instead of two per layer."""
+        """(d bias [cout], d strength []) views into the pool: one fill per network and pass instead of two per layer.
+        The pool made by the forward serves ONE backward pass (the views are handed to autograd as gradients and may end up as
+        param.grad); _Bank.backward drops it, so a second pass over a retained graph gets a fresh, zeroed pool here."""
+        if self.zpool is None:
+            torch.cuda.synchronize()                       # rare path (retain_graph): order the fill against both stream branches the blunt way
+            self.zpool = torch.zeros([self.ztotal], device=self.styles[0].device, dtype=torch.float32)
+            if self.side is not None:
+                self.zpool.record_stream(self.side)
+            torch.cuda.synchronize()
         o = self.zoff[lidx]
         return self.zpool[o:o + cout], self.zpool[o + cout]
 
@@ -324,6 +361,7 @@ class _Bank(torch.autograd.Function):
         for sp in bank.specs:
             bank.zoff.append(tot)
             tot += (sp.cout + 1 + 3) // 4 * 4
+        bank.ztotal = tot
         bank.zpool = torch.zeros([tot], device=dev, dtype=torch.float32)
         arr = _bank_array(bank, n, dev)
         call('b200_bank_styles_fwd', ctypes.addressof(arr), len(bank.specs), ptr(ws), n, num_ws, w_dim, stream())
@@ -365,6 +403,8 @@ class _Bank(torch.autograd.Function):
         call('b200_bank_weights_bwd', ctypes.addressof(arr), len(specs), n, stream())
         call('b200_bank_styles_bwd', ctypes.addressof(arr), len(specs), ptr(ws), ptr(d_ws), n, num_ws, w_dim, stream())
         bank.dwmod = [None] * len(specs)
+        bank.zpool = None          # its slices now belong to autograd (possibly as param.grad): never accumulate into them again
+        bank.token = None          # token -> grad_fn -> ctx.bank -> bank was a reference cycle keeping the per-step weight tensors alive
         return (d_ws, None, *grads)
 
 
@@ -573,10 +613,11 @@ def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp,
     """Returns (z, (z_hi, z_lo) or None).  x_split: the producer's split-bf16 copies of x, if it made them.
     bank / lidx: take styles and modulated weights from a WeightBank entry instead of (weight, styles)."""
     xh, xl = x_split if x_split is not None else (None, None)
-    if bank is not None:
-        z, zh, zl = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank, lidx)
-    else:
-        z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
+    with prof_range('modulated_conv2d'):
+        if bank is not None:
+            z, zh, zl = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank, lidx)
+        else:
+            z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
     return z, ((zh, zl) if zh is not None else None)
 
 
@@ -685,9 +726,10 @@ class _ToRGB(torch.autograd.Function):
 
 def torgb_layer(x, weight, styles, bias, img_prev, clamp, x_split=None, bank=None, lidx=-1):
     xh, xl = x_split if x_split is not None else (None, None)
-    if bank is not None:
-        return _ToRGB.apply(x, xh, xl, None, None, bias, img_prev, clamp, bank.token, bank, lidx)
-    return _ToRGB.apply(x, xh, xl, weight, styles, bias, img_prev, clamp)
+    with prof_range('modulated_conv2d'):
+        if bank is not None:
+            return _ToRGB.apply(x, xh, xl, None, None, bias, img_prev, clamp, bank.token, bank, lidx)
+        return _ToRGB.apply(x, xh, xl, weight, styles, bias, img_prev, clamp)
 
 
 # ----------------------------------------------------------------------------------------------

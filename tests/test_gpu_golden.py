@@ -140,3 +140,21 @@ def test_tensors_on_a_non_current_device_guarded(golden_dir):
         out = G.synthesis(case.ws.to(dev), case.c.to(dev), noise_mode='const')
     assert out['image'].device == dev
     assert np.abs(out['image_raw'].cpu().numpy() - case.fx['image_raw']).max() < TOL_OUT
+
+
+def test_second_backward_over_a_retained_graph(golden_dir):
+    """ADVICE r1: the pooled zero-initialised accumulators (d bias, d noise_strength of all layers) serve one backward pass only;
+    a second pass over the same graph must ADD the same gradients again, not accumulate into buffers autograd already owns."""
+    case = load_case(golden_dir, 'tiny_r64_s16')
+    G = build_G(case, requires_grad=True)
+    out = synth(G, case, case.ws.cuda(), case.c.cuda())
+    loss = oracle.pti_loss(out, case.t512.cuda(), case.t_raw.cuda())
+    loss.backward(retain_graph=True)
+    once = {n: p.grad.detach().clone() for n, p in G.named_parameters() if p.grad is not None}
+    loss.backward()
+    for n, p in G.named_parameters():
+        if p.grad is None:
+            continue
+        ref = 2 * once[n]
+        err = (p.grad - ref).abs().max().item()
+        assert err <= 1e-4 * max(ref.abs().max().item(), 1e-6) + 1e-7, (n, err)
