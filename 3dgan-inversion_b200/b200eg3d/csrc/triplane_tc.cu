@@ -150,6 +150,14 @@ __device__ __forceinline__ uint32_t bar_a2_full(uint32_t b, int s) { return b + 
 __device__ __forceinline__ uint32_t bar_d2_full(uint32_t b, int s) { return b + 8u * (2 * NGRP + 4 + s); }   // 2
 constexpr int BAR_TMEM_SLOT = 8 * (2 * NGRP + 6);
 
+// Producer / consumer hand-off between two groups of 128 threads on a hardware named barrier: the producers bar.arrive (do not
+// block), the consumers bar.sync (block until all `count` threads of both groups have arrived).  Used for the thread-to-thread
+// d_f staging hand-off (consumer set <-> its scatter group), where both sides are ordinary shared-memory accesses; the
+// hand-offs to and from the tensor core use mbarriers (tcgen05.commit can only signal those).
+constexpr int NB_DF_FULL = 1, NB_DF_FREE = 3;       // + set; barrier 0 is __syncthreads
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
@@ -457,7 +465,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
         for (int s = 0; s < 2; ++s) {
             mbar_init(bb_set(B, BB_D1, s), 1); mbar_init(bb_set(B, BB_A2, s), 4); mbar_init(bb_set(B, BB_D2, s), 1);
             mbar_init(bb_set(B, BB_A3, s), 4); mbar_init(bb_set(B, BB_D3, s), 1); mbar_init(bb_set(B, BB_A4, s), 4);
-            mbar_init(bb_set(B, BB_D4, s), 1); mbar_init(bb_set(B, BB_DF_FULL, s), 4); mbar_init(bb_set(B, BB_DF_FREE, s), 4);
+            mbar_init(bb_set(B, BB_D4, s), 1);
         }
         mbar_init(B + BB_ACC_DONE, 1);
         fence_barrier_init();
@@ -504,12 +512,11 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                 *reinterpret_cast<float4*>(sx + lane * SPX + 4) = make_float4(f[4], f[5], __int_as_float(m0 | (m1 << 4) | (m2 << 8)), 0.f);
                 if (pi >= 0 && !p.coords) tdepth = p.depths[row0 + pi];
             }
-            mbar_wait_sleep(bb_set(B, BB_DF_FULL, sg), it & 1);
+            named_sync(NB_DF_FULL + sg, 256);                                    // the consumer set has staged this tile's d_f
             float4 g[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) g[i] = *reinterpret_cast<const float4*>(stg + sw128(w * 32 + i * 4 + pt, l8));
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bb_set(B, BB_DF_FREE, sg));               // the staging rows are in registers now
+            named_arrive(NB_DF_FREE + sg, 256);                                  // the staging rows are in registers now
             if (dpl) {
                 float* pc = dpl + l8 * 4;
 #pragma unroll
@@ -675,7 +682,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
             // ---- S1: h' = lg2(1 + 2^y)
             mbar_wait(bb_set(B, BB_D1, set), it & 1);
             tc_fence_after();
-            if (it > 0) mbar_wait(bb_set(B, BB_DF_FREE, set), (it - 1) & 1);       // the scatter warps have taken the previous d_f out of A2lo
+            if (it > 0) named_sync(NB_DF_FREE + set, 256);                         // the scatter warps have taken the previous d_f out of A2lo
             {   // keep this tile's F (hi half: chunks 0..3 of the row) for the dW1 contraction at the end of the chain; the stage goes back to the gather
                 const uint8_t* a1 = sm + BO_A1 + (lt % BW_ST) * 16384;
                 uint8_t* fc = sm + BO_FC + set * 16384;
@@ -787,8 +794,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
                 for (int c = 0; c < 8; ++c)
                     *reinterpret_cast<float4*>(a2l + sw128(row, c)) = make_float4(df[4 * c], df[4 * c + 1], df[4 * c + 2], df[4 * c + 3]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bb_set(B, BB_DF_FULL, set));
+            named_arrive(NB_DF_FULL + set, 256);
         }
         // ---- drain of the weight / bias gradient accumulators (set 0's four warps cover the 128 TMEM lanes)
         if (WGRAD && set == 0 && nloc > 0) {
