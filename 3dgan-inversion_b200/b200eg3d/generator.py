@@ -513,7 +513,8 @@ class ImportanceRenderer(torch.nn.Module):
         auto = rendering_options['ray_start'] == rendering_options['ray_end'] == 'auto'
         disparity = bool(rendering_options.get('disparity_space_sampling', False))
         if self.fixed_noise is not None:
-            u_strat, u_imp = self.fixed_noise
+            # a (u_strat, u_imp) pair used for every call, or a list of pairs consumed one per call (tests replaying several renders)
+            u_strat, u_imp = self.fixed_noise.pop(0) if isinstance(self.fixed_noise, list) else self.fixed_noise
             u_strat = u_strat.to(dev)
             u_imp = u_imp.to(dev) if S2 > 0 else None
         else:

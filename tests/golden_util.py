@@ -179,3 +179,41 @@ def stage1_inputs(name, R, H):
     return {'init_ext': c0[:, :16].reshape(1, 4, 4).clone(), 'extrinsic': c1[:, :16].reshape(1, 4, 4).clone(),
             'intrinsic': c0[0, 16:25].clone(), 'depth': depth.reshape(1, 1, R, R).contiguous(), 'can_image': can.contiguous(),
             'target': torch.rand(1, 3, 256, 256, generator=g) * 2 - 1}
+
+
+def stage1_pose_net(seed=13):
+    """Seeded stand-in for the camera encoder (cam_predictor of w_projector.py:160-171, use_6d branch): target image [1,3,256,256]
+    in 0..255 -> 6-D rotation representation near the canonical pose."""
+    import torch.nn as nn
+    net = nn.Sequential(nn.AvgPool2d(32), nn.Flatten(), nn.Linear(3 * 8 * 8, 6))
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        net[2].weight.copy_(torch.randn(net[2].weight.shape, generator=g) * 2e-5)
+        net[2].bias.copy_(torch.tensor([1.0, 0.05, 0.0, 0.02, -1.0, 0.03]))
+    return net
+
+
+def stage1_feature_fn(net, scale=5e-5):
+    """The feature-distance network of the fixture: the stand-in stack on the 0..255 image scaled to 0..1, features scaled so that the
+    squared feature distance is O(1e3) like the warping and regulariser terms (call signature of the reference's vgg16(...))."""
+    return lambda img, resize_images=False, return_lpips=True: net(img * (1.0 / 255.0)) * scale
+
+
+def stage1_noise_init(named_bufs, seed=17):
+    """Start values of the 17 noise buffers (w_projector.py:128-133 draws them with randn_like): one seeded generator, buffer order."""
+    gen = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for _, buf in named_bufs:
+            buf.copy_(torch.randn(buf.shape, generator=gen).to(buf.device))
+
+
+def stage1_iter_setup(R=32, S=8, seed=31):
+    """Inputs of the one-iteration w-projection fixture (tests/golden/stage1_iter.npz): tiny generator, stand-in networks, start state."""
+    g = torch.Generator().manual_seed(seed)
+    rk = sp.rendering_kwargs(depth_resolution=S, depth_resolution_importance=S)
+    return {'R': R, 'S': S, 'rk': rk, 'gk': sp.G_KWARGS_TINY, 'param_seed': 7,
+            'target': torch.rand(3, 512, 512, generator=g) * 2 - 1,
+            'w_start': sp.latent_ws(5)[:, :1].clone(),
+            'translation': torch.tensor([[0.01, -0.02, 0.015]]),
+            'w_noise': torch.randn(1, 1, 512, generator=g) * 0.02,
+            'step': 60, 'num_steps': 400, 'w_std': 1.0}

@@ -158,3 +158,36 @@ def test_second_backward_over_a_retained_graph(golden_dir):
         ref = 2 * once[n]
         err = (p.grad - ref).abs().max().item()
         assert err <= 1e-4 * max(ref.abs().max().item(), 1e-6) + 1e-7, (n, err)
+
+
+def test_generator_io_on_device(golden_dir, tmp_path):
+    """SURVEY 8 f4 on the GPU: pickle -> seam.load_old_G (a source generator exposing the REAL reference's name / shape manifest) and the
+    tuned-generator checkpoint round trip both reproduce the fixture image."""
+    import pickle
+    import b200eg3d
+    from golden_util import manifest
+    from test_cabi_and_host import _ManifestModule
+    case = load_case(golden_dir, 'tiny_r64_s16')
+    src = _ManifestModule(manifest('tiny'), case.gk, case.rk)
+    sp.fill_params_(dict(list(src.named_parameters()) + list(src.named_buffers())), case.param_seed)
+    src.neural_rendering_resolution = case.R
+    pkl = str(tmp_path / 'network.pkl')
+    with open(pkl, 'wb') as f:
+        pickle.dump({'G_ema': src}, f)                                       # layout of the EG3D pickles (models_utils.py:21-25)
+    G = b200eg3d.seam.load_old_G(pkl, device='cuda')
+    assert G.neural_rendering_resolution == case.R and next(G.parameters()).is_cuda
+    G.renderer.fixed_noise = (case.u_strat, case.u_imp)
+    with torch.no_grad():
+        a = G.synthesis(case.ws.cuda(), case.c.cuda(), noise_mode='const')
+    assert np.abs(a['image_raw'].cpu().numpy() - case.fx['image_raw']).max() < TOL_OUT
+    assert check_image(a['image'], case.fx, TOL_OUT)[0] < TOL_OUT
+    ck = str(tmp_path / 'tuned.pt')
+    with torch.no_grad():
+        G.decoder.net[0].bias.add_(0.25)                                     # "tuned"
+    b200eg3d.seam.save_tuned_G(G, ck)
+    G2 = b200eg3d.seam.load_tuned_G(ck, device='cuda')
+    G2.renderer.fixed_noise = (case.u_strat, case.u_imp)
+    with torch.no_grad():
+        b1 = G.synthesis(case.ws.cuda(), case.c.cuda(), noise_mode='const')
+        b2_ = G2.synthesis(case.ws.cuda(), case.c.cuda(), noise_mode='const')
+    assert torch.allclose(b1['image'], b2_['image'], atol=1e-4) and not torch.allclose(b1['image_raw'], a['image_raw'], atol=1e-3)

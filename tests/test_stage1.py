@@ -155,3 +155,62 @@ def test_pose_helpers_match_reference_fixture():
     assert torch.equal(projector.get_features(x, net, '14'), s1.get_features(x, net, '14'))
     with pytest.raises(ValueError):
         projector.get_features(x, net, '5')
+
+
+@pytest.mark.gpu
+def test_projection_iteration_matches_reference_loop_body(b2):
+    """One whole w-projection iteration (w_projector.py:160-268) on the b200eg3d path against tests/golden/stage1_iter.npz, which
+    oracle/make_goldens_stage1_iter.py recorded by EXECUTING the reference's own loop body (extracted with ast) around the unmodified
+    reference generator / calc_warping_loss / rot6d_to_rotmat: loss and its three parts, the gradients of the latent, the pose
+    predictor and the translation, and every optimised quantity after the three Adam steps and the noise normalisation."""
+    import synth_params as sp
+    from golden_util import stage1_feature_fn, stage1_iter_setup, stage1_noise_init, stage1_pose_net
+    from b200eg3d import projector
+    from b200eg3d.coach import ProjectionStep
+    fx = np.load(os.path.join(os.path.dirname(GOLD), 'stage1_iter.npz'))
+    cfg = stage1_iter_setup()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    G = b2.TriPlaneGenerator(rendering_kwargs=cfg['rk'], **cfg['gk']).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), cfg['param_seed'])
+    G = G.cuda()
+    G.neural_rendering_resolution = cfg['R']
+    for m in G.modules():
+        if hasattr(m, 'noise_strength'):
+            m.noise_strength.data.fill_(0.05)
+    feat, torch_vgg, pose = stage1_feature_net(11).cuda(), stage1_feature_net(12).cuda(), stage1_pose_net(13).cuda()
+    target = cfg['target'].cuda()
+    t255 = torch.nn.functional.interpolate(((target + 1) / 2 * 255).unsqueeze(0), size=(256, 256), mode='area')
+    c0 = sp.camera(0.0, 0.0).cuda()
+    st = ProjectionStep(G, cfg['w_start'].cuda(), list(pose.parameters()), lambda: projector.rot6d_to_rotmat(pose(t255)),
+                        c0[:, :16].reshape(1, 4, 4).contiguous(), c0[0, 16:25].contiguous(), target.unsqueeze(0).contiguous(),
+                        stage1_feature_fn(feat), torch_vgg, first_inv_lr=8e-3, cam_lr=6e-6, translation_lr=2e-4, graphed=False)
+    named = list(st.noise_bufs.items()) + list(st.noise_bufs2.items())
+    stage1_noise_init(named)
+    with torch.no_grad():
+        st.translation_opt.copy_(cfg['translation'].cuda())
+    # the four uniform draws of the two renders (predicted camera, canonical camera), in the order the reference consumed them
+    G.renderer.fixed_noise = [(torch.from_numpy(fx['draw0']), torch.from_numpy(fx['draw1'])), (torch.from_numpy(fx['draw2']), torch.from_numpy(fx['draw3']))]
+    loss = st.step(cfg['w_noise'].cuda(), lr=float(fx['lr']))
+    parts = {k: float(v) for k, v in st.parts.items()}
+    print('loss', loss.item(), float(fx['loss']), parts, float(fx['dist']), float(fx['warp_loss']), float(fx['reg_loss']))
+    assert abs(parts['dist'] - float(fx['dist'])) <= 2e-3 * float(fx['dist'])
+    assert abs(parts['warp'] - float(fx['warp_loss'])) <= 2e-3 * float(fx['warp_loss'])
+    assert abs(parts['reg'] - float(fx['reg_loss'])) <= 1e-4 * float(fx['reg_loss'])
+    assert abs(loss.item() - float(fx['loss'])) <= 1e-3 * float(fx['loss'])
+    assert relerr(st.w_opt.grad, torch.from_numpy(fx['grad_w_opt'])) < 1e-2
+    assert relerr(st.translation_opt.grad, torch.from_numpy(fx['grad_translation'])) < 1e-2
+    assert relerr(pose[2].bias.grad, torch.from_numpy(fx['grad_pose_b'])) < 1e-2
+    # after the optimiser steps: Adam's first update is +-lr per element, so compare the MOVES (a sign flip of a near-zero gradient
+    # is a full 2 lr on that element)
+    for mine, start, key in ((st.w_opt, cfg['w_start'], 'w_opt_after'), (st.translation_opt, cfg['translation'], 'translation_after')):
+        move, ref = mine.detach().cpu() - start, torch.from_numpy(fx[key]) - start
+        assert relerr(move, ref) < 0.15, key
+    assert relerr(pose[2].bias.detach() - stage1_pose_net(13)[2].bias.cuda(), torch.from_numpy(fx['pose_b_after']) - stage1_pose_net(13)[2].bias) < 0.15
+    for name, buf in named:
+        key = name.replace('.', '_')
+        stride = max(1, buf.shape[0] // 32)
+        assert relerr(buf.detach()[::stride, ::stride], torch.from_numpy(fx['noise_after_' + key])) < 2e-2, name
+        mom = fx['noise_after_mom_' + key]
+        assert abs(buf.detach().double().square().sum().item() - mom[1]) <= 1e-3 * mom[1], name          # unit second moment after w_projector.py:262-268
+        assert relerr(buf.grad.norm().reshape(1), torch.tensor([float(fx['noise_grad_norm_' + key])])) < 2e-2, name
