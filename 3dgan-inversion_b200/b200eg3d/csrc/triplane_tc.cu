@@ -25,7 +25,7 @@ using namespace tri;
 using namespace tc;
 
 constexpr int TILE = 128, OUTP = 48;
-constexpr int NCONS = 8, MMA_WARP = 8, GATHER0 = 9, NGRP = 3, NG = 4 * NGRP;   // 3 gather groups of 4 warps = 3 tiles being gathered
+constexpr int NCONS = 8, MMA_WARP = 8, GATHER0 = 9, NGRP = 4, NG = 4 * NGRP;   // 4 gather groups of 4 warps = 4 tiles being gathered
 constexpr int FW_THREADS = (NCONS + 1 + NG) * 32;              // 672
 
 // shared-memory map (bytes from a 1024-aligned base)

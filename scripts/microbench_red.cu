@@ -13,6 +13,17 @@ __global__ void k_red_v4(float* dst, int lines_mask, int iters) {
         asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(a), "f"(1.f) : "memory");
     }
 }
+__global__ void k_gather_v4(const float* __restrict__ src, float* out, int lines_mask, int iters) {      // what the sampler's gather does
+    const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        const uint32_t line = hash32((gw * iters + i) * 4 + (lane >> 3)) & lines_mask;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)line * 32 + (lane & 7) * 4));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 1234.5f) out[0] = acc.x;
+}
 __global__ void k_red_s(float* dst, int lines_mask, int iters) {
     const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     for (int i = 0; i < iters; ++i) {
@@ -41,6 +52,15 @@ int main() {
     float* d; cudaMalloc(&d, (size_t)nlines * 128); cudaMemset(d, 0, (size_t)nlines * 128);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float ms;
+    for (int warps = 8; warps <= 32; warps *= 2) {
+        const int iters = 2048, mask = (25 << 20) / 128 - 1 >= (1 << 17) ? (1 << 17) - 1 : (1 << 17) - 1;      // 16 MB of lines (power of two below the 25 MB planes)
+        k_gather_v4<<<148, warps * 32>>>(d, d, mask, 64);
+        cudaEventRecord(e0); k_gather_v4<<<148, warps * 32>>>(d, d, mask, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        double lines = 148.0 * warps * iters * 4;
+        printf("gather.v4 %2d warps/SM: %8.3f ms  %6.2f clk/line/SM @1.9GHz  %7.1f GB/s (L2-resident 128-byte lines, random)\n", warps, ms,
+               ms * 1e-3 * 1.9e9 / (lines / 148), lines * 128 / ms / 1e6);
+    }
     for (int warps = 4; warps <= 16; warps *= 2) {
         const int iters = 2048;
         k_red_v4<<<148, warps * 32>>>(d, nlines - 1, 64);
