@@ -14,7 +14,7 @@ _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 
 # b200_version() this binding table was written for.  Bumped together with csrc/conv_api.cu whenever a prototype changes: a
 # stale or variant .so (B200EG3D_LIB) with other argument lists would otherwise be called with the wrong stack layout.
-EXPECTED_VERSION = 200
+EXPECTED_VERSION = 201
 
 # name -> argument ctypes (every function returns int status; 0 = ok)
 SIGNATURES = {
@@ -29,7 +29,8 @@ SIGNATURES = {
     'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_fwd_tc_act': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
-    'b200_conv_wgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_wgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_adam_step': [_P, _I, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     'b200_modconv_weight_prep': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200_modconv_weight_prep_bwd': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     'b200_bias_act': [_P, _P, _P, _P, _P, _P, _I, _L, _L, _I, _I, _F, _F, _F, _P],

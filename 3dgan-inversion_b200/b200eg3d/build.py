@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200eg3d.so')
-SOURCES = ['bank.cu', 'conv_tc.cu', 'conv_api.cu', 'conv_simt.cu', 'modconv.cu', 'elementwise.cu', 'triplane.cu', 'triplane_tc.cu', 'raymarch.cu', 'losses.cu', 'projector.cu']
+SOURCES = ['bank.cu', 'conv_tc.cu', 'conv_api.cu', 'conv_simt.cu', 'modconv.cu', 'elementwise.cu', 'triplane.cu', 'triplane_tc.cu', 'raymarch.cu', 'losses.cu', 'projector.cu', 'optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC,-fvisibility=hidden', '--use_fast_math=false']
 

@@ -14,7 +14,7 @@ import math
 import numpy as np
 import torch
 
-from . import losses, projector
+from . import losses, optim, projector
 from .graphs import GraphedStep
 
 
@@ -27,7 +27,7 @@ class PTIStep:
         self.params = [p for n, p in G.named_parameters() if '.mapping.' not in n]     # base_coach.py:96-99 tunes G; mapping is unused
         for p in self.params:
             p.requires_grad_(True)
-        self.opt = torch.optim.Adam(self.params, lr=lr, fused=True, capturable=bool(graphed))
+        self.opt = optim.Adam(self.params, lr=lr)             # one launch per step, device-side step counter (graph-capturable)
         self.l2, self.tv, self.extra = pt_l2_lambda, depth_tv_lambda, extra_loss
         self.noise_mode, self.force_fp32 = noise_mode, force_fp32
         self.graph = None
@@ -87,11 +87,10 @@ class ProjectionStep:
         self.translation_opt = torch.zeros(1, 3, device=dev, requires_grad=True)
         self.pose_fn = pose_fn
         self.lr = torch.tensor(first_inv_lr, device=dev, dtype=torch.float32)
-        cap = bool(graphed)
-        self.optimizer = torch.optim.Adam([self.w_opt] + list(self.noise_bufs.values()) + list(self.noise_bufs2.values()),
-                                          betas=(0.9, 0.999), lr=self.lr, fused=True, capturable=cap)
-        self.cam_optimizer = torch.optim.Adam(list(pose_params), lr=cam_lr, betas=(0.9, 0.999), fused=True, capturable=cap)
-        self.translation_optimizer = torch.optim.Adam([self.translation_opt], lr=translation_lr, fused=True, capturable=cap)
+        self.optimizer = optim.Adam([self.w_opt] + list(self.noise_bufs.values()) + list(self.noise_bufs2.values()),
+                                    betas=(0.9, 0.999), lr=self.lr)
+        self.cam_optimizer = optim.Adam(list(pose_params), lr=cam_lr, betas=(0.9, 0.999))
+        self.translation_optimizer = optim.Adam([self.translation_opt], lr=translation_lr)
         self.init_ext, self.intrinsic = init_ext, intrinsic
         self.w2c = torch.linalg.inv(init_ext.reshape(4, 4)).contiguous()              # constant; linalg.inv cannot be graph-captured
         self.target_images = target_images

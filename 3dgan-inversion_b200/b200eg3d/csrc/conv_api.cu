@@ -93,7 +93,7 @@ B200_API int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int 
 }
 
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 200; }
+B200_API int b200_version() { return 201; }
 
 // Programmatic dependent launch on (1) / off (0) for subsequent launches; returns the previous setting.  Profiling aid: with PDL a
 // traced kernel duration includes the time it waits for its predecessor.

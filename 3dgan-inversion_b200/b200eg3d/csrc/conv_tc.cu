@@ -658,10 +658,10 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
     return launch_pix<true>(p, n, st);
 }
 
-// wgrad on bf16 operands: dwmod[n][taps][cout][cin] (fp32, overwritten) = sum over pixels of dy (x) x.
+// wgrad on bf16 operands: dwmod[n][taps][cout][cin] (fp32; overwritten, or added to when accumulate != 0) = sum over pixels of dy (x) x.
 // x_* [n][h][w][cin], dy_* [n][h][w][cout] (up == 2: the (2h+1)x(2w+1) transposed-conv grid).
 B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod, int n,
-                                int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+                                int h, int w, int cin, int cout, int ksize, int up, int npass, int accumulate, void* stream) {
     B200_REQUIRE(b200_conv_tc_supported(2, h, w, cin, cout, ksize, up), "conv_wgrad_tc: unsupported shape");
     B200_REQUIRE(npass == 1 || (npass == 3 && x_lo && dy_lo), "conv_wgrad_tc: npass must be 1, or 3 with lo operands");
     cudaStream_t st = (cudaStream_t)stream;
@@ -693,7 +693,7 @@ B200_API int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* 
     if (ksplit > p.ntiles) ksplit = p.ntiles;
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
-    B200_CUDA(cudaMemsetAsync(dwmod, 0, sizeof(float) * (size_t)n * taps * cout * cin, st));
+    if (!accumulate) B200_CUDA(cudaMemsetAsync(dwmod, 0, sizeof(float) * (size_t)n * taps * cout * cin, st));
     B200_FUNC_ATTR_ONCE(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     dim3 grid(mt, nt, n * (taps / p.tg) * ksplit);
     B200_CUDA(launch_pdl(conv_tc_wgrad_kernel, grid, dim3(192), SMEM_BYTES, st, p));

@@ -39,6 +39,9 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           'overlap': os.environ.get('B200EG3D_OVERLAP', '1') != '0',
           # walk 8x16-pixel ray patches front to back in the tri-plane kernels instead of ray after ray (measured slower: see DESIGN.md)
           'ray_patch_order': os.environ.get('B200EG3D_RAY_PATCH_ORDER', '0') != '0',
+          # weight-gradient GEMMs on their own stream (they only feed the bank's backward): their split-K reduction tails and launch
+          # latencies overlap the dgrad chain; d wmod of all layers is one pool, zeroed once per step off the critical path
+          'wgrad_stream': os.environ.get('B200EG3D_WGRAD_STREAM', '1') != '0',
           'ranges': os.environ.get('B200EG3D_RANGES', '0') != '0'}
 
 
@@ -104,7 +107,7 @@ def _conv_wgrad(x, dy, dwmod, n, h, w, cin, cout, k, up):
         npass = CONFIG['wgrad_passes']
         xh, xl = _split(x, npass == 3)
         dh, dl = _split(dy, npass == 3)
-        call('b200_conv_wgrad_tc', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(dwmod), n, h, w, cin, cout, k, up, npass, stream())
+        call('b200_conv_wgrad_tc', ptr(xh), ptr(xl), ptr(dh), ptr(dl), ptr(dwmod), n, h, w, cin, cout, k, up, npass, 0, stream())
     else:
         call('b200_conv_wgrad', ptr(x), ptr(dy), ptr(dwmod), n, h, w, cin, cout, k, up, stream())
 
@@ -309,6 +312,9 @@ class WeightBank:
         self.zpool = None          # one zero-filled buffer for the small backward accumulators (d bias, d noise_strength) of all layers
         self.zoff = []
         self.side = None           # second stream some layers ran on (CONFIG['overlap']); the bank's backward joins it
+        self.dwpool = None         # d wmod of every tensor-core layer in one buffer, zeroed once per step (the wgrad kernels accumulate)
+        self.dwoff, self.dwtotal, self.dwpool_home = [], 0, None
+        self.wstream = None        # stream the weight-gradient GEMMs run on (CONFIG['wgrad_stream']); the bank's backward joins it
 
     def zeros(self, lidx, cout):
         """(d bias [cout], d strength []) views into the pool: one fill per network and pass instead of two per layer.
@@ -322,6 +328,43 @@ class WeightBank:
             torch.cuda.synchronize()
         o = self.zoff[lidx]
         return self.zpool[o:o + cout], self.zpool[o + cout]
+
+    def dwslice(self, lidx, n):
+        """Zero-initialised d wmod [n, taps, cout, cin] of layer lidx inside the pool, or None when the layer is not pooled."""
+        if self.dwoff[lidx] < 0:
+            return None
+        if self.dwpool is None:
+            # first weight gradient of this backward pass: one fill for all layers, on the stream the wgrad kernels run on
+            cur = torch.cuda.current_stream()
+            self.dwpool = torch.empty([self.dwtotal], device=self.styles[0].device, dtype=torch.float32)
+            if CONFIG['wgrad_stream']:
+                self.wstream = wgrad_stream(self.dwpool.device)
+                self.wstream.wait_stream(cur)           # the block may still be in use by earlier work of the allocating stream
+                with torch.cuda.stream(self.wstream):
+                    self.dwpool.zero_()
+                self.dwpool.record_stream(self.wstream)
+            else:
+                self.dwpool.zero_()
+            self.dwpool_home = cur
+        sp = self.specs[lidx]
+        o = self.dwoff[lidx]
+        return self.dwpool[o:o + n * sp.taps * sp.cout * sp.cin].view(n, sp.taps, sp.cout, sp.cin)
+
+    def run_wgrad(self, tensors, fn):
+        """Run fn() (one wgrad launch reading `tensors`) on the weight-gradient stream, after the work queued on the current one."""
+        ws = self.wstream
+        if ws is None:
+            cur = torch.cuda.current_stream()
+            if self.dwpool_home is not None and cur != self.dwpool_home:
+                cur.wait_stream(self.dwpool_home)       # the pool was zeroed on the stream of the first layer backward
+            fn()
+            return
+        ws.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ws):
+            fn()
+        for t in tensors:
+            if t is not None:
+                t.record_stream(ws)
 
 
 def _bank_array(bank, n, dev, bwd=None):
@@ -369,6 +412,12 @@ class _Bank(torch.autograd.Function):
         ctx.bank = bank
         ctx.save_for_backward(ws)
         bank.need_wgrad = any(ctx.needs_input_grad)
+        bank.dwpool, bank.wstream = None, None
+        bank.dwoff, tot = [], 0
+        for sp in bank.specs:                       # layout of the d wmod pool (allocated and zeroed by the first wgrad of the backward)
+            bank.dwoff.append(tot if sp.tc_b else -1)
+            tot += n * sp.taps * sp.cout * sp.cin if sp.tc_b else 0
+        bank.dwtotal = tot
         return torch.zeros([1], device=dev, dtype=torch.float32)
 
     @staticmethod
@@ -382,6 +431,12 @@ class _Bank(torch.autograd.Function):
         specs = bank.specs
         if bank.side is not None:                   # d wmod of the side-stream layers carries no autograd edge: join explicitly
             torch.cuda.current_stream().wait_stream(bank.side)
+        if bank.wstream is not None:
+            torch.cuda.current_stream().wait_stream(bank.wstream)
+        if bank.dwpool is not None:
+            if bank.wstream is None and bank.dwpool_home != torch.cuda.current_stream():
+                torch.cuda.current_stream().wait_stream(bank.dwpool_home)      # filled on the stream of the first layer backward
+            bank.dwpool.record_stream(torch.cuda.current_stream())
         d_ws = torch.zeros_like(ws) if need[0] else None
         total_cin = sum(sp.cin for sp in specs)
         ds_all = torch.zeros([total_cin * n], device=dev, dtype=torch.float32)
@@ -403,20 +458,31 @@ class _Bank(torch.autograd.Function):
         call('b200_bank_weights_bwd', ctypes.addressof(arr), len(specs), n, stream())
         call('b200_bank_styles_bwd', ctypes.addressof(arr), len(specs), ptr(ws), ptr(d_ws), n, num_ws, w_dim, stream())
         bank.dwmod = [None] * len(specs)
+        bank.dwpool = None
         bank.zpool = None          # its slices now belong to autograd (possibly as param.grad): never accumulate into them again
         bank.token = None          # token -> grad_fn -> ctx.bank -> bank was a reference cycle keeping the per-step weight tensors alive
         return (d_ws, None, *grads)
 
 
 _SIDE = {}
+_WGRAD = {}
+
+
+def _device_stream(table, device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in table:
+        table[key] = torch.cuda.Stream(device=key)
+    return table[key]
 
 
 def side_stream(device):
     """The per-device second stream of CONFIG['overlap'] (created on first use)."""
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=key)
-    return _SIDE[key]
+    return _device_stream(_SIDE, device)
+
+
+def wgrad_stream(device):
+    """The per-device stream of CONFIG['wgrad_stream'] (created on first use)."""
+    return _device_stream(_WGRAD, device)
 
 
 def make_bank(ws, specs):
@@ -584,8 +650,13 @@ class _ModConvLayer(torch.autograd.Function):
             if need_x:
                 call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cout, k, up, dp, stream())
             if need_w:
-                dwmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
-                call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cout, k, up, wp, stream())
+                dwmod = bank.dwslice(lidx, n) if bank is not None else None
+                if dwmod is not None:
+                    bank.run_wgrad((xs, xs_lo, dy_hi, dy_lo), lambda: call(
+                        'b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cout, k, up, wp, 1, stream()))
+                else:
+                    dwmod = torch.empty([n, taps, cout, cin], device=dev, dtype=torch.float32)
+                    call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cout, k, up, wp, 0, stream())
         else:
             dy = torch.empty_like(dzc)
             call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr), ptr(dnoise),
@@ -692,7 +763,10 @@ class _ToRGB(torch.autograd.Function):
         dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
         dW = ds = None
         if need_w:
-            dwmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
+            dwmod = bank.dwslice(lidx, n) if (bank is not None and tc_b) else None
+            pooled = dwmod is not None
+            if not pooled:
+                dwmod = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.float32)
         # gradient of bias + clamp from the saved clamped output (bias_act.cu:143-145), d bias reduced in the same pass
         if tc_b:
             dp, wp = CONFIG['dgrad_passes'], CONFIG['wgrad_passes']
@@ -702,8 +776,11 @@ class _ToRGB(torch.autograd.Function):
                  n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
                 call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cimg, 1, 1, dp, stream())
-            if need_w:
-                call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, stream())
+            if need_w and pooled:
+                bank.run_wgrad((xs, xs_lo, dy_hi, dy_lo), lambda: call(
+                    'b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, 1, stream()))
+            elif need_w:
+                call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, 0, stream())
         else:
             dy = torch.empty_like(dimg)
             call('b200_layer_act_bwd', ptr(dimg), ptr(y), ptr(dy), None, None, ptr(dbias), None, None, 0, None, None,

@@ -98,8 +98,10 @@ int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void* w_hi, c
                          int cout, int ksize, int npass, float alpha, float act_gain, float clamp, void* stream);
 int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx,
                        int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+/* accumulate == 0: dwmod is overwritten (zeroed inside the call, then reduced into); accumulate != 0: the partial sums are ADDED to
+ * dwmod, which the caller zeroed earlier (one fill for every layer of a network, off the critical path). */
 int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod,
-                       int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+                       int n, int h, int w, int cin, int cout, int ksize, int up, int npass, int accumulate, void* stream);
 
 /* ---- bias / activation (torch_utils/ops/bias_act.cpp:36 bias_act(x,b,xref,yref,dy,grad,dim,act,alpha,gain,clamp)) ---- */
 
@@ -200,6 +202,15 @@ int b200_pti_loss_bwd(const float* image, const long* image_strides, const float
                       const float* real, int n, int C, int H, int W, int R, float l2_lambda, float tv_lambda, const float* dloss,
                       float* d_image, const long* d_image_strides, float* d_raw, const long* d_raw_strides, float* d_depth,
                       void* stream);
+
+/* ---- optimiser (training/coaches/base_coach.py:96-99, training/projectors/w_projector.py:134-140: torch.optim.Adam) ---------- */
+/* One Adam update (torch.optim.Adam rule, amsgrad off) of `count` tensors in one launch (one per 320 tensors).  tensors: HOST array
+ * of records of device pointers; records with n == 0 are skipped.  lr_dev: device scalar learning rate, or NULL to use `lr`.
+ * step: device float = updates applied so far (0 at the start), advanced by one per call on the device, so a captured CUDA graph
+ * replays the same launch every step; ticket: device uint32, zero-initialised, owned by the optimiser. */
+typedef struct { float* p; const float* g; float* m; float* v; long n; } B200AdamTensor;
+int b200_adam_step(const B200AdamTensor* tensors, int count, const float* lr_dev, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, float* step, unsigned* ticket, void* stream);
 
 /* ---- stage-1 (w-projection) caller-side kernels ------------------------------------------------- */
 /* training/warping_loss.py:18-43 fused: rays of the predicted camera `ext` (ray_sampler.py:24-73), surface point o + d*depth

@@ -41,4 +41,4 @@ for (name, cin, cout, res) in [('sr.block1.conv1  64->64  @512^2', 64, 64, 512),
     fl = 2.0 * h * w * 9 * cin * cout
     timeit(lambda: call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, 1, 3, stream()), name + ' fwd x3', fl)
     timeit(lambda: call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, 1, 3, stream()), name + ' dgrad x3', fl)
-    timeit(lambda: call('b200_conv_wgrad_tc', ptr(xh), None, ptr(dh), None, ptr(dw), n, h, w, cin, cout, k, 1, 1, stream()), name + ' wgrad x1', fl)
+    timeit(lambda: call('b200_conv_wgrad_tc', ptr(xh), None, ptr(dh), None, ptr(dw), n, h, w, cin, cout, k, 1, 1, 0, stream()), name + ' wgrad x1', fl)

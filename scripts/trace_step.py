@@ -11,7 +11,8 @@ from b200eg3d import losses
 dev = torch.device('cuda', 0)
 G, ws, c, t512, _ = bench.make_problem(0, dev)
 params = [p for n, p in G.named_parameters() if '.mapping.' not in n]
-opt = torch.optim.Adam(params, lr=3e-4, fused=True, capturable=True)
+from b200eg3d.optim import Adam
+opt = Adam(params, lr=3e-4)
 res = [t.to(dev) for t in (ws, c, t512)]
 
 def step(ws, c, t512):

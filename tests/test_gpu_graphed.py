@@ -1,5 +1,5 @@
 """The execution mode bench.py times -- the whole optimisation step replayed as a CUDA graph (graphs.GraphedStep: two stream
-branches, programmatic dependent launch, capturable fused Adam) -- against the plain eager loop from the same state:
+branches, programmatic dependent launch, the one-launch Adam of b200eg3d.optim) -- against the plain eager loop from the same state:
 loss trajectory and EVERY parameter after three steps.  A stale static input, a missed cross-stream edge or a gradient that
 is accumulated instead of overwritten on replay would show up here.
 

@@ -438,3 +438,64 @@ def test_conv_fwd_tc_fused_epilogue_matches_two_kernel_path(b2, noise_mode):
          ptr(strength) if noise is not None else None, nbs, n, h, w, cin, cout, 3, 3, 0.2, math.sqrt(2), 1.5, stream())
     assert float(z0.abs().max()) == 1.5                                          # the clamp is active
     assert maxdiff(z1, z0) < 1e-6 and maxdiff(h1.float(), h0.float()) < 1e-2 and maxdiff((h1.float() + l1.float()), z0) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- optimiser
+
+@pytest.mark.parametrize('lr_on_device', [False, True])
+def test_adam_matches_torch_adam(b2, lr_on_device):
+    """b200eg3d.optim.Adam (one b200_adam_step launch for the whole list) against torch.optim.Adam: ragged sizes (vector path,
+    scalar tail, unaligned views), a parameter without gradient, five steps with changing gradients."""
+    from b200eg3d.optim import Adam
+    g = gen(5)
+    base = torch.randn(70001, generator=g).cuda()
+    shapes = [(512, 512, 3, 3), (3,), (17, 5), (1,), (8192,), (8193,)]
+    pa = [torch.randn(*s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    pa.append(base[1:40000].detach().clone().requires_grad_(True))
+    pa.append(torch.randn(64, generator=g).cuda().requires_grad_(True))            # never receives a gradient
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    lr = 3e-3
+    oa = Adam(pa, lr=torch.tensor(lr, device='cuda') if lr_on_device else lr, betas=(0.9, 0.999), eps=1e-8)
+    ob = torch.optim.Adam(pb, lr=lr, betas=(0.9, 0.999), eps=1e-8)
+    for it in range(5):
+        for a, b in zip(pa[:-1], pb[:-1]):
+            gr = torch.randn(a.shape, generator=g).cuda() * (10.0 ** (it - 2))
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    assert float(oa.step_count) == 5.0
+    for a, b in zip(pa, pb):
+        assert relerr(a, b) < 2e-6, (a.shape, relerr(a, b))
+    assert maxdiff(pa[-1], pb[-1]) == 0.0
+    sd = oa.state_dict()
+    oa.load_state_dict(sd)
+    assert float(oa.state[pa[0]]['step']) == 5.0
+
+
+def test_wgrad_pool_and_stream_match_serial_path(b2, monkeypatch, golden_dir):
+    """The weight gradients of a synthesis network are accumulated into one zero-filled pool by wgrad kernels running on their own
+    stream (ops.CONFIG['wgrad_stream']); with the stream off the same kernels run in line.  Both must give the same gradients."""
+    import synth_params as sp
+    from golden_util import load_case
+    case = load_case(golden_dir, 'tiny_r64_s16')
+    G = b2.TriPlaneGenerator(rendering_kwargs=case.rk, **case.gk).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), case.param_seed)
+    G = G.cuda().float()
+    G.neural_rendering_resolution = case.R
+    G.renderer.fixed_noise = (case.u_strat.cuda(), case.u_imp.cuda())
+    ws, c = case.ws.cuda(), case.c.cuda()
+    named = [(n, p) for n, p in G.named_parameters() if '.mapping.' not in n]
+    grads = []
+    for on in (True, False, True):
+        monkeypatch.setitem(b2.ops.CONFIG, 'wgrad_stream', on)
+        for _, p in named:
+            p.grad = None
+        out = G.synthesis(ws, c, noise_mode='const')
+        (out['image'].square().mean() + out['image_raw'].square().mean()).backward()
+        torch.cuda.synchronize()
+        grads.append([p.grad.clone() if p.grad is not None else None for _, p in named])
+    assert sum(g is not None and float(g.abs().max()) > 0 for g in grads[0]) > 20
+    for (n, _), a, b, a2 in zip(named, *grads):
+        if a is None:
+            assert b is None and a2 is None, n
+            continue
+        assert relerr(a, b) < 1e-4 and relerr(a2, b) < 1e-4, (n, relerr(a, b), relerr(a2, b))
