@@ -91,6 +91,8 @@ def load():
     lib.b200_version.argtypes = []
     lib.b200_set_pdl.restype = ctypes.c_int
     lib.b200_set_pdl.argtypes = [_I]
+    lib.b200_set_conv_pair.restype = ctypes.c_int
+    lib.b200_set_conv_pair.argtypes = [_I]
     lib.b200_set_mlp_passes.restype = ctypes.c_int
     lib.b200_set_mlp_passes.argtypes = [_I]
     lib.b200_set_triplane_impl.restype = ctypes.c_int

@@ -30,7 +30,7 @@ constexpr int SMEM_BYTES = RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 // One "class" = one iteration grid with its tap list.  Plain convolutions have a single class; the stride-2 transposed
 // convolution has four (output parities), merged into ONE launch so that their CTAs fill the GPU together.
 struct TcClass {
-    int th, tw, tiles_x, Hi, Wi, ntaps, ooy, oox;
+    int th, tw, tiles_x, ntiles, Hi, Wi, ntaps, ooy, oox;
     int dy[9], dx[9], wt[9];
 };
 
@@ -38,7 +38,8 @@ struct TcPixParams {
     CUtensorMap tmA[4][2];       // per class: hi, lo : 4-D {C, W, H, N}  (the box depends on the class's tile shape)
     CUtensorMap tmB[2];          // hi, lo : 2-D {inner, rows}
     TcClass c[4];
-    int cta_start[5];            // prefix sums of (tiles * ksplit) per class
+    int cta_start[5];            // prefix sums of (tiles * ksplit) per class; CTA pairs (cg == 2): tiles counted in pairs
+    int cg;                      // 1: one CTA per 128-pixel tile; 2: a CTA pair issues M = 256 MMAs over two tiles and shares B
     int ncls;
     int kchunks, npass;
     int s;                       // source pixel = iteration pixel * s + (dy, dx)
@@ -71,7 +72,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // Persistent: one CTA per SM walks the work list (pixel tile x k-slice x N tile x sample) with a stride of gridDim.x.  The
 // shared-memory ring keeps running across work items (the producer prefetches the next tile while the MMAs of the current
 // one drain) and the accumulator is double-buffered in TMEM, so the epilogue of item i overlaps the main loop of item i+1.
-template <bool B_MN>
+//
+// CG == 2 (launched as clusters of two CTAs): the pair walks the list together, CTA rank r takes pixel tile 2i + r of pair-tile i
+// and loads rows [r * BN/2, (r+1) * BN/2) of the B tile; the leader's single thread issues cta_group::2 MMAs (M = 256) that read
+// both CTAs' shared memory and write both CTAs' tensor memory.  Per CTA that is A + B/2 per k-block instead of A + B from L2
+// (the L2 -> SM fabric, ~43 B/clk/SM, is what bounds the single-CTA kernel: 64 KB per 768 tensor-clocks), and B is read from
+// shared memory once per pair.
+template <bool B_MN, int CG>
 __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_constant__ TcPixParams p) {
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
@@ -88,21 +95,24 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nst = p.nstages;
-    const uint32_t b_tile = (uint32_t)p.BN * TILE_K * 2;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int walker = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, nwalkers = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int bn_cta = p.BN / CG;                                      // B rows (N) this CTA holds
+    const uint32_t b_tile = (uint32_t)bn_cta * TILE_K * 2;
     const uint32_t a_lo_off = A_BYTES, b_hi_off = p.npass == 3 ? 2 * A_BYTES : A_BYTES, b_lo_off = b_hi_off + b_tile;
-    const uint32_t tcols = 2 * p.BN <= 128 ? 128u : 256u;
+    const uint32_t tcols = 2 * p.BN <= 128 ? 128u : (2 * p.BN <= 256 ? 256u : 512u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nst; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4 * CG); }
         fence_barrier_init();
         for (int k = 0; k < p.ncls; ++k) { tma_prefetch_desc(&p.tmA[k][0]); if (p.npass == 3) tma_prefetch_desc(&p.tmA[k][1]); }
         tma_prefetch_desc(&p.tmB[0]);
         if (p.npass == 3) tma_prefetch_desc(&p.tmB[1]);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, tcols);
+    if (warp == 1) { if (CG == 2) tmem_alloc_cg2(tmem_slot, tcols); else tmem_alloc(tmem_slot, tcols); }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // pair: the peer's barriers must exist before anything signals them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
     pdl_wait();                       // barriers, descriptors and TMEM are set up while the previous kernel drains
@@ -118,8 +128,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         o.cls = cls;
         const TcClass& kc = p.c[cls];
         const int local = lx - p.cta_start[cls];
-        const int tile = local / p.ksplit, ksi = local % p.ksplit;
+        const int tile = (local / p.ksplit) * CG + (int)rank, ksi = local % p.ksplit;
         o.x0 = (tile % kc.tiles_x) * kc.tw; o.y0 = (tile / kc.tiles_x) * kc.th;
+        if (CG == 2 && tile >= kc.ntiles) o.y0 = 1 << 20;         // odd tile count: the pair's second CTA multiplies zero-filled rows, stores nothing
         const int nk_all = kc.ntaps * p.kchunks;
         const int per = (nk_all + p.ksplit - 1) / p.ksplit;
         o.it0 = ksi * per;
@@ -130,62 +141,101 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         if (lane == 0) {
             const int nh = p.npass == 3 ? 2 : 1;
             const uint32_t bytes = (uint32_t)(A_BYTES + b_tile) * nh;
-            int g = 0;                                             // running k-block counter: ring position and phase
-            for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+            int g = 0, s = 0, ph = 0;                              // k-blocks issued; ring position and phase of the next one
+            for (int w = walker; w < p.nwork; w += nwalkers) {
                 Item o; decode(w, o);
                 const TcClass& kc = p.c[o.cls];
+                int t = o.it0 / p.kchunks, kc0 = o.it0 % p.kchunks;   // tap and channel chunk of the next k-block
                 for (int it = 0; it < o.nk; ++it, ++g) {
-                    const int s = g % nst, ph = (g / nst) & 1;
                     mbar_wait(empty(s), ph ^ 1);
-                    mbar_arrive_expect_tx(full(s), bytes);
-                    const int t = (o.it0 + it) / p.kchunks, c0 = ((o.it0 + it) % p.kchunks) * TILE_K;
+                    // pair: both CTAs' loads count on the LEADER's full barrier, which the leader arms with the bytes of both
+#ifdef B200_DBG_NO_TMA
+                    if (rank == 0) mbar_arrive(full(s));
+                    if (++s == nst) { s = 0; ph ^= 1; }
+                    if (++kc0 == p.kchunks) { kc0 = 0; ++t; }
+                    continue;
+#endif
+                    if (rank == 0) mbar_arrive_expect_tx(full(s), bytes * CG);
+                    const uint32_t fbar = CG == 2 ? mapa_u32(full(s), 0) : full(s);
+                    const int c0 = kc0 * TILE_K;
                     const uint32_t st = base + s * p.stage_bytes;
                     const int ax = o.x0 * p.s + kc.dx[t], ay = o.y0 * p.s + kc.dy[t];
+                    const int nb = o.n0 + (int)rank * bn_cta;          // first B row (N index) of this CTA
                     for (int h = 0; h < nh; ++h) {
-                        tma_load_4d(st + h * a_lo_off, &p.tmA[o.cls][h], full(s), c0, ax, ay, o.b);
                         const uint32_t bdst = st + (h ? b_lo_off : b_hi_off);
-                        if (!B_MN) {
-                            tma_load_2d(bdst, &p.tmB[h], full(s), c0, (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + o.n0);
+                        if (CG == 2) {
+                            tma_load_4d_cg2(st + h * a_lo_off, &p.tmA[o.cls][h], fbar, c0, ax, ay, o.b);
+                            if (!B_MN) {
+                                tma_load_2d_cg2(bdst, &p.tmB[h], fbar, c0, (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + nb);
+                            } else {
+                                const int krow = (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + c0;
+                                for (int j = 0; j < bn_cta / 64; ++j) tma_load_2d_cg2(bdst + j * (TILE_K * 128), &p.tmB[h], fbar, nb + j * 64, krow);
+                            }
                         } else {
-                            const int krow = (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + c0;
-                            for (int j = 0; j < p.BN / 64; ++j) tma_load_2d(bdst + j * (TILE_K * 128), &p.tmB[h], full(s), o.n0 + j * 64, krow);
+                            tma_load_4d(st + h * a_lo_off, &p.tmA[o.cls][h], fbar, c0, ax, ay, o.b);
+                            if (!B_MN) {
+                                tma_load_2d(bdst, &p.tmB[h], fbar, c0, (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + nb);
+                            } else {
+                                const int krow = (o.b * p.b_taps + kc.wt[t]) * p.b_rows_per_tap + c0;
+                                for (int j = 0; j < bn_cta / 64; ++j) tma_load_2d(bdst + j * (TILE_K * 128), &p.tmB[h], fbar, nb + j * 64, krow);
+                            }
                         }
                     }
+                    if (++s == nst) { s = 0; ph ^= 1; }
+                    if (++kc0 == p.kchunks) { kc0 = 0; ++t; }
+                }
+            }
+            if (CG == 2) {
+                // pair: the leader's multicast commits still arrive on this CTA's empty barriers after the last load was issued;
+                // wait for the release of every stage still in use so that no arrival targets a CTA that has already retired
+                for (int j = 0; j < nst && j < g; ++j) {
+                    const int gg = g - 1 - j;
+                    mbar_wait(empty(gg % nst), (gg / nst) & 1);
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16(TILE_M, p.BN, 0, B_MN ? 1 : 0);
-            int g = 0, li = 0;
-            for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+        if (rank == 0) {
+            // The whole warp runs this loop converged (descriptor arithmetic stays warp-uniform); lane 0 issues.  Descriptors are
+            // built once: per k-block only the 16-byte-unit start addresses move.
+            const uint32_t idesc = instr_desc_bf16(TILE_M * CG, p.BN, 0, B_MN ? 1 : 0);
+            const uint32_t dhi = smem_desc_hi(1024);
+            const uint32_t a_hi0 = smem_desc_lo(base, 0), a_lo0 = smem_desc_lo(base + a_lo_off, 0);
+            const uint32_t b_hi0 = smem_desc_lo(base + b_hi_off, B_MN ? TILE_K * 128 : 0), b_lo0 = smem_desc_lo(base + b_lo_off, B_MN ? TILE_K * 128 : 0);
+            constexpr uint32_t KA = 32 >> 4, KB = (B_MN ? 2048 : 32) >> 4;          // k16 step of the two operands, in 16-byte units
+            const uint32_t stage16 = (uint32_t)p.stage_bytes >> 4;
+            const bool three = p.npass == 3;
+            int s = 0, ph = 0, li = 0;
+            for (int w = walker; w < p.nwork; w += nwalkers) {
                 Item o; decode(w, o);
                 if (o.nk == 0) continue;
                 const int acc = li & 1;
                 mbar_wait(tempty(acc), ((li >> 1) & 1) ^ 1);       // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)(acc * p.BN);
-                for (int it = 0; it < o.nk; ++it, ++g) {
-                    const int s = g % nst, ph = (g / nst) & 1;
+                for (int it = 0; it < o.nk; ++it) {
                     mbar_wait(full(s), ph);
                     tc_fence_after();
-                    const uint32_t st = base + s * p.stage_bytes;
-                    const uint32_t a_hi = st, a_lo = st + a_lo_off, b_hi = st + b_hi_off, b_lo = st + b_lo_off;
+                    const uint32_t so = (uint32_t)s * stage16;
+                    if (elect_one()) {
+#ifndef B200_DBG_NO_MMA
 #pragma unroll
-                    for (int k = 0; k < TILE_K / 16; ++k) {
-                        const uint32_t ao = k * 32, bo = B_MN ? k * 2048 : k * 32;
-                        const uint32_t blbo = B_MN ? TILE_K * 128 : 0;
-                        const uint64_t dah = smem_desc(a_hi + ao, 0, 1024), dbh = smem_desc(b_hi + bo, blbo, 1024);
-                        umma_bf16(d, dah, dbh, idesc, (it | k) != 0);
-                        if (p.npass == 3) {
-                            const uint64_t dal = smem_desc(a_lo + ao, 0, 1024), dbl = smem_desc(b_lo + bo, blbo, 1024);
-                            umma_bf16(d, dah, dbl, idesc, 1);
-                            umma_bf16(d, dal, dbh, idesc, 1);
+                        for (int k = 0; k < TILE_K / 16; ++k) {
+                            const uint64_t ah = desc_pack(a_hi0 + so + k * KA, dhi), bh = desc_pack(b_hi0 + so + k * KB, dhi);
+                            if (CG == 2) umma_bf16_cg2(d, ah, bh, idesc, (it | k) != 0); else umma_bf16(d, ah, bh, idesc, (it | k) != 0);
+                            if (three) {
+                                const uint64_t al = desc_pack(a_lo0 + so + k * KA, dhi), bl = desc_pack(b_lo0 + so + k * KB, dhi);
+                                if (CG == 2) { umma_bf16_cg2(d, ah, bl, idesc, 1); umma_bf16_cg2(d, al, bh, idesc, 1); }
+                                else { umma_bf16(d, ah, bl, idesc, 1); umma_bf16(d, al, bh, idesc, 1); }
+                            }
                         }
+#endif
+                        if (CG == 2) umma_commit_cg2(empty(s)); else umma_commit(empty(s));       // pair: frees the stage in both CTAs
+                        if (it == o.nk - 1) { if (CG == 2) umma_commit_cg2(tfull(acc)); else umma_commit(tfull(acc)); }
                     }
-                    umma_commit(empty(s));
+                    __syncwarp();
+                    if (++s == nst) { s = 0; ph ^= 1; }
                 }
-                umma_commit(tfull(acc));
                 ++li;
             }
         }
@@ -193,7 +243,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const bool vec = (p.N & 3) == 0;
         int li = 0;
-        for (int w = blockIdx.x; w < p.nwork; w += gridDim.x) {
+        for (int w = walker; w < p.nwork; w += nwalkers) {
             Item o; decode(w, o);
             if (o.nk == 0) continue;
             const TcClass& kc = p.c[o.cls];
@@ -207,11 +257,14 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
             float* crow = p.C + (long)o.b * p.c_bs + opix * p.ldc + o.n0;
             for (int c0 = 0; c0 < p.BN; c0 += 32) {
                 float v[32];
+#ifdef B200_DBG_NO_EPI
+                if (c0 + 32 < p.BN) continue;
+#endif
                 tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c0), v);
                 if (c0 + 32 >= p.BN) {                 // last read of this accumulator: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty(acc));
+                    if (lane == 0) { if (CG == 2) mbar_arrive_cluster(mapa_u32(tempty(acc), 0)); else mbar_arrive(tempty(acc)); }
                 }
                 if (valid && p.act) {                  // fused layer epilogue (launch code guarantees ksplit == 1, N % 32 == 0, plain output grid)
                     const float nz = p.noise ? __ldg(p.noise + (long)o.b * p.noise_bs + (long)iy * kc.Wi + ix) * __ldg(p.strength) : 0.f;
@@ -244,6 +297,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
                         }
                     }
                 } else if (valid) {
+#ifdef B200_DBG_NO_STORE
+                    if (v[0] != 12345.678f) continue;
+#endif
                     if (vec && o.n0 + c0 + 32 <= p.N) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -261,8 +317,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, tcols);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();       // pair: nobody leaves while the peer may still touch its memory
+    if (warp == 1) { if (CG == 2) tmem_dealloc_cg2(tmem, tcols); else tmem_dealloc(tmem, tcols); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -355,31 +411,37 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
-                const uint32_t idesc = instr_desc_bf16(TILE_M, p.BN, 1, 1);
-                for (int it = 0; it < nk; ++it) {
-                    const int s = it % STAGES, ph = (it / STAGES) & 1;
-                    mbar_wait(full(s), ph);
-                    tc_fence_after();
-                    const uint32_t st = base + s * STAGE_BYTES;
+            // converged warp, one elected lane issues (see the pixel-GEMM kernel): descriptor halves built once per tile
+            const uint32_t idesc = instr_desc_bf16(TILE_M, p.BN, 1, 1);
+            const uint32_t dhi = smem_desc_hi(1024);
+            constexpr uint32_t LBO = TILE_K * 128, KS = 2048 >> 4;             // 64-element MN blocks 8 KB apart; k16 step = 16 rows of 128 B
+            const bool three = p.npass == 3;
+            int s = 0, ph = 0;
+            for (int it = 0; it < nk; ++it) {
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t st = base + s * STAGE_BYTES;
+                if (elect_one()) {
                     for (int j = 0; j < p.tg; ++j) {
-                        const uint32_t a_hi = a_addr(st, j, 0), b_hi = b_addr(st, j, 0);
+                        const uint32_t ah0 = smem_desc_lo(a_addr(st, j, 0), LBO), bh0 = smem_desc_lo(b_addr(st, j, 0), LBO);
                         const uint32_t d = tmem + (uint32_t)(j * p.BN);
 #pragma unroll
                         for (int k = 0; k < TILE_K / 16; ++k) {
-                            const uint32_t o = k * 2048, lbo = TILE_K * 128;
-                            const uint64_t dah = smem_desc(a_hi + o, lbo, 1024), dbh = smem_desc(b_hi + o, lbo, 1024);
+                            const uint64_t dah = desc_pack(ah0 + k * KS, dhi), dbh = desc_pack(bh0 + k * KS, dhi);
                             umma_bf16(d, dah, dbh, idesc, (it | k) != 0);
-                            if (p.npass == 3) {
-                                const uint64_t dal = smem_desc(a_addr(st, j, 1) + o, lbo, 1024), dbl = smem_desc(b_addr(st, j, 1) + o, lbo, 1024);
+                            if (three) {
+                                const uint64_t dal = desc_pack(smem_desc_lo(a_addr(st, j, 1), LBO) + k * KS, dhi);
+                                const uint64_t dbl = desc_pack(smem_desc_lo(b_addr(st, j, 1), LBO) + k * KS, dhi);
                                 umma_bf16(d, dah, dbl, idesc, 1);
                                 umma_bf16(d, dal, dbh, idesc, 1);
                             }
                         }
                     }
                     umma_commit(empty(s));
+                    if (it == nk - 1) umma_commit(accum_bar);
                 }
-                umma_commit(accum_bar);
+                __syncwarp();
+                if (++s == STAGES) { s = 0; ph ^= 1; }
             }
         } else {
             const int q = warp & 3;
@@ -494,21 +556,74 @@ int pick_bn(int n) {           // N tile of the K-major-B kernels (a multiple of
     return 128;
 }
 
+// CTA-pair mode (cta_group::2) switch: -1 = take B200EG3D_CONV_PAIR from the environment on first use (default on)
+int g_conv_pair = -1;
+bool conv_pair_enabled() {
+    if (g_conv_pair < 0) { const char* e = getenv("B200EG3D_CONV_PAIR"); g_conv_pair = (e && e[0] == '0') ? 0 : 1; }
+    return g_conv_pair == 1;
+}
+
+// how many CTA pairs of this kernel the device runs at once (one CTA per SM: 74 on a full B200); 0 if clusters cannot be placed
+template <bool B_MN>
+int max_pairs() {
+    static int cached[B200_MAX_DEVICES] = {};
+    const int dev = b200_current_device();
+    if (!cached[dev]) {
+        if (cudaFuncSetAttribute(conv_tc_pix_kernel<B_MN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+            cudaGetLastError(); cached[dev] = -1; return 0;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 148); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_pix_kernel<B_MN, 2>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        cached[dev] = n > 0 ? n : -1;
+    }
+    return cached[dev] > 0 ? cached[dev] : 0;
+}
+
+// Pair mode pays when the list still fills the machine with half as many walkers: at least 3/4 of the pairs get an item.
+inline bool pair_fills(long pair_items) { return pair_items >= 56; }
+
 template <bool B_MN>
 int launch_pix(TcPixParams& p, int batch, cudaStream_t st) {
-    B200_FUNC_ATTR_ONCE(conv_tc_pix_kernel<B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     p.ntn = (p.N + p.BN - 1) / p.BN;
     p.nwork = p.cta_start[p.ncls] * p.ntn * batch;
-    p.stage_bytes = (A_BYTES + p.BN * TILE_K * 2) * (p.npass == 3 ? 2 : 1);
+    p.stage_bytes = (A_BYTES + (p.BN / p.cg) * TILE_K * 2) * (p.npass == 3 ? 2 : 1);
     p.nstages = RING_BYTES / p.stage_bytes < MAX_ST ? RING_BYTES / p.stage_bytes : MAX_ST;
+    if (p.cg == 2) {
+        B200_FUNC_ATTR_ONCE((conv_tc_pix_kernel<B_MN, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        const int pairs = max_pairs<B_MN>();
+        B200_REQUIRE(pairs > 0, "conv_tc: CTA pairs cannot be scheduled on this device");
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (p.nwork < pairs ? p.nwork : pairs)); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pix_kernel<B_MN, 2>, p));
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
+    B200_FUNC_ATTR_ONCE((conv_tc_pix_kernel<B_MN, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     const int sms = b200_sm_count();
     const int grid = p.nwork < sms ? p.nwork : sms;
-    B200_CUDA(launch_pdl(conv_tc_pix_kernel<B_MN>, dim3(grid), dim3(192), SMEM_BYTES, st, p));
+    B200_CUDA(launch_pdl(conv_tc_pix_kernel<B_MN, 1>, dim3(grid), dim3(192), SMEM_BYTES, st, p));
     B200_CHECK_LAUNCH();
     return 0;
 }
 
 }  // namespace
+
+// CTA-pair (cta_group::2) tiles of the forward / dgrad kernels on (1, default; env B200EG3D_CONV_PAIR=0 disables) or off (0):
+// the single-CTA kernel stays available as the cross-check.  Returns the previous setting.
+B200_API int b200_set_conv_pair(int on) {
+    const int prev = conv_pair_enabled() ? 1 : 0;
+    g_conv_pair = on ? 1 : 0;
+    return prev;
+}
 
 // 1 when the tcgen05 path handles this shape; kind: 0 forward, 1 dgrad, 2 wgrad
 B200_API int b200_conv_tc_supported(int kind, int h, int w, int cin, int cout, int ksize, int up) {
@@ -552,10 +667,8 @@ static int conv_fwd_tc_impl(const void* x_hi, const void* x_lo, const void* w_hi
     const int taps = ksize * ksize;
     TcPixParams p{};
     p.kchunks = (cin + 63) / 64; p.npass = npass; p.s = 1; p.b_rows_per_tap = cout; p.b_taps = taps;
-    p.BN = pick_bn(cout); p.N = cout; p.C = y; p.ldc = cout;
+    p.BN = pick_bn(cout); p.N = cout; p.C = y; p.ldc = cout; p.cg = 1;
     const int ntn = (cout + p.BN - 1) / p.BN;
-    for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
-        if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, p.BN)) return e;
     int tiles[4];
     if (up == 1) {
         p.ncls = 1;
@@ -585,9 +698,19 @@ static int conv_fwd_tc_impl(const void* x_hi, const void* x_lo, const void* w_hi
             }
         p.ksplit = pick_ksplit(total * ntn * n, p.kchunks);      // the (1,1) class has a single tap: at least kchunks k-blocks
     }
+    // CTA pairs for the layers that fill the machine without split-K; 256-wide N tiles when the list stays long enough
+    if (p.ksplit == 1 && conv_pair_enabled() && max_pairs<false>() > 0) {
+        long ptiles = 0;
+        for (int k = 0; k < p.ncls; ++k) ptiles += (tiles[k] + 1) / 2;
+        if (cout >= 256 && pair_fills(ptiles * ((cout + 255) / 256) * n)) { p.cg = 2; p.BN = 256; }
+        else if (pair_fills(ptiles * ntn * n)) p.cg = 2;
+    }
+    for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
+        if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, p.BN / p.cg)) return e;
     p.cta_start[0] = 0;
     for (int k = 0; k < p.ncls; ++k) {
-        p.cta_start[k + 1] = p.cta_start[k] + tiles[k] * p.ksplit;
+        p.c[k].ntiles = tiles[k];
+        p.cta_start[k + 1] = p.cta_start[k] + (p.cg == 2 ? (tiles[k] + 1) / 2 : tiles[k]) * p.ksplit;
         for (int i = 0; i < (npass == 3 ? 2 : 1); ++i)
             if (int e = make_map_nhwc(&p.tmA[k][i], i ? x_lo : x_hi, n, h, w, cin, p.c[k].tw, p.c[k].th, 1)) return e;
     }
@@ -638,7 +761,7 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
     const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
     TcPixParams p{};
     p.kchunks = (cout + 63) / 64; p.npass = npass; p.s = up; p.b_rows_per_tap = cout; p.b_taps = taps;
-    p.BN = cin > 64 ? 128 : 64; p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin;
+    p.BN = cin > 64 ? 128 : 64; p.N = cin; p.C = dx; p.ldc = cin; p.c_bs = (long)h * w * cin; p.cg = 1;
     p.ncls = 1;
     TcClass& c = p.c[0];
     c.Hi = h; c.Wi = w; pick_tile(h, w, c.th, c.tw); c.tiles_x = (w + c.tw - 1) / c.tw;
@@ -652,8 +775,15 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
         if (int e = make_map_2d(&p.tmB[i], i ? w_lo : w_hi, (long)n * taps * cout, cin, 64)) return e;
     }
     const int tiles0 = c.tiles_x * ((h + c.th - 1) / c.th);
+    c.ntiles = tiles0;
     p.ksplit = pick_ksplit(tiles0 * ((cin + p.BN - 1) / p.BN) * n, taps * p.kchunks);
-    p.cta_start[0] = 0; p.cta_start[1] = tiles0 * p.ksplit;
+    // CTA pairs: each CTA holds a 64-multiple of the MN-major B tile's columns, so N tiles of 128 or 256
+    if (p.ksplit == 1 && cin >= 128 && conv_pair_enabled() && max_pairs<true>() > 0) {
+        const long ptiles = (tiles0 + 1) / 2;
+        if (cin >= 256 && pair_fills(ptiles * ((cin + 255) / 256) * n)) { p.cg = 2; p.BN = 256; }
+        else if (pair_fills(ptiles * ((cin + 127) / 128) * n)) { p.cg = 2; p.BN = 128; }
+    }
+    p.cta_start[0] = 0; p.cta_start[1] = (p.cg == 2 ? (tiles0 + 1) / 2 : tiles0) * p.ksplit;
     if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)n * h * w * cin, st));
     return launch_pix<true>(p, n, st);
 }

@@ -100,6 +100,59 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC issue ONE M = 256 MMA; each holds its own 128 rows of A and
+// half of B's N rows in its shared memory, and its own 128 accumulator rows in its tensor memory.  Only the leader (cluster
+// rank 0) issues MMAs; it waits on ITS full barrier, which the TMA loads of both CTAs signal, and releases stages /
+// accumulators in both CTAs with multicast commits.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data lands in THIS CTA, the transaction bytes are counted on `bar`, a shared::cluster address
+// (the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+// executed by the same warp of BOTH CTAs of the pair
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs when all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+
 // UMMA shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100): start address, leading / stride byte offsets.
 //   K-major  tile [rows][64 bf16]: rows are 128 B apart, 8-row groups SBO = 1024 B apart (LBO unused)
 //   MN-major tile [k rows][64 bf16]: 8-row k groups SBO = 1024 B apart, 64-element MN blocks LBO apart
@@ -111,6 +164,29 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+
+// The same descriptor split into its 32-bit halves.  Only the start address changes between MMAs of a pipeline, so the issuing
+// warp keeps the constant high word and adds 16-byte units to the low word (one integer add per operand instead of rebuilding a
+// 64-bit value: the single issuing thread's instruction stream is what bounds the MMA rate of small tiles).
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t smem_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+
+// One lane of a converged warp (elect.sync): the compiler then knows that exactly one thread executes the guarded tcgen05
+// instructions and emits them straight-line on the uniform datapath (a plain `lane == 0` test makes it serialise over lanes).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+    uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d;
 }
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D; majors: 0 = K-major, 1 = MN-major.

@@ -27,6 +27,9 @@ const char* b200_last_error(void);      /* replaces TORCH_CHECK -> RuntimeError 
 int b200_set_pdl(int on);               /* programmatic dependent launch of the conv / epilogue / FIR kernels on (default; env
                                            B200EG3D_PDL=0 disables) or off; returns the previous setting.  Profiling aid. */
 
+int b200_set_conv_pair(int on);         /* CTA-pair (cta_group::2, M = 256) tiles of the tensor-core forward / dgrad convolutions on (default;
+                                           env B200EG3D_CONV_PAIR=0 disables) or off = the single-CTA kernel, kept as the cross-check.
+                                           Returns the previous setting. */
 int b200_set_mlp_passes(int passes);    /* operand passes of the fused decoder MLP forward: 3 = split operands, fp32-equivalent (default;
                                            env B200EG3D_MLP_PASSES=1 selects 1), 1 = single pass ("fast mode", non-parity).
                                            Returns the previous setting. */

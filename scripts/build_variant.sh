@@ -3,8 +3,9 @@
 set -e
 D=3dgan-inversion_b200/b200eg3d
 mkdir -p $D/variants /tmp/b200_variant_$1
-for f in bank conv_tc conv_api conv_simt modconv elementwise triplane raymarch losses projector; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden $2 -c $D/csrc/$f.cu -o /tmp/b200_variant_$1/$f.o &
+for src in $D/csrc/*.cu; do
+  f=$(basename $src .cu)
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden $2 -c $src -o /tmp/b200_variant_$1/$f.o &
 done
 wait
 nvcc -shared -o $D/variants/lib_$1.so /tmp/b200_variant_$1/*.o -lcudart

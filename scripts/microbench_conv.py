@@ -27,18 +27,31 @@ def timeit(fn, name, flops, iters=10):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     print(f'{name:46s} {ms * 1e3:8.1f} us   {flops / ms / 1e9:8.1f} TFLOP/s (algorithmic)')
+    return ms
 
 
-for (name, cin, cout, res) in [('sr.block1.conv1  64->64  @512^2', 64, 64, 512), ('b64.conv1  512->512 @64^2', 512, 512, 64),
-                               ('b256.conv1 128->128 @256^2', 128, 128, 256)]:
+LAYERS = [('b64.conv0   512->512 up  32->64', 512, 512, 32, 2), ('b64.conv1   512->512 @64^2', 512, 512, 64, 1),
+          ('b128.conv0  512->256 up  64->128', 512, 256, 64, 2), ('b128.conv1  256->256 @128^2', 256, 256, 128, 1),
+          ('b256.conv0  256->128 up 128->256', 256, 128, 128, 2), ('b256.conv1  128->128 @256^2', 128, 128, 256, 1),
+          ('sr0.conv0    32->128 up 128->256', 32, 128, 128, 2), ('sr0.conv1   128->128 @256^2', 128, 128, 256, 1),
+          ('sr1.conv0   128->64  up 256->512', 128, 64, 256, 2), ('sr1.conv1    64->64  @512^2', 64, 64, 512, 1)]
+tot = {'fwd': 0.0, 'dgrad': 0.0, 'wgrad': 0.0}
+for (name, cin, cout, res, up) in LAYERS:
     n, h, w, k = 1, res, res, 3
+    hs = res if up == 1 else 2 * res + 1
     xh, xl = bf(n, h, w, cin), bf(n, h, w, cin)
     wh, wl = bf(n, 9, cout, cin), bf(n, 9, cout, cin)
-    dh, dl = bf(n, h, w, cout), bf(n, h, w, cout)
-    y = torch.empty(n, h, w, cout, device=dev)
+    dh, dl = bf(n, hs, hs, cout), bf(n, hs, hs, cout)
+    y = torch.empty(n, hs, hs, cout, device=dev)
     dx = torch.empty(n, h, w, cin, device=dev)
     dw = torch.empty(n, 9, cout, cin, device=dev)
     fl = 2.0 * h * w * 9 * cin * cout
-    timeit(lambda: call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, 1, 3, stream()), name + ' fwd x3', fl)
-    timeit(lambda: call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, 1, 3, stream()), name + ' dgrad x3', fl)
-    timeit(lambda: call('b200_conv_wgrad_tc', ptr(xh), None, ptr(dh), None, ptr(dw), n, h, w, cin, cout, k, 1, 1, 0, stream()), name + ' wgrad x1', fl)
+    for kind, fn in (('fwd', lambda: call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, 3, stream())),
+                     ('dgrad', lambda: call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, 3, stream())),
+                     ('wgrad', lambda: call('b200_conv_wgrad_tc', ptr(xh), None, ptr(dh), None, ptr(dw), n, h, w, cin, cout, k, up, 1, 0, stream()))):
+        if kind == 'wgrad' and '--only-fwd-dgrad' in sys.argv:
+            continue
+        ms = timeit(fn, f'{name} {kind}', fl)
+        if ms:
+            tot[kind] += ms
+print('totals (us):', {k_: round(v * 1e3, 1) for k_, v in tot.items()})

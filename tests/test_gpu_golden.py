@@ -157,7 +157,9 @@ def test_second_backward_over_a_retained_graph(golden_dir):
             continue
         ref = 2 * once[n]
         err = (p.grad - ref).abs().max().item()
-        assert err <= 1e-4 * max(ref.abs().max().item(), 1e-6) + 1e-7, (n, err)
+        # the two passes differ by the order of their floating-point atomics (~1e-4 of the largest element); a pool that was
+        # accumulated into twice would be off by the size of the gradient itself
+        assert err <= 1e-3 * max(ref.abs().max().item(), 1e-6) + 1e-7, (n, err)
 
 
 def test_generator_io_on_device(golden_dir, tmp_path):
