@@ -76,7 +76,7 @@ B200_API int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int 
     cudaStream_t st = (cudaStream_t)stream;
     const int taps = ksize * ksize;
     if (ksize == 1 && up == 1 && cout <= 4 && cin % 4 == 0 && cin <= 512)
-        return launch_conv_wgrad_thin(x, dy, dwmod, n, (long)h * w, cout, cin, st);
+        return launch_conv_wgrad_thin(x, nullptr, nullptr, dy, dwmod, n, (long)h * w, cout, cin, st);
     ConvWgradParams p{};
     const int hs = up == 1 ? h : 2 * h + 1, ws = up == 1 ? w : 2 * w + 1;
     p.A = dy; p.a_bs = (long)hs * ws * cout; p.HA = hs; p.WA = ws; p.Cm = cout; p.sAy = p.sAx = up;
@@ -92,8 +92,19 @@ B200_API int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int 
     return launch_conv_wgrad_simt(p, n, st);
 }
 
+// wgrad of a 1x1 convolution with at most 4 output channels (the ToRGB layers of the super-resolution blocks) whose input exists
+// only as a split-bf16 pair (x = x_hi + x_lo): dwmod[n][1][cout][cin] = sum over pixels of dy (x) x.  1 when the shape is handled.
+B200_API int b200_conv1x1_thin_supported(int cin, int cout) { return cout >= 1 && cout <= 4 && cin % 4 == 0 && cin >= 4 && cin <= 512; }
+B200_API int b200_conv1x1_wgrad_split(const void* x_hi, const void* x_lo, const float* dy, float* dwmod, int n, long npix, int cin, int cout,
+                                      void* stream) {
+    B200_REQUIRE(b200_conv1x1_thin_supported(cin, cout), "conv1x1_wgrad_split: needs cout <= 4, cin % 4 == 0, cin <= 512");
+    B200_REQUIRE(x_hi && x_lo && dy && dwmod, "conv1x1_wgrad_split: null pointer");
+    if (n <= 0 || npix <= 0) return 0;
+    return launch_conv_wgrad_thin(nullptr, x_hi, x_lo, dy, dwmod, n, npix, cout, cin, (cudaStream_t)stream);
+}
+
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 201; }
+B200_API int b200_version() { return 202; }
 
 // Programmatic dependent launch on (1) / off (0) for subsequent launches; returns the previous setting.  Profiling aid: with PDL a
 // traced kernel duration includes the time it waits for its predecessor.

@@ -32,5 +32,6 @@ struct ConvWgradParams {
 
 int launch_conv_pix_simt(const ConvPixParams& p, int batch, cudaStream_t st);
 int launch_conv_wgrad_simt(ConvWgradParams p, int batch, cudaStream_t st);
-int launch_conv_wgrad_thin(const float* x, const float* dy, float* dW, int batch, long npix, int cm, int cn, cudaStream_t st);
+int launch_conv_wgrad_thin(const float* x, const void* x_hi, const void* x_lo, const float* dy, float* dW, int batch, long npix, int cm, int cn,
+                           cudaStream_t st);
 int launch_conv_dgrad_thin(const float* dy, const float* w, float* dx, int batch, long npix, int cm, int cn, cudaStream_t st);

@@ -8,6 +8,7 @@
 // with a tap table (dy, dx, weight-slice) and integer strides describing the gather.  They handle any
 // channel count (guards everywhere) and are used for layers whose shapes do not fit the tcgen05 tiles.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "conv_geom.h"
 
 #define BM 128
@@ -225,12 +226,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(ConvWgradParams p) {
 // Thin 1x1 weight gradient (Cm <= 4 output channels, e.g. the 3-channel ToRGB of the super-resolution blocks):
 // dW[m][n] = sum_pixels dy[pixel][m] * x[pixel][n].  Pure streaming reduction over x (HBM-bound); a 128x128 GEMM tile
 // would waste 97% of its rows.
-__global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+// SPLIT: x comes as its split-bf16 pair (x = hi + lo), the only copy the lean activation path keeps.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ xhi,
+                                                              const __nv_bfloat16* __restrict__ xlo, const float* __restrict__ dy,
                                                               float* __restrict__ dW, long npix, int cm, int cn, long x_bs,
                                                               long dy_bs, long c_bs) {
     __shared__ float red[4 * 512];
     const int b = blockIdx.y;
-    x += (long)b * x_bs; dy += (long)b * dy_bs; dW += (long)b * c_bs;
+    if (SPLIT) { xhi += (long)b * x_bs; xlo += (long)b * x_bs; } else x += (long)b * x_bs;
+    dy += (long)b * dy_bs; dW += (long)b * c_bs;
     const int c4 = cn >> 2, ppb = blockDim.x / c4;
     const int sub = threadIdx.x / c4, cc = threadIdx.x % c4;
     float acc[4][4];
@@ -240,7 +245,16 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(const float* __res
         for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
     if (sub < ppb) {
         for (long pix = (long)blockIdx.x * ppb + sub; pix < npix; pix += (long)gridDim.x * ppb) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + pix * cn) + cc);
+            float4 xv;
+            if (SPLIT) {
+                const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(xhi + pix * cn) + cc), l2 = __ldg(reinterpret_cast<const uint2*>(xlo + pix * cn) + cc);
+                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h2);
+                const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l2);
+                xv = make_float4(__bfloat162float(hb[0]) + __bfloat162float(lb[0]), __bfloat162float(hb[1]) + __bfloat162float(lb[1]),
+                                 __bfloat162float(hb[2]) + __bfloat162float(lb[2]), __bfloat162float(hb[3]) + __bfloat162float(lb[3]));
+            } else {
+                xv = __ldg(reinterpret_cast<const float4*>(x + pix * cn) + cc);
+            }
             const float* d = dy + pix * cm;
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
@@ -265,12 +279,17 @@ __global__ void __launch_bounds__(256) conv_wgrad_thin_kernel(const float* __res
     for (int i = threadIdx.x; i < cm * cn; i += blockDim.x) atomicAdd(dW + i, red[i]);
 }
 
-int launch_conv_wgrad_thin(const float* x, const float* dy, float* dW, int batch, long npix, int cm, int cn, cudaStream_t st) {
+int launch_conv_wgrad_thin(const float* x, const void* x_hi, const void* x_lo, const float* dy, float* dW, int batch, long npix, int cm, int cn,
+                           cudaStream_t st) {
     B200_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)batch * cm * cn, st));
     const int ppb = 256 / (cn / 4);
     const long nb = (npix + ppb - 1) / ppb;
     dim3 grid((unsigned)(nb < 148 * 4 ? nb : 148 * 4), batch);
-    conv_wgrad_thin_kernel<<<grid, 256, 0, st>>>(x, dy, dW, npix, cm, cn, npix * cn, npix * cm, (long)cm * cn);
+    if (x)
+        conv_wgrad_thin_kernel<false><<<grid, 256, 0, st>>>(x, nullptr, nullptr, dy, dW, npix, cm, cn, npix * cn, npix * cm, (long)cm * cn);
+    else
+        conv_wgrad_thin_kernel<true><<<grid, 256, 0, st>>>(nullptr, (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, dy, dW, npix, cm, cn,
+                                                          npix * cn, npix * cm, (long)cm * cn);
     B200_CHECK_LAUNCH();
     return 0;
 }

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_pix_kernel(const __grid_consta
                             if (p.clamp >= 0.f) t = (t > -p.clamp && t < p.clamp) ? t : (t >= 0.f ? p.clamp : -p.clamp);
                             v[j + q] = t;
                         }
-                        *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (p.C) *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                     }
                     const long eo = (long)o.b * p.c_bs + opix * p.ldc + o.n0 + c0;
 #pragma unroll
@@ -735,18 +735,20 @@ B200_API int b200_conv_tc_act_fusable(int n, int h, int w, int cin, int cout, in
     if (!b200_conv_tc_supported(0, h, w, cin, cout, ksize, 1) || cout % 32 != 0) return 0;
     // The epilogue of tile i runs under the main loop of tile i+1: that hides it only when a tile has enough k-blocks.  Measured:
     // with 9 / 18 k-blocks per tile (64- / 128-channel layers) the fused kernel loses what the separate epilogue launch cost.
-    if (ksize * ksize * ((cin + 63) / 64) < 36) return 0;
+    static int min_kb = -1;
+    if (min_kb < 0) { const char* e = getenv("B200EG3D_ACT_FUSE_MIN_KBLOCKS"); min_kb = e ? atoi(e) : 36; }
+    if (ksize * ksize * ((cin + 63) / 64) < min_kb) return 0;
     return fwd_ksplit(n, h, w, cin, cout, ksize) == 1;
 }
 
 // up == 1 forward convolution with the layer epilogue applied while the accumulator leaves tensor memory:
 //   z = clamp(lrelu_alpha(conv + noise[pix] * *strength + bias[c]) * act_gain, +-clamp)   (networks_stylegan2.py:318-329)
-// written as fp32 z and as split-bf16 z_hi / z_lo (z_lo may be NULL).  noise: [h*w] (noise_bs == 0) or [n][h*w]; may be NULL.
+// written as fp32 z (may be NULL: the split pair is then the only copy) and as split-bf16 z_hi / z_lo (z_lo may be NULL).  noise: [h*w] (noise_bs == 0) or [n][h*w]; may be NULL.
 B200_API int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, void* z_hi,
                                   void* z_lo, const float* bias, const float* noise, const float* strength, long noise_bs, int n,
                                   int h, int w, int cin, int cout, int ksize, int npass, float alpha, float act_gain, float clamp,
                                   void* stream) {
-    B200_REQUIRE(z, "conv_fwd_tc_act: null output");
+    B200_REQUIRE(z_hi, "conv_fwd_tc_act: the split-bf16 output is required (z may be NULL)");
     FwdEpilogue ep{bias, noise, strength, noise_bs, alpha, act_gain, clamp, z_hi, z_lo};
     return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, z, n, h, w, cin, cout, ksize, 1, npass, &ep, stream);
 }

@@ -231,6 +231,7 @@ B200_API int b200_layer_act_fwd(const float* y, float* z, void* z_hi, void* z_lo
 // Also reduces dbias[c] += sum_pix dy, dstrength += sum dy*noise, dnoise[pix] += strength * sum_c dy.
 template <int R>
 __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ z,
+                                                            const __nv_bfloat16* __restrict__ zhi, const __nv_bfloat16* __restrict__ zlo,
                                                             float* __restrict__ dy, __nv_bfloat16* __restrict__ dyhi,
                                                             __nv_bfloat16* __restrict__ dylo, float* __restrict__ dbias,
                                                             const float* __restrict__ noise, const float* __restrict__ strength,
@@ -250,13 +251,12 @@ __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restr
     const long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     for (long pix = (long)blockIdx.x * (blockDim.x >> 5) + wid; pix < npix; pix += nwarps) {
         const float* dzr = dz + pix * c;
-        const float* zr = z + pix * c;
         float row = 0.f;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
             const int ch = lane + 32 * j;
             if (ch < c) {
-                const float zz = zr[ch];
+                const float zz = z ? z[pix * c + ch] : __bfloat162float(zhi[pix * c + ch]) + (zlo ? __bfloat162float(zlo[pix * c + ch]) : 0.f);
                 float g = dzr[ch] * gain;
                 if (lrelu && !(zz > 0.f)) g *= alpha;
                 if (clamp >= 0.f && !(zz > -clamp && zz < clamp)) g = 0.f;
@@ -299,6 +299,7 @@ __global__ void __launch_bounds__(256) layer_act_bwd_kernel(const float* __restr
 // Vectorised variant for c % 4 == 0 and c <= 512: a group of G = c/4 (<= 128) threads owns one pixel, 4 channels per thread.
 // Per-thread column sums are kept in registers across the grid-stride loop (a thread always sees the same 4 channels).
 __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __restrict__ dz, const float4* __restrict__ z,
+                                                                const uint2* __restrict__ zhi, const uint2* __restrict__ zlo,
                                                                 float4* __restrict__ dy, uint2* __restrict__ dyhi,
                                                                 uint2* __restrict__ dylo, float* __restrict__ dbias,
                                                                 const float* __restrict__ noise, const float* __restrict__ strength,
@@ -313,6 +314,7 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
     const int ppb = blockDim.x / c4;                 // pixels per block iteration
     const int sub = threadIdx.x / c4, cc = threadIdx.x % c4;
     const bool active = sub < ppb;
+    const bool shfl_rows = c4 <= 32 && (c4 & (c4 - 1)) == 0;        // a pixel's c4 threads sit in one warp (every thread is active then)
     for (int i = threadIdx.x; i < 4 * c4; i += blockDim.x) s_col[i] = 0.f;
     if (threadIdx.x == 0) s_str = 0.f;
     __syncthreads();
@@ -324,9 +326,27 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
         float row = 0.f;
         if (active && pix < npix) {
             const long i = pix * c4 + cc;
-            const float4 zz = z[i], dd = dz[i];
+            const float4 dd = dz[i];
             float g[4] = {dd.x * gain, dd.y * gain, dd.z * gain, dd.w * gain};
-            const float zv[4] = {zz.x, zz.y, zz.z, zz.w};
+            float zv[4];
+            if (z) {
+                const float4 zz = z[i];
+                zv[0] = zz.x; zv[1] = zz.y; zv[2] = zz.z; zv[3] = zz.w;
+            } else {
+                // reference output from its split-bf16 copy: hi alone decides the sign (bf16 rounding keeps sign and zero);
+                // the clamp test needs hi + lo only where hi itself reaches the clamp (a value just below it rounds up to it)
+                const uint2 h2 = zhi[i];
+                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h2);
+                bool edge = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { zv[j] = __bfloat162float(hb[j]); edge |= clamp >= 0.f && !(zv[j] > -clamp && zv[j] < clamp); }
+                if (edge && zlo) {
+                    const uint2 l2 = zlo[i];
+                    const __nv_bfloat16* lb = reinterpret_cast<const __nv_bfloat16*>(&l2);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) zv[j] += __bfloat162float(lb[j]);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (lrelu && !(zv[j] > 0.f)) g[j] *= alpha;
@@ -337,7 +357,15 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
             if (dy) dy[i] = make_float4(g[0], g[1], g[2], g[3]);
             if (dyhi) split4(g, dyhi, dylo, i);
         }
-        if (noise) {                                  // per-pixel sum over channels -> d noise, d strength
+        if (noise && shfl_rows) {                     // per-pixel sum over channels -> d noise, d strength: the pixel's threads are lanes of one warp
+            float r = row;
+            for (int o = c4 >> 1; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (cc == 0 && pix < npix) {
+                const long nidx = (pix / hw) * noise_bs + pix % hw;
+                sacc += r * noise[nidx];
+                if (dnoise) atomicAdd(dnoise + nidx, r * str);
+            }
+        } else if (noise) {
             s_row[threadIdx.x] = row;
             __syncthreads();
             if (active && cc == 0 && pix < npix) {
@@ -360,25 +388,29 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
     if (noise && dstrength && threadIdx.x == 0) atomicAdd(dstrength, s_str);
 }
 
-B200_API int b200_layer_act_bwd(const float* dz, const float* z, float* dy, void* dy_hi, void* dy_lo, float* dbias,
-                                const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise, int n,
-                                int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
+B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi, void* dy_lo,
+                                float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise,
+                                int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
     // dbias / dstrength / dnoise are ACCUMULATED into (callers zero them); any of them may be null.
+    // The saved output comes as fp32 z, or (z == NULL) as its split-bf16 copy z_hi (+ z_lo, needed for the clamp test only).
     const long npix = (long)n * hw;
     if (npix <= 0 || c <= 0) return 0;
     B200_REQUIRE(c <= 512, "layer_act_bwd: at most 512 channels");
+    B200_REQUIRE(z || z_hi, "layer_act_bwd: the saved output is needed as z or as z_hi / z_lo");
+    B200_REQUIRE(z || z_lo || clamp < 0.f, "layer_act_bwd: the clamp test on a split output needs z_lo");
     cudaStream_t st = (cudaStream_t)stream;
     if (c % 4 == 0) {
         const int c4 = c / 4, ppb = 256 / c4;
         const long nb = (npix + ppb - 1) / ppb;
         const int blocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
-        B200_CUDA(launch_pdl(layer_act_bwd_vec_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)dz, (const float4*)z, (float4*)dy, (uint2*)dy_hi,
+        B200_CUDA(launch_pdl(layer_act_bwd_vec_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)dz, (const float4*)z, (const uint2*)z_hi,
+                             (const uint2*)z_lo, (float4*)dy, (uint2*)dy_hi,
                              (uint2*)dy_lo, dbias, noise, strength, noise_bs, dstrength, dnoise, npix, hw, c4, lrelu, alpha, gain, clamp));
         return 0;
     }
     B200_REQUIRE(!dy_hi, "layer_act_bwd: bf16 outputs need a channel count that is a multiple of 4");
     const int blocks = (int)((npix + 7) / 8 < 148 * 8 ? (npix + 7) / 8 : 148 * 8);
-#define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, dy, (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, dbias, \
+#define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, (const __nv_bfloat16*)z_hi, (const __nv_bfloat16*)z_lo, dy, (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, dbias, \
                                                                      noise, strength, noise_bs, dstrength, dnoise, npix, hw, c, lrelu, \
                                                                      alpha, gain, clamp)
     if (c <= 32) LAUNCH_R(1); else if (c <= 64) LAUNCH_R(2); else if (c <= 128) LAUNCH_R(4);

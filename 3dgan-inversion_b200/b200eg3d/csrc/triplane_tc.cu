@@ -181,6 +181,17 @@ __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      
     return ok != 0;
 }
 
+// Probe by lane 0, result broadcast: the MMA warps below run CONVERGED (descriptor arithmetic stays on the uniform datapath) and
+// one elected lane issues -- a `lane == 0` branch around the whole loop makes the compiler rebuild every 64-bit descriptor in
+// vector registers and move it across (R2UR), ~100 clocks per MMA, which sat on the tile's phase chain.
+__device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity, int lane) {
+    uint32_t ok = 0;
+    if (lane == 0) ok = mbar_test(bar, parity) ? 1u : 0u;
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+// K-major operand, 128-byte swizzle, 8-row groups 1 KB apart: descriptor for start address `a` (high word `hi` = smem_desc_hi(1024))
+__device__ __forceinline__ uint64_t kdesc(uint32_t a, uint32_t hi) { return desc_pack(smem_desc_lo(a, 0), hi); }
+
 // SIGMA_ONLY: density queries on voxel grids (single_id_coach.py:118-140) write column 0 of the second layer only.
 template <bool SIGMA_ONLY>
 __global__ void __launch_bounds__(FW_THREADS, 1) triplane_fwd_tc_kernel(TriplaneParams p) {
@@ -233,45 +244,53 @@ __global__ void __launch_bounds__(FW_THREADS, 1) triplane_fwd_tc_kernel(Triplane
         // operand tile is ready first goes first, so a slow activation stage never holds back the next tile's layer 1.
         // D1[s] / D2[s] (s = tile parity) are free again once layer 2 of the tile two back has been issued: its a2_full arrival
         // follows the consumer's last read of both.
-        if (lane == 0) {
+        {
             const uint32_t id1 = instr_desc_bf16(128, HID, 0, 0), id2 = instr_desc_bf16(128, OUTP, 0, 0);
+            const uint32_t dhi = smem_desc_hi(1024);
+            const bool three = p.fwd_passes == 3;
             int n1 = 0, n2 = 0;
             while (n2 < nloc) {
                 bool did = false;
                 if (n1 < nloc && n1 - n2 < 2) {
                     const int st = n1 % NGRP, it = n1 / NGRP, s = n1 & 1;
-                    if (mbar_test(bar_a1_full(B, st), it & 1)) {
+                    if (mbar_test_warp(bar_a1_full(B, st), it & 1, lane)) {
                         tc_fence_after();
                         const uint32_t a = sm_u + OFF_A1 + st * 16384, d1 = tmem + (uint32_t)(s * 128);
-                        const int nk = p.fwd_passes == 3 ? 4 : 2;
-                        for (int k = 0; k < nk; ++k)           // [F_hi F_lo] x [W1_hi W1_hi]   (single pass: F_hi x W1_hi only)
-                            umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + OFF_W1A + k * 32, 0, 1024), id1, k != 0);
-                        if (p.fwd_passes == 3) {
+                        if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < 2; ++k)        // F_hi x W1_lo
-                                umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + OFF_W1B + k * 32, 0, 1024), id1, 1);
+                            for (int k = 0; k < 4; ++k)        // [F_hi F_lo] x [W1_hi W1_hi]   (single pass: F_hi x W1_hi only)
+                                if (k < 2 || three) umma_bf16(d1, kdesc(a + k * 32, dhi), kdesc(sm_u + OFF_W1A + k * 32, dhi), id1, k != 0);
+                            if (three) {
+#pragma unroll
+                                for (int k = 0; k < 2; ++k)    // F_hi x W1_lo
+                                    umma_bf16(d1, kdesc(a + k * 32, dhi), kdesc(sm_u + OFF_W1B + k * 32, dhi), id1, 1);
+                            }
+                            umma_commit(bar_a1_empty(B, st));
+                            umma_commit(bar_d1_full(B, s));
                         }
-                        umma_commit(bar_a1_empty(B, st));
-                        umma_commit(bar_d1_full(B, s));
+                        __syncwarp();
                         ++n1;
                         did = true;
                     }
                 }
                 if (n2 < n1) {
                     const int s = n2 & 1, it = n2 >> 1;
-                    if (mbar_test(bar_a2_full(B, s), it & 1)) {
+                    if (mbar_test_warp(bar_a2_full(B, s), it & 1, lane)) {
                         tc_fence_after();
                         const uint32_t ah = sm_u + OFF_A2 + s * 32768, al = ah + 16384, d2 = tmem + (uint32_t)(s * 128 + 64);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t dah = smem_desc(ah + k * 32, 0, 1024), dbh = smem_desc(sm_u + OFF_W2H + k * 32, 0, 1024);
-                            umma_bf16(d2, dah, dbh, id2, k != 0);
-                            if (p.fwd_passes == 3) {
-                                umma_bf16(d2, dah, smem_desc(sm_u + OFF_W2L + k * 32, 0, 1024), id2, 1);
-                                umma_bf16(d2, smem_desc(al + k * 32, 0, 1024), dbh, id2, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t dah = kdesc(ah + k * 32, dhi), dbh = kdesc(sm_u + OFF_W2H + k * 32, dhi);
+                                umma_bf16(d2, dah, dbh, id2, k != 0);
+                                if (three) {
+                                    umma_bf16(d2, dah, kdesc(sm_u + OFF_W2L + k * 32, dhi), id2, 1);
+                                    umma_bf16(d2, kdesc(al + k * 32, dhi), dbh, id2, 1);
+                                }
                             }
+                            umma_commit(bar_d2_full(B, s));
                         }
-                        umma_commit(bar_d2_full(B, s));
+                        __syncwarp();
                         ++n2;
                         did = true;
                     }
@@ -594,78 +613,92 @@ __global__ void __launch_bounds__(BW_THREADS, 1) triplane_bwd_tc_kernel(Triplane
         }
     } else if (warp == BW_MMA_WARP) {
         // ------------------------------------------------------------------ tensor-core issue (one lane), four cursors
-        if (lane == 0) {
+        {
             const uint32_t id1 = instr_desc_bf16(128, HID, 0, 0), id2 = instr_desc_bf16(128, OUTP, 0, 0);
             const uint32_t id3 = instr_desc_bf16(128, HID, 0, 0), id4 = instr_desc_bf16(128, C, 0, 0);
             const uint32_t idw2 = instr_desc_bf16(128, OUTP, 1, 1), idw1 = instr_desc_bf16(128, HID, 1, 1);
+            const uint32_t dhi = smem_desc_hi(1024);
             int n1 = 0, n2 = 0, n3 = 0, n4 = 0;
             while (n4 < nloc) {
                 bool did = false;
-                if (n4 < n3 && mbar_test(bb_set(B, BB_A4, n4 & 1), (n4 >> 1) & 1)) {          // P4: d_f and dW1
+                if (n4 < n3 && mbar_test_warp(bb_set(B, BB_A4, n4 & 1), (n4 >> 1) & 1, lane)) {          // P4: d_f and dW1
                     tc_fence_after();
                     const int s = n4 & 1;
                     const uint32_t da = sm_u + BO_A2 + s * 32768, d4 = tmem + (uint32_t)(s * 192 + 64);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t a = smem_desc(da + k * 32, 0, 1024);
-                        umma_bf16(d4, a, smem_desc(sm_u + BO_W1TH + k * 32, 0, 1024), id4, k != 0);
-                        umma_bf16(d4, a, smem_desc(sm_u + BO_W1TL + k * 32, 0, 1024), id4, 1);
-                    }
-                    if (WGRAD) {
-                        const uint32_t f = sm_u + BO_FC + s * 16384;
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a = kdesc(da + k * 32, dhi);
+                            umma_bf16(d4, a, kdesc(sm_u + BO_W1TH + k * 32, dhi), id4, k != 0);
+                            umma_bf16(d4, a, kdesc(sm_u + BO_W1TL + k * 32, dhi), id4, 1);
+                        }
+                        if (WGRAD) {
+                            const uint32_t f = sm_u + BO_FC + s * 16384;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)            // rows 64..127 of the M = 128 operand: the 16 x 64 ones block, for every k-step
-                            umma_bf16(tmem + TM_ACC1, smem_desc(f + k * 2048, sm_u + BO_ONES - (f + k * 2048), 1024), smem_desc(da + k * 2048, 0, 1024),
-                                      idw1, (n4 | k) != 0);
+                            for (int k = 0; k < 8; ++k)        // rows 64..127 of the M = 128 operand: the 16 x 64 ones block, for every k-step
+                                umma_bf16(tmem + TM_ACC1, desc_pack(smem_desc_lo(f + k * 2048, sm_u + BO_ONES - (f + k * 2048)), dhi),
+                                          kdesc(da + k * 2048, dhi), idw1, (n4 | k) != 0);
+                        }
+                        umma_commit(bb_set(B, BB_D4, s));
                     }
-                    umma_commit(bb_set(B, BB_D4, s));
+                    __syncwarp();
                     ++n4; did = true;
                 }
-                if (n3 < n2 && mbar_test(bb_set(B, BB_A3, n3 & 1), (n3 >> 1) & 1)) {          // P3: dh and dW2
+                if (n3 < n2 && mbar_test_warp(bb_set(B, BB_A3, n3 & 1), (n3 >> 1) & 1, lane)) {          // P3: dh and dW2
                     tc_fence_after();
                     const int s = n3 & 1;
                     const uint32_t hh = sm_u + BO_A2 + s * 32768, dO = hh + 16384, d3 = tmem + (uint32_t)(s * 192 + 128);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        const uint64_t a = smem_desc(dO + k * 32, 0, 1024);
-                        umma_bf16(d3, a, smem_desc(sm_u + BO_W2TH + k * 32, 0, 1024), id3, k != 0);
-                        umma_bf16(d3, a, smem_desc(sm_u + BO_W2TL + k * 32, 0, 1024), id3, 1);
-                    }
-                    if (WGRAD) {
+                        for (int k = 0; k < 3; ++k) {
+                            const uint64_t a = kdesc(dO + k * 32, dhi);
+                            umma_bf16(d3, a, kdesc(sm_u + BO_W2TH + k * 32, dhi), id3, k != 0);
+                            umma_bf16(d3, a, kdesc(sm_u + BO_W2TL + k * 32, dhi), id3, 1);
+                        }
+                        if (WGRAD) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            umma_bf16(tmem + TM_ACC2, smem_desc(hh + k * 2048, sm_u + BO_ONES - (hh + k * 2048), 1024), smem_desc(dO + k * 2048, 0, 1024),
-                                      idw2, (n3 | k) != 0);
+                            for (int k = 0; k < 8; ++k)
+                                umma_bf16(tmem + TM_ACC2, desc_pack(smem_desc_lo(hh + k * 2048, sm_u + BO_ONES - (hh + k * 2048)), dhi),
+                                          kdesc(dO + k * 2048, dhi), idw2, (n3 | k) != 0);
+                        }
+                        umma_commit(bb_set(B, BB_D3, s));
                     }
-                    umma_commit(bb_set(B, BB_D3, s));
+                    __syncwarp();
                     ++n3; did = true;
                 }
-                if (n2 < n1 && mbar_test(bb_set(B, BB_A2, n2 & 1), (n2 >> 1) & 1)) {          // P2: layer 2 (recompute)
+                if (n2 < n1 && mbar_test_warp(bb_set(B, BB_A2, n2 & 1), (n2 >> 1) & 1, lane)) {          // P2: layer 2 (recompute)
                     tc_fence_after();
                     const int s = n2 & 1;
                     const uint32_t ah = sm_u + BO_A2 + s * 32768, al = ah + 16384, d2 = tmem + (uint32_t)(s * 192 + 64);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t dah = smem_desc(ah + k * 32, 0, 1024), dbh = smem_desc(sm_u + BO_W2H + k * 32, 0, 1024);
-                        umma_bf16(d2, dah, dbh, id2, k != 0);
-                        umma_bf16(d2, smem_desc(al + k * 32, 0, 1024), dbh, id2, 1);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t dah = kdesc(ah + k * 32, dhi), dbh = kdesc(sm_u + BO_W2H + k * 32, dhi);
+                            umma_bf16(d2, dah, dbh, id2, k != 0);
+                            umma_bf16(d2, kdesc(al + k * 32, dhi), dbh, id2, 1);
+                        }
+                        umma_commit(bb_set(B, BB_D2, s));
                     }
-                    umma_commit(bb_set(B, BB_D2, s));
+                    __syncwarp();
                     ++n2; did = true;
                 }
-                if (n1 < nloc && n1 - n4 < 2 && mbar_test(bb_a1_full(B, n1 % BW_ST), (n1 / BW_ST) & 1)) {   // P1: layer 1 (recompute); D1[s] is free after S3 of tile n1 - 2
+                if (n1 < nloc && n1 - n4 < 2 && mbar_test_warp(bb_a1_full(B, n1 % BW_ST), (n1 / BW_ST) & 1, lane)) {   // P1: layer 1 (recompute); D1[s] is free after S3 of tile n1 - 2
                     tc_fence_after();
                     const int s = n1 & 1;
                     const uint32_t a = sm_u + BO_A1 + (n1 % BW_ST) * 16384, d1 = tmem + (uint32_t)(s * 192);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16(d1, smem_desc(a + k * 32, 0, 1024), smem_desc(sm_u + BO_W1A + k * 32, 0, 1024), id1, k != 0);
-                    umma_commit(bb_set(B, BB_D1, s));
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d1, kdesc(a + k * 32, dhi), kdesc(sm_u + BO_W1A + k * 32, dhi), id1, k != 0);
+                        umma_commit(bb_set(B, BB_D1, s));
+                    }
+                    __syncwarp();
                     ++n1; did = true;
                 }
                 if (!did) __nanosleep(32);
             }
-            umma_commit(B + BB_ACC_DONE);
+            if (elect_one()) umma_commit(B + BB_ACC_DONE);
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ consumers: set = tile parity, thread = point = TMEM lane

@@ -132,9 +132,10 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None, bank=None, lidx=-1):
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None, bank=None, lidx=-1, want_z=True):
         """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None.
-        bank / lidx: styles and modulated weights come from a pre-computed ops.WeightBank entry (w is then unused)."""
+        bank / lidx: styles and modulated weights come from a pre-computed ops.WeightBank entry (w is then unused).
+        want_z=False: the caller's consumers all read the pair (ops.lean_ok): z comes back as a shape-only placeholder."""
         assert noise_mode in ['random', 'const', 'none']
         if not fused_modconv:
             return self._forward_unfused(x, w, noise_mode, gain), None
@@ -146,7 +147,7 @@ class SynthesisLayer(torch.nn.Module):
             noise = self.noise_const
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return ops.modconv_layer(x, self.weight, styles, self.bias, noise, self.noise_strength if noise is not None else None,
-                                 self.up, self.act_gain * gain, clamp, x_split=x_split, bank=bank, lidx=lidx)
+                                 self.up, self.act_gain * gain, clamp, x_split=x_split, bank=bank, lidx=lidx, want_z=want_z)
 
 
     def _forward_unfused(self, x, w, noise_mode, gain):
@@ -240,7 +241,7 @@ class SynthesisBlock(torch.nn.Module):
         return specs
 
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, x_split=None, return_split=False,
-                bank=None, bank_base=0, side=None, **layer_kwargs):
+                bank=None, bank_base=0, side=None, lean_out=False, **layer_kwargs):
         """x_split / return_split carry the split-bf16 copies of the activations between consecutive blocks;
         bank / bank_base: pre-computed styles + modulated weights (ops.WeightBank) and this block's first entry."""
         w_iter = iter(ws.unbind(dim=1))
@@ -256,9 +257,13 @@ class SynthesisBlock(torch.nn.Module):
             x = self.const.to(torch.float32).permute(1, 2, 0).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous()
             sp = None
         else:
-            x, sp = self.conv0(x, next(w_iter), x_split=x_split, bank=bank, lidx=li, **layer_kwargs)
+            # activations between tensor-core layers travel as their split-bf16 pair only (no fp32 copy): conv0 feeds conv1,
+            # conv1 feeds this block's ToRGB and the next block's conv0
+            lean0 = bool(fused_modconv) and ops.lean_ok(bank, [li + 1])
+            x, sp = self.conv0(x, next(w_iter), x_split=x_split, bank=bank, lidx=li, want_z=not lean0, **layer_kwargs)
             li += 1
-        x, sp = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, **layer_kwargs)
+        lean1 = bool(fused_modconv) and lean_out and ops.lean_ok(bank, [li + 1, li + 2])
+        x, sp = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, want_z=not lean1, **layer_kwargs)
         if side is None:
             img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1, fused_modconv=bool(fused_modconv))
         else:
@@ -329,7 +334,7 @@ class SynthesisNetwork(torch.nn.Module):
                     t.record_stream(side)
         for i, (res, cur_ws) in enumerate(zip(self.block_resolutions, block_ws)):
             x, img, sp = getattr(self, f'b{res}')(x, img, cur_ws, x_split=sp, return_split=True, bank=bank, bank_base=bases[i],
-                                                  side=side, **block_kwargs)
+                                                  side=side, lean_out=True, **block_kwargs)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
             img.record_stream(torch.cuda.current_stream())
@@ -395,8 +400,8 @@ class SuperresolutionHybrid8X(torch.nn.Module):
             for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool, rgb]:
                 if t is not None:
                     t.record_stream(side)
-        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, bank=bank, bank_base=0, side=side, **block_kwargs)
-        x, rgb = self.block1(x, rgb, ws, x_split=sp, bank=bank, bank_base=base1, side=side, **block_kwargs)
+        x, rgb, sp = self.block0(x, rgb, ws, return_split=True, bank=bank, bank_base=0, side=side, lean_out=True, **block_kwargs)
+        x, rgb = self.block1(x, rgb, ws, x_split=sp, bank=bank, bank_base=base1, side=side, lean_out=True, **block_kwargs)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
             rgb.record_stream(torch.cuda.current_stream())

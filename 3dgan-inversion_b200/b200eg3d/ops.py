@@ -42,6 +42,9 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           # weight-gradient GEMMs on their own stream (they only feed the bank's backward): their split-K reduction tails and launch
           # latencies overlap the dgrad chain; d wmod of all layers is one pool, zeroed once per step off the critical path
           'wgrad_stream': os.environ.get('B200EG3D_WGRAD_STREAM', '1') != '0',
+          # inside a synthesis network keep activations only as the split-bf16 pair the next tensor-core conv reads: no fp32 copy is
+          # written by the layer epilogues or re-read by the activation backward (the returned fp32 tensor is then a placeholder)
+          'lean_acts': os.environ.get('B200EG3D_LEAN_ACTS', '1') != '0',
           'ranges': os.environ.get('B200EG3D_RANGES', '0') != '0'}
 
 
@@ -530,10 +533,13 @@ class _ModConvLayer(torch.autograd.Function):
 
     @staticmethod
     @device_guard
-    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp, token=None, bank=None, lidx=-1):
+    def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp, token=None, bank=None, lidx=-1,
+                want_z=True):
         ctx.set_materialize_grads(False)       # no zero-filled gradients for the non-differentiable bf16 outputs
-        x = _f32c(x)
         n, h, w, cin = x.shape
+        have_split = x_hi is not None and (x_lo is not None or CONFIG['fwd_passes'] != 3)
+        if not have_split:
+            x = _f32c(x)                       # (with the producer's split pair at hand x may be a shape-only placeholder: never touch it)
         if bank is not None:
             sp = bank.specs[lidx]
             cout, k = sp.cout, sp.k
@@ -559,7 +565,12 @@ class _ModConvLayer(torch.autograd.Function):
         else:
             tc = _tc_ok(0, h, w, cin, cout, k, up) and _tc_ok(1, h, w, cin, cout, k, up) and _tc_ok(2, h, w, cin, cout, k, up)
             dcoef = torch.empty([n, cout], device=dev, dtype=torch.float32)
-        z = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
+        lean = tc and not want_z               # keep the output only as its split-bf16 pair
+        if lean:
+            z = _placeholder([n, oh, ow, cout], dev)
+        else:
+            z = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
+        zp = None if lean else ptr(z)
         if tc:
             fp = CONFIG['fwd_passes']
             keep_lo = fp == 3 or CONFIG['dgrad_passes'] == 3
@@ -571,23 +582,26 @@ class _ModConvLayer(torch.autograd.Function):
                 call('b200_modconv_weight_prep', ptr(W), ptr(s), None, ptr(w_hi), ptr(w_lo), ptr(dcoef), n, cout, cin, taps, 1, stream())
             if x_hi is None or (fp == 3 and x_lo is None):
                 x_hi, x_lo = _split(x, fp == 3)
-            z_hi, z_lo = _bf16_like(z), _bf16_like(z)
+            z_hi = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.bfloat16)
+            z_lo = torch.empty_like(z_hi)
             if up == 1 and _lib.load().b200_conv_tc_act_fusable(n, h, w, cin, cout, k) == 1:
                 # epilogue applied while the accumulator leaves tensor memory: no fp32 round trip of the raw conv output
-                call('b200_conv_fwd_tc_act', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(z), ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st),
+                call('b200_conv_fwd_tc_act', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), zp, ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st),
                      nbs, n, h, w, cin, cout, k, fp, 0.2, float(act_gain), clampf, stream())
             elif up == 1:
-                y = torch.empty_like(z)
+                y = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
                 call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cout, k, 1, fp, stream())
-                call('b200_layer_act_fwd', ptr(y), ptr(z), ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
+                call('b200_layer_act_fwd', ptr(y), zp, ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
                      float(act_gain), clampf, stream())
             else:
                 zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
                 call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(zt), n, h, w, cin, cout, k, 2, fp, stream())
                 # 4x4 FIR (pad 1, gain 4) fused with the layer epilogue and the bf16 split for the next conv
-                call('b200_upfirdn2d_fused', ptr(zt), ptr(fir_filter(dev)), None, ptr(z), ptr(z_hi), ptr(z_lo), n, 2 * h + 1, 2 * w + 1,
+                call('b200_upfirdn2d_fused', ptr(zt), ptr(fir_filter(dev)), None, zp, ptr(z_hi), ptr(z_lo), n, 2 * h + 1, 2 * w + 1,
                      cout, 4, 4, 1, 1, 1, 1, 1, 1, 0, 4.0, 1, ptr(b), ptr(nz), ptr(st), nbs, 1, 0.2, float(act_gain), clampf, stream())
-            ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, dcoef, z, nz, st)
+            # the activation backward needs the OUTPUT (sign and clamp): the fp32 copy, or -- lean -- the split pair the consumer keeps anyway
+            ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, dcoef,
+                                  None if lean else z, nz, st, z_hi if lean else None, z_lo if lean else None)
             ctx.mark_non_differentiable(z_hi, z_lo)
         else:
             if bank is not None:
@@ -605,7 +619,7 @@ class _ModConvLayer(torch.autograd.Function):
             call('b200_layer_act_fwd', ptr(y), ptr(z), None, None, ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
                  float(act_gain), clampf, stream())
             z_hi = z_lo = None
-            ctx.save_for_backward(x, None, W, s, wmod, None, dcoef, z, nz, st)
+            ctx.save_for_backward(x, None, W, s, wmod, None, dcoef, z, nz, st, None, None)
         ctx.cfg = (tc, up, float(act_gain), clampf, k, nbs, (n, h, w, cin, cout))
         ctx.bank, ctx.lidx = bank, lidx
         return z, z_hi, z_lo
@@ -614,13 +628,14 @@ class _ModConvLayer(torch.autograd.Function):
     @device_guard
     def backward(ctx, dz, _dhi, _dlo):
         if dz is None:
-            return (None,) * 14
-        xs, xs_lo, W, s, wm, wm_lo, dcoef, z, nz, st = ctx.saved_tensors
+            return (None,) * 15
+        xs, xs_lo, W, s, wm, wm_lo, dcoef, z, nz, st, zr_hi, zr_lo = ctx.saved_tensors
         tc, up, act_gain, clamp, k, nbs, (n, h, w, cin, cout) = ctx.cfg
         bank, lidx = ctx.bank, ctx.lidx
         taps = k * k
-        dev = z.device
-        oh, ow = z.shape[1:3]
+        dev = dz.device
+        oh, ow = h * up, w * up
+        zref = (ptr(z), ptr(zr_hi), ptr(zr_lo))          # saved output: fp32, or (lean) its split pair
         need = ctx.needs_input_grad
         need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dzc = _f32c(dz)
@@ -639,11 +654,11 @@ class _ModConvLayer(torch.autograd.Function):
             lo = (need_x and dp == 3) or (need_w and wp == 3)
             if up == 1:
                 dy_hi, dy_lo = _bf16_like(dzc), (_bf16_like(dzc) if lo else None)
-                call('b200_layer_act_bwd', ptr(dzc), ptr(z), None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
+                call('b200_layer_act_bwd', ptr(dzc), *zref, None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
                      ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
             else:
                 dy = torch.empty_like(dzc)
-                call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
+                call('b200_layer_act_bwd', ptr(dzc), *zref, ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
                      ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
                 # adjoint of the FIR (pad 2, flipped filter) straight to split bf16 on the (2h+1)x(2w+1) grid
                 _, dy_hi, dy_lo = _fir_fused(dy, fir_filter(dev), 1, 1, (2, 2, 2, 2), True, 4.0, want_f32=False, want_split=True, need_lo=lo)
@@ -659,7 +674,7 @@ class _ModConvLayer(torch.autograd.Function):
                     call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cout, k, up, wp, 0, stream())
         else:
             dy = torch.empty_like(dzc)
-            call('b200_layer_act_bwd', ptr(dzc), ptr(z), ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr), ptr(dnoise),
+            call('b200_layer_act_bwd', ptr(dzc), *zref, ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr), ptr(dnoise),
                  n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
             if up == 2:
                 dy = _upfirdn_nhwc_raw(dy, fir_filter(dev), (1, 1), (1, 1), (2, 2, 2, 2), True, 4.0)
@@ -677,16 +692,48 @@ class _ModConvLayer(torch.autograd.Function):
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin, taps, 1, stream())
-        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None, dtok, None, None
+        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None, dtok, None, None, None
 
 
-def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None, bank=None, lidx=-1):
+def _placeholder(shape, device):
+    """Shape-only fp32 stand-in (zero strides, one element of storage) for an activation that exists only as its split-bf16 pair:
+    autograd routes the gradient of that shape through it, nothing ever reads its values."""
+    key = str(device)
+    if key not in _PLACEHOLDER:
+        _PLACEHOLDER[key] = torch.zeros([1], device=device, dtype=torch.float32)
+    return _PLACEHOLDER[key].expand(shape)
+
+
+_PLACEHOLDER = {}
+
+
+def lean_ok(bank, consumers):
+    """True when every consumer layer (bank indices) of an activation reads it through the split-bf16 pair in both directions, so the
+    producer may skip the fp32 copy (CONFIG['lean_acts']).  A consumer qualifies when its forward runs on the tensor cores and its
+    backward does too, or is the thin 1x1 path that takes the pair (the 3-channel ToRGB layers)."""
+    if bank is None or not CONFIG['lean_acts'] or not CONFIG['tc']:
+        return False
+    lib = _lib.load()
+    for l in consumers:
+        if l >= len(bank.specs):
+            continue
+        sp = bank.specs[l]
+        thin = sp.k == 1 and sp.up == 1 and lib.b200_conv1x1_thin_supported(sp.cin, sp.cout) == 1
+        if not (sp.tc_f and (sp.tc_b or thin)):
+            return False
+    return True
+
+
+def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None, bank=None, lidx=-1, want_z=True):
     """Returns (z, (z_hi, z_lo) or None).  x_split: the producer's split-bf16 copies of x, if it made them.
-    bank / lidx: take styles and modulated weights from a WeightBank entry instead of (weight, styles)."""
+    bank / lidx: take styles and modulated weights from a WeightBank entry instead of (weight, styles).
+    want_z=False (tensor-core layers only): do not write the fp32 output; z is then a shape-only placeholder and the pair is the
+    activation (see lean_ok)."""
     xh, xl = x_split if x_split is not None else (None, None)
     with prof_range('modulated_conv2d'):
         if bank is not None:
-            z, zh, zl = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank, lidx)
+            z, zh, zl = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank, lidx,
+                                            bool(want_z))
         else:
             z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
     return z, ((zh, zl) if zh is not None else None)
@@ -703,10 +750,12 @@ class _ToRGB(torch.autograd.Function):
     @device_guard
     def forward(ctx, x, x_hi, x_lo, weight, styles, bias, img_prev, clamp, token=None, bank=None, lidx=-1):
         ctx.set_materialize_grads(False)
-        x = _f32c(x)
         n, h, w, cin = x.shape
         dev = x.device
         fp = CONFIG['fwd_passes']
+        have_split = x_hi is not None and x_lo is not None
+        if not have_split:
+            x = _f32c(x)                       # (with the producer's split pair at hand x may be a shape-only placeholder: never touch it)
         if bank is not None:
             sp = bank.specs[lidx]
             cimg, W, s = sp.cout, sp._W, bank.styles[lidx]
@@ -731,7 +780,7 @@ class _ToRGB(torch.autograd.Function):
         if tc_f:
             call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cimg, 1, 1, fp, stream())
         else:
-            call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
+            call('b200_conv_fwd', ptr(_f32c(x)), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
         b = _f32c(bias)
         cl = float(clamp if clamp is not None else -1)
         call('b200_bias_act', ptr(y), ptr(b), None, None, None, ptr(y), 0, y.numel(), 1, cimg, 1, 0.0, 1.0, cl, stream())
@@ -739,12 +788,16 @@ class _ToRGB(torch.autograd.Function):
             img = _upfirdn_nhwc_raw(_f32c(img_prev), fir_filter(dev), (2, 2), (1, 1), (2, 1, 2, 1), False, 4.0, add=y)
         else:
             img = y
-        ctx.cfg = (cl, img_prev is not None, tc_b, (n, h, w, cin, cimg))
+        # fp32 backward (channel counts the tensor cores cannot take): the thin 1x1 weight gradient reads x from the pair when it exists
+        split_x = (not tc_b) and have_split and _lib.load().b200_conv1x1_thin_supported(cin, cimg) == 1
+        ctx.cfg = (cl, img_prev is not None, tc_b, (n, h, w, cin, cimg), split_x)
         ctx.bank, ctx.lidx = bank, lidx
         if tc_b:
             ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, y)
+        elif split_x:
+            ctx.save_for_backward(x_hi, x_lo, W, s, wmod, None, y)
         else:
-            ctx.save_for_backward(x, None, W, s, wmod, None, y)
+            ctx.save_for_backward(_f32c(x), None, W, s, wmod, None, y)
         return img
 
     @staticmethod
@@ -753,7 +806,7 @@ class _ToRGB(torch.autograd.Function):
         if dimg is None:
             return (None,) * 11
         xs, xs_lo, W, s, wm, wm_lo, y = ctx.saved_tensors
-        cl, has_prev, tc_b, (n, h, w, cin, cimg) = ctx.cfg
+        cl, has_prev, tc_b, (n, h, w, cin, cimg), split_x = ctx.cfg
         bank, lidx = ctx.bank, ctx.lidx
         dev = y.device
         need = ctx.needs_input_grad
@@ -772,7 +825,7 @@ class _ToRGB(torch.autograd.Function):
             dp, wp = CONFIG['dgrad_passes'], CONFIG['wgrad_passes']
             lo = (need_x and dp == 3) or (need_w and wp == 3)
             dy_hi, dy_lo = _bf16_like(dimg), (_bf16_like(dimg) if lo else None)
-            call('b200_layer_act_bwd', ptr(dimg), ptr(y), None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), None, None, 0, None, None,
+            call('b200_layer_act_bwd', ptr(dimg), ptr(y), None, None, None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), None, None, 0, None, None,
                  n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
                 call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cimg, 1, 1, dp, stream())
@@ -783,11 +836,13 @@ class _ToRGB(torch.autograd.Function):
                 call('b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, 0, stream())
         else:
             dy = torch.empty_like(dimg)
-            call('b200_layer_act_bwd', ptr(dimg), ptr(y), ptr(dy), None, None, ptr(dbias), None, None, 0, None, None,
+            call('b200_layer_act_bwd', ptr(dimg), ptr(y), None, None, ptr(dy), None, None, ptr(dbias), None, None, 0, None, None,
                  n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
                 call('b200_conv_dgrad', ptr(dy), ptr(wm), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
-            if need_w:
+            if need_w and split_x:
+                call('b200_conv1x1_wgrad_split', ptr(xs), ptr(xs_lo), ptr(dy), ptr(dwmod), n, h * w, cin, cimg, stream())
+            elif need_w:
                 call('b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream())
         if need_w and bank is not None:
             bank.dwmod[lidx] = dwmod

@@ -83,6 +83,11 @@ int b200_conv_dgrad(const float* dy, const float* wmod, float* dx, int n, int h,
                     int ksize, int up, void* stream);
 int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int n, int h, int w, int cin, int cout,
                     int ksize, int up, void* stream);
+/* The same weight gradient for a 1x1 convolution with <= 4 output channels (the ToRGB layers of the super-resolution blocks) whose
+ * input exists only as its split-bf16 pair x = x_hi + x_lo ([n][npix][cin] bf16 each); b200_conv1x1_thin_supported -> 1 if handled. */
+int b200_conv1x1_thin_supported(int cin, int cout);
+int b200_conv1x1_wgrad_split(const void* x_hi, const void* x_lo, const float* dy, float* dwmod, int n, long npix, int cin, int cout,
+                             void* stream);
 
 /* tcgen05 / TMA tensor-core convolutions on split-bf16 operands (same geometry as above).
  * npass = 3: hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (fp32-parity mode); npass = 1: hi*hi only (lo may be NULL).
@@ -92,8 +97,8 @@ int b200_split_bf16(const float* x, void* hi_bf16, void* lo_bf16 /* may be NULL 
 int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y,
                      int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
 /* up == 1 forward convolution with the SynthesisLayer epilogue (networks_stylegan2.py:318-329) applied while the accumulator
- * leaves tensor memory: z = clamp(lrelu_alpha(conv + noise[pix] * *strength + bias[c]) * act_gain, +-clamp), written as fp32 z and
- * as the split-bf16 pair z_hi / z_lo (z_lo may be NULL) that feeds the next convolution.  noise [h*w] (noise_bs 0) or [n][h*w]
+ * leaves tensor memory: z = clamp(lrelu_alpha(conv + noise[pix] * *strength + bias[c]) * act_gain, +-clamp), written as fp32 z (may
+ * be NULL: the pair is then the only copy) and as the split-bf16 pair z_hi / z_lo (z_lo may be NULL) that feeds the next convolution.  noise [h*w] (noise_bs 0) or [n][h*w]
  * (noise_bs h*w), may be NULL.  Only for shapes b200_conv_tc_act_fusable reports 1 (no split-K, cout % 32 == 0). */
 int b200_conv_tc_act_fusable(int n, int h, int w, int cin, int cout, int ksize);
 int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* z, void* z_hi, void* z_lo,
@@ -120,9 +125,10 @@ int b200_bias_act(const float* x, const float* b, const float* xref, const float
 int b200_layer_act_fwd(const float* y, float* z /* may be NULL */, void* z_hi_bf16 /* may be NULL */, void* z_lo_bf16,
                        const float* bias, const float* noise, const float* strength, long noise_bs,
                        int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream);
-/* Backward from the saved OUTPUT z (bias_act.cu:73-77,143-145): dy, plus ACCUMULATED dbias[c], dstrength[1], dnoise (any NULL). */
-int b200_layer_act_bwd(const float* dz, const float* z, float* dy /* may be NULL */, void* dy_hi_bf16 /* may be NULL */,
-                       void* dy_lo_bf16, float* dbias, const float* noise, const float* strength,
+/* Backward from the saved OUTPUT (bias_act.cu:73-77,143-145): dy, plus ACCUMULATED dbias[c], dstrength[1], dnoise (any NULL).
+ * The output comes as fp32 z or, when z is NULL, as its split-bf16 copy z_hi (+ z_lo, read only where z_hi reaches the clamp). */
+int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi_bf16, const void* z_lo_bf16, float* dy /* may be NULL */,
+                       void* dy_hi_bf16 /* may be NULL */, void* dy_lo_bf16, float* dbias, const float* noise, const float* strength,
                        long noise_bs, float* dstrength, float* dnoise, int n, int hw, int c, int lrelu, float alpha, float gain,
                        float clamp, void* stream);
 

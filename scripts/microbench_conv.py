@@ -16,10 +16,24 @@ def bf(*shape):
 ONCE = '--once' in sys.argv          # ncu captures: launch every kernel exactly once
 
 
+COLD = '--cold' in sys.argv          # flush the L2 (write 512 MB) before every timed launch: operands come from HBM as in the step
+_flush = torch.empty(128 * 1024 * 1024, device=dev, dtype=torch.float32) if COLD else None
+
+
 def timeit(fn, name, flops, iters=10):
     fn(); torch.cuda.synchronize()
     if ONCE:
         return
+    if COLD:
+        ts = []
+        for _ in range(5):
+            _flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[2]
+        print(f'{name:46s} {ms * 1e3:8.1f} us   {flops / ms / 1e9:8.1f} TFLOP/s (algorithmic, cold L2)')
+        return ms
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):

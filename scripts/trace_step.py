@@ -40,3 +40,28 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
     out.append(f'{v[1] / N / 1e3:9.3f} ms {v[0] / N:7.1f} launches {100 * v[1] / tot:6.2f}%  {k}')
 print('\n'.join(out))
 open(os.path.join(ROOT, 'gpurun_out', 'trace_step_pdl%s_ov%s.txt' % (os.environ.get('B200EG3D_PDL', '1'), os.environ.get('B200EG3D_OVERLAP', '1'))), 'w').write('\n'.join(out) + '\n')
+
+# ---- timeline of the LAST replay: start, duration, stream of every kernel; idle gaps of the union; per-stream busy time
+try:
+    kev = [e for e in prof.profiler.kineto_results.events() if e.device_type() == torch.autograd.DeviceType.CUDA and e.duration_ns() > 0]
+    kev.sort(key=lambda e: e.start_ns())
+    per = len(kev) // N
+    last = kev[-per:]
+    t0 = last[0].start_ns()
+    lines, busy_end, idle, streams = [], t0, 0.0, collections.defaultdict(float)
+    for e in last:
+        s, d = e.start_ns() - t0, e.duration_ns()
+        gap = e.start_ns() - busy_end
+        if gap > 0:
+            idle += gap
+        busy_end = max(busy_end, e.start_ns() + d)
+        streams[e.device_resource_id()] += d
+        nm = e.name().replace('(anonymous namespace)::', '').replace('void ', '').split('(')[0][:60]
+        lines.append(f'{s / 1e3:9.1f} us  +{d / 1e3:7.1f} us  stream {e.device_resource_id():3d}  {"gap %.1f" % (gap / 1e3) if gap > 1500 else "":10s} {nm}')
+    span = busy_end - t0
+    head = [f'# timeline of one graph replay: span {span / 1e6:.3f} ms, no kernel running for {idle / 1e6:.3f} ms of it',
+            '# busy time per stream (ms): ' + ', '.join(f'{k}: {v / 1e6:.3f}' for k, v in sorted(streams.items()))]
+    open(os.path.join(ROOT, 'gpurun_out', 'timeline_step.txt'), 'w').write('\n'.join(head + lines) + '\n')
+    print('\n'.join(head))
+except Exception as ex:                      # profiler internals differ between torch versions
+    print('timeline unavailable:', ex)

@@ -565,3 +565,83 @@ def test_conv_tc_pair_tiles_match_single_cta(b2, kind, n, h, w, cin, cout, k, up
     assert maxdiff(outs[0], outs[1]) <= 1e-6 * float(outs[1].abs().max()), maxdiff(outs[0], outs[1])
     if ref is not None:
         assert relerr(outs[0], ref) < 2e-5, relerr(outs[0], ref)
+
+
+# ---------------------------------------------------------------------------------------------- lean activations (no fp32 copy)
+
+@pytest.mark.parametrize('c', [64, 128, 256, 20])
+def test_layer_act_bwd_from_split_output_matches_fp32_output(b2, c):
+    """b200_layer_act_bwd with the saved output given as its split-bf16 pair (hi decides the sign, hi + lo the clamp test, read only
+    where hi reaches the clamp) == the same call with the fp32 output, including values AT the clamp and just below it."""
+    from b200eg3d._lib import call, ptr, stream
+    g = gen(c)
+    n, hw, clamp, gain = 2, 37 * 23, 2.0, math.sqrt(2)
+    z = (torch.randn(n, hw, c, generator=g) * 1.5).clamp(-clamp, clamp)
+    flat = z.view(-1)
+    flat[::7] = clamp                                   # clamped from above
+    flat[1::11] = -clamp
+    flat[2::13] = clamp - 1e-3                          # rounds UP to the clamp in bf16, but is not clamped
+    flat[3::17] = -(clamp - 3e-4)
+    flat[4::19] = 0.0
+    z = z.cuda()
+    dz = torch.randn(n, hw, c, generator=g).cuda()
+    noise = torch.randn(hw, generator=g).cuda()
+    strength = torch.full([], 0.4).cuda()
+    zh, zl = b2.ops._split(z, True) if c % 4 == 0 else (z.to(torch.bfloat16), (z - z.to(torch.bfloat16).float()).to(torch.bfloat16))
+    res = []
+    for zr in ((ptr(z), None, None), (None, ptr(zh), ptr(zl))):
+        dy = torch.empty_like(dz)
+        dbias, dstr, dnoise = torch.zeros(c, device='cuda'), torch.zeros([], device='cuda'), torch.zeros_like(noise)
+        call('b200_layer_act_bwd', ptr(dz), *zr, ptr(dy), None, None, ptr(dbias), ptr(noise), ptr(strength), 0, ptr(dstr), ptr(dnoise),
+             n, hw, c, 1, 0.2, gain, clamp, stream())
+        res.append((dy, dbias, dstr, dnoise))
+    assert maxdiff(res[0][0], res[1][0]) == 0.0
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert relerr(a, b) < 1e-5
+    ref = dz * gain * torch.where(z > 0, 1.0, 0.2) * (z.abs() < clamp)
+    assert maxdiff(res[1][0], ref) < 1e-6
+
+
+def test_conv1x1_wgrad_from_split_input(b2):
+    from b200eg3d._lib import call, ptr, stream
+    g = gen(3)
+    n, npix, cin, cout = 2, 4099, 64, 3
+    x = torch.randn(n, npix, cin, generator=g).cuda()
+    dy = torch.randn(n, npix, cout, generator=g).cuda()
+    xh, xl = b2.ops._split(x, True)
+    dw = torch.empty(n, 1, cout, cin, device='cuda')
+    call('b200_conv1x1_wgrad_split', ptr(xh), ptr(xl), ptr(dy), ptr(dw), n, npix, cin, cout, stream())
+    ref = torch.einsum('npo,npi->noi', dy.double(), (xh.double() + xl.double()))
+    assert relerr(dw[:, 0], ref) < 1e-5
+    assert relerr(dw[:, 0], torch.einsum('npo,npi->noi', dy.double(), x.double())) < 1e-4
+
+
+def test_lean_activations_match_fp32_copies(b2, monkeypatch, golden_dir):
+    """ops.CONFIG['lean_acts']: activations between tensor-core layers exist only as their split-bf16 pair (the layer's fp32 output is a
+    shape-only placeholder).  Image, raw image and every gradient must equal the path that keeps the fp32 copies."""
+    import synth_params as sp
+    from golden_util import load_case
+    case = load_case(golden_dir, 'full_r64_s16')
+    G = b2.TriPlaneGenerator(rendering_kwargs=case.rk, **case.gk).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), case.param_seed)
+    G = G.cuda().float()
+    G.neural_rendering_resolution = case.R
+    G.renderer.fixed_noise = (case.u_strat.cuda(), case.u_imp.cuda())
+    ws, c = case.ws.cuda(), case.c.cuda()
+    named = [(n, p) for n, p in G.named_parameters() if '.mapping.' not in n]
+    outs = []
+    for lean in (True, False):
+        monkeypatch.setitem(b2.ops.CONFIG, 'lean_acts', lean)
+        for _, p in named:
+            p.grad = None
+        out = G.synthesis(ws, c, noise_mode='const')
+        (out['image'].square().mean() + out['image_raw'].square().mean()).backward()
+        torch.cuda.synchronize()
+        outs.append((out['image'].detach().clone(), out['image_raw'].detach().clone(), [p.grad.clone() if p.grad is not None else None for _, p in named]))
+    # two forward passes differ by the order of the split-K atomics of the 4x4 .. 32x32 blocks (~1e-7), which the importance
+    # sampling amplifies: a few 1e-5 between ANY two runs
+    assert maxdiff(outs[0][0], outs[1][0]) < 2e-4 and maxdiff(outs[0][1], outs[1][1]) < 2e-4
+    for (n, _), a, b in zip(named, outs[0][2], outs[1][2]):
+        if a is None or a.ndim < 2:
+            continue        # scalar / vector gradients are cancellation-dominated (atomic order), see test_wgrad_pool_and_stream_match_serial_path
+        assert relerr(a, b) < 1e-2, (n, relerr(a, b))
