@@ -8,12 +8,24 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 
+// o[0..3] -> hi = bf16(o), lo = bf16(o - hi), stored as two 8-byte vectors (packed two-at-a-time conversions: F2FP.BF16)
 __device__ __forceinline__ void split4(const float* o, uint2* hi, uint2* lo, long i) {
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { h[j] = __float2bfloat16_rn(o[j]); l[j] = __float2bfloat16_rn(o[j] - __bfloat162float(h[j])); }
-    if (hi) hi[i] = *reinterpret_cast<uint2*>(h);
-    if (lo) lo[i] = *reinterpret_cast<uint2*>(l);
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[0], o[1]), h23 = __floats2bfloat162_rn(o[2], o[3]);
+    if (hi) hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (lo) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(o[0] - f01.x, o[1] - f01.y), l23 = __floats2bfloat162_rn(o[2] - f23.x, o[3] - f23.y);
+        lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
+}
+
+// SynthesisLayer activation tail: leaky relu (slope alpha in [0, 1]: max(t, alpha t)), gain, symmetric clamp (clamp < 0: none)
+__device__ __forceinline__ float lrelu_gain_clamp(float t, bool lrelu01, int lrelu, float alpha, float gain, float clamp) {
+    if (lrelu01) t = fmaxf(t, t * alpha);
+    else if (lrelu) t = t > 0.f ? t : t * alpha;
+    t *= gain;
+    if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
+    return t;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -388,6 +400,93 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
     if (noise && dstrength && threadIdx.x == 0) atomicAdd(dstrength, s_str);
 }
 
+// The same backward, specialised at compile time on where the saved output comes from (fp32 / split pair), where dy goes (fp32 /
+// split pair), whether there is a noise input and how many 4-channel vectors a thread owns (VPT: a pixel's c/4/VPT threads are lanes
+// of one warp, so its channel sum is a few shuffles): 32-bit indices, no run-time flag tests in the element loop.
+// (ncu on the generic kernel: 43 instructions per element, a third of them flag tests and 64-bit index math.)
+template <bool ZSPLIT, bool OSPLIT, bool NOISE, int VPT>
+__global__ void __launch_bounds__(256) layer_act_bwd_fast_kernel(const float4* __restrict__ dz, const float4* __restrict__ z,
+                                                                 const uint2* __restrict__ zhi, const uint2* __restrict__ zlo,
+                                                                 float4* __restrict__ dy, uint2* __restrict__ dyhi, uint2* __restrict__ dylo,
+                                                                 float* __restrict__ dbias, const float* __restrict__ noise,
+                                                                 const float* __restrict__ strength, unsigned noise_bs,
+                                                                 float* __restrict__ dstrength, float* __restrict__ dnoise, unsigned npix,
+                                                                 unsigned hw, int c4, float gain_neg, float gain, float clamp) {
+    __shared__ float s_col[512];
+    __shared__ float s_str;
+    pdl_trigger();
+    pdl_wait();
+    const unsigned L = (unsigned)c4 / VPT;                 // threads per pixel
+    const unsigned ppb = 256u / L, sub = threadIdx.x / L, cc = threadIdx.x % L;
+    const bool active = sub < ppb;
+    for (int i = threadIdx.x; i < 4 * c4; i += 256) s_col[i] = 0.f;
+    if (threadIdx.x == 0) s_str = 0.f;
+    __syncthreads();
+    const float str = NOISE ? *strength : 0.f;
+    const bool clamp_on = clamp >= 0.f;
+    float col[VPT][4];
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) col[k][0] = col[k][1] = col[k][2] = col[k][3] = 0.f;
+    float sacc = 0.f;
+    for (unsigned p0 = blockIdx.x * ppb; p0 < npix; p0 += gridDim.x * ppb) {
+        const unsigned pix = p0 + sub;
+        const bool ok = active && pix < npix;
+        float r = 0.f;
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                const unsigned i = pix * (unsigned)c4 + cc + k * L;
+                const float4 dd = __ldg(dz + i);
+                float zv[4];
+                if (ZSPLIT) {
+                    const uint2 h2 = __ldg(zhi + i);
+                    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h2.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&h2.y));
+                    zv[0] = a.x; zv[1] = a.y; zv[2] = b.x; zv[3] = b.y;
+                    // hi alone decides the sign; the clamp test needs hi + lo only where hi itself reaches the clamp
+                    if (clamp_on && fmaxf(fmaxf(fabsf(zv[0]), fabsf(zv[1])), fmaxf(fabsf(zv[2]), fabsf(zv[3]))) >= clamp) {
+                        const uint2 l2 = __ldg(zlo + i);
+                        const float2 la = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l2.x)), lb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&l2.y));
+                        zv[0] += la.x; zv[1] += la.y; zv[2] += lb.x; zv[3] += lb.y;
+                    }
+                } else {
+                    const float4 zz = __ldg(z + i);
+                    zv[0] = zz.x; zv[1] = zz.y; zv[2] = zz.z; zv[3] = zz.w;
+                }
+                const float d4[4] = {dd.x, dd.y, dd.z, dd.w};
+                float g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float t = d4[j] * (zv[j] > 0.f ? gain : gain_neg);
+                    if (clamp_on) t = fabsf(zv[j]) < clamp ? t : 0.f;
+                    g[j] = t;
+                    col[k][j] += t;
+                }
+                if (NOISE) r += (g[0] + g[1]) + (g[2] + g[3]);
+                if (OSPLIT) split4(g, dyhi, dylo, i);
+                else dy[i] = make_float4(g[0], g[1], g[2], g[3]);
+            }
+        }
+        if (NOISE) {                                  // per-pixel sum over channels -> d noise, d strength (L is a power of two <= 32 here)
+            for (unsigned o = L >> 1; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+            if (cc == 0 && ok) {
+                const unsigned q = pix / hw, nidx = q * noise_bs + (pix - q * hw);
+                sacc = fmaf(r, __ldg(noise + nidx), sacc);
+                if (dnoise) atomicAdd(dnoise + nidx, r * str);
+            }
+        }
+    }
+    if (dbias && active) {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(&s_col[(cc + k * L) * 4 + j], col[k][j]);
+    }
+    if (NOISE && dstrength && sacc != 0.f) atomicAdd(&s_str, sacc);
+    __syncthreads();
+    if (dbias) for (int i = threadIdx.x; i < 4 * c4; i += 256) atomicAdd(dbias + i, s_col[i]);
+    if (NOISE && dstrength && threadIdx.x == 0) atomicAdd(dstrength, s_str);
+}
+
 B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi, void* dy_lo,
                                 float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise,
                                 int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
@@ -403,6 +502,30 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_h
         const int c4 = c / 4, ppb = 256 / c4;
         const long nb = (npix + ppb - 1) / ppb;
         const int blocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
+        const bool osplit = dy_hi && dy_lo && !dy, ofp32 = dy && !dy_hi;
+        const bool zsplit = !z;
+        // vectors per thread: keep a pixel's threads inside one warp (needed for the shuffle sum when there is a noise input)
+        const int vpt = c4 <= 32 ? 1 : (c4 <= 64 ? 2 : 4);
+        const int lanes = c4 / vpt;
+        const bool pow2 = (lanes & (lanes - 1)) == 0;
+        if (c4 % vpt == 0 && lanes <= 32 && (pow2 || !noise) && npix * c4 < (1L << 31) && (osplit || ofp32) && (!noise || strength) &&
+            (zsplit ? (z_lo != nullptr || clamp < 0.f) : true) && (long)n * noise_bs < (1L << 31)) {
+            const float gneg = lrelu ? gain * alpha : gain;
+            const int ppb2 = 256 / lanes;
+            const long nb2 = (npix + ppb2 - 1) / ppb2;
+            const int blocks2 = (int)(nb2 < 148 * 8 ? nb2 : 148 * 8);
+#define LAUNCH_F(ZS, OS, NZ, V) B200_CUDA(launch_pdl(layer_act_bwd_fast_kernel<ZS, OS, NZ, V>, dim3(blocks2), dim3(256), 0, st, (const float4*)dz, \
+                (const float4*)z, (const uint2*)z_hi, (const uint2*)z_lo, (float4*)dy, (uint2*)dy_hi, (uint2*)dy_lo, dbias, noise, strength, \
+                (unsigned)noise_bs, dstrength, dnoise, (unsigned)npix, (unsigned)hw, c4, gneg, gain, clamp))
+#define LAUNCH_V(ZS, OS, NZ) do { if (vpt == 1) LAUNCH_F(ZS, OS, NZ, 1); else if (vpt == 2) LAUNCH_F(ZS, OS, NZ, 2); else LAUNCH_F(ZS, OS, NZ, 4); } while (0)
+            if (zsplit) { if (osplit) { if (noise) LAUNCH_V(true, true, true); else LAUNCH_V(true, true, false); }
+                          else { if (noise) LAUNCH_V(true, false, true); else LAUNCH_V(true, false, false); } }
+            else { if (osplit) { if (noise) LAUNCH_V(false, true, true); else LAUNCH_V(false, true, false); }
+                   else { if (noise) LAUNCH_V(false, false, true); else LAUNCH_V(false, false, false); } }
+#undef LAUNCH_V
+#undef LAUNCH_F
+            return 0;
+        }
         B200_CUDA(launch_pdl(layer_act_bwd_vec_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)dz, (const float4*)z, (const uint2*)z_hi,
                              (const uint2*)z_lo, (float4*)dy, (uint2*)dy_hi,
                              (uint2*)dy_lo, dbias, noise, strength, noise_bs, dstrength, dnoise, npix, hw, c4, lrelu, alpha, gain, clamp));
@@ -431,6 +554,7 @@ struct UpfirdnParams {
     float gain;
     // optional SynthesisLayer epilogue applied to the filtered value (act != 0)
     int act; const float* bias; const float* noise; const float* strength; long noise_bs; int lrelu; float alpha, act_gain, clamp;
+    int separable;          // caller's guarantee: f[a][q] = f[a][0] * f[0][q] / f[0][0] (the [1,3,3,1] x [1,3,3,1] resampling filter)
 };
 
 // V = channels per thread (4 or 1).  F > 0: square FxF filter with compile-time UP / DOWN (fully unrolled taps);
@@ -473,7 +597,19 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
                 acc[0] = fmaf(g, __ldg(src), acc[0]);
             }
         };
-        if (F > 0) {
+        if (F == 4 && UP == 2 && DOWN == 1) {
+            // zero-insertion upsampling: only the taps whose parity matches the output position land on an input sample (2 x 2 of
+            // the 16); pick their rows / columns by parity instead of testing all 16
+            const int a0 = (p.pady0 - oy) & 1, q0 = (p.padx0 - ox) & 1;
+#pragma unroll
+            for (int ia = 0; ia < 2; ++ia)
+#pragma unroll
+                for (int iq = 0; iq < 2; ++iq) {
+                    const float ge = q0 ? fr[(2 * ia) * 4 + 2 * iq + 1] : fr[(2 * ia) * 4 + 2 * iq];
+                    const float go = q0 ? fr[(2 * ia + 1) * 4 + 2 * iq + 1] : fr[(2 * ia + 1) * 4 + 2 * iq];
+                    tap(a0 + 2 * ia, q0 + 2 * iq, a0 ? go : ge);
+                }
+        } else if (F > 0) {
 #pragma unroll
             for (int a = 0; a < F; ++a)
 #pragma unroll
@@ -515,6 +651,111 @@ __global__ void upfirdn2d_kernel(UpfirdnParams p) {
             if (p.yhi) split4(out, p.yhi, p.ylo, o / 4);
         } else {
             p.y[o] = out[0];
+        }
+    }
+}
+
+// Separable 4x4 FIR at unit rate as a sliding window down a column strip: one thread owns SW output columns x 4 channels and walks
+// SH output rows.  Every input row is loaded once (SW + 3 vector loads), filtered horizontally (4 taps) into a ring of the last four
+// h-rows, and each output row is the 4-tap vertical combination of the ring: 8 FMA per output element instead of 16 in the 2 x 4
+// patch kernel below (ncu: 67 instructions per element there, most of them index arithmetic and the epilogue's selects).
+template <int SH, int SW>
+__global__ void __launch_bounds__(128) fir4_col_kernel(UpfirdnParams p) {
+    pdl_trigger();
+    pdl_wait();
+    const unsigned cv = p.c >> 2;
+    const unsigned sxn = (p.ow + SW - 1) / SW, syn = (p.oh + SH - 1) / SH;
+    const unsigned total = (unsigned)p.n * syn * sxn * cv;
+    // effective filter (flip, gain) and its separable factors: fr[a][q] = u[a] * v[q]
+    float u[4], v[4];
+    {
+        const float f00 = (p.flip ? p.f[0] : p.f[15]) * p.gain;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[k] = (p.flip ? p.f[k] : p.f[15 - k]) * p.gain;
+            u[k] = (p.flip ? p.f[4 * k] : p.f[15 - 4 * k]) * p.gain / f00;
+        }
+    }
+    const float str = (p.act && p.noise && p.strength) ? *p.strength : 0.f;
+    const bool lrelu01 = p.lrelu && p.alpha >= 0.f && p.alpha <= 1.f;
+    const int pitch = p.w * p.c;                              // elements per input row (launch_upfirdn: tensors < 2^31 elements)
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int cc = (int)(i % cv) * 4;
+        unsigned r = i / cv;
+        const int ox0 = (int)(r % sxn) * SW; r /= sxn;
+        const int oy0 = (int)(r % syn) * SH;
+        const int b = (int)(r / syn);
+        const int ixb = ox0 - p.padx0;
+        const float* xb = p.x + (long)b * p.h * pitch + cc + (long)ixb * p.c;       // first column of the window (may lie left of the image)
+        const bool xin = ixb >= 0 && ixb + SW + 3 <= p.w;                           // every window column inside: no per-load tests
+        float bb[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.act && p.bias) { const float4 bv = *reinterpret_cast<const float4*>(p.bias + cc); bb[0] = bv.x; bb[1] = bv.y; bb[2] = bv.z; bb[3] = bv.w; }
+
+        // input row iy -> registers (zero outside the image: upfirdn2d zero padding); issued one row ahead of its use
+        auto load_row = [&](int iy, float4 (&row)[SW + 3]) {
+            const bool yin = iy >= 0 && iy < p.h;
+            const float* rowp = xb + (yin ? iy : 0) * pitch;
+            if (yin && xin) {
+#pragma unroll
+                for (int rx = 0; rx < SW + 3; ++rx) row[rx] = __ldg(reinterpret_cast<const float4*>(rowp + rx * p.c));
+            } else {
+#pragma unroll
+                for (int rx = 0; rx < SW + 3; ++rx) {
+                    const int ix = ixb + rx;
+                    row[rx] = (yin && ix >= 0 && ix < p.w) ? __ldg(reinterpret_cast<const float4*>(rowp + rx * p.c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        };
+        // horizontal 4-tap pass: row -> h[0..SW)
+        auto filt = [&](const float4 (&row)[SW + 3], float4 (&h)[SW]) {
+#pragma unroll
+            for (int xx = 0; xx < SW; ++xx) {
+                h[xx] = make_float4(v[0] * row[xx].x, v[0] * row[xx].y, v[0] * row[xx].z, v[0] * row[xx].w);
+#pragma unroll
+                for (int q = 1; q < 4; ++q) {
+                    h[xx].x = fmaf(v[q], row[xx + q].x, h[xx].x); h[xx].y = fmaf(v[q], row[xx + q].y, h[xx].y);
+                    h[xx].z = fmaf(v[q], row[xx + q].z, h[xx].z); h[xx].w = fmaf(v[q], row[xx + q].w, h[xx].w);
+                }
+            }
+        };
+        // output row oy = u0 * ha + u1 * hb + u2 * hc + u3 * hd (h-rows of input rows oy - pady0 .. oy - pady0 + 3), then the consumers
+        auto emit = [&](int oy, const float4 (&ha)[SW], const float4 (&hb)[SW], const float4 (&hc)[SW], const float4 (&hd)[SW]) {
+            if (oy >= p.oh) return;
+            const long orow = (((long)b * p.oh + oy) * p.ow + ox0) * p.c + cc;
+            const float* nzp = (p.act && p.noise) ? p.noise + (long)b * p.noise_bs + (long)oy * p.ow + ox0 : nullptr;
+#pragma unroll
+            for (int xx = 0; xx < SW; ++xx) {
+                if (ox0 + xx >= p.ow) continue;
+                float out[4];
+                out[0] = fmaf(u[0], ha[xx].x, fmaf(u[1], hb[xx].x, fmaf(u[2], hc[xx].x, u[3] * hd[xx].x)));
+                out[1] = fmaf(u[0], ha[xx].y, fmaf(u[1], hb[xx].y, fmaf(u[2], hc[xx].y, u[3] * hd[xx].y)));
+                out[2] = fmaf(u[0], ha[xx].z, fmaf(u[1], hb[xx].z, fmaf(u[2], hc[xx].z, u[3] * hd[xx].z)));
+                out[3] = fmaf(u[0], ha[xx].w, fmaf(u[1], hb[xx].w, fmaf(u[2], hc[xx].w, u[3] * hd[xx].w)));
+                const long o = orow + xx * p.c;
+                if (p.add) { const float4 ad = __ldg(reinterpret_cast<const float4*>(p.add + o)); out[0] += ad.x; out[1] += ad.y; out[2] += ad.z; out[3] += ad.w; }
+                if (p.act) {
+                    const float nz = nzp ? __ldg(nzp + xx) * str : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) out[j] = lrelu_gain_clamp(out[j] + (nz + bb[j]), lrelu01, p.lrelu, p.alpha, p.act_gain, p.clamp);
+                }
+                if (p.y) *reinterpret_cast<float4*>(p.y + o) = make_float4(out[0], out[1], out[2], out[3]);
+                if (p.yhi) split4(out, p.yhi, p.ylo, o >> 2);
+            }
+        };
+
+        float4 h0[SW], h1[SW], h2[SW], h3[SW], ra[SW + 3], rb[SW + 3];
+        const int iy0 = oy0 - p.pady0;
+        load_row(iy0, ra); load_row(iy0 + 1, rb);
+        filt(ra, h0); load_row(iy0 + 2, ra);
+        filt(rb, h1); load_row(iy0 + 3, rb);
+        filt(ra, h2); load_row(iy0 + 4, ra);
+#pragma unroll 1
+        for (int g = 0; g < SH; g += 4) {
+            if (oy0 + g >= p.oh) break;
+            filt(rb, h3); load_row(iy0 + g + 5, rb); emit(oy0 + g, h0, h1, h2, h3);
+            filt(ra, h0); load_row(iy0 + g + 6, ra); emit(oy0 + g + 1, h1, h2, h3, h0);
+            filt(rb, h1); load_row(iy0 + g + 7, rb); emit(oy0 + g + 2, h2, h3, h0, h1);
+            filt(ra, h2); load_row(iy0 + g + 8, ra); emit(oy0 + g + 3, h3, h0, h1, h2);
         }
     }
 }
@@ -622,7 +863,25 @@ static int launch_upfirdn(UpfirdnParams& p, int padx1, int pady1, cudaStream_t s
 #ifndef B200_FIR_STRIP_MIN
 #define B200_FIR_STRIP_MIN (148L * 256)
 #endif
-        if (strips >= B200_FIR_STRIP_MIN) {
+#ifndef B200_FIR_SW
+#define B200_FIR_SW 2
+#endif
+#ifndef B200_FIR_T16
+#define B200_FIR_T16 4096
+#endif
+        constexpr int SW = B200_FIR_SW;
+        if (p.separable && (long)p.n * ((p.oh + 7) / 8) * ((p.ow + SW - 1) / SW) * (p.c / 4) >= 148L * 256) {
+            // column strips: 16 rows per thread when that still leaves >= 8 warps per SM, else 8
+            const long t16 = (long)p.n * ((p.oh + 15) / 16) * ((p.ow + SW - 1) / SW) * (p.c / 4);
+            if (t16 >= 148L * B200_FIR_T16) {
+                const int cb = (int)((t16 + 127) / 128 < 148 * 64 ? (t16 + 127) / 128 : 148 * 64);
+                B200_CUDA(launch_pdl(fir4_col_kernel<16, SW>, dim3(cb), dim3(128), 0, st, p));
+            } else {
+                const long t8 = (long)p.n * ((p.oh + 7) / 8) * ((p.ow + SW - 1) / SW) * (p.c / 4);
+                const int cb = (int)((t8 + 127) / 128 < 148 * 64 ? (t8 + 127) / 128 : 148 * 64);
+                B200_CUDA(launch_pdl(fir4_col_kernel<8, SW>, dim3(cb), dim3(128), 0, st, p));
+            }
+        } else if (strips >= B200_FIR_STRIP_MIN) {
             const int sb = (int)((strips + 255) / 256 < 148 * 32 ? (strips + 255) / 256 : 148 * 32);
             B200_CUDA(launch_pdl(fir4_strip_kernel, dim3(sb), dim3(256), 0, st, p));
         } else {
@@ -655,8 +914,9 @@ B200_API int b200_upfirdn2d(const float* x, const float* f, const float* add, fl
 B200_API int b200_upfirdn2d_fused(const float* x, const float* f, const float* add, float* y, void* y_hi, void* y_lo, int n, int h,
                                   int w, int c, int fh, int fw, int up, int down, int padx0, int padx1, int pady0, int pady1,
                                   int flip, float gain, int act, const float* bias, const float* noise, const float* strength,
-                                  long noise_bs, int lrelu, float alpha, float act_gain, float clamp, void* stream) {
+                                  long noise_bs, int lrelu, float alpha, float act_gain, float clamp, int separable, void* stream) {
     UpfirdnParams p{};
+    p.separable = separable;
     p.x = x; p.f = f; p.add = add; p.y = y; p.yhi = (uint2*)y_hi; p.ylo = (uint2*)y_lo; p.n = n; p.h = h; p.w = w; p.c = c;
     p.fh = fh; p.fw = fw; p.upx = p.upy = up; p.downx = p.downy = down; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip; p.gain = gain;
     p.act = act; p.bias = bias; p.noise = noise; p.strength = strength; p.noise_bs = noise_bs; p.lrelu = lrelu; p.alpha = alpha;

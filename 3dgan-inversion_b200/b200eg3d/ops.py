@@ -502,7 +502,7 @@ def _bf16_like(t):
     return torch.empty(t.shape, device=t.device, dtype=torch.bfloat16)
 
 
-def _fir_fused(x, f2, up, down, pad, flip, gain, want_f32=True, want_split=False, need_lo=True, add=None, act=None):
+def _fir_fused(x, f2, up, down, pad, flip, gain, want_f32=True, want_split=False, need_lo=True, add=None, act=None, separable=False):
     """b200_upfirdn2d_fused on NHWC x.  act = (bias, noise, strength, noise_bs, act_gain, clamp) or None.
     Returns (y fp32 | None, y_hi | None, y_lo | None)."""
     n, h, w, c = x.shape
@@ -519,7 +519,7 @@ def _fir_fused(x, f2, up, down, pad, flip, gain, want_f32=True, want_split=False
         bias, noise, strength, nbs, act_gain, clamp = act
         a = (1, ptr(bias), ptr(noise), ptr(strength), nbs, 1, 0.2, float(act_gain), float(clamp))
     call('b200_upfirdn2d_fused', ptr(x), ptr(f2), ptr(add), ptr(y), ptr(yh), ptr(yl), n, h, w, c, fh, fw, up, down, px0, px1, py0, py1,
-         int(flip), float(gain), *a, stream())
+         int(flip), float(gain), *a, int(separable), stream())
     return y, yh, yl
 
 
@@ -598,7 +598,7 @@ class _ModConvLayer(torch.autograd.Function):
                 call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(zt), n, h, w, cin, cout, k, 2, fp, stream())
                 # 4x4 FIR (pad 1, gain 4) fused with the layer epilogue and the bf16 split for the next conv
                 call('b200_upfirdn2d_fused', ptr(zt), ptr(fir_filter(dev)), None, zp, ptr(z_hi), ptr(z_lo), n, 2 * h + 1, 2 * w + 1,
-                     cout, 4, 4, 1, 1, 1, 1, 1, 1, 0, 4.0, 1, ptr(b), ptr(nz), ptr(st), nbs, 1, 0.2, float(act_gain), clampf, stream())
+                     cout, 4, 4, 1, 1, 1, 1, 1, 1, 0, 4.0, 1, ptr(b), ptr(nz), ptr(st), nbs, 1, 0.2, float(act_gain), clampf, 1, stream())
             # the activation backward needs the OUTPUT (sign and clamp): the fp32 copy, or -- lean -- the split pair the consumer keeps anyway
             ctx.save_for_backward(x_hi, x_lo if CONFIG['wgrad_passes'] == 3 else None, W, s, w_hi, w_lo, dcoef,
                                   None if lean else z, nz, st, z_hi if lean else None, z_lo if lean else None)
@@ -661,7 +661,8 @@ class _ModConvLayer(torch.autograd.Function):
                 call('b200_layer_act_bwd', ptr(dzc), *zref, ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
                      ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
                 # adjoint of the FIR (pad 2, flipped filter) straight to split bf16 on the (2h+1)x(2w+1) grid
-                _, dy_hi, dy_lo = _fir_fused(dy, fir_filter(dev), 1, 1, (2, 2, 2, 2), True, 4.0, want_f32=False, want_split=True, need_lo=lo)
+                _, dy_hi, dy_lo = _fir_fused(dy, fir_filter(dev), 1, 1, (2, 2, 2, 2), True, 4.0, want_f32=False, want_split=True, need_lo=lo,
+                                             separable=True)          # fir_filter() is the outer product [1,3,3,1] x [1,3,3,1] / 64
             if need_x:
                 call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cout, k, up, dp, stream())
             if need_w:

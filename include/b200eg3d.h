@@ -141,11 +141,13 @@ int b200_upfirdn2d(const float* x, const float* f, const float* add, float* y, i
 
 /* Same filter geometry (square up / down factors) with fused consumers: act != 0 applies the SynthesisLayer epilogue
  * (+ noise*strength + bias, lrelu, act_gain, clamp: conv2d_resample.py:128 followed by networks_stylegan2.py:318-329 in one pass);
- * y (fp32) and y_hi / y_lo (split bf16 for the next tensor-core conv) are optional outputs, at least one is required. */
+ * y (fp32) and y_hi / y_lo (split bf16 for the next tensor-core conv) are optional outputs, at least one is required.
+ * separable != 0: the caller guarantees f[a][q] = f[a][0] * f[0][q] / f[0][0] (the [1,3,3,1] x [1,3,3,1] resampling filter of
+ * upfirdn2d.setup_filter); 4x4 unit-rate filters then run as a sliding column window (8 instead of 16 MACs per element). */
 int b200_upfirdn2d_fused(const float* x, const float* f, const float* add, float* y, void* y_hi_bf16, void* y_lo_bf16,
                          int n, int h, int w, int c, int fh, int fw, int up, int down, int padx0, int padx1, int pady0, int pady1,
                          int flip, float gain, int act, const float* bias, const float* noise, const float* strength,
-                         long noise_bs, int lrelu, float alpha, float act_gain, float clamp, void* stream);
+                         long noise_bs, int lrelu, float alpha, float act_gain, float clamp, int separable, void* stream);
 
 /* ---- fused tri-plane sampling + OSG decoder (renderer.py:39-66 sample_from_planes, triplane.py:124-136 OSGDecoder.forward) ---- */
 /* planes [n][hp][wp][96] (plane p = channels 32p..32p+31).  Points: coords [n][P][3], or (coords NULL) rays ray_o/ray_d

@@ -6,6 +6,7 @@ import torch
 from b200eg3d._lib import call, ptr, stream
 from b200eg3d import ops
 dev = 'cuda'
+SEP = 0 if '--patch' in sys.argv else 1          # --patch: the 2 x 4 patch kernel (non-separable path)
 f = ops.fir_filter(torch.device(dev))
 for (res, c) in [(8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 128), (256, 128), (512, 64)]:
     x = torch.randn(1, res + 1, res + 1, c, device=dev)
@@ -14,9 +15,9 @@ for (res, c) in [(8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 12
     dy = torch.randn(1, res, res, c, device=dev)
     gh = torch.empty(1, res + 1, res + 1, c, device=dev, dtype=torch.bfloat16); gl = torch.empty_like(gh)
     fwd = lambda: call('b200_upfirdn2d_fused', ptr(x), ptr(f), None, ptr(z), ptr(zh), ptr(zl), 1, res + 1, res + 1, c, 4, 4, 1, 1, 1, 1, 1, 1, 0, 4.0,
-                       1, ptr(b), ptr(nz), ptr(st), 0, 1, 0.2, 1.414, 256.0, stream())
+                       1, ptr(b), ptr(nz), ptr(st), 0, 1, 0.2, 1.414, 256.0, SEP, stream())
     bwd = lambda: call('b200_upfirdn2d_fused', ptr(dy), ptr(f), None, None, ptr(gh), ptr(gl), 1, res, res, c, 4, 4, 1, 1, 2, 2, 2, 2, 1, 4.0,
-                       0, None, None, None, 0, 0, 0.0, 1.0, -1.0, stream())
+                       0, None, None, None, 0, 0, 0.0, 1.0, -1.0, SEP, stream())
     out = []
     for fn in (fwd, bwd):
         fn(); torch.cuda.synchronize()

@@ -645,3 +645,34 @@ def test_lean_activations_match_fp32_copies(b2, monkeypatch, golden_dir):
         if a is None or a.ndim < 2:
             continue        # scalar / vector gradients are cancellation-dominated (atomic order), see test_wgrad_pool_and_stream_match_serial_path
         assert relerr(a, b) < 1e-2, (n, relerr(a, b))
+
+
+@pytest.mark.parametrize('h,w,c,pad,flip,act', [(513, 513, 64, 1, 0, True), (257, 257, 128, 1, 0, True), (256, 256, 128, 2, 1, False),
+                                                (130, 203, 64, 2, 1, False), (131, 201, 128, 1, 0, True)])
+def test_fir_column_window_matches_patch_kernel(b2, h, w, c, pad, flip, act):
+    """b200_upfirdn2d_fused with the separable hint (sliding column window, 8 MACs per element) == the 2 x 4 patch kernel and the
+    oracle's upfirdn2d on the same input: forward shape (pad 1, layer epilogue, split outputs) and adjoint shape (pad 2, flipped)."""
+    from b200eg3d._lib import call, ptr, stream
+    g = gen(h + w + c)
+    x = torch.randn(1, h, w, c, generator=g).cuda()
+    f = b2.ops.fir_filter(torch.device('cuda'))
+    oh, ow = h + 2 * pad - 3, w + 2 * pad - 3
+    bias = torch.randn(c, generator=g).cuda()
+    noise = torch.randn(oh, ow, generator=g).cuda()
+    strength = torch.full([], 0.3).cuda()
+    outs = []
+    for sep in (1, 0):
+        y = torch.full([1, oh, ow, c], float('nan'), device='cuda')
+        yh = torch.empty(1, oh, ow, c, device='cuda', dtype=torch.bfloat16)
+        yl = torch.empty_like(yh)
+        a = (1, ptr(bias), ptr(noise), ptr(strength), 0, 1, 0.2, math.sqrt(2), 1.5) if act else (0, None, None, None, 0, 0, 0.0, 1.0, -1.0)
+        call('b200_upfirdn2d_fused', ptr(x), ptr(f), None, ptr(y), ptr(yh), ptr(yl), 1, h, w, c, 4, 4, 1, 1, pad, pad, pad, pad, flip, 4.0,
+             *a, sep, stream())
+        outs.append((y, yh.float() + yl.float()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[0][0]).all()
+    assert maxdiff(outs[0][0], outs[1][0]) < 2e-5 and maxdiff(outs[0][1], outs[1][1]) < 2e-4
+    if not act:
+        ff = f.cpu().flip([0, 1]) if flip else f.cpu()          # the filter is symmetric: flipping is exercised, not distinguished
+        ref = oracle.upfirdn2d(nchw(x).cpu(), ff, pad=(pad, pad, pad, pad), gain=4.0)
+        assert maxdiff(nchw(outs[0][0]), ref) < 2e-5
