@@ -16,5 +16,6 @@ from . import seam  # noqa: F401
 from . import losses  # noqa: F401
 from . import projector  # noqa: F401
 from . import geometry  # noqa: F401
+from . import optim  # noqa: F401
 
 __version__ = '0.1.0'
