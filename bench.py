@@ -461,6 +461,8 @@ def run_b200(args):
                          ('stage1', lambda: extra_stage1(rank, world, dev)),
                          ('cfg5', lambda: extra_cfg5(rank, world, dev)),
                          ('two_in_flight', lambda: extra_two_in_flight(rank, world, dev))):
+            if name == 'two_in_flight' and world > 1:
+                continue                                # a single-GPU throughput figure; the scaling runs carry the three workloads above
             try:
                 extra[name] = fn()
             except Exception as e:                      # a secondary leg must never cost the headline number
