@@ -14,7 +14,7 @@ _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 
 # b200_version() this binding table was written for.  Bumped together with csrc/conv_api.cu whenever a prototype changes: a
 # stale or variant .so (B200EG3D_LIB) with other argument lists would otherwise be called with the wrong stack layout.
-EXPECTED_VERSION = 203
+EXPECTED_VERSION = 204
 
 # name -> argument ctypes (every function returns int status; 0 = ok)
 SIGNATURES = {
@@ -26,9 +26,9 @@ SIGNATURES = {
     'b200_bank_weights_bwd': [_P, _I, _I, _P],
     'b200_bank_styles_bwd': [_P, _I, _P, _P, _I, _I, _I, _P],
     'b200_split_bf16': [_P, _P, _P, _L, _P],
-    'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_fwd_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_fwd_tc_act': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _F, _F, _F, _P],
-    'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    'b200_conv_dgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_conv_wgrad_tc': [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'b200_adam_step': [_P, _I, _P, _F, _F, _F, _F, _F, _P, _P, _P],
     'b200_modconv_weight_prep': [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -106,6 +106,8 @@ def load():
     lib.b200_conv_tc_supported.argtypes = [_I] * 7
     lib.b200_conv1x1_thin_supported.restype = ctypes.c_int
     lib.b200_conv1x1_thin_supported.argtypes = [_I, _I]
+    lib.b200_conv_tc_ksplit.restype = ctypes.c_int
+    lib.b200_conv_tc_ksplit.argtypes = [_I] * 8
     lib.b200_conv_tc_act_fusable.restype = ctypes.c_int
     lib.b200_conv_tc_act_fusable.argtypes = [_I] * 6
     lib.b200_noise_pyramid_work_floats.restype = ctypes.c_long

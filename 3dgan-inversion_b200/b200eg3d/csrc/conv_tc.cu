@@ -660,7 +660,8 @@ static int fwd_ksplit(int n, int h, int w, int cin, int cout, int ksize) {      
 }
 
 static int conv_fwd_tc_impl(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int n, int h,
-                            int w, int cin, int cout, int ksize, int up, int npass, const FwdEpilogue* ep, void* stream) {
+                            int w, int cin, int cout, int ksize, int up, int npass, const FwdEpilogue* ep, int prezeroed, void* stream,
+                            int* ksplit_out = nullptr) {
     B200_REQUIRE(b200_conv_tc_supported(0, h, w, cin, cout, ksize, up), "conv_fwd_tc: unsupported shape");
     B200_REQUIRE(npass == 1 || (npass == 3 && x_lo && w_lo), "conv_fwd_tc: npass must be 1, or 3 with lo operands");
     cudaStream_t st = (cudaStream_t)stream;
@@ -699,6 +700,7 @@ static int conv_fwd_tc_impl(const void* x_hi, const void* x_lo, const void* w_hi
         p.ksplit = pick_ksplit(total * ntn * n, p.kchunks);      // the (1,1) class has a single tap: at least kchunks k-blocks
     }
     // CTA pairs for the layers that fill the machine without split-K; 256-wide N tiles when the list stays long enough
+    if (ksplit_out) { *ksplit_out = p.ksplit; return 0; }        // planning query (b200_conv_tc_ksplit): no launch
     if (p.ksplit == 1 && conv_pair_enabled() && max_pairs<false>() > 0) {
         long ptiles = 0;
         for (int k = 0; k < p.ncls; ++k) ptiles += (tiles[k] + 1) / 2;
@@ -721,13 +723,27 @@ static int conv_fwd_tc_impl(const void* x_hi, const void* x_lo, const void* w_hi
         p.alpha = ep->alpha; p.act_gain = ep->act_gain; p.clamp = ep->clamp;
         p.z_hi = (__nv_bfloat16*)ep->z_hi; p.z_lo = (__nv_bfloat16*)ep->z_lo;
     }
-    if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * p.c_bs, st));
+    if (p.ksplit > 1 && !prezeroed) B200_CUDA(cudaMemsetAsync(y, 0, sizeof(float) * (size_t)n * p.c_bs, st));
     return launch_pix<false>(p, n, st);
 }
 
+// prezeroed != 0: y is already zero (one fill for all split-K outputs of a network, made by the caller): a split-K launch then adds its
+// partial sums without clearing y first.  Launches that do not split K overwrite y either way.
 B200_API int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y, int n, int h,
-                              int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
-    return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, y, n, h, w, cin, cout, ksize, up, npass, nullptr, stream);
+                              int w, int cin, int cout, int ksize, int up, int npass, int prezeroed, void* stream) {
+    return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, y, n, h, w, cin, cout, ksize, up, npass, nullptr, prezeroed, stream);
+}
+
+// Split-K factor the forward (kind 0) / dgrad (kind 1) launch of this shape uses (1: the output is overwritten, > 1: partial sums are
+// added with red.global and the output has to start at zero).  Lets a caller pool the zero-initialised outputs of a whole network.
+static int dgrad_ksplit(int n, int h, int w, int cin, int cout, int ksize);
+B200_API int b200_conv_tc_ksplit(int kind, int n, int h, int w, int cin, int cout, int ksize, int up) {
+    if (!b200_conv_tc_supported(kind, h, w, cin, cout, ksize, up) || n <= 0) return 1;
+    if (kind == 1) return dgrad_ksplit(n, h, w, cin, cout, ksize);
+    if (kind != 0) return 1;
+    int ks = 1;
+    if (conv_fwd_tc_impl(nullptr, nullptr, nullptr, nullptr, nullptr, n, h, w, cin, cout, ksize, up, 1, nullptr, 0, nullptr, &ks)) return 1;
+    return ks;
 }
 
 // 1 when b200_conv_fwd_tc_act can fuse the SynthesisLayer epilogue into the convolution's TMEM drain for this shape.
@@ -750,12 +766,19 @@ B200_API int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void
                                   void* stream) {
     B200_REQUIRE(z_hi, "conv_fwd_tc_act: the split-bf16 output is required (z may be NULL)");
     FwdEpilogue ep{bias, noise, strength, noise_bs, alpha, act_gain, clamp, z_hi, z_lo};
-    return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, z, n, h, w, cin, cout, ksize, 1, npass, &ep, stream);
+    return conv_fwd_tc_impl(x_hi, x_lo, w_hi, w_lo, z, n, h, w, cin, cout, ksize, 1, npass, &ep, 0, stream);
 }
 
 // dgrad on split-bf16 operands.  dy_* bf16 ([h][w][cout], or the (2h+1)x(2w+1) grid when up == 2), w_* as above, dx fp32.
+static int dgrad_ksplit(int n, int h, int w, int cin, int cout, int ksize) {
+    int th, tw;
+    pick_tile(h, w, th, tw);
+    const int tiles0 = ((w + tw - 1) / tw) * ((h + th - 1) / th), bn = cin > 64 ? 128 : 64;
+    return pick_ksplit(tiles0 * ((cin + bn - 1) / bn) * n, ksize * ksize * ((cout + 63) / 64));
+}
+
 B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx, int n,
-                                int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream) {
+                                int h, int w, int cin, int cout, int ksize, int up, int npass, int prezeroed, void* stream) {
     B200_REQUIRE(b200_conv_tc_supported(1, h, w, cin, cout, ksize, up), "conv_dgrad_tc: unsupported shape");
     B200_REQUIRE(npass == 1 || (npass == 3 && dy_lo && w_lo), "conv_dgrad_tc: npass must be 1, or 3 with lo operands");
     cudaStream_t st = (cudaStream_t)stream;
@@ -786,7 +809,7 @@ B200_API int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void
         else if (pair_fills(ptiles * ((cin + 127) / 128) * n)) { p.cg = 2; p.BN = 128; }
     }
     p.cta_start[0] = 0; p.cta_start[1] = (p.cg == 2 ? (tiles0 + 1) / 2 : tiles0) * p.ksplit;
-    if (p.ksplit > 1) B200_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)n * h * w * cin, st));
+    if (p.ksplit > 1 && !prezeroed) B200_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)n * h * w * cin, st));
     return launch_pix<true>(p, n, st);
 }
 

@@ -329,7 +329,7 @@ class SynthesisNetwork(torch.nn.Module):
         side = ops.side_stream(ws.device) if (ops.CONFIG['overlap'] and bank is not None and ws.is_cuda) else None
         if side is not None:
             bank.side = side
-            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool]:
+            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool, bank.zf, bank.zb]:
                 if t is not None:
                     t.record_stream(side)
         for i, (res, cur_ws) in enumerate(zip(self.block_resolutions, block_ws)):
@@ -397,7 +397,7 @@ class SuperresolutionHybrid8X(torch.nn.Module):
         if side is not None:
             bank.side = side
             side.wait_stream(torch.cuda.current_stream())           # rgb (skip input) and the bank were produced on the main stream
-            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool, rgb]:
+            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + [bank.zpool, bank.zf, bank.zb, rgb]:
                 if t is not None:
                     t.record_stream(side)
         x, rgb, sp = self.block0(x, rgb, ws, return_split=True, bank=bank, bank_base=0, side=side, lean_out=True, **block_kwargs)

@@ -45,6 +45,8 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           # inside a synthesis network keep activations only as the split-bf16 pair the next tensor-core conv reads: no fp32 copy is
           # written by the layer epilogues or re-read by the activation backward (the returned fp32 tensor is then a placeholder)
           'lean_acts': os.environ.get('B200EG3D_LEAN_ACTS', '1') != '0',
+          # one zero fill per network pass for the outputs of all split-K convolutions instead of a memset before each launch
+          'zero_pools': os.environ.get('B200EG3D_ZERO_POOLS', '1') != '0',
           'ranges': os.environ.get('B200EG3D_RANGES', '0') != '0'}
 
 
@@ -90,7 +92,7 @@ def _conv_fwd(x, wmod, y, n, h, w, cin, cout, k, up):
         npass = CONFIG['fwd_passes']
         xh, xl = _split(x, npass == 3)
         wh, wl = _split(wmod, npass == 3)
-        call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, npass, stream())
+        call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, npass, 0, stream())
     else:
         call('b200_conv_fwd', ptr(x), ptr(wmod), ptr(y), n, h, w, cin, cout, k, up, stream())
 
@@ -100,7 +102,7 @@ def _conv_dgrad(dy, wmod, dx, n, h, w, cin, cout, k, up):
         npass = CONFIG['dgrad_passes']
         dh, dl = _split(dy, npass == 3)
         wh, wl = _split(wmod, npass == 3)
-        call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, npass, stream())
+        call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, npass, 0, stream())
     else:
         call('b200_conv_dgrad', ptr(dy), ptr(wmod), ptr(dx), n, h, w, cin, cout, k, up, stream())
 
@@ -315,6 +317,9 @@ class WeightBank:
         self.zpool = None          # one zero-filled buffer for the small backward accumulators (d bias, d noise_strength) of all layers
         self.zoff = []
         self.side = None           # second stream some layers ran on (CONFIG['overlap']); the bank's backward joins it
+        # outputs of the split-K convolutions (the 4x4 .. 32x32 blocks) start from zero: two pools, filled once per network pass,
+        # instead of a memset in front of every such launch (forward outputs / backward input gradients)
+        self.zf, self.zf_off, self.zb, self.zb_off = None, [], None, []
         self.dwpool = None         # d wmod of every tensor-core layer in one buffer, zeroed once per step (the wgrad kernels accumulate)
         self.dwoff, self.dwtotal, self.dwpool_home = [], 0, None
         self.wstream = None        # stream the weight-gradient GEMMs run on (CONFIG['wgrad_stream']); the bank's backward joins it
@@ -331,6 +336,21 @@ class WeightBank:
             torch.cuda.synchronize()
         o = self.zoff[lidx]
         return self.zpool[o:o + cout], self.zpool[o + cout]
+
+    def take_f(self, lidx, shape):
+        """Zero-filled forward output of layer lidx from the pool, or None (the launch does not split K / no pool)."""
+        return self._take(self.zf, self.zf_off, lidx, shape)
+
+    def take_b(self, lidx, shape):
+        """Zero-filled input gradient of layer lidx from the backward pool, or None.  The pool serves ONE backward pass."""
+        return self._take(self.zb, self.zb_off, lidx, shape)
+
+    @staticmethod
+    def _take(pool, offs, lidx, shape):
+        if pool is None or lidx < 0 or offs[lidx] < 0:
+            return None
+        cnt = int(np.prod(shape))
+        return pool[offs[lidx]:offs[lidx] + cnt].view(shape)
 
     def dwslice(self, lidx, n):
         """Zero-initialised d wmod [n, taps, cout, cin] of layer lidx inside the pool, or None when the layer is not pooled."""
@@ -415,6 +435,19 @@ class _Bank(torch.autograd.Function):
         ctx.bank = bank
         ctx.save_for_backward(ws)
         bank.need_wgrad = any(ctx.needs_input_grad)
+        # zero pools for the split-K launches (the library tells which shapes split K at this batch size)
+        lib = _lib.load()
+        bank.zf_off, bank.zb_off, tf, tb = [], [], 0, 0
+        for sp in bank.specs:
+            raw = sp.h * sp.w if sp.up == 1 else (2 * sp.h + 1) * (2 * sp.w + 1)
+            kf = lib.b200_conv_tc_ksplit(0, n, sp.h, sp.w, sp.cin, sp.cout, sp.k, sp.up) if (sp.tc_f and CONFIG['zero_pools']) else 1
+            kd = lib.b200_conv_tc_ksplit(1, n, sp.h, sp.w, sp.cin, sp.cout, sp.k, sp.up) if (sp.tc_b and CONFIG['zero_pools']) else 1
+            bank.zf_off.append(tf if kf > 1 else -1)
+            tf += n * raw * sp.cout if kf > 1 else 0
+            bank.zb_off.append(tb if kd > 1 else -1)
+            tb += n * sp.h * sp.w * sp.cin if kd > 1 else 0
+        bank.zf = torch.zeros([tf], device=dev, dtype=torch.float32) if tf else None
+        bank.zb = torch.zeros([tb], device=dev, dtype=torch.float32) if (tb and any(ctx.needs_input_grad)) else None
         bank.dwpool, bank.wstream = None, None
         bank.dwoff, tot = [], 0
         for sp in bank.specs:                       # layout of the d wmod pool (allocated and zeroed by the first wgrad of the backward)
@@ -461,6 +494,7 @@ class _Bank(torch.autograd.Function):
         call('b200_bank_weights_bwd', ctypes.addressof(arr), len(specs), n, stream())
         call('b200_bank_styles_bwd', ctypes.addressof(arr), len(specs), ptr(ws), ptr(d_ws), n, num_ws, w_dim, stream())
         bank.dwmod = [None] * len(specs)
+        bank.zb = None             # served this backward pass; a second pass over a retained graph lets the kernels clear their outputs
         bank.dwpool = None
         bank.zpool = None          # its slices now belong to autograd (possibly as param.grad): never accumulate into them again
         bank.token = None          # token -> grad_fn -> ctx.bank -> bank was a reference cycle keeping the per-step weight tensors alive
@@ -589,13 +623,19 @@ class _ModConvLayer(torch.autograd.Function):
                 call('b200_conv_fwd_tc_act', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), zp, ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st),
                      nbs, n, h, w, cin, cout, k, fp, 0.2, float(act_gain), clampf, stream())
             elif up == 1:
-                y = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
-                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cout, k, 1, fp, stream())
+                y = bank.take_f(lidx, [n, oh, ow, cout]) if bank is not None else None
+                pz = int(y is not None)
+                if y is None:
+                    y = torch.empty([n, oh, ow, cout], device=dev, dtype=torch.float32)
+                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cout, k, 1, fp, pz, stream())
                 call('b200_layer_act_fwd', ptr(y), zp, ptr(z_hi), ptr(z_lo), ptr(b), ptr(nz), ptr(st), nbs, n, oh * ow, cout, 1, 0.2,
                      float(act_gain), clampf, stream())
             else:
-                zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
-                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(zt), n, h, w, cin, cout, k, 2, fp, stream())
+                zt = bank.take_f(lidx, [n, 2 * h + 1, 2 * w + 1, cout]) if bank is not None else None
+                pz = int(zt is not None)
+                if zt is None:
+                    zt = torch.empty([n, 2 * h + 1, 2 * w + 1, cout], device=dev, dtype=torch.float32)
+                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(zt), n, h, w, cin, cout, k, 2, fp, pz, stream())
                 # 4x4 FIR (pad 1, gain 4) fused with the layer epilogue and the bf16 split for the next conv
                 call('b200_upfirdn2d_fused', ptr(zt), ptr(fir_filter(dev)), None, zp, ptr(z_hi), ptr(z_lo), n, 2 * h + 1, 2 * w + 1,
                      cout, 4, 4, 1, 1, 1, 1, 1, 1, 0, 4.0, 1, ptr(b), ptr(nz), ptr(st), nbs, 1, 0.2, float(act_gain), clampf, 1, stream())
@@ -647,7 +687,10 @@ class _ModConvLayer(torch.autograd.Function):
             dbias = torch.zeros([cout], device=dev, dtype=torch.float32)
             dstr = torch.zeros([], device=dev, dtype=torch.float32) if has_noise else None
         dnoise = torch.zeros_like(nz) if (has_noise and need[6]) else None
-        dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
+        dx = bank.take_b(lidx, [n, h, w, cin]) if (need_x and tc and bank is not None) else None
+        pz = int(dx is not None)
+        if dx is None and need_x:
+            dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32)
         dW = ds = None
         if tc:
             dp, wp = CONFIG['dgrad_passes'], CONFIG['wgrad_passes']
@@ -664,7 +707,7 @@ class _ModConvLayer(torch.autograd.Function):
                 _, dy_hi, dy_lo = _fir_fused(dy, fir_filter(dev), 1, 1, (2, 2, 2, 2), True, 4.0, want_f32=False, want_split=True, need_lo=lo,
                                              separable=True)          # fir_filter() is the outer product [1,3,3,1] x [1,3,3,1] / 64
             if need_x:
-                call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cout, k, up, dp, stream())
+                call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cout, k, up, dp, pz, stream())
             if need_w:
                 dwmod = bank.dwslice(lidx, n) if bank is not None else None
                 if dwmod is not None:
@@ -775,11 +818,14 @@ class _ToRGB(torch.autograd.Function):
                 w_hi = torch.empty([n, 1, cimg, cin], device=dev, dtype=torch.bfloat16)
                 w_lo = torch.empty_like(w_hi)
             call('b200_modconv_weight_prep', ptr(W), ptr(s), ptr(wmod), ptr(w_hi), ptr(w_lo), None, n, cimg, cin, 1, 0, stream())
-        y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
+        y = bank.take_f(lidx, [n, h, w, cimg]) if (bank is not None and tc_f) else None
+        pz = int(y is not None)
+        if y is None:
+            y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
         if (tc_f or tc_b) and (x_hi is None or x_lo is None):
             x_hi, x_lo = _split(x, True)
         if tc_f:
-            call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cimg, 1, 1, fp, stream())
+            call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cimg, 1, 1, fp, pz, stream())
         else:
             call('b200_conv_fwd', ptr(_f32c(x)), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
         b = _f32c(bias)
@@ -814,7 +860,10 @@ class _ToRGB(torch.autograd.Function):
         need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dimg = _f32c(dimg)
         dbias = bank.zeros(lidx, cimg)[0] if bank is not None else torch.zeros([cimg], device=dev, dtype=torch.float32)
-        dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32) if need_x else None
+        dx = bank.take_b(lidx, [n, h, w, cin]) if (need_x and tc_b and bank is not None) else None
+        pz = int(dx is not None)
+        if dx is None and need_x:
+            dx = torch.empty([n, h, w, cin], device=dev, dtype=torch.float32)
         dW = ds = None
         if need_w:
             dwmod = bank.dwslice(lidx, n) if (bank is not None and tc_b) else None
@@ -829,7 +878,7 @@ class _ToRGB(torch.autograd.Function):
             call('b200_layer_act_bwd', ptr(dimg), ptr(y), None, None, None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), None, None, 0, None, None,
                  n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
-                call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cimg, 1, 1, dp, stream())
+                call('b200_conv_dgrad_tc', ptr(dy_hi), ptr(dy_lo), ptr(wm), ptr(wm_lo), ptr(dx), n, h, w, cin, cimg, 1, 1, dp, pz, stream())
             if need_w and pooled:
                 bank.run_wgrad((xs, xs_lo, dy_hi, dy_lo), lambda: call(
                     'b200_conv_wgrad_tc', ptr(xs), ptr(xs_lo), ptr(dy_hi), ptr(dy_lo), ptr(dwmod), n, h, w, cin, cimg, 1, 1, wp, 1, stream()))

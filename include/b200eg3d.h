@@ -94,8 +94,12 @@ int b200_conv1x1_wgrad_split(const void* x_hi, const void* x_lo, const float* dy
  * b200_conv_tc_supported(kind, ...) -> 1 if the shape is handled (kind 0 fwd, 1 dgrad, 2 wgrad), else use the fp32 entry points. */
 int b200_conv_tc_supported(int kind, int h, int w, int cin, int cout, int ksize, int up);
 int b200_split_bf16(const float* x, void* hi_bf16, void* lo_bf16 /* may be NULL */, long count, void* stream);
+/* Layers with few output tiles split K over CTAs and ADD partial sums (red.global): b200_conv_tc_ksplit(kind 0 fwd / 1 dgrad, ...) > 1.
+ * Such a launch clears its output first, unless prezeroed != 0: the caller then guarantees an all-zero y / dx (one fill for every
+ * split-K output of a network instead of a memset in front of each launch).  Launches that do not split K overwrite either way. */
+int b200_conv_tc_ksplit(int kind, int n, int h, int w, int cin, int cout, int ksize, int up);
 int b200_conv_fwd_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, float* y,
-                     int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+                     int n, int h, int w, int cin, int cout, int ksize, int up, int npass, int prezeroed, void* stream);
 /* up == 1 forward convolution with the SynthesisLayer epilogue (networks_stylegan2.py:318-329) applied while the accumulator
  * leaves tensor memory: z = clamp(lrelu_alpha(conv + noise[pix] * *strength + bias[c]) * act_gain, +-clamp), written as fp32 z (may
  * be NULL: the pair is then the only copy) and as the split-bf16 pair z_hi / z_lo (z_lo may be NULL) that feeds the next convolution.  noise [h*w] (noise_bs 0) or [n][h*w]
@@ -105,7 +109,7 @@ int b200_conv_fwd_tc_act(const void* x_hi, const void* x_lo, const void* w_hi, c
                          const float* bias, const float* noise, const float* strength, long noise_bs, int n, int h, int w, int cin,
                          int cout, int ksize, int npass, float alpha, float act_gain, float clamp, void* stream);
 int b200_conv_dgrad_tc(const void* dy_hi, const void* dy_lo, const void* w_hi, const void* w_lo, float* dx,
-                       int n, int h, int w, int cin, int cout, int ksize, int up, int npass, void* stream);
+                       int n, int h, int w, int cin, int cout, int ksize, int up, int npass, int prezeroed, void* stream);
 /* accumulate == 0: dwmod is overwritten (zeroed inside the call, then reduced into); accumulate != 0: the partial sums are ADDED to
  * dwmod, which the caller zeroed earlier (one fill for every layer of a network, off the critical path). */
 int b200_conv_wgrad_tc(const void* x_hi, const void* x_lo, const void* dy_hi, const void* dy_lo, float* dwmod,

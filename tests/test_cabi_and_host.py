@@ -36,7 +36,7 @@ def test_ctypes_table_matches_header():
     from b200eg3d import _lib
     syms = set(declared_symbols())
     bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_set_mlp_passes', 'b200_set_triplane_impl', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes', 'b200_triplane_fsave_bytes',
-                                        'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable', 'b200_set_conv_pair', 'b200_conv1x1_thin_supported'}
+                                        'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable', 'b200_set_conv_pair', 'b200_conv1x1_thin_supported', 'b200_conv_tc_ksplit'}
     assert syms == bound, (sorted(syms - bound), sorted(bound - syms))
     src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
     for name, args in _lib.SIGNATURES.items():      # argument counts agree with the prototypes
@@ -57,6 +57,11 @@ def test_shape_support_query_needs_no_gpu():
     prev = lib.b200_set_conv_pair(0)
     assert lib.b200_set_conv_pair(prev) == 0 and lib.b200_set_conv_pair(prev) == prev
     assert lib.b200_conv1x1_thin_supported(64, 3) == 1 and lib.b200_conv1x1_thin_supported(64, 96) == 0
+    # the 4x4 .. 32x32 blocks split K (their outputs must start at zero), the large layers do not; unsupported shapes report 1
+    assert lib.b200_conv_tc_ksplit(0, 1, 16, 16, 512, 512, 3, 1) > 1 and lib.b200_conv_tc_ksplit(1, 1, 16, 16, 512, 512, 3, 1) > 1
+    assert lib.b200_conv_tc_ksplit(0, 1, 8, 8, 512, 512, 3, 2) > 1
+    assert lib.b200_conv_tc_ksplit(0, 1, 256, 256, 128, 128, 3, 1) == 1 and lib.b200_conv_tc_ksplit(1, 1, 256, 256, 128, 128, 3, 1) == 1
+    assert lib.b200_conv_tc_ksplit(0, 1, 16, 16, 12, 20, 3, 1) == 1
 
 
 @pytest.mark.parametrize('arch', ['tiny', 'full'])

@@ -431,7 +431,7 @@ def test_conv_fwd_tc_fused_epilogue_matches_two_kernel_path(b2, noise_mode):
     y = torch.empty(n, h, w, cout, device='cuda')
     z0, z1 = torch.empty_like(y), torch.empty_like(y)
     h0, l0, h1, l1 = [torch.empty(n, h, w, cout, device='cuda', dtype=torch.bfloat16) for _ in range(4)]
-    call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, 3, 1, 3, stream())
+    call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, 3, 1, 3, 0, stream())
     call('b200_layer_act_fwd', ptr(y), ptr(z0), ptr(h0), ptr(l0), ptr(bias), ptr(noise), ptr(strength) if noise is not None else None, nbs,
          n, h * w, cout, 1, 0.2, math.sqrt(2), 1.5, stream())
     call('b200_conv_fwd_tc_act', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(z1), ptr(h1), ptr(l1), ptr(bias), ptr(noise),
@@ -537,7 +537,7 @@ def test_conv_tc_pair_tiles_match_single_cta(b2, kind, n, h, w, cin, cout, k, up
         for pair in (1, 0):
             prev = lib.b200_set_conv_pair(pair)
             y = torch.full([n, hs, ws_, cout], float('nan'), device='cuda')
-            call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, 3, stream())
+            call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, 3, 0, stream())
             lib.b200_set_conv_pair(prev)
             outs.append(y)
         wt = wm.double().reshape(n, k, k, cout, cin)
@@ -556,7 +556,7 @@ def test_conv_tc_pair_tiles_match_single_cta(b2, kind, n, h, w, cin, cout, k, up
         for pair in (1, 0):
             prev = lib.b200_set_conv_pair(pair)
             dx = torch.full([n, h, w, cin], float('nan'), device='cuda')
-            call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, 3, stream())
+            call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, 3, 0, stream())
             lib.b200_set_conv_pair(prev)
             outs.append(dx)
         ref = None
@@ -676,3 +676,34 @@ def test_fir_column_window_matches_patch_kernel(b2, h, w, c, pad, flip, act):
         ff = f.cpu().flip([0, 1]) if flip else f.cpu()          # the filter is symmetric: flipping is exercised, not distinguished
         ref = oracle.upfirdn2d(nchw(x).cpu(), ff, pad=(pad, pad, pad, pad), gain=4.0)
         assert maxdiff(nchw(outs[0][0]), ref) < 2e-5
+
+
+def test_zero_pools_match_per_launch_memsets(b2, monkeypatch, golden_dir):
+    """ops.CONFIG['zero_pools']: the outputs of all split-K convolutions of a network come from one zero-filled pool (the launches are told
+    `prezeroed`); switched off, every such launch clears its own output.  Same image and gradients either way."""
+    import synth_params as sp
+    from golden_util import load_case
+    from b200eg3d._lib import load
+    assert load().b200_conv_tc_ksplit(0, 1, 16, 16, 512, 512, 3, 1) > 1
+    case = load_case(golden_dir, 'full_r64_s16')
+    G = b2.TriPlaneGenerator(rendering_kwargs=case.rk, **case.gk).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), case.param_seed)
+    G = G.cuda().float()
+    G.neural_rendering_resolution = case.R
+    G.renderer.fixed_noise = (case.u_strat.cuda(), case.u_imp.cuda())
+    ws, c = case.ws.cuda(), case.c.cuda()
+    named = [(n, p) for n, p in G.named_parameters() if '.mapping.' not in n]
+    outs = []
+    for on in (True, False):
+        monkeypatch.setitem(b2.ops.CONFIG, 'zero_pools', on)
+        for _, p in named:
+            p.grad = None
+        out = G.synthesis(ws, c, noise_mode='const')
+        (out['image'].square().mean() + out['image_raw'].square().mean()).backward()
+        torch.cuda.synchronize()
+        outs.append((out['image'].detach().clone(), [p.grad.clone() if p.grad is not None else None for _, p in named]))
+    assert maxdiff(outs[0][0], outs[1][0]) < 2e-4
+    for (n, _), a, b in zip(named, outs[0][1], outs[1][1]):
+        if a is None or a.ndim < 2:
+            continue
+        assert relerr(a, b) < 1e-2, (n, relerr(a, b))
