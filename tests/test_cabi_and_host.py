@@ -228,3 +228,13 @@ def test_tuned_generator_checkpoint_roundtrip(tmp_path):
     torch.save({'format': 'other'}, path)
     with pytest.raises(ValueError):
         b200eg3d.seam.load_tuned_G(path, device='cpu')
+
+
+def test_optimizer_has_no_cpu_path():
+    """b200eg3d.optim.Adam runs only as the one-launch CUDA kernel: CPU parameters are rejected at construction (no silent fallback)."""
+    import torch
+    from b200eg3d.optim import Adam
+    with pytest.raises(ValueError):
+        Adam([torch.zeros(4, requires_grad=True)], lr=1e-3)
+    with pytest.raises(ValueError):
+        Adam([], lr=1e-3)
