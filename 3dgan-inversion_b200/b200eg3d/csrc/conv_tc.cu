@@ -392,6 +392,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
                 for (int it = 0; it < nk; ++it) {
                     const int s = it % STAGES, ph = (it / STAGES) & 1;
                     mbar_wait(empty(s), ph ^ 1);
+#ifdef B200_DBG_NO_TMA
+                    mbar_arrive(full(s));
+                    continue;
+#endif
                     mbar_arrive_expect_tx(full(s), bytes);
                     const int tile = kb0 + it;
                     const int x0 = (tile % p.tiles_x) * p.tw, y0 = (tile / p.tiles_x) * p.th;
@@ -428,6 +432,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
 #pragma unroll
                         for (int k = 0; k < TILE_K / 16; ++k) {
                             const uint64_t dah = desc_pack(ah0 + k * KS, dhi), dbh = desc_pack(bh0 + k * KS, dhi);
+#ifdef B200_DBG_NO_MMA
+                            if (it >= 0) continue;
+#endif
                             umma_bf16(d, dah, dbh, idesc, (it | k) != 0);
                             if (three) {
                                 const uint64_t dal = desc_pack(smem_desc_lo(a_addr(st, j, 1), LBO) + k * KS, dhi);
@@ -454,6 +461,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_kernel(const __grid_cons
                 for (int c0 = 0; c0 < p.BN; c0 += 32) {
                     float v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * p.BN + c0), v);
+#ifdef B200_DBG_NO_STORE
+                    if (v[0] != 12345.678f) continue;
+#endif
                     if (m < p.Cm) {
                         if (vec && n0 + c0 + 32 <= p.Cn) {
 #pragma unroll

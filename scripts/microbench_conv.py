@@ -62,8 +62,10 @@ for (name, cin, cout, res, up) in LAYERS:
     fl = 2.0 * h * w * 9 * cin * cout
     for kind, fn in (('fwd', lambda: call('b200_conv_fwd_tc', ptr(xh), ptr(xl), ptr(wh), ptr(wl), ptr(y), n, h, w, cin, cout, k, up, 3, 0, stream())),
                      ('dgrad', lambda: call('b200_conv_dgrad_tc', ptr(dh), ptr(dl), ptr(wh), ptr(wl), ptr(dx), n, h, w, cin, cout, k, up, 3, 0, stream())),
-                     ('wgrad', lambda: call('b200_conv_wgrad_tc', ptr(xh), None, ptr(dh), None, ptr(dw), n, h, w, cin, cout, k, up, 1, 0, stream()))):
+                     ('wgrad', lambda: call('b200_conv_wgrad_tc', ptr(xh), None, ptr(dh), None, ptr(dw), n, h, w, cin, cout, k, up, 1, int('--wgrad-accumulate' in sys.argv), stream()))):
         if kind == 'wgrad' and '--only-fwd-dgrad' in sys.argv:
+            continue
+        if kind != 'wgrad' and '--only-wgrad' in sys.argv:
             continue
         ms = timeit(fn, f'{name} {kind}', fl)
         if ms:
