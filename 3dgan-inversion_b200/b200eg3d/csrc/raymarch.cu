@@ -14,6 +14,15 @@ __device__ __forceinline__ unsigned f2ord(float f) {      // order-preserving fl
     const unsigned b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// one ray's colour rows (one 128-byte line per sample) on their way into L2 while its depths are ranked and marched: the
+// accumulation loop then waits for L2 hits, not for HBM, six times in a row
+__device__ __forceinline__ void prefetch_rows(const float* rows, int count, int lane) {
+    if (rows)
+        for (int i = lane; i < count; i += 32) prefetch_l2(rows + (long)i * 32);
+}
+
 __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
@@ -87,12 +96,23 @@ __global__ void __launch_bounds__(128) ray_importance_kernel(const float* __rest
         __syncwarp();
         // pdf over w_hat[1 : L-1] + 1e-5 (NB = L-2 entries), cdf with leading zero (NB+1 entries) in trans[]
         const int NB = L - 2;
-        if (lane == 0) {
-            float tot = 0.f;
-            for (int i = 0; i < NB; ++i) tot += alpha[1 + i] + 1e-5f;
-            float c = 0.f;
-            trans[0] = 0.f;
-            for (int i = 0; i < NB; ++i) { c += (alpha[1 + i] + 1e-5f) / tot; trans[1 + i] = c; }
+        {   // (normalise, then cumulative sum -- renderer.py:277-279 -- as a warp reduction and a chunked warp scan)
+            float part = 0.f;
+            for (int i = lane; i < NB; i += 32) part += alpha[1 + i] + 1e-5f;
+            const float tot = warp_sum(part);
+            float carry = 0.f;
+            if (lane == 0) trans[0] = 0.f;
+            for (int i0 = 0; i0 < NB; i0 += 32) {
+                const int i = i0 + lane;
+                float v = i < NB ? (alpha[1 + i] + 1e-5f) / tot : 0.f;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v += up;
+                }
+                if (i < NB) trans[1 + i] = carry + v;
+                carry += __shfl_sync(0xffffffffu, v, 31);
+            }
         }
         __syncwarp();
         for (int j = lane; j < S_imp; j += 32) {
@@ -136,16 +156,29 @@ __device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray
     sorted = __all_sync(0xffffffffu, sorted);
     if (sorted) {
         const float* tf = traw + S1;
-        for (int j = lane; j < S2; j += 32) {                 // rank among the fine samples
+        const bool vec4 = ((S1 | S2) & 3) == 0;               // tf is then 16-byte aligned: four depths per (broadcast) shared load
+        for (int j = lane; j < S2; j += 32) {                 // rank among the fine samples: #{t_k < t_j}, ties (rare) by index
             const float tj = tf[j];
-            int r = 0;
-            for (int k = 0; k < S2; ++k) { const float tk = tf[k]; r += (tk < tj) || (tk == tj && k < j); }
+            int lt = 0, le = 0;
+            if (vec4) {
+                for (int k = 0; k < S2; k += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(tf + k);
+                    lt += (t4.x < tj) + (t4.y < tj) + (t4.z < tj) + (t4.w < tj);
+                    le += (t4.x <= tj) + (t4.y <= tj) + (t4.z <= tj) + (t4.w <= tj);
+                }
+            } else {
+                for (int k = 0; k < S2; ++k) { const float tk = tf[k]; lt += tk < tj; le += tk <= tj; }
+            }
+            int r = lt;
+            if (le - lt > 1)                                  // equal depths among the fine samples: stable order
+                for (int k = 0; k < j; ++k) r += tf[k] == tj;
             rk[S1 + j] = r;
             scratch[r] = tj;
         }
         __syncwarp();
         for (int i = lane; i < S; i += 32) {
             const float ti = traw[i];
+            const float sg = i < S1 ? p.sigma_c[ray * S1 + i] : p.sigma_f[ray * S2 + i - S1];   // in flight during the search
             int r;
             if (i < S1) {                                      // lower_bound in the sorted fine depths
                 int lo = 0, hi = S2;
@@ -158,7 +191,7 @@ __device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray
             }
             rk[i] = r;
             ts[r] = ti;
-            ss[r] = i < S1 ? p.sigma_c[ray * S1 + i] : p.sigma_f[ray * S2 + i - S1];
+            ss[r] = sg;
         }
     } else {
         for (int i = lane; i < S; i += 32) {
@@ -174,7 +207,7 @@ __device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray
 }
 
 __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams p, int SP) {
-    extern __shared__ float dyn[];                 // per warp: 6 float arrays + the rank array, SP entries each
+    extern __shared__ __align__(16) float dyn[];                 // per warp: 6 float arrays + the rank array, SP entries each
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* traw = dyn + wid * 7 * SP; float* ts = traw + SP; float* ss = ts + SP; float* alpha = ss + SP;
     float* trans = alpha + SP; float* w = trans + SP;
@@ -182,6 +215,8 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
     const int S = p.S1 + p.S2;
     const float dmin = ord2f(p.minmax[0]), dmax = ord2f(p.minmax[1]);
     for (long ray = (long)blockIdx.x * 4 + wid; ray < p.n_rays; ray += (long)gridDim.x * 4) {
+        prefetch_rows(p.rgb_c + ray * p.S1 * 32, p.S1, lane);
+        prefetch_rows(p.S2 ? p.rgb_f + ray * p.S2 * 32 : nullptr, p.S2, lane);
         load_and_rank(p, ray, traw, ts, ss, rk, alpha, lane);
         march_weights(ts, ss, S, alpha, trans, w, lane);
         float ws = 0.f, dn = 0.f;
@@ -193,20 +228,37 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
             traw[i] = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
         }
         __syncwarp();
-        float acc = 0.f;
-        for (int i0 = 0; i0 < S; i0 += 16) {          // 16 colour rows (128 B each, lane = channel) in flight per warp
-            float c[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int i = i0 + j;
-                c[j] = i >= S ? 0.f : (i < p.S1 ? __ldg(p.rgb_c + (ray * p.S1 + i) * 32 + lane) : __ldg(p.rgb_f + (ray * p.S2 + i - p.S1) * 32 + lane));
+        // colour accumulation: eight lanes share one sample row (4 channels each), four rows per warp instruction, coarse and
+        // fine rows in separate loops (one base pointer each: no per-row select); the four row groups are summed by two shuffles
+        const int sub = lane >> 3, j4 = lane & 7;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            const float4* rc = reinterpret_cast<const float4*>(p.rgb_c + ray * p.S1 * 32) + j4;
+#pragma unroll 4
+            for (int i = sub; i < p.S1; i += 4) {
+                const float om = traw[i];
+                const float4 c = __ldg(rc + i * 8);
+                acc.x = fmaf(om, c.x, acc.x); acc.y = fmaf(om, c.y, acc.y); acc.z = fmaf(om, c.z, acc.z); acc.w = fmaf(om, c.w, acc.w);
             }
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (i0 + j < S) acc = fmaf(traw[i0 + j], c[j], acc);
+            const float4* rf = reinterpret_cast<const float4*>(p.rgb_f + ray * p.S2 * 32) + j4;
+            const float* omf = traw + p.S1;
+#pragma unroll 4
+            for (int i = sub; i < p.S2; i += 4) {
+                const float om = omf[i];
+                const float4 c = __ldg(rf + i * 8);
+                acc.x = fmaf(om, c.x, acc.x); acc.y = fmaf(om, c.y, acc.y); acc.z = fmaf(om, c.z, acc.z); acc.w = fmaf(om, c.w, acc.w);
+            }
         }
-        if (p.white_back) acc += 1.f - ws;
-        p.feat[ray * 32 + lane] = acc * 2.f - 1.f;
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+        }
+        if (sub == 0) {
+            const float wb = p.white_back ? 1.f - ws : 0.f;
+            reinterpret_cast<float4*>(p.feat + ray * 32)[j4] = make_float4((acc.x + wb) * 2.f - 1.f, (acc.y + wb) * 2.f - 1.f,
+                                                                           (acc.z + wb) * 2.f - 1.f, (acc.w + wb) * 2.f - 1.f);
+        }
         if (lane == 0) {
             float d = dn / ws;
             d = (d != d) ? dmax : fminf(fmaxf(d, dmin), dmax);
@@ -218,7 +270,7 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
 }
 
 __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams p, int SP) {
-    extern __shared__ float dyn[];                 // per warp: 8 float arrays + the rank array, SP entries each
+    extern __shared__ __align__(16) float dyn[];                 // per warp: 8 float arrays + the rank array, SP entries each
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* traw = dyn + wid * 9 * SP; float* ts = traw + SP; float* ss = ts + SP; float* alpha = ss + SP;
     float* trans = alpha + SP; float* w = trans + SP; float* dom = w + SP; float* dsb = dom + SP;
@@ -226,6 +278,8 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
     const int S = p.S1 + p.S2;
     const float dmin = ord2f(p.minmax[0]), dmax = ord2f(p.minmax[1]);
     for (long ray = (long)blockIdx.x * 4 + wid; ray < p.n_rays; ray += (long)gridDim.x * 4) {
+        prefetch_rows(p.rgb_c + ray * p.S1 * 32, p.S1, lane);
+        prefetch_rows(p.S2 ? p.rgb_f + ray * p.S2 * 32 : nullptr, p.S2, lane);
         load_and_rank(p, ray, traw, ts, ss, rk, alpha, lane);
         march_weights(ts, ss, S, alpha, trans, w, lane);
         float ws = 0.f, dn = 0.f;
@@ -245,22 +299,29 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
             gsum = g4.x + g4.y + g4.z + g4.w;
             gsum += __shfl_xor_sync(0xffffffffu, gsum, 1); gsum += __shfl_xor_sync(0xffffffffu, gsum, 2); gsum += __shfl_xor_sync(0xffffffffu, gsum, 4);
         }
+        // coarse rows, then fine rows (one base pointer per loop: no per-row select in the address arithmetic)
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int cnt = part ? p.S2 : p.S1;
+            const int* rkp = rk + (part ? p.S1 : 0);
+            const long row0 = part ? ray * p.S2 * 32 : ray * p.S1 * 32;
+            const float4* src = reinterpret_cast<const float4*>((part ? p.rgb_f : p.rgb_c) + row0) + j4;
+            float4* dst = reinterpret_cast<float4*>((part ? p.d_rgb_f : p.d_rgb_c) + row0) + j4;
 #pragma unroll 4
-        for (int i0 = 0; i0 < S; i0 += 4) {
-            const int i = i0 + sub;
-            const bool v = i < S;
-            const int r = v ? rk[i] : 0;
-            const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
-            const bool co = i < p.S1;
-            const long row = co ? (ray * p.S1 + i) * 32 : (ray * p.S2 + i - p.S1) * 32;
-            float t = 0.f;
-            if (v) {
-                const float4 c = __ldg(reinterpret_cast<const float4*>((co ? p.rgb_c : p.rgb_f) + row) + j4);
-                t = g4.x * c.x + g4.y * c.y + g4.z * c.z + g4.w * c.w;
-                reinterpret_cast<float4*>((co ? p.d_rgb_c : p.d_rgb_f) + row)[j4] = make_float4(om * g4.x, om * g4.y, om * g4.z, om * g4.w);
+            for (int i0 = 0; i0 < cnt; i0 += 4) {
+                const int i = i0 + sub;
+                const bool v = i < cnt;
+                const int r = v ? rkp[i] : 0;
+                const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+                float t = 0.f;
+                if (v) {
+                    const float4 c = __ldg(src + i * 8);
+                    t = g4.x * c.x + g4.y * c.y + g4.z * c.z + g4.w * c.w;
+                    dst[i * 8] = make_float4(om * g4.x, om * g4.y, om * g4.z, om * g4.w);
+                }
+                t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+                if (v && j4 == 0) dom[r] = t;
             }
-            t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
-            if (v && j4 == 0) dom[r] = t;
         }
         __syncwarp();
         // d w_k, stored in dsb[]
@@ -270,13 +331,26 @@ __global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams 
             dsb[k] = dw;
         }
         __syncwarp();
-        // reverse scan: d alpha_k (into dom[])
-        if (lane == 0) {
-            float dTn = 0.f;
-            for (int k = S - 2; k >= 0; --k) {
-                const float dw = dsb[k];
-                dom[k] = trans[k] * (dw - dTn);
-                dTn = dw * alpha[k] + dTn * (1.f - alpha[k] + 1e-10f);
+        // reverse scan: d alpha_k (into dom[]).  x_k = dw_k alpha_k + x_{k+1} (1 - alpha_k + 1e-10), x_{S-1} = 0 (the gradient flowing
+        // into the transmittance ahead of interval k), d alpha_k = T_k (dw_k - x_{k+1}).  Each interval is the affine map
+        // x -> A + B x; a warp-wide suffix scan composes the maps of 32 intervals, chunks run from the far end of the ray
+        {
+            float carry = 0.f;
+            for (int k0 = ((S - 2) >> 5) << 5; k0 >= 0; k0 -= 32) {
+                const int k = k0 + lane;
+                const bool v = k < S - 1;
+                const float dw = v ? dsb[k] : 0.f, al = v ? alpha[k] : 0.f;
+                float A = dw * al, B = v ? (1.f - al + 1e-10f) : 1.f;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float A2 = __shfl_down_sync(0xffffffffu, A, o), B2 = __shfl_down_sync(0xffffffffu, B, o);
+                    if (lane + o < 32) { A = fmaf(B, A2, A); B *= B2; }
+                }
+                const float x = fmaf(B, carry, A);                         // x_k
+                float xn = __shfl_down_sync(0xffffffffu, x, 1);            // x_{k+1}
+                if (lane == 31) xn = carry;
+                if (v) dom[k] = trans[k] * (dw - xn);
+                carry = __shfl_sync(0xffffffffu, x, 0);
             }
         }
         __syncwarp();
@@ -377,7 +451,7 @@ B200_API int b200_ray_importance(const float* t_c, const float* sigma_c, const f
     B200_REQUIRE(S >= 4 && S <= MAXS, "ray_importance: need 4 <= depth_resolution <= 256");
     if (n_rays <= 0 || S_imp <= 0) return 0;
     const int SP = (S + 3) & ~3;
-    const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
+    const int blocks = (int)((n_rays + 3) / 4 < (1L << 30) ? (n_rays + 3) / 4 : (1L << 30));   // one ray per warp: the block scheduler balances the SMs
     ray_importance_kernel<<<blocks, 128, 4 * 5 * SP * sizeof(float), (cudaStream_t)stream>>>(t_c, sigma_c, u, t_f, n_rays, S, S_imp, SP);
     B200_CHECK_LAUNCH();
     return 0;
@@ -387,12 +461,13 @@ B200_API int b200_ray_composite_fwd(const float* t_c, const float* sigma_c, cons
                                     const float* sigma_f, const float* rgb_f, int S2, const unsigned* minmax,
                                     int white_back, long n_rays, float* feat, float* depth, float* wsum, void* stream) {
     B200_REQUIRE(S1 >= 1 && S2 >= 0 && S1 + S2 >= 2 && S1 + S2 <= MAXS, "ray_composite: need 2 <= samples per ray <= 256");
+    B200_REQUIRE(((((uintptr_t)rgb_c | (uintptr_t)rgb_f | (uintptr_t)feat) & 15) == 0), "ray_composite: colour rows must be 16-byte aligned");
     if (n_rays <= 0) return 0;
     CompositeParams p{};
     p.t_c = t_c; p.sigma_c = sigma_c; p.rgb_c = rgb_c; p.S1 = S1; p.t_f = t_f; p.sigma_f = sigma_f; p.rgb_f = rgb_f; p.S2 = S2;
     p.minmax = minmax; p.white_back = white_back; p.n_rays = n_rays; p.feat = feat; p.depth = depth; p.wsum = wsum;
     const int SP = (S1 + S2 + 3) & ~3;
-    const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
+    const int blocks = (int)((n_rays + 3) / 4 < (1L << 30) ? (n_rays + 3) / 4 : (1L << 30));   // one ray per warp: the block scheduler balances the SMs
     ray_composite_fwd_kernel<<<blocks, 128, 4 * 7 * SP * sizeof(float), (cudaStream_t)stream>>>(p, SP);
     B200_CHECK_LAUNCH();
     return 0;
@@ -405,6 +480,8 @@ B200_API int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, cons
                                     void* stream) {
     B200_REQUIRE(S1 >= 1 && S2 >= 0 && S1 + S2 >= 2 && S1 + S2 <= MAXS, "ray_composite: need 2 <= samples per ray <= 256");
     B200_REQUIRE(d_feat, "ray_composite_bwd: d_feat is required");
+    B200_REQUIRE(((((uintptr_t)rgb_c | (uintptr_t)rgb_f | (uintptr_t)d_feat | (uintptr_t)d_rgb_c | (uintptr_t)d_rgb_f) & 15) == 0),
+                 "ray_composite_bwd: colour rows must be 16-byte aligned");
     if (n_rays <= 0) return 0;
     CompositeParams p{};
     p.t_c = t_c; p.sigma_c = sigma_c; p.rgb_c = rgb_c; p.S1 = S1; p.t_f = t_f; p.sigma_f = sigma_f; p.rgb_f = rgb_f; p.S2 = S2;
@@ -412,7 +489,7 @@ B200_API int b200_ray_composite_bwd(const float* t_c, const float* sigma_c, cons
     p.d_feat = d_feat; p.d_depth = d_depth; p.d_wsum = d_wsum;
     p.d_rgb_c = d_rgb_c; p.d_sigma_c = d_sigma_c; p.d_rgb_f = d_rgb_f; p.d_sigma_f = d_sigma_f;
     const int SP = (S1 + S2 + 3) & ~3;
-    const int blocks = (int)((n_rays + 3) / 4 < 148 * 16 ? (n_rays + 3) / 4 : 148 * 16);
+    const int blocks = (int)((n_rays + 3) / 4 < (1L << 30) ? (n_rays + 3) / 4 : (1L << 30));   // one ray per warp: the block scheduler balances the SMs
     ray_composite_bwd_kernel<<<blocks, 128, 4 * 9 * SP * sizeof(float), (cudaStream_t)stream>>>(p, SP);
     B200_CHECK_LAUNCH();
     return 0;
