@@ -206,7 +206,15 @@ __device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams p, int SP) {
+#ifndef RAY_MINB
+#define RAY_MINB 10
+#endif
+#ifndef RAY_UNROLL
+#define RAY_UNROLL 4
+#endif
+#define RAY_PRAGMA_(x) _Pragma(#x)
+#define RAY_PRAGMA(x) RAY_PRAGMA_(x)
+__global__ void __launch_bounds__(128, RAY_MINB) ray_composite_fwd_kernel(CompositeParams p, int SP) {
     extern __shared__ __align__(16) float dyn[];                 // per warp: 6 float arrays + the rank array, SP entries each
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* traw = dyn + wid * 7 * SP; float* ts = traw + SP; float* ss = ts + SP; float* alpha = ss + SP;
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         {
             const float4* rc = reinterpret_cast<const float4*>(p.rgb_c + ray * p.S1 * 32) + j4;
-#pragma unroll 4
+RAY_PRAGMA(unroll RAY_UNROLL)
             for (int i = sub; i < p.S1; i += 4) {
                 const float om = traw[i];
                 const float4 c = __ldg(rc + i * 8);
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
             }
             const float4* rf = reinterpret_cast<const float4*>(p.rgb_f + ray * p.S2 * 32) + j4;
             const float* omf = traw + p.S1;
-#pragma unroll 4
+RAY_PRAGMA(unroll RAY_UNROLL)
             for (int i = sub; i < p.S2; i += 4) {
                 const float om = omf[i];
                 const float4 c = __ldg(rf + i * 8);
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(128) ray_composite_fwd_kernel(CompositeParams 
     }
 }
 
-__global__ void __launch_bounds__(128) ray_composite_bwd_kernel(CompositeParams p, int SP) {
+__global__ void __launch_bounds__(128, RAY_MINB) ray_composite_bwd_kernel(CompositeParams p, int SP) {
     extern __shared__ __align__(16) float dyn[];                 // per warp: 8 float arrays + the rank array, SP entries each
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     float* traw = dyn + wid * 9 * SP; float* ts = traw + SP; float* ss = ts + SP; float* alpha = ss + SP;
