@@ -14,7 +14,7 @@ _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 
 # b200_version() this binding table was written for.  Bumped together with csrc/conv_api.cu whenever a prototype changes: a
 # stale or variant .so (B200EG3D_LIB) with other argument lists would otherwise be called with the wrong stack layout.
-EXPECTED_VERSION = 204
+EXPECTED_VERSION = 205
 
 # name -> argument ctypes (every function returns int status; 0 = ok)
 SIGNATURES = {
@@ -50,7 +50,7 @@ SIGNATURES = {
     'b200_noise_normalize': [_I, _P, _P, _P, _P],
     'b200_ray_sampler_fwd': [_P, _P, _I, _I, _P, _P, _P],
     'b200_ray_sampler_bwd': [_P, _P, _I, _I, _P, _P, _P, _P],
-    'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P],
+    'b200_ray_depths_coarse': [_P, _P, _P, _L, _I, _F, _P, _P],
     'b200_depth_minmax': [_P, _L, _P, _P],
     'b200_ray_importance': [_P, _P, _P, _P, _L, _I, _I, _P],
     'b200_ray_composite_fwd': [_P, _P, _P, _I, _P, _P, _P, _I, _P, _I, _L, _P, _P, _P, _P],

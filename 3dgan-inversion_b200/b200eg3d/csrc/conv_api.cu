@@ -104,7 +104,7 @@ B200_API int b200_conv1x1_wgrad_split(const void* x_hi, const void* x_lo, const 
 }
 
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 204; }
+B200_API int b200_version() { return 205; }
 
 // Programmatic dependent launch on (1) / off (0) for subsequent launches; returns the previous setting.  Profiling aid: with PDL a
 // traced kernel duration includes the time it waits for its predecessor.

@@ -27,10 +27,25 @@ __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// min / max of a thread's values -> the two order-preserving words (one atomic pair per warp)
+__device__ __forceinline__ void warp_minmax_commit(float lo, float hi, unsigned* __restrict__ mm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+}
+
 __global__ void depths_coarse_kernel(const float* __restrict__ t_base, const float* __restrict__ u, float* __restrict__ t,
-                                     long total, int S, float delta) {
-    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
-        t[i] = t_base[i % S] + u[i] * delta;
+                                     long total, int S, float delta, unsigned* __restrict__ mm) {
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const float v = t_base[i % S] + u[i] * delta;
+        t[i] = v;
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+    if (mm) warp_minmax_commit(lo, hi, mm);          // the depth clamp's global range, gathered where the depths are made
 }
 
 __global__ void depth_minmax_kernel(const float* __restrict__ t, long total, unsigned* __restrict__ mm) {
@@ -39,12 +54,7 @@ __global__ void depth_minmax_kernel(const float* __restrict__ t, long total, uns
         const float v = t[i];
         lo = fminf(lo, v); hi = fmaxf(hi, v);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-    }
-    if ((threadIdx.x & 31) == 0) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+    warp_minmax_commit(lo, hi, mm);
 }
 
 // alpha_k / weights of the mid-point rule on SORTED samples held in shared memory (lane-strided + lane-0 scan)
@@ -435,12 +445,13 @@ __global__ void ray_sampler_kernel(const float* __restrict__ c2w, const float* _
 }
 }  // namespace
 
+// minmax (may be NULL): the two words of b200_depth_minmax, updated with this call's depths (saves the separate pass over t)
 B200_API int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta,
-                                    void* stream) {
+                                    unsigned* minmax, void* stream) {
     const long total = n_rays * S;
     if (total <= 0) return 0;
     const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
-    depths_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t_base, u, t, total, S, delta);
+    depths_coarse_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(t_base, u, t, total, S, delta, minmax);
     B200_CHECK_LAUNCH();
     return 0;
 }

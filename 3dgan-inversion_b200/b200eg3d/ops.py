@@ -975,6 +975,16 @@ def run_model_nhwc(planes_nhwc, decoder, coords, box_warp):
     return _RunModel.apply(planes_nhwc, coords, W1, b1, W2, b2, lr_mul, box_warp)
 
 
+_MM_INIT = {}
+
+
+def _minmax_init(device):
+    key = str(device)
+    if key not in _MM_INIT:
+        _MM_INIT[key] = torch.tensor([-1, 0], device=device, dtype=torch.int32)
+    return _MM_INIT[key]
+
+
 class _Render(torch.autograd.Function):
     """ImportanceRenderer.forward as one autograd node (renderer.py:143-195, numeric ray_start / ray_end).
 
@@ -997,11 +1007,14 @@ class _Render(torch.autograd.Function):
         S2 = 0 if u_imp is None else u_imp.shape[1]
         w = [_f32c(t) for t in (W1, b1, W2, b2)]
         st = stream()
+        # global depth range for the clamp of ray_marcher.py:50, as two order-preserving uint words {0xFFFFFFFF, 0} = (+inf, -inf)
+        minmax = _minmax_init(dev).clone()
         if t_coarse is not None:          # per-ray limits / disparity sampling: depths prepared by the caller (renderer.py:230-242)
             t_c = _f32c(t_coarse).reshape(n, M, S)
+            call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(minmax), st)
         else:
             t_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
-            call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), st)
+            call('b200_ray_depths_coarse', ptr(_f32c(t_base)), ptr(_f32c(u_strat)), ptr(t_c), n * M, S, float(delta), ptr(minmax), st)
         rgb_c = torch.empty([n, M, S, 32], device=dev, dtype=torch.float32)
         sig_c = torch.empty([n, M, S], device=dev, dtype=torch.float32)
         rw = 0
@@ -1013,9 +1026,6 @@ class _Render(torch.autograd.Function):
              *map(ptr, w), float(lr_mul), ptr(rgb_c), ptr(sig_c), ptr(fs_c), st)
         if density_noise > 0:
             sig_c += (torch.randn_like(sig_c.view(n, M * S, 1)) * density_noise).view(n, M, S)      # renderer.py:201-202 (same draw shape)
-        minmax = torch.zeros([2], device=dev, dtype=torch.int32)
-        minmax[:1].fill_(-1)                      # {0xFFFFFFFF, 0}: order-preserving uint encodings of +inf / -inf
-        call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(minmax), st)
         t_f = rgb_f = sig_f = fs_f = None
         if S2 > 0:
             t_f = torch.empty([n, M, S2], device=dev, dtype=torch.float32)
@@ -1027,7 +1037,8 @@ class _Render(torch.autograd.Function):
                  *map(ptr, w), float(lr_mul), ptr(rgb_f), ptr(sig_f), ptr(fs_f), st)
             if density_noise > 0:
                 sig_f += (torch.randn_like(sig_f.view(n, M * S2, 1)) * density_noise).view(n, M, S2)
-            call('b200_depth_minmax', ptr(t_f), t_f.numel(), ptr(minmax), st)
+            # no second pass over t_f: every fine depth is an interpolation between two mid-points of its ray's coarse depths
+            # (renderer.py:297-307), so the range of the merged samples IS the range of the coarse ones
         feat = torch.empty([n, M, 32], device=dev, dtype=torch.float32)
         depth = torch.empty([n, M, 1], device=dev, dtype=torch.float32)
         wsum = torch.empty([n, M, 1], device=dev, dtype=torch.float32)

@@ -189,8 +189,10 @@ int b200_set_triplane_impl(int impl);
 int b200_ray_sampler_fwd(const float* cam2world, const float* intrinsics, int n, int R, float* ray_o, float* ray_d, void* stream);
 int b200_ray_sampler_bwd(const float* cam2world, const float* intrinsics, int n, int R, const float* d_ray_o, const float* d_ray_d,
                          float* d_cam2world, void* stream);
-/* t[ray][s] = t_base[s] + u[ray][s] * delta          (renderer.py:224-247 sample_stratified, numeric ray_start/ray_end) */
-int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta, void* stream);
+/* t[ray][s] = t_base[s] + u[ray][s] * delta          (renderer.py:224-247 sample_stratified, numeric ray_start/ray_end).
+ * minmax (may be NULL): the two words of b200_depth_minmax below, updated with the depths this call makes. */
+int b200_ray_depths_coarse(const float* t_base, const float* u, float* t, long n_rays, int S, float delta, unsigned* minmax,
+                           void* stream);
 /* global min / max of depths for the clamp of ray_marcher.py:50; minmax: 2 x uint32 (order-preserving), initialised {~0u, 0} */
 int b200_depth_minmax(const float* t, long total, unsigned* minmax, void* stream);
 /* coarse weights -> maxpool/avgpool smoothing -> inverse-CDF fine depths (renderer.py:249-308).  u [n_rays][S_imp]. */

@@ -707,3 +707,40 @@ def test_zero_pools_match_per_launch_memsets(b2, monkeypatch, golden_dir):
         if a is None or a.ndim < 2:
             continue
         assert relerr(a, b) < 1e-2, (n, relerr(a, b))
+
+
+@pytest.mark.parametrize('M,S', [(1000, 48), (37, 7), (4096, 96)])
+def test_depths_coarse_range_and_fine_depths_inside(b2, M, S):
+    """b200_ray_depths_coarse also gathers the global depth range (the two order-preserving words of b200_depth_minmax) -- and the
+    fine depths of b200_ray_importance are interpolations between mid-points of their ray's coarse depths (renderer.py:297-307),
+    so they never leave that ray's coarse range: the range of the merged samples that ray_marcher.py:50 clamps to IS the coarse
+    range, which is why ops._Render makes no second pass over the fine depths."""
+    import struct
+    from b200eg3d._lib import call, ptr, stream
+    g = gen(M + S)
+    t_base = torch.linspace(2.25, 3.3, S).cuda()
+    u = torch.rand(M, S, generator=g).cuda()
+    delta = (3.3 - 2.25) / (S - 1)
+    t_c = torch.empty(M, S, device='cuda')
+    mm = torch.tensor([-1, 0], dtype=torch.int32, device='cuda')
+    call('b200_ray_depths_coarse', ptr(t_base), ptr(u), ptr(t_c), M, S, float(delta), ptr(mm), stream())
+    ref = t_base[None, :] + u * delta
+    assert (t_c - ref).abs().max().item() < 1e-6        # (the kernel may contract the multiply-add)
+
+    def dec(word):
+        w = int(word) & 0xffffffff
+        bits = (w & 0x7fffffff) if (w & 0x80000000) else (~w & 0xffffffff)
+        return struct.unpack('<f', struct.pack('<I', bits))[0]
+    lo, hi = (dec(v) for v in mm.cpu().tolist())
+    assert lo == t_c.min().item() and hi == t_c.max().item()
+    mm2 = torch.tensor([-1, 0], dtype=torch.int32, device='cuda')
+    call('b200_depth_minmax', ptr(t_c), t_c.numel(), ptr(mm2), stream())
+    assert torch.equal(mm, mm2)
+    if S >= 4:
+        sig = (torch.randn(M, S, generator=g) * 4).cuda()
+        sig[: M // 8] = -30.0                                # empty rays: flat weights, the degenerate branch of sample_pdf
+        u2 = torch.rand(M, S, generator=g).cuda()
+        u2[0, 0], u2[0, 1] = 0.0, 1.0 - 2.0 ** -24           # the ends of the unit interval
+        t_f = torch.empty(M, S, device='cuda')
+        call('b200_ray_importance', ptr(t_c), ptr(sig), ptr(u2), ptr(t_f), M, S, S, stream())
+        assert (t_f >= t_c.min(dim=1, keepdim=True).values).all() and (t_f <= t_c.max(dim=1, keepdim=True).values).all()
