@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libb200eg3d.so')
 SOURCES = ['bank.cu', 'conv_tc.cu', 'conv_api.cu', 'conv_simt.cu', 'modconv.cu', 'elementwise.cu', 'triplane.cu', 'triplane_tc.cu', 'raymarch.cu', 'losses.cu', 'projector.cu', 'optim.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-              '-Xcompiler', '-fPIC,-fvisibility=hidden', '--use_fast_math=false']
+              '-Xcompiler', '-fPIC,-fvisibility=hidden']
 
 
 def _nvcc():
@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith('--use_fast_math')]
+    flags = list(NVCC_FLAGS)
     procs = []
     objs = []
     for s in SOURCES:

@@ -167,23 +167,36 @@ __device__ __forceinline__ void load_and_rank(const CompositeParams& p, long ray
     if (sorted) {
         const float* tf = traw + S1;
         const bool vec4 = ((S1 | S2) & 3) == 0;               // tf is then 16-byte aligned: four depths per (broadcast) shared load
-        for (int j = lane; j < S2; j += 32) {                 // rank among the fine samples: #{t_k < t_j}, ties (rare) by index
+        // rank among the fine samples = #{t_k < t_j}; distinct depths fill every slot of scratch[] exactly once, so a slot that
+        // still holds the NaN it starts with means two equal depths (rare): only then the stable (depth, index) order is counted
+        for (int j = lane; j < S2; j += 32) scratch[j] = __int_as_float(0x7fc00000);
+        __syncwarp();
+        for (int j = lane; j < S2; j += 32) {
             const float tj = tf[j];
-            int lt = 0, le = 0;
+            int lt = 0;
             if (vec4) {
                 for (int k = 0; k < S2; k += 4) {
                     const float4 t4 = *reinterpret_cast<const float4*>(tf + k);
                     lt += (t4.x < tj) + (t4.y < tj) + (t4.z < tj) + (t4.w < tj);
-                    le += (t4.x <= tj) + (t4.y <= tj) + (t4.z <= tj) + (t4.w <= tj);
                 }
             } else {
-                for (int k = 0; k < S2; ++k) { const float tk = tf[k]; lt += tk < tj; le += tk <= tj; }
+                for (int k = 0; k < S2; ++k) lt += tf[k] < tj;
             }
-            int r = lt;
-            if (le - lt > 1)                                  // equal depths among the fine samples: stable order
-                for (int k = 0; k < j; ++k) r += tf[k] == tj;
-            rk[S1 + j] = r;
-            scratch[r] = tj;
+            rk[S1 + j] = lt;
+            scratch[lt] = tj;
+        }
+        __syncwarp();
+        bool hole = false;
+        for (int j = lane; j < S2; j += 32) { const float v = scratch[j]; hole = hole || (v != v); }
+        if (__any_sync(0xffffffffu, hole)) {
+            __syncwarp();
+            for (int j = lane; j < S2; j += 32) {
+                const float tj = tf[j];
+                int r = 0;
+                for (int k = 0; k < S2; ++k) { const float tk = tf[k]; r += (tk < tj) || (tk == tj && k < j); }
+                rk[S1 + j] = r;
+                scratch[r] = tj;
+            }
         }
         __syncwarp();
         for (int i = lane; i < S; i += 32) {
@@ -317,30 +330,47 @@ __global__ void __launch_bounds__(128, RAY_MINB) ray_composite_bwd_kernel(Compos
             gsum = g4.x + g4.y + g4.z + g4.w;
             gsum += __shfl_xor_sync(0xffffffffu, gsum, 1); gsum += __shfl_xor_sync(0xffffffffu, gsum, 2); gsum += __shfl_xor_sync(0xffffffffu, gsum, 4);
         }
-        // coarse rows, then fine rows (one base pointer per loop: no per-row select in the address arithmetic)
+        // omega_i = (w[rank(i) - 1] + w[rank(i)]) / 2 per ORIGINAL sample, once, lane-parallel (into traw[], free now)
+        for (int i = lane; i < S; i += 32) {
+            const int r = rk[i];
+            traw[i] = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+        }
+        __syncwarp();
+        // coarse rows, then fine rows (one base pointer per loop, no per-row select); the dot products land in dsb[] by ORIGINAL
+        // index and are permuted into rank order afterwards, lane-parallel -- the row loop carries no rank arithmetic
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
-            const int cnt = part ? p.S2 : p.S1;
-            const int* rkp = rk + (part ? p.S1 : 0);
+            const int cnt = part ? p.S2 : p.S1, off = part ? p.S1 : 0;
             const long row0 = part ? ray * p.S2 * 32 : ray * p.S1 * 32;
-            const float4* src = reinterpret_cast<const float4*>((part ? p.rgb_f : p.rgb_c) + row0) + j4;
-            float4* dst = reinterpret_cast<float4*>((part ? p.d_rgb_f : p.d_rgb_c) + row0) + j4;
+            const float4* src = reinterpret_cast<const float4*>((part ? p.rgb_f : p.rgb_c) + row0) + j4 + sub * 8;
+            float4* dst = reinterpret_cast<float4*>((part ? p.d_rgb_f : p.d_rgb_c) + row0) + j4 + sub * 8;
+            const float* omp = traw + off + sub;
+            float* tdp = dsb + off + sub;
+            const int full = cnt & ~3;
 #pragma unroll 4
-            for (int i0 = 0; i0 < cnt; i0 += 4) {
-                const int i = i0 + sub;
-                const bool v = i < cnt;
-                const int r = v ? rkp[i] : 0;
-                const float om = 0.5f * ((r > 0 ? w[r - 1] : 0.f) + (r < S - 1 ? w[r] : 0.f));
+            for (int i0 = 0; i0 < full; i0 += 4) {
+                const float om = omp[i0];
+                const float4 c = __ldg(src + i0 * 8);
+                float t = g4.x * c.x + g4.y * c.y + g4.z * c.z + g4.w * c.w;
+                dst[i0 * 8] = make_float4(om * g4.x, om * g4.y, om * g4.z, om * g4.w);
+                t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
+                if (j4 == 0) tdp[i0] = t;
+            }
+            if (full < cnt) {                                   // sample counts that are not a multiple of four: one partial group
+                const bool v = full + sub < cnt;
                 float t = 0.f;
                 if (v) {
-                    const float4 c = __ldg(src + i * 8);
+                    const float om = omp[full];
+                    const float4 c = __ldg(src + full * 8);
                     t = g4.x * c.x + g4.y * c.y + g4.z * c.z + g4.w * c.w;
-                    dst[i * 8] = make_float4(om * g4.x, om * g4.y, om * g4.z, om * g4.w);
+                    dst[full * 8] = make_float4(om * g4.x, om * g4.y, om * g4.z, om * g4.w);
                 }
                 t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4);
-                if (v && j4 == 0) dom[r] = t;
+                if (v && j4 == 0) tdp[full] = t;
             }
         }
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) dom[rk[i]] = dsb[i];
         __syncwarp();
         // d w_k, stored in dsb[]
         for (int k = lane; k < S - 1; k += 32) {
