@@ -103,6 +103,9 @@ __global__ void __launch_bounds__(128) ray_importance_kernel(const float* __rest
     float* ts = dyn + wid * 5 * SP; float* ss = ts + SP; float* alpha = ss + SP; float* trans = alpha + SP; float* w = trans + SP;
     for (long ray = (long)blockIdx.x * 4 + wid; ray < n_rays; ray += (long)gridDim.x * 4) {
         for (int k = lane; k < S; k += 32) { ts[k] = t_c[ray * S + k]; ss[k] = sigma_c[ray * S + k]; }
+        // this lane's first two uniform draws: in flight during the march (they are needed last)
+        const float u0 = lane < S_imp ? __ldg(u + ray * S_imp + lane) : 0.f;
+        const float u1 = lane + 32 < S_imp ? __ldg(u + ray * S_imp + lane + 32) : 0.f;
         __syncwarp();
         march_weights(ts, ss, S, alpha, trans, w, lane);
         const int L = S - 1;                       // number of weights
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(128) ray_importance_kernel(const float* __rest
         }
         __syncwarp();
         for (int j = lane; j < S_imp; j += 32) {
-            const float uu = u[ray * S_imp + j];
+            const float uu = j == lane ? u0 : (j == lane + 32 ? u1 : u[ray * S_imp + j]);
             int lo = 0, hi = NB + 1;                // searchsorted(right=True): first index with cdf > u
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (trans[mid] <= uu) lo = mid + 1; else hi = mid; }
             const int below = max(lo - 1, 0), above = min(lo, NB);
@@ -337,6 +340,11 @@ __global__ void __launch_bounds__(128, RAY_MINB) ray_composite_bwd_kernel(Compos
 #if RAY_PF_MODE == 0
         prefetch_rows(p.S2 ? p.rgb_f + ray * p.S2 * 32 : nullptr, p.S2, lane);
 #endif
+        // the ray's incoming gradients: loaded now, used after the march (nothing below depends on them until then)
+        const int sub = lane >> 3, j4 = lane & 7;
+        float4 g4 = __ldg(reinterpret_cast<const float4*>(p.d_feat + ray * 32) + j4);
+        const float gD_in = p.d_depth ? __ldg(p.d_depth + ray) : 0.f;
+        const float gW = p.d_wsum ? __ldg(p.d_wsum + ray) : 0.f;
         load_and_rank(p, ray, traw, ts, ss, rk, alpha, lane);
 #if RAY_PF_MODE == 1 || RAY_PF_MODE == 3
         prefetch_rows(p.S2 ? p.rgb_f + ray * p.S2 * 32 : nullptr, p.S2, lane);
@@ -347,12 +355,9 @@ __global__ void __launch_bounds__(128, RAY_MINB) ray_composite_bwd_kernel(Compos
         ws = warp_sum(ws); dn = warp_sum(dn);
         const float D = dn / ws;
         const bool d_pass = (D == D) && D >= dmin && D <= dmax;
-        const float gD = (d_pass && p.d_depth) ? p.d_depth[ray] : 0.f;
-        const float gW = p.d_wsum ? p.d_wsum[ray] : 0.f;
+        const float gD = d_pass ? gD_in : 0.f;
         // through rgb*2-1.  Eight lanes share one sample row (4 channels each): every warp instruction reads / writes four full
         // 128-byte colour rows; d omega_rank(i) = sum_ch g[ch] * c_i[ch] is reduced over the 8 lanes with three shuffles.
-        const int sub = lane >> 3, j4 = lane & 7;
-        float4 g4 = __ldg(reinterpret_cast<const float4*>(p.d_feat + ray * 32) + j4);
         g4.x *= 2.f; g4.y *= 2.f; g4.z *= 2.f; g4.w *= 2.f;
         float gsum = 0.f;                                        // through + 1 - wsum
         if (p.white_back) {
