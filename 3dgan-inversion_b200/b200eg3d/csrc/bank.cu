@@ -225,27 +225,41 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
                       *reinterpret_cast<uint32_t*>(&d));
 }
 
-template <int TAPS>
+__device__ __forceinline__ uint2 pack4_bf16(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    return make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+}
+
+// CPT = channels per thread, chosen per table: 4 when a cout's cin/4 threads fit one block for every layer (cin <= 1024: every
+// EG3D network), else 8.  TAPS*4 instead of TAPS*8 live weights per thread halves the register count, so two or three blocks
+// share an SM and one block's loads overlap another's reduction barrier and stores (one resident block of 8 warps left the memory
+// system idle between its phases).
+
+template <int TAPS, int CPT>
 __device__ __forceinline__ void weights_fwd_vec(const B200BankLayer& L, int blk, int n, float* red) {
-    const int cin = L.cin, cout = L.cout, gs = cin >> 3, cpb = 256 / gs;     // gs: power of two for every EG3D layer; else fall back
-    const int o = blk * cpb + (int)threadIdx.x / gs, i0 = ((int)threadIdx.x % gs) * 8;
+    const int cin = L.cin, cout = L.cout, gs = cin / CPT, cpb = 256 / gs;     // gs: power of two for every EG3D layer; else fall back
+    const int o = blk * cpb + (int)threadIdx.x / gs, i0 = ((int)threadIdx.x % gs) * CPT;
     const bool live = o < cout && (int)threadIdx.x < cpb * gs;
-    float w[TAPS * 8];
+    float w[TAPS * CPT];
     if (live) {
         const float4* src = reinterpret_cast<const float4*>(L.weight + ((long)o * cin + i0) * TAPS);
 #pragma unroll
-        for (int q = 0; q < TAPS * 2; ++q) { const float4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+        for (int q = 0; q < TAPS * CPT / 4; ++q) { const float4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
     }
     __nv_bfloat16* whi = (__nv_bfloat16*)L.w_hi;
     __nv_bfloat16* wlo = (__nv_bfloat16*)L.w_lo;
     for (int b = 0; b < n; ++b) {
-        float v[TAPS * 8];
+        float v[TAPS * CPT];
         float acc = 0.f;
         if (live) {
-            const float4 s0 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0), s1 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0 + 4);
-            const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            float s[CPT];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int q = 0; q < CPT / 4; ++q) {
+                const float4 sv = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0 + 4 * q);
+                s[4 * q] = sv.x; s[4 * q + 1] = sv.y; s[4 * q + 2] = sv.z; s[4 * q + 3] = sv.w;
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
 #pragma unroll
                 for (int tp = 0; tp < TAPS; ++tp) { v[j * TAPS + tp] = w[j * TAPS + tp] * s[j]; acc = fmaf(v[j * TAPS + tp], v[j * TAPS + tp], acc); }
         }
@@ -259,22 +273,24 @@ __device__ __forceinline__ void weights_fwd_vec(const B200BankLayer& L, int blk,
             const long ob = (long)b * TAPS * cout * cin;
 #pragma unroll
             for (int tp = 0; tp < TAPS; ++tp) {
-                float x[8], lo[8];
+                float x[CPT], lo[CPT];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = v[j * TAPS + tp] * d;
+                for (int j = 0; j < CPT; ++j) x[j] = v[j * TAPS + tp] * d;
                 const long oi = ob + ((long)tp * cout + o) * cin + i0;
                 if (L.wmod) {
-                    *reinterpret_cast<float4*>(L.wmod + oi) = make_float4(x[0], x[1], x[2], x[3]);
-                    *reinterpret_cast<float4*>(L.wmod + oi + 4) = make_float4(x[4], x[5], x[6], x[7]);
+#pragma unroll
+                    for (int q = 0; q < CPT / 4; ++q)
+                        *reinterpret_cast<float4*>(L.wmod + oi + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
                 }
                 if (whi) {
-                    const uint4 h = pack8_bf16(x);
-                    *reinterpret_cast<uint4*>(whi + oi) = h;
+                    __nv_bfloat16 hb[CPT];
+                    if (CPT == 8) { const uint4 h = pack8_bf16(x); *reinterpret_cast<uint4*>(whi + oi) = h; *reinterpret_cast<uint4*>(hb) = h; }
+                    else { const uint2 h = pack4_bf16(x); *reinterpret_cast<uint2*>(whi + oi) = h; *reinterpret_cast<uint2*>(hb) = h; }
                     if (wlo) {
-                        const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&h);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) lo[j] = x[j] - __bfloat162float(hb[j]);
-                        *reinterpret_cast<uint4*>(wlo + oi) = pack8_bf16(lo);
+                        for (int j = 0; j < CPT; ++j) lo[j] = x[j] - __bfloat162float(hb[j]);
+                        if (CPT == 8) *reinterpret_cast<uint4*>(wlo + oi) = pack8_bf16(lo);
+                        else *reinterpret_cast<uint2*>(wlo + oi) = pack4_bf16(lo);
                     }
                 }
             }
@@ -282,41 +298,50 @@ __device__ __forceinline__ void weights_fwd_vec(const B200BankLayer& L, int blk,
     }
 }
 
-__global__ void __launch_bounds__(256) bank_weights_fwd_vec_kernel(const __grid_constant__ BankTable t, int n) {
+// resident blocks per SM asked of the compiler (CPT = 4): forward 3 (80 registers, 48 B of spill: 48 -> 45 us per step), backward 2
+// (128 registers; at 3 it spills 200 B per thread: 71 -> 107 us)
+template <int CPT>
+__global__ void __launch_bounds__(256, CPT == 4 ? 3 : 1) bank_weights_fwd_vec_kernel(const __grid_constant__ BankTable t, int n) {
     __shared__ float red[8];
     const int l = find_layer(t, blockIdx.x);
     const B200BankLayer& L = t.l[l];
-    if (L.taps == 9) weights_fwd_vec<9>(L, blockIdx.x - t.start[l], n, red);
-    else weights_fwd_vec<1>(L, blockIdx.x - t.start[l], n, red);
+    if (L.taps == 9) weights_fwd_vec<9, CPT>(L, blockIdx.x - t.start[l], n, red);
+    else weights_fwd_vec<1, CPT>(L, blockIdx.x - t.start[l], n, red);
 }
 
-template <int TAPS>
+template <int TAPS, int CPT>
 __device__ __forceinline__ void weights_bwd_vec(const B200BankLayer& L, int blk, int n, float* red, float* sds) {
-    const int cin = L.cin, cout = L.cout, gs = cin >> 3, cpb = 256 / gs;
-    const int o = blk * cpb + (int)threadIdx.x / gs, i0 = ((int)threadIdx.x % gs) * 8;
+    const int cin = L.cin, cout = L.cout, gs = cin / CPT, cpb = 256 / gs;
+    const int o = blk * cpb + (int)threadIdx.x / gs, i0 = ((int)threadIdx.x % gs) * CPT;
     const bool live = o < cout && (int)threadIdx.x < cpb * gs;
-    float w[TAPS * 8], dW[TAPS * 8];
+    float w[TAPS * CPT], dW[TAPS * CPT];
 #pragma unroll
-    for (int q = 0; q < TAPS * 8; ++q) { w[q] = 0.f; dW[q] = 0.f; }
+    for (int q = 0; q < TAPS * CPT; ++q) { w[q] = 0.f; dW[q] = 0.f; }
     if (live) {
         const float4* src = reinterpret_cast<const float4*>(L.weight + ((long)o * cin + i0) * TAPS);
 #pragma unroll
-        for (int q = 0; q < TAPS * 2; ++q) { const float4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+        for (int q = 0; q < TAPS * CPT / 4; ++q) { const float4 v = __ldg(src + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
     }
     for (int b = 0; b < n; ++b) {
-        float s[8], g[TAPS * 8];
+        float s[CPT], g[TAPS * CPT];
         float d = 1.f, acc = 0.f;
         if (live) {
-            const float4 s0 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0), s1 = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0 + 4);
-            s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+#pragma unroll
+            for (int q = 0; q < CPT / 4; ++q) {
+                const float4 sv = *reinterpret_cast<const float4*>(L.styles + (long)b * cin + i0 + 4 * q);
+                s[4 * q] = sv.x; s[4 * q + 1] = sv.y; s[4 * q + 2] = sv.z; s[4 * q + 3] = sv.w;
+            }
             const float* G = L.dwmod + (long)b * TAPS * cout * cin;
 #pragma unroll
             for (int tp = 0; tp < TAPS; ++tp) {
-                const float4 g0 = *reinterpret_cast<const float4*>(G + ((long)tp * cout + o) * cin + i0);
-                const float4 g1 = *reinterpret_cast<const float4*>(G + ((long)tp * cout + o) * cin + i0 + 4);
-                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                float gg[CPT];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { g[j * TAPS + tp] = gg[j]; acc = fmaf(gg[j], w[j * TAPS + tp] * s[j], acc); }
+                for (int q = 0; q < CPT / 4; ++q) {
+                    const float4 gv = *reinterpret_cast<const float4*>(G + ((long)tp * cout + o) * cin + i0 + 4 * q);
+                    gg[4 * q] = gv.x; gg[4 * q + 1] = gv.y; gg[4 * q + 2] = gv.z; gg[4 * q + 3] = gv.w;
+                }
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) { g[j * TAPS + tp] = gg[j]; acc = fmaf(gg[j], w[j * TAPS + tp] * s[j], acc); }
             }
         }
         float d3dot = 0.f;
@@ -325,12 +350,12 @@ __device__ __forceinline__ void weights_bwd_vec(const B200BankLayer& L, int blk,
             if (live) d = L.dcoef[(long)b * cout + o];
             d3dot = d * d * d * dot;
         }
-        float dsv[8];
+        float dsv[CPT];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dsv[j] = 0.f;
+        for (int j = 0; j < CPT; ++j) dsv[j] = 0.f;
         if (live) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CPT; ++j) {
 #pragma unroll
                 for (int tp = 0; tp < TAPS; ++tp) {
                     float gv = g[j * TAPS + tp] * d;
@@ -342,8 +367,9 @@ __device__ __forceinline__ void weights_bwd_vec(const B200BankLayer& L, int blk,
         }
         if (L.d_styles) {       // d styles: sum the block's couts in shared memory, then one coalesced atomic per input channel
             __syncthreads();
-            *reinterpret_cast<float4*>(sds + threadIdx.x * 8) = make_float4(dsv[0], dsv[1], dsv[2], dsv[3]);
-            *reinterpret_cast<float4*>(sds + threadIdx.x * 8 + 4) = make_float4(dsv[4], dsv[5], dsv[6], dsv[7]);
+#pragma unroll
+            for (int q = 0; q < CPT / 4; ++q)
+                *reinterpret_cast<float4*>(sds + threadIdx.x * CPT + 4 * q) = make_float4(dsv[4 * q], dsv[4 * q + 1], dsv[4 * q + 2], dsv[4 * q + 3]);
             __syncthreads();
             for (int i = threadIdx.x; i < cin; i += 256) {
                 float a = 0.f;
@@ -355,36 +381,40 @@ __device__ __forceinline__ void weights_bwd_vec(const B200BankLayer& L, int blk,
     if (live && L.d_weight) {
         float4* dst = reinterpret_cast<float4*>(L.d_weight + ((long)o * cin + i0) * TAPS);
 #pragma unroll
-        for (int q = 0; q < TAPS * 2; ++q) dst[q] = make_float4(dW[4 * q], dW[4 * q + 1], dW[4 * q + 2], dW[4 * q + 3]);
+        for (int q = 0; q < TAPS * CPT / 4; ++q) dst[q] = make_float4(dW[4 * q], dW[4 * q + 1], dW[4 * q + 2], dW[4 * q + 3]);
     }
 }
 
-__global__ void __launch_bounds__(256) bank_weights_bwd_vec_kernel(const __grid_constant__ BankTable t, int n) {
+template <int CPT>
+__global__ void __launch_bounds__(256, CPT == 4 ? 2 : 1) bank_weights_bwd_vec_kernel(const __grid_constant__ BankTable t, int n) {
     __shared__ float red[8];
-    __shared__ __align__(16) float sds[256 * 8];
+    __shared__ __align__(16) float sds[256 * CPT];
     const int l = find_layer(t, blockIdx.x);
     const B200BankLayer& L = t.l[l];
     if (!L.dwmod) return;
-    if (L.taps == 9) weights_bwd_vec<9>(L, blockIdx.x - t.start[l], n, red, sds);
-    else weights_bwd_vec<1>(L, blockIdx.x - t.start[l], n, red, sds);
+    if (L.taps == 9) weights_bwd_vec<9, CPT>(L, blockIdx.x - t.start[l], n, red, sds);
+    else weights_bwd_vec<1, CPT>(L, blockIdx.x - t.start[l], n, red, sds);
 }
 
-bool host_vec_ok(const B200BankLayer& L) {
-    const int gs = L.cin >> 3;
-    return (L.taps == 9 || L.taps == 1) && (L.cin & 7) == 0 && L.cin <= 2048 && (gs & (gs - 1)) == 0;
+bool host_vec_ok(const B200BankLayer& L, int cpt) {
+    const int gs = L.cin / cpt;
+    return (L.taps == 9 || L.taps == 1) && (L.cin & 7) == 0 && L.cin <= 256 * cpt && (gs & (gs - 1)) == 0;
 }
 
-// block table of the vectorised kernels: ceil(cout / (256 / (cin/8))) blocks per layer
-int fill_table_vec(BankTable& t, const B200BankLayer* layers, int n_layers, bool& all_vec) {
+// block table of the vectorised kernels: ceil(cout / (256 / (cin/cpt))) blocks per layer; cpt = 4 when every layer allows it
+int fill_table_vec(BankTable& t, const B200BankLayer* layers, int n_layers, bool& all_vec, int& cpt) {
     B200_REQUIRE(layers && n_layers > 0 && n_layers <= MAXL, "bank: between 1 and 32 layers");
     t.n_layers = n_layers;
     t.start[0] = 0;
+    cpt = 4;
+    for (int l = 0; l < n_layers; ++l)
+        if (layers[l].cin > 1024) cpt = 8;
     all_vec = true;
     for (int l = 0; l < n_layers; ++l) {
         t.l[l] = layers[l];
         B200_REQUIRE(layers[l].cin > 0 && layers[l].cout > 0 && layers[l].taps > 0, "bank: bad layer shape");
-        if (!host_vec_ok(layers[l])) { all_vec = false; break; }
-        const int cpb = 256 / (layers[l].cin >> 3);
+        if (!host_vec_ok(layers[l], cpt)) { all_vec = false; break; }
+        const int cpb = 256 / (layers[l].cin / cpt);
         t.start[l + 1] = t.start[l] + (layers[l].cout + cpb - 1) / cpb;
     }
     return 0;
@@ -426,9 +456,11 @@ B200_API int b200_bank_styles_fwd(const B200BankLayer* layers, int n_layers, con
 B200_API int b200_bank_weights_fwd(const B200BankLayer* layers, int n_layers, int n, void* stream) {
     BankTable t;
     bool all_vec = false;
-    if (int e = fill_table_vec(t, layers, n_layers, all_vec)) return e;
+    int cpt = 8;
+    if (int e = fill_table_vec(t, layers, n_layers, all_vec, cpt)) return e;
     if (all_vec) {
-        bank_weights_fwd_vec_kernel<<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
+        if (cpt == 4) bank_weights_fwd_vec_kernel<4><<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
+        else bank_weights_fwd_vec_kernel<8><<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
         B200_CHECK_LAUNCH();
         return 0;
     }
@@ -443,9 +475,11 @@ B200_API int b200_bank_weights_fwd(const B200BankLayer* layers, int n_layers, in
 B200_API int b200_bank_weights_bwd(const B200BankLayer* layers, int n_layers, int n, void* stream) {
     BankTable t;
     bool all_vec = false;
-    if (int e = fill_table_vec(t, layers, n_layers, all_vec)) return e;
+    int cpt = 8;
+    if (int e = fill_table_vec(t, layers, n_layers, all_vec, cpt)) return e;
     if (all_vec) {
-        bank_weights_bwd_vec_kernel<<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
+        if (cpt == 4) bank_weights_bwd_vec_kernel<4><<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
+        else bank_weights_bwd_vec_kernel<8><<<t.start[n_layers], 256, 0, (cudaStream_t)stream>>>(t, n);
         B200_CHECK_LAUNCH();
         return 0;
     }

@@ -744,3 +744,51 @@ def test_depths_coarse_range_and_fine_depths_inside(b2, M, S):
         t_f = torch.empty(M, S, device='cuda')
         call('b200_ray_importance', ptr(t_c), ptr(sig), ptr(u2), ptr(t_f), M, S, S, stream())
         assert (t_f >= t_c.min(dim=1, keepdim=True).values).all() and (t_f <= t_c.max(dim=1, keepdim=True).values).all()
+
+
+@pytest.mark.parametrize('n', [1, 2])
+@pytest.mark.parametrize('table', ['eg3d', 'odd'])
+def test_bank_weight_kernels_match_per_layer_prep(b2, table, n):
+    """The grouped ('bank') weight kernels -- every layer of a synthesis network in one launch (b200_bank_weights_fwd / _bwd,
+    networks_stylegan2.py:58-67 and its backward) -- against the per-layer entry points b200_modconv_weight_prep(_bwd) on the same
+    styles: modulated weights as fp32 and as the split-bf16 pair, demodulation coefficients, d W and d styles.  'eg3d' = shapes the
+    vectorised kernels take (every layer of the 512-128 generator has one of them), 'odd' adds a channel count that sends the whole
+    table down the generic kernels."""
+    import ctypes
+    from b200eg3d import _lib
+    from b200eg3d._lib import call, ptr, stream
+    shapes = [(512, 512, 9, 1), (256, 512, 9, 1), (128, 256, 9, 1), (64, 128, 9, 1), (64, 64, 9, 1), (128, 32, 9, 1), (3, 512, 1, 0), (3, 64, 1, 0),
+              (96, 256, 9, 1), (32, 16, 9, 1), (3, 8, 1, 0)]
+    if table == 'odd':
+        shapes = shapes[:3] + [(40, 24, 9, 1), (3, 24, 1, 0)]
+    g = gen(17 + n)
+    arr = (_lib.BankLayer * len(shapes))()
+    keep = []
+    for l, (cout, cin, taps, demod) in enumerate(shapes):
+        W = torch.randn(cout, cin, taps, generator=g).cuda()
+        s = (torch.randn(n, cin, generator=g) * 0.5 + 1.0).cuda()
+        t = dict(W=W, s=s, dcoef=torch.zeros(n, cout, device='cuda'), wmod=torch.zeros(n, taps, cout, cin, device='cuda'),
+                 w_hi=torch.zeros(n, taps, cout, cin, device='cuda', dtype=torch.bfloat16), w_lo=torch.zeros(n, taps, cout, cin, device='cuda', dtype=torch.bfloat16),
+                 dwmod=(torch.randn(n, taps, cout, cin, generator=g)).cuda(), dW=torch.zeros(cout, cin, taps, device='cuda'), ds=torch.zeros(n, cin, device='cuda'))
+        keep.append(t)
+        e = arr[l]
+        e.weight, e.styles, e.dcoef, e.wmod, e.w_hi, e.w_lo = ptr(W), ptr(s), ptr(t['dcoef']) if demod else None, ptr(t['wmod']), ptr(t['w_hi']), ptr(t['w_lo'])
+        e.dwmod, e.d_weight, e.d_styles = ptr(t['dwmod']), ptr(t['dW']), ptr(t['ds'])
+        e.widx, e.cin, e.cout, e.taps, e.demod, e.post_scale = 0, cin, cout, taps, demod, 1.0
+    call('b200_bank_weights_fwd', ctypes.addressof(arr), len(shapes), n, stream())
+    call('b200_bank_weights_bwd', ctypes.addressof(arr), len(shapes), n, stream())
+    for (cout, cin, taps, demod), t in zip(shapes, keep):
+        wmod, hi, lo = torch.empty_like(t['wmod']), torch.empty_like(t['w_hi']), torch.empty_like(t['w_lo'])
+        dcoef = torch.ones(n, cout, device='cuda')
+        call('b200_modconv_weight_prep', ptr(t['W']), ptr(t['s']), ptr(wmod), ptr(hi), ptr(lo), ptr(dcoef) if demod else None, n, cout, cin, taps, demod, stream())
+        dW, ds = torch.empty_like(t['dW']), torch.empty_like(t['ds'])
+        call('b200_modconv_weight_prep_bwd', ptr(t['W']), ptr(t['s']), ptr(dcoef) if demod else None, ptr(t['dwmod']), ptr(dW), ptr(ds), n, cout, cin, taps, demod, stream())
+        tag = (cout, cin, taps)
+        scale = wmod.abs().max().item()
+        assert maxdiff(t['wmod'], wmod) <= 2e-6 * scale, tag
+        if demod:
+            assert relerr(t['dcoef'], dcoef) < 1e-6, tag
+        # the pair reconstructs the fp32 weight to ~2^-17 (two bf16 roundings); both paths split the same way
+        assert maxdiff(t['w_hi'].float() + t['w_lo'].float(), wmod) <= 2e-5 * scale, tag
+        assert maxdiff(t['w_hi'].float(), hi.float()) <= 2 ** -7 * scale, tag            # (a rounding boundary may flip one bf16 ulp)
+        assert relerr(t['dW'], dW) < 2e-5 and relerr(t['ds'], ds) < 2e-5, tag
