@@ -487,6 +487,39 @@ __global__ void __launch_bounds__(256) layer_act_bwd_fast_kernel(const float4* _
     if (NOISE && dstrength && threadIdx.x == 0) atomicAdd(dstrength, s_str);
 }
 
+// c <= 4 channels (the ToRGB images), no noise input, fp32 in / out: one thread per pixel, the warp reads 32 * c consecutive floats;
+// d bias reduced per warp, then per block, one atomic per channel and block.  (The warp-per-pixel kernel above ran 3 of 32 lanes.)
+__global__ void __launch_bounds__(256) layer_act_bwd_thin_kernel(const float* __restrict__ dz, const float* __restrict__ z,
+                                                                 float* __restrict__ dy, float* __restrict__ dbias, long npix, int c,
+                                                                 int lrelu, float alpha, float gain, float clamp) {
+    __shared__ float s_col[4];
+    if (threadIdx.x < 4) s_col[threadIdx.x] = 0.f;
+    __syncthreads();
+    float col[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            if (ch < c) {
+                const float zz = z[pix * c + ch];
+                float g = dz[pix * c + ch] * gain;
+                if (lrelu && !(zz > 0.f)) g *= alpha;
+                if (clamp >= 0.f && !(zz > -clamp && zz < clamp)) g = 0.f;
+                dy[pix * c + ch] = g;
+                col[ch] += g;
+            }
+        }
+    }
+    if (dbias) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+            const float v = warp_sum(col[ch]);
+            if ((threadIdx.x & 31) == 0 && ch < c) atomicAdd(&s_col[ch], v);
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < c) atomicAdd(dbias + threadIdx.x, s_col[threadIdx.x]);
+    }
+}
+
 B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi, void* dy_lo,
                                 float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise,
                                 int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
@@ -532,6 +565,12 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_h
         return 0;
     }
     B200_REQUIRE(!dy_hi, "layer_act_bwd: bf16 outputs need a channel count that is a multiple of 4");
+    if (c <= 4 && z && dy && !noise) {        // the 3-channel ToRGB outputs: a thread per pixel instead of a warp per pixel
+        const long nb = (npix + 255) / 256;
+        layer_act_bwd_thin_kernel<<<(int)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, st>>>(dz, z, dy, dbias, npix, c, lrelu, alpha, gain, clamp);
+        B200_CHECK_LAUNCH();
+        return 0;
+    }
     const int blocks = (int)((npix + 7) / 8 < 148 * 8 ? (npix + 7) / 8 : 148 * 8);
 #define LAUNCH_R(R) layer_act_bwd_kernel<R><<<blocks, 256, 0, st>>>(dz, z, (const __nv_bfloat16*)z_hi, (const __nv_bfloat16*)z_lo, dy, (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, dbias, \
                                                                      noise, strength, noise_bs, dstrength, dnoise, npix, hw, c, lrelu, \

@@ -783,6 +783,22 @@ def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp,
     return z, ((zh, zl) if zh is not None else None)
 
 
+def _off_chain(bank, tensors, fn):
+    """Run fn() (a weight-gradient launch whose only consumer is the bank's backward) on the weight-gradient stream behind the work
+    queued on the current one; in place when there is no bank / no such stream."""
+    if bank is None or not CONFIG['wgrad_stream']:
+        fn()
+        return
+    ws = wgrad_stream(tensors[0].device)
+    bank.wstream = ws                           # _Bank.backward joins it (the same per-device stream WeightBank.dwslice picks)
+    ws.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ws):
+        fn()
+    for t in tensors:
+        if t is not None:
+            t.record_stream(ws)
+
+
 class _ToRGB(torch.autograd.Function):
     """img = [upsample2d(img_prev)] + clamp(conv1x1(x, W*styles) + bias, +-clamp)     (networks_stylegan2.py:353-357, 451-457)
 
@@ -890,10 +906,14 @@ class _ToRGB(torch.autograd.Function):
                  n, h * w, cimg, 0, 0.0, 1.0, cl, stream())
             if need_x:
                 call('b200_conv_dgrad', ptr(dy), ptr(wm), ptr(dx), n, h, w, cin, cimg, 1, 1, stream())
+            # the thin weight gradients feed only the bank's backward: on the weight-gradient stream, so that this node (and with it
+            # the main chain waiting for dx) ends after the dgrad
             if need_w and split_x:
-                call('b200_conv1x1_wgrad_split', ptr(xs), ptr(xs_lo), ptr(dy), ptr(dwmod), n, h * w, cin, cimg, stream())
+                _off_chain(bank, (xs, xs_lo, dy, dwmod), lambda: call(
+                    'b200_conv1x1_wgrad_split', ptr(xs), ptr(xs_lo), ptr(dy), ptr(dwmod), n, h * w, cin, cimg, stream()))
             elif need_w:
-                call('b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream())
+                _off_chain(bank, (xs, dy, dwmod), lambda: call(
+                    'b200_conv_wgrad', ptr(xs), ptr(dy), ptr(dwmod), n, h, w, cin, cimg, 1, 1, stream()))
         if need_w and bank is not None:
             bank.dwmod[lidx] = dwmod
         elif need_w:
