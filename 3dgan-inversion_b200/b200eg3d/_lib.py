@@ -14,7 +14,7 @@ _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 
 # b200_version() this binding table was written for.  Bumped together with csrc/conv_api.cu whenever a prototype changes: a
 # stale or variant .so (B200EG3D_LIB) with other argument lists would otherwise be called with the wrong stack layout.
-EXPECTED_VERSION = 205
+EXPECTED_VERSION = 206
 
 # name -> argument ctypes (every function returns int status; 0 = ok)
 SIGNATURES = {
@@ -37,6 +37,7 @@ SIGNATURES = {
     'b200_layer_act_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_layer_act_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_conv1x1_wgrad_split': [_P, _P, _P, _P, _I, _L, _I, _I, _P],
+    'b200_conv1x1_fwd_thin': [_P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
     'b200_upfirdn2d': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],
     'b200_upfirdn2d_fused': [_P] * 6 + [_I] * 13 + [_F, _I, _P, _P, _P, _L, _I, _F, _F, _F, _I, _P],
     'b200_triplane_mlp_fwd': [_P, _I, _I, _I, _P, _P, _P, _P, _I, _I, _L, _F, _P, _P, _P, _P, _F, _P, _P, _P, _P],
@@ -106,6 +107,8 @@ def load():
     lib.b200_conv_tc_supported.argtypes = [_I] * 7
     lib.b200_conv1x1_thin_supported.restype = ctypes.c_int
     lib.b200_conv1x1_thin_supported.argtypes = [_I, _I]
+    lib.b200_conv1x1_fwd_thin_supported.restype = ctypes.c_int
+    lib.b200_conv1x1_fwd_thin_supported.argtypes = [_I, _I]
     lib.b200_conv_tc_ksplit.restype = ctypes.c_int
     lib.b200_conv_tc_ksplit.argtypes = [_I] * 8
     lib.b200_conv_tc_act_fusable.restype = ctypes.c_int

@@ -103,8 +103,22 @@ B200_API int b200_conv1x1_wgrad_split(const void* x_hi, const void* x_lo, const 
     return launch_conv_wgrad_thin(nullptr, x_hi, x_lo, dy, dwmod, n, npix, cout, cin, (cudaStream_t)stream);
 }
 
+// Forward of such a layer from the split pair, bias and clamp included: y [n][npix][cout] = clamp((x_hi + x_lo) . wmod^T + bias).
+// wmod [n][cout][cin] fp32; bias [cout] or NULL; clamp < 0: none.  Shapes: b200_conv1x1_fwd_thin_supported.
+B200_API int b200_conv1x1_fwd_thin_supported(int cin, int cout) {
+    const int lpp = cin >> 3;
+    return cout >= 1 && cout <= 4 && cin % 8 == 0 && cin >= 8 && cin <= 512 && (lpp & (lpp - 1)) == 0;
+}
+B200_API int b200_conv1x1_fwd_thin(const void* x_hi, const void* x_lo, const float* wmod, const float* bias, float* y, int n, long npix,
+                                   int cin, int cout, float clamp, void* stream) {
+    B200_REQUIRE(b200_conv1x1_fwd_thin_supported(cin, cout), "conv1x1_fwd_thin: needs cout <= 4 and cin a power of two in 8 .. 512");
+    B200_REQUIRE(x_hi && x_lo && wmod && y, "conv1x1_fwd_thin: null pointer");
+    if (n <= 0 || npix <= 0) return 0;
+    return launch_conv_fwd_thin(x_hi, x_lo, wmod, bias, y, n, npix, cout, cin, clamp, (cudaStream_t)stream);
+}
+
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 205; }
+B200_API int b200_version() { return 206; }
 
 // Programmatic dependent launch on (1) / off (0) for subsequent launches; returns the previous setting.  Profiling aid: with PDL a
 // traced kernel duration includes the time it waits for its predecessor.

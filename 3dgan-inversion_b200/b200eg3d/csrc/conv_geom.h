@@ -35,3 +35,5 @@ int launch_conv_wgrad_simt(ConvWgradParams p, int batch, cudaStream_t st);
 int launch_conv_wgrad_thin(const float* x, const void* x_hi, const void* x_lo, const float* dy, float* dW, int batch, long npix, int cm, int cn,
                            cudaStream_t st);
 int launch_conv_dgrad_thin(const float* dy, const float* w, float* dx, int batch, long npix, int cm, int cn, cudaStream_t st);
+int launch_conv_fwd_thin(const void* x_hi, const void* x_lo, const float* w, const float* bias, float* y, int batch, long npix, int cm,
+                         int cn, float clamp, cudaStream_t st);

@@ -294,6 +294,79 @@ int launch_conv_wgrad_thin(const float* x, const void* x_hi, const void* x_lo, c
     return 0;
 }
 
+// Thin forward of a 1x1 convolution with <= 4 output channels whose input exists as its split-bf16 pair (the ToRGB layers of the
+// super-resolution blocks: 64 / 128 input channels at 512^2 / 256^2), with the layer's bias and clamp applied on the way out:
+//   y[pix][o] = clamp(sum_c (x_hi + x_lo)[pix][c] * w[o][c] + bias[o]).
+// A streaming read of x (HBM-bound); a 128-wide tensor-core tile would compute 125 columns of padding and write the raw sum for a
+// second (bias + clamp) pass.  LPP = cin / 8 lanes share a pixel (8 channels each, one 16-byte load per half), their partial sums are
+// combined with shuffles; a lane's 8 x cout weights stay in registers.
+template <int NCH>
+__global__ void __launch_bounds__(256) conv_fwd_thin_kernel(const uint4* __restrict__ xhi, const uint4* __restrict__ xlo,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            float* __restrict__ y, long npix, int cm, int cn, int lpp, float clamp) {
+    const int b = blockIdx.y;
+    const long xoff = (long)b * npix * (cn >> 3);
+    xhi += xoff; xlo += xoff; y += (long)b * npix * cm; w += (long)b * cm * cn;
+    const int lane = threadIdx.x & 31, sub = lane / lpp, cl = lane % lpp;
+    const int ppw = 32 / lpp;                                        // pixels per warp and iteration
+    float wr[NCH][4][8];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wr[ch][m][j] = m < cm ? w[m * cn + (ch * lpp + cl) * 8 + j] : 0.f;
+    float bv[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) bv[m] = (bias && m < cm) ? bias[m] : 0.f;
+    const long warp0 = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long p0 = warp0 * ppw; p0 < npix; p0 += nwarps * ppw) {
+        const long pix = p0 + sub;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (pix < npix) {
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const long vi = pix * (cn >> 3) + ch * lpp + cl;
+                const uint4 h = __ldg(xhi + vi), l = __ldg(xlo + vi);
+                const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {                       // two bf16 per word: low half = even channel
+                    const float x0 = __uint_as_float(hw[q] << 16) + __uint_as_float(lw[q] << 16);
+                    const float x1 = __uint_as_float(hw[q] & 0xffff0000u) + __uint_as_float(lw[q] & 0xffff0000u);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) acc[m] = fmaf(x1, wr[ch][m][2 * q + 1], fmaf(x0, wr[ch][m][2 * q], acc[m]));
+                }
+            }
+        }
+        for (int o = lpp >> 1; o > 0; o >>= 1) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+        }
+        if (cl == 0 && pix < npix) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                if (m < cm) {
+                    float t = acc[m] + bv[m];
+                    if (clamp >= 0.f) t = fminf(fmaxf(t, -clamp), clamp);
+                    y[pix * cm + m] = t;
+                }
+        }
+    }
+}
+
+int launch_conv_fwd_thin(const void* x_hi, const void* x_lo, const float* w, const float* bias, float* y, int batch, long npix, int cm,
+                         int cn, float clamp, cudaStream_t st) {
+    if (npix <= 0 || batch <= 0) return 0;
+    int lpp = cn >> 3, nch = 1;
+    if (lpp > 32) { nch = lpp / 32; lpp = 32; }
+    const long nb = (npix * lpp + 255) / 256;
+    dim3 grid((unsigned)(nb < 148 * 8 ? nb : 148 * 8), batch);
+    if (nch == 1) conv_fwd_thin_kernel<1><<<grid, 256, 0, st>>>((const uint4*)x_hi, (const uint4*)x_lo, w, bias, y, npix, cm, cn, lpp, clamp);
+    else conv_fwd_thin_kernel<2><<<grid, 256, 0, st>>>((const uint4*)x_hi, (const uint4*)x_lo, w, bias, y, npix, cm, cn, lpp, clamp);
+    B200_CHECK_LAUNCH();
+    return 0;
+}
+
 // Thin data gradient of a 1x1 convolution with <= 4 output channels (the ToRGB layers of the super-resolution blocks):
 // dx[pix][ci] = sum_o dy[pix][o] * w[o][ci] is a streaming write of the cin-wide activation gradient -- one thread per
 // (pixel, 4 input channels), weights in shared memory.

@@ -36,14 +36,28 @@ __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// min / max of a thread's values -> the two order-preserving words (one atomic pair per warp)
-__device__ __forceinline__ void warp_minmax_commit(float lo, float hi, unsigned* __restrict__ mm) {
+// min / max of a block's values -> the two order-preserving words: warp shuffles, then one warp over the per-warp results, ONE
+// atomic pair per block (a pair per warp -- ~10 000 same-address atomics -- tripled the time of the kernel that makes the depths)
+__device__ __forceinline__ void block_minmax_commit(float lo, float hi, unsigned* __restrict__ mm) {
+    __shared__ float s_lo[32], s_hi[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
         hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     }
-    if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_lo[wid] = lo; s_hi[wid] = hi; }
+    __syncthreads();
+    if (wid == 0) {
+        lo = lane < nw ? s_lo[lane] : FLT_MAX;
+        hi = lane < nw ? s_hi[lane] : -FLT_MAX;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0 && lo <= hi) { atomicMin(mm, f2ord(lo)); atomicMax(mm + 1, f2ord(hi)); }
+    }
 }
 
 __global__ void depths_coarse_kernel(const float* __restrict__ t_base, const float* __restrict__ u, float* __restrict__ t,
@@ -54,7 +68,7 @@ __global__ void depths_coarse_kernel(const float* __restrict__ t_base, const flo
         t[i] = v;
         lo = fminf(lo, v); hi = fmaxf(hi, v);
     }
-    if (mm) warp_minmax_commit(lo, hi, mm);          // the depth clamp's global range, gathered where the depths are made
+    if (mm) block_minmax_commit(lo, hi, mm);         // the depth clamp's global range, gathered where the depths are made
 }
 
 __global__ void depth_minmax_kernel(const float* __restrict__ t, long total, unsigned* __restrict__ mm) {
@@ -63,7 +77,7 @@ __global__ void depth_minmax_kernel(const float* __restrict__ t, long total, uns
         const float v = t[i];
         lo = fminf(lo, v); hi = fmaxf(hi, v);
     }
-    warp_minmax_commit(lo, hi, mm);
+    block_minmax_commit(lo, hi, mm);
 }
 
 // alpha_k / weights of the mid-point rule on SORTED samples held in shared memory (lane-strided + lane-0 scan)

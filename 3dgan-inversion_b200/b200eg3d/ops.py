@@ -840,13 +840,18 @@ class _ToRGB(torch.autograd.Function):
             y = torch.empty([n, h, w, cimg], device=dev, dtype=torch.float32)
         if (tc_f or tc_b) and (x_hi is None or x_lo is None):
             x_hi, x_lo = _split(x, True)
-        if tc_f:
-            call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cimg, 1, 1, fp, pz, stream())
-        else:
-            call('b200_conv_fwd', ptr(_f32c(x)), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
         b = _f32c(bias)
         cl = float(clamp if clamp is not None else -1)
-        call('b200_bias_act', ptr(y), ptr(b), None, None, None, ptr(y), 0, y.numel(), 1, cimg, 1, 0.0, 1.0, cl, stream())
+        if have_split and wmod is not None and _lib.load().b200_conv1x1_fwd_thin_supported(cin, cimg) == 1:
+            # 3-channel images from 64 / 128 input channels: a streaming dot product over the split pair with bias and clamp on the
+            # way out, instead of a 128-wide tensor-core tile (125 columns of padding) plus a bias / clamp pass
+            call('b200_conv1x1_fwd_thin', ptr(x_hi), ptr(x_lo), ptr(wmod), ptr(b), ptr(y), n, h * w, cin, cimg, cl, stream())
+        else:
+            if tc_f:
+                call('b200_conv_fwd_tc', ptr(x_hi), ptr(x_lo), ptr(w_hi), ptr(w_lo), ptr(y), n, h, w, cin, cimg, 1, 1, fp, pz, stream())
+            else:
+                call('b200_conv_fwd', ptr(_f32c(x)), ptr(wmod), ptr(y), n, h, w, cin, cimg, 1, 1, stream())
+            call('b200_bias_act', ptr(y), ptr(b), None, None, None, ptr(y), 0, y.numel(), 1, cimg, 1, 0.0, 1.0, cl, stream())
         if img_prev is not None:
             img = _upfirdn_nhwc_raw(_f32c(img_prev), fir_filter(dev), (2, 2), (1, 1), (2, 1, 2, 1), False, 4.0, add=y)
         else:

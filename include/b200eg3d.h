@@ -88,6 +88,12 @@ int b200_conv_wgrad(const float* x, const float* dy, float* dwmod, int n, int h,
 int b200_conv1x1_thin_supported(int cin, int cout);
 int b200_conv1x1_wgrad_split(const void* x_hi, const void* x_lo, const float* dy, float* dwmod, int n, long npix, int cin, int cout,
                              void* stream);
+/* The forward of such a layer from the split pair with the ToRGB bias and clamp (networks_stylegan2.py:353-357) applied on the way
+ * out: y [n][npix][cout] = clamp((x_hi + x_lo) . wmod^T + bias, +-clamp).  wmod [n][cout][cin] fp32, bias [cout] or NULL, clamp < 0:
+ * none.  b200_conv1x1_fwd_thin_supported -> 1 if handled (cout <= 4, cin a power of two in 8 .. 512). */
+int b200_conv1x1_fwd_thin_supported(int cin, int cout);
+int b200_conv1x1_fwd_thin(const void* x_hi, const void* x_lo, const float* wmod, const float* bias, float* y, int n, long npix, int cin,
+                          int cout, float clamp, void* stream);
 
 /* tcgen05 / TMA tensor-core convolutions on split-bf16 operands (same geometry as above).
  * npass = 3: hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM (fp32-parity mode); npass = 1: hi*hi only (lo may be NULL).

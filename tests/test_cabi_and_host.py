@@ -36,7 +36,7 @@ def test_ctypes_table_matches_header():
     from b200eg3d import _lib
     syms = set(declared_symbols())
     bound = set(_lib.SIGNATURES) | {'b200_version', 'b200_last_error', 'b200_set_pdl', 'b200_set_mlp_passes', 'b200_set_triplane_impl', 'b200_conv_tc_supported', 'b200_triplane_bwd_workspace_bytes', 'b200_triplane_fsave_bytes',
-                                        'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable', 'b200_set_conv_pair', 'b200_conv1x1_thin_supported', 'b200_conv_tc_ksplit'}
+                                        'b200_noise_pyramid_work_floats', 'b200_conv_tc_act_fusable', 'b200_set_conv_pair', 'b200_conv1x1_thin_supported', 'b200_conv_tc_ksplit', 'b200_conv1x1_fwd_thin_supported'}
     assert syms == bound, (sorted(syms - bound), sorted(bound - syms))
     src = re.sub(r'/\*.*?\*/', '', open(HEADER).read(), flags=re.S)
     for name, args in _lib.SIGNATURES.items():      # argument counts agree with the prototypes

@@ -792,3 +792,28 @@ def test_bank_weight_kernels_match_per_layer_prep(b2, table, n):
         assert maxdiff(t['w_hi'].float() + t['w_lo'].float(), wmod) <= 2e-5 * scale, tag
         assert maxdiff(t['w_hi'].float(), hi.float()) <= 2 ** -7 * scale, tag            # (a rounding boundary may flip one bf16 ulp)
         assert relerr(t['dW'], dW) < 2e-5 and relerr(t['ds'], ds) < 2e-5, tag
+
+
+@pytest.mark.parametrize('cin,cout,npix,n,clamp', [(64, 3, 4097, 1, 256.0), (128, 3, 1000, 2, 0.5), (8, 1, 33, 1, -1.0), (512, 4, 260, 1, 1.0),
+                                                    (32, 3, 7, 3, -1.0)])
+def test_conv1x1_fwd_thin(b2, cin, cout, npix, n, clamp):
+    """b200_conv1x1_fwd_thin (the super-resolution ToRGB layers: modulated 1x1 convolution to <= 4 channels from the split-bf16 pair,
+    bias and clamp applied on the way out; networks_stylegan2.py:353-357) against the same sum in fp64."""
+    from b200eg3d._lib import call, ptr, stream
+    g = gen(cin * 7 + cout + npix)
+    x = torch.randn(n, npix, cin, generator=g).cuda()
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    wmod = (torch.randn(n, cout, cin, generator=g) / cin ** 0.5).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    y = torch.empty(n, npix, cout, device='cuda')
+    assert b2._lib.load().b200_conv1x1_fwd_thin_supported(cin, cout) == 1
+    call('b200_conv1x1_fwd_thin', ptr(hi), ptr(lo), ptr(wmod), ptr(bias), ptr(y), n, npix, cin, cout, float(clamp), stream())
+    ref = torch.einsum('npc,noc->npo', (hi.double() + lo.double()), wmod.double()) + bias.double()
+    if clamp >= 0:
+        ref = ref.clamp(-clamp, clamp)
+    assert maxdiff(y, ref) < 2e-5
+    y2 = torch.empty_like(y)
+    call('b200_conv1x1_fwd_thin', ptr(hi), ptr(lo), ptr(wmod), None, ptr(y2), n, npix, cin, cout, -1.0, stream())
+    assert maxdiff(y2, torch.einsum('npc,noc->npo', (hi.double() + lo.double()), wmod.double())) < 2e-5
+    assert b2._lib.load().b200_conv1x1_fwd_thin_supported(24, 3) == 0 and b2._lib.load().b200_conv1x1_fwd_thin_supported(64, 5) == 0
