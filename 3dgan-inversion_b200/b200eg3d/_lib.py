@@ -14,7 +14,7 @@ _P, _I, _L, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float
 
 # b200_version() this binding table was written for.  Bumped together with csrc/conv_api.cu whenever a prototype changes: a
 # stale or variant .so (B200EG3D_LIB) with other argument lists would otherwise be called with the wrong stack layout.
-EXPECTED_VERSION = 206
+EXPECTED_VERSION = 207
 
 # name -> argument ctypes (every function returns int status; 0 = ok)
 SIGNATURES = {
@@ -36,6 +36,8 @@ SIGNATURES = {
     'b200_bias_act': [_P, _P, _P, _P, _P, _P, _I, _L, _L, _I, _I, _F, _F, _F, _P],
     'b200_layer_act_fwd': [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _F, _F, _F, _P],
     'b200_layer_act_bwd': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200_layer_act_bwd_sum2': [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P],
+    'b200_layer_act_bwd_sum2_supported': [_I, _I, _I, _I, _L],
     'b200_conv1x1_wgrad_split': [_P, _P, _P, _P, _I, _L, _I, _I, _P],
     'b200_conv1x1_fwd_thin': [_P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P],
     'b200_upfirdn2d': [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P],

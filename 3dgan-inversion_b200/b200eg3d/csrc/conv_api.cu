@@ -118,7 +118,7 @@ B200_API int b200_conv1x1_fwd_thin(const void* x_hi, const void* x_lo, const flo
 }
 
 B200_API const char* b200_last_error() { return g_b200_err; }
-B200_API int b200_version() { return 206; }
+B200_API int b200_version() { return 207; }
 
 // Programmatic dependent launch on (1) / off (0) for subsequent launches; returns the previous setting.  Profiling aid: with PDL a
 // traced kernel duration includes the time it waits for its predecessor.

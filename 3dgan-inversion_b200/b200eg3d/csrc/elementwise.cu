@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) layer_act_bwd_vec_kernel(const float4* __
 // of one warp, so its channel sum is a few shuffles): 32-bit indices, no run-time flag tests in the element loop.
 // (ncu on the generic kernel: 43 instructions per element, a third of them flag tests and 64-bit index math.)
 template <bool ZSPLIT, bool OSPLIT, bool NOISE, int VPT>
-__global__ void __launch_bounds__(256) layer_act_bwd_fast_kernel(const float4* __restrict__ dz, const float4* __restrict__ z,
+__global__ void __launch_bounds__(256) layer_act_bwd_fast_kernel(const float4* __restrict__ dz, const float4* __restrict__ dz2, const float4* __restrict__ z,
                                                                  const uint2* __restrict__ zhi, const uint2* __restrict__ zlo,
                                                                  float4* __restrict__ dy, uint2* __restrict__ dyhi, uint2* __restrict__ dylo,
                                                                  float* __restrict__ dbias, const float* __restrict__ noise,
@@ -436,7 +436,11 @@ __global__ void __launch_bounds__(256) layer_act_bwd_fast_kernel(const float4* _
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const unsigned i = pix * (unsigned)c4 + cc + k * L;
-                const float4 dd = __ldg(dz + i);
+                float4 dd = __ldg(dz + i);
+                if (dz2) {                            // second consumer's gradient (b200_layer_act_bwd_sum2): summed here, not in a pass of its own
+                    const float4 ee = __ldg(dz2 + i);
+                    dd.x += ee.x; dd.y += ee.y; dd.z += ee.z; dd.w += ee.w;
+                }
                 float zv[4];
                 if (ZSPLIT) {
                     const uint2 h2 = __ldg(zhi + i);
@@ -520,9 +524,20 @@ __global__ void __launch_bounds__(256) layer_act_bwd_thin_kernel(const float* __
     }
 }
 
-B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi, void* dy_lo,
-                                float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise,
-                                int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
+// Shapes the compile-time specialised kernel takes: channel vectors of a pixel inside one warp (a power-of-two count when the noise
+// gradient needs the shuffle sum), 32-bit element indices.
+static bool act_bwd_fast_shape(long npix, int c, bool has_noise, long n, long noise_bs) {
+    if (c <= 0 || c % 4 != 0 || c > 512) return false;
+    const int c4 = c / 4;
+    const int vpt = c4 <= 32 ? 1 : (c4 <= 64 ? 2 : 4);
+    const int lanes = c4 / vpt;
+    const bool pow2 = (lanes & (lanes - 1)) == 0;
+    return c4 % vpt == 0 && lanes <= 32 && (pow2 || !has_noise) && npix * c4 < (1L << 31) && n * noise_bs < (1L << 31);
+}
+
+static int layer_act_bwd_impl(const float* dz, const float* dz2, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi, void* dy_lo,
+                              float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise,
+                              int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
     // dbias / dstrength / dnoise are ACCUMULATED into (callers zero them); any of them may be null.
     // The saved output comes as fp32 z, or (z == NULL) as its split-bf16 copy z_hi (+ z_lo, needed for the clamp test only).
     const long npix = (long)n * hw;
@@ -540,15 +555,14 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_h
         // vectors per thread: keep a pixel's threads inside one warp (needed for the shuffle sum when there is a noise input)
         const int vpt = c4 <= 32 ? 1 : (c4 <= 64 ? 2 : 4);
         const int lanes = c4 / vpt;
-        const bool pow2 = (lanes & (lanes - 1)) == 0;
-        if (c4 % vpt == 0 && lanes <= 32 && (pow2 || !noise) && npix * c4 < (1L << 31) && (osplit || ofp32) && (!noise || strength) &&
-            (zsplit ? (z_lo != nullptr || clamp < 0.f) : true) && (long)n * noise_bs < (1L << 31)) {
+        if (act_bwd_fast_shape(npix, c, noise != nullptr, n, noise_bs) && (osplit || ofp32) && (!noise || strength) &&
+            (zsplit ? (z_lo != nullptr || clamp < 0.f) : true)) {
             const float gneg = lrelu ? gain * alpha : gain;
             const int ppb2 = 256 / lanes;
             const long nb2 = (npix + ppb2 - 1) / ppb2;
             const int blocks2 = (int)(nb2 < 148 * 8 ? nb2 : 148 * 8);
 #define LAUNCH_F(ZS, OS, NZ, V) B200_CUDA(launch_pdl(layer_act_bwd_fast_kernel<ZS, OS, NZ, V>, dim3(blocks2), dim3(256), 0, st, (const float4*)dz, \
-                (const float4*)z, (const uint2*)z_hi, (const uint2*)z_lo, (float4*)dy, (uint2*)dy_hi, (uint2*)dy_lo, dbias, noise, strength, \
+                (const float4*)dz2, (const float4*)z, (const uint2*)z_hi, (const uint2*)z_lo, (float4*)dy, (uint2*)dy_hi, (uint2*)dy_lo, dbias, noise, strength, \
                 (unsigned)noise_bs, dstrength, dnoise, (unsigned)npix, (unsigned)hw, c4, gneg, gain, clamp))
 #define LAUNCH_V(ZS, OS, NZ) do { if (vpt == 1) LAUNCH_F(ZS, OS, NZ, 1); else if (vpt == 2) LAUNCH_F(ZS, OS, NZ, 2); else LAUNCH_F(ZS, OS, NZ, 4); } while (0)
             if (zsplit) { if (osplit) { if (noise) LAUNCH_V(true, true, true); else LAUNCH_V(true, true, false); }
@@ -559,12 +573,14 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_h
 #undef LAUNCH_F
             return 0;
         }
+        B200_REQUIRE(!dz2, "layer_act_bwd_sum2: this shape takes the generic kernels, which read one gradient (b200_layer_act_bwd_sum2_supported)");
         B200_CUDA(launch_pdl(layer_act_bwd_vec_kernel, dim3(blocks), dim3(256), 0, st, (const float4*)dz, (const float4*)z, (const uint2*)z_hi,
                              (const uint2*)z_lo, (float4*)dy, (uint2*)dy_hi,
                              (uint2*)dy_lo, dbias, noise, strength, noise_bs, dstrength, dnoise, npix, hw, c4, lrelu, alpha, gain, clamp));
         return 0;
     }
     B200_REQUIRE(!dy_hi, "layer_act_bwd: bf16 outputs need a channel count that is a multiple of 4");
+    B200_REQUIRE(!dz2, "layer_act_bwd_sum2: the channel count must be a multiple of 4 (b200_layer_act_bwd_sum2_supported)");
     if (c <= 4 && z && dy && !noise) {        // the 3-channel ToRGB outputs: a thread per pixel instead of a warp per pixel
         const long nb = (npix + 255) / 256;
         layer_act_bwd_thin_kernel<<<(int)(nb < 148 * 8 ? nb : 148 * 8), 256, 0, st>>>(dz, z, dy, dbias, npix, c, lrelu, alpha, gain, clamp);
@@ -580,6 +596,28 @@ B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_h
 #undef LAUNCH_R
     B200_CHECK_LAUNCH();
     return 0;
+}
+
+B200_API int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi, void* dy_lo,
+                                float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise,
+                                int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
+    return layer_act_bwd_impl(dz, nullptr, z, z_hi, z_lo, dy, dy_hi, dy_lo, dbias, noise, strength, noise_bs, dstrength, dnoise, n, hw, c, lrelu,
+                              alpha, gain, clamp, stream);
+}
+
+// The same with the incoming gradient given as two addends (an activation with two consumers -- the next convolution and the block's
+// ToRGB layer: autograd would sum the two gradients in a pass of its own, 3 x 4 bytes per element; here the second is one more load).
+// dz + dz2 is formed in fp32 exactly as that pass would.  Shapes: b200_layer_act_bwd_sum2_supported.
+B200_API int b200_layer_act_bwd_sum2(const float* dz, const float* dz2, const float* z, const void* z_hi, const void* z_lo, float* dy, void* dy_hi,
+                                     void* dy_lo, float* dbias, const float* noise, const float* strength, long noise_bs, float* dstrength,
+                                     float* dnoise, int n, int hw, int c, int lrelu, float alpha, float gain, float clamp, void* stream) {
+    B200_REQUIRE(dz && dz2, "layer_act_bwd_sum2: both gradients are required");
+    return layer_act_bwd_impl(dz, dz2, z, z_hi, z_lo, dy, dy_hi, dy_lo, dbias, noise, strength, noise_bs, dstrength, dnoise, n, hw, c, lrelu,
+                              alpha, gain, clamp, stream);
+}
+
+B200_API int b200_layer_act_bwd_sum2_supported(int n, int hw, int c, int has_noise, long noise_bs) {
+    return act_bwd_fast_shape((long)n * hw, c, has_noise != 0, n, noise_bs) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------

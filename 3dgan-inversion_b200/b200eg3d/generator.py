@@ -132,13 +132,15 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None, bank=None, lidx=-1, want_z=True):
-        """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None.
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, x_split=None, bank=None, lidx=-1, want_z=True, fork=False):
+        """Returns (z, split) where split is the (hi, lo) bf16 pair of z for the next tensor-core conv, or None; with fork=True
+        (z, split, z_second): a second handle of z for its second consumer (ops.modconv_layer).
         bank / lidx: styles and modulated weights come from a pre-computed ops.WeightBank entry (w is then unused).
         want_z=False: the caller's consumers all read the pair (ops.lean_ok): z comes back as a shape-only placeholder."""
         assert noise_mode in ['random', 'const', 'none']
         if not fused_modconv:
-            return self._forward_unfused(x, w, noise_mode, gain), None
+            z = self._forward_unfused(x, w, noise_mode, gain)
+            return (z, None, z) if fork else (z, None)
         styles = self.affine(w) if bank is None else None
         noise = None
         if self.use_noise and noise_mode == 'random':
@@ -147,7 +149,7 @@ class SynthesisLayer(torch.nn.Module):
             noise = self.noise_const
         clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         return ops.modconv_layer(x, self.weight, styles, self.bias, noise, self.noise_strength if noise is not None else None,
-                                 self.up, self.act_gain * gain, clamp, x_split=x_split, bank=bank, lidx=lidx, want_z=want_z)
+                                 self.up, self.act_gain * gain, clamp, x_split=x_split, bank=bank, lidx=lidx, want_z=want_z, fork=fork)
 
 
     def _forward_unfused(self, x, w, noise_mode, gain):
@@ -263,17 +265,22 @@ class SynthesisBlock(torch.nn.Module):
             x, sp = self.conv0(x, next(w_iter), x_split=x_split, bank=bank, lidx=li, want_z=not lean0, **layer_kwargs)
             li += 1
         lean1 = bool(fused_modconv) and lean_out and ops.lean_ok(bank, [li + 1, li + 2])
-        x, sp = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, want_z=not lean1, **layer_kwargs)
+        # conv1's output feeds the next block AND this block's ToRGB: the ToRGB layer gets a handle of its own (x_rgb), so that the two
+        # gradients are summed inside conv1's activation backward rather than by an accumulation pass in between
+        fork1 = lean1 and ops.CONFIG['fork_grads']
+        out = self.conv1(x, next(w_iter), x_split=sp, bank=bank, lidx=li, want_z=not lean1, fork=fork1, **layer_kwargs)
+        x, sp = out[0], out[1]
+        x_rgb = out[2] if fork1 else x
         if side is None:
-            img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1, fused_modconv=bool(fused_modconv))
+            img = self.torgb(x_rgb, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1, fused_modconv=bool(fused_modconv))
         else:
             # ToRGB + skip upsample on the second stream: they depend on this block's x only, the next block's convolutions
             # do not depend on them.  Tensors that cross streams are registered with the allocator (record_stream).
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                img = self.torgb(x, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
-            for t in (x,) + (tuple(sp) if sp is not None else ()):
+                img = self.torgb(x_rgb, next(w_iter), img_prev=img, x_split=sp, bank=bank, lidx=li + 1)
+            for t in (x, x_rgb) + (tuple(sp) if sp is not None else ()):
                 if t is not None:
                     t.record_stream(side)
         if return_split:

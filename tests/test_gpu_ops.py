@@ -647,6 +647,76 @@ def test_lean_activations_match_fp32_copies(b2, monkeypatch, golden_dir):
         assert relerr(a, b) < 1e-2, (n, relerr(a, b))
 
 
+@pytest.mark.parametrize('c,split_out', [(64, True), (128, True), (256, True), (512, True), (128, False)])
+def test_layer_act_bwd_two_addends_equal_presummed_gradient(b2, c, split_out):
+    """b200_layer_act_bwd_sum2(dz, dz2) == b200_layer_act_bwd(dz + dz2), bit for bit in dy (the kernel forms the same fp32 sum autograd's
+    accumulation pass would), for the split and the fp32 form of the saved output; shapes outside the specialised kernel report 0."""
+    from b200eg3d._lib import call, ptr, stream
+    lib = b2._lib.load()
+    g = gen(c + 5)
+    n, hw, clamp, gain = 2, 29 * 31, 2.0, math.sqrt(2)
+    z = (torch.randn(n, hw, c, generator=g) * 1.5).clamp(-clamp, clamp).cuda()
+    dz, dz2 = torch.randn(n, hw, c, generator=g).cuda(), torch.randn(n, hw, c, generator=g).cuda()
+    noise = torch.randn(hw, generator=g).cuda()
+    strength = torch.full([], 0.4).cuda()
+    zh, zl = b2.ops._split(z, True)
+    assert lib.b200_layer_act_bwd_sum2_supported(n, hw, c, 1, 0) == 1
+    assert lib.b200_layer_act_bwd_sum2_supported(n, hw, 20, 1, 0) == 0 and lib.b200_layer_act_bwd_sum2_supported(n, hw, 20, 0, 0) == 1   # 5 lanes: no shuffle sum
+    assert lib.b200_layer_act_bwd_sum2_supported(n, hw, 3, 0, 0) == 0
+    for zr in ((ptr(z), None, None), (None, ptr(zh), ptr(zl))):
+        res = []
+        for two in (True, False):
+            dy = torch.empty_like(dz) if not split_out else None
+            dyh = torch.empty(n, hw, c, device='cuda', dtype=torch.bfloat16) if split_out else None
+            dyl = torch.empty_like(dyh) if split_out else None
+            dbias, dstr, dnoise = torch.zeros(c, device='cuda'), torch.zeros([], device='cuda'), torch.zeros_like(noise)
+            tail = (ptr(dy), ptr(dyh), ptr(dyl), ptr(dbias), ptr(noise), ptr(strength), 0, ptr(dstr), ptr(dnoise), n, hw, c, 1, 0.2, gain, clamp,
+                    stream())
+            if two:
+                call('b200_layer_act_bwd_sum2', ptr(dz), ptr(dz2), *zr, *tail)
+            else:
+                dsum = dz + dz2
+                call('b200_layer_act_bwd', ptr(dsum), *zr, *tail)
+            res.append((dy if not split_out else dyh.float() + dyl.float(), dbias, dstr, dnoise))
+        torch.cuda.synchronize()
+        assert maxdiff(res[0][0], res[1][0]) == 0.0
+        for a, b in zip(res[0][1:], res[1][1:]):
+            assert relerr(a, b) < 1e-5
+        ref = (dz + dz2) * gain * torch.where(z > 0, 1.0, 0.2) * (z.abs() < clamp)
+        assert maxdiff(res[0][0], ref) < (1e-6 if not split_out else 2e-4)
+
+
+def test_forked_gradients_match_autograd_accumulation(b2, monkeypatch, golden_dir):
+    """ops.CONFIG['fork_grads']: conv1's output reaches the next block and the block's ToRGB through two handles, and the two gradients
+    are summed inside the activation backward.  Every gradient must equal the path where autograd adds them in a pass of its own."""
+    import synth_params as sp
+    from golden_util import load_case
+    case = load_case(golden_dir, 'full_r64_s16')
+    G = b2.TriPlaneGenerator(rendering_kwargs=case.rk, **case.gk).eval()
+    sp.fill_params_(dict(list(G.named_parameters()) + list(G.named_buffers())), case.param_seed)
+    G = G.cuda().float()
+    G.neural_rendering_resolution = case.R
+    G.renderer.fixed_noise = (case.u_strat.cuda(), case.u_imp.cuda())
+    c = case.c.cuda()
+    named = [(n, p) for n, p in G.named_parameters() if '.mapping.' not in n]
+    outs = []
+    for fork in (True, False):
+        monkeypatch.setitem(b2.ops.CONFIG, 'fork_grads', fork)
+        for _, p in named:
+            p.grad = None
+        ws = case.ws.cuda().requires_grad_(True)
+        out = G.synthesis(ws, c, noise_mode='const')
+        (out['image'].square().mean() + out['image_raw'].square().mean()).backward()
+        torch.cuda.synchronize()
+        outs.append((out['image'].detach().clone(), ws.grad.clone(), [p.grad.clone() if p.grad is not None else None for _, p in named]))
+    assert maxdiff(outs[0][0], outs[1][0]) < 2e-4
+    assert relerr(outs[0][1], outs[1][1]) < 1e-3, relerr(outs[0][1], outs[1][1])
+    for (n, _), a, b in zip(named, outs[0][2], outs[1][2]):
+        if a is None or a.ndim < 2:
+            continue
+        assert relerr(a, b) < 1e-2, (n, relerr(a, b))
+
+
 @pytest.mark.parametrize('h,w,c,pad,flip,act', [(513, 513, 64, 1, 0, True), (257, 257, 128, 1, 0, True), (256, 256, 128, 2, 1, False),
                                                 (130, 203, 64, 2, 1, False), (131, 201, 128, 1, 0, True)])
 def test_fir_column_window_matches_patch_kernel(b2, h, w, c, pad, flip, act):
