@@ -388,18 +388,44 @@ class SuperresolutionHybrid8X(torch.nn.Module):
         with on_device(ws):
             return self._forward_nhwc(rgb, x, ws, **block_kwargs)
 
-    def _forward_nhwc(self, rgb, x, ws, **block_kwargs):
-        ws = ws[:, -1:, :].repeat(1, 3, 1)
+    def _make_bank(self, ws3):
+        specs = self.block0.bank_specs(0)
+        base1 = len(specs)
+        specs += self.block1.bank_specs(0)
+        return ops.make_bank(ws3.contiguous(), specs), base1
+
+    def prepare_bank(self, ws):
+        """Styles and modulated weights of the module's six layers depend on the latents only: made on the second stream ahead of
+        time (the caller runs the renderer meanwhile), their backward runs there too, beside the renderer's.  Returns an opaque
+        handle for forward_nhwc(..., prepared=handle), or None when there is no second stream to run on."""
+        if not (ops.CONFIG['bank'] and ops.CONFIG['overlap'] and ops.CONFIG['early_sr_bank'] and ws.is_cuda):
+            return None
+        with on_device(ws):
+            side, main = ops.side_stream(ws.device), torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ws3 = ws[:, -1:, :].repeat(1, 3, 1)
+                bank, base1 = self._make_bank(ws3)
+            ws.record_stream(side)
+            return ws3, bank, base1, side
+
+    def _forward_nhwc(self, rgb, x, ws, prepared=None, **block_kwargs):
         if x.shape[1] != self.input_resolution:
             size = (self.input_resolution, self.input_resolution)
             x = _to_nhwc(F.interpolate(_to_nchw_view(x), size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias))
             rgb = _to_nhwc(F.interpolate(_to_nchw_view(rgb), size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias))
         bank, base1 = None, 0
-        if ops.CONFIG['bank']:
-            specs = self.block0.bank_specs(0)
-            base1 = len(specs)
-            specs += self.block1.bank_specs(0)
-            bank = ops.make_bank(ws.contiguous(), specs)
+        if prepared is not None:
+            ws, bank, base1, pside = prepared
+            main = torch.cuda.current_stream()
+            main.wait_stream(pside)                                 # the bank's kernels ran on the second stream
+            for t in bank.w_hi + bank.w_lo + bank.wmod + bank.styles + bank.dcoef + [bank.zpool, bank.zf, bank.zb, ws]:
+                if t is not None:
+                    t.record_stream(main)                           # allocated on the second stream, read by the layers on this one
+        else:
+            ws = ws[:, -1:, :].repeat(1, 3, 1)
+            if ops.CONFIG['bank']:
+                bank, base1 = self._make_bank(ws)
         side = ops.side_stream(ws.device) if (ops.CONFIG['overlap'] and bank is not None and ws.is_cuda) else None
         if side is not None:
             bank.side = side
@@ -623,6 +649,11 @@ class TriPlaneGenerator(torch.nn.Module):
         if cache_backbone:
             self._last_planes = planes
         planes = planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1])
+        # the super-resolution module's styles and modulated weights need the latents only: started on the second stream here, so that
+        # they (and, in the backward pass, their gradients) run beside the renderer instead of in front of the first SR convolution
+        prepared = None
+        if synthesis_kwargs.get('fused_modconv', True) is not False and hasattr(self.superresolution, 'prepare_bank'):
+            prepared = self.superresolution.prepare_bank(ws)
         feature_samples, depth_samples, _ = self.renderer(planes, self.decoder, ray_origins, ray_directions, self.rendering_kwargs)
         H = W = self.neural_rendering_resolution
         feature_nhwc = feature_samples.reshape(N, H, W, feature_samples.shape[-1])                 # [N,M,32] is already NHWC
@@ -630,6 +661,8 @@ class TriPlaneGenerator(torch.nn.Module):
         feature_image = _to_nchw_view(feature_nhwc)
         rgb_image = feature_image[:, :3]
         sr_kwargs = {k: v for k, v in synthesis_kwargs.items() if k != 'noise_mode'}
+        if prepared is not None:
+            sr_kwargs['prepared'] = prepared
         sr_image = self.superresolution(rgb_image, feature_image, ws, noise_mode=self.rendering_kwargs['superresolution_noise_mode'],
                                         **sr_kwargs)
         return {'image': sr_image, 'image_raw': rgb_image, 'image_depth': depth_image}

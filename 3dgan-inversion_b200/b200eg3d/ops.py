@@ -45,6 +45,8 @@ CONFIG = {'tc': os.environ.get('B200EG3D_TC', '1') != '0',
           # inside a synthesis network keep activations only as the split-bf16 pair the next tensor-core conv reads: no fp32 copy is
           # written by the layer epilogues or re-read by the activation backward (the returned fp32 tensor is then a placeholder)
           'lean_acts': os.environ.get('B200EG3D_LEAN_ACTS', '1') != '0',
+          # styles + modulated weights of the super-resolution module on the second stream, beside the renderer (forward and backward)
+          'early_sr_bank': os.environ.get('B200EG3D_EARLY_SR_BANK', '1') != '0',
           # an activation with two consumers hands each its own handle: the two gradients are summed in the activation backward
           'fork_grads': os.environ.get('B200EG3D_FORK_GRADS', '1') != '0',
           # one zero fill per network pass for the outputs of all split-K convolutions instead of a memset before each launch

@@ -686,9 +686,12 @@ def test_layer_act_bwd_two_addends_equal_presummed_gradient(b2, c, split_out):
         assert maxdiff(res[0][0], ref) < (1e-6 if not split_out else 2e-4)
 
 
-def test_forked_gradients_match_autograd_accumulation(b2, monkeypatch, golden_dir):
+@pytest.mark.parametrize('key', ['fork_grads', 'early_sr_bank'])
+def test_forked_gradients_match_autograd_accumulation(b2, monkeypatch, golden_dir, key):
     """ops.CONFIG['fork_grads']: conv1's output reaches the next block and the block's ToRGB through two handles, and the two gradients
-    are summed inside the activation backward.  Every gradient must equal the path where autograd adds them in a pass of its own."""
+    are summed inside the activation backward.  Every gradient must equal the path where autograd adds them in a pass of its own.
+    ops.CONFIG['early_sr_bank']: the super-resolution module's styles / modulated weights (and their backward) on the second stream
+    beside the renderer must equal the stream-ordered placement in front of the first SR convolution."""
     import synth_params as sp
     from golden_util import load_case
     case = load_case(golden_dir, 'full_r64_s16')
@@ -701,7 +704,7 @@ def test_forked_gradients_match_autograd_accumulation(b2, monkeypatch, golden_di
     named = [(n, p) for n, p in G.named_parameters() if '.mapping.' not in n]
     outs = []
     for fork in (True, False):
-        monkeypatch.setitem(b2.ops.CONFIG, 'fork_grads', fork)
+        monkeypatch.setitem(b2.ops.CONFIG, key, fork)
         for _, p in named:
             p.grad = None
         ws = case.ws.cuda().requires_grad_(True)
