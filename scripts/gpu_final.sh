@@ -1,7 +1,7 @@
-# usage: bash scripts/gpu_final_r2z4.sh <tag>    the round's closing evidence (one GPU, ~5 min): full GPU suite twice (the second pass looks for
+# usage: bash scripts/gpu_final.sh <tag>    the round's closing evidence (one GPU, ~5 min): full GPU suite twice (the second pass looks for
 #   order-of-atomics flakiness), smoke(), the default bench line (all legs), ncu launch list of ONE eager step, CUPTI timeline of one graph replay
 mkdir -p gpurun_out
-T=${1:-r2z4}
+T=${1:-r2z5}
 timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_${T}.log 2>&1
 echo "pytest rc=$?"; grep -E "passed|failed|^FAILED|^E  " gpurun_out/pytest_${T}.log | cut -c1-220 | head -20
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_${T}.log 2>&1; tail -2 gpurun_out/smoke_${T}.log
