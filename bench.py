@@ -569,11 +569,10 @@ def run_b200(args):
             'metric': METRIC, 'value': round(world * args.steps / (ms * 1e-3), 3), 'unit': 'steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': round(ms / args.steps, 3), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
-            'config': {'workload': WORKLOAD, 'parallelism': f'independent images x{world}',
-                       'l2': 'per-step working set (>1 GB of activations and gradients) exceeds the 126 MB L2; no explicit flush',
-                       'loss': 'mse512 + mse128 + depth TV, fused kernel b200eg3d.losses.pti_loss (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4 (b200eg3d.optim.Adam: one b200_adam_step launch per step)',
-                       'launch': 'eager (one Python-driven launch per kernel)' if args.eager else
-                                 'whole step captured once in a CUDA graph (b200eg3d.graphs.GraphedStep) and replayed'},
+            'config': workload_config(world),
+            'impl_notes': {'loss': 'fused kernel b200eg3d.losses.pti_loss', 'optimizer': 'b200eg3d.optim.Adam: one b200_adam_step launch per step',
+                           'launch': 'eager (one Python-driven launch per kernel)' if args.eager else
+                                     'whole step captured once in a CUDA graph (b200eg3d.graphs.GraphedStep) and replayed'},
             'e2e': {'value': round(world * args.steps / (ms_e2e * 1e-3), 3), 'unit': 'steps/s', 'h2d_bytes_per_step': n_in,
                     'd2h_bytes_per_step': 4, 'host_reads': len(e2e_losses),
                     'pipelining': 'double-buffered: H2D of step i+1 on a copy stream under step i, loss of step i read on the host one step later'},
@@ -718,6 +717,13 @@ def cpu_baseline(warm, steps):
             'seconds_per_step': round(t, 2)}
 
 
+def workload_config(world):
+    """The workload both arms (--impl b200 / reference) run: the same dict in both lines; what an arm does to run it goes to `impl_notes`."""
+    return {'workload': WORKLOAD, 'parallelism': f'independent images x{world}',
+            'l2': 'per-step working set (>1 GB of activations and gradients) exceeds the 126 MB L2; no explicit flush',
+            'loss': 'mse512 + mse128 + depth TV (LPIPS weights unavailable offline)', 'optimizer': 'Adam lr 3e-4'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -731,7 +737,8 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': res['value'], 'unit': 'steps/s', 'n_gpus': int(os.environ.get('WORLD_SIZE', 1)),
             'steps': k, 'warmup': w, 'ms_per_step': round(1e3 / res['value'], 1), 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic (random-init generator, random targets)',
-            'config': {'workload': WORKLOAD, 'note': 'reference CPU path restated by the oracle port, all host threads; steps bounded to ~90 s'},
+            'config': workload_config(int(os.environ.get('WORLD_SIZE', 1))),
+            'impl_notes': {'what': 'reference CPU path restated by the oracle port, all host threads, rank 0 only; steps bounded to ~90 s'},
             'cpu_baseline': dict(res, value=res['value']),
             'e2e': {'value': res['value'], 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
