@@ -62,6 +62,12 @@ def test_shape_support_query_needs_no_gpu():
     assert lib.b200_conv_tc_ksplit(0, 1, 8, 8, 512, 512, 3, 2) > 1
     assert lib.b200_conv_tc_ksplit(0, 1, 256, 256, 128, 128, 3, 1) == 1 and lib.b200_conv_tc_ksplit(1, 1, 256, 256, 128, 128, 3, 1) == 1
     assert lib.b200_conv_tc_ksplit(0, 1, 16, 16, 12, 20, 3, 1) == 1
+    # two-addend activation backward: channel vectors of a pixel inside one warp, a power-of-two count when the noise gradient needs
+    # the shuffle sum, 32-bit element indices
+    q = lib.b200_layer_act_bwd_sum2_supported
+    assert q(1, 256 * 256, 128, 1, 0) == 1 and q(1, 64 * 64, 512, 1, 0) == 1 and q(4, 16, 64, 0, 16) == 1
+    assert q(1, 64, 20, 1, 0) == 0 and q(1, 64, 20, 0, 0) == 1 and q(1, 64, 3, 0, 0) == 0 and q(1, 64, 1024, 0, 0) == 0
+    assert q(64, 512 * 512, 512, 0, 0) == 0                                   # 2^33 elements: the generic kernels' 64-bit indices
 
 
 @pytest.mark.parametrize('arch', ['tiny', 'full'])
