@@ -799,7 +799,7 @@ def modconv_layer(x, weight, styles, bias, noise, strength, up, act_gain, clamp,
     xh, xl = x_split if x_split is not None else (None, None)
     with prof_range('modulated_conv2d'):
         if bank is not None:
-            if fork and not want_z:
+            if fork and not want_z and bank.specs[lidx].tc_f:      # (a layer off the tensor cores writes its fp32 output: one handle, autograd adds)
                 z, zh, zl, z2 = _ModConvLayer.apply(x, xh, xl, None, None, bias, noise, strength, up, act_gain, clamp, bank.token, bank,
                                                     lidx, False, True)
                 return z, (zh, zl), z2
